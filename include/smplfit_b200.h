@@ -1,0 +1,171 @@
+/*
+ * smplfit_b200 -- C ABI of the Blackwell-native SMPL fitter hot path (libsmplfit_b200.so).
+ *
+ * The reference (isarandi/smplfitter) is pure Python: it has no FFI seam, so the drop-in
+ * boundary is its `smplfitter.pt` Python API and this library is what a maintainer would bind
+ * *behind* those methods.  Every entry point below names the reference
+ * method it replaces (paths relative to /root/reference/src/smplfitter/):
+ *
+ *   smplfit_forward            <- pt/bodymodel.py:121-307     BodyModel.forward
+ *   smplfit_fit                <- pt/bodyfitter.py:283-549    BodyFitter.fit (+ the stages it calls:
+ *                                   _part_sums :235, _fit_shape :840, _fit_shape_gram :960,
+ *                                   _fit_shape_general :1104, _fit_global_rotations :1321,
+ *                                   _fit_global_rotations_dependent :1418) and pt/rotation.py
+ *   smplfit_fit_known_pose     <- pt/bodyfitter.py:552-653    BodyFitter.fit_with_known_pose
+ *   smplfit_convert_vertices   <- pt/bodyconverter.py:129-149 BodyConverter.convert_vertices
+ *
+ * Conventions: plain pointers and sizes only (no torch types).  All pointers are DEVICE
+ * pointers unless the name says host; float arrays are contiguous float32 in the layouts of
+ * the reference tensors; work is enqueued on `stream` (a cudaStream_t passed as void*) and the
+ * calls never synchronise.  Outputs and the workspace are allocated by the caller (sizes from
+ * the *_workspace_bytes functions).  Return value: 0 = OK, negative = error (message via
+ * smplfit_last_error()).  Numerical failure never raises: NaNs propagate, as in the reference
+ * (pt/bodyfitter.py:1083 ignores cholesky_ex info; pt/rotation.py:8-11 divide_no_nan).
+ */
+#ifndef SMPLFIT_B200_H_
+#define SMPLFIT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMPLFIT_OK 0
+#define SMPLFIT_ERR_ARG (-1)
+#define SMPLFIT_ERR_UNSUPPORTED (-2)
+#define SMPLFIT_ERR_WORKSPACE (-3)
+#define SMPLFIT_ERR_CUDA (-4)
+
+#define SMPLFIT_MAX_JOINTS 64
+#define SMPLFIT_MAX_UNKNOWNS 17 /* betas (+ kid) solved by the register-resident Gram kernels */
+
+/* Model constants: reference layouts (pt/bodymodel.py:80-93) plus the derived device tables
+ * built once on the host by smplfitter_b200/masks.py (pt/bodyfitter.py:36-233 semantics). */
+typedef struct smplfit_model {
+  int32_t num_vertices; /* V */
+  int32_t num_joints;   /* J */
+  int32_t num_betas;    /* S */
+  int32_t num_pose_feats; /* P = 9 (J-1) */
+  int32_t skin_k;       /* influences per vertex in the sparse skin table */
+  int32_t is_smpl_family;
+  int32_t n_used;       /* vertices taking part in part statistics (first n_used of `order`) */
+  int32_t n_segments;   /* statistics segments (<= seg_len vertices of one part each) */
+  int32_t chunk_len;    /* vertices per shape-pass chunk */
+  int32_t max_cas;      /* row length of cas_table */
+  int32_t reserved0, reserved1;
+  const float* v_template;     /* (V,3) pose-corrected template */
+  const float* shapedirs;      /* (V,3,S) */
+  const float* posedirs;       /* (V,3,P) */
+  const float* kid_shapedir;   /* (V,3) */
+  const float* J_template;     /* (J,3) */
+  const float* J_shapedirs;    /* (J,3,S) */
+  const float* kid_J_shapedir; /* (J,3) */
+  const float* J_regressor;    /* (J,V) post-LBS joint regressor */
+  const float* template_mesh;  /* (V,3) zero-pose zero-shape mesh (pt/bodyfitter.py:49) */
+  const int32_t* parents;      /* (J) parents[0] = -1 */
+  const int32_t* skin_idx;     /* (V,K) */
+  const float* skin_w;         /* (V,K) */
+  const int32_t* order;        /* (V) internal vertex order -> model vertex (used vertices, grouped by part, first) */
+  const int32_t* seg_start;    /* (n_segments+1) offsets into `order` */
+  const int32_t* seg_part;     /* (n_segments) */
+  const int32_t* part_seg_begin; /* (J+1) segment range per part */
+  const int32_t* part_kind;    /* (J) 0 none, 1 multi-joint, 2 bone, 3 leaf, 4 copy */
+  const int32_t* part_copy_src;/* (J) */
+  const int32_t* part_flags;   /* (J) bit0 = has statistics, bit1 = adjustable in the final pass */
+  const int32_t* cas_table;    /* (J,max_cas) children-and-self joint lists, -1 padded */
+  const int32_t* cas_count;    /* (J) */
+  const int32_t* inv_order;    /* (V) model vertex -> internal position */
+  const float* posedirs_fit;   /* (3V, Ppad) posedirs rows in internal order, K zero-padded to Ppad = roundup(P,16) */
+  const float* v_template_fit; /* (3V) v_template in internal order */
+  /* fitter-level tables (depend on enable_kid): NS = S (+1 with the kid blend shape) unknowns */
+  int32_t fit_ns;
+  int32_t fit_reserved;
+  const float* fit_shapedirs;  /* (V,3,NS): shapedirs with the kid column appended (pt/bodyfitter.py:1139-1149) */
+  const float* fit_Jt_ext;     /* (J,3,1+NS): [J_template | J_shapedirs | kid_J_shapedir] (pt/bodyfitter.py:52-58) */
+  const float* template_joints_regressed; /* (J,3) J_regressor @ template_mesh (no-joints first fit) */
+  const float* J_regressor_fit; /* (J,V) J_regressor with columns in internal order */
+  const void* reserved_ptr[4];
+} smplfit_model_t;
+
+/* Options of BodyFitter.fit (pt/bodyfitter.py:283-302). */
+typedef struct smplfit_fit_opts {
+  int32_t num_iter;
+  int32_t final_adjust_rots;
+  int32_t enable_kid;          /* fitter built with enable_kid (extra unknown, general solve) */
+  int32_t want_pose_rotvecs;   /* requested_keys contains 'pose_rotvecs' */
+  int32_t want_rel_orient;     /* ... or 'relative_orientations' */
+  int32_t shape_weights;       /* 1: the shape stage honours vertex/joint weights (pt/bodyfitter.py:1018-1028) */
+  int32_t scale_mode;          /* 0 none, 1 scale_target, 2 scale_fit (last solve only) */
+  int32_t reserved;
+  float beta_regularizer;
+  float beta_regularizer2;
+  float kid_regularizer;       /* resolved on the host (None -> beta_regularizer) */
+  float scale_regularizer;
+} smplfit_fit_opts_t;
+
+const char* smplfit_version(void);
+/* sizeof(smplfit_model_t) (which = 0) / sizeof(smplfit_fit_opts_t) (which = 1): lets a binding verify its struct mirror. */
+size_t smplfit_struct_size(int which);
+const char* smplfit_last_error(void);
+
+/* -- BodyModel.forward (pt/bodymodel.py:121-307) --------------------------------------
+ * rot_mode: 0 = pose_rotvecs (B,3J); 1 = rel_rotmats (B,J,3,3); 2 = glob_rotmats (B,J,3,3);
+ *           3 = identity (no rotation input).  betas (B,n_betas) may be NULL/0; trans (B,3)
+ * and kid (B) may be NULL.  out_vertices may be NULL (return_vertices=False). */
+size_t smplfit_forward_workspace_bytes(const smplfit_model_t* m, int64_t batch);
+int smplfit_forward(const smplfit_model_t* m, int64_t batch, int rot_mode, const float* rot,
+                    const float* betas, int n_betas, const float* trans, const float* kid,
+                    float* out_vertices, float* out_joints, float* out_orientations,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* -- BodyFitter.fit (pt/bodyfitter.py:283-549) ----------------------------------------
+ * target_vertices (B,V,3); target_joints (B,J,3) or NULL; vertex_weights (B,V) / joint_weights
+ * (B,J) or NULL; beta_reg_reference (B,S) or NULL (initial_shape_betas); kid_reg_reference (B)
+ * or NULL.  init_* are the forward of the initial guess (reference vertices (B,V,3), joints
+ * (B,J,3), orientations (B,J,3,3)) or all NULL for the template start (pt/bodyfitter.py:363-394).
+ * Outputs (any may be NULL except betas/trans/orientations): pose_rotvecs (B,3J),
+ * shape_betas (B,S), trans (B,3), orientations (B,J,3,3), relative_orientations (B,J,3,3),
+ * kid_factor (B), scale_corr (B). */
+size_t smplfit_fit_workspace_bytes(const smplfit_model_t* m, int64_t batch, const smplfit_fit_opts_t* o,
+                                   int has_joints, int has_vw, int has_jw);
+int smplfit_fit(const smplfit_model_t* m, int64_t batch, const float* target_vertices,
+                const float* target_joints, const float* vertex_weights, const float* joint_weights,
+                const float* beta_reg_reference, const float* kid_reg_reference,
+                const float* init_vertices, const float* init_joints, const float* init_orientations,
+                const smplfit_fit_opts_t* opts, float* out_pose_rotvecs, float* out_shape_betas,
+                float* out_trans, float* out_orientations, float* out_rel_orientations,
+                float* out_kid_factor, float* out_scale_corr, void* workspace,
+                size_t workspace_bytes, void* stream);
+
+/* -- BodyFitter.fit_with_known_pose (pt/bodyfitter.py:552-653): shape/translation only.
+ * glob_rotmats (B,J,3,3) are the global orientations of the known pose. */
+int smplfit_fit_known_pose(const smplfit_model_t* m, int64_t batch, const float* glob_rotmats,
+                           const float* target_vertices, const float* target_joints,
+                           const float* vertex_weights, const float* joint_weights,
+                           const float* beta_reg_reference, const float* kid_reg_reference,
+                           const smplfit_fit_opts_t* opts, float* out_shape_betas, float* out_trans,
+                           float* out_rel_orientations, float* out_kid_factor, float* out_scale_corr,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* -- BodyConverter.convert_vertices (pt/bodyconverter.py:129-149): CSR (V_out x V_in) applied to
+ * every instance: out (B,V_out,3) = M @ in (B,V_in,3). */
+int smplfit_convert_vertices(const int32_t* indptr, const int32_t* indices, const float* data,
+                             int32_t v_out, int32_t v_in, int64_t batch, const float* in_vertices,
+                             float* out_vertices, void* stream);
+
+/* Number of kernels launched by this library on the calling thread since the last reset
+ * (bench.py reports it as gpu_launches). */
+int64_t smplfit_launch_count(int reset);
+
+/* Per-kernel device timing for benchmarking: while enabled every launch is bracketed by CUDA
+ * events on its stream; smplfit_profile_report synchronises on them and writes one
+ * "kernel\tlaunches\ttotal_ms\n" line per kernel into `out` (host buffer). */
+int smplfit_profile(int enable);
+int smplfit_profile_report(char* out, size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMPLFIT_B200_H_ */

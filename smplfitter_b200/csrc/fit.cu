@@ -1,0 +1,419 @@
+// C-ABI entry points of BodyFitter.fit / fit_with_known_pose: workspace carving and the
+// launch sequence.  Kernels live in fit_kernels.cuh (vertex passes) and solve_kernels.cuh
+// (per-instance solves).  Reference: /root/reference/src/smplfitter/pt/bodyfitter.py:283-549.
+#include <string.h>
+
+#include "common.cuh"
+#include "fit_kernels.cuh"
+#include "solve_kernels.cuh"
+#include "vposed_tc.cuh"
+
+namespace sf {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+
+struct FitWs {
+  float *mean, *tT, *tjT, *vwT, *jwT, *vposedT, *R, *R2, *RT, *Pext, *feat, *gpart, *beta, *trans, *refj,
+      *skin, *spart, *aT, *ajT, *initjT;
+  void* tc_scratch;
+  size_t bytes;
+};
+
+static int shape_nacc(int ns) { return ns * (ns + 1) / 2 + ns + 3 * ns + 3 + 1; }
+
+static FitWs carve(void* base, const smplfit_model_t* m, int64_t B, int has_joints, int has_vw, int has_jw,
+                   int has_init) {
+  FitWs w{};
+  Carver c(base);
+  const size_t Bp = roundup((int)B, 32);
+  const int V = m->num_vertices, J = m->num_joints, NS = m->fit_ns;
+  const int Kp = roundup(m->num_pose_feats, 16);
+  const int n_chunks = (V + m->chunk_len - 1) / m->chunk_len;
+  w.mean = c.take<float>(3 * Bp);
+  w.tT = c.take<float>((size_t)3 * V * Bp);
+  w.tjT = c.take<float>((size_t)3 * J * Bp);
+  w.vwT = has_vw ? c.take<float>((size_t)V * Bp) : nullptr;
+  w.jwT = has_jw ? c.take<float>((size_t)J * Bp) : nullptr;
+  w.vposedT = c.take<float>((size_t)3 * V * Bp);
+  w.R = c.take<float>((size_t)9 * J * Bp);
+  w.R2 = c.take<float>((size_t)9 * J * Bp);
+  w.RT = c.take<float>((size_t)J * (12 + 3 * NS) * Bp);
+  w.Pext = c.take<float>((size_t)J * 3 * (1 + NS) * Bp);
+  w.feat = c.take<float>((size_t)Bp * Kp);
+  w.gpart = c.take<float>((size_t)n_chunks * shape_nacc(NS) * Bp);
+  w.beta = c.take<float>((size_t)NS * Bp);
+  w.trans = c.take<float>(3 * Bp);
+  w.refj = c.take<float>((size_t)3 * J * Bp);
+  w.skin = c.take<float>((size_t)12 * J * Bp);
+  w.spart = c.take<float>((size_t)m->n_segments * 16 * Bp);
+  const bool need_aT = !has_joints || has_init;
+  w.aT = need_aT ? c.take<float>((size_t)3 * V * Bp) : nullptr;
+  w.ajT = need_aT ? c.take<float>((size_t)3 * J * Bp) : nullptr;
+  w.initjT = has_init ? c.take<float>((size_t)3 * J * Bp) : nullptr;
+  w.tc_scratch = c.take<char>(vposed_tc_scratch_bytes(m, (int)Bp));
+  w.bytes = c.off + 256;
+  return w;
+}
+
+static TreeTables tables(const smplfit_model_t* m) {
+  TreeTables t;
+  t.parents = m->parents;
+  t.part_kind = m->part_kind;
+  t.part_copy_src = m->part_copy_src;
+  t.part_flags = m->part_flags;
+  t.cas_table = m->cas_table;
+  t.cas_count = m->cas_count;
+  t.part_seg_begin = m->part_seg_begin;
+  t.Jt_ext = m->fit_Jt_ext;
+  t.J = m->num_joints;
+  t.NS = m->fit_ns;
+  t.max_cas = m->max_cas;
+  return t;
+}
+
+static int check_model(const smplfit_model_t* m) {
+  if (!m) return fail(SMPLFIT_ERR_ARG, "model is NULL");
+  if (m->num_joints > SMPLFIT_MAX_JOINTS) return fail(SMPLFIT_ERR_UNSUPPORTED, "num_joints > 64");
+  if (m->fit_ns < 2 || m->fit_ns > SMPLFIT_MAX_UNKNOWNS)
+    return fail(SMPLFIT_ERR_UNSUPPORTED, "number of shape unknowns must be in [2, 17]");
+  return SMPLFIT_OK;
+}
+
+template <int NS, bool WEIGHTED>
+static void launch_shape_pass_w(const ShapeArgs& sa, int groups, cudaStream_t st) {
+  constexpr int RW = 12 + 3 * NS;
+  const size_t smem = (size_t)sa.J * RW * 32 * sizeof(float);
+  const int cta_chunks = 8;
+  ShapeArgs a = sa;
+  a.chunks_per_cta = cta_chunks;
+  dim3 grid((sa.n_chunks + cta_chunks - 1) / cta_chunks, groups);
+  if (smem <= 200 * 1024) {
+    auto k = k_shape_pass<NS, WEIGHTED, true>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    SF_LAUNCH(k, grid, 256, smem, st, a);
+  } else {
+    auto k = k_shape_pass<NS, WEIGHTED, false>;
+    SF_LAUNCH(k, grid, 256, 0, st, a);
+  }
+}
+
+template <int NS>
+static void launch_shape_pass(const ShapeArgs& sa, int groups, cudaStream_t st) {
+  if (sa.vwT) launch_shape_pass_w<NS, true>(sa, groups, st);
+  else launch_shape_pass_w<NS, false>(sa, groups, st);
+}
+
+template <int NS>
+static void launch_shape_solve(const SolveArgs& so, int Bp, cudaStream_t st) {
+  SF_LAUNCH(k_shape_solve<NS>, Bp / 32, 32, 0, st, so);
+}
+
+#define SF_NS_DISPATCH(NSV, CALL)                 \
+  switch (NSV) {                                  \
+    case 2: { constexpr int NS = 2; CALL; } break;   \
+    case 3: { constexpr int NS = 3; CALL; } break;   \
+    case 4: { constexpr int NS = 4; CALL; } break;   \
+    case 5: { constexpr int NS = 5; CALL; } break;   \
+    case 6: { constexpr int NS = 6; CALL; } break;   \
+    case 7: { constexpr int NS = 7; CALL; } break;   \
+    case 8: { constexpr int NS = 8; CALL; } break;   \
+    case 9: { constexpr int NS = 9; CALL; } break;   \
+    case 10: { constexpr int NS = 10; CALL; } break; \
+    case 11: { constexpr int NS = 11; CALL; } break; \
+    case 12: { constexpr int NS = 12; CALL; } break; \
+    case 13: { constexpr int NS = 13; CALL; } break; \
+    case 14: { constexpr int NS = 14; CALL; } break; \
+    case 15: { constexpr int NS = 15; CALL; } break; \
+    case 16: { constexpr int NS = 16; CALL; } break; \
+    case 17: { constexpr int NS = 17; CALL; } break; \
+    default: break;                               \
+  }
+
+struct FitCtx {
+  const smplfit_model_t* m;
+  FitWs w;
+  int B, Bp, groups, Kp, n_chunks;
+  cudaStream_t st;
+  const float *vwT_shape, *jwT_shape;  // shape-stage weights (pt/bodyfitter.py:1018-1028)
+  bool has_joints;
+};
+
+static void run_gemm(FitCtx& c) {
+  const smplfit_model_t* m = c.m;
+  if (vposed_tc_run(m, c.w.feat, c.w.vposedT, c.Bp, c.Kp, c.w.tc_scratch, c.st)) return;
+  dim3 grid((3 * m->num_vertices + 127) / 128, (c.Bp + 63) / 64);
+  SF_LAUNCH(k_vposed_gemm_simt, grid, 256, 0, c.st, m->posedirs_fit, m->v_template_fit, c.w.feat,
+            3 * m->num_vertices, c.Kp, c.Bp, c.w.vposedT);
+}
+
+static void run_shape(FitCtx& c, const float* R_unused, const float* beta_ref, const float* kid_ref,
+                      const smplfit_fit_opts_t* o) {
+  (void)R_unused;
+  const smplfit_model_t* m = c.m;
+  run_gemm(c);
+  ShapeArgs sa;
+  sa.tT = c.w.tT; sa.vwT = c.vwT_shape; sa.vposedT = c.w.vposedT; sa.RT = c.w.RT;
+  sa.shapedirs = m->fit_shapedirs; sa.skin_idx = m->skin_idx; sa.skin_w = m->skin_w; sa.order = m->order;
+  sa.partials = c.w.gpart; sa.V = m->num_vertices; sa.J = m->num_joints; sa.Bp = c.Bp; sa.skin_k = m->skin_k;
+  sa.chunk_len = m->chunk_len; sa.n_chunks = c.n_chunks; sa.chunks_per_cta = 8;
+  SF_NS_DISPATCH(m->fit_ns, (launch_shape_pass<NS>(sa, c.groups, c.st)));
+  SolveArgs so;
+  so.partials = c.w.gpart; so.Pext = c.w.Pext; so.RT = c.w.RT;
+  so.tjT = c.has_joints ? c.w.tjT : nullptr; so.jwT = c.jwT_shape;
+  so.beta_ref = beta_ref; so.kid_ref = kid_ref;
+  so.beta = c.w.beta; so.trans = c.w.trans; so.refj = c.w.refj; so.skin = c.w.skin;
+  so.n_chunks = c.n_chunks; so.J = m->num_joints; so.S = m->num_betas; so.Bp = c.Bp; so.B = c.B;
+  so.V = m->num_vertices; so.weighted = c.vwT_shape != nullptr;
+  so.reg = o->beta_regularizer; so.reg2 = o->beta_regularizer2; so.kid_reg = o->kid_regularizer;
+  SF_NS_DISPATCH(m->fit_ns, (launch_shape_solve<NS>(so, c.Bp, c.st)));
+}
+
+// statistics of (targets, reference) for the rotation stage; ref_mode as in k_stats
+static void run_stats(FitCtx& c, int ref_mode, const float* ca0T, const float* aT_in, float* aT_out) {
+  const smplfit_model_t* m = c.m;
+  StatsArgs s;
+  s.tT = c.w.tT; s.vwT = c.w.vwT; s.ct0 = c.w.tjT; s.ca0 = ca0T; s.ca0_const = m->J_template;
+  s.vposedT = c.w.vposedT; s.beta = c.w.beta; s.skin = c.w.skin; s.aT_in = aT_in; s.aT_out = aT_out;
+  s.partials = c.w.spart; s.template_mesh = m->template_mesh; s.shapedirs = m->fit_shapedirs;
+  s.skin_idx = m->skin_idx; s.skin_w = m->skin_w; s.order = m->order; s.seg_start = m->seg_start;
+  s.seg_part = m->seg_part; s.part_flags = m->part_flags; s.n_segments = m->n_segments; s.Bp = c.Bp;
+  s.ns = m->fit_ns; s.skin_k = m->skin_k; s.all_segments = (aT_out != nullptr);
+  const long long warps = (long long)m->n_segments * c.groups;
+  const int blocks = (int)((warps + 3) / 4);
+  const bool wt = c.w.vwT != nullptr;
+  if (ref_mode == 0) {
+    if (wt) SF_LAUNCH((k_stats<0, true>), blocks, 128, 0, c.st, s); else SF_LAUNCH((k_stats<0, false>), blocks, 128, 0, c.st, s);
+  } else if (ref_mode == 1) {
+    if (wt) SF_LAUNCH((k_stats<1, true>), blocks, 128, 0, c.st, s); else SF_LAUNCH((k_stats<1, false>), blocks, 128, 0, c.st, s);
+  } else {
+    if (wt) SF_LAUNCH((k_stats<2, true>), blocks, 128, 0, c.st, s); else SF_LAUNCH((k_stats<2, false>), blocks, 128, 0, c.st, s);
+  }
+}
+
+static void run_regress(FitCtx& c, const float* X, float* out) {
+  const smplfit_model_t* m = c.m;
+  const int jblocks = (m->num_joints + 7) / 8;
+  const long long warps = (long long)c.groups * jblocks;
+  SF_LAUNCH(k_regress, (int)((warps + 3) / 4), 128, 0, c.st, m->J_regressor_fit, X, m->num_vertices,
+            m->num_joints, c.Bp, out);
+}
+
+template <int C>
+static void run_transpose(FitCtx& c, const float* src, int N, const int32_t* inv, const float* mean, float* dst) {
+  dim3 grid((N + 31) / 32, c.groups), block(32, 8);
+  SF_LAUNCH(k_transpose<C>, grid, block, 0, c.st, src, N, c.B, c.Bp, inv, mean, dst);
+}
+
+}  // namespace sf
+
+using namespace sf;
+
+extern "C" const char* smplfit_version(void) { return "smplfit_b200 0.1.0 (sm_100a)"; }
+extern "C" const char* smplfit_last_error(void) { return g_err; }
+extern "C" int smplfit_profile(int enable) {
+  g_prof_on = enable != 0;
+  return SMPLFIT_OK;
+}
+extern "C" int smplfit_profile_report(char* out, size_t cap) {
+  // aggregate by kernel name: "name\tlaunches\ttotal_ms\n"
+  struct Agg { const char* name; int n; double ms; };
+  std::vector<Agg> agg;
+  for (auto& r : g_prof) {
+    cudaEventSynchronize(r.b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+    bool found = false;
+    for (auto& a : agg)
+      if (a.name == r.name || strcmp(a.name, r.name) == 0) { a.n++; a.ms += ms; found = true; break; }
+    if (!found) agg.push_back(Agg{r.name, 1, (double)ms});
+  }
+  g_prof.clear();
+  size_t off = 0;
+  if (out && cap) out[0] = 0;
+  for (auto& a : agg) {
+    char line[256];
+    const int len = snprintf(line, sizeof(line), "%s\t%d\t%.6f\n", a.name, a.n, a.ms);
+    if (out && off + len + 1 < cap) { memcpy(out + off, line, len + 1); off += len; }
+  }
+  return SMPLFIT_OK;
+}
+extern "C" size_t smplfit_struct_size(int which) {
+  return which == 0 ? sizeof(smplfit_model_t) : which == 1 ? sizeof(smplfit_fit_opts_t) : 0;
+}
+extern "C" int64_t smplfit_launch_count(int reset) {
+  const long long v = reset ? g_launches.exchange(0) : g_launches.load();
+  return (int64_t)v;
+}
+
+extern "C" size_t smplfit_fit_workspace_bytes(const smplfit_model_t* m, int64_t batch, const smplfit_fit_opts_t* o,
+                                              int has_joints, int has_vw, int has_jw) {
+  (void)o;
+  if (check_model(m) != SMPLFIT_OK || batch <= 0) return 0;
+  return carve(nullptr, m, batch, has_joints, has_vw, has_jw, /*has_init=*/1).bytes;
+}
+
+extern "C" int smplfit_fit(const smplfit_model_t* m, int64_t batch, const float* target_vertices,
+                           const float* target_joints, const float* vertex_weights, const float* joint_weights,
+                           const float* beta_reg_reference, const float* kid_reg_reference,
+                           const float* init_vertices, const float* init_joints, const float* init_orientations,
+                           const smplfit_fit_opts_t* o, float* out_pose_rotvecs, float* out_shape_betas,
+                           float* out_trans, float* out_orientations, float* out_rel_orientations,
+                           float* out_kid_factor, float* out_scale_corr, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  if (int e = check_model(m)) return e;
+  if (!o || !target_vertices || !out_shape_betas || !out_trans || !out_orientations)
+    return fail(SMPLFIT_ERR_ARG, "missing required pointer");
+  if (batch <= 0 || batch > (1 << 24)) return fail(SMPLFIT_ERR_ARG, "batch out of range");
+  if (o->num_iter < 1) return fail(SMPLFIT_ERR_ARG, "num_iter must be >= 1");
+  if (o->scale_mode != 0 || out_scale_corr != nullptr)
+    return fail(SMPLFIT_ERR_UNSUPPORTED, "scale_target / scale_fit are not implemented on the CUDA path yet");
+  if ((o->enable_kid != 0) != (m->fit_ns == m->num_betas + 1))
+    return fail(SMPLFIT_ERR_ARG, "enable_kid does not match the fitter tables");
+  const bool has_init = init_vertices != nullptr;
+  if (has_init && (!init_joints || !init_orientations)) return fail(SMPLFIT_ERR_ARG, "incomplete initial guess");
+  const bool has_joints = target_joints != nullptr;
+  FitCtx c;
+  c.m = m;
+  c.B = (int)batch;
+  c.Bp = roundup(c.B, 32);
+  c.groups = c.Bp / 32;
+  c.Kp = roundup(m->num_pose_feats, 16);
+  c.n_chunks = (m->num_vertices + m->chunk_len - 1) / m->chunk_len;
+  c.st = reinterpret_cast<cudaStream_t>(stream);
+  c.has_joints = has_joints;
+  c.w = carve(workspace, m, batch, has_joints, vertex_weights != nullptr, joint_weights != nullptr, has_init);
+  if (!workspace || c.w.bytes > workspace_bytes) return fail(SMPLFIT_ERR_WORKSPACE, "workspace too small");
+  FitWs& w = c.w;
+  const int V = m->num_vertices, J = m->num_joints;
+
+  // -- re-layout + centring (pt/bodyfitter.py:355-361) --
+  SF_LAUNCH(k_mean, (c.Bp * 32 + 255) / 256, 256, 0, c.st, target_vertices, target_joints, V, J, c.B, c.Bp, w.mean);
+  run_transpose<3>(c, target_vertices, V, m->inv_order, w.mean, w.tT);
+  if (vertex_weights) run_transpose<1>(c, vertex_weights, V, m->inv_order, nullptr, w.vwT);
+  if (joint_weights) run_transpose<1>(c, joint_weights, J, nullptr, nullptr, w.jwT);
+  if (has_joints) run_transpose<3>(c, target_joints, J, nullptr, w.mean, w.tjT);
+  else run_regress(c, w.tT, w.tjT);
+  // shape-stage weight rule (pt/bodyfitter.py:1018-1028)
+  c.vwT_shape = o->shape_weights ? w.vwT : nullptr;
+  c.jwT_shape = (o->shape_weights && has_joints) ? w.jwT : nullptr;
+
+  RotArgs ra;
+  ra.partials = w.spart; ra.tjT = w.tjT; ra.jwT = w.jwT; ra.R_new = w.R; ra.RT = w.RT; ra.Pext = w.Pext;
+  ra.feat = w.feat; ra.t = tables(m); ra.B = c.B; ra.Bp = c.Bp; ra.Kp = c.Kp; ra.front_only = 0;
+  // -- first rotation fit (pt/bodyfitter.py:363-394) --
+  if (has_init) {
+    run_transpose<3>(c, init_vertices, V, m->inv_order, nullptr, w.aT);
+    run_transpose<3>(c, init_joints, J, nullptr, nullptr, w.initjT);
+    dim3 g9((9 * J + 31) / 32, c.groups), blk(32, 8);
+    SF_LAUNCH(k_transpose<1>, g9, blk, 0, c.st, init_orientations, 9 * J, c.B, c.Bp, (const int32_t*)nullptr,
+              (const float*)nullptr, w.R2);  // [9J][Bp]
+    run_stats(c, 2, w.initjT, w.aT, nullptr);
+    const float* aj = w.initjT;
+    if (!has_joints) {
+      run_regress(c, w.aT, w.ajT);
+      aj = w.ajT;
+    }
+    ra.ajT = aj; ra.aj_const = nullptr; ra.ca0T = w.initjT; ra.ca0_const = nullptr; ra.R_old = w.R2;
+  } else {
+    run_stats(c, 0, nullptr, nullptr, nullptr);
+    ra.ajT = nullptr; ra.aj_const = has_joints ? m->J_template : m->template_joints_regressed;
+    ra.ca0T = nullptr; ra.ca0_const = m->J_template; ra.R_old = nullptr;
+  }
+  SF_LAUNCH(k_rot_solve, c.Bp / 32, 32, 0, c.st, ra);
+
+  // -- alternate shape and rotation fits (pt/bodyfitter.py:399-461) --
+  const float* R_final = w.R;
+  for (int it = 0; it < o->num_iter; ++it) {
+    run_shape(c, w.R, beta_reg_reference, kid_reg_reference, o);
+    const bool last = (it == o->num_iter - 1);
+    if (last && !o->final_adjust_rots) break;
+    float* aT_out = has_joints ? nullptr : w.aT;
+    run_stats(c, 1, w.refj, nullptr, aT_out);
+    const float* aj = w.refj;
+    if (!has_joints) {
+      run_regress(c, w.aT, w.ajT);
+      aj = w.ajT;
+    }
+    if (!last) {
+      ra.ajT = aj; ra.aj_const = nullptr; ra.ca0T = w.refj; ra.ca0_const = nullptr; ra.R_old = w.R; ra.R_new = w.R;
+      SF_LAUNCH(k_rot_solve, c.Bp / 32, 32, 0, c.st, ra);
+    } else {
+      AdjustArgs aa;
+      aa.partials = w.spart; aa.tjT = w.tjT; aa.ajT = aj; aa.refj = w.refj; aa.jwT = w.jwT; aa.R_prev = w.R;
+      aa.beta = w.beta; aa.trans = w.trans; aa.R_out = w.R2; aa.t = tables(m); aa.Bp = c.Bp;
+      SF_LAUNCH(k_adjust_solve, c.Bp / 32, 32, 0, c.st, aa);
+      R_final = w.R2;
+    }
+  }
+  OutputArgs oa;
+  oa.R_final = R_final;
+  oa.R_rel_src = (o->want_pose_rotvecs || o->want_rel_orient) ? R_final : w.R;
+  oa.beta = w.beta; oa.trans = w.trans; oa.mean = w.mean; oa.parents = m->parents;
+  oa.pose_rotvecs = o->want_pose_rotvecs ? out_pose_rotvecs : nullptr;
+  oa.shape_betas = out_shape_betas; oa.out_trans = out_trans; oa.orientations = out_orientations;
+  oa.rel_orient = out_rel_orientations; oa.kid = o->enable_kid ? out_kid_factor : nullptr;
+  oa.J = J; oa.S = m->num_betas; oa.NS = m->fit_ns; oa.B = c.B; oa.Bp = c.Bp;
+  SF_LAUNCH(k_output, c.Bp / 32, 32, 0, c.st, oa);
+  SF_CHECK_LAST();
+  return SMPLFIT_OK;
+}
+
+extern "C" int smplfit_fit_known_pose(const smplfit_model_t* m, int64_t batch, const float* glob_rotmats,
+                                      const float* target_vertices, const float* target_joints,
+                                      const float* vertex_weights, const float* joint_weights,
+                                      const float* beta_reg_reference, const float* kid_reg_reference,
+                                      const smplfit_fit_opts_t* o, float* out_shape_betas, float* out_trans,
+                                      float* out_rel_orientations, float* out_kid_factor, float* out_scale_corr,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+  if (int e = check_model(m)) return e;
+  if (!o || !glob_rotmats || !target_vertices || !out_shape_betas || !out_trans)
+    return fail(SMPLFIT_ERR_ARG, "missing required pointer");
+  if (batch <= 0 || batch > (1 << 24)) return fail(SMPLFIT_ERR_ARG, "batch out of range");
+  if (o->scale_mode != 0 || out_scale_corr != nullptr)
+    return fail(SMPLFIT_ERR_UNSUPPORTED, "scale_target / scale_fit are not implemented on the CUDA path yet");
+  if ((o->enable_kid != 0) != (m->fit_ns == m->num_betas + 1))
+    return fail(SMPLFIT_ERR_ARG, "enable_kid does not match the fitter tables");
+  const bool has_joints = target_joints != nullptr;
+  FitCtx c;
+  c.m = m;
+  c.B = (int)batch;
+  c.Bp = roundup(c.B, 32);
+  c.groups = c.Bp / 32;
+  c.Kp = roundup(m->num_pose_feats, 16);
+  c.n_chunks = (m->num_vertices + m->chunk_len - 1) / m->chunk_len;
+  c.st = reinterpret_cast<cudaStream_t>(stream);
+  c.has_joints = has_joints;
+  c.w = carve(workspace, m, batch, has_joints, vertex_weights != nullptr, joint_weights != nullptr, 1);
+  if (!workspace || c.w.bytes > workspace_bytes) return fail(SMPLFIT_ERR_WORKSPACE, "workspace too small");
+  FitWs& w = c.w;
+  const int V = m->num_vertices, J = m->num_joints;
+  SF_LAUNCH(k_mean, (c.Bp * 32 + 255) / 256, 256, 0, c.st, target_vertices, target_joints, V, J, c.B, c.Bp, w.mean);
+  run_transpose<3>(c, target_vertices, V, m->inv_order, w.mean, w.tT);
+  if (vertex_weights) run_transpose<1>(c, vertex_weights, V, m->inv_order, nullptr, w.vwT);
+  if (joint_weights) run_transpose<1>(c, joint_weights, J, nullptr, nullptr, w.jwT);
+  if (has_joints) run_transpose<3>(c, target_joints, J, nullptr, w.mean, w.tjT);
+  c.vwT_shape = o->shape_weights ? w.vwT : nullptr;
+  c.jwT_shape = (o->shape_weights && has_joints) ? w.jwT : nullptr;
+  run_transpose<1>(c, glob_rotmats, 9 * J, nullptr, nullptr, w.R2);
+  RotArgs ra;
+  ra.partials = nullptr; ra.tjT = nullptr; ra.ajT = nullptr; ra.aj_const = nullptr; ra.ca0T = nullptr;
+  ra.ca0_const = nullptr; ra.jwT = nullptr; ra.R_old = w.R2; ra.R_new = w.R; ra.RT = w.RT; ra.Pext = w.Pext;
+  ra.feat = w.feat; ra.t = tables(m); ra.B = c.B; ra.Bp = c.Bp; ra.Kp = c.Kp; ra.front_only = 1;
+  SF_LAUNCH(k_rot_solve, c.Bp / 32, 32, 0, c.st, ra);
+  run_shape(c, w.R, beta_reg_reference, kid_reg_reference, o);
+  // orientations output is not part of this method's result; reuse the scratch R2 for it
+  OutputArgs oa;
+  oa.R_final = w.R; oa.R_rel_src = w.R; oa.beta = w.beta; oa.trans = w.trans; oa.mean = w.mean;
+  oa.parents = m->parents; oa.pose_rotvecs = nullptr; oa.shape_betas = out_shape_betas; oa.out_trans = out_trans;
+  oa.orientations = nullptr; oa.rel_orient = out_rel_orientations;
+  oa.kid = o->enable_kid ? out_kid_factor : nullptr;
+  oa.J = J; oa.S = m->num_betas; oa.NS = m->fit_ns; oa.B = c.B; oa.Bp = c.Bp;
+  SF_LAUNCH(k_output, c.Bp / 32, 32, 0, c.st, oa);
+  SF_CHECK_LAST();
+  return SMPLFIT_OK;
+}

@@ -1,0 +1,464 @@
+// Kernels of BodyFitter.fit for sm_100a.
+//
+// Data layout ("instance-minor"): every per-instance array lives in HBM as [row][Bp] with the
+// batch index fastest (Bp = batch rounded up to 32).  A warp's 32 lanes are 32 instances, so
+// every global access of the hot passes is one fully coalesced 128-byte line, model constants
+// are warp-uniform broadcasts, and all per-instance accumulators stay in registers with no
+// cross-lane reduction.  The caller's (B,V,3) targets are re-laid out once (k_transpose).
+//
+// Vertices are processed in an internal order (grouped by body part, see masks.py), so a
+// statistics segment belongs to one part and is flushed exactly once.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/smplfit_b200.h"
+#include "linalg.cuh"
+
+namespace sf {
+
+#define SF_IM(ptr, row, Bp, b) (ptr)[(size_t)(row) * (size_t)(Bp) + (size_t)(b)]
+
+// ---------------------------------------------------------------------------------------
+// k_mean: unweighted mean over cat[vertices, joints] (pt/bodyfitter.py:355-361); one warp
+// per instance, coalesced row reads, shuffle reduction.
+// ---------------------------------------------------------------------------------------
+static __global__ void k_mean(const float* __restrict__ tv, const float* __restrict__ tj, int V, int J, int B,
+                       int Bp, float* __restrict__ mean) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= Bp) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;  // phases k%3 = 0,1,2 -> coordinate (lane + 2k) % 3
+  if (warp < B) {
+    const float* row = tv + (size_t)warp * 3 * V;
+    const int n = 3 * V;
+    int i = lane;
+    for (; i + 64 < n; i += 96) {
+      a0 += row[i];
+      a1 += row[i + 32];
+      a2 += row[i + 64];
+    }
+    if (i < n) a0 += row[i];
+    if (i + 32 < n) a1 += row[i + 32];
+    if (tj != nullptr) {
+      const float* jr = tj + (size_t)warp * 3 * J;
+      const int nj = 3 * J;
+      int k = lane;
+      for (; k + 64 < nj; k += 96) {
+        a0 += jr[k];
+        a1 += jr[k + 32];
+        a2 += jr[k + 64];
+      }
+      if (k < nj) a0 += jr[k];
+      if (k + 32 < nj) a1 += jr[k + 32];
+    }
+  }
+  const int c0 = lane % 3;
+  float s[3];
+  s[c0] = a0;
+  s[(c0 + 2) % 3] = a1;
+  s[(c0 + 1) % 3] = a2;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v = s[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    s[c] = v;
+  }
+  if (lane < 3) {
+    const float cnt = (float)(V + (tj != nullptr ? J : 0));
+    SF_IM(mean, lane, Bp, warp) = (warp < B) ? s[lane] / cnt : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// k_transpose: (B,N,C) instance-major -> [pos(n)*C + c][Bp] instance-minor, optionally
+// subtracting the per-instance mean (C == 3) and renumbering rows through `inv_order`.
+// 32 instances x 32 items per CTA through a padded shared tile; both sides coalesced.
+// ---------------------------------------------------------------------------------------
+template <int C>
+__global__ void k_transpose(const float* __restrict__ src, int N, int B, int Bp,
+                            const int32_t* __restrict__ inv_order, const float* __restrict__ mean,
+                            float* __restrict__ dst) {
+  __shared__ float tile[32][32 * C + 1];
+  const int n0 = blockIdx.x * 32;
+  const int g = blockIdx.y;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // (32, 8)
+  const int width = min(32, N - n0) * C;
+  for (int r = ty; r < 32; r += 8) {
+    const int b = g * 32 + r;
+    for (int e = tx; e < 32 * C; e += 32)
+      tile[r][e] = (b < B && e < width) ? src[((size_t)b * N + n0) * C + e] : 0.f;
+  }
+  __syncthreads();
+  const int b = g * 32 + tx;
+  for (int e = ty; e < width; e += 8) {
+    const int n = n0 + e / C, c = e % C;
+    const int pos = inv_order ? inv_order[n] : n;
+    float v = tile[tx][e];
+    if (mean != nullptr) v -= SF_IM(mean, c, Bp, b);
+    SF_IM(dst, pos * C + c, Bp, b) = (b < B) ? v : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// k_vposed_gemm_simt: v_posed^T[n][b] = v_template_fit[n] + sum_k posedirs_fit[n][k] feat[b][k]
+// (pt/bodyfitter.py:913-916).  Plain FP32 shared-memory tiled GEMM (128 x 64 x 16 tiles,
+// 8 x 4 register micro-tiles); the tcgen05 kernel in vposed_tc.cu replaces it.
+// ---------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(256) k_vposed_gemm_simt(const float* __restrict__ A, const float* __restrict__ vt,
+                                                          const float* __restrict__ F, int M, int Kp, int Bp,
+                                                          float* __restrict__ Cout) {
+  __shared__ float As[16][128 + 4];
+  __shared__ float Fs[16][64 + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * 128, b0 = blockIdx.y * 64;
+  const int ty = tid >> 4, tx = tid & 15;  // 16 x 16 threads; thread tile 8 (m) x 4 (b)
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < Kp; k0 += 16) {
+#pragma unroll
+    for (int l = 0; l < 2; ++l) {
+      const int idx = tid + l * 256;       // 512 float4 = 128 rows x 4
+      const int r = idx >> 2, kq = (idx & 3) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m0 + r < M) v = *reinterpret_cast<const float4*>(A + (size_t)(m0 + r) * Kp + k0 + kq);
+      As[kq + 0][r] = v.x; As[kq + 1][r] = v.y; As[kq + 2][r] = v.z; As[kq + 3][r] = v.w;
+    }
+    {
+      const int r = tid >> 2, kq = (tid & 3) * 4;  // 256 float4 = 64 rows x 4
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (b0 + r < Bp) v = *reinterpret_cast<const float4*>(F + (size_t)(b0 + r) * Kp + k0 + kq);
+      Fs[kq + 0][r] = v.x; Fs[kq + 1][r] = v.y; Fs[kq + 2][r] = v.z; Fs[kq + 3][r] = v.w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float a[8], f[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = As[k][ty * 8 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) f[j] = Fs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], f[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + ty * 8 + i;
+    if (m < M && b0 + tx * 4 < Bp) {
+      const float t = vt[m];
+      float4 o = make_float4(acc[i][0] + t, acc[i][1] + t, acc[i][2] + t, acc[i][3] + t);
+      *reinterpret_cast<float4*>(Cout + (size_t)m * Bp + b0 + tx * 4) = o;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// k_regress: joints^T[j*3+c][b] = sum_i Jreg_fit[j][i] X^T[i*3+c][b]
+// (pt/bodyfitter.py:1342-1344).  One warp per (instance group, block of 8 joints).
+// ---------------------------------------------------------------------------------------
+static __global__ void k_regress(const float* __restrict__ Jreg, const float* __restrict__ X, int V, int J, int Bp,
+                          float* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int jblocks = (J + 7) / 8;
+  const int g = warp / jblocks, jb = warp % jblocks;
+  if (g * 32 >= Bp) return;
+  const int b = g * 32 + lane;
+  const int j0 = jb * 8;
+  float acc[8][3];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) acc[q][0] = acc[q][1] = acc[q][2] = 0.f;
+  for (int i = 0; i < V; ++i) {
+    const float x = SF_IM(X, i * 3 + 0, Bp, b), y = SF_IM(X, i * 3 + 1, Bp, b), z = SF_IM(X, i * 3 + 2, Bp, b);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (j0 + q < J) {
+        const float w = __ldg(Jreg + (size_t)(j0 + q) * V + i);
+        if (w != 0.f) {
+          acc[q][0] = fmaf(w, x, acc[q][0]);
+          acc[q][1] = fmaf(w, y, acc[q][1]);
+          acc[q][2] = fmaf(w, z, acc[q][2]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    if (j0 + q < J) {
+      SF_IM(out, (j0 + q) * 3 + 0, Bp, b) = acc[q][0];
+      SF_IM(out, (j0 + q) * 3 + 1, Bp, b) = acc[q][1];
+      SF_IM(out, (j0 + q) * 3 + 2, Bp, b) = acc[q][2];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// k_stats: per-(segment, instance) sufficient statistics of the rotation stage
+// (pt/bodyfitter.py:235-280), accumulated about provisional centres so nothing cancels:
+//   M  = sum w (t - ct0)(a - ca0)^T   (9)     st = sum w (t - ct0)   (3)
+//   sa = sum w (a - ca0)              (3)     W  = sum w             (1)
+// REF: 0 = template mesh (first fit, B_ref = 1), 1 = reference vertices skinned on the fly
+// from (v_posed, betas, per-joint [R|t]), 2 = explicit reference vertices a^T.
+// One warp per (instance group, segment); lane = instance.
+// ---------------------------------------------------------------------------------------
+struct StatsArgs {
+  const float* tT;        // [3V][Bp] centred targets (internal order)
+  const float* vwT;       // [V][Bp] or null
+  const float* ct0;       // [3J][Bp] provisional target-side centres (target joints)
+  const float* ca0;       // [3J][Bp] provisional reference-side centres (REF != 0)
+  const float* ca0_const; // (J,3) for REF == 0
+  const float* vposedT;   // [3V][Bp] (REF == 1)
+  const float* beta;      // [NS][Bp] (REF == 1)
+  const float* skin;      // [12J][Bp] (REF == 1): rows j*12 + (0..8 R, 9..11 t)
+  const float* aT_in;     // [3V][Bp] (REF == 2)
+  float* aT_out;          // optional [3V][Bp] store of the reference vertices (REF == 1)
+  float* partials;        // [n_segments][16][Bp]
+  const float* template_mesh;  // (V,3)
+  const float* shapedirs;      // (V,3,NS)
+  const int32_t* skin_idx;
+  const float* skin_w;
+  const int32_t* order;
+  const int32_t* seg_start;
+  const int32_t* seg_part;
+  const int32_t* part_flags;
+  int n_segments, Bp, ns, skin_k, all_segments;
+};
+
+template <int REF, bool WEIGHTED>
+__global__ void __launch_bounds__(128) k_stats(const StatsArgs a) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int seg = warp % a.n_segments, g = warp / a.n_segments;
+  if (g * 32 >= a.Bp) return;
+  const int Bp = a.Bp;
+  const int b = g * 32 + lane;
+  const int part = a.seg_part[seg];
+  const bool stat = (a.part_flags[part] & 1) != 0;
+  if (!stat && !(REF == 1 && a.aT_out != nullptr && a.all_segments)) return;
+  float ct[3], ca[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    ct[c] = SF_IM(a.ct0, part * 3 + c, Bp, b);
+    ca[c] = (REF == 0) ? __ldg(a.ca0_const + part * 3 + c) : SF_IM(a.ca0, part * 3 + c, Bp, b);
+  }
+  float beta[SMPLFIT_MAX_UNKNOWNS];
+  if (REF == 1) {
+#pragma unroll
+    for (int s = 0; s < SMPLFIT_MAX_UNKNOWNS; ++s) beta[s] = (s < a.ns) ? SF_IM(a.beta, s, Bp, b) : 0.f;
+  }
+  float M[9], st[3], sa[3], W = 0.f;
+#pragma unroll
+  for (int e = 0; e < 9; ++e) M[e] = 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) st[c] = sa[c] = 0.f;
+  const int i0 = a.seg_start[seg], i1 = a.seg_start[seg + 1];
+  for (int i = i0; i < i1; ++i) {
+    const int v = a.order[i];
+    float ref[3];
+    if (REF == 0) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) ref[c] = __ldg(a.template_mesh + v * 3 + c);
+    } else if (REF == 2) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) ref[c] = SF_IM(a.aT_in, i * 3 + c, Bp, b);
+    } else {
+      float vs[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float x = SF_IM(a.vposedT, i * 3 + c, Bp, b);
+        const float* sd = a.shapedirs + ((size_t)v * 3 + c) * a.ns;
+#pragma unroll
+        for (int s = 0; s < SMPLFIT_MAX_UNKNOWNS; ++s)
+          if (s < a.ns) x = fmaf(__ldg(sd + s), beta[s], x);
+        vs[c] = x;
+      }
+      ref[0] = ref[1] = ref[2] = 0.f;
+      for (int k = 0; k < a.skin_k; ++k) {
+        const int j = __ldg(a.skin_idx + v * a.skin_k + k);
+        const float w = __ldg(a.skin_w + v * a.skin_k + k);
+        const float* sk = a.skin + (size_t)(j * 12) * Bp + b;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float y = sk[(size_t)(9 + c) * Bp];
+          y = fmaf(sk[(size_t)(c * 3 + 0) * Bp], vs[0], y);
+          y = fmaf(sk[(size_t)(c * 3 + 1) * Bp], vs[1], y);
+          y = fmaf(sk[(size_t)(c * 3 + 2) * Bp], vs[2], y);
+          ref[c] = fmaf(w, y, ref[c]);
+        }
+      }
+      if (a.aT_out != nullptr) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) SF_IM(a.aT_out, i * 3 + c, Bp, b) = ref[c];
+      }
+    }
+    if (stat) {
+      const float w = WEIGHTED ? SF_IM(a.vwT, i, Bp, b) : 1.f;
+      float dt[3], wa[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        dt[c] = SF_IM(a.tT, i * 3 + c, Bp, b) - ct[c];
+        wa[c] = w * (ref[c] - ca[c]);
+        st[c] = fmaf(w, dt[c], st[c]);
+        sa[c] += wa[c];
+      }
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) M[r * 3 + c] = fmaf(dt[r], wa[c], M[r * 3 + c]);
+      W += w;
+    }
+  }
+  if (stat) {
+    float* out = a.partials + (size_t)seg * 16 * Bp + b;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) out[(size_t)e * Bp] = M[e];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      out[(size_t)(9 + c) * Bp] = st[c];
+      out[(size_t)(12 + c) * Bp] = sa[c];
+    }
+    out[(size_t)15 * Bp] = W;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// k_shape_pass<NS>: per-(chunk, instance) normal-equation pieces of the shape solve
+// (pt/bodyfitter.py:999-1048):  per vertex  Rb = sum_k w_k R_jk,  Tb = sum_k w_k T_jk,
+//   pos = Rb v_posed + Tb[:,0],   jac[:,s] = Rb S_v[:,s] + Tb[:,1+s],   b = t - pos,
+// accumulating  G = sum w jac^T jac (upper triangle), r = sum w jac^T b, SA = sum w jac,
+// Sb = sum w b, W = sum w  in registers.  The per-joint [R | T_ext] rows of the CTA's 32
+// instances are staged once in shared memory ([row][lane], conflict-free); warps split the
+// CTA's chunks.  Falls back to global/L1 reads when the rows do not fit (SMEM_RT = false).
+// ---------------------------------------------------------------------------------------
+template <int NS>
+struct ShapeAcc {
+  static constexpr int NG = NS * (NS + 1) / 2;
+  static constexpr int N = NG + NS + 3 * NS + 3 + 1;  // G, r, SA, Sb, W
+};
+
+struct ShapeArgs {
+  const float* tT;       // [3V][Bp]
+  const float* vwT;      // [V][Bp] or null (shape-stage weights)
+  const float* vposedT;  // [3V][Bp]
+  const float* RT;       // [J * RW][Bp], RW = 12 + 3 NS: 9 R, then T_ext[c][0..NS]
+  const float* shapedirs;  // (V,3,NS)
+  const int32_t* skin_idx;
+  const float* skin_w;
+  const int32_t* order;
+  float* partials;       // [n_chunks][ShapeAcc<NS>::N][Bp]
+  int V, J, Bp, skin_k, chunk_len, n_chunks, chunks_per_cta;
+};
+
+template <int NS, bool WEIGHTED, bool SMEM_RT>
+__global__ void __launch_bounds__(256) k_shape_pass(const ShapeArgs a) {
+  extern __shared__ float s_rt[];  // [J*RW][32]
+  constexpr int RW = 12 + 3 * NS;
+  constexpr int TW = 3 * (1 + NS);
+  const int g = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Bp = a.Bp;
+  const int b = g * 32 + lane;
+  if (SMEM_RT) {
+    const int rows = a.J * RW;
+    for (int r = warp; r < rows; r += 8) s_rt[r * 32 + lane] = SF_IM(a.RT, r, Bp, b);
+    __syncthreads();
+  }
+  const int chunk = blockIdx.x * a.chunks_per_cta + warp;
+  if (warp >= a.chunks_per_cta || chunk >= a.n_chunks) return;
+  float G[ShapeAcc<NS>::NG], r[NS], SA[3][NS], Sb[3], W = 0.f;
+#pragma unroll
+  for (int e = 0; e < ShapeAcc<NS>::NG; ++e) G[e] = 0.f;
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    r[s] = 0.f;
+    SA[0][s] = SA[1][s] = SA[2][s] = 0.f;
+  }
+  Sb[0] = Sb[1] = Sb[2] = 0.f;
+  const int i0 = chunk * a.chunk_len, i1 = min(a.V, i0 + a.chunk_len);
+  for (int i = i0; i < i1; ++i) {
+    const int v = __ldg(a.order + i);
+    float Rb[9], Tb[TW];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) Rb[e] = 0.f;
+#pragma unroll
+    for (int e = 0; e < TW; ++e) Tb[e] = 0.f;
+    for (int k = 0; k < a.skin_k; ++k) {
+      const int j = __ldg(a.skin_idx + v * a.skin_k + k);
+      const float w = __ldg(a.skin_w + v * a.skin_k + k);
+      if (SMEM_RT) {
+        const float* p = s_rt + (size_t)(j * RW) * 32 + lane;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) Rb[e] = fmaf(w, p[e * 32], Rb[e]);
+#pragma unroll
+        for (int e = 0; e < TW; ++e) Tb[e] = fmaf(w, p[(9 + e) * 32], Tb[e]);
+      } else {
+        const float* p = a.RT + (size_t)(j * RW) * Bp + b;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) Rb[e] = fmaf(w, p[(size_t)e * Bp], Rb[e]);
+#pragma unroll
+        for (int e = 0; e < TW; ++e) Tb[e] = fmaf(w, p[(size_t)(9 + e) * Bp], Tb[e]);
+      }
+    }
+    float vp[3], bv[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) vp[c] = SF_IM(a.vposedT, i * 3 + c, Bp, b);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float pos = fmaf(Rb[c * 3], vp[0], fmaf(Rb[c * 3 + 1], vp[1], fmaf(Rb[c * 3 + 2], vp[2], Tb[c * (1 + NS)])));
+      bv[c] = SF_IM(a.tT, i * 3 + c, Bp, b) - pos;
+    }
+    // jac[c][s] overwrites Tb[c][1+s]
+    const float* sd = a.shapedirs + (size_t)v * 3 * NS;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const float s0 = __ldg(sd + s), s1 = __ldg(sd + NS + s), s2 = __ldg(sd + 2 * NS + s);
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        Tb[c * (1 + NS) + 1 + s] =
+            fmaf(Rb[c * 3], s0, fmaf(Rb[c * 3 + 1], s1, fmaf(Rb[c * 3 + 2], s2, Tb[c * (1 + NS) + 1 + s])));
+    }
+    const float w = WEIGHTED ? SF_IM(a.vwT, i, Bp, b) : 1.f;
+    if (WEIGHTED) W += w;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float wb = WEIGHTED ? w * bv[c] : bv[c];
+      Sb[c] += wb;
+      int e = 0;
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const float js = Tb[c * (1 + NS) + 1 + s];
+        const float wj = WEIGHTED ? w * js : js;
+        SA[c][s] += wj;
+        r[s] = fmaf(wj, bv[c], r[s]);
+#pragma unroll
+        for (int t = s; t < NS; ++t) {
+          G[e] = fmaf(wj, Tb[c * (1 + NS) + 1 + t], G[e]);
+          ++e;
+        }
+      }
+    }
+  }
+  if (!WEIGHTED) W = (float)(i1 - i0);
+  float* out = a.partials + (size_t)chunk * ShapeAcc<NS>::N * Bp + b;
+  int o = 0;
+#pragma unroll
+  for (int e = 0; e < ShapeAcc<NS>::NG; ++e) out[(size_t)(o++) * Bp] = G[e];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) out[(size_t)(o++) * Bp] = r[s];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int s = 0; s < NS; ++s) out[(size_t)(o++) * Bp] = SA[c][s];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) out[(size_t)(o++) * Bp] = Sb[c];
+  out[(size_t)o * Bp] = W;
+}
+
+}  // namespace sf

@@ -1,0 +1,519 @@
+// Per-instance "small" stages of BodyFitter.fit: one thread per instance, instance-minor
+// arrays ([row][Bp]) so every access is coalesced across the warp.  All 3x3 / SxS algebra is
+// register- or local-resident; nothing here touches per-vertex data.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/smplfit_b200.h"
+#include "linalg.cuh"
+
+namespace sf {
+
+#ifndef SF_IM
+#define SF_IM(ptr, row, Bp, b) (ptr)[(size_t)(row) * (size_t)(Bp) + (size_t)(b)]
+#endif
+
+struct TreeTables {
+  const int32_t* parents;
+  const int32_t* part_kind;
+  const int32_t* part_copy_src;
+  const int32_t* part_flags;
+  const int32_t* cas_table;
+  const int32_t* cas_count;
+  const int32_t* part_seg_begin;
+  const float* Jt_ext;  // (J,3,1+NS)
+  int J, NS, max_cas;
+};
+
+__device__ __forceinline__ void load3(const float* p, int row, int Bp, int b, float* out) {
+  out[0] = SF_IM(p, row * 3 + 0, Bp, b);
+  out[1] = SF_IM(p, row * 3 + 1, Bp, b);
+  out[2] = SF_IM(p, row * 3 + 2, Bp, b);
+}
+__device__ __forceinline__ void load3_or_const(const float* p, const float* cst, int row, int Bp, int b, float* out) {
+  if (p != nullptr) {
+    load3(p, row, Bp, b, out);
+  } else {
+    out[0] = __ldg(cst + row * 3);
+    out[1] = __ldg(cst + row * 3 + 1);
+    out[2] = __ldg(cst + row * 3 + 2);
+  }
+}
+
+// Segment partials of one part -> centred cross-covariance about (ct, ca):
+//   sum w (t-ct)(a-ca)^T = M + st (ca0-ca)^T + (ct0-ct) sa^T + W (ct0-ct)(ca0-ca)^T
+__device__ inline void part_covariance(const float* partials, const int32_t* seg_begin, int part, int Bp, int b,
+                                       const float* ct0, const float* ca0, const float* ct, const float* ca,
+                                       float* A) {
+  double acc[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) acc[e] = 0.0;
+  for (int s = seg_begin[part]; s < seg_begin[part + 1]; ++s) {
+    const float* p = partials + (size_t)s * 16 * Bp + b;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) acc[e] += (double)p[(size_t)e * Bp];
+  }
+  const float dt[3] = {ct0[0] - ct[0], ct0[1] - ct[1], ct0[2] - ct[2]};
+  const float da[3] = {ca0[0] - ca[0], ca0[1] - ca[1], ca0[2] - ca[2]};
+  const float W = (float)acc[15];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      A[r * 3 + c] = (float)acc[r * 3 + c] + (float)acc[9 + r] * da[c] + dt[r] * (float)acc[12 + c] + W * dt[r] * da[c];
+}
+
+// ---------------------------------------------------------------------------------------
+// k_rot_solve: _fit_global_rotations after the vertex pass (pt/bodyfitter.py:1352-1416),
+// the left-multiplication onto the running orientations (:422-433), and the pose-dependent
+// front part of the next shape solve (:869-911): relative rotations -> pose features,
+// joint positions with their shape Jacobian (FK), per-joint translation offsets.
+// ---------------------------------------------------------------------------------------
+struct RotArgs {
+  const float* partials;   // [n_segments][16][Bp]
+  const float* tjT;        // [3J][Bp] target joints (given or regressed), centred
+  const float* ajT;        // [3J][Bp] reference joints, or null -> aj_const
+  const float* aj_const;   // (J,3)
+  const float* ca0T;       // [3J][Bp] provisional reference centres of the stats pass, or null -> ca0_const
+  const float* ca0_const;  // (J,3)
+  const float* jwT;        // [J][Bp] or null
+  const float* R_old;      // [9J][Bp] or null (identity)
+  float* R_new;            // [9J][Bp]
+  float* RT;               // [J*(12+3NS)][Bp] or null (skip the shape front)
+  float* Pext;             // [J*3*(1+NS)][Bp]
+  float* feat;             // [Bp][Kp]
+  TreeTables t;
+  int B, Bp, Kp;
+  int front_only;  // 1: keep R_old (orientations given by the caller) and only run the shape front
+};
+
+static __global__ void __launch_bounds__(32) k_rot_solve(const RotArgs a) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.Bp) return;
+  const int J = a.t.J, Bp = a.Bp, NS = a.t.NS;
+  float Rfit[SMPLFIT_MAX_JOINTS * 9];
+  for (int i = 0; i < J; ++i) {
+    const int kind = a.front_only ? 0 : a.t.part_kind[i];
+    float* R = Rfit + i * 9;
+    if (kind == 0 || kind == 4) {
+#pragma unroll
+      for (int e = 0; e < 9; ++e) R[e] = (e % 4 == 0) ? 1.f : 0.f;
+      continue;
+    }
+    const int n = a.t.cas_count[i];
+    const int32_t* cas = a.t.cas_table + i * a.t.max_cas;
+    // children-mean centres (center_matrix, pt/bodyfitter.py:125-129, :1352-1353)
+    float mt[3] = {0.f, 0.f, 0.f}, ma[3] = {0.f, 0.f, 0.f};
+    for (int k = 0; k < n; ++k) {
+      float tj[3], aj[3];
+      load3(a.tjT, cas[k], Bp, b, tj);
+      load3_or_const(a.ajT, a.aj_const, cas[k], Bp, b, aj);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        mt[c] += tj[c];
+        ma[c] += aj[c];
+      }
+    }
+    const float inv = 1.f / (float)n;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      mt[c] *= inv;
+      ma[c] *= inv;
+    }
+    float A[9];
+    if (kind == 1) {
+      // multi-joint part: Kabsch on its joints alone (pt/bodyfitter.py:1361-1383)
+#pragma unroll
+      for (int e = 0; e < 9; ++e) A[e] = 0.f;
+      for (int k = 0; k < n; ++k) {
+        float tj[3], aj[3];
+        load3(a.tjT, cas[k], Bp, b, tj);
+        load3_or_const(a.ajT, a.aj_const, cas[k], Bp, b, aj);
+        const float w = a.jwT ? SF_IM(a.jwT, cas[k], Bp, b) : 1.f;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) A[r * 3 + c] = fmaf(tj[r] - mt[r], w * (aj[c] - ma[c]), A[r * 3 + c]);
+      }
+      proj_so3(A, R);
+      continue;
+    }
+    float ct0[3], ca0[3];
+    load3(a.tjT, i, Bp, b, ct0);
+    load3_or_const(a.ca0T, a.ca0_const, i, Bp, b, ca0);
+    part_covariance(a.partials, a.t.part_seg_begin, i, Bp, b, ct0, ca0, mt, ma, A);
+    if (kind == 3) {  // leaf part: Kabsch on its vertices
+      proj_so3(A, R);
+      continue;
+    }
+    // bone part: swing aligns the bone, twist from the vertex covariance (pt/bodyfitter.py:1389-1412)
+    float bt[3], br[3], t0[3], t1[3], r0[3], r1[3];
+    load3(a.tjT, cas[0], Bp, b, t0);
+    load3(a.tjT, cas[1], Bp, b, t1);
+    load3_or_const(a.ajT, a.aj_const, cas[0], Bp, b, r0);
+    load3_or_const(a.ajT, a.aj_const, cas[1], Bp, b, r1);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      bt[c] = t1[c] - t0[c];
+      br[c] = r1[c] - r0[c];
+    }
+    const float nt = sqrtf(bt[0] * bt[0] + bt[1] * bt[1] + bt[2] * bt[2]);
+    const float nr = sqrtf(br[0] * br[0] + br[1] * br[1] + br[2] * br[2]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      bt[c] = div_no_nan(bt[c], nt);
+      br[c] = div_no_nan(br[c], nr);
+    }
+    float Rs[9], H[9];
+    align_unit_vectors(br, bt, Rs);
+    // H = Rs A^T
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) H[r * 3 + c] = Rs[r * 3] * A[c * 3] + Rs[r * 3 + 1] * A[c * 3 + 1] + Rs[r * 3 + 2] * A[c * 3 + 2];
+    const float trH = H[0] + H[4] + H[8];
+    float Hb[3];
+    mat3_vec(H, bt, Hb);
+    const float bHb = bt[0] * Hb[0] + bt[1] * Hb[1] + bt[2] * Hb[2];
+    const float vee[3] = {H[5] - H[7], H[6] - H[2], H[1] - H[3]};
+    const float ang = atan2f(bt[0] * vee[0] + bt[1] * vee[1] + bt[2] * vee[2], trH - bHb);
+    float rv[3] = {bt[0] * ang, bt[1] * ang, bt[2] * ang}, Rt[9];
+    rotvec2mat(rv, Rt);
+    mat3_mul(Rt, Rs, R);
+  }
+  // assemble (toe parts take the feet's fit, pt/bodyfitter.py:1414-1416) and left-multiply
+  for (int i = 0; i < J; ++i) {
+    const int src = (!a.front_only && a.t.part_kind[i] == 4) ? a.t.part_copy_src[i] : i;
+    float Rn[9];
+    if (a.R_old != nullptr) {
+      float Ro[9];
+#pragma unroll
+      for (int e = 0; e < 9; ++e) Ro[e] = SF_IM(a.R_old, i * 9 + e, Bp, b);
+      mat3_mul(Rfit + src * 9, Ro, Rn);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 9; ++e) Rn[e] = Rfit[src * 9 + e];
+    }
+#pragma unroll
+    for (int e = 0; e < 9; ++e) SF_IM(a.R_new, i * 9 + e, Bp, b) = Rn[e];
+  }
+  if (a.RT == nullptr) return;
+  // ---- shape front (pt/bodyfitter.py:869-911) ----
+  const int TW = 3 * (1 + NS), RW = 12 + 3 * NS;
+  for (int j = 0; j < J; ++j) {
+    float Rj[9];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) Rj[e] = SF_IM(a.R_new, j * 9 + e, Bp, b);
+    const int par = a.t.parents[j];
+    const float* Jt = a.t.Jt_ext + (size_t)j * TW;
+    if (j == 0) {
+      for (int e = 0; e < TW; ++e) SF_IM(a.Pext, e, Bp, b) = __ldg(Jt + e);
+    } else {
+      float Rp[9], rel[9];
+#pragma unroll
+      for (int e = 0; e < 9; ++e) Rp[e] = SF_IM(a.R_new, par * 9 + e, Bp, b);
+      mat3_tmul(Rp, Rj, rel);
+      if (b < a.B || true) {
+#pragma unroll
+        for (int e = 0; e < 9; ++e) a.feat[(size_t)b * a.Kp + (j - 1) * 9 + e] = rel[e];
+      }
+      const float* Jp = a.t.Jt_ext + (size_t)par * TW;
+      for (int s = 0; s <= NS; ++s) {
+        const float d0 = __ldg(Jt + s) - __ldg(Jp + s);
+        const float d1 = __ldg(Jt + (1 + NS) + s) - __ldg(Jp + (1 + NS) + s);
+        const float d2 = __ldg(Jt + 2 * (1 + NS) + s) - __ldg(Jp + 2 * (1 + NS) + s);
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          SF_IM(a.Pext, j * TW + c * (1 + NS) + s, Bp, b) =
+              SF_IM(a.Pext, par * TW + c * (1 + NS) + s, Bp, b) + (Rp[c * 3] * d0 + Rp[c * 3 + 1] * d1 + Rp[c * 3 + 2] * d2);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 9; ++e) SF_IM(a.RT, j * RW + e, Bp, b) = Rj[e];
+    for (int s = 0; s <= NS; ++s) {
+      const float j0 = __ldg(Jt + s), j1 = __ldg(Jt + (1 + NS) + s), j2 = __ldg(Jt + 2 * (1 + NS) + s);
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        SF_IM(a.RT, j * RW + 9 + c * (1 + NS) + s, Bp, b) =
+            SF_IM(a.Pext, j * TW + c * (1 + NS) + s, Bp, b) - (Rj[c * 3] * j0 + Rj[c * 3 + 1] * j1 + Rj[c * 3 + 2] * j2);
+    }
+  }
+  for (int k = 9 * (J - 1); k < a.Kp; ++k) a.feat[(size_t)b * a.Kp + k] = 0.f;
+}
+
+// ---------------------------------------------------------------------------------------
+// k_front_from_R: the shape front alone, for orientations given by the caller
+// (fit_with_known_pose, pt/bodyfitter.py:617-639).  Reuses k_rot_solve's tail by running it
+// with every part marked "none" and R_old = the given orientations.
+// ---------------------------------------------------------------------------------------
+
+// ---------------------------------------------------------------------------------------
+// k_shape_solve<NS>: combine the chunk partials in double, add the joint block, centre with
+// the covariance identity, regularise, Cholesky-solve, recover the translation
+// (pt/bodyfitter.py:1050-1089; general solve :1199-1283 is algebraically the same system),
+// then emit what the next vertex pass needs: betas, translation, the reference joints
+// (:1093-1098) and the per-joint skinning transforms [R | T0 + T1 x + trans].
+// ---------------------------------------------------------------------------------------
+struct SolveArgs {
+  const float* partials;  // [n_chunks][NACC][Bp]
+  const float* Pext;      // [J*3*(1+NS)][Bp]
+  const float* RT;        // [J*(12+3NS)][Bp]
+  const float* tjT;       // [3J][Bp] or null (no joint block)
+  const float* jwT;       // [J][Bp] or null (unit weights)
+  const float* beta_ref;  // (B,S) instance-major or null
+  const float* kid_ref;   // (B) or null
+  float* beta;            // [NS][Bp]
+  float* trans;           // [3][Bp]
+  float* refj;            // [3J][Bp]
+  float* skin;            // [12J][Bp]
+  int n_chunks, J, S, Bp, B, V, weighted;
+  float reg, reg2, kid_reg;
+};
+
+template <int NS>
+__global__ void __launch_bounds__(32) k_shape_solve(const SolveArgs a) {
+  constexpr int NG = NS * (NS + 1) / 2;
+  constexpr int NACC = NG + NS + 3 * NS + 3 + 1;
+  constexpr int TW = 3 * (1 + NS), RW = 12 + 3 * NS;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.Bp) return;
+  const int Bp = a.Bp, J = a.J;
+  double G[NS][NS], r[NS], SA[3][NS], Sb[3], W = 0.0;
+  {
+    double acc[NACC];
+#pragma unroll 1
+    for (int e = 0; e < NACC; ++e) acc[e] = 0.0;
+    for (int c = 0; c < a.n_chunks; ++c) {
+      const float* p = a.partials + (size_t)c * NACC * Bp + b;
+#pragma unroll 4
+      for (int e = 0; e < NACC; ++e) acc[e] += (double)p[(size_t)e * Bp];
+    }
+    int o = 0;
+    for (int s = 0; s < NS; ++s)
+      for (int t = s; t < NS; ++t) {
+        G[s][t] = acc[o];
+        G[t][s] = acc[o];
+        ++o;
+      }
+    for (int s = 0; s < NS; ++s) r[s] = acc[o++];
+    for (int c = 0; c < 3; ++c)
+      for (int s = 0; s < NS; ++s) SA[c][s] = acc[o++];
+    for (int c = 0; c < 3; ++c) Sb[c] = acc[o++];
+    W = acc[o];
+  }
+  if (a.tjT != nullptr) {
+    for (int j = 0; j < J; ++j) {
+      const double w = a.jwT ? (double)SF_IM(a.jwT, j, Bp, b) : 1.0;
+      W += w;
+      for (int c = 0; c < 3; ++c) {
+        const float* prow = a.Pext + (size_t)(j * TW + c * (1 + NS)) * Bp + b;
+        const double bj = (double)SF_IM(a.tjT, j * 3 + c, Bp, b) - (double)prow[0];
+        Sb[c] += w * bj;
+        double jac[NS];
+        for (int s = 0; s < NS; ++s) jac[s] = (double)prow[(size_t)(1 + s) * Bp];
+        for (int s = 0; s < NS; ++s) {
+          const double wj = w * jac[s];
+          SA[c][s] += wj;
+          r[s] += wj * bj;
+          for (int t = 0; t < NS; ++t) G[s][t] += wj * jac[t];
+        }
+      }
+    }
+  }
+  const double Ws = (W == 0.0) ? 1.0 : W;
+  double rhs[NS];
+  for (int s = 0; s < NS; ++s) {
+    double rc = r[s];
+    for (int c = 0; c < 3; ++c) rc -= SA[c][s] * Sb[c] / Ws;
+    for (int t = 0; t < NS; ++t) {
+      double g = G[s][t];
+      for (int c = 0; c < 3; ++c) g -= SA[c][s] * SA[c][t] / Ws;
+      G[s][t] = g;
+    }
+    double lam = (s < 2) ? (double)a.reg2 : (double)a.reg;
+    double ref = 0.0;
+    if (s < a.S) {
+      if (a.beta_ref != nullptr && b < a.B) ref = (double)a.beta_ref[(size_t)b * a.S + s];
+    } else {  // kid unknown
+      lam = (double)a.kid_reg;
+      if (a.kid_ref != nullptr && b < a.B) ref = (double)a.kid_ref[b];
+    }
+    G[s][s] += lam;
+    rhs[s] = rc + lam * ref;
+  }
+  chol_solve<NS>(G, rhs, NS);
+  float x[NS], tr[3];
+  for (int s = 0; s < NS; ++s) {
+    x[s] = (float)rhs[s];
+    SF_IM(a.beta, s, Bp, b) = x[s];
+  }
+  for (int c = 0; c < 3; ++c) {
+    double m = Sb[c] / Ws;
+    for (int s = 0; s < NS; ++s) m -= SA[c][s] / Ws * rhs[s];
+    tr[c] = (float)m;
+    SF_IM(a.trans, c, Bp, b) = tr[c];
+  }
+  for (int j = 0; j < J; ++j) {
+#pragma unroll
+    for (int e = 0; e < 9; ++e) SF_IM(a.skin, j * 12 + e, Bp, b) = SF_IM(a.RT, j * RW + e, Bp, b);
+    for (int c = 0; c < 3; ++c) {
+      const float* prow = a.Pext + (size_t)(j * TW + c * (1 + NS)) * Bp + b;
+      const float* trow = a.RT + (size_t)(j * RW + 9 + c * (1 + NS)) * Bp + b;
+      float pj = 0.f, tj = 0.f;
+      for (int s = 0; s < NS; ++s) {
+        pj = fmaf(prow[(size_t)(1 + s) * Bp], x[s], pj);
+        tj = fmaf(trow[(size_t)(1 + s) * Bp], x[s], tj);
+      }
+      SF_IM(a.refj, j * 3 + c, Bp, b) = prow[0] + pj + tr[c];
+      SF_IM(a.skin, j * 12 + 9 + c, Bp, b) = trow[0] + tj + tr[c];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// k_adjust_solve: _fit_global_rotations_dependent (pt/bodyfitter.py:1418-1595, sequential
+// form): walk the tree, re-anchor each adjustable part at its recomputed joint position.
+// ---------------------------------------------------------------------------------------
+struct AdjustArgs {
+  const float* partials;  // stats of (target, final reference) about (ct0 = tj_i, ca0 = refj_i)
+  const float* tjT;       // [3J][Bp]
+  const float* ajT;       // [3J][Bp] reference joints of the joint term (given-joints: == refj)
+  const float* refj;      // [3J][Bp] true reference joints (c_a)
+  const float* jwT;       // [J][Bp] or null
+  const float* R_prev;    // [9J][Bp]
+  const float* beta;      // [NS][Bp]
+  const float* trans;     // [3][Bp]
+  float* R_out;           // [9J][Bp]
+  TreeTables t;
+  int Bp;
+};
+
+static __global__ void __launch_bounds__(32) k_adjust_solve(const AdjustArgs a) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.Bp) return;
+  const int J = a.t.J, NS = a.t.NS, Bp = a.Bp;
+  const int TW = 3 * (1 + NS);
+  float x[SMPLFIT_MAX_UNKNOWNS];
+  for (int s = 0; s < NS; ++s) x[s] = SF_IM(a.beta, s, Bp, b);
+  float pos[SMPLFIT_MAX_JOINTS * 3], rest[SMPLFIT_MAX_JOINTS * 3];
+  for (int j = 0; j < J; ++j)
+    for (int c = 0; c < 3; ++c) {
+      const float* Jt = a.t.Jt_ext + (size_t)j * TW + c * (1 + NS);
+      float v = __ldg(Jt);
+      for (int s = 0; s < NS; ++s) v = fmaf(__ldg(Jt + 1 + s), x[s], v);
+      rest[j * 3 + c] = v;
+    }
+  for (int i = 0; i < J; ++i) {
+    const int par = a.t.parents[i];
+    if (i == 0) {
+      for (int c = 0; c < 3; ++c) pos[c] = rest[c] + SF_IM(a.trans, c, Bp, b);
+    } else {
+      float Rp[9];
+#pragma unroll
+      for (int e = 0; e < 9; ++e) Rp[e] = SF_IM(a.R_out, par * 9 + e, Bp, b);
+      const float bone[3] = {rest[i * 3] - rest[par * 3], rest[i * 3 + 1] - rest[par * 3 + 1], rest[i * 3 + 2] - rest[par * 3 + 2]};
+      float rb[3];
+      mat3_vec(Rp, bone, rb);
+      for (int c = 0; c < 3; ++c) pos[i * 3 + c] = pos[par * 3 + c] + rb[c];
+    }
+    const int kind = a.t.part_kind[i];
+    float Rn[9];
+    if (kind == 4) {  // toes copy the (already adjusted) feet
+      const int src = a.t.part_copy_src[i];
+#pragma unroll
+      for (int e = 0; e < 9; ++e) Rn[e] = SF_IM(a.R_out, src * 9 + e, Bp, b);
+    } else if ((a.t.part_flags[i] & 2) == 0) {
+#pragma unroll
+      for (int e = 0; e < 9; ++e) Rn[e] = SF_IM(a.R_prev, i * 9 + e, Bp, b);
+    } else {
+      float ct0[3], ca[3], A[9];
+      load3(a.tjT, i, Bp, b, ct0);
+      load3(a.refj, i, Bp, b, ca);
+      part_covariance(a.partials, a.t.part_seg_begin, i, Bp, b, ct0, ca, pos + i * 3, ca, A);
+      const int n = a.t.cas_count[i];
+      const int32_t* cas = a.t.cas_table + i * a.t.max_cas;
+      for (int k = 0; k < n; ++k) {
+        float tj[3], aj[3];
+        load3(a.tjT, cas[k], Bp, b, tj);
+        load3(a.ajT, cas[k], Bp, b, aj);
+        const float w = a.jwT ? SF_IM(a.jwT, cas[k], Bp, b) : 1.f;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            A[r * 3 + c] = fmaf(tj[r] - pos[i * 3 + r], w * (aj[c] - ca[c]), A[r * 3 + c]);
+      }
+      float Rf[9], Ro[9];
+      proj_so3(A, Rf);
+#pragma unroll
+      for (int e = 0; e < 9; ++e) Ro[e] = SF_IM(a.R_prev, i * 9 + e, Bp, b);
+      mat3_mul(Rf, Ro, Rn);
+    }
+#pragma unroll
+    for (int e = 0; e < 9; ++e) SF_IM(a.R_out, i * 9 + e, Bp, b) = Rn[e];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// k_output: caller-facing results in the reference layouts (pt/bodyfitter.py:513-549):
+// trans + target mean, orientations, relative orientations, pose rotation vectors.
+// ---------------------------------------------------------------------------------------
+struct OutputArgs {
+  const float* R_final;  // [9J][Bp]
+  const float* R_rel_src;  // orientations the relative rotations are derived from
+  const float* beta;     // [NS][Bp]
+  const float* trans;    // [3][Bp]
+  const float* mean;     // [3][Bp]
+  const int32_t* parents;
+  float* pose_rotvecs;   // (B,3J) or null
+  float* shape_betas;    // (B,S)
+  float* out_trans;      // (B,3)
+  float* orientations;   // (B,J,3,3)
+  float* rel_orient;     // (B,J,3,3) or null
+  float* kid;            // (B) or null
+  int J, S, NS, B, Bp;
+};
+
+static __global__ void __launch_bounds__(32) k_output(const OutputArgs a) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.B) return;
+  const int J = a.J, Bp = a.Bp;
+  for (int s = 0; s < a.S; ++s) a.shape_betas[(size_t)b * a.S + s] = SF_IM(a.beta, s, Bp, b);
+  if (a.kid != nullptr) a.kid[b] = SF_IM(a.beta, a.S, Bp, b);
+  for (int c = 0; c < 3; ++c) a.out_trans[(size_t)b * 3 + c] = SF_IM(a.trans, c, Bp, b) + SF_IM(a.mean, c, Bp, b);
+  for (int j = 0; j < J; ++j) {
+    float R[9];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) {
+      R[e] = SF_IM(a.R_final, j * 9 + e, Bp, b);
+      if (a.orientations != nullptr) a.orientations[((size_t)b * J + j) * 9 + e] = R[e];
+    }
+    if (a.rel_orient != nullptr || a.pose_rotvecs != nullptr) {
+      float Rs[9], rel[9];
+#pragma unroll
+      for (int e = 0; e < 9; ++e) Rs[e] = SF_IM(a.R_rel_src, j * 9 + e, Bp, b);
+      if (j == 0) {
+#pragma unroll
+        for (int e = 0; e < 9; ++e) rel[e] = Rs[e];
+      } else {
+        float Rp[9];
+        const int par = a.parents[j];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) Rp[e] = SF_IM(a.R_rel_src, par * 9 + e, Bp, b);
+        mat3_tmul(Rp, Rs, rel);
+      }
+      if (a.rel_orient != nullptr) {
+#pragma unroll
+        for (int e = 0; e < 9; ++e) a.rel_orient[((size_t)b * J + j) * 9 + e] = rel[e];
+      }
+      if (a.pose_rotvecs != nullptr) {
+        float rv[3];
+        mat2rotvec(rel, rv);
+        for (int c = 0; c < 3; ++c) a.pose_rotvecs[(size_t)b * 3 * J + j * 3 + c] = rv[c];
+      }
+    }
+  }
+}
+
+}  // namespace sf

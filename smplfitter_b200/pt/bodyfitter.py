@@ -1,0 +1,274 @@
+"""``BodyFitter`` -- drop-in for ``smplfitter.pt.BodyFitter``
+(/root/reference/src/smplfitter/pt/bodyfitter.py:15-1681): closed-form inverse of the body
+model.  ``fit`` / ``fit_with_known_pose`` run entirely in the sm_100a CUDA library
+(``smplfit_fit`` / ``smplfit_fit_known_pose``); this module only validates arguments, owns the
+static index tables (bit-exact with the reference's ``__init__``, see masks.py) and marshals
+pointers.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _native
+
+
+class BodyFitter(nn.Module):
+    """Fits body-model parameters to target vertices (and optionally joints).
+
+    Parameters:
+        body_model: the ``smplfitter_b200.pt.BodyModel`` to fit.
+        enable_kid: adds the kid blend-shape factor as an unknown (pt/bodyfitter.py:25-33).
+    """
+
+    def __init__(self, body_model, enable_kid: bool = False):
+        super().__init__()
+        self.body_model = body_model
+        self.n_betas = body_model.shapedirs.shape[2]
+        self.enable_kid = enable_kid
+        plan = body_model._plan
+        self.is_smpl_family = plan.is_smpl_family
+        # reference-named static tables (pt/bodyfitter.py:36-233)
+        i64 = lambda x: torch.tensor(np.asarray(x), dtype=torch.int64)  # noqa: E731
+        self.part_assignment = nn.Buffer(i64(plan.part_assignment))
+        self.part_vertex_selectors = [i64(s) for s in plan.part_vertex_selectors]
+        self.children_and_self = plan.children_and_self
+        self.descendants_and_self = plan.descendants_and_self
+        self.multi_joint_parts = plan.multi_joint_parts
+        self.bone_parts = plan.bone_parts
+        self.leaf_parts = plan.leaf_parts
+        self.adjustable_parts = plan.adjustable_parts
+        self.used_vertex_indices = nn.Buffer(i64(plan.used_vertex_indices))
+        self.assemble_indices = nn.Buffer(i64(plan.assemble_indices))
+        self.bone_pairs = nn.Buffer(i64(plan.bone_pairs))
+        self.fk_js = nn.Buffer(i64(plan.fk_js))
+        self.fk_ps = nn.Buffer(i64(plan.fk_ps))
+        self.fk_level_sizes = plan.fk_level_sizes
+        self.num_fk_levels = len(plan.fk_level_sizes)
+        self.adj_parts = nn.Buffer(i64(plan.adj_parts))
+        self.adj_level_sizes = plan.adj_level_sizes
+        self.adj_last_level = plan.adj_last_level
+        self.adj_part_joints = nn.Buffer(i64(plan.adj_part_joints))
+        self.leveladj_supported = plan.leveladj_supported
+        self.cas_flat = nn.Buffer(i64(plan.cas_flat))
+        self.cas_starts = plan.cas_starts
+        self.default_mesh_tf = body_model._t_template_mesh
+        J, V, S = body_model.num_joints, body_model.num_vertices, self.n_betas
+        self.gram_supported = (not enable_kid) and J * 3 * V * S <= 2 ** 26
+        # unknown-wise extended tables: [betas | kid]
+        sd = body_model.shapedirs
+        jt = [body_model.J_template.reshape(-1, 3, 1), body_model.J_shapedirs]
+        if enable_kid:
+            sd = torch.cat([sd, body_model.kid_shapedir[:, :, None]], dim=2)
+            jt.append(body_model.kid_J_shapedir.reshape(-1, 3, 1))
+        self.register_buffer('_t_fit_shapedirs', sd.contiguous().clone(), persistent=False)
+        self.J_template_ext = nn.Buffer(torch.cat(jt, dim=2).contiguous())
+        self._ns = S + (1 if enable_kid else 0)
+
+    def _struct(self) -> _native.ModelStruct:
+        return self.body_model._struct(dict(
+            fit_ns=self._ns,
+            fit_shapedirs=self._t_fit_shapedirs.data_ptr(),
+            fit_Jt_ext=self.J_template_ext.data_ptr(),
+        ))
+
+    # ------------------------------------------------------------------------------
+    def _prep(self, x, shape, name):
+        if x is None:
+            return None
+        if isinstance(x, np.ndarray):
+            raise TypeError(f"Expected torch.Tensor for '{name}', got numpy.ndarray.")
+        dev = self.body_model.v_template.device
+        x = x.to(device=dev, dtype=torch.float32)
+        if tuple(x.shape) != tuple(shape):
+            raise ValueError(f"'{name}' must have shape {tuple(shape)}, got {tuple(x.shape)}")
+        return x.contiguous()
+
+    def _opts(self, num_iter, final_adjust_rots, requested_keys, shape_weights, beta_regularizer,
+              beta_regularizer2, kid_regularizer, scale_mode, scale_regularizer) -> _native.FitOpts:
+        o = _native.FitOpts()
+        o.num_iter = int(num_iter)
+        o.final_adjust_rots = int(bool(final_adjust_rots))
+        o.enable_kid = int(self.enable_kid)
+        o.want_pose_rotvecs = int('pose_rotvecs' in requested_keys)
+        o.want_rel_orient = int('relative_orientations' in requested_keys)
+        o.shape_weights = int(shape_weights)
+        o.scale_mode = scale_mode
+        o.beta_regularizer = float(beta_regularizer)
+        o.beta_regularizer2 = float(beta_regularizer2)
+        o.kid_regularizer = float(beta_regularizer if kid_regularizer is None else kid_regularizer)
+        o.scale_regularizer = float(scale_regularizer)
+        return o
+
+    @staticmethod
+    def _shape_weights_rule(target_joints, vertex_weights, joint_weights) -> bool:
+        """pt/bodyfitter.py:1018-1028: weights enter the shape solve only as a complete set."""
+        if target_joints is not None:
+            return vertex_weights is not None and joint_weights is not None
+        return vertex_weights is not None
+
+    def _pad_ref(self, ref, B, name):
+        if ref is None:
+            return None
+        dev = self.body_model.v_template.device
+        ref = ref.to(device=dev, dtype=torch.float32)
+        out = torch.zeros((B, self.n_betas), device=dev, dtype=torch.float32)
+        n = min(ref.shape[1], self.n_betas)
+        out[:, :n] = ref[:, :n]
+        return out
+
+    # ------------------------------------------------------------------------------
+    def fit(
+        self,
+        target_vertices: torch.Tensor,
+        target_joints: Optional[torch.Tensor] = None,
+        vertex_weights: Optional[torch.Tensor] = None,
+        joint_weights: Optional[torch.Tensor] = None,
+        num_iter: int = 1,
+        beta_regularizer: float = 1,
+        beta_regularizer2: float = 0,
+        scale_regularizer: float = 0,
+        kid_regularizer: Optional[float] = None,
+        share_beta: bool = False,
+        final_adjust_rots: bool = True,
+        scale_target: bool = False,
+        scale_fit: bool = False,
+        initial_pose_rotvecs: Optional[torch.Tensor] = None,
+        initial_shape_betas: Optional[torch.Tensor] = None,
+        initial_kid_factor: Optional[torch.Tensor] = None,
+        requested_keys: Optional[list] = None,
+    ) -> dict[str, torch.Tensor]:
+        """Fit pose, shape and translation (pt/bodyfitter.py:283-549; same arguments and result keys)."""
+        if requested_keys is None:
+            requested_keys = ['pose_rotvecs']
+        if scale_target and scale_fit:
+            raise ValueError('Only one of estim_scale_target and estim_scale_fit can be True')
+        if share_beta:
+            raise NotImplementedError('share_beta is not implemented on the CUDA path (SURVEY.md 8f-2)')
+        if scale_target or scale_fit:
+            raise NotImplementedError('scale_target / scale_fit are not implemented on the CUDA path yet')
+        bm = self.body_model
+        dev = bm.v_template.device
+        _native.require_cuda(bm.v_template, 'the body model')
+        if isinstance(target_vertices, np.ndarray):
+            raise TypeError("Expected torch.Tensor for 'target_vertices', got numpy.ndarray.")
+        if target_vertices.ndim != 3:
+            raise ValueError(f'target_vertices must be (batch, {bm.num_vertices}, 3)')
+        B, V, J, S = target_vertices.shape[0], bm.num_vertices, bm.num_joints, self.n_betas
+        tv = self._prep(target_vertices, (B, V, 3), 'target_vertices')
+        tj = self._prep(target_joints, (B, J, 3), 'target_joints')
+        vw = self._prep(vertex_weights, (B, V), 'vertex_weights')
+        jw = self._prep(joint_weights, (B, J), 'joint_weights')
+        new = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)  # noqa: E731
+        out = dict(shape_betas=new(B, S), trans=new(B, 3), orientations=new(B, J, 3, 3),
+                   relative_orientations=new(B, J, 3, 3))
+        rotvecs = new(B, 3 * J) if 'pose_rotvecs' in requested_keys else None
+        kid = new(B) if self.enable_kid else None
+        if B == 0:
+            if rotvecs is not None:
+                out['pose_rotvecs'] = rotvecs
+            if kid is not None:
+                out['kid_factor'] = kid
+            return out
+        init_v = init_j = init_o = None
+        if initial_pose_rotvecs is not None or initial_shape_betas is not None:
+            init = bm(shape_betas=initial_shape_betas, kid_factor=initial_kid_factor,
+                      pose_rotvecs=initial_pose_rotvecs)
+            expand = lambda x: x.expand(B, *x.shape[1:]).contiguous()  # noqa: E731
+            init_v, init_j, init_o = expand(init['vertices']), expand(init['joints']), expand(init['orientations'])
+        beta_ref = self._pad_ref(initial_shape_betas, B, 'initial_shape_betas')
+        kid_ref = None
+        if initial_kid_factor is not None and self.enable_kid:
+            kid_ref = torch.as_tensor(initial_kid_factor, dtype=torch.float32, device=dev).reshape(-1).expand(B).contiguous()
+        o = self._opts(num_iter, final_adjust_rots, requested_keys,
+                       self._shape_weights_rule(tj, vw, jw), beta_regularizer, beta_regularizer2,
+                       kid_regularizer, 0, scale_regularizer)
+        L = _native.lib()
+        s = self._struct()
+        ws_bytes = L.smplfit_fit_workspace_bytes(C.byref(s), B, C.byref(o), int(tj is not None),
+                                                 int(vw is not None), int(jw is not None))
+        if ws_bytes == 0:
+            _native.check(-2 if self._ns > 17 else -1)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        p = _native.ptr
+        with torch.cuda.device(dev):
+            _native.check(L.smplfit_fit(
+                C.byref(s), B, p(tv), p(tj), p(vw), p(jw), p(beta_ref), p(kid_ref), p(init_v), p(init_j),
+                p(init_o), C.byref(o), p(rotvecs), p(out['shape_betas']), p(out['trans']),
+                p(out['orientations']), p(out['relative_orientations']), p(kid), 0, ws.data_ptr(), ws_bytes,
+                _native.stream_ptr(dev),
+            ))
+        ws.record_stream(torch.cuda.current_stream(dev))
+        if rotvecs is not None:
+            out['pose_rotvecs'] = rotvecs
+        if kid is not None:
+            out['kid_factor'] = kid
+        return out
+
+    # ------------------------------------------------------------------------------
+    def fit_with_known_pose(
+        self,
+        pose_rotvecs: torch.Tensor,
+        target_vertices: torch.Tensor,
+        target_joints: Optional[torch.Tensor] = None,
+        vertex_weights: Optional[torch.Tensor] = None,
+        joint_weights: Optional[torch.Tensor] = None,
+        beta_regularizer: float = 1,
+        beta_regularizer2: float = 0,
+        scale_regularizer: float = 0,
+        kid_regularizer: Optional[float] = None,
+        share_beta: bool = False,
+        scale_target: bool = False,
+        scale_fit: bool = False,
+        beta_regularizer_reference: Optional[torch.Tensor] = None,
+        kid_regularizer_reference: Optional[torch.Tensor] = None,
+        requested_keys: Optional[list] = None,
+    ) -> dict[str, torch.Tensor]:
+        """Shape and translation for a known pose (pt/bodyfitter.py:552-653)."""
+        if scale_target and scale_fit:
+            raise ValueError('Only one of estim_scale_target and estim_scale_fit can be True')
+        if share_beta or scale_target or scale_fit:
+            raise NotImplementedError('share_beta / scale options are not implemented on the CUDA path yet')
+        bm = self.body_model
+        dev = bm.v_template.device
+        _native.require_cuda(bm.v_template, 'the body model')
+        B, V, J, S = target_vertices.shape[0], bm.num_vertices, bm.num_joints, self.n_betas
+        tv = self._prep(target_vertices, (B, V, 3), 'target_vertices')
+        tj = self._prep(target_joints, (B, J, 3), 'target_joints')
+        vw = self._prep(vertex_weights, (B, V), 'vertex_weights')
+        jw = self._prep(joint_weights, (B, J), 'joint_weights')
+        glob = bm(pose_rotvecs=pose_rotvecs, return_vertices=False)['orientations']
+        new = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)  # noqa: E731
+        out = dict(shape_betas=new(B, S), trans=new(B, 3), relative_orientations=new(B, J, 3, 3))
+        kid = new(B) if self.enable_kid else None
+        beta_ref = self._pad_ref(beta_regularizer_reference, B, 'beta_regularizer_reference')
+        kid_ref = None
+        if kid_regularizer_reference is not None and self.enable_kid:
+            kid_ref = kid_regularizer_reference.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+        o = self._opts(1, False, [], self._shape_weights_rule(tj, vw, jw), beta_regularizer, beta_regularizer2,
+                       kid_regularizer, 0, scale_regularizer)
+        L = _native.lib()
+        s = self._struct()
+        ws_bytes = L.smplfit_fit_workspace_bytes(C.byref(s), B, C.byref(o), int(tj is not None),
+                                                 int(vw is not None), int(jw is not None))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        p = _native.ptr
+        with torch.cuda.device(dev):
+            _native.check(L.smplfit_fit_known_pose(
+                C.byref(s), B, p(glob), p(tv), p(tj), p(vw), p(jw), p(beta_ref), p(kid_ref), C.byref(o),
+                p(out['shape_betas']), p(out['trans']), p(out['relative_orientations']), p(kid), 0,
+                ws.data_ptr(), ws_bytes, _native.stream_ptr(dev),
+            ))
+        ws.record_stream(torch.cuda.current_stream(dev))
+        if kid is not None:
+            out['kid_factor'] = kid
+        return out
+
+    def fit_with_known_shape(self, *args, **kwargs):
+        """pt/bodyfitter.py:656-838 -- pose-only variant; not on the CUDA path yet."""
+        raise NotImplementedError('fit_with_known_shape is not implemented on the CUDA path yet')

@@ -1,0 +1,308 @@
+"""``BodyModel`` -- drop-in for ``smplfitter.pt.BodyModel``
+(/root/reference/src/smplfitter/pt/bodymodel.py:12-453) whose ``forward`` runs in the sm_100a
+CUDA library (``smplfit_forward``).  Same constructor and method signatures, same buffers,
+same result dictionaries, same error conventions (:164-200, :210-217).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _native, masks, modeldata
+
+SEG_LEN = 64  # vertices per statistics segment
+CHUNK_LEN = 128  # vertices per shape-pass chunk
+
+
+def _segments(part_sorted: np.ndarray, num_joints: int):
+    """Split the part-grouped vertex order into segments of <= SEG_LEN vertices of one part."""
+    seg_start, seg_part = [0], []
+    part_seg_begin = np.zeros(num_joints + 1, dtype=np.int32)
+    V = len(part_sorted)
+    i = 0
+    for p in range(num_joints):
+        part_seg_begin[p] = len(seg_part)
+        n = int((part_sorted == p).sum())
+        done = 0
+        while done < n:
+            step = min(SEG_LEN, n - done)
+            seg_part.append(p)
+            seg_start.append(i + done + step)
+            done += step
+        i += n
+    part_seg_begin[num_joints] = len(seg_part)
+    assert i == V
+    return np.array(seg_start, np.int32), np.array(seg_part, np.int32), part_seg_begin
+
+
+class BodyModel(nn.Module):
+    """Statistical body model of the SMPL family (forward linear blend skinning).
+
+    Parameters are those of the reference (pt/bodymodel.py:53-64).  Model data comes from
+    ``smplfitter_b200.modeldata.initialize`` (same signature as the reference seam
+    common.py:219): an installed provider for the licensed files, or the synthetic stand-in.
+    """
+
+    def __init__(
+        self,
+        model_name: str = 'smpl',
+        gender: str = 'neutral',
+        model_root: Optional[str] = None,
+        num_betas: Optional[int] = None,
+        vertex_subset_size: Optional[int] = None,
+        vertex_subset=None,
+        faces=None,
+        joint_regressor_post_lbs=None,
+        device=None,
+    ):
+        super().__init__()
+        self.gender = gender
+        self.model_name = model_name
+        data = modeldata.initialize(
+            model_name, gender, model_root, num_betas, vertex_subset_size, vertex_subset, faces,
+            joint_regressor_post_lbs,
+        )
+        f32 = lambda x: torch.tensor(np.asarray(x), dtype=torch.float32)  # noqa: E731
+        self.v_template = nn.Buffer(f32(data.v_template))
+        self.shapedirs = nn.Buffer(f32(data.shapedirs))
+        self.posedirs = nn.Buffer(f32(data.posedirs))
+        self.J_regressor_post_lbs = nn.Buffer(f32(data.J_regressor_post_lbs))
+        self.J_template = nn.Buffer(f32(data.J_template))
+        self.J_shapedirs = nn.Buffer(f32(data.J_shapedirs))
+        self.kid_shapedir = nn.Buffer(f32(data.kid_shapedir))
+        self.kid_J_shapedir = nn.Buffer(f32(data.kid_J_shapedir))
+        self.weights = nn.Buffer(f32(data.weights))
+        self.kintree_parents_tensor = nn.Buffer(torch.tensor(data.kintree_parents, dtype=torch.int64))
+        self.kintree_parents = data.kintree_parents
+        self.faces = data.faces
+        self.num_joints = data.num_joints
+        self.num_vertices = data.num_vertices
+        self.num_betas = self.shapedirs.shape[2]
+        self.vertex_subset = data.vertex_subset
+        self.joint_names = data.joint_names
+        if self.vertex_subset is None:
+            self.vertex_subset = np.arange(self.num_vertices)
+        for i in range(1, self.num_joints):
+            if not 0 <= int(self.kintree_parents[i]) < i:
+                raise ValueError('kinematic tree must list parents before children')
+
+        # ---- derived device tables (host precompute, see masks.py) ----
+        w32 = self.weights.numpy()
+        self._plan = masks.build_fit_plan(w32, self.kintree_parents, model_name)
+        plan = self._plan
+        V, J = self.num_vertices, self.num_joints
+        P = 9 * (J - 1)
+        order = np.argsort(plan.part_assignment, kind='stable').astype(np.int32)
+        inv_order = np.empty(V, np.int32)
+        inv_order[order] = np.arange(V, dtype=np.int32)
+        seg_start, seg_part, part_seg_begin = _segments(plan.part_assignment[order], J)
+        skin_idx, skin_w, K = masks.sparse_skin_table(w32)
+        Kp = (P + 15) // 16 * 16
+        posedirs_fit = np.zeros((V * 3, Kp), np.float32)
+        posedirs_fit[:, :P] = self.posedirs.numpy()[order].reshape(V * 3, P)
+        eye_feat = np.tile(np.eye(3, dtype=np.float32), [J - 1, 1]).reshape(-1)
+        v_posed0 = self.v_template.numpy() + np.einsum('vcp,p->vc', self.posedirs.numpy(), eye_feat)
+        template_mesh = (v_posed0 * w32.sum(axis=1, keepdims=True)).astype(np.float32)  # pt/bodyfitter.py:49
+        flags = (plan.part_is_stat.astype(np.int32) | (plan.part_is_adjustable.astype(np.int32) << 1))
+        jreg = self.J_regressor_post_lbs.numpy()
+        i32 = lambda x: torch.tensor(np.ascontiguousarray(x), dtype=torch.int32)  # noqa: E731
+        t = {
+            'parents': i32(plan.parents), 'skin_idx': i32(skin_idx), 'skin_w': f32(skin_w),
+            'order': i32(order), 'inv_order': i32(inv_order), 'seg_start': i32(seg_start),
+            'seg_part': i32(seg_part), 'part_seg_begin': i32(part_seg_begin),
+            'part_kind': i32(plan.part_kind), 'part_copy_src': i32(plan.part_copy_src),
+            'part_flags': i32(flags), 'cas_table': i32(plan.cas_table), 'cas_count': i32(plan.cas_count),
+            'posedirs_fit': f32(posedirs_fit), 'v_template_fit': f32(self.v_template.numpy()[order].reshape(-1)),
+            'template_mesh': f32(template_mesh),
+            'template_joints_regressed': f32(jreg @ template_mesh),
+            'J_regressor_fit': f32(jreg[:, order]),
+        }
+        for k, v in t.items():
+            self.register_buffer('_t_' + k, v, persistent=False)
+        self._dims = dict(
+            num_vertices=V, num_joints=J, num_betas=self.num_betas, num_pose_feats=P, skin_k=K,
+            is_smpl_family=int(plan.is_smpl_family), n_used=int(plan.part_is_stat[plan.part_assignment].sum()),
+            n_segments=len(seg_part), chunk_len=CHUNK_LEN, max_cas=plan.cas_table.shape[1],
+        )
+        if device is not None:
+            self.to(device)
+
+    # ------------------------------------------------------------------------------
+    def _struct(self, extra: Optional[dict] = None) -> _native.ModelStruct:
+        """Fill the C struct with the current device addresses of the buffers."""
+        _native.require_cuda(self.v_template, 'the body model')
+        s = _native.ModelStruct()
+        for k, v in self._dims.items():
+            setattr(s, k, v)
+        s.v_template = self.v_template.data_ptr()
+        s.shapedirs = self.shapedirs.data_ptr()
+        s.posedirs = self.posedirs.data_ptr()
+        s.kid_shapedir = self.kid_shapedir.data_ptr()
+        s.J_template = self.J_template.data_ptr()
+        s.J_shapedirs = self.J_shapedirs.data_ptr()
+        s.kid_J_shapedir = self.kid_J_shapedir.data_ptr()
+        s.J_regressor = self.J_regressor_post_lbs.data_ptr()
+        for name in ('parents', 'skin_idx', 'skin_w', 'order', 'inv_order', 'seg_start', 'seg_part',
+                     'part_seg_begin', 'part_kind', 'part_copy_src', 'part_flags', 'cas_table', 'cas_count',
+                     'posedirs_fit', 'v_template_fit', 'template_mesh', 'template_joints_regressed',
+                     'J_regressor_fit'):
+            setattr(s, name, getattr(self, '_t_' + name).data_ptr())
+        s.fit_ns = 0
+        if extra:
+            for k, v in extra.items():
+                setattr(s, k, v)
+        return s
+
+    # ------------------------------------------------------------------------------
+    def forward(
+        self,
+        pose_rotvecs: Optional[torch.Tensor] = None,
+        shape_betas: Optional[torch.Tensor] = None,
+        trans: Optional[torch.Tensor] = None,
+        kid_factor: Optional[torch.Tensor] = None,
+        rel_rotmats: Optional[torch.Tensor] = None,
+        glob_rotmats: Optional[torch.Tensor] = None,
+        return_vertices: bool = True,
+    ) -> dict[str, torch.Tensor]:
+        """Vertices, joints and global orientations for a batch (pt/bodymodel.py:121-307)."""
+        n_rot = sum(x is not None for x in (pose_rotvecs, rel_rotmats, glob_rotmats))
+        if n_rot > 1:
+            raise ValueError(
+                'Only one rotation input may be provided (pose_rotvecs, rel_rotmats, or glob_rotmats).'
+            )
+        for name, arg, min_ndim in [
+            ('pose_rotvecs', pose_rotvecs, 2), ('shape_betas', shape_betas, 2), ('trans', trans, 2),
+            ('kid_factor', kid_factor, 1), ('rel_rotmats', rel_rotmats, 4), ('glob_rotmats', glob_rotmats, 4),
+        ]:
+            if arg is not None:
+                if isinstance(arg, np.ndarray):
+                    raise TypeError(
+                        f"Expected torch.Tensor for '{name}', got numpy.ndarray. "
+                        f'Convert with torch.from_numpy() or torch.as_tensor().'
+                    )
+                if arg.ndim < min_ndim:
+                    raise ValueError(
+                        f"Expected batched input for '{name}' with at least {min_ndim} dimensions, but "
+                        f'got shape {tuple(arg.shape)}. For single (unbatched) inputs, use model.single() '
+                        f'instead.'
+                    )
+        batch_size = 0
+        for arg in (pose_rotvecs, shape_betas, trans, rel_rotmats, glob_rotmats):
+            if arg is not None:
+                batch_size = arg.shape[0]
+                break
+        device = self.v_template.device
+        J, V = self.num_joints, self.num_vertices
+        if batch_size == 0:
+            result = dict(
+                joints=torch.empty((0, J, 3), device=device),
+                orientations=torch.empty((0, J, 3, 3), device=device),
+            )
+            if return_vertices:
+                result['vertices'] = torch.empty((0, V, 3), device=device)
+            return result
+        _native.require_cuda(self.v_template, 'the body model')
+
+        def prep(x, shape=None):
+            x = x.to(device=device, dtype=torch.float32)
+            if shape is not None:
+                x = x.reshape(shape)
+            return x.contiguous()
+
+        if rel_rotmats is not None:
+            rot, mode = prep(rel_rotmats, (batch_size, J, 3, 3)), 1
+        elif pose_rotvecs is not None:
+            rot, mode = prep(pose_rotvecs, (batch_size, J * 3)), 0
+        elif glob_rotmats is not None:
+            rot, mode = prep(glob_rotmats, (batch_size, J, 3, 3)), 2
+        else:
+            rot, mode = None, 3
+        betas = prep(shape_betas) if shape_betas is not None else None
+        n_betas = 0 if betas is None else betas.shape[1]
+        if betas is not None and betas.shape[0] != batch_size:
+            betas = betas.expand(batch_size, n_betas).contiguous()
+        tr = prep(trans) if trans is not None else None
+        if tr is not None and tr.shape[0] != batch_size:
+            tr = tr.expand(batch_size, 3).contiguous()
+        kid = None
+        if kid_factor is not None:
+            kid = torch.as_tensor(kid_factor, dtype=torch.float32, device=device).reshape(-1)
+            kid = kid.expand(batch_size).contiguous()
+        joints = torch.empty((batch_size, J, 3), device=device, dtype=torch.float32)
+        orient = torch.empty((batch_size, J, 3, 3), device=device, dtype=torch.float32)
+        verts = torch.empty((batch_size, V, 3), device=device, dtype=torch.float32) if return_vertices else None
+        L = _native.lib()
+        s = self._struct()
+        ws_bytes = L.smplfit_forward_workspace_bytes(C.byref(s), batch_size)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+        with torch.cuda.device(device):
+            _native.check(L.smplfit_forward(
+                C.byref(s), batch_size, mode, _native.ptr(rot), _native.ptr(betas), n_betas, _native.ptr(tr),
+                _native.ptr(kid), _native.ptr(verts), _native.ptr(joints), _native.ptr(orient),
+                ws.data_ptr(), ws_bytes, _native.stream_ptr(device),
+            ))
+        ws.record_stream(torch.cuda.current_stream(device))
+        result = dict(joints=joints, orientations=orient)
+        if return_vertices:
+            result['vertices'] = verts
+        return result
+
+    def single(
+        self,
+        pose_rotvecs: Optional[torch.Tensor] = None,
+        shape_betas: Optional[torch.Tensor] = None,
+        trans: Optional[torch.Tensor] = None,
+        kid_factor: Optional[torch.Tensor] = None,
+        rel_rotmats: Optional[torch.Tensor] = None,
+        glob_rotmats: Optional[torch.Tensor] = None,
+        return_vertices: bool = True,
+    ) -> dict[str, torch.Tensor]:
+        """Unbatched variant (pt/bodymodel.py:309-380)."""
+        un = lambda x: x.unsqueeze(0) if x is not None else None  # noqa: E731
+        pose_rotvecs, shape_betas, trans = un(pose_rotvecs), un(shape_betas), un(trans)
+        rel_rotmats, glob_rotmats = un(rel_rotmats), un(glob_rotmats)
+        if all(x is None for x in (pose_rotvecs, shape_betas, trans, rel_rotmats, glob_rotmats)):
+            shape_betas = torch.zeros((1, 0), dtype=torch.float32, device=self.v_template.device)
+        result = self.forward(
+            pose_rotvecs=pose_rotvecs, shape_betas=shape_betas, trans=trans, kid_factor=kid_factor,
+            rel_rotmats=rel_rotmats, glob_rotmats=glob_rotmats, return_vertices=return_vertices,
+        )
+        return {k: v.squeeze(0) for k, v in result.items()}
+
+    def rototranslate(
+        self,
+        R: torch.Tensor,
+        t: Optional[torch.Tensor] = None,
+        pose_rotvecs: Optional[torch.Tensor] = None,
+        shape_betas: Optional[torch.Tensor] = None,
+        trans: Optional[torch.Tensor] = None,
+        kid_factor: Optional[torch.Tensor] = None,
+        post_translate: bool = True,
+    ) -> tuple[torch.Tensor, torch.Tensor]:
+        """Rotate/translate a body in parametric form (pt/bodymodel.py:382-453).
+
+        A handful of 3-vector operations on one instance: host-side tensor algebra, not part of
+        the batched hot path.
+        """
+        from .rotation import mat2rotvec, rotvec2mat
+
+        if t is None:
+            t = torch.zeros(3, device=R.device, dtype=R.dtype)
+        if pose_rotvecs is None or shape_betas is None or trans is None:
+            raise ValueError('pose_rotvecs, shape_betas, and trans are required.')
+        new_rotmat = R @ rotvec2mat(pose_rotvecs[:3])
+        new_pose_rotvec = torch.cat([mat2rotvec(new_rotmat), pose_rotvecs[3:]], dim=0)
+        pelvis = self.J_template[0] + self.J_shapedirs[0, :, : shape_betas.shape[0]] @ shape_betas
+        if kid_factor is not None:
+            pelvis = pelvis + self.kid_J_shapedir[0] * kid_factor
+        eye3 = torch.eye(3, device=R.device, dtype=R.dtype)
+        if post_translate:
+            new_trans = trans @ R.mT + t + pelvis @ (R.mT - eye3)
+        else:
+            new_trans = (trans - t) @ R.mT + pelvis @ (R.mT - eye3)
+        return new_pose_rotvec, new_trans

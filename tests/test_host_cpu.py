@@ -1,0 +1,105 @@
+"""CPU: host-side logic -- static masks bit-exact vs the reference fixtures, device tables
+self-consistent, C-ABI library loads and exports every declared symbol (no compute calls)."""
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from smplfitter_b200 import masks, modeldata
+from tests import golden_cases as gc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize('name', list(gc.MASK_CASES))
+def test_masks_bit_exact(name):
+    mname, mkw = gc.MASK_CASES[name]
+    g = gc.load(name)
+    data = modeldata.initialize(mname, **mkw)
+    plan = masks.build_fit_plan(np.asarray(data.weights, np.float32), data.kintree_parents, mname)
+    assert np.array_equal(plan.part_assignment, g['part_assignment'])
+    assert np.array_equal(plan.used_vertex_indices, g['used_vertex_indices'])
+    assert plan.multi_joint_parts == list(g['multi'])
+    assert plan.bone_parts == list(g['bone'])
+    assert plan.leaf_parts == list(g['leaf'])
+    assert plan.adjustable_parts == list(g['adjustable'])
+    for key in ('assemble_indices', 'bone_pairs', 'fk_js', 'fk_ps', 'adj_parts', 'adj_part_joints', 'cas_flat'):
+        assert np.array_equal(getattr(plan, key), g[key]), key
+    assert plan.fk_level_sizes == list(g['fk_level_sizes'])
+    assert plan.adj_level_sizes == list(g['adj_level_sizes'])
+    assert plan.cas_starts == list(g['cas_starts'])
+    assert np.array_equal(plan.part_counts, g['part_counts'])
+    assert np.array_equal(plan.center_matrix, g['center_matrix'])
+    assert np.array_equal(plan.mjp_joint_membership, g['mjp_joint_membership'])
+    assert np.array_equal(plan.part_matrix.sum(1), g['part_matrix_rowsum'])
+    assert np.array_equal(plan.part_matrix.argmax(0), g['part_matrix_argmax'])
+
+
+@pytest.mark.parametrize('mname', ['smpl_tiny', 'smplx_tiny', 'smpl'])
+def test_device_tables(mname):
+    from smplfitter_b200.pt import BodyFitter, BodyModel
+
+    bm = BodyModel(mname)
+    fitter = BodyFitter(bm)
+    V, J = bm.num_vertices, bm.num_joints
+    order = bm._t_order.numpy()
+    inv = bm._t_inv_order.numpy()
+    assert sorted(order.tolist()) == list(range(V))
+    assert np.array_equal(inv[order], np.arange(V))
+    part = fitter.part_assignment.numpy()
+    seg_start, seg_part = bm._t_seg_start.numpy(), bm._t_seg_part.numpy()
+    psb = bm._t_part_seg_begin.numpy()
+    assert seg_start[0] == 0 and seg_start[-1] == V
+    for s in range(len(seg_part)):
+        vs = order[seg_start[s]:seg_start[s + 1]]
+        assert 0 < len(vs) <= 64 and np.all(part[vs] == seg_part[s])
+    for p in range(J):
+        assert np.all(seg_part[psb[p]:psb[p + 1]] == p)
+        n = sum(seg_start[s + 1] - seg_start[s] for s in range(psb[p], psb[p + 1]))
+        assert n == int((part == p).sum())
+    idx, w = bm._t_skin_idx.numpy(), bm._t_skin_w.numpy()
+    dense = np.zeros((V, J), np.float32)
+    np.add.at(dense, (np.arange(V)[:, None], idx), w)
+    assert np.array_equal(dense, bm.weights.numpy())
+    pf = bm._t_posedirs_fit.numpy()
+    P = 9 * (J - 1)
+    assert np.array_equal(pf[:, :P].reshape(V, 3, P), bm.posedirs.numpy()[order]) and not pf[:, P:].any()
+
+
+def test_library_exports_declared_symbols():
+    from smplfitter_b200 import _native
+
+    lib = _native.lib()
+    header = open(os.path.join(ROOT, 'include', 'smplfit_b200.h')).read()
+    names = set(re.findall(r'\b(smplfit_[a-z_]+)\s*\(', header))
+    assert {'smplfit_fit', 'smplfit_forward', 'smplfit_convert_vertices', 'smplfit_fit_known_pose'} <= names
+    for n in names:
+        assert hasattr(lib, n), n
+    assert lib.smplfit_struct_size(0) == ctypes.sizeof(_native.ModelStruct)
+    assert lib.smplfit_struct_size(1) == ctypes.sizeof(_native.FitOpts)
+    assert b'sm_100a' in lib.smplfit_version()
+
+
+def test_no_cpu_fallback():
+    """The product path refuses to run without CUDA instead of silently falling back."""
+    import torch
+
+    from smplfitter_b200.pt import BodyFitter, BodyModel
+
+    bm = BodyModel('smpl_tiny')
+    with pytest.raises(RuntimeError, match='CUDA'):
+        bm(pose_rotvecs=torch.zeros(2, 72))
+    with pytest.raises(RuntimeError, match='CUDA'):
+        BodyFitter(bm).fit(torch.zeros(2, bm.num_vertices, 3))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, 'smplfitter_b200')
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith('.py'):
+                src = open(os.path.join(root, f)).read()
+                assert 'oracle' not in src.replace('no oracle', ''), os.path.join(root, f)
