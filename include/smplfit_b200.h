@@ -86,6 +86,8 @@ typedef struct smplfit_model {
   const float* fit_Jt_ext;     /* (J,3,1+NS): [J_template | J_shapedirs | kid_J_shapedir] (pt/bodyfitter.py:52-58) */
   const float* template_joints_regressed; /* (J,3) J_regressor @ template_mesh (no-joints first fit) */
   const float* J_regressor_fit; /* (J,V) J_regressor with columns in internal order */
+  const float* posedirs_hi;     /* (3V, Kt) tf32-exact high part of posedirs_fit, Kt = roundup(P,32) */
+  const float* posedirs_lo;     /* (3V, Kt) posedirs_fit - posedirs_hi */
   const void* reserved_ptr[4];
 } smplfit_model_t;
 
@@ -164,6 +166,12 @@ int64_t smplfit_launch_count(int reset);
  * "kernel\tlaunches\ttotal_ms\n" line per kernel into `out` (host buffer). */
 int smplfit_profile(int enable);
 int smplfit_profile_report(char* out, size_t cap);
+
+/* Test hook: v_posed^T [3V][Bp] = v_template + posedirs . feat for feat [Bp][roundup(P,16)] (Bp % 32 == 0);
+ * use_tc = 1 forces the tcgen05 kernel (error if unavailable), 0 the FP32 SIMT kernel. */
+size_t smplfit_debug_vposed_scratch_bytes(const smplfit_model_t* m, int Bp);
+int smplfit_debug_vposed(const smplfit_model_t* m, const float* feat, int Bp, int use_tc, float* out,
+                         void* scratch, void* stream);
 
 #ifdef __cplusplus
 }

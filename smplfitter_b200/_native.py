@@ -31,7 +31,8 @@ class ModelStruct(C.Structure):
         'cas_table', 'cas_count', 'inv_order', 'posedirs_fit', 'v_template_fit',
     ]
     _ptr_fields_b = [
-        'fit_shapedirs', 'fit_Jt_ext', 'template_joints_regressed', 'J_regressor_fit',
+        'fit_shapedirs', 'fit_Jt_ext', 'template_joints_regressed', 'J_regressor_fit', 'posedirs_hi',
+        'posedirs_lo',
     ]
     _fields_ = (
         [(n, C.c_int32) for n in _int_fields]
@@ -100,6 +101,10 @@ def lib():
     L.smplfit_profile.argtypes = [C.c_int]
     L.smplfit_profile_report.restype = C.c_int
     L.smplfit_profile_report.argtypes = [C.c_char_p, C.c_size_t]
+    L.smplfit_debug_vposed_scratch_bytes.restype = C.c_size_t
+    L.smplfit_debug_vposed_scratch_bytes.argtypes = [C.POINTER(ModelStruct), C.c_int]
+    L.smplfit_debug_vposed.restype = C.c_int
+    L.smplfit_debug_vposed.argtypes = [C.POINTER(ModelStruct), _F, C.c_int, C.c_int, _F, _F, _F]
     L.smplfit_convert_vertices.restype = C.c_int
     L.smplfit_convert_vertices.argtypes = [_F, _F, _F, C.c_int32, C.c_int32, C.c_int64, _F, _F, _F]
     if L.smplfit_struct_size(0) != C.sizeof(ModelStruct) or L.smplfit_struct_size(1) != C.sizeof(FitOpts):

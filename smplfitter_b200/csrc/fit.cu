@@ -43,7 +43,7 @@ static FitWs carve(void* base, const smplfit_model_t* m, int64_t B, int has_join
   w.RT = c.take<float>((size_t)J * (12 + 3 * NS) * Bp);
   w.Pext = c.take<float>((size_t)J * 3 * (1 + NS) * Bp);
   w.feat = c.take<float>((size_t)Bp * Kp);
-  w.gpart = c.take<float>((size_t)n_chunks * shape_nacc(NS) * Bp);
+  w.gpart = c.take<float>((size_t)((n_chunks + 7) / 8) * shape_nacc(NS) * Bp);
   w.beta = c.take<float>((size_t)NS * Bp);
   w.trans = c.take<float>(3 * Bp);
   w.refj = c.take<float>((size_t)3 * J * Bp);
@@ -85,18 +85,18 @@ static int check_model(const smplfit_model_t* m) {
 template <int NS, bool WEIGHTED>
 static void launch_shape_pass_w(const ShapeArgs& sa, int groups, cudaStream_t st) {
   constexpr int RW = 12 + 3 * NS;
-  const size_t smem = (size_t)sa.J * RW * 32 * sizeof(float);
-  const int cta_chunks = 8;
+  const size_t smem_rt = (size_t)sa.J * RW * 32 * sizeof(float);
+  const size_t smem_red = (size_t)4 * ShapeAcc<NS>::N * 32 * sizeof(float);
   ShapeArgs a = sa;
-  a.chunks_per_cta = cta_chunks;
-  dim3 grid((sa.n_chunks + cta_chunks - 1) / cta_chunks, groups);
-  if (smem <= 200 * 1024) {
-    auto k = k_shape_pass<NS, WEIGHTED, true>;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    SF_LAUNCH(k, grid, 256, smem, st, a);
+  a.chunks_per_cta = 8;
+  dim3 grid((sa.n_chunks + 7) / 8, groups);
+  if (smem_rt <= 200 * 1024) {
+    const size_t smem = smem_rt > smem_red ? smem_rt : smem_red;
+    cudaFuncSetAttribute(k_shape_pass<NS, WEIGHTED, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    SF_LAUNCH((k_shape_pass<NS, WEIGHTED, true>), grid, 256, smem, st, a);
   } else {
-    auto k = k_shape_pass<NS, WEIGHTED, false>;
-    SF_LAUNCH(k, grid, 256, 0, st, a);
+    cudaFuncSetAttribute(k_shape_pass<NS, WEIGHTED, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_red);
+    SF_LAUNCH((k_shape_pass<NS, WEIGHTED, false>), grid, 256, smem_red, st, a);
   }
 }
 
@@ -165,7 +165,7 @@ static void run_shape(FitCtx& c, const float* R_unused, const float* beta_ref, c
   so.tjT = c.has_joints ? c.w.tjT : nullptr; so.jwT = c.jwT_shape;
   so.beta_ref = beta_ref; so.kid_ref = kid_ref;
   so.beta = c.w.beta; so.trans = c.w.trans; so.refj = c.w.refj; so.skin = c.w.skin;
-  so.n_chunks = c.n_chunks; so.J = m->num_joints; so.S = m->num_betas; so.Bp = c.Bp; so.B = c.B;
+  so.n_chunks = (c.n_chunks + 7) / 8; so.J = m->num_joints; so.S = m->num_betas; so.Bp = c.Bp; so.B = c.B;
   so.V = m->num_vertices; so.weighted = c.vwT_shape != nullptr;
   so.reg = o->beta_regularizer; so.reg2 = o->beta_regularizer2; so.kid_reg = o->kid_regularizer;
   SF_NS_DISPATCH(m->fit_ns, (launch_shape_solve<NS>(so, c.Bp, c.st)));
@@ -414,6 +414,27 @@ extern "C" int smplfit_fit_known_pose(const smplfit_model_t* m, int64_t batch, c
   oa.kid = o->enable_kid ? out_kid_factor : nullptr;
   oa.J = J; oa.S = m->num_betas; oa.NS = m->fit_ns; oa.B = c.B; oa.Bp = c.Bp;
   SF_LAUNCH(k_output, c.Bp / 32, 32, 0, c.st, oa);
+  SF_CHECK_LAST();
+  return SMPLFIT_OK;
+}
+
+// Test hook: the pose-blend-shape contraction alone (tests/test_gpu_gemm.py compares the tcgen05
+// path with the FP32 SIMT kernel and a float64 host product).  feat is [Bp][Kp] row-major.
+extern "C" size_t smplfit_debug_vposed_scratch_bytes(const smplfit_model_t* m, int Bp) {
+  return vposed_tc_scratch_bytes(m, Bp) + 256;
+}
+extern "C" int smplfit_debug_vposed(const smplfit_model_t* m, const float* feat, int Bp, int use_tc, float* out,
+                                    void* scratch, void* stream) {
+  if (!m || !feat || !out || Bp <= 0 || Bp % 32) return fail(SMPLFIT_ERR_ARG, "bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int Kp = roundup(m->num_pose_feats, 16);
+  if (use_tc) {
+    if (!vposed_tc_run(m, feat, out, Bp, Kp, scratch, st)) return fail(SMPLFIT_ERR_UNSUPPORTED, "tcgen05 path unavailable");
+  } else {
+    dim3 grid((3 * m->num_vertices + 127) / 128, (Bp + 63) / 64);
+    SF_LAUNCH(k_vposed_gemm_simt, grid, 256, 0, st, m->posedirs_fit, m->v_template_fit, feat, 3 * m->num_vertices,
+              Kp, Bp, out);
+  }
   SF_CHECK_LAST();
   return SMPLFIT_OK;
 }

@@ -358,107 +358,122 @@ struct ShapeArgs {
 
 template <int NS, bool WEIGHTED, bool SMEM_RT>
 __global__ void __launch_bounds__(256) k_shape_pass(const ShapeArgs a) {
-  extern __shared__ float s_rt[];  // [J*RW][32]
+  extern __shared__ __align__(16) float s_rt[];  // [J*RW][32] staged rows, later reused for the CTA reduction
   constexpr int RW = 12 + 3 * NS;
   constexpr int TW = 3 * (1 + NS);
+  constexpr int NACC = ShapeAcc<NS>::N;
   const int g = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Bp = a.Bp;
   const int b = g * 32 + lane;
   if (SMEM_RT) {
-    const int rows = a.J * RW;
-    for (int r = warp; r < rows; r += 8) s_rt[r * 32 + lane] = SF_IM(a.RT, r, Bp, b);
+    // stage the 32-instance slice of every [R | T_ext] row with 16-byte cp.async (row = 128 B)
+    const int n16 = a.J * RW * 8;
+    for (int q = threadIdx.x; q < n16; q += 256) {
+      const int r = q >> 3, part = q & 7;
+      const float* src = a.RT + (size_t)r * Bp + g * 32 + part * 4;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_rt + r * 32 + part * 4);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
   }
-  const int chunk = blockIdx.x * a.chunks_per_cta + warp;
-  if (warp >= a.chunks_per_cta || chunk >= a.n_chunks) return;
-  float G[ShapeAcc<NS>::NG], r[NS], SA[3][NS], Sb[3], W = 0.f;
+  const int chunk = blockIdx.x * 8 + warp;
+  const bool active = chunk < a.n_chunks;
+  float acc[NACC];  // G (upper triangle), r, SA, Sb, W
 #pragma unroll
-  for (int e = 0; e < ShapeAcc<NS>::NG; ++e) G[e] = 0.f;
+  for (int e = 0; e < NACC; ++e) acc[e] = 0.f;
+  constexpr int OG = 0, OR = ShapeAcc<NS>::NG, OSA = OR + NS, OSB = OSA + 3 * NS, OW = OSB + 3;
+  if (active) {
+    const int i0 = chunk * a.chunk_len, i1 = min(a.V, i0 + a.chunk_len);
+    for (int i = i0; i < i1; ++i) {
+      const int v = __ldg(a.order + i);
+      float Rb[9], Tb[TW];
 #pragma unroll
-  for (int s = 0; s < NS; ++s) {
-    r[s] = 0.f;
-    SA[0][s] = SA[1][s] = SA[2][s] = 0.f;
-  }
-  Sb[0] = Sb[1] = Sb[2] = 0.f;
-  const int i0 = chunk * a.chunk_len, i1 = min(a.V, i0 + a.chunk_len);
-  for (int i = i0; i < i1; ++i) {
-    const int v = __ldg(a.order + i);
-    float Rb[9], Tb[TW];
+      for (int e = 0; e < 9; ++e) Rb[e] = 0.f;
 #pragma unroll
-    for (int e = 0; e < 9; ++e) Rb[e] = 0.f;
+      for (int e = 0; e < TW; ++e) Tb[e] = 0.f;
+      for (int k = 0; k < a.skin_k; ++k) {
+        const int j = __ldg(a.skin_idx + v * a.skin_k + k);
+        const float w = __ldg(a.skin_w + v * a.skin_k + k);
+        if (SMEM_RT) {
+          const float* p = s_rt + (size_t)(j * RW) * 32 + lane;
 #pragma unroll
-    for (int e = 0; e < TW; ++e) Tb[e] = 0.f;
-    for (int k = 0; k < a.skin_k; ++k) {
-      const int j = __ldg(a.skin_idx + v * a.skin_k + k);
-      const float w = __ldg(a.skin_w + v * a.skin_k + k);
-      if (SMEM_RT) {
-        const float* p = s_rt + (size_t)(j * RW) * 32 + lane;
+          for (int e = 0; e < 9; ++e) Rb[e] = fmaf(w, p[e * 32], Rb[e]);
 #pragma unroll
-        for (int e = 0; e < 9; ++e) Rb[e] = fmaf(w, p[e * 32], Rb[e]);
+          for (int e = 0; e < TW; ++e) Tb[e] = fmaf(w, p[(9 + e) * 32], Tb[e]);
+        } else {
+          const float* p = a.RT + (size_t)(j * RW) * Bp + b;
 #pragma unroll
-        for (int e = 0; e < TW; ++e) Tb[e] = fmaf(w, p[(9 + e) * 32], Tb[e]);
-      } else {
-        const float* p = a.RT + (size_t)(j * RW) * Bp + b;
+          for (int e = 0; e < 9; ++e) Rb[e] = fmaf(w, p[(size_t)e * Bp], Rb[e]);
 #pragma unroll
-        for (int e = 0; e < 9; ++e) Rb[e] = fmaf(w, p[(size_t)e * Bp], Rb[e]);
-#pragma unroll
-        for (int e = 0; e < TW; ++e) Tb[e] = fmaf(w, p[(size_t)(9 + e) * Bp], Tb[e]);
+          for (int e = 0; e < TW; ++e) Tb[e] = fmaf(w, p[(size_t)(9 + e) * Bp], Tb[e]);
+        }
       }
-    }
-    float vp[3], bv[3];
+      float vp[3], bv[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) vp[c] = SF_IM(a.vposedT, i * 3 + c, Bp, b);
+      for (int c = 0; c < 3; ++c) vp[c] = SF_IM(a.vposedT, i * 3 + c, Bp, b);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float pos = fmaf(Rb[c * 3], vp[0], fmaf(Rb[c * 3 + 1], vp[1], fmaf(Rb[c * 3 + 2], vp[2], Tb[c * (1 + NS)])));
-      bv[c] = SF_IM(a.tT, i * 3 + c, Bp, b) - pos;
-    }
-    // jac[c][s] overwrites Tb[c][1+s]
-    const float* sd = a.shapedirs + (size_t)v * 3 * NS;
-#pragma unroll
-    for (int s = 0; s < NS; ++s) {
-      const float s0 = __ldg(sd + s), s1 = __ldg(sd + NS + s), s2 = __ldg(sd + 2 * NS + s);
-#pragma unroll
-      for (int c = 0; c < 3; ++c)
-        Tb[c * (1 + NS) + 1 + s] =
-            fmaf(Rb[c * 3], s0, fmaf(Rb[c * 3 + 1], s1, fmaf(Rb[c * 3 + 2], s2, Tb[c * (1 + NS) + 1 + s])));
-    }
-    const float w = WEIGHTED ? SF_IM(a.vwT, i, Bp, b) : 1.f;
-    if (WEIGHTED) W += w;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float wb = WEIGHTED ? w * bv[c] : bv[c];
-      Sb[c] += wb;
-      int e = 0;
+      for (int c = 0; c < 3; ++c) {
+        const float pos = fmaf(Rb[c * 3], vp[0], fmaf(Rb[c * 3 + 1], vp[1], fmaf(Rb[c * 3 + 2], vp[2], Tb[c * (1 + NS)])));
+        bv[c] = SF_IM(a.tT, i * 3 + c, Bp, b) - pos;
+      }
+      // jac[c][s] overwrites Tb[c][1+s]
+      const float* sd = a.shapedirs + (size_t)v * 3 * NS;
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
-        const float js = Tb[c * (1 + NS) + 1 + s];
-        const float wj = WEIGHTED ? w * js : js;
-        SA[c][s] += wj;
-        r[s] = fmaf(wj, bv[c], r[s]);
+        const float s0 = __ldg(sd + s), s1 = __ldg(sd + NS + s), s2 = __ldg(sd + 2 * NS + s);
 #pragma unroll
-        for (int t = s; t < NS; ++t) {
-          G[e] = fmaf(wj, Tb[c * (1 + NS) + 1 + t], G[e]);
-          ++e;
+        for (int c = 0; c < 3; ++c)
+          Tb[c * (1 + NS) + 1 + s] =
+              fmaf(Rb[c * 3], s0, fmaf(Rb[c * 3 + 1], s1, fmaf(Rb[c * 3 + 2], s2, Tb[c * (1 + NS) + 1 + s])));
+      }
+      const float w = WEIGHTED ? SF_IM(a.vwT, i, Bp, b) : 1.f;
+      if (WEIGHTED) acc[OW] += w;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float wb = WEIGHTED ? w * bv[c] : bv[c];
+        acc[OSB + c] += wb;
+        int e = OG;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          const float js = Tb[c * (1 + NS) + 1 + s];
+          const float wj = WEIGHTED ? w * js : js;
+          acc[OSA + c * NS + s] += wj;
+          acc[OR + s] = fmaf(wj, bv[c], acc[OR + s]);
+#pragma unroll
+          for (int t = s; t < NS; ++t) {
+            acc[e] = fmaf(wj, Tb[c * (1 + NS) + 1 + t], acc[e]);
+            ++e;
+          }
         }
       }
     }
+    if (!WEIGHTED) acc[OW] = (float)(i1 - i0);
   }
-  if (!WEIGHTED) W = (float)(i1 - i0);
-  float* out = a.partials + (size_t)chunk * ShapeAcc<NS>::N * Bp + b;
-  int o = 0;
+  // ---- deterministic tree reduction over the CTA's 8 warps through shared memory ----
+  float* red = s_rt;  // [4][NACC][32]
+#pragma unroll 1
+  for (int half = 4; half >= 1; half >>= 1) {
+    __syncthreads();  // staged rows (or the previous round) are dead
+    if (warp >= half && warp < 2 * half) {
+      float* dst = red + (size_t)(warp - half) * NACC * 32 + lane;
 #pragma unroll
-  for (int e = 0; e < ShapeAcc<NS>::NG; ++e) out[(size_t)(o++) * Bp] = G[e];
+      for (int e = 0; e < NACC; ++e) dst[e * 32] = acc[e];
+    }
+    __syncthreads();
+    if (warp < half) {
+      const float* src = red + (size_t)warp * NACC * 32 + lane;
 #pragma unroll
-  for (int s = 0; s < NS; ++s) out[(size_t)(o++) * Bp] = r[s];
+      for (int e = 0; e < NACC; ++e) acc[e] += src[e * 32];
+    }
+  }
+  if (warp == 0) {
+    float* out = a.partials + (size_t)blockIdx.x * NACC * Bp + b;
 #pragma unroll
-  for (int c = 0; c < 3; ++c)
-#pragma unroll
-    for (int s = 0; s < NS; ++s) out[(size_t)(o++) * Bp] = SA[c][s];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) out[(size_t)(o++) * Bp] = Sb[c];
-  out[(size_t)o * Bp] = W;
+    for (int e = 0; e < NACC; ++e) out[(size_t)e * Bp] = acc[e];
+  }
 }
 
 }  // namespace sf

@@ -1,6 +1,296 @@
+// Tensor-core path of the pose-blend-shape contraction
+//     v_posed^T[n][b] = v_template_fit[n] + sum_k posedirs_fit[n][k] feat[b][k]
+// (pt/bodymodel.py:293, pt/bodyfitter.py:913-916) -- the one genuinely dense GEMM of the path:
+// (3V x P) x (P x B), P = 9 (J-1).
+//
+// sm_100a design: D[128 instances][128 vertex-coords] accumulates in TMEM (tcgen05.mma,
+// cta_group::1, kind::tf32, M = 128, N = 128, K = 8 per instruction).  Both operands are
+// K-major fp32 tiles of 128 rows x 32 floats (= one 128-byte swizzle atom row) brought in by TMA
+// (cp.async.bulk.tensor.2d, SWIZZLE_128B) through a 3-stage mbarrier ring.  Instances are the
+// M side so that in the epilogue TMEM lane == instance: each warp stores 32 consecutive
+// instances of one v_posed^T row = one coalesced 128-byte line per column.
+//
+// Precision: TF32 keeps 10 mantissa bits, not enough for the 1e-4 parity gate, so every
+// operand is split x = hi + lo (hi = x with the low 13 mantissa bits cleared, lo = x - hi) and
+// the product is accumulated as hi*hi + hi*lo + lo*hi in the fp32 accumulator (error ~2^-21
+// relative, i.e. fp32-GEMM grade).  posedirs hi/lo are model constants; the per-call feature
+// split is a tiny elementwise kernel.
+//
+// Warp roles (128 threads): warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane),
+// warp 2 = TMEM allocator; all four warps run the epilogue (warp w owns TMEM lanes 32w..32w+31).
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
 #include "vposed_tc.cuh"
 
 namespace sf {
-size_t vposed_tc_scratch_bytes(const smplfit_model_t*, int) { return 0; }
-bool vposed_tc_run(const smplfit_model_t*, const float*, float*, int, int, void*, cudaStream_t) { return false; }
+
+namespace {
+
+constexpr int TILE_M = 128;   // instances per CTA tile (TMEM lanes)
+constexpr int TILE_N = 128;   // v_posed^T rows (vertex coordinates) per CTA tile
+constexpr int TILE_K = 32;    // floats per k-block = 128 bytes = swizzle atom width
+constexpr int STAGES = 3;
+constexpr int TILE_BYTES = TILE_M * TILE_K * 4;  // 16 KB per operand tile
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;      // F_hi, F_lo, P_hi, P_lo
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t TMEM_COLS = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start
+// address >> 4 in bits [0,14), LBO (unused for swizzled K-major) = 1 in [16,30), SBO = 1024 B
+// (8 rows x 128 B) >> 4 in [32,46), version 1 in [46,48), layout SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// tcgen05 instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both
+// K-major, N >> 3 in [17,23), M >> 4 in [24,29).
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct TcMaps {
+  CUtensorMap f_hi, f_lo, p_hi, p_lo;
+};
+
+__global__ void __launch_bounds__(128, 1)
+k_vposed_tc(const __grid_constant__ TcMaps maps, const float* __restrict__ vt, float* __restrict__ out, int M_rows,
+            int Bp, int k_blocks) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* accum_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * TILE_N;  // v_posed^T rows
+  const int b0 = blockIdx.y * TILE_M;  // instances
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.f_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.f_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.p_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.p_lo) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accum_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ---- TMA producer ----
+    for (int kb = 0; kb < k_blocks; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      mbar_wait(&empty[s], ph ^ 1);
+      uint8_t* st = smem + s * STAGE_BYTES;
+      mbar_expect_tx(&full[s], STAGE_BYTES);
+      tma_load_2d(st + 0 * TILE_BYTES, &maps.f_hi, &full[s], kb * TILE_K, b0);
+      tma_load_2d(st + 1 * TILE_BYTES, &maps.f_lo, &full[s], kb * TILE_K, b0);
+      tma_load_2d(st + 2 * TILE_BYTES, &maps.p_hi, &full[s], kb * TILE_K, n0);
+      tma_load_2d(st + 3 * TILE_BYTES, &maps.p_lo, &full[s], kb * TILE_K, n0);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---- MMA issuer ----
+    uint32_t acc = 0;
+    for (int kb = 0; kb < k_blocks; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      mbar_wait(&full[s], ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+      const uint64_t fhi = make_desc(base), flo = make_desc(base + TILE_BYTES);
+      const uint64_t phi = make_desc(base + 2 * TILE_BYTES), plo = make_desc(base + 3 * TILE_BYTES);
+#pragma unroll
+      for (int k = 0; k < TILE_K / 8; ++k) {
+        const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 32 bytes per K = 8 step inside the swizzle atom
+        mma_tf32(tmem_base, flo + adv, phi + adv, acc);  // small terms first
+        acc = 1;
+        mma_tf32(tmem_base, fhi + adv, plo + adv, 1);
+        mma_tf32(tmem_base, fhi + adv, phi + adv, 1);
+      }
+      mma_commit(&empty[s]);  // frees the smem stage when these MMAs retire
+    }
+    mma_commit(accum_full);
+  }
+  __syncwarp();
+
+  // ---- epilogue: TMEM -> registers -> + v_template -> coalesced global stores ----
+  mbar_wait(accum_full, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const int b = b0 + warp * 32 + lane;
+#pragma unroll 1
+  for (int c0 = 0; c0 < TILE_N; c0 += 32) {
+    uint32_t r[32];
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int n = n0 + c0 + j;
+      if (n < M_rows && b < Bp) out[(size_t)n * Bp + b] = __uint_as_float(r[j]) + __ldg(vt + n);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// feat [Bp][Kp] -> hi / lo [Bp][Kt] (Kt = k_blocks * 32, zero padded)
+__global__ void k_split_feat(const float* __restrict__ feat, int Bp, int Kp, int Kt, float* __restrict__ hi,
+                             float* __restrict__ lo) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)Bp * Kt) return;
+  const int b = (int)(idx / Kt), k = (int)(idx % Kt);
+  const float x = (k < Kp && b < Bp) ? feat[(size_t)b * Kp + k] : 0.f;
+  const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  hi[idx] = h;
+  lo[idx] = x - h;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+bool make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)TILE_K, (cuuint32_t)TILE_M};
+  cuuint32_t elem[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, elem,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int g_tc_mode = -1;  // -1: read SMPLFIT_B200_GEMM env on first use; 0 = SIMT, 1 = tcgen05
+
+}  // namespace
+
+size_t vposed_tc_scratch_bytes(const smplfit_model_t* m, int Bp) {
+  const int Kt = roundup(m->num_pose_feats, TILE_K);
+  const int Bt = roundup(Bp, TILE_M);
+  return (size_t)2 * Bt * Kt * sizeof(float) + 512;
+}
+
+bool vposed_tc_run(const smplfit_model_t* m, const float* feat, float* vposedT, int Bp, int Kp, void* scratch,
+                   cudaStream_t st) {
+  if (g_tc_mode < 0) {
+    const char* e = getenv("SMPLFIT_B200_GEMM");
+    g_tc_mode = (e && strcmp(e, "simt") == 0) ? 0 : 1;
+  }
+  if (g_tc_mode == 0 || m->posedirs_hi == nullptr || m->posedirs_lo == nullptr || scratch == nullptr) return false;
+  const int Kt = roundup(m->num_pose_feats, TILE_K);
+  const int Bt = roundup(Bp, TILE_M);
+  const int rows = 3 * m->num_vertices;
+  float* hi = reinterpret_cast<float*>(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
+  float* lo = hi + (size_t)Bt * Kt;
+  TcMaps maps;
+  if (!make_map(&maps.f_hi, hi, Bt, Kt) || !make_map(&maps.f_lo, lo, Bt, Kt) ||
+      !make_map(&maps.p_hi, m->posedirs_hi, rows, Kt) || !make_map(&maps.p_lo, m->posedirs_lo, rows, Kt))
+    return false;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(k_vposed_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    attr_set = true;
+  }
+  const size_t n = (size_t)Bt * Kt;
+  // rows [Bp, Bt) of the split features are never written by k_split_feat's bound: clear via the kernel itself
+  SF_LAUNCH(k_split_feat, (unsigned)((n + 255) / 256), 256, 0, st, feat, Bp, Kp, Kt, hi, lo);
+  dim3 grid((rows + TILE_N - 1) / TILE_N, Bt / TILE_M);
+  SF_LAUNCH(k_vposed_tc, grid, 128, SMEM_BYTES, st, maps, m->v_template_fit, vposedT, rows, Bp, Kt / TILE_K);
+  return true;
+}
+
 }  // namespace sf

@@ -34,7 +34,7 @@ class BodyFitter(nn.Module):
         plan = body_model._plan
         self.is_smpl_family = plan.is_smpl_family
         # reference-named static tables (pt/bodyfitter.py:36-233)
-        i64 = lambda x: torch.tensor(np.asarray(x), dtype=torch.int64)  # noqa: E731
+        i64 = lambda x: torch.tensor(np.ascontiguousarray(np.asarray(x), dtype=np.int64))  # noqa: E731
         self.part_assignment = nn.Buffer(i64(plan.part_assignment))
         self.part_vertex_selectors = [i64(s) for s in plan.part_vertex_selectors]
         self.children_and_self = plan.children_and_self

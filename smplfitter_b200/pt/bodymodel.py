@@ -67,7 +67,7 @@ class BodyModel(nn.Module):
             model_name, gender, model_root, num_betas, vertex_subset_size, vertex_subset, faces,
             joint_regressor_post_lbs,
         )
-        f32 = lambda x: torch.tensor(np.asarray(x), dtype=torch.float32)  # noqa: E731
+        f32 = lambda x: torch.tensor(np.ascontiguousarray(np.asarray(x), dtype=np.float32))  # noqa: E731
         self.v_template = nn.Buffer(f32(data.v_template))
         self.shapedirs = nn.Buffer(f32(data.shapedirs))
         self.posedirs = nn.Buffer(f32(data.posedirs))
@@ -105,6 +105,11 @@ class BodyModel(nn.Module):
         Kp = (P + 15) // 16 * 16
         posedirs_fit = np.zeros((V * 3, Kp), np.float32)
         posedirs_fit[:, :P] = self.posedirs.numpy()[order].reshape(V * 3, P)
+        Kt = (P + 31) // 32 * 32
+        pd = np.zeros((V * 3, Kt), np.float32)
+        pd[:, :P] = posedirs_fit[:, :P]
+        pd_hi = (pd.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)  # tf32-exact part
+        pd_lo = pd - pd_hi
         eye_feat = np.tile(np.eye(3, dtype=np.float32), [J - 1, 1]).reshape(-1)
         v_posed0 = self.v_template.numpy() + np.einsum('vcp,p->vc', self.posedirs.numpy(), eye_feat)
         template_mesh = (v_posed0 * w32.sum(axis=1, keepdims=True)).astype(np.float32)  # pt/bodyfitter.py:49
@@ -121,6 +126,7 @@ class BodyModel(nn.Module):
             'template_mesh': f32(template_mesh),
             'template_joints_regressed': f32(jreg @ template_mesh),
             'J_regressor_fit': f32(jreg[:, order]),
+            'posedirs_hi': f32(pd_hi), 'posedirs_lo': f32(pd_lo),
         }
         for k, v in t.items():
             self.register_buffer('_t_' + k, v, persistent=False)
@@ -150,8 +156,11 @@ class BodyModel(nn.Module):
         for name in ('parents', 'skin_idx', 'skin_w', 'order', 'inv_order', 'seg_start', 'seg_part',
                      'part_seg_begin', 'part_kind', 'part_copy_src', 'part_flags', 'cas_table', 'cas_count',
                      'posedirs_fit', 'v_template_fit', 'template_mesh', 'template_joints_regressed',
-                     'J_regressor_fit'):
+                     'J_regressor_fit', 'posedirs_hi', 'posedirs_lo'):
             setattr(s, name, getattr(self, '_t_' + name).data_ptr())
+        for name, buf in self.named_buffers():
+            if not buf.is_contiguous():
+                raise RuntimeError(f'smplfitter_b200: buffer {name} must be contiguous')
         s.fit_ns = 0
         if extra:
             for k, v in extra.items():
