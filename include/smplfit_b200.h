@@ -88,6 +88,13 @@ typedef struct smplfit_model {
   const float* J_regressor_fit; /* (J,V) J_regressor with columns in internal order */
   const float* posedirs_hi;     /* (3V, Kt) tf32-exact high part of posedirs_fit, Kt = roundup(P,32) */
   const float* posedirs_lo;     /* (3V, Kt) posedirs_fit - posedirs_hi */
+  const float* template_mesh_fit; /* (V,3) template_mesh in internal order */
+  const float* fit_rec;         /* (V, rec_len) packed per-vertex records, internal order: 4 skin weights (descending),
+                                   4 joint ids (int bits), shapedirs[3][NS]; NULL when skin_k > 4 */
+  const double* fit_wS;         /* (J,3,NS) sum_v w_vk S_v  (closed-form SA of the unweighted shape solve) */
+  const double* fit_wsum;       /* (J)      sum_v w_vk */
+  int32_t fit_rec_len;          /* floats per record = roundup(8 + 3 NS, 4) */
+  int32_t fit_reserved2;
   const void* reserved_ptr[4];
 } smplfit_model_t;
 

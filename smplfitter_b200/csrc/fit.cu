@@ -5,6 +5,7 @@
 
 #include "common.cuh"
 #include "fit_kernels.cuh"
+#include "passes.cuh"
 #include "solve_kernels.cuh"
 #include "vposed_tc.cuh"
 
@@ -82,63 +83,13 @@ static int check_model(const smplfit_model_t* m) {
   return SMPLFIT_OK;
 }
 
-template <int NS, bool WEIGHTED>
-static void launch_shape_pass_w(const ShapeArgs& sa, int groups, cudaStream_t st) {
-  constexpr int RW = 12 + 3 * NS;
-  const size_t smem_rt = (size_t)sa.J * RW * 32 * sizeof(float);
-  const size_t smem_red = (size_t)4 * ShapeAcc<NS>::N * 32 * sizeof(float);
-  ShapeArgs a = sa;
-  a.chunks_per_cta = 8;
-  dim3 grid((sa.n_chunks + 7) / 8, groups);
-  if (smem_rt <= 200 * 1024) {
-    const size_t smem = smem_rt > smem_red ? smem_rt : smem_red;
-    cudaFuncSetAttribute(k_shape_pass<NS, WEIGHTED, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    SF_LAUNCH((k_shape_pass<NS, WEIGHTED, true>), grid, 256, smem, st, a);
-  } else {
-    cudaFuncSetAttribute(k_shape_pass<NS, WEIGHTED, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_red);
-    SF_LAUNCH((k_shape_pass<NS, WEIGHTED, false>), grid, 256, smem_red, st, a);
-  }
-}
-
-template <int NS>
-static void launch_shape_pass(const ShapeArgs& sa, int groups, cudaStream_t st) {
-  if (sa.vwT) launch_shape_pass_w<NS, true>(sa, groups, st);
-  else launch_shape_pass_w<NS, false>(sa, groups, st);
-}
-
-template <int NS>
-static void launch_shape_solve(const SolveArgs& so, int Bp, cudaStream_t st) {
-  SF_LAUNCH(k_shape_solve<NS>, Bp / 32, 32, 0, st, so);
-}
-
-#define SF_NS_DISPATCH(NSV, CALL)                 \
-  switch (NSV) {                                  \
-    case 2: { constexpr int NS = 2; CALL; } break;   \
-    case 3: { constexpr int NS = 3; CALL; } break;   \
-    case 4: { constexpr int NS = 4; CALL; } break;   \
-    case 5: { constexpr int NS = 5; CALL; } break;   \
-    case 6: { constexpr int NS = 6; CALL; } break;   \
-    case 7: { constexpr int NS = 7; CALL; } break;   \
-    case 8: { constexpr int NS = 8; CALL; } break;   \
-    case 9: { constexpr int NS = 9; CALL; } break;   \
-    case 10: { constexpr int NS = 10; CALL; } break; \
-    case 11: { constexpr int NS = 11; CALL; } break; \
-    case 12: { constexpr int NS = 12; CALL; } break; \
-    case 13: { constexpr int NS = 13; CALL; } break; \
-    case 14: { constexpr int NS = 14; CALL; } break; \
-    case 15: { constexpr int NS = 15; CALL; } break; \
-    case 16: { constexpr int NS = 16; CALL; } break; \
-    case 17: { constexpr int NS = 17; CALL; } break; \
-    default: break;                               \
-  }
-
 struct FitCtx {
   const smplfit_model_t* m;
   FitWs w;
   int B, Bp, groups, Kp, n_chunks;
   cudaStream_t st;
   const float *vwT_shape, *jwT_shape;  // shape-stage weights (pt/bodyfitter.py:1018-1028)
-  bool has_joints;
+  bool has_joints, use_rec;
 };
 
 static void run_gemm(FitCtx& c) {
@@ -157,18 +108,20 @@ static void run_shape(FitCtx& c, const float* R_unused, const float* beta_ref, c
   ShapeArgs sa;
   sa.tT = c.w.tT; sa.vwT = c.vwT_shape; sa.vposedT = c.w.vposedT; sa.RT = c.w.RT;
   sa.shapedirs = m->fit_shapedirs; sa.skin_idx = m->skin_idx; sa.skin_w = m->skin_w; sa.order = m->order;
-  sa.partials = c.w.gpart; sa.V = m->num_vertices; sa.J = m->num_joints; sa.Bp = c.Bp; sa.skin_k = m->skin_k;
-  sa.chunk_len = m->chunk_len; sa.n_chunks = c.n_chunks; sa.chunks_per_cta = 8;
-  SF_NS_DISPATCH(m->fit_ns, (launch_shape_pass<NS>(sa, c.groups, c.st)));
+  sa.partials = c.w.gpart; sa.rec = m->fit_rec; sa.V = m->num_vertices; sa.J = m->num_joints; sa.Bp = c.Bp;
+  sa.skin_k = m->skin_k; sa.chunk_len = m->chunk_len; sa.n_chunks = c.n_chunks; sa.chunks_per_cta = 8;
+  launch_shape_pass(sa, m->fit_ns, c.groups, c.use_rec, c.st);
   SolveArgs so;
   so.partials = c.w.gpart; so.Pext = c.w.Pext; so.RT = c.w.RT;
   so.tjT = c.has_joints ? c.w.tjT : nullptr; so.jwT = c.jwT_shape;
   so.beta_ref = beta_ref; so.kid_ref = kid_ref;
   so.beta = c.w.beta; so.trans = c.w.trans; so.refj = c.w.refj; so.skin = c.w.skin;
+  so.wS = m->fit_wS; so.wsum = m->fit_wsum;
   so.n_chunks = (c.n_chunks + 7) / 8; so.J = m->num_joints; so.S = m->num_betas; so.Bp = c.Bp; so.B = c.B;
   so.V = m->num_vertices; so.weighted = c.vwT_shape != nullptr;
+  so.sa_closed_form = (c.use_rec && c.vwT_shape == nullptr && m->fit_wS != nullptr) ? 1 : 0;
   so.reg = o->beta_regularizer; so.reg2 = o->beta_regularizer2; so.kid_reg = o->kid_regularizer;
-  SF_NS_DISPATCH(m->fit_ns, (launch_shape_solve<NS>(so, c.Bp, c.st)));
+  launch_shape_solve(so, m->fit_ns, c.st);
 }
 
 // statistics of (targets, reference) for the rotation stage; ref_mode as in k_stats
@@ -181,16 +134,14 @@ static void run_stats(FitCtx& c, int ref_mode, const float* ca0T, const float* a
   s.skin_idx = m->skin_idx; s.skin_w = m->skin_w; s.order = m->order; s.seg_start = m->seg_start;
   s.seg_part = m->seg_part; s.part_flags = m->part_flags; s.n_segments = m->n_segments; s.Bp = c.Bp;
   s.ns = m->fit_ns; s.skin_k = m->skin_k; s.all_segments = (aT_out != nullptr);
-  const long long warps = (long long)m->n_segments * c.groups;
-  const int blocks = (int)((warps + 3) / 4);
-  const bool wt = c.w.vwT != nullptr;
-  if (ref_mode == 0) {
-    if (wt) SF_LAUNCH((k_stats<0, true>), blocks, 128, 0, c.st, s); else SF_LAUNCH((k_stats<0, false>), blocks, 128, 0, c.st, s);
-  } else if (ref_mode == 1) {
-    if (wt) SF_LAUNCH((k_stats<1, true>), blocks, 128, 0, c.st, s); else SF_LAUNCH((k_stats<1, false>), blocks, 128, 0, c.st, s);
-  } else {
-    if (wt) SF_LAUNCH((k_stats<2, true>), blocks, 128, 0, c.st, s); else SF_LAUNCH((k_stats<2, false>), blocks, 128, 0, c.st, s);
-  }
+  StatsRecArgs r;
+  r.tT = s.tT; r.vwT = s.vwT; r.ct0 = s.ct0; r.ca0 = s.ca0; r.ca0_const = s.ca0_const; r.vposedT = s.vposedT;
+  r.beta = s.beta; r.skin = s.skin; r.aT_in = aT_in; r.aT_out = aT_out; r.partials = s.partials; r.rec = m->fit_rec;
+  r.template_fit = m->template_mesh_fit; r.seg_start = s.seg_start; r.seg_part = s.seg_part;
+  r.part_flags = s.part_flags; r.n_segments = s.n_segments; r.Bp = c.Bp; r.J = m->num_joints;
+  r.all_segments = s.all_segments; r.segs_per_warp = 2;
+  const bool use_rec = m->fit_rec != nullptr && m->skin_k <= 4 && m->template_mesh_fit != nullptr;
+  launch_stats(s, r, m->fit_ns, ref_mode, c.w.vwT != nullptr, use_rec, c.groups, c.st);
 }
 
 static void run_regress(FitCtx& c, const float* X, float* out) {
@@ -286,6 +237,7 @@ extern "C" int smplfit_fit(const smplfit_model_t* m, int64_t batch, const float*
   c.n_chunks = (m->num_vertices + m->chunk_len - 1) / m->chunk_len;
   c.st = reinterpret_cast<cudaStream_t>(stream);
   c.has_joints = has_joints;
+  c.use_rec = shape_pass_uses_records(m);
   c.w = carve(workspace, m, batch, has_joints, vertex_weights != nullptr, joint_weights != nullptr, has_init);
   if (!workspace || c.w.bytes > workspace_bytes) return fail(SMPLFIT_ERR_WORKSPACE, "workspace too small");
   FitWs& w = c.w;
@@ -388,6 +340,7 @@ extern "C" int smplfit_fit_known_pose(const smplfit_model_t* m, int64_t batch, c
   c.n_chunks = (m->num_vertices + m->chunk_len - 1) / m->chunk_len;
   c.st = reinterpret_cast<cudaStream_t>(stream);
   c.has_joints = has_joints;
+  c.use_rec = shape_pass_uses_records(m);
   c.w = carve(workspace, m, batch, has_joints, vertex_weights != nullptr, joint_weights != nullptr, 1);
   if (!workspace || c.w.bytes > workspace_bytes) return fail(SMPLFIT_ERR_WORKSPACE, "workspace too small");
   FitWs& w = c.w;

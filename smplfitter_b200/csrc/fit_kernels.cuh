@@ -340,7 +340,8 @@ __global__ void __launch_bounds__(128) k_stats(const StatsArgs a) {
 template <int NS>
 struct ShapeAcc {
   static constexpr int NG = NS * (NS + 1) / 2;
-  static constexpr int N = NG + NS + 3 * NS + 3 + 1;  // G, r, SA, Sb, W
+  static constexpr int N = NG + NS + 3 + 3 * NS + 1;  // G, r, Sb, SA, W
+  static constexpr int N_UNWEIGHTED = NG + NS + 3;   // G, r, Sb (SA in closed form, W = V)
 };
 
 struct ShapeArgs {
@@ -353,6 +354,7 @@ struct ShapeArgs {
   const float* skin_w;
   const int32_t* order;
   float* partials;       // [n_chunks][ShapeAcc<NS>::N][Bp]
+  const float* rec;      // [V][Rec<NS>::LEN] packed per-vertex records (internal order)
   int V, J, Bp, skin_k, chunk_len, n_chunks, chunks_per_cta;
 };
 
@@ -384,7 +386,7 @@ __global__ void __launch_bounds__(256) k_shape_pass(const ShapeArgs a) {
   float acc[NACC];  // G (upper triangle), r, SA, Sb, W
 #pragma unroll
   for (int e = 0; e < NACC; ++e) acc[e] = 0.f;
-  constexpr int OG = 0, OR = ShapeAcc<NS>::NG, OSA = OR + NS, OSB = OSA + 3 * NS, OW = OSB + 3;
+  constexpr int OG = 0, OR = ShapeAcc<NS>::NG, OSB = OR + NS, OSA = OSB + 3, OW = OSA + 3 * NS;  // [G | r | Sb | SA | W]
   if (active) {
     const int i0 = chunk * a.chunk_len, i1 = min(a.V, i0 + a.chunk_len);
     for (int i = i0; i < i1; ++i) {
@@ -473,6 +475,370 @@ __global__ void __launch_bounds__(256) k_shape_pass(const ShapeArgs a) {
     float* out = a.partials + (size_t)blockIdx.x * NACC * Bp + b;
 #pragma unroll
     for (int e = 0; e < NACC; ++e) out[(size_t)e * Bp] = acc[e];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Packed per-vertex record (internal order), LEN floats, 16-byte aligned:
+//   [0..3] skin weights, descending (slot 0 = the vertex's dominant joint), zero padded
+//   [4..7] joint ids of those slots (int bits)
+//   [8 .. 8+3NS) shapedirs[c][s] (with the kid column when enabled)
+// One record = 2 cache lines read with warp-uniform 16-byte loads, no index indirection.
+// ---------------------------------------------------------------------------------------
+template <int NS>
+struct Rec {
+  static constexpr int LEN = (8 + 3 * NS + 3) / 4 * 4;
+  static constexpr int NSD4 = (3 * NS + 3) / 4;  // float4 loads covering the shapedirs
+};
+
+// ---------------------------------------------------------------------------------------
+// k_shape_pass_rec<NS>: the shape pass for models with <= 4 influences per vertex whose
+// per-joint rows fit in shared memory (SMPL-size).  Same math as k_shape_pass; differences:
+//  * records instead of indexed tables; the next vertex's skin words and its streamed
+//    t / v_posed values are prefetched one iteration ahead (the pass was long-scoreboard bound);
+//  * the dominant joint's [R | T_ext] rows are cached in registers -- vertices are grouped by
+//    part, so they change only at part boundaries -- cutting shared-memory reads by ~25 %;
+//  * zero-weight slots are skipped (warp-uniform branch);
+//  * without per-vertex weights SA = sum_v jac_v is not accumulated: it has the closed form
+//    sum_k (R_k D_k + n_k T_k[:,1:]) with model constants D_k = sum_v w_vk S_v, n_k = sum_v w_vk,
+//    evaluated in k_shape_solve.
+// ---------------------------------------------------------------------------------------
+template <int NS, bool WEIGHTED>
+__global__ void __launch_bounds__(256) k_shape_pass_rec(const ShapeArgs a) {
+  extern __shared__ __align__(16) float s_rt[];
+  constexpr int RW = 12 + 3 * NS;
+  constexpr int TW = 3 * (1 + NS);
+  constexpr int REC = Rec<NS>::LEN;
+  constexpr int NUSED = WEIGHTED ? ShapeAcc<NS>::N : ShapeAcc<NS>::N_UNWEIGHTED;
+  constexpr int OG = 0, OR = ShapeAcc<NS>::NG, OSB = OR + NS, OSA = OSB + 3, OW = OSA + 3 * NS;
+  const int g = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Bp = a.Bp;
+  const int b = g * 32 + lane;
+  {
+    const int n16 = a.J * RW * 8;
+    for (int q = threadIdx.x; q < n16; q += 256) {
+      const int r = q >> 3, part = q & 7;
+      const float* src = a.RT + (size_t)r * Bp + g * 32 + part * 4;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_rt + r * 32 + part * 4);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+  }
+  const int chunk = blockIdx.x * 8 + warp;
+  const bool active = chunk < a.n_chunks;
+  float acc[NUSED];
+#pragma unroll
+  for (int e = 0; e < NUSED; ++e) acc[e] = 0.f;
+  if (active) {
+    const int i0 = chunk * a.chunk_len, i1 = min(a.V, i0 + a.chunk_len);
+    const float* rec = a.rec + (size_t)i0 * REC;
+    float4 nw = __ldg(reinterpret_cast<const float4*>(rec));
+    int4 nj = __ldg(reinterpret_cast<const int4*>(rec + 4));
+    float nt[3], nvp[3], nvw = 1.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      nt[c] = SF_IM(a.tT, i0 * 3 + c, Bp, b);
+      nvp[c] = SF_IM(a.vposedT, i0 * 3 + c, Bp, b);
+    }
+    if (WEIGHTED) nvw = SF_IM(a.vwT, i0, Bp, b);
+    float Rc[9], Tc[TW];
+    int cj = -1;
+    for (int i = i0; i < i1; ++i) {
+      const float4 w4 = nw;
+      const int4 j4 = nj;
+      float t[3], vp[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        t[c] = nt[c];
+        vp[c] = nvp[c];
+      }
+      const float wv = nvw;
+      float S[Rec<NS>::NSD4 * 4];
+#pragma unroll
+      for (int q = 0; q < Rec<NS>::NSD4; ++q) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(rec + 8) + q);
+        S[q * 4] = x.x; S[q * 4 + 1] = x.y; S[q * 4 + 2] = x.z; S[q * 4 + 3] = x.w;
+      }
+      if (i + 1 < i1) {  // prefetch the next vertex
+        rec += REC;
+        nw = __ldg(reinterpret_cast<const float4*>(rec));
+        nj = __ldg(reinterpret_cast<const int4*>(rec + 4));
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          nt[c] = SF_IM(a.tT, (i + 1) * 3 + c, Bp, b);
+          nvp[c] = SF_IM(a.vposedT, (i + 1) * 3 + c, Bp, b);
+        }
+        if (WEIGHTED) nvw = SF_IM(a.vwT, i + 1, Bp, b);
+      }
+      if (j4.x != cj) {  // part boundary: refresh the register copy of the dominant joint's rows
+        cj = j4.x;
+        const float* p = s_rt + (size_t)(cj * RW) * 32 + lane;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) Rc[e] = p[e * 32];
+#pragma unroll
+        for (int e = 0; e < TW; ++e) Tc[e] = p[(9 + e) * 32];
+      }
+      float Rb[9], Tb[TW];
+#pragma unroll
+      for (int e = 0; e < 9; ++e) Rb[e] = w4.x * Rc[e];
+#pragma unroll
+      for (int e = 0; e < TW; ++e) Tb[e] = w4.x * Tc[e];
+      const float wk[3] = {w4.y, w4.z, w4.w};
+      const int jk[3] = {j4.y, j4.z, j4.w};
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (wk[k] != 0.f) {
+          const float* p = s_rt + (size_t)(jk[k] * RW) * 32 + lane;
+#pragma unroll
+          for (int e = 0; e < 9; ++e) Rb[e] = fmaf(wk[k], p[e * 32], Rb[e]);
+#pragma unroll
+          for (int e = 0; e < TW; ++e) Tb[e] = fmaf(wk[k], p[(9 + e) * 32], Tb[e]);
+        }
+      }
+      float bv[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float pos = fmaf(Rb[c * 3], vp[0], fmaf(Rb[c * 3 + 1], vp[1], fmaf(Rb[c * 3 + 2], vp[2], Tb[c * (1 + NS)])));
+        bv[c] = t[c] - pos;
+      }
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const float s0 = S[s], s1 = S[NS + s], s2 = S[2 * NS + s];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          Tb[c * (1 + NS) + 1 + s] =
+              fmaf(Rb[c * 3], s0, fmaf(Rb[c * 3 + 1], s1, fmaf(Rb[c * 3 + 2], s2, Tb[c * (1 + NS) + 1 + s])));
+      }
+      if (WEIGHTED) acc[OW] += wv;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        acc[OSB + c] += WEIGHTED ? wv * bv[c] : bv[c];
+        int e = OG;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          const float js = Tb[c * (1 + NS) + 1 + s];
+          const float wj = WEIGHTED ? wv * js : js;
+          if (WEIGHTED) acc[OSA + c * NS + s] += wj;
+          acc[OR + s] = fmaf(wj, bv[c], acc[OR + s]);
+#pragma unroll
+          for (int t2 = s; t2 < NS; ++t2) {
+            acc[e] = fmaf(wj, Tb[c * (1 + NS) + 1 + t2], acc[e]);
+            ++e;
+          }
+        }
+      }
+    }
+  }
+  float* red = s_rt;  // [4][NUSED][32]
+#pragma unroll 1
+  for (int half = 4; half >= 1; half >>= 1) {
+    __syncthreads();
+    if (warp >= half && warp < 2 * half) {
+      float* dst = red + (size_t)(warp - half) * NUSED * 32 + lane;
+#pragma unroll
+      for (int e = 0; e < NUSED; ++e) dst[e * 32] = acc[e];
+    }
+    __syncthreads();
+    if (warp < half) {
+      const float* src = red + (size_t)warp * NUSED * 32 + lane;
+#pragma unroll
+      for (int e = 0; e < NUSED; ++e) acc[e] += src[e * 32];
+    }
+  }
+  if (warp == 0) {
+    float* out = a.partials + (size_t)blockIdx.x * ShapeAcc<NS>::N * Bp + b;
+#pragma unroll
+    for (int e = 0; e < NUSED; ++e) out[(size_t)e * Bp] = acc[e];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// k_stats_rec<NS, REF, WEIGHTED>: the statistics pass in the same style (records, one-ahead
+// prefetch, per-joint skinning transforms of the CTA's 32 instances staged in shared memory,
+// dominant joint cached in registers).  8 warps per CTA, SEGS_PER_WARP segments per warp.
+// ---------------------------------------------------------------------------------------
+struct StatsRecArgs {
+  const float* tT;
+  const float* vwT;
+  const float* ct0;
+  const float* ca0;
+  const float* ca0_const;
+  const float* vposedT;
+  const float* beta;
+  const float* skin;          // [12J][Bp]
+  const float* aT_in;
+  float* aT_out;
+  float* partials;
+  const float* rec;           // [V][Rec<NS>::LEN]
+  const float* template_fit;  // (V,3) template mesh, internal order (REF == 0)
+  const int32_t* seg_start;
+  const int32_t* seg_part;
+  const int32_t* part_flags;
+  int n_segments, Bp, J, all_segments, segs_per_warp;
+};
+
+template <int NS, int REF, bool WEIGHTED>
+__global__ void __launch_bounds__(256) k_stats_rec(const StatsRecArgs a) {
+  extern __shared__ __align__(16) float s_skin[];  // [12J][32]
+  constexpr int REC = Rec<NS>::LEN;
+  const int g = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Bp = a.Bp;
+  const int b = g * 32 + lane;
+  if (REF == 1) {
+    const int n16 = a.J * 12 * 8;
+    for (int q = threadIdx.x; q < n16; q += 256) {
+      const int r = q >> 3, part = q & 7;
+      const float* src = a.skin + (size_t)r * Bp + g * 32 + part * 4;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_skin + r * 32 + part * 4);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+  }
+  float beta[NS];
+  if (REF == 1) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) beta[s] = SF_IM(a.beta, s, Bp, b);
+  }
+  for (int q = 0; q < a.segs_per_warp; ++q) {
+    const int seg = (blockIdx.x * a.segs_per_warp + q) * 8 + warp;
+    if (seg >= a.n_segments) break;
+    const int part = a.seg_part[seg];
+    const bool stat = (a.part_flags[part] & 1) != 0;
+    if (!stat && !(REF == 1 && a.aT_out != nullptr && a.all_segments)) continue;
+    float ct[3], ca[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      ct[c] = SF_IM(a.ct0, part * 3 + c, Bp, b);
+      ca[c] = (REF == 0) ? __ldg(a.ca0_const + part * 3 + c) : SF_IM(a.ca0, part * 3 + c, Bp, b);
+    }
+    float M[9], st[3], sa[3], W = 0.f;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) M[e] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) st[c] = sa[c] = 0.f;
+    const int i0 = a.seg_start[seg], i1 = a.seg_start[seg + 1];
+    const float* rec = a.rec + (size_t)i0 * REC;
+    float4 nw = make_float4(0.f, 0.f, 0.f, 0.f);
+    int4 nj = make_int4(0, 0, 0, 0);
+    float nt[3], nx[3], nvw = 1.f;  // nx: v_posed (REF 1), explicit reference (REF 2), template (REF 0)
+    if (REF == 1) {
+      nw = __ldg(reinterpret_cast<const float4*>(rec));
+      nj = __ldg(reinterpret_cast<const int4*>(rec + 4));
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      nt[c] = SF_IM(a.tT, i0 * 3 + c, Bp, b);
+      nx[c] = (REF == 0) ? __ldg(a.template_fit + i0 * 3 + c)
+                         : SF_IM((REF == 1 ? a.vposedT : a.aT_in), i0 * 3 + c, Bp, b);
+    }
+    if (WEIGHTED) nvw = SF_IM(a.vwT, i0, Bp, b);
+    float Sc[12];
+    int cj = -1;
+    for (int i = i0; i < i1; ++i) {
+      const float4 w4 = nw;
+      const int4 j4 = nj;
+      float t[3], x[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        t[c] = nt[c];
+        x[c] = nx[c];
+      }
+      const float wv = nvw;
+      float S[Rec<NS>::NSD4 * 4];
+      if (REF == 1) {
+#pragma unroll
+        for (int qq = 0; qq < Rec<NS>::NSD4; ++qq) {
+          const float4 y = __ldg(reinterpret_cast<const float4*>(rec + 8) + qq);
+          S[qq * 4] = y.x; S[qq * 4 + 1] = y.y; S[qq * 4 + 2] = y.z; S[qq * 4 + 3] = y.w;
+        }
+      }
+      if (i + 1 < i1) {
+        rec += REC;
+        if (REF == 1) {
+          nw = __ldg(reinterpret_cast<const float4*>(rec));
+          nj = __ldg(reinterpret_cast<const int4*>(rec + 4));
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          nt[c] = SF_IM(a.tT, (i + 1) * 3 + c, Bp, b);
+          nx[c] = (REF == 0) ? __ldg(a.template_fit + (i + 1) * 3 + c)
+                             : SF_IM((REF == 1 ? a.vposedT : a.aT_in), (i + 1) * 3 + c, Bp, b);
+        }
+        if (WEIGHTED) nvw = SF_IM(a.vwT, i + 1, Bp, b);
+      }
+      float ref[3];
+      if (REF == 1) {
+        float vs[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float y = x[c];
+#pragma unroll
+          for (int s = 0; s < NS; ++s) y = fmaf(S[c * NS + s], beta[s], y);
+          vs[c] = y;
+        }
+        if (j4.x != cj) {
+          cj = j4.x;
+          const float* p = s_skin + (size_t)(cj * 12) * 32 + lane;
+#pragma unroll
+          for (int e = 0; e < 12; ++e) Sc[e] = p[e * 32];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          ref[c] = w4.x * fmaf(Sc[c * 3], vs[0], fmaf(Sc[c * 3 + 1], vs[1], fmaf(Sc[c * 3 + 2], vs[2], Sc[9 + c])));
+        const float wk[3] = {w4.y, w4.z, w4.w};
+        const int jk[3] = {j4.y, j4.z, j4.w};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          if (wk[k] != 0.f) {
+            const float* p = s_skin + (size_t)(jk[k] * 12) * 32 + lane;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const float y = fmaf(p[(c * 3) * 32], vs[0], fmaf(p[(c * 3 + 1) * 32], vs[1], fmaf(p[(c * 3 + 2) * 32], vs[2], p[(9 + c) * 32])));
+              ref[c] = fmaf(wk[k], y, ref[c]);
+            }
+          }
+        }
+        if (a.aT_out != nullptr) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) SF_IM(a.aT_out, i * 3 + c, Bp, b) = ref[c];
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) ref[c] = x[c];
+      }
+      if (stat) {
+        float dt[3], wa[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          dt[c] = t[c] - ct[c];
+          wa[c] = WEIGHTED ? wv * (ref[c] - ca[c]) : (ref[c] - ca[c]);
+          st[c] = WEIGHTED ? fmaf(wv, dt[c], st[c]) : st[c] + dt[c];
+          sa[c] += wa[c];
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) M[r * 3 + c] = fmaf(dt[r], wa[c], M[r * 3 + c]);
+        W += wv;
+      }
+    }
+    if (stat) {
+      float* out = a.partials + (size_t)seg * 16 * Bp + b;
+#pragma unroll
+      for (int e = 0; e < 9; ++e) out[(size_t)e * Bp] = M[e];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        out[(size_t)(9 + c) * Bp] = st[c];
+        out[(size_t)(12 + c) * Bp] = sa[c];
+      }
+      out[(size_t)15 * Bp] = W;
+    }
   }
 }
 

@@ -1,0 +1,17 @@
+// Launchers of the templated vertex-pass / solve kernels (instantiated in pass_shape.cu and
+// pass_stats.cu so the translation units build in parallel).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "fit_kernels.cuh"
+#include "solve_kernels.cuh"
+
+namespace sf {
+// true when the record kernels apply (<= 4 influences per vertex and the per-joint rows of 32
+// instances fit in shared memory)
+bool shape_pass_uses_records(const smplfit_model_t* m);
+void launch_shape_pass(const ShapeArgs& a, int ns, int groups, bool use_rec, cudaStream_t st);
+void launch_shape_solve(const SolveArgs& a, int ns, cudaStream_t st);
+void launch_stats(const StatsArgs& legacy, const StatsRecArgs& rec, int ns, int ref_mode, bool weighted, bool use_rec,
+                  int groups, cudaStream_t st);
+}  // namespace sf

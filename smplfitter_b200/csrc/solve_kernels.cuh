@@ -267,7 +267,10 @@ struct SolveArgs {
   float* trans;           // [3][Bp]
   float* refj;            // [3J][Bp]
   float* skin;            // [12J][Bp]
+  const double* wS;      // (J,3,NS) D_k = sum_v w_vk S_v (closed-form SA), or null
+  const double* wsum;    // (J)      n_k = sum_v w_vk
   int n_chunks, J, S, Bp, B, V, weighted;
+  int sa_closed_form;    // 1: partials hold only [G | r | Sb]; SA from (wS, wsum), W = V
   float reg, reg2, kid_reg;
 };
 
@@ -281,13 +284,15 @@ __global__ void __launch_bounds__(32) k_shape_solve(const SolveArgs a) {
   const int Bp = a.Bp, J = a.J;
   double G[NS][NS], r[NS], SA[3][NS], Sb[3], W = 0.0;
   {
+    // partial layout [G (upper triangle) | r | Sb | SA | W]
+    const int nrows = a.sa_closed_form ? (NG + NS + 3) : NACC;
     double acc[NACC];
 #pragma unroll 1
     for (int e = 0; e < NACC; ++e) acc[e] = 0.0;
     for (int c = 0; c < a.n_chunks; ++c) {
       const float* p = a.partials + (size_t)c * NACC * Bp + b;
 #pragma unroll 4
-      for (int e = 0; e < NACC; ++e) acc[e] += (double)p[(size_t)e * Bp];
+      for (int e = 0; e < nrows; ++e) acc[e] += (double)p[(size_t)e * Bp];
     }
     int o = 0;
     for (int s = 0; s < NS; ++s)
@@ -297,10 +302,30 @@ __global__ void __launch_bounds__(32) k_shape_solve(const SolveArgs a) {
         ++o;
       }
     for (int s = 0; s < NS; ++s) r[s] = acc[o++];
-    for (int c = 0; c < 3; ++c)
-      for (int s = 0; s < NS; ++s) SA[c][s] = acc[o++];
     for (int c = 0; c < 3; ++c) Sb[c] = acc[o++];
-    W = acc[o];
+    if (!a.sa_closed_form) {
+      for (int c = 0; c < 3; ++c)
+        for (int s = 0; s < NS; ++s) SA[c][s] = acc[o++];
+      W = acc[o];
+    } else {
+      // SA = sum_v jac_v = sum_k (R_k D_k + n_k T_k[:, 1:])  (exact identity of the LBS Jacobian)
+      for (int c = 0; c < 3; ++c)
+        for (int s = 0; s < NS; ++s) SA[c][s] = 0.0;
+      for (int k = 0; k < J; ++k) {
+        const double nk = a.wsum[k];
+        if (nk == 0.0) continue;
+        const float* rt = a.RT + (size_t)(k * RW) * Bp + b;
+        for (int c = 0; c < 3; ++c) {
+          const double r0 = (double)rt[(size_t)(c * 3) * Bp], r1 = (double)rt[(size_t)(c * 3 + 1) * Bp],
+                       r2 = (double)rt[(size_t)(c * 3 + 2) * Bp];
+          const double* D = a.wS + (size_t)k * 3 * NS;
+          for (int s = 0; s < NS; ++s)
+            SA[c][s] += r0 * D[s] + r1 * D[NS + s] + r2 * D[2 * NS + s] +
+                        nk * (double)rt[(size_t)(9 + c * (1 + NS) + 1 + s) * Bp];
+        }
+      }
+      W = (double)a.V;
+    }
   }
   if (a.tjT != nullptr) {
     for (int j = 0; j < J; ++j) {

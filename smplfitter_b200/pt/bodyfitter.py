@@ -69,12 +69,43 @@ class BodyFitter(nn.Module):
         self.register_buffer('_t_fit_shapedirs', sd.contiguous().clone(), persistent=False)
         self.J_template_ext = nn.Buffer(torch.cat(jt, dim=2).contiguous())
         self._ns = S + (1 if enable_kid else 0)
+        # packed per-vertex records (internal order) and the closed-form SA constants
+        ns = self._ns
+        order = body_model._t_order.numpy()
+        sd_np = sd.numpy().astype(np.float32)
+        w_np = body_model.weights.numpy()
+        wS = np.einsum('vk,vcs->kcs', w_np.astype(np.float64), sd_np.astype(np.float64))
+        self.register_buffer('_t_fit_wS', torch.tensor(np.ascontiguousarray(wS)), persistent=False)
+        self.register_buffer('_t_fit_wsum', torch.tensor(w_np.astype(np.float64).sum(axis=0)), persistent=False)
+        K = body_model._dims['skin_k']
+        self._rec_len = (8 + 3 * ns + 3) // 4 * 4
+        if K <= 4:
+            idx = body_model._t_skin_idx.numpy()
+            ww = body_model._t_skin_w.numpy()
+            idx4 = np.zeros((V, 4), np.int32)
+            w4 = np.zeros((V, 4), np.float32)
+            idx4[:, :K], w4[:, :K] = idx, ww
+            idx4[:, K:] = idx[:, :1]
+            srt = np.argsort(-w4, axis=1, kind='stable')
+            idx4 = np.take_along_axis(idx4, srt, axis=1)
+            w4 = np.take_along_axis(w4, srt, axis=1)
+            rec = np.zeros((V, self._rec_len), np.float32)
+            rec[:, 0:4] = w4
+            rec[:, 4:8] = idx4.view(np.float32)
+            rec[:, 8:8 + 3 * ns] = sd_np.reshape(V, 3 * ns)
+            self.register_buffer('_t_fit_rec', torch.tensor(np.ascontiguousarray(rec[order])), persistent=False)
+        else:
+            self._t_fit_rec = None
 
     def _struct(self) -> _native.ModelStruct:
         return self.body_model._struct(dict(
             fit_ns=self._ns,
             fit_shapedirs=self._t_fit_shapedirs.data_ptr(),
             fit_Jt_ext=self.J_template_ext.data_ptr(),
+            fit_rec=0 if self._t_fit_rec is None else self._t_fit_rec.data_ptr(),
+            fit_rec_len=self._rec_len,
+            fit_wS=self._t_fit_wS.data_ptr(),
+            fit_wsum=self._t_fit_wsum.data_ptr(),
         ))
 
     # ------------------------------------------------------------------------------

@@ -127,6 +127,7 @@ class BodyModel(nn.Module):
             'template_joints_regressed': f32(jreg @ template_mesh),
             'J_regressor_fit': f32(jreg[:, order]),
             'posedirs_hi': f32(pd_hi), 'posedirs_lo': f32(pd_lo),
+            'template_mesh_fit': f32(template_mesh[order]),
         }
         for k, v in t.items():
             self.register_buffer('_t_' + k, v, persistent=False)
@@ -156,7 +157,7 @@ class BodyModel(nn.Module):
         for name in ('parents', 'skin_idx', 'skin_w', 'order', 'inv_order', 'seg_start', 'seg_part',
                      'part_seg_begin', 'part_kind', 'part_copy_src', 'part_flags', 'cas_table', 'cas_count',
                      'posedirs_fit', 'v_template_fit', 'template_mesh', 'template_joints_regressed',
-                     'J_regressor_fit', 'posedirs_hi', 'posedirs_lo'):
+                     'J_regressor_fit', 'posedirs_hi', 'posedirs_lo', 'template_mesh_fit'):
             setattr(s, name, getattr(self, '_t_' + name).data_ptr())
         for name, buf in self.named_buffers():
             if not buf.is_contiguous():
