@@ -71,17 +71,17 @@ class BodyFitter(nn.Module):
         self._ns = S + (1 if enable_kid else 0)
         # packed per-vertex records (internal order) and the closed-form SA constants
         ns = self._ns
-        order = body_model._t_order.numpy()
-        sd_np = sd.numpy().astype(np.float32)
-        w_np = body_model.weights.numpy()
+        order = body_model._t_order.cpu().numpy()
+        sd_np = sd.cpu().numpy().astype(np.float32)
+        w_np = body_model.weights.cpu().numpy()
         wS = np.einsum('vk,vcs->kcs', w_np.astype(np.float64), sd_np.astype(np.float64))
         self.register_buffer('_t_fit_wS', torch.tensor(np.ascontiguousarray(wS)), persistent=False)
         self.register_buffer('_t_fit_wsum', torch.tensor(w_np.astype(np.float64).sum(axis=0)), persistent=False)
         K = body_model._dims['skin_k']
         self._rec_len = (8 + 3 * ns + 3) // 4 * 4
         if K <= 4:
-            idx = body_model._t_skin_idx.numpy()
-            ww = body_model._t_skin_w.numpy()
+            idx = body_model._t_skin_idx.cpu().numpy()
+            ww = body_model._t_skin_w.cpu().numpy()
             idx4 = np.zeros((V, 4), np.int32)
             w4 = np.zeros((V, 4), np.float32)
             idx4[:, :K], w4[:, :K] = idx, ww
@@ -96,6 +96,7 @@ class BodyFitter(nn.Module):
             self.register_buffer('_t_fit_rec', torch.tensor(np.ascontiguousarray(rec[order])), persistent=False)
         else:
             self._t_fit_rec = None
+        self.to(body_model.v_template.device)
 
     def _struct(self) -> _native.ModelStruct:
         return self.body_model._struct(dict(
