@@ -17,6 +17,7 @@ bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
 
 struct FitWs {
+  double* Gd;
   float *mean, *tT, *tjT, *vwT, *jwT, *vposedT, *R, *R2, *RT, *Pext, *feat, *gpart, *beta, *trans, *refj,
       *skin, *spart, *aT, *ajT, *initjT;
   void* tc_scratch;
@@ -45,6 +46,7 @@ static FitWs carve(void* base, const smplfit_model_t* m, int64_t B, int has_join
   w.Pext = c.take<float>((size_t)J * 3 * (1 + NS) * Bp);
   w.feat = c.take<float>((size_t)Bp * Kp);
   w.gpart = c.take<float>((size_t)((n_chunks + 7) / 8) * shape_nacc(NS) * Bp);
+  w.Gd = c.take<double>((size_t)shape_nacc(NS) * Bp);
   w.beta = c.take<float>((size_t)NS * Bp);
   w.trans = c.take<float>(3 * Bp);
   w.refj = c.take<float>((size_t)3 * J * Bp);
@@ -121,7 +123,7 @@ static void run_shape(FitCtx& c, const float* R_unused, const float* beta_ref, c
   so.V = m->num_vertices; so.weighted = c.vwT_shape != nullptr;
   so.sa_closed_form = (c.use_rec && c.vwT_shape == nullptr && m->fit_wS != nullptr) ? 1 : 0;
   so.reg = o->beta_regularizer; so.reg2 = o->beta_regularizer2; so.kid_reg = o->kid_regularizer;
-  launch_shape_solve(so, m->fit_ns, c.st);
+  launch_shape_solve(so, c.w.Gd, m->fit_ns, c.groups, c.st);
 }
 
 // statistics of (targets, reference) for the rotation stage; ref_mode as in k_stats
@@ -150,6 +152,14 @@ static void run_regress(FitCtx& c, const float* X, float* out) {
   const long long warps = (long long)c.groups * jblocks;
   SF_LAUNCH(k_regress, (int)((warps + 3) / 4), 128, 0, c.st, m->J_regressor_fit, X, m->num_vertices,
             m->num_joints, c.Bp, out);
+}
+
+// rotation fit per (instance, part), then the pose-dependent front of the next shape solve
+static void run_rot(FitCtx& c, const RotArgs& ra, bool fit) {
+  const int J = c.m->num_joints;
+  if (fit) SF_LAUNCH(k_rot_fit, dim3(c.groups, J), 32, 0, c.st, ra);
+  SF_LAUNCH(k_front_rel, dim3(c.groups, J), 32, 0, c.st, ra);
+  SF_LAUNCH(k_front_fk, dim3(c.groups, c.m->fit_ns + 1), 32, 0, c.st, ra);
 }
 
 template <int C>
@@ -256,7 +266,7 @@ extern "C" int smplfit_fit(const smplfit_model_t* m, int64_t batch, const float*
 
   RotArgs ra;
   ra.partials = w.spart; ra.tjT = w.tjT; ra.jwT = w.jwT; ra.R_new = w.R; ra.RT = w.RT; ra.Pext = w.Pext;
-  ra.feat = w.feat; ra.t = tables(m); ra.B = c.B; ra.Bp = c.Bp; ra.Kp = c.Kp; ra.front_only = 0;
+  ra.feat = w.feat; ra.t = tables(m); ra.B = c.B; ra.Bp = c.Bp; ra.Kp = c.Kp;
   // -- first rotation fit (pt/bodyfitter.py:363-394) --
   if (has_init) {
     run_transpose<3>(c, init_vertices, V, m->inv_order, nullptr, w.aT);
@@ -276,7 +286,7 @@ extern "C" int smplfit_fit(const smplfit_model_t* m, int64_t batch, const float*
     ra.ajT = nullptr; ra.aj_const = has_joints ? m->J_template : m->template_joints_regressed;
     ra.ca0T = nullptr; ra.ca0_const = m->J_template; ra.R_old = nullptr;
   }
-  SF_LAUNCH(k_rot_solve, c.Bp / 32, 32, 0, c.st, ra);
+  run_rot(c, ra, true);
 
   // -- alternate shape and rotation fits (pt/bodyfitter.py:399-461) --
   const float* R_final = w.R;
@@ -293,7 +303,7 @@ extern "C" int smplfit_fit(const smplfit_model_t* m, int64_t batch, const float*
     }
     if (!last) {
       ra.ajT = aj; ra.aj_const = nullptr; ra.ca0T = w.refj; ra.ca0_const = nullptr; ra.R_old = w.R; ra.R_new = w.R;
-      SF_LAUNCH(k_rot_solve, c.Bp / 32, 32, 0, c.st, ra);
+      run_rot(c, ra, true);
     } else {
       AdjustArgs aa;
       aa.partials = w.spart; aa.tjT = w.tjT; aa.ajT = aj; aa.refj = w.refj; aa.jwT = w.jwT; aa.R_prev = w.R;
@@ -352,12 +362,12 @@ extern "C" int smplfit_fit_known_pose(const smplfit_model_t* m, int64_t batch, c
   if (has_joints) run_transpose<3>(c, target_joints, J, nullptr, w.mean, w.tjT);
   c.vwT_shape = o->shape_weights ? w.vwT : nullptr;
   c.jwT_shape = (o->shape_weights && has_joints) ? w.jwT : nullptr;
-  run_transpose<1>(c, glob_rotmats, 9 * J, nullptr, nullptr, w.R2);
+  run_transpose<1>(c, glob_rotmats, 9 * J, nullptr, nullptr, w.R);
   RotArgs ra;
   ra.partials = nullptr; ra.tjT = nullptr; ra.ajT = nullptr; ra.aj_const = nullptr; ra.ca0T = nullptr;
-  ra.ca0_const = nullptr; ra.jwT = nullptr; ra.R_old = w.R2; ra.R_new = w.R; ra.RT = w.RT; ra.Pext = w.Pext;
-  ra.feat = w.feat; ra.t = tables(m); ra.B = c.B; ra.Bp = c.Bp; ra.Kp = c.Kp; ra.front_only = 1;
-  SF_LAUNCH(k_rot_solve, c.Bp / 32, 32, 0, c.st, ra);
+  ra.ca0_const = nullptr; ra.jwT = nullptr; ra.R_old = nullptr; ra.R_new = w.R; ra.RT = w.RT; ra.Pext = w.Pext;
+  ra.feat = w.feat; ra.t = tables(m); ra.B = c.B; ra.Bp = c.Bp; ra.Kp = c.Kp;
+  run_rot(c, ra, false);
   run_shape(c, w.R, beta_reg_reference, kid_reg_reference, o);
   // orientations output is not part of this method's result; reuse the scratch R2 for it
   OutputArgs oa;

@@ -58,10 +58,15 @@ void launch_shape_pass(const ShapeArgs& a, int ns, int groups, bool use_rec, cud
 }
 
 template <int NS>
-static void shape_solve_t(const SolveArgs& so, cudaStream_t st) {
-  SF_LAUNCH(k_shape_solve<NS>, so.Bp / 32, 32, 0, st, so);
+static void shape_solve_t(const SolveArgs& so, double* Gd, int groups, cudaStream_t st) {
+  constexpr int NACC = ShapeAcc<NS>::N;
+  SF_LAUNCH(k_gram_entries<NS>, dim3(groups, NACC), 32, 0, st, so, Gd);
+  SF_LAUNCH(k_shape_solve<NS>, groups, 32, 0, st, so, Gd);
+  SF_LAUNCH(k_shape_out, dim3(groups, so.J), 32, 0, st, so, NS);
 }
 
-void launch_shape_solve(const SolveArgs& a, int ns, cudaStream_t st) { SF_NS_SWITCH(ns, (shape_solve_t<NS>(a, st))); }
+void launch_shape_solve(const SolveArgs& a, double* Gd, int ns, int groups, cudaStream_t st) {
+  SF_NS_SWITCH(ns, (shape_solve_t<NS>(a, Gd, groups, st)));
+}
 
 }  // namespace sf

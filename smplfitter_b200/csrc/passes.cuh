@@ -11,7 +11,7 @@ namespace sf {
 // instances fit in shared memory)
 bool shape_pass_uses_records(const smplfit_model_t* m);
 void launch_shape_pass(const ShapeArgs& a, int ns, int groups, bool use_rec, cudaStream_t st);
-void launch_shape_solve(const SolveArgs& a, int ns, cudaStream_t st);
+void launch_shape_solve(const SolveArgs& a, double* Gd, int ns, int groups, cudaStream_t st);
 void launch_stats(const StatsArgs& legacy, const StatsRecArgs& rec, int ns, int ref_mode, bool weighted, bool use_rec,
                   int groups, cudaStream_t st);
 }  // namespace sf

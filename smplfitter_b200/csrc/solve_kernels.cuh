@@ -85,161 +85,183 @@ struct RotArgs {
   float* feat;             // [Bp][Kp]
   TreeTables t;
   int B, Bp, Kp;
-  int front_only;  // 1: keep R_old (orientations given by the caller) and only run the shape front
 };
 
-static __global__ void __launch_bounds__(32) k_rot_solve(const RotArgs a) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= a.Bp) return;
-  const int J = a.t.J, Bp = a.Bp, NS = a.t.NS;
-  float Rfit[SMPLFIT_MAX_JOINTS * 9];
-  for (int i = 0; i < J; ++i) {
-    const int kind = a.front_only ? 0 : a.t.part_kind[i];
-    float* R = Rfit + i * 9;
-    if (kind == 0 || kind == 4) {
+// Rotation fit of one body part (device function shared by the kernels below).
+__device__ inline void fit_part(const RotArgs& a, int i, int b, float* R) {
+  const int Bp = a.Bp;
+  const int kind = a.t.part_kind[i];
+  if (kind == 0 || kind == 4) {
 #pragma unroll
-      for (int e = 0; e < 9; ++e) R[e] = (e % 4 == 0) ? 1.f : 0.f;
-      continue;
+    for (int e = 0; e < 9; ++e) R[e] = (e % 4 == 0) ? 1.f : 0.f;
+    return;
+  }
+  const int n = a.t.cas_count[i];
+  const int32_t* cas = a.t.cas_table + i * a.t.max_cas;
+  // children-mean centres (center_matrix, pt/bodyfitter.py:125-129, :1352-1353)
+  float mt[3] = {0.f, 0.f, 0.f}, ma[3] = {0.f, 0.f, 0.f};
+  for (int k = 0; k < n; ++k) {
+    float tj[3], aj[3];
+    load3(a.tjT, cas[k], Bp, b, tj);
+    load3_or_const(a.ajT, a.aj_const, cas[k], Bp, b, aj);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      mt[c] += tj[c];
+      ma[c] += aj[c];
     }
-    const int n = a.t.cas_count[i];
-    const int32_t* cas = a.t.cas_table + i * a.t.max_cas;
-    // children-mean centres (center_matrix, pt/bodyfitter.py:125-129, :1352-1353)
-    float mt[3] = {0.f, 0.f, 0.f}, ma[3] = {0.f, 0.f, 0.f};
+  }
+  const float inv = 1.f / (float)n;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    mt[c] *= inv;
+    ma[c] *= inv;
+  }
+  float A[9];
+  if (kind == 1) {
+    // multi-joint part: Kabsch on its joints alone (pt/bodyfitter.py:1361-1383)
+#pragma unroll
+    for (int e = 0; e < 9; ++e) A[e] = 0.f;
     for (int k = 0; k < n; ++k) {
       float tj[3], aj[3];
       load3(a.tjT, cas[k], Bp, b, tj);
       load3_or_const(a.ajT, a.aj_const, cas[k], Bp, b, aj);
+      const float w = a.jwT ? SF_IM(a.jwT, cas[k], Bp, b) : 1.f;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        mt[c] += tj[c];
-        ma[c] += aj[c];
-      }
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) A[r * 3 + c] = fmaf(tj[r] - mt[r], w * (aj[c] - ma[c]), A[r * 3 + c]);
     }
-    const float inv = 1.f / (float)n;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      mt[c] *= inv;
-      ma[c] *= inv;
-    }
-    float A[9];
-    if (kind == 1) {
-      // multi-joint part: Kabsch on its joints alone (pt/bodyfitter.py:1361-1383)
-#pragma unroll
-      for (int e = 0; e < 9; ++e) A[e] = 0.f;
-      for (int k = 0; k < n; ++k) {
-        float tj[3], aj[3];
-        load3(a.tjT, cas[k], Bp, b, tj);
-        load3_or_const(a.ajT, a.aj_const, cas[k], Bp, b, aj);
-        const float w = a.jwT ? SF_IM(a.jwT, cas[k], Bp, b) : 1.f;
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-          for (int c = 0; c < 3; ++c) A[r * 3 + c] = fmaf(tj[r] - mt[r], w * (aj[c] - ma[c]), A[r * 3 + c]);
-      }
-      proj_so3(A, R);
-      continue;
-    }
-    float ct0[3], ca0[3];
-    load3(a.tjT, i, Bp, b, ct0);
-    load3_or_const(a.ca0T, a.ca0_const, i, Bp, b, ca0);
-    part_covariance(a.partials, a.t.part_seg_begin, i, Bp, b, ct0, ca0, mt, ma, A);
-    if (kind == 3) {  // leaf part: Kabsch on its vertices
-      proj_so3(A, R);
-      continue;
-    }
-    // bone part: swing aligns the bone, twist from the vertex covariance (pt/bodyfitter.py:1389-1412)
-    float bt[3], br[3], t0[3], t1[3], r0[3], r1[3];
-    load3(a.tjT, cas[0], Bp, b, t0);
-    load3(a.tjT, cas[1], Bp, b, t1);
-    load3_or_const(a.ajT, a.aj_const, cas[0], Bp, b, r0);
-    load3_or_const(a.ajT, a.aj_const, cas[1], Bp, b, r1);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      bt[c] = t1[c] - t0[c];
-      br[c] = r1[c] - r0[c];
-    }
-    const float nt = sqrtf(bt[0] * bt[0] + bt[1] * bt[1] + bt[2] * bt[2]);
-    const float nr = sqrtf(br[0] * br[0] + br[1] * br[1] + br[2] * br[2]);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      bt[c] = div_no_nan(bt[c], nt);
-      br[c] = div_no_nan(br[c], nr);
-    }
-    float Rs[9], H[9];
-    align_unit_vectors(br, bt, Rs);
-    // H = Rs A^T
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) H[r * 3 + c] = Rs[r * 3] * A[c * 3] + Rs[r * 3 + 1] * A[c * 3 + 1] + Rs[r * 3 + 2] * A[c * 3 + 2];
-    const float trH = H[0] + H[4] + H[8];
-    float Hb[3];
-    mat3_vec(H, bt, Hb);
-    const float bHb = bt[0] * Hb[0] + bt[1] * Hb[1] + bt[2] * Hb[2];
-    const float vee[3] = {H[5] - H[7], H[6] - H[2], H[1] - H[3]};
-    const float ang = atan2f(bt[0] * vee[0] + bt[1] * vee[1] + bt[2] * vee[2], trH - bHb);
-    float rv[3] = {bt[0] * ang, bt[1] * ang, bt[2] * ang}, Rt[9];
-    rotvec2mat(rv, Rt);
-    mat3_mul(Rt, Rs, R);
+    proj_so3(A, R);
+    return;
   }
-  // assemble (toe parts take the feet's fit, pt/bodyfitter.py:1414-1416) and left-multiply
-  for (int i = 0; i < J; ++i) {
-    const int src = (!a.front_only && a.t.part_kind[i] == 4) ? a.t.part_copy_src[i] : i;
-    float Rn[9];
-    if (a.R_old != nullptr) {
-      float Ro[9];
-#pragma unroll
-      for (int e = 0; e < 9; ++e) Ro[e] = SF_IM(a.R_old, i * 9 + e, Bp, b);
-      mat3_mul(Rfit + src * 9, Ro, Rn);
-    } else {
-#pragma unroll
-      for (int e = 0; e < 9; ++e) Rn[e] = Rfit[src * 9 + e];
-    }
-#pragma unroll
-    for (int e = 0; e < 9; ++e) SF_IM(a.R_new, i * 9 + e, Bp, b) = Rn[e];
+  float ct0[3], ca0[3];
+  load3(a.tjT, i, Bp, b, ct0);
+  load3_or_const(a.ca0T, a.ca0_const, i, Bp, b, ca0);
+  part_covariance(a.partials, a.t.part_seg_begin, i, Bp, b, ct0, ca0, mt, ma, A);
+  if (kind == 3) {  // leaf part: Kabsch on its vertices
+    proj_so3(A, R);
+    return;
   }
-  if (a.RT == nullptr) return;
-  // ---- shape front (pt/bodyfitter.py:869-911) ----
+  // bone part: swing aligns the bone, twist from the vertex covariance (pt/bodyfitter.py:1389-1412)
+  float bt[3], br[3], t0[3], t1[3], r0[3], r1[3];
+  load3(a.tjT, cas[0], Bp, b, t0);
+  load3(a.tjT, cas[1], Bp, b, t1);
+  load3_or_const(a.ajT, a.aj_const, cas[0], Bp, b, r0);
+  load3_or_const(a.ajT, a.aj_const, cas[1], Bp, b, r1);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    bt[c] = t1[c] - t0[c];
+    br[c] = r1[c] - r0[c];
+  }
+  const float nt = sqrtf(bt[0] * bt[0] + bt[1] * bt[1] + bt[2] * bt[2]);
+  const float nr = sqrtf(br[0] * br[0] + br[1] * br[1] + br[2] * br[2]);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    bt[c] = div_no_nan(bt[c], nt);
+    br[c] = div_no_nan(br[c], nr);
+  }
+  float Rs[9], H[9];
+  align_unit_vectors(br, bt, Rs);
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) H[r * 3 + c] = Rs[r * 3] * A[c * 3] + Rs[r * 3 + 1] * A[c * 3 + 1] + Rs[r * 3 + 2] * A[c * 3 + 2];
+  const float trH = H[0] + H[4] + H[8];
+  float Hb[3];
+  mat3_vec(H, bt, Hb);
+  const float bHb = bt[0] * Hb[0] + bt[1] * Hb[1] + bt[2] * Hb[2];
+  const float vee[3] = {H[5] - H[7], H[6] - H[2], H[1] - H[3]};
+  const float ang = atan2f(bt[0] * vee[0] + bt[1] * vee[1] + bt[2] * vee[2], trH - bHb);
+  float rv[3] = {bt[0] * ang, bt[1] * ang, bt[2] * ang}, Rt[9];
+  rotvec2mat(rv, Rt);
+  mat3_mul(Rt, Rs, R);
+}
+
+// k_rot_fit: one thread per (instance, part).  Fits the part's rotation (toe parts re-fit their
+// foot, pt/bodyfitter.py:1414-1416) and left-multiplies it onto the running orientation
+// (:422-433).  In-place safe: thread (b, i) only touches R[i][b].
+static __global__ void __launch_bounds__(32) k_rot_fit(const RotArgs a) {
+  const int b = blockIdx.x * 32 + threadIdx.x;
+  const int i = blockIdx.y;
+  if (b >= a.Bp) return;
+  const int Bp = a.Bp;
+  const int src = (a.t.part_kind[i] == 4) ? a.t.part_copy_src[i] : i;
+  float Rf[9], Rn[9];
+  fit_part(a, src, b, Rf);
+  if (a.R_old != nullptr) {
+    float Ro[9];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) Ro[e] = SF_IM(a.R_old, i * 9 + e, Bp, b);
+    mat3_mul(Rf, Ro, Rn);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 9; ++e) Rn[e] = Rf[e];
+  }
+#pragma unroll
+  for (int e = 0; e < 9; ++e) SF_IM(a.R_new, i * 9 + e, Bp, b) = Rn[e];
+}
+
+// k_front_rel: one thread per (instance, joint): relative rotation -> pose features, and the
+// rotation rows of the [R | T_ext] table (pt/bodyfitter.py:869-876, :913).
+static __global__ void __launch_bounds__(32) k_front_rel(const RotArgs a) {
+  const int b = blockIdx.x * 32 + threadIdx.x;
+  const int j = blockIdx.y;
+  if (b >= a.Bp) return;
+  const int Bp = a.Bp, NS = a.t.NS, J = a.t.J;
+  const int RW = 12 + 3 * NS;
+  float Rj[9];
+#pragma unroll
+  for (int e = 0; e < 9; ++e) {
+    Rj[e] = SF_IM(a.R_new, j * 9 + e, Bp, b);
+    SF_IM(a.RT, j * RW + e, Bp, b) = Rj[e];
+  }
+  if (j > 0) {
+    const int par = a.t.parents[j];
+    float Rp[9], rel[9];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) Rp[e] = SF_IM(a.R_new, par * 9 + e, Bp, b);
+    mat3_tmul(Rp, Rj, rel);
+#pragma unroll
+    for (int e = 0; e < 9; ++e) a.feat[(size_t)b * a.Kp + (j - 1) * 9 + e] = rel[e];
+  } else {
+    for (int k = 9 * (J - 1); k < a.Kp; ++k) a.feat[(size_t)b * a.Kp + k] = 0.f;
+  }
+}
+
+// k_front_fk: one thread per (instance, column s of [position | shape Jacobian]): forward
+// kinematics of that column down the tree and the per-joint translation offsets
+// (pt/bodyfitter.py:880-911).
+static __global__ void __launch_bounds__(32) k_front_fk(const RotArgs a) {
+  const int b = blockIdx.x * 32 + threadIdx.x;
+  const int s = blockIdx.y;
+  if (b >= a.Bp) return;
+  const int Bp = a.Bp, NS = a.t.NS, J = a.t.J;
   const int TW = 3 * (1 + NS), RW = 12 + 3 * NS;
+  float P[SMPLFIT_MAX_JOINTS * 3];
   for (int j = 0; j < J; ++j) {
+    const float* Jt = a.t.Jt_ext + (size_t)j * TW;
+    const float j0 = __ldg(Jt + s), j1 = __ldg(Jt + (1 + NS) + s), j2 = __ldg(Jt + 2 * (1 + NS) + s);
     float Rj[9];
 #pragma unroll
     for (int e = 0; e < 9; ++e) Rj[e] = SF_IM(a.R_new, j * 9 + e, Bp, b);
-    const int par = a.t.parents[j];
-    const float* Jt = a.t.Jt_ext + (size_t)j * TW;
     if (j == 0) {
-      for (int e = 0; e < TW; ++e) SF_IM(a.Pext, e, Bp, b) = __ldg(Jt + e);
+      P[0] = j0; P[1] = j1; P[2] = j2;
     } else {
-      float Rp[9], rel[9];
+      const int par = a.t.parents[j];
+      const float* Jp = a.t.Jt_ext + (size_t)par * TW;
+      const float d0 = j0 - __ldg(Jp + s), d1 = j1 - __ldg(Jp + (1 + NS) + s), d2 = j2 - __ldg(Jp + 2 * (1 + NS) + s);
+      float Rp[9];
 #pragma unroll
       for (int e = 0; e < 9; ++e) Rp[e] = SF_IM(a.R_new, par * 9 + e, Bp, b);
-      mat3_tmul(Rp, Rj, rel);
-      if (b < a.B || true) {
 #pragma unroll
-        for (int e = 0; e < 9; ++e) a.feat[(size_t)b * a.Kp + (j - 1) * 9 + e] = rel[e];
-      }
-      const float* Jp = a.t.Jt_ext + (size_t)par * TW;
-      for (int s = 0; s <= NS; ++s) {
-        const float d0 = __ldg(Jt + s) - __ldg(Jp + s);
-        const float d1 = __ldg(Jt + (1 + NS) + s) - __ldg(Jp + (1 + NS) + s);
-        const float d2 = __ldg(Jt + 2 * (1 + NS) + s) - __ldg(Jp + 2 * (1 + NS) + s);
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-          SF_IM(a.Pext, j * TW + c * (1 + NS) + s, Bp, b) =
-              SF_IM(a.Pext, par * TW + c * (1 + NS) + s, Bp, b) + (Rp[c * 3] * d0 + Rp[c * 3 + 1] * d1 + Rp[c * 3 + 2] * d2);
-      }
+      for (int c = 0; c < 3; ++c) P[j * 3 + c] = P[par * 3 + c] + (Rp[c * 3] * d0 + Rp[c * 3 + 1] * d1 + Rp[c * 3 + 2] * d2);
     }
 #pragma unroll
-    for (int e = 0; e < 9; ++e) SF_IM(a.RT, j * RW + e, Bp, b) = Rj[e];
-    for (int s = 0; s <= NS; ++s) {
-      const float j0 = __ldg(Jt + s), j1 = __ldg(Jt + (1 + NS) + s), j2 = __ldg(Jt + 2 * (1 + NS) + s);
-#pragma unroll
-      for (int c = 0; c < 3; ++c)
-        SF_IM(a.RT, j * RW + 9 + c * (1 + NS) + s, Bp, b) =
-            SF_IM(a.Pext, j * TW + c * (1 + NS) + s, Bp, b) - (Rj[c * 3] * j0 + Rj[c * 3 + 1] * j1 + Rj[c * 3 + 2] * j2);
+    for (int c = 0; c < 3; ++c) {
+      SF_IM(a.Pext, j * TW + c * (1 + NS) + s, Bp, b) = P[j * 3 + c];
+      SF_IM(a.RT, j * RW + 9 + c * (1 + NS) + s, Bp, b) = P[j * 3 + c] - (Rj[c * 3] * j0 + Rj[c * 3 + 1] * j1 + Rj[c * 3 + 2] * j2);
     }
   }
-  for (int k = 9 * (J - 1); k < a.Kp; ++k) a.feat[(size_t)b * a.Kp + k] = 0.f;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -274,78 +296,91 @@ struct SolveArgs {
   float reg, reg2, kid_reg;
 };
 
+// k_gram_entries<NS>: one thread per (instance, entry of [G | r | Sb | SA | W]): chunk partials
+// + joint block (+ closed-form SA), in double.  blockIdx.y = entry (warp-uniform).
 template <int NS>
-__global__ void __launch_bounds__(32) k_shape_solve(const SolveArgs a) {
+__global__ void __launch_bounds__(32) k_gram_entries(const SolveArgs a, double* __restrict__ Gd) {
   constexpr int NG = NS * (NS + 1) / 2;
-  constexpr int NACC = NG + NS + 3 * NS + 3 + 1;
+  constexpr int NACC = NG + NS + 3 + 3 * NS + 1;
   constexpr int TW = 3 * (1 + NS), RW = 12 + 3 * NS;
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.x * 32 + threadIdx.x;
+  const int e = blockIdx.y;
   if (b >= a.Bp) return;
   const int Bp = a.Bp, J = a.J;
-  double G[NS][NS], r[NS], SA[3][NS], Sb[3], W = 0.0;
-  {
-    // partial layout [G (upper triangle) | r | Sb | SA | W]
-    const int nrows = a.sa_closed_form ? (NG + NS + 3) : NACC;
-    double acc[NACC];
-#pragma unroll 1
-    for (int e = 0; e < NACC; ++e) acc[e] = 0.0;
-    for (int c = 0; c < a.n_chunks; ++c) {
-      const float* p = a.partials + (size_t)c * NACC * Bp + b;
-#pragma unroll 4
-      for (int e = 0; e < nrows; ++e) acc[e] += (double)p[(size_t)e * Bp];
+  // decode the entry
+  int kind, s = 0, t = 0, c = 0;  // 0 G(s,t), 1 r(s), 2 Sb(c), 3 SA(c,s), 4 W
+  if (e < NG) {
+    kind = 0;
+    int o = e;
+    while (o >= NS - s) { o -= NS - s; ++s; }
+    t = s + o;
+  } else if (e < NG + NS) { kind = 1; s = e - NG; }
+  else if (e < NG + NS + 3) { kind = 2; c = e - NG - NS; }
+  else if (e < NG + NS + 3 + 3 * NS) { kind = 3; c = (e - NG - NS - 3) / NS; s = (e - NG - NS - 3) % NS; }
+  else kind = 4;
+  double acc = 0.0;
+  const bool from_partials = !(a.sa_closed_form && kind >= 3);
+  if (from_partials) {
+    for (int q = 0; q < a.n_chunks; ++q) acc += (double)a.partials[((size_t)q * NACC + e) * Bp + b];
+  } else if (kind == 4) {
+    acc = (double)a.V;
+  } else {  // SA(c,s) = sum_k (R_k D_k + n_k T_k[:,1:])
+    for (int k = 0; k < J; ++k) {
+      const double nk = a.wsum[k];
+      if (nk == 0.0) continue;
+      const float* rt = a.RT + (size_t)(k * RW) * Bp + b;
+      const double* D = a.wS + (size_t)k * 3 * NS;
+      acc += (double)rt[(size_t)(c * 3) * Bp] * D[s] + (double)rt[(size_t)(c * 3 + 1) * Bp] * D[NS + s] +
+             (double)rt[(size_t)(c * 3 + 2) * Bp] * D[2 * NS + s] + nk * (double)rt[(size_t)(9 + c * (1 + NS) + 1 + s) * Bp];
     }
+  }
+  if (a.tjT != nullptr) {  // joint block (pt/bodyfitter.py:1050-1058, _gram_block :1598)
+    for (int j = 0; j < J; ++j) {
+      const double w = a.jwT ? (double)SF_IM(a.jwT, j, Bp, b) : 1.0;
+      if (kind == 4) { acc += w; continue; }
+      if (kind == 0 || kind == 1) {
+        for (int cc = 0; cc < 3; ++cc) {
+          const float* prow = a.Pext + (size_t)(j * TW + cc * (1 + NS)) * Bp + b;
+          const double js = (double)prow[(size_t)(1 + s) * Bp];
+          const double other = (kind == 0) ? (double)prow[(size_t)(1 + t) * Bp]
+                                           : (double)SF_IM(a.tjT, j * 3 + cc, Bp, b) - (double)prow[0];
+          acc += w * js * other;
+        }
+      } else {
+        const float* prow = a.Pext + (size_t)(j * TW + c * (1 + NS)) * Bp + b;
+        acc += (kind == 2) ? w * ((double)SF_IM(a.tjT, j * 3 + c, Bp, b) - (double)prow[0])
+                           : w * (double)prow[(size_t)(1 + s) * Bp];
+      }
+    }
+  }
+  Gd[(size_t)e * Bp + b] = acc;
+}
+
+// k_shape_solve<NS>: one thread per instance: centre with the covariance identity, regularise,
+// Cholesky-solve in double, recover the translation (pt/bodyfitter.py:1060-1089; the general
+// solve :1199-1283 is algebraically the same system).
+template <int NS>
+__global__ void __launch_bounds__(32) k_shape_solve(const SolveArgs a, const double* __restrict__ Gd) {
+  constexpr int NG = NS * (NS + 1) / 2;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.Bp) return;
+  const int Bp = a.Bp;
+  double G[NS][NS], r[NS], SA[3][NS], Sb[3];
+  {
     int o = 0;
     for (int s = 0; s < NS; ++s)
       for (int t = s; t < NS; ++t) {
-        G[s][t] = acc[o];
-        G[t][s] = acc[o];
+        const double v = Gd[(size_t)o * Bp + b];
+        G[s][t] = v;
+        G[t][s] = v;
         ++o;
       }
-    for (int s = 0; s < NS; ++s) r[s] = acc[o++];
-    for (int c = 0; c < 3; ++c) Sb[c] = acc[o++];
-    if (!a.sa_closed_form) {
-      for (int c = 0; c < 3; ++c)
-        for (int s = 0; s < NS; ++s) SA[c][s] = acc[o++];
-      W = acc[o];
-    } else {
-      // SA = sum_v jac_v = sum_k (R_k D_k + n_k T_k[:, 1:])  (exact identity of the LBS Jacobian)
-      for (int c = 0; c < 3; ++c)
-        for (int s = 0; s < NS; ++s) SA[c][s] = 0.0;
-      for (int k = 0; k < J; ++k) {
-        const double nk = a.wsum[k];
-        if (nk == 0.0) continue;
-        const float* rt = a.RT + (size_t)(k * RW) * Bp + b;
-        for (int c = 0; c < 3; ++c) {
-          const double r0 = (double)rt[(size_t)(c * 3) * Bp], r1 = (double)rt[(size_t)(c * 3 + 1) * Bp],
-                       r2 = (double)rt[(size_t)(c * 3 + 2) * Bp];
-          const double* D = a.wS + (size_t)k * 3 * NS;
-          for (int s = 0; s < NS; ++s)
-            SA[c][s] += r0 * D[s] + r1 * D[NS + s] + r2 * D[2 * NS + s] +
-                        nk * (double)rt[(size_t)(9 + c * (1 + NS) + 1 + s) * Bp];
-        }
-      }
-      W = (double)a.V;
-    }
+    for (int s = 0; s < NS; ++s) r[s] = Gd[(size_t)(o++) * Bp + b];
+    for (int c = 0; c < 3; ++c) Sb[c] = Gd[(size_t)(o++) * Bp + b];
+    for (int c = 0; c < 3; ++c)
+      for (int s = 0; s < NS; ++s) SA[c][s] = Gd[(size_t)(o++) * Bp + b];
   }
-  if (a.tjT != nullptr) {
-    for (int j = 0; j < J; ++j) {
-      const double w = a.jwT ? (double)SF_IM(a.jwT, j, Bp, b) : 1.0;
-      W += w;
-      for (int c = 0; c < 3; ++c) {
-        const float* prow = a.Pext + (size_t)(j * TW + c * (1 + NS)) * Bp + b;
-        const double bj = (double)SF_IM(a.tjT, j * 3 + c, Bp, b) - (double)prow[0];
-        Sb[c] += w * bj;
-        double jac[NS];
-        for (int s = 0; s < NS; ++s) jac[s] = (double)prow[(size_t)(1 + s) * Bp];
-        for (int s = 0; s < NS; ++s) {
-          const double wj = w * jac[s];
-          SA[c][s] += wj;
-          r[s] += wj * bj;
-          for (int t = 0; t < NS; ++t) G[s][t] += wj * jac[t];
-        }
-      }
-    }
-  }
+  const double W = Gd[(size_t)(NG + NS + 3 + 3 * NS) * Bp + b];
   const double Ws = (W == 0.0) ? 1.0 : W;
   double rhs[NS];
   for (int s = 0; s < NS; ++s) {
@@ -368,31 +403,37 @@ __global__ void __launch_bounds__(32) k_shape_solve(const SolveArgs a) {
     rhs[s] = rc + lam * ref;
   }
   chol_solve<NS>(G, rhs, NS);
-  float x[NS], tr[3];
-  for (int s = 0; s < NS; ++s) {
-    x[s] = (float)rhs[s];
-    SF_IM(a.beta, s, Bp, b) = x[s];
-  }
+  for (int s = 0; s < NS; ++s) SF_IM(a.beta, s, Bp, b) = (float)rhs[s];
   for (int c = 0; c < 3; ++c) {
     double m = Sb[c] / Ws;
     for (int s = 0; s < NS; ++s) m -= SA[c][s] / Ws * rhs[s];
-    tr[c] = (float)m;
-    SF_IM(a.trans, c, Bp, b) = tr[c];
+    SF_IM(a.trans, c, Bp, b) = (float)m;
   }
-  for (int j = 0; j < J; ++j) {
+}
+
+// k_shape_out: one thread per (instance, joint): reference joint (pt/bodyfitter.py:1093-1098)
+// and the skinning transform [R | T0 + T1 x + trans] the statistics pass consumes.
+static __global__ void __launch_bounds__(32) k_shape_out(const SolveArgs a, int NS) {
+  const int b = blockIdx.x * 32 + threadIdx.x;
+  const int j = blockIdx.y;
+  if (b >= a.Bp) return;
+  const int Bp = a.Bp;
+  const int TW = 3 * (1 + NS), RW = 12 + 3 * NS;
+  float x[SMPLFIT_MAX_UNKNOWNS];
+  for (int s = 0; s < NS; ++s) x[s] = SF_IM(a.beta, s, Bp, b);
 #pragma unroll
-    for (int e = 0; e < 9; ++e) SF_IM(a.skin, j * 12 + e, Bp, b) = SF_IM(a.RT, j * RW + e, Bp, b);
-    for (int c = 0; c < 3; ++c) {
-      const float* prow = a.Pext + (size_t)(j * TW + c * (1 + NS)) * Bp + b;
-      const float* trow = a.RT + (size_t)(j * RW + 9 + c * (1 + NS)) * Bp + b;
-      float pj = 0.f, tj = 0.f;
-      for (int s = 0; s < NS; ++s) {
-        pj = fmaf(prow[(size_t)(1 + s) * Bp], x[s], pj);
-        tj = fmaf(trow[(size_t)(1 + s) * Bp], x[s], tj);
-      }
-      SF_IM(a.refj, j * 3 + c, Bp, b) = prow[0] + pj + tr[c];
-      SF_IM(a.skin, j * 12 + 9 + c, Bp, b) = trow[0] + tj + tr[c];
+  for (int e = 0; e < 9; ++e) SF_IM(a.skin, j * 12 + e, Bp, b) = SF_IM(a.RT, j * RW + e, Bp, b);
+  for (int c = 0; c < 3; ++c) {
+    const float tr = SF_IM(a.trans, c, Bp, b);
+    const float* prow = a.Pext + (size_t)(j * TW + c * (1 + NS)) * Bp + b;
+    const float* trow = a.RT + (size_t)(j * RW + 9 + c * (1 + NS)) * Bp + b;
+    float pj = 0.f, tj = 0.f;
+    for (int s = 0; s < NS; ++s) {
+      pj = fmaf(prow[(size_t)(1 + s) * Bp], x[s], pj);
+      tj = fmaf(trow[(size_t)(1 + s) * Bp], x[s], tj);
     }
+    SF_IM(a.refj, j * 3 + c, Bp, b) = prow[0] + pj + tr;
+    SF_IM(a.skin, j * 12 + 9 + c, Bp, b) = trow[0] + tj + tr;
   }
 }
 
