@@ -45,7 +45,7 @@ static FitWs carve(void* base, const smplfit_model_t* m, int64_t B, int has_join
   w.RT = c.take<float>((size_t)J * (12 + 3 * NS) * Bp);
   w.Pext = c.take<float>((size_t)J * 3 * (1 + NS) * Bp);
   w.feat = c.take<float>((size_t)Bp * Kp);
-  w.gpart = c.take<float>((size_t)((n_chunks + 7) / 8) * shape_nacc(NS) * Bp);
+  w.gpart = c.take<float>((size_t)max_shape_partials(m) * shape_nacc(NS) * Bp);
   w.Gd = c.take<double>((size_t)shape_nacc(NS) * Bp);
   w.beta = c.take<float>((size_t)NS * Bp);
   w.trans = c.take<float>(3 * Bp);
@@ -92,6 +92,7 @@ struct FitCtx {
   cudaStream_t st;
   const float *vwT_shape, *jwT_shape;  // shape-stage weights (pt/bodyfitter.py:1018-1028)
   bool has_joints, use_rec;
+  ShapePlan plan;
 };
 
 static void run_gemm(FitCtx& c) {
@@ -111,15 +112,15 @@ static void run_shape(FitCtx& c, const float* R_unused, const float* beta_ref, c
   sa.tT = c.w.tT; sa.vwT = c.vwT_shape; sa.vposedT = c.w.vposedT; sa.RT = c.w.RT;
   sa.shapedirs = m->fit_shapedirs; sa.skin_idx = m->skin_idx; sa.skin_w = m->skin_w; sa.order = m->order;
   sa.partials = c.w.gpart; sa.rec = m->fit_rec; sa.V = m->num_vertices; sa.J = m->num_joints; sa.Bp = c.Bp;
-  sa.skin_k = m->skin_k; sa.chunk_len = m->chunk_len; sa.n_chunks = c.n_chunks; sa.chunks_per_cta = 8;
-  launch_shape_pass(sa, m->fit_ns, c.groups, c.use_rec, c.st);
+  sa.skin_k = m->skin_k; sa.chunk_len = c.plan.chunk_len; sa.n_chunks = c.plan.n_chunks; sa.chunks_per_cta = c.plan.warps;
+  launch_shape_pass(sa, m->fit_ns, c.groups, c.plan, c.st);
   SolveArgs so;
   so.partials = c.w.gpart; so.Pext = c.w.Pext; so.RT = c.w.RT;
   so.tjT = c.has_joints ? c.w.tjT : nullptr; so.jwT = c.jwT_shape;
   so.beta_ref = beta_ref; so.kid_ref = kid_ref;
   so.beta = c.w.beta; so.trans = c.w.trans; so.refj = c.w.refj; so.skin = c.w.skin;
   so.wS = m->fit_wS; so.wsum = m->fit_wsum;
-  so.n_chunks = (c.n_chunks + 7) / 8; so.J = m->num_joints; so.S = m->num_betas; so.Bp = c.Bp; so.B = c.B;
+  so.n_chunks = c.plan.n_partials; so.J = m->num_joints; so.S = m->num_betas; so.Bp = c.Bp; so.B = c.B;
   so.V = m->num_vertices; so.weighted = c.vwT_shape != nullptr;
   so.sa_closed_form = (c.use_rec && c.vwT_shape == nullptr && m->fit_wS != nullptr) ? 1 : 0;
   so.reg = o->beta_regularizer; so.reg2 = o->beta_regularizer2; so.kid_reg = o->kid_regularizer;
@@ -247,7 +248,8 @@ extern "C" int smplfit_fit(const smplfit_model_t* m, int64_t batch, const float*
   c.n_chunks = (m->num_vertices + m->chunk_len - 1) / m->chunk_len;
   c.st = reinterpret_cast<cudaStream_t>(stream);
   c.has_joints = has_joints;
-  c.use_rec = shape_pass_uses_records(m);
+  c.plan = plan_shape_pass(m, c.groups);
+  c.use_rec = c.plan.use_rec;
   c.w = carve(workspace, m, batch, has_joints, vertex_weights != nullptr, joint_weights != nullptr, has_init);
   if (!workspace || c.w.bytes > workspace_bytes) return fail(SMPLFIT_ERR_WORKSPACE, "workspace too small");
   FitWs& w = c.w;
@@ -350,7 +352,8 @@ extern "C" int smplfit_fit_known_pose(const smplfit_model_t* m, int64_t batch, c
   c.n_chunks = (m->num_vertices + m->chunk_len - 1) / m->chunk_len;
   c.st = reinterpret_cast<cudaStream_t>(stream);
   c.has_joints = has_joints;
-  c.use_rec = shape_pass_uses_records(m);
+  c.plan = plan_shape_pass(m, c.groups);
+  c.use_rec = c.plan.use_rec;
   c.w = carve(workspace, m, batch, has_joints, vertex_weights != nullptr, joint_weights != nullptr, 1);
   if (!workspace || c.w.bytes > workspace_bytes) return fail(SMPLFIT_ERR_WORKSPACE, "workspace too small");
   FitWs& w = c.w;

@@ -503,21 +503,22 @@ struct Rec {
 //    sum_k (R_k D_k + n_k T_k[:,1:]) with model constants D_k = sum_v w_vk S_v, n_k = sum_v w_vk,
 //    evaluated in k_shape_solve.
 // ---------------------------------------------------------------------------------------
-template <int NS, bool WEIGHTED>
-__global__ void __launch_bounds__(256) k_shape_pass_rec(const ShapeArgs a) {
+template <int NS, bool WEIGHTED, int WARPS, bool CACHE>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_shape_pass_rec(const ShapeArgs a) {
   extern __shared__ __align__(16) float s_rt[];
   constexpr int RW = 12 + 3 * NS;
   constexpr int TW = 3 * (1 + NS);
   constexpr int REC = Rec<NS>::LEN;
   constexpr int NUSED = WEIGHTED ? ShapeAcc<NS>::N : ShapeAcc<NS>::N_UNWEIGHTED;
   constexpr int OG = 0, OR = ShapeAcc<NS>::NG, OSB = OR + NS, OSA = OSB + 3, OW = OSA + 3 * NS;
+  static_assert(WARPS == 8 || WARPS == 12 || WARPS == 16, "tree reduction expects 8, 12 or 16 warps");
   const int g = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Bp = a.Bp;
   const int b = g * 32 + lane;
   {
     const int n16 = a.J * RW * 8;
-    for (int q = threadIdx.x; q < n16; q += 256) {
+    for (int q = threadIdx.x; q < n16; q += WARPS * 32) {
       const int r = q >> 3, part = q & 7;
       const float* src = a.RT + (size_t)r * Bp + g * 32 + part * 4;
       const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_rt + r * 32 + part * 4);
@@ -527,7 +528,7 @@ __global__ void __launch_bounds__(256) k_shape_pass_rec(const ShapeArgs a) {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
   }
-  const int chunk = blockIdx.x * 8 + warp;
+  const int chunk = blockIdx.x * WARPS + warp;
   const bool active = chunk < a.n_chunks;
   float acc[NUSED];
 #pragma unroll
@@ -544,7 +545,7 @@ __global__ void __launch_bounds__(256) k_shape_pass_rec(const ShapeArgs a) {
       nvp[c] = SF_IM(a.vposedT, i0 * 3 + c, Bp, b);
     }
     if (WEIGHTED) nvw = SF_IM(a.vwT, i0, Bp, b);
-    float Rc[9], Tc[TW];
+    float Rc[CACHE ? 9 : 1], Tc[CACHE ? TW : 1];
     int cj = -1;
     for (int i = i0; i < i1; ++i) {
       const float4 w4 = nw;
@@ -556,12 +557,7 @@ __global__ void __launch_bounds__(256) k_shape_pass_rec(const ShapeArgs a) {
         vp[c] = nvp[c];
       }
       const float wv = nvw;
-      float S[Rec<NS>::NSD4 * 4];
-#pragma unroll
-      for (int q = 0; q < Rec<NS>::NSD4; ++q) {
-        const float4 x = __ldg(reinterpret_cast<const float4*>(rec + 8) + q);
-        S[q * 4] = x.x; S[q * 4 + 1] = x.y; S[q * 4 + 2] = x.z; S[q * 4 + 3] = x.w;
-      }
+      const float* sd = rec + 8;  // this vertex's shapedirs (warp-uniform loads at the point of use)
       if (i + 1 < i1) {  // prefetch the next vertex
         rec += REC;
         nw = __ldg(reinterpret_cast<const float4*>(rec));
@@ -573,19 +569,27 @@ __global__ void __launch_bounds__(256) k_shape_pass_rec(const ShapeArgs a) {
         }
         if (WEIGHTED) nvw = SF_IM(a.vwT, i + 1, Bp, b);
       }
-      if (j4.x != cj) {  // part boundary: refresh the register copy of the dominant joint's rows
-        cj = j4.x;
-        const float* p = s_rt + (size_t)(cj * RW) * 32 + lane;
-#pragma unroll
-        for (int e = 0; e < 9; ++e) Rc[e] = p[e * 32];
-#pragma unroll
-        for (int e = 0; e < TW; ++e) Tc[e] = p[(9 + e) * 32];
-      }
       float Rb[9], Tb[TW];
+      if (CACHE) {
+        if (j4.x != cj) {  // part boundary: refresh the register copy of the dominant joint's rows
+          cj = j4.x;
+          const float* p = s_rt + (size_t)(cj * RW) * 32 + lane;
 #pragma unroll
-      for (int e = 0; e < 9; ++e) Rb[e] = w4.x * Rc[e];
+          for (int e = 0; e < 9; ++e) Rc[e] = p[e * 32];
 #pragma unroll
-      for (int e = 0; e < TW; ++e) Tb[e] = w4.x * Tc[e];
+          for (int e = 0; e < TW; ++e) Tc[e] = p[(9 + e) * 32];
+        }
+#pragma unroll
+        for (int e = 0; e < 9; ++e) Rb[e] = w4.x * Rc[e];
+#pragma unroll
+        for (int e = 0; e < TW; ++e) Tb[e] = w4.x * Tc[e];
+      } else {
+        const float* p = s_rt + (size_t)(j4.x * RW) * 32 + lane;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) Rb[e] = w4.x * p[e * 32];
+#pragma unroll
+        for (int e = 0; e < TW; ++e) Tb[e] = w4.x * p[(9 + e) * 32];
+      }
       const float wk[3] = {w4.y, w4.z, w4.w};
       const int jk[3] = {j4.y, j4.z, j4.w};
 #pragma unroll
@@ -606,7 +610,7 @@ __global__ void __launch_bounds__(256) k_shape_pass_rec(const ShapeArgs a) {
       }
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
-        const float s0 = S[s], s1 = S[NS + s], s2 = S[2 * NS + s];
+        const float s0 = __ldg(sd + s), s1 = __ldg(sd + NS + s), s2 = __ldg(sd + 2 * NS + s);
 #pragma unroll
         for (int c = 0; c < 3; ++c)
           Tb[c * (1 + NS) + 1 + s] =
@@ -632,7 +636,22 @@ __global__ void __launch_bounds__(256) k_shape_pass_rec(const ShapeArgs a) {
       }
     }
   }
-  float* red = s_rt;  // [4][NUSED][32]
+  // deterministic tree reduction over the CTA's warps through shared memory ([8][NUSED][32] max)
+  float* red = s_rt;
+  if (WARPS > 8) {  // fold warps 8.. onto warps 0..WARPS-9
+    __syncthreads();
+    if (warp >= 8) {
+      float* dst = red + (size_t)(warp - 8) * NUSED * 32 + lane;
+#pragma unroll
+      for (int e = 0; e < NUSED; ++e) dst[e * 32] = acc[e];
+    }
+    __syncthreads();
+    if (warp < WARPS - 8) {
+      const float* src = red + (size_t)warp * NUSED * 32 + lane;
+#pragma unroll
+      for (int e = 0; e < NUSED; ++e) acc[e] += src[e * 32];
+    }
+  }
 #pragma unroll 1
   for (int half = 4; half >= 1; half >>= 1) {
     __syncthreads();

@@ -1,4 +1,6 @@
 // Instantiations + launchers of the shape pass and the shape solve for NS = 2..17 unknowns.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "passes.cuh"
 
@@ -31,18 +33,83 @@ bool shape_pass_uses_records(const smplfit_model_t* m) {
   return m->fit_rec != nullptr && m->skin_k <= 4 && rt_smem_bytes(m->num_joints, m->fit_ns) <= 200 * 1024;
 }
 
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+// variant of the record kernel: 0 = 8 warps + register cache, 1 = 12 warps no cache, 2 = 12 warps + cache,
+// 3 = 16 warps no cache (SMPLFIT_B200_SHAPE_VARIANT, for A/B runs)
+static int shape_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SMPLFIT_B200_SHAPE_VARIANT");
+    v = e ? atoi(e) : 0;
+    if (v < 0 || v > 3) v = 0;
+  }
+  return v;
+}
+static int variant_warps(int v) { return v == 0 ? 8 : (v == 3 ? 16 : 12); }
+
+ShapePlan plan_shape_pass(const smplfit_model_t* m, int groups) {
+  ShapePlan p;
+  p.use_rec = shape_pass_uses_records(m);
+  p.warps = p.use_rec ? variant_warps(shape_variant()) : 8;
+  // CTAs per instance group chosen so that the grid fills whole waves of the SM count
+  const int V = m->num_vertices, sms = num_sms();
+  const int c_min = (V + p.warps * 256 - 1) / (p.warps * 256), c_max = (V + p.warps * 32 - 1) / (p.warps * 32);
+  double best = -1.0;
+  int best_c = c_min;
+  for (int c = c_min; c <= c_max; ++c) {
+    const long long ctas = (long long)groups * c;
+    const long long waves = (ctas + sms - 1) / sms;
+    const double eff = (double)ctas / (double)(waves * sms) - 1e-4 * c;  // prefer fewer, longer chunks on ties
+    if (eff > best) { best = eff; best_c = c; }
+  }
+  p.chunk_len = (V + p.warps * best_c - 1) / (p.warps * best_c);
+  p.n_chunks = (V + p.chunk_len - 1) / p.chunk_len;
+  p.n_partials = (p.n_chunks + p.warps - 1) / p.warps;
+  return p;
+}
+
+int max_shape_partials(const smplfit_model_t* m) {
+  const int V = m->num_vertices;
+  return (V + 8 * 32 - 1) / (8 * 32) + 1;
+}
+
+template <int NS, bool WEIGHTED, int WARPS, bool CACHE>
+static void shape_rec_launch(const ShapeArgs& a, int groups, const ShapePlan& p, cudaStream_t st) {
+  const size_t smem_rt = rt_smem_bytes(a.J, NS);
+  const size_t smem_red = (size_t)8 * ShapeAcc<NS>::N * 32 * sizeof(float);
+  const size_t smem = smem_rt > smem_red ? smem_rt : smem_red;
+  cudaFuncSetAttribute(k_shape_pass_rec<NS, WEIGHTED, WARPS, CACHE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  SF_LAUNCH((k_shape_pass_rec<NS, WEIGHTED, WARPS, CACHE>), dim3(p.n_partials, groups), WARPS * 32, smem, st, a);
+}
+
 template <int NS, bool WEIGHTED>
-static void shape_pass_t(const ShapeArgs& sa, int groups, bool use_rec, cudaStream_t st) {
+static void shape_pass_t(const ShapeArgs& sa, int groups, const ShapePlan& p, cudaStream_t st) {
   const size_t smem_rt = rt_smem_bytes(sa.J, NS);
   const size_t smem_red = (size_t)4 * ShapeAcc<NS>::N * 32 * sizeof(float);
   ShapeArgs a = sa;
-  a.chunks_per_cta = 8;
-  dim3 grid((sa.n_chunks + 7) / 8, groups);
-  if (use_rec) {
-    const size_t smem = smem_rt > smem_red ? smem_rt : smem_red;
-    cudaFuncSetAttribute(k_shape_pass_rec<NS, WEIGHTED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    SF_LAUNCH((k_shape_pass_rec<NS, WEIGHTED>), grid, 256, smem, st, a);
-  } else if (smem_rt <= 200 * 1024) {
+  a.chunk_len = p.chunk_len;
+  a.n_chunks = p.n_chunks;
+  a.chunks_per_cta = p.warps;
+  if (p.use_rec) {
+    switch (shape_variant()) {
+      case 1: shape_rec_launch<NS, WEIGHTED, 12, false>(a, groups, p, st); break;
+      case 2: shape_rec_launch<NS, WEIGHTED, 12, true>(a, groups, p, st); break;
+      case 3: shape_rec_launch<NS, WEIGHTED, 16, false>(a, groups, p, st); break;
+      default: shape_rec_launch<NS, WEIGHTED, 8, true>(a, groups, p, st); break;
+    }
+    return;
+  }
+  dim3 grid(p.n_partials, groups);
+  if (smem_rt <= 200 * 1024) {
     const size_t smem = smem_rt > smem_red ? smem_rt : smem_red;
     cudaFuncSetAttribute(k_shape_pass<NS, WEIGHTED, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     SF_LAUNCH((k_shape_pass<NS, WEIGHTED, true>), grid, 256, smem, st, a);
@@ -52,9 +119,9 @@ static void shape_pass_t(const ShapeArgs& sa, int groups, bool use_rec, cudaStre
   }
 }
 
-void launch_shape_pass(const ShapeArgs& a, int ns, int groups, bool use_rec, cudaStream_t st) {
-  if (a.vwT) { SF_NS_SWITCH(ns, (shape_pass_t<NS, true>(a, groups, use_rec, st))); }
-  else { SF_NS_SWITCH(ns, (shape_pass_t<NS, false>(a, groups, use_rec, st))); }
+void launch_shape_pass(const ShapeArgs& a, int ns, int groups, const ShapePlan& p, cudaStream_t st) {
+  if (a.vwT) { SF_NS_SWITCH(ns, (shape_pass_t<NS, true>(a, groups, p, st))); }
+  else { SF_NS_SWITCH(ns, (shape_pass_t<NS, false>(a, groups, p, st))); }
 }
 
 template <int NS>

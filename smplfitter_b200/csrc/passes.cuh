@@ -10,7 +10,14 @@ namespace sf {
 // true when the record kernels apply (<= 4 influences per vertex and the per-joint rows of 32
 // instances fit in shared memory)
 bool shape_pass_uses_records(const smplfit_model_t* m);
-void launch_shape_pass(const ShapeArgs& a, int ns, int groups, bool use_rec, cudaStream_t st);
+// chunking of the shape pass for a given batch: balanced against the SM count at launch time
+struct ShapePlan {
+  bool use_rec;
+  int warps, chunk_len, n_chunks, n_partials;
+};
+ShapePlan plan_shape_pass(const smplfit_model_t* m, int groups);
+int max_shape_partials(const smplfit_model_t* m);
+void launch_shape_pass(const ShapeArgs& a, int ns, int groups, const ShapePlan& p, cudaStream_t st);
 void launch_shape_solve(const SolveArgs& a, double* Gd, int ns, int groups, cudaStream_t st);
 void launch_stats(const StatsArgs& legacy, const StatsRecArgs& rec, int ns, int ref_mode, bool weighted, bool use_rec,
                   int groups, cudaStream_t st);
