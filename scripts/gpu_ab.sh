@@ -13,3 +13,7 @@ except Exception as e:
     print('variant $v failed', e); print(open('gpurun_out/ab_$v.log').read()[-500:])
 PY
 done
+if [ -n "$TEST_VARIANT" ]; then
+  SMPLFIT_B200_SHAPE_VARIANT=$TEST_VARIANT timeout 900 python -m pytest tests -m gpu -q -x --timeout 600 > gpurun_out/pytest_variant.log 2>&1
+  echo "pytest variant $TEST_VARIANT rc=$?"; tail -4 gpurun_out/pytest_variant.log
+fi

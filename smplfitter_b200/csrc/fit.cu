@@ -19,7 +19,7 @@ std::vector<ProfRec> g_prof;
 struct FitWs {
   double* Gd;
   float *mean, *tT, *tjT, *vwT, *jwT, *vposedT, *R, *R2, *RT, *Pext, *feat, *gpart, *beta, *trans, *refj,
-      *skin, *spart, *aT, *ajT, *initjT;
+      *skin, *spart, *aT, *ajT, *initjT, *RT4;
   void* tc_scratch;
   size_t bytes;
 };
@@ -44,6 +44,7 @@ static FitWs carve(void* base, const smplfit_model_t* m, int64_t B, int has_join
   w.R2 = c.take<float>((size_t)9 * J * Bp);
   w.RT = c.take<float>((size_t)J * (12 + 3 * NS) * Bp);
   w.Pext = c.take<float>((size_t)J * 3 * (1 + NS) * Bp);
+  w.RT4 = c.take<float>((size_t)J * quad_rows_ns(NS) * Bp);
   w.feat = c.take<float>((size_t)Bp * Kp);
   w.gpart = c.take<float>((size_t)max_shape_partials(m) * shape_nacc(NS) * Bp);
   w.Gd = c.take<double>((size_t)shape_nacc(NS) * Bp);
@@ -111,7 +112,7 @@ static void run_shape(FitCtx& c, const float* R_unused, const float* beta_ref, c
   ShapeArgs sa;
   sa.tT = c.w.tT; sa.vwT = c.vwT_shape; sa.vposedT = c.w.vposedT; sa.RT = c.w.RT;
   sa.shapedirs = m->fit_shapedirs; sa.skin_idx = m->skin_idx; sa.skin_w = m->skin_w; sa.order = m->order;
-  sa.partials = c.w.gpart; sa.rec = m->fit_rec; sa.V = m->num_vertices; sa.J = m->num_joints; sa.Bp = c.Bp;
+  sa.partials = c.w.gpart; sa.rec = m->fit_rec; sa.RT4 = c.w.RT4; sa.V = m->num_vertices; sa.J = m->num_joints; sa.Bp = c.Bp;
   sa.skin_k = m->skin_k; sa.chunk_len = c.plan.chunk_len; sa.n_chunks = c.plan.n_chunks; sa.chunks_per_cta = c.plan.warps;
   launch_shape_pass(sa, m->fit_ns, c.groups, c.plan, c.st);
   SolveArgs so;
@@ -268,7 +269,7 @@ extern "C" int smplfit_fit(const smplfit_model_t* m, int64_t batch, const float*
 
   RotArgs ra;
   ra.partials = w.spart; ra.tjT = w.tjT; ra.jwT = w.jwT; ra.R_new = w.R; ra.RT = w.RT; ra.Pext = w.Pext;
-  ra.feat = w.feat; ra.t = tables(m); ra.B = c.B; ra.Bp = c.Bp; ra.Kp = c.Kp;
+  ra.feat = w.feat; ra.t = tables(m); ra.B = c.B; ra.Bp = c.Bp; ra.Kp = c.Kp; ra.RT4 = w.RT4;
   // -- first rotation fit (pt/bodyfitter.py:363-394) --
   if (has_init) {
     run_transpose<3>(c, init_vertices, V, m->inv_order, nullptr, w.aT);
@@ -369,7 +370,7 @@ extern "C" int smplfit_fit_known_pose(const smplfit_model_t* m, int64_t batch, c
   RotArgs ra;
   ra.partials = nullptr; ra.tjT = nullptr; ra.ajT = nullptr; ra.aj_const = nullptr; ra.ca0T = nullptr;
   ra.ca0_const = nullptr; ra.jwT = nullptr; ra.R_old = nullptr; ra.R_new = w.R; ra.RT = w.RT; ra.Pext = w.Pext;
-  ra.feat = w.feat; ra.t = tables(m); ra.B = c.B; ra.Bp = c.Bp; ra.Kp = c.Kp;
+  ra.feat = w.feat; ra.t = tables(m); ra.B = c.B; ra.Bp = c.Bp; ra.Kp = c.Kp; ra.RT4 = w.RT4;
   run_rot(c, ra, false);
   run_shape(c, w.R, beta_reg_reference, kid_reg_reference, o);
   // orientations output is not part of this method's result; reuse the scratch R2 for it

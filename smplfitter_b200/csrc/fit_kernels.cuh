@@ -355,6 +355,7 @@ struct ShapeArgs {
   const int32_t* order;
   float* partials;       // [n_chunks][ShapeAcc<NS>::N][Bp]
   const float* rec;      // [V][Rec<NS>::LEN] packed per-vertex records (internal order)
+  const float* RT4;      // [J * Quad<NS>::NQ][Bp] float4 quad layout of the per-joint rows (k_shape_pass_v2)
   int V, J, Bp, skin_k, chunk_len, n_chunks, chunks_per_cta;
 };
 
@@ -487,9 +488,24 @@ __global__ void __launch_bounds__(256) k_shape_pass(const ShapeArgs a) {
 // ---------------------------------------------------------------------------------------
 template <int NS>
 struct Rec {
-  static constexpr int LEN = (8 + 3 * NS + 3) / 4 * 4;
-  static constexpr int NSD4 = (3 * NS + 3) / 4;  // float4 loads covering the shapedirs
+  static constexpr int NSP = (NS + 1) / 2 * 2;            // shape columns padded to even (float2 pairs)
+  static constexpr int LEN = (8 + 3 * NSP + 3) / 4 * 4;   // shapedirs[x][s] at 8 + x * NSP + s
 };
+// Quad layout of the per-joint rows for the packed-math shape pass: row order
+//   0..8 R[c][x], 9 pad, 10..12 T[c][0], 13 pad, 14 + c*NSP + s -> T[c][1+s]; NQ = rows / 4 (padded);
+// in memory [joint][quad][instance][4] so one instance's 4 rows are one 16-byte word.
+template <int NS>
+struct Quad {
+  static constexpr int NSP = Rec<NS>::NSP;
+  static constexpr int ROWS = (14 + 3 * NSP + 3) / 4 * 4;
+  static constexpr int NQ = ROWS / 4;
+};
+__host__ __device__ inline int quad_rows(int ns) { const int nsp = (ns + 1) / 2 * 2; return (14 + 3 * nsp + 3) / 4 * 4; }
+// row index inside a joint's quad block of T_ext[c][col] (col = 0 position, 1+s Jacobian) / R[e]
+__host__ __device__ inline int quad_row_T(int ns, int c, int col) {
+  const int nsp = (ns + 1) / 2 * 2;
+  return col == 0 ? 10 + c : 14 + c * nsp + (col - 1);
+}
 
 // ---------------------------------------------------------------------------------------
 // k_shape_pass_rec<NS>: the shape pass for models with <= 4 influences per vertex whose
@@ -610,7 +626,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_shape_pass_rec(const ShapeArg
       }
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
-        const float s0 = __ldg(sd + s), s1 = __ldg(sd + NS + s), s2 = __ldg(sd + 2 * NS + s);
+        const float s0 = __ldg(sd + s), s1 = __ldg(sd + Rec<NS>::NSP + s), s2 = __ldg(sd + 2 * Rec<NS>::NSP + s);
 #pragma unroll
         for (int c = 0; c < 3; ++c)
           Tb[c * (1 + NS) + 1 + s] =
@@ -671,6 +687,247 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_shape_pass_rec(const ShapeArg
     float* out = a.partials + (size_t)blockIdx.x * ShapeAcc<NS>::N * Bp + b;
 #pragma unroll
     for (int e = 0; e < NUSED; ++e) out[(size_t)e * Bp] = acc[e];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// k_shape_pass_v2<NS>: packed-math shape pass (Blackwell FFMA2, two FP32 FMAs per issue slot).
+// The pass is issue-bound, so the arithmetic is arranged in float2 pairs along the shape index:
+//  * per-joint rows live in shared memory as float4 quads per instance (Quad<NS> order):
+//    one LDS.128 + two FFMA2 blend four rows; the dominant joint's quads are cached in registers;
+//  * jac[c][s,s+1] += (R[c][x], R[c][x]) * shapedirs[x][s,s+1]   (uniform 8-byte record loads);
+//  * G[s][t,t+1] += (jac[c][s], jac[c][s]) * jac[c][t,t+1] for pairs t >= s & ~1
+//    (one extra lower-triangle entry per odd row, dropped when the partials are written).
+// Same outputs and partial layout as k_shape_pass_rec.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 sf_fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 sf_mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+
+template <int NS>
+struct PackedG {
+  static constexpr int H = Rec<NS>::NSP / 2;  // pairs per row
+  __host__ __device__ static constexpr int row_off(int s) {  // first pair slot of row s
+    int o = 0;
+    for (int r = 0; r < s; ++r) o += H - r / 2;
+    return o;
+  }
+  static constexpr int NPAIRS = row_off(NS);
+};
+
+template <int NS, bool WEIGHTED>
+__global__ void __launch_bounds__(256, 1) k_shape_pass_v2(const ShapeArgs a) {
+  extern __shared__ __align__(16) float s_rt[];  // [J][NQ][32] float4
+  constexpr int NSP = Rec<NS>::NSP, H = NSP / 2;
+  constexpr int NQ = Quad<NS>::NQ;
+  constexpr int REC = Rec<NS>::LEN;
+  constexpr int NP = PackedG<NS>::NPAIRS;
+  constexpr int NRED = 2 * NP + 2 * H + 3 + (WEIGHTED ? 6 * H + 1 : 0);  // floats tree-reduced per lane
+  const int g = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Bp = a.Bp;
+  const int b = g * 32 + lane;
+  {
+    // RT4 is [J*NQ][Bp] float4: the CTA's slice of each (joint, quad) row is 32 x 16 B contiguous
+    const int n = a.J * NQ * 32;
+    const float4* src = reinterpret_cast<const float4*>(a.RT4);
+    for (int q = threadIdx.x; q < n; q += 256) {
+      const int r = q >> 5, l = q & 31;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_rt + (size_t)q * 4);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + (size_t)r * Bp + g * 32 + l) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+  }
+  const float4* sq = reinterpret_cast<const float4*>(s_rt);
+  const int chunk = blockIdx.x * 8 + warp;
+  const bool active = chunk < a.n_chunks;
+  float2 G2[NP], r2[H], SA2[WEIGHTED ? 3 * H : 1];
+  float Sb[3], Wsum = 0.f;
+#pragma unroll
+  for (int e = 0; e < NP; ++e) G2[e] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < H; ++e) r2[e] = make_float2(0.f, 0.f);
+  if (WEIGHTED) {
+#pragma unroll
+    for (int e = 0; e < 3 * H; ++e) SA2[e] = make_float2(0.f, 0.f);
+  }
+  Sb[0] = Sb[1] = Sb[2] = 0.f;
+  if (active) {
+    const int i0 = chunk * a.chunk_len, i1 = min(a.V, i0 + a.chunk_len);
+    const float* rec = a.rec + (size_t)i0 * REC;
+    float4 nw = __ldg(reinterpret_cast<const float4*>(rec));
+    int4 nj = __ldg(reinterpret_cast<const int4*>(rec + 4));
+    float nt[3], nvp[3], nvw = 1.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      nt[c] = SF_IM(a.tT, i0 * 3 + c, Bp, b);
+      nvp[c] = SF_IM(a.vposedT, i0 * 3 + c, Bp, b);
+    }
+    if (WEIGHTED) nvw = SF_IM(a.vwT, i0, Bp, b);
+    float4 Cq[NQ];
+    int cj = -1;
+    for (int i = i0; i < i1; ++i) {
+      const float4 w4 = nw;
+      const int4 j4 = nj;
+      float t[3], vp[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        t[c] = nt[c];
+        vp[c] = nvp[c];
+      }
+      const float wv = nvw;
+      const float2* sd2 = reinterpret_cast<const float2*>(rec + 8);  // shapedirs[x][sp] pairs, NSP/2 per x
+      if (i + 1 < i1) {
+        rec += REC;
+        nw = __ldg(reinterpret_cast<const float4*>(rec));
+        nj = __ldg(reinterpret_cast<const int4*>(rec + 4));
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          nt[c] = SF_IM(a.tT, (i + 1) * 3 + c, Bp, b);
+          nvp[c] = SF_IM(a.vposedT, (i + 1) * 3 + c, Bp, b);
+        }
+        if (WEIGHTED) nvw = SF_IM(a.vwT, i + 1, Bp, b);
+      }
+      if (j4.x != cj) {
+        cj = j4.x;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) Cq[q] = sq[(size_t)(cj * NQ + q) * 32 + lane];
+      }
+      // blended rows as pairs: B2[2q] = rows (4q, 4q+1), B2[2q+1] = rows (4q+2, 4q+3)
+      float2 B2[2 * NQ];
+      {
+        const float2 ww = make_float2(w4.x, w4.x);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          B2[2 * q] = sf_mul2(ww, make_float2(Cq[q].x, Cq[q].y));
+          B2[2 * q + 1] = sf_mul2(ww, make_float2(Cq[q].z, Cq[q].w));
+        }
+      }
+      const float wk[3] = {w4.y, w4.z, w4.w};
+      const int jk[3] = {j4.y, j4.z, j4.w};
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (wk[k] != 0.f) {
+          const float2 ww = make_float2(wk[k], wk[k]);
+          const float4* p = sq + (size_t)(jk[k] * NQ) * 32 + lane;
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) {
+            const float4 v = p[q * 32];
+            B2[2 * q] = sf_fma2(ww, make_float2(v.x, v.y), B2[2 * q]);
+            B2[2 * q + 1] = sf_fma2(ww, make_float2(v.z, v.w), B2[2 * q + 1]);
+          }
+        }
+      }
+      // rows: R[c][x] = row c*3+x; T0[c] = row 10+c; jac pairs start at pair index 7
+      auto rowv = [&](int r) -> float { return (r & 1) ? B2[r >> 1].y : B2[r >> 1].x; };
+      float bv[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float pos = fmaf(rowv(c * 3), vp[0], fmaf(rowv(c * 3 + 1), vp[1], fmaf(rowv(c * 3 + 2), vp[2], rowv(10 + c))));
+        bv[c] = t[c] - pos;
+      }
+      float2* J2 = B2 + 7;  // J2[c * H + sp] = (jac[c][2sp], jac[c][2sp+1])
+#pragma unroll
+      for (int x = 0; x < 3; ++x) {
+        float2 S2[H];
+#pragma unroll
+        for (int sp = 0; sp < H; ++sp) S2[sp] = __ldg(sd2 + x * H + sp);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float r = rowv(c * 3 + x);
+          const float2 rr = make_float2(r, r);
+#pragma unroll
+          for (int sp = 0; sp < H; ++sp) J2[c * H + sp] = sf_fma2(rr, S2[sp], J2[c * H + sp]);
+        }
+      }
+      if (WEIGHTED) Wsum += wv;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float wb = WEIGHTED ? wv * bv[c] : bv[c];
+        Sb[c] += wb;
+        const float2 bb = make_float2(wb, wb);
+        if (WEIGHTED) {
+          const float2 w2 = make_float2(wv, wv);
+#pragma unroll
+          for (int sp = 0; sp < H; ++sp) SA2[c * H + sp] = sf_fma2(w2, J2[c * H + sp], SA2[c * H + sp]);
+        }
+#pragma unroll
+        for (int sp = 0; sp < H; ++sp) r2[sp] = sf_fma2(J2[c * H + sp], bb, r2[sp]);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          const float js = (s & 1) ? J2[c * H + (s >> 1)].y : J2[c * H + (s >> 1)].x;
+          const float wj = WEIGHTED ? wv * js : js;
+          const float2 jj = make_float2(wj, wj);
+#pragma unroll
+          for (int q = s / 2; q < H; ++q) {
+            G2[PackedG<NS>::row_off(s) + q - s / 2] = sf_fma2(jj, J2[c * H + q], G2[PackedG<NS>::row_off(s) + q - s / 2]);
+          }
+        }
+      }
+    }
+  }
+  // ---- tree reduction over the 8 warps (float view of the accumulators) ----
+  float* red = s_rt;
+  auto fold = [&](bool write, int slot) {
+    float* base = red + (size_t)slot * NRED * 32 + lane;
+    int o = 0;
+#pragma unroll
+    for (int e = 0; e < NP; ++e) {
+      if (write) { base[(o) * 32] = G2[e].x; base[(o + 1) * 32] = G2[e].y; }
+      else { G2[e].x += base[(o) * 32]; G2[e].y += base[(o + 1) * 32]; }
+      o += 2;
+    }
+#pragma unroll
+    for (int e = 0; e < H; ++e) {
+      if (write) { base[(o) * 32] = r2[e].x; base[(o + 1) * 32] = r2[e].y; }
+      else { r2[e].x += base[(o) * 32]; r2[e].y += base[(o + 1) * 32]; }
+      o += 2;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (write) base[o * 32] = Sb[c]; else Sb[c] += base[o * 32];
+      ++o;
+    }
+    if (WEIGHTED) {
+#pragma unroll
+      for (int e = 0; e < 3 * H; ++e) {
+        if (write) { base[(o) * 32] = SA2[e].x; base[(o + 1) * 32] = SA2[e].y; }
+        else { SA2[e].x += base[(o) * 32]; SA2[e].y += base[(o + 1) * 32]; }
+        o += 2;
+      }
+      if (write) base[o * 32] = Wsum; else Wsum += base[o * 32];
+    }
+  };
+#pragma unroll 1
+  for (int half = 4; half >= 1; half >>= 1) {
+    __syncthreads();
+    if (warp >= half && warp < 2 * half) fold(true, warp - half);
+    __syncthreads();
+    if (warp < half) fold(false, warp);
+  }
+  if (warp == 0) {
+    // standard partial layout [G upper | r | Sb | SA | W]
+    float* out = a.partials + (size_t)blockIdx.x * ShapeAcc<NS>::N * Bp + b;
+    int o = 0;
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+      for (int t2 = s; t2 < NS; ++t2) {
+        const float2 gp = G2[PackedG<NS>::row_off(s) + t2 / 2 - s / 2];
+        out[(size_t)(o++) * Bp] = (t2 & 1) ? gp.y : gp.x;
+      }
+#pragma unroll
+    for (int s = 0; s < NS; ++s) out[(size_t)(o++) * Bp] = (s & 1) ? r2[s >> 1].y : r2[s >> 1].x;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[(size_t)(o++) * Bp] = Sb[c];
+    if (WEIGHTED) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int s = 0; s < NS; ++s) out[(size_t)(o++) * Bp] = (s & 1) ? SA2[c * H + (s >> 1)].y : SA2[c * H + (s >> 1)].x;
+      out[(size_t)o * Bp] = Wsum;
+    }
   }
 }
 
@@ -769,14 +1026,7 @@ __global__ void __launch_bounds__(256) k_stats_rec(const StatsRecArgs a) {
         x[c] = nx[c];
       }
       const float wv = nvw;
-      float S[Rec<NS>::NSD4 * 4];
-      if (REF == 1) {
-#pragma unroll
-        for (int qq = 0; qq < Rec<NS>::NSD4; ++qq) {
-          const float4 y = __ldg(reinterpret_cast<const float4*>(rec + 8) + qq);
-          S[qq * 4] = y.x; S[qq * 4 + 1] = y.y; S[qq * 4 + 2] = y.z; S[qq * 4 + 3] = y.w;
-        }
-      }
+      const float* sd = rec + 8;
       if (i + 1 < i1) {
         rec += REC;
         if (REF == 1) {
@@ -798,7 +1048,7 @@ __global__ void __launch_bounds__(256) k_stats_rec(const StatsRecArgs a) {
         for (int c = 0; c < 3; ++c) {
           float y = x[c];
 #pragma unroll
-          for (int s = 0; s < NS; ++s) y = fmaf(S[c * NS + s], beta[s], y);
+          for (int s = 0; s < NS; ++s) y = fmaf(__ldg(sd + c * Rec<NS>::NSP + s), beta[s], y);
           vs[c] = y;
         }
         if (j4.x != cj) {

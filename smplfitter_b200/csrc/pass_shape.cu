@@ -44,17 +44,17 @@ static int num_sms() {
 }
 
 // variant of the record kernel: 0 = 8 warps + register cache, 1 = 12 warps no cache, 2 = 12 warps + cache,
-// 3 = 16 warps no cache (SMPLFIT_B200_SHAPE_VARIANT, for A/B runs)
+// 3 = 16 warps no cache, 4 = packed FFMA2 math (SMPLFIT_B200_SHAPE_VARIANT, for A/B runs)
 static int shape_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("SMPLFIT_B200_SHAPE_VARIANT");
     v = e ? atoi(e) : 0;
-    if (v < 0 || v > 3) v = 0;
+    if (v < 0 || v > 4) v = 0;
   }
   return v;
 }
-static int variant_warps(int v) { return v == 0 ? 8 : (v == 3 ? 16 : 12); }
+static int variant_warps(int v) { return (v == 0 || v == 4) ? 8 : (v == 3 ? 16 : 12); }
 
 ShapePlan plan_shape_pass(const smplfit_model_t* m, int groups) {
   ShapePlan p;
@@ -92,6 +92,15 @@ static void shape_rec_launch(const ShapeArgs& a, int groups, const ShapePlan& p,
 }
 
 template <int NS, bool WEIGHTED>
+static void shape_v2_launch(const ShapeArgs& a, int groups, const ShapePlan& p, cudaStream_t st) {
+  const size_t smem_rt = (size_t)a.J * Quad<NS>::NQ * 32 * 16;
+  const size_t smem_red = (size_t)4 * (2 * PackedG<NS>::NPAIRS + 8 * (Rec<NS>::NSP / 2) + 4) * 32 * sizeof(float);
+  const size_t smem = smem_rt > smem_red ? smem_rt : smem_red;
+  cudaFuncSetAttribute(k_shape_pass_v2<NS, WEIGHTED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  SF_LAUNCH((k_shape_pass_v2<NS, WEIGHTED>), dim3(p.n_partials, groups), 256, smem, st, a);
+}
+
+template <int NS, bool WEIGHTED>
 static void shape_pass_t(const ShapeArgs& sa, int groups, const ShapePlan& p, cudaStream_t st) {
   const size_t smem_rt = rt_smem_bytes(sa.J, NS);
   const size_t smem_red = (size_t)4 * ShapeAcc<NS>::N * 32 * sizeof(float);
@@ -104,6 +113,7 @@ static void shape_pass_t(const ShapeArgs& sa, int groups, const ShapePlan& p, cu
       case 1: shape_rec_launch<NS, WEIGHTED, 12, false>(a, groups, p, st); break;
       case 2: shape_rec_launch<NS, WEIGHTED, 12, true>(a, groups, p, st); break;
       case 3: shape_rec_launch<NS, WEIGHTED, 16, false>(a, groups, p, st); break;
+      case 4: shape_v2_launch<NS, WEIGHTED>(a, groups, p, st); break;
       default: shape_rec_launch<NS, WEIGHTED, 8, true>(a, groups, p, st); break;
     }
     return;

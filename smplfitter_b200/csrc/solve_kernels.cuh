@@ -14,6 +14,8 @@ namespace sf {
 #define SF_IM(ptr, row, Bp, b) (ptr)[(size_t)(row) * (size_t)(Bp) + (size_t)(b)]
 #endif
 
+__host__ __device__ inline int quad_rows_ns(int ns) { const int nsp = (ns + 1) / 2 * 2; return (14 + 3 * nsp + 3) / 4 * 4; }
+
 struct TreeTables {
   const int32_t* parents;
   const int32_t* part_kind;
@@ -81,6 +83,7 @@ struct RotArgs {
   const float* R_old;      // [9J][Bp] or null (identity)
   float* R_new;            // [9J][Bp]
   float* RT;               // [J*(12+3NS)][Bp] or null (skip the shape front)
+  float* RT4;              // optional quad layout of the same rows (fit_kernels.cuh Quad<NS>), or null
   float* Pext;             // [J*3*(1+NS)][Bp]
   float* feat;             // [Bp][Kp]
   TreeTables t;
@@ -201,6 +204,10 @@ static __global__ void __launch_bounds__(32) k_rot_fit(const RotArgs a) {
   for (int e = 0; e < 9; ++e) SF_IM(a.R_new, i * 9 + e, Bp, b) = Rn[e];
 }
 
+__device__ __forceinline__ void rt4_store(float* RT4, int j, int nq, int row, int Bp, int b, float v) {
+  RT4[(((size_t)(j * nq + (row >> 2))) * Bp + b) * 4 + (row & 3)] = v;
+}
+
 // k_front_rel: one thread per (instance, joint): relative rotation -> pose features, and the
 // rotation rows of the [R | T_ext] table (pt/bodyfitter.py:869-876, :913).
 static __global__ void __launch_bounds__(32) k_front_rel(const RotArgs a) {
@@ -214,6 +221,16 @@ static __global__ void __launch_bounds__(32) k_front_rel(const RotArgs a) {
   for (int e = 0; e < 9; ++e) {
     Rj[e] = SF_IM(a.R_new, j * 9 + e, Bp, b);
     SF_IM(a.RT, j * RW + e, Bp, b) = Rj[e];
+  }
+  if (a.RT4 != nullptr) {
+    const int rows = quad_rows_ns(NS), nq = rows / 4, nsp = (NS + 1) / 2 * 2;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) rt4_store(a.RT4, j, nq, e, Bp, b, Rj[e]);
+    rt4_store(a.RT4, j, nq, 9, Bp, b, 0.f);
+    rt4_store(a.RT4, j, nq, 13, Bp, b, 0.f);
+    for (int c = 0; c < 3; ++c)
+      for (int sx = NS; sx < nsp; ++sx) rt4_store(a.RT4, j, nq, 14 + c * nsp + sx, Bp, b, 0.f);
+    for (int r = 14 + 3 * nsp; r < rows; ++r) rt4_store(a.RT4, j, nq, r, Bp, b, 0.f);
   }
   if (j > 0) {
     const int par = a.t.parents[j];
@@ -258,8 +275,13 @@ static __global__ void __launch_bounds__(32) k_front_fk(const RotArgs a) {
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
+      const float tv = P[j * 3 + c] - (Rj[c * 3] * j0 + Rj[c * 3 + 1] * j1 + Rj[c * 3 + 2] * j2);
       SF_IM(a.Pext, j * TW + c * (1 + NS) + s, Bp, b) = P[j * 3 + c];
-      SF_IM(a.RT, j * RW + 9 + c * (1 + NS) + s, Bp, b) = P[j * 3 + c] - (Rj[c * 3] * j0 + Rj[c * 3 + 1] * j1 + Rj[c * 3 + 2] * j2);
+      SF_IM(a.RT, j * RW + 9 + c * (1 + NS) + s, Bp, b) = tv;
+      if (a.RT4 != nullptr) {
+        const int nsp = (NS + 1) / 2 * 2;
+        rt4_store(a.RT4, j, quad_rows_ns(NS) / 4, s == 0 ? 10 + c : 14 + c * nsp + (s - 1), Bp, b, tv);
+      }
     }
   }
 }

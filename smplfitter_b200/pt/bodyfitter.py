@@ -78,7 +78,8 @@ class BodyFitter(nn.Module):
         self.register_buffer('_t_fit_wS', torch.tensor(np.ascontiguousarray(wS)), persistent=False)
         self.register_buffer('_t_fit_wsum', torch.tensor(w_np.astype(np.float64).sum(axis=0)), persistent=False)
         K = body_model._dims['skin_k']
-        self._rec_len = (8 + 3 * ns + 3) // 4 * 4
+        nsp = (ns + 1) // 2 * 2
+        self._rec_len = (8 + 3 * nsp + 3) // 4 * 4
         if K <= 4:
             idx = body_model._t_skin_idx.cpu().numpy()
             ww = body_model._t_skin_w.cpu().numpy()
@@ -92,7 +93,8 @@ class BodyFitter(nn.Module):
             rec = np.zeros((V, self._rec_len), np.float32)
             rec[:, 0:4] = w4
             rec[:, 4:8] = idx4.view(np.float32)
-            rec[:, 8:8 + 3 * ns] = sd_np.reshape(V, 3 * ns)
+            for x in range(3):
+                rec[:, 8 + x * nsp:8 + x * nsp + ns] = sd_np[:, x, :]
             self.register_buffer('_t_fit_rec', torch.tensor(np.ascontiguousarray(rec[order])), persistent=False)
         else:
             self._t_fit_rec = None
