@@ -1026,7 +1026,15 @@ __global__ void __launch_bounds__(256) k_stats_rec(const StatsRecArgs a) {
         x[c] = nx[c];
       }
       const float wv = nvw;
-      const float* sd = rec + 8;
+      float S[3 * Rec<NS>::NSP];
+      if (REF == 1) {
+#pragma unroll
+        for (int qq = 0; qq < 3 * Rec<NS>::NSP / 2; ++qq) {
+          const float2 y = __ldg(reinterpret_cast<const float2*>(rec + 8) + qq);
+          S[2 * qq] = y.x;
+          S[2 * qq + 1] = y.y;
+        }
+      }
       if (i + 1 < i1) {
         rec += REC;
         if (REF == 1) {
@@ -1048,7 +1056,7 @@ __global__ void __launch_bounds__(256) k_stats_rec(const StatsRecArgs a) {
         for (int c = 0; c < 3; ++c) {
           float y = x[c];
 #pragma unroll
-          for (int s = 0; s < NS; ++s) y = fmaf(__ldg(sd + c * Rec<NS>::NSP + s), beta[s], y);
+          for (int s = 0; s < NS; ++s) y = fmaf(S[c * Rec<NS>::NSP + s], beta[s], y);
           vs[c] = y;
         }
         if (j4.x != cj) {

@@ -43,18 +43,18 @@ static int num_sms() {
   return n;
 }
 
-// variant of the record kernel: 0 = 8 warps + register cache, 1 = 12 warps no cache, 2 = 12 warps + cache,
-// 3 = 16 warps no cache, 4 = packed FFMA2 math (SMPLFIT_B200_SHAPE_VARIANT, for A/B runs)
+// variant of the record kernel (SMPLFIT_B200_SHAPE_VARIANT, for A/B runs): 4 = packed FFMA2 math (default),
+// 0 = scalar FFMA, 8 warps + register cache, 1 = scalar FFMA, 12 warps, no cache
 static int shape_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("SMPLFIT_B200_SHAPE_VARIANT");
-    v = e ? atoi(e) : 0;
-    if (v < 0 || v > 4) v = 0;
+    v = e ? atoi(e) : 4;
+    if (v < 0 || v > 4) v = 4;
   }
   return v;
 }
-static int variant_warps(int v) { return (v == 0 || v == 4) ? 8 : (v == 3 ? 16 : 12); }
+static int variant_warps(int v) { return v == 1 ? 12 : 8; }
 
 ShapePlan plan_shape_pass(const smplfit_model_t* m, int groups) {
   ShapePlan p;
@@ -111,8 +111,6 @@ static void shape_pass_t(const ShapeArgs& sa, int groups, const ShapePlan& p, cu
   if (p.use_rec) {
     switch (shape_variant()) {
       case 1: shape_rec_launch<NS, WEIGHTED, 12, false>(a, groups, p, st); break;
-      case 2: shape_rec_launch<NS, WEIGHTED, 12, true>(a, groups, p, st); break;
-      case 3: shape_rec_launch<NS, WEIGHTED, 16, false>(a, groups, p, st); break;
       case 4: shape_v2_launch<NS, WEIGHTED>(a, groups, p, st); break;
       default: shape_rec_launch<NS, WEIGHTED, 8, true>(a, groups, p, st); break;
     }

@@ -141,7 +141,12 @@ def test_fit_vs_oracle_midsize():
     tv = fw['vertices'] + torch.from_numpy((rs.randn(B, 6890, 3) * 0.003).astype(np.float32)).cuda()
     tj = fw['joints']
     kw = dict(num_iter=3, beta_regularizer=1.0, requested_keys=['pose_rotvecs', 'relative_orientations'])
+    assert torch.isfinite(tv).all() and torch.isfinite(tj).all(), 'forward produced non-finite values'
+    tv_before = tv.clone()
     out = {k: v.cpu().numpy() for k, v in fitter.fit(tv, tj, **kw).items()}
+    assert torch.equal(tv, tv_before), 'fit() modified its input'
+    for k, v in out.items():
+        assert np.isfinite(v).all(), k
     om = oracle_np.OracleModel(modeldata.initialize(mname), mname)
     sel = np.array([0, 1, 31, 32, 33, 63, 64, 69])
     ora = oracle_np.OracleFitter(om).fit(tv.cpu().numpy()[sel], tj.cpu().numpy()[sel], **kw)
@@ -163,7 +168,8 @@ def test_fit_roundtrip_full_batch():
     """BASELINE config 2 size (B = 4096, num_iter = 3): size-independent properties --
     round-trip accuracy as in the reference's own test (tests/test_fitter_common.py:31-72,
     mean vertex error < 5e-3 m), batch-composition invariance (instance k of the big batch
-    equals the same instance fitted in a batch of 8), determinism."""
+    equals the same instance fitted in a batch of 8 up to fp32 rounding), bit-exact determinism of
+    repeated calls."""
     bm, fitter = get_model('smpl')
     g = torch.Generator(device='cuda').manual_seed(5)
     B = 4096
@@ -180,7 +186,9 @@ def test_fit_roundtrip_full_batch():
     sel = torch.tensor([0, 7, 100, 2047, 2048, 3000, 4094, 4095], device='cuda')
     small = fitter.fit(fw['vertices'][sel], fw['joints'][sel], **kw)
     for k in ('pose_rotvecs', 'shape_betas', 'trans'):
-        assert torch.equal(small[k], fit[k][sel]), k
+        # chunking is balanced against the SM count per batch size, so summation order (not the
+        # math) differs between batch compositions: agreement to fp32 rounding
+        assert (small[k] - fit[k][sel]).abs().max().item() < 1e-5, k
     again = fitter.fit(fw['vertices'], fw['joints'], **kw)
     for k in ('pose_rotvecs', 'shape_betas', 'trans'):
         assert torch.equal(again[k], fit[k]), k
