@@ -3,12 +3,15 @@
 // (pt/bodymodel.py:293, pt/bodyfitter.py:913-916) -- the one genuinely dense GEMM of the path:
 // (3V x P) x (P x B), P = 9 (J-1).
 //
-// sm_100a design: D[128 instances][128 vertex-coords] accumulates in TMEM (tcgen05.mma,
-// cta_group::1, kind::tf32, M = 128, N = 128, K = 8 per instruction).  Both operands are
-// K-major fp32 tiles of 128 rows x 32 floats (= one 128-byte swizzle atom row) brought in by TMA
-// (cp.async.bulk.tensor.2d, SWIZZLE_128B) through a 3-stage mbarrier ring.  Instances are the
-// M side so that in the epilogue TMEM lane == instance: each warp stores 32 consecutive
-// instances of one v_posed^T row = one coalesced 128-byte line per column.
+// sm_100a design: persistent CTAs (one per SM) loop over 128-instance x 256-row tiles.
+// D[128][256] accumulates in TMEM (tcgen05.mma, cta_group::1, kind::tf32, M = 128, N = 256, K = 8
+// per instruction); the 512 TMEM columns hold two accumulators so the epilogue of tile i overlaps
+// the MMAs of tile i+1.  Both operands are K-major fp32 tiles of 32 floats per row (= one
+// 128-byte swizzle atom row) brought in by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) through a
+// 2-stage mbarrier ring (96 KB per stage).  Instances are the M side so that in the epilogue TMEM
+// lane == instance: each warp stores 32 consecutive instances of one v_posed^T row = one
+// coalesced 128-byte line per column.  Tiles are ordered so CTAs working at the same time share
+// the posedirs tile in L2.
 //
 // Precision: TF32 keeps 10 mantissa bits, not enough for the 1e-4 parity gate, so every
 // operand is split x = hi + lo (hi = x with the low 13 mantissa bits cleared, lo = x - hi) and
@@ -16,8 +19,8 @@
 // relative, i.e. fp32-GEMM grade).  posedirs hi/lo are model constants; the per-call feature
 // split is a tiny elementwise kernel.
 //
-// Warp roles (128 threads): warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane),
-// warp 2 = TMEM allocator; all four warps run the epilogue (warp w owns TMEM lanes 32w..32w+31).
+// Warp roles (256 threads): warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane),
+// warp 2 = TMEM allocator, warps 4-7 = epilogue (warp 4+q owns TMEM lanes 32q..32q+31).
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -29,19 +32,24 @@ namespace sf {
 
 namespace {
 
-constexpr int TILE_M = 128;   // instances per CTA tile (TMEM lanes)
-constexpr int TILE_N = 128;   // v_posed^T rows (vertex coordinates) per CTA tile
+constexpr int TILE_M = 128;   // instances per tile (TMEM lanes)
+constexpr int TILE_N = 256;   // v_posed^T rows (vertex coordinates) per tile
 constexpr int TILE_K = 32;    // floats per k-block = 128 bytes = swizzle atom width
-constexpr int STAGES = 3;
-constexpr int TILE_BYTES = TILE_M * TILE_K * 4;  // 16 KB per operand tile
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;      // F_hi, F_lo, P_hi, P_lo
+constexpr int STAGES = 2;
+constexpr int A_BYTES = TILE_M * TILE_K * 4;     // 16 KB per feature tile
+constexpr int B_BYTES = TILE_N * TILE_K * 4;     // 32 KB per posedirs tile
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // F_hi, F_lo, P_hi, P_lo = 96 KB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr uint32_t TMEM_COLS = 128;
+constexpr uint32_t TMEM_COLS = 512;              // two 128 x 256 fp32 accumulators
+constexpr int THREADS = 256;                     // warp 0 TMA, 1 MMA, 2 TMEM alloc, 4-7 epilogue
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -102,18 +110,17 @@ struct TcMaps {
   CUtensorMap f_hi, f_lo, p_hi, p_lo;
 };
 
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(THREADS, 1)
 k_vposed_tc(const __grid_constant__ TcMaps maps, const float* __restrict__ vt, float* __restrict__ out, int M_rows,
-            int Bp, int k_blocks) {
+            int Bp, int k_blocks, int tiles_m, int total_tiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty = full + STAGES;
-  uint64_t* accum_full = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+  uint64_t* acc_full = empty + STAGES;   // [2] accumulator ready for the epilogue
+  uint64_t* acc_empty = acc_full + 2;    // [2] accumulator drained (4 epilogue warps arrive)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * TILE_N;  // v_posed^T rows
-  const int b0 = blockIdx.y * TILE_M;  // instances
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.f_hi) : "memory");
@@ -126,7 +133,10 @@ k_vposed_tc(const __grid_constant__ TcMaps maps, const float* __restrict__ vt, f
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(accum_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -140,66 +150,94 @@ k_vposed_tc(const __grid_constant__ TcMaps maps, const float* __restrict__ vt, f
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 && lane == 0) {
-    // ---- TMA producer ----
-    for (int kb = 0; kb < k_blocks; ++kb) {
-      const int s = kb % STAGES;
-      const uint32_t ph = (kb / STAGES) & 1;
-      mbar_wait(&empty[s], ph ^ 1);
-      uint8_t* st = smem + s * STAGE_BYTES;
-      mbar_expect_tx(&full[s], STAGE_BYTES);
-      tma_load_2d(st + 0 * TILE_BYTES, &maps.f_hi, &full[s], kb * TILE_K, b0);
-      tma_load_2d(st + 1 * TILE_BYTES, &maps.f_lo, &full[s], kb * TILE_K, b0);
-      tma_load_2d(st + 2 * TILE_BYTES, &maps.p_hi, &full[s], kb * TILE_K, n0);
-      tma_load_2d(st + 3 * TILE_BYTES, &maps.p_lo, &full[s], kb * TILE_K, n0);
-    }
-  } else if (warp == 1 && lane == 0) {
-    // ---- MMA issuer ----
-    uint32_t acc = 0;
-    for (int kb = 0; kb < k_blocks; ++kb) {
-      const int s = kb % STAGES;
-      const uint32_t ph = (kb / STAGES) & 1;
-      mbar_wait(&full[s], ph);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
-      const uint64_t fhi = make_desc(base), flo = make_desc(base + TILE_BYTES);
-      const uint64_t phi = make_desc(base + 2 * TILE_BYTES), plo = make_desc(base + 3 * TILE_BYTES);
-#pragma unroll
-      for (int k = 0; k < TILE_K / 8; ++k) {
-        const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 32 bytes per K = 8 step inside the swizzle atom
-        mma_tf32(tmem_base, flo + adv, phi + adv, acc);  // small terms first
-        acc = 1;
-        mma_tf32(tmem_base, fhi + adv, plo + adv, 1);
-        mma_tf32(tmem_base, fhi + adv, phi + adv, 1);
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---- TMA producer: persistent over this CTA's tiles ----
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int b0 = (tile % tiles_m) * TILE_M, n0 = (tile / tiles_m) * TILE_N;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* st = smem + s * STAGE_BYTES;
+          mbar_expect_tx(&full[s], STAGE_BYTES);
+          tma_load_2d(st, &maps.f_hi, &full[s], kb * TILE_K, b0);
+          tma_load_2d(st + A_BYTES, &maps.f_lo, &full[s], kb * TILE_K, b0);
+          tma_load_2d(st + 2 * A_BYTES, &maps.p_hi, &full[s], kb * TILE_K, n0);
+          tma_load_2d(st + 2 * A_BYTES + B_BYTES, &maps.p_lo, &full[s], kb * TILE_K, n0);
+        }
       }
-      mma_commit(&empty[s]);  // frees the smem stage when these MMAs retire
     }
-    mma_commit(accum_full);
-  }
-  __syncwarp();
-
-  // ---- epilogue: TMEM -> registers -> + v_template -> coalesced global stores ----
-  mbar_wait(accum_full, 0);
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const int b = b0 + warp * 32 + lane;
-#pragma unroll 1
-  for (int c0 = 0; c0 < TILE_N; c0 += 32) {
-    uint32_t r[32];
-    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---- MMA issuer ----
+      int it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        const int as = tcount & 1;
+        const uint32_t aph = (tcount >> 1) & 1;
+        mbar_wait(&acc_empty[as], aph ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * TILE_N);
+        uint32_t acc = 0;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+          const uint64_t fhi = make_desc(base), flo = make_desc(base + A_BYTES);
+          const uint64_t phi = make_desc(base + 2 * A_BYTES), plo = make_desc(base + 2 * A_BYTES + B_BYTES);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int n = n0 + c0 + j;
-      if (n < M_rows && b < Bp) out[(size_t)n * Bp + b] = __uint_as_float(r[j]) + __ldg(vt + n);
+          for (int k = 0; k < TILE_K / 8; ++k) {
+            const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 32 bytes per K = 8 step inside the swizzle atom
+            mma_tf32(d_tmem, flo + adv, phi + adv, acc);  // small terms first
+            acc = 1;
+            mma_tf32(d_tmem, fhi + adv, plo + adv, 1);
+            mma_tf32(d_tmem, fhi + adv, phi + adv, 1);
+          }
+          mma_commit(&empty[s]);  // frees the smem stage when these MMAs retire
+        }
+        mma_commit(&acc_full[as]);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ---- epilogue warps: TMEM -> registers -> + v_template -> coalesced global stores ----
+    const int q = warp - 4;  // TMEM lane quadrant (warp id % 4)
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const int as = tcount & 1;
+      const uint32_t aph = (tcount >> 1) & 1;
+      const int b0 = (tile % tiles_m) * TILE_M, n0 = (tile / tiles_m) * TILE_N;
+      mbar_wait(&acc_full[as], aph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int b = b0 + q * 32 + lane;
+#pragma unroll 1
+      for (int c0 = 0; c0 < TILE_N; c0 += 32) {
+        if (n0 + c0 >= M_rows) break;
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TILE_N + c0);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = n0 + c0 + j;
+          if (n < M_rows && b < Bp) out[(size_t)n * Bp + b] = __uint_as_float(r[j]) + __ldg(vt + n);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -239,12 +277,12 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-bool make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols) {
+bool make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {cols * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)TILE_K, (cuuint32_t)TILE_M};
+  cuuint32_t box[2] = {(cuuint32_t)TILE_K, (cuuint32_t)box_rows};
   cuuint32_t elem[2] = {1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, elem,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -274,8 +312,8 @@ bool vposed_tc_run(const smplfit_model_t* m, const float* feat, float* vposedT, 
   float* hi = reinterpret_cast<float*>(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
   float* lo = hi + (size_t)Bt * Kt;
   TcMaps maps;
-  if (!make_map(&maps.f_hi, hi, Bt, Kt) || !make_map(&maps.f_lo, lo, Bt, Kt) ||
-      !make_map(&maps.p_hi, m->posedirs_hi, rows, Kt) || !make_map(&maps.p_lo, m->posedirs_lo, rows, Kt))
+  if (!make_map(&maps.f_hi, hi, Bt, Kt, TILE_M) || !make_map(&maps.f_lo, lo, Bt, Kt, TILE_M) ||
+      !make_map(&maps.p_hi, m->posedirs_hi, rows, Kt, TILE_N) || !make_map(&maps.p_lo, m->posedirs_lo, rows, Kt, TILE_N))
     return false;
   static bool attr_set = false;
   if (!attr_set) {
@@ -288,8 +326,16 @@ bool vposed_tc_run(const smplfit_model_t* m, const float* feat, float* vposedT, 
   const size_t n = (size_t)Bt * Kt;
   // rows [Bp, Bt) of the split features are never written by k_split_feat's bound: clear via the kernel itself
   SF_LAUNCH(k_split_feat, (unsigned)((n + 255) / 256), 256, 0, st, feat, Bp, Kp, Kt, hi, lo);
-  dim3 grid((rows + TILE_N - 1) / TILE_N, Bt / TILE_M);
-  SF_LAUNCH(k_vposed_tc, grid, 128, SMEM_BYTES, st, maps, m->v_template_fit, vposedT, rows, Bp, Kt / TILE_K);
+  const int tiles_m = Bt / TILE_M, tiles_n = (rows + TILE_N - 1) / TILE_N, total = tiles_m * tiles_n;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  const int grid = total < sms ? total : sms;
+  SF_LAUNCH(k_vposed_tc, grid, THREADS, SMEM_BYTES, st, maps, m->v_template_fit, vposedT, rows, Bp, Kt / TILE_K, tiles_m,
+            total);
   return true;
 }
 
