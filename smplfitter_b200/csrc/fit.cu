@@ -19,7 +19,8 @@ std::vector<ProfRec> g_prof;
 struct FitWs {
   double* Gd;
   float *mean, *tT, *tjT, *vwT, *jwT, *vposedT, *R, *R2, *RT, *Pext, *feat, *gpart, *beta, *trans, *refj,
-      *skin, *spart, *aT, *ajT, *initjT, *RT4;
+      *skin, *spart, *aT, *ajT, *initjT, *RT4, *zpart, *scale;
+  double* Zd;
   void* tc_scratch;
   size_t bytes;
 };
@@ -57,6 +58,9 @@ static FitWs carve(void* base, const smplfit_model_t* m, int64_t B, int has_join
   w.aT = need_aT ? c.take<float>((size_t)3 * V * Bp) : nullptr;
   w.ajT = need_aT ? c.take<float>((size_t)3 * J * Bp) : nullptr;
   w.initjT = has_init ? c.take<float>((size_t)3 * J * Bp) : nullptr;
+  w.zpart = c.take<float>((size_t)scale_chunks(m) * (NS + 5) * Bp);
+  w.Zd = c.take<double>((size_t)(NS + 5) * Bp);
+  w.scale = c.take<float>(Bp);
   w.tc_scratch = c.take<char>(vposed_tc_scratch_bytes(m, (int)Bp));
   w.bytes = c.off + 256;
   return w;
@@ -104,9 +108,8 @@ static void run_gemm(FitCtx& c) {
             3 * m->num_vertices, c.Kp, c.Bp, c.w.vposedT);
 }
 
-static void run_shape(FitCtx& c, const float* R_unused, const float* beta_ref, const float* kid_ref,
+static void run_shape(FitCtx& c, int scale_mode, const float* beta_ref, const float* kid_ref,
                       const smplfit_fit_opts_t* o) {
-  (void)R_unused;
   const smplfit_model_t* m = c.m;
   run_gemm(c);
   ShapeArgs sa;
@@ -125,7 +128,17 @@ static void run_shape(FitCtx& c, const float* R_unused, const float* beta_ref, c
   so.V = m->num_vertices; so.weighted = c.vwT_shape != nullptr;
   so.sa_closed_form = (c.use_rec && c.vwT_shape == nullptr && m->fit_wS != nullptr) ? 1 : 0;
   so.reg = o->beta_regularizer; so.reg2 = o->beta_regularizer2; so.kid_reg = o->kid_regularizer;
-  launch_shape_solve(so, c.w.Gd, m->fit_ns, c.groups, c.st);
+  so.scale_mode = scale_mode; so.zpartials = c.w.zpart; so.n_zchunks = scale_chunks(m);
+  so.scale_reg = o->scale_regularizer; so.scale_out = c.w.scale;
+  if (scale_mode != 0) {
+    ShapeArgs sz = sa;
+    sz.partials = c.w.zpart;
+    launch_scale_pass(sz, m->fit_ns, scale_mode, c.groups, c.st);
+    // the scale pass writes its own partial layout: point the solve at it
+    launch_shape_solve_scale(so, c.w.Gd, c.w.Zd, m->fit_ns, c.groups, c.st);
+  } else {
+    launch_shape_solve(so, c.w.Gd, m->fit_ns, c.groups, c.st);
+  }
 }
 
 // statistics of (targets, reference) for the rotation stage; ref_mode as in k_stats
@@ -233,8 +246,8 @@ extern "C" int smplfit_fit(const smplfit_model_t* m, int64_t batch, const float*
     return fail(SMPLFIT_ERR_ARG, "missing required pointer");
   if (batch <= 0 || batch > (1 << 24)) return fail(SMPLFIT_ERR_ARG, "batch out of range");
   if (o->num_iter < 1) return fail(SMPLFIT_ERR_ARG, "num_iter must be >= 1");
-  if (o->scale_mode != 0 || out_scale_corr != nullptr)
-    return fail(SMPLFIT_ERR_UNSUPPORTED, "scale_target / scale_fit are not implemented on the CUDA path yet");
+  if (o->scale_mode < 0 || o->scale_mode > 2) return fail(SMPLFIT_ERR_ARG, "bad scale_mode");
+  if (o->scale_mode != 0 && !out_scale_corr) return fail(SMPLFIT_ERR_ARG, "scale_corr output required");
   if ((o->enable_kid != 0) != (m->fit_ns == m->num_betas + 1))
     return fail(SMPLFIT_ERR_ARG, "enable_kid does not match the fitter tables");
   const bool has_init = init_vertices != nullptr;
@@ -294,8 +307,8 @@ extern "C" int smplfit_fit(const smplfit_model_t* m, int64_t batch, const float*
   // -- alternate shape and rotation fits (pt/bodyfitter.py:399-461) --
   const float* R_final = w.R;
   for (int it = 0; it < o->num_iter; ++it) {
-    run_shape(c, w.R, beta_reg_reference, kid_reg_reference, o);
     const bool last = (it == o->num_iter - 1);
+    run_shape(c, last ? o->scale_mode : 0, beta_reg_reference, kid_reg_reference, o);
     if (last && !o->final_adjust_rots) break;
     float* aT_out = has_joints ? nullptr : w.aT;
     run_stats(c, 1, w.refj, nullptr, aT_out);
@@ -311,6 +324,7 @@ extern "C" int smplfit_fit(const smplfit_model_t* m, int64_t batch, const float*
       AdjustArgs aa;
       aa.partials = w.spart; aa.tjT = w.tjT; aa.ajT = aj; aa.refj = w.refj; aa.jwT = w.jwT; aa.R_prev = w.R;
       aa.beta = w.beta; aa.trans = w.trans; aa.R_out = w.R2; aa.t = tables(m); aa.Bp = c.Bp;
+      aa.scale = o->scale_mode ? w.scale : nullptr; aa.scale_mode = o->scale_mode;
       SF_LAUNCH(k_adjust_solve, c.Bp / 32, 32, 0, c.st, aa);
       R_final = w.R2;
     }
@@ -322,6 +336,8 @@ extern "C" int smplfit_fit(const smplfit_model_t* m, int64_t batch, const float*
   oa.pose_rotvecs = o->want_pose_rotvecs ? out_pose_rotvecs : nullptr;
   oa.shape_betas = out_shape_betas; oa.out_trans = out_trans; oa.orientations = out_orientations;
   oa.rel_orient = out_rel_orientations; oa.kid = o->enable_kid ? out_kid_factor : nullptr;
+  oa.scale = o->scale_mode ? w.scale : nullptr; oa.scale_corr = o->scale_mode ? out_scale_corr : nullptr;
+  oa.scale_mode = o->scale_mode;
   oa.J = J; oa.S = m->num_betas; oa.NS = m->fit_ns; oa.B = c.B; oa.Bp = c.Bp;
   SF_LAUNCH(k_output, c.Bp / 32, 32, 0, c.st, oa);
   SF_CHECK_LAST();
@@ -339,8 +355,8 @@ extern "C" int smplfit_fit_known_pose(const smplfit_model_t* m, int64_t batch, c
   if (!o || !glob_rotmats || !target_vertices || !out_shape_betas || !out_trans)
     return fail(SMPLFIT_ERR_ARG, "missing required pointer");
   if (batch <= 0 || batch > (1 << 24)) return fail(SMPLFIT_ERR_ARG, "batch out of range");
-  if (o->scale_mode != 0 || out_scale_corr != nullptr)
-    return fail(SMPLFIT_ERR_UNSUPPORTED, "scale_target / scale_fit are not implemented on the CUDA path yet");
+  if (o->scale_mode < 0 || o->scale_mode > 2) return fail(SMPLFIT_ERR_ARG, "bad scale_mode");
+  if (o->scale_mode != 0 && !out_scale_corr) return fail(SMPLFIT_ERR_ARG, "scale_corr output required");
   if ((o->enable_kid != 0) != (m->fit_ns == m->num_betas + 1))
     return fail(SMPLFIT_ERR_ARG, "enable_kid does not match the fitter tables");
   const bool has_joints = target_joints != nullptr;
@@ -372,13 +388,16 @@ extern "C" int smplfit_fit_known_pose(const smplfit_model_t* m, int64_t batch, c
   ra.ca0_const = nullptr; ra.jwT = nullptr; ra.R_old = nullptr; ra.R_new = w.R; ra.RT = w.RT; ra.Pext = w.Pext;
   ra.feat = w.feat; ra.t = tables(m); ra.B = c.B; ra.Bp = c.Bp; ra.Kp = c.Kp; ra.RT4 = w.RT4;
   run_rot(c, ra, false);
-  run_shape(c, w.R, beta_reg_reference, kid_reg_reference, o);
+  run_shape(c, o->scale_mode, beta_reg_reference, kid_reg_reference, o);
   // orientations output is not part of this method's result; reuse the scratch R2 for it
   OutputArgs oa;
   oa.R_final = w.R; oa.R_rel_src = w.R; oa.beta = w.beta; oa.trans = w.trans; oa.mean = w.mean;
   oa.parents = m->parents; oa.pose_rotvecs = nullptr; oa.shape_betas = out_shape_betas; oa.out_trans = out_trans;
   oa.orientations = nullptr; oa.rel_orient = out_rel_orientations;
   oa.kid = o->enable_kid ? out_kid_factor : nullptr;
+  // pt/bodyfitter.py:644: the mean is added back unscaled here; scale_corr is still reported
+  oa.scale = o->scale_mode ? w.scale : nullptr; oa.scale_corr = o->scale_mode ? out_scale_corr : nullptr;
+  oa.scale_mode = 0;
   oa.J = J; oa.S = m->num_betas; oa.NS = m->fit_ns; oa.B = c.B; oa.Bp = c.Bp;
   SF_LAUNCH(k_output, c.Bp / 32, 32, 0, c.st, oa);
   SF_CHECK_LAST();

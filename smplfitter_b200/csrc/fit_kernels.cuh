@@ -1119,4 +1119,81 @@ __global__ void __launch_bounds__(256) k_stats_rec(const StatsRecArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// k_scale_pass<NS, MODE>: extra accumulations of the final shape solve when a scale factor is
+// estimated (pt/bodyfitter.py:1171-1176): the design matrix gets one more column z, with
+// z = -target (MODE 1, scale_target) or z = pos (MODE 2, scale_fit).  Per (chunk, instance):
+//   Gz[s] = sum w z.jac[:,s],  Gzz = sum w z.z,  rz = sum w z.b,  SAz[c] = sum w z_c.
+// Only used once per fit and only in scale mode, so it simply recomputes pos / jac with global
+// reads of the per-joint rows (no shared-memory staging).  Layout of the partials: [Gz | Gzz | rz | SAz].
+// ---------------------------------------------------------------------------------------
+template <int NS, int MODE>
+__global__ void __launch_bounds__(128) k_scale_pass(const ShapeArgs a) {
+  constexpr int RW = 12 + 3 * NS;
+  constexpr int TW = 3 * (1 + NS);
+  constexpr int NZ = NS + 5;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int chunk = warp % a.n_chunks, g = warp / a.n_chunks;
+  const int Bp = a.Bp;
+  if (g * 32 >= Bp) return;
+  const int b = g * 32 + lane;
+  float Gz[NS], Gzz = 0.f, rz = 0.f, SAz[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int s = 0; s < NS; ++s) Gz[s] = 0.f;
+  const int i0 = chunk * a.chunk_len, i1 = min(a.V, i0 + a.chunk_len);
+  for (int i = i0; i < i1; ++i) {
+    const int v = __ldg(a.order + i);
+    float Rb[9], Tb[TW];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) Rb[e] = 0.f;
+#pragma unroll
+    for (int e = 0; e < TW; ++e) Tb[e] = 0.f;
+    for (int k = 0; k < a.skin_k; ++k) {
+      const int j = __ldg(a.skin_idx + v * a.skin_k + k);
+      const float w = __ldg(a.skin_w + v * a.skin_k + k);
+      if (w == 0.f) continue;
+      const float* p = a.RT + (size_t)(j * RW) * Bp + b;
+#pragma unroll
+      for (int e = 0; e < 9; ++e) Rb[e] = fmaf(w, p[(size_t)e * Bp], Rb[e]);
+#pragma unroll
+      for (int e = 0; e < TW; ++e) Tb[e] = fmaf(w, p[(size_t)(9 + e) * Bp], Tb[e]);
+    }
+    float vp[3], t[3], pos[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      vp[c] = SF_IM(a.vposedT, i * 3 + c, Bp, b);
+      t[c] = SF_IM(a.tT, i * 3 + c, Bp, b);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      pos[c] = fmaf(Rb[c * 3], vp[0], fmaf(Rb[c * 3 + 1], vp[1], fmaf(Rb[c * 3 + 2], vp[2], Tb[c * (1 + NS)])));
+    const float* sd = a.shapedirs + (size_t)v * 3 * NS;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const float s0 = __ldg(sd + s), s1 = __ldg(sd + NS + s), s2 = __ldg(sd + 2 * NS + s);
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        Tb[c * (1 + NS) + 1 + s] = fmaf(Rb[c * 3], s0, fmaf(Rb[c * 3 + 1], s1, fmaf(Rb[c * 3 + 2], s2, Tb[c * (1 + NS) + 1 + s])));
+    }
+    const float w = a.vwT ? SF_IM(a.vwT, i, Bp, b) : 1.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float z = (MODE == 1) ? -t[c] : pos[c];
+      const float wz = w * z;
+      SAz[c] += wz;
+      Gzz = fmaf(wz, z, Gzz);
+      rz = fmaf(wz, t[c] - pos[c], rz);
+#pragma unroll
+      for (int s = 0; s < NS; ++s) Gz[s] = fmaf(wz, Tb[c * (1 + NS) + 1 + s], Gz[s]);
+    }
+  }
+  float* out = a.partials + (size_t)chunk * NZ * Bp + b;
+#pragma unroll
+  for (int s = 0; s < NS; ++s) out[(size_t)s * Bp] = Gz[s];
+  out[(size_t)NS * Bp] = Gzz;
+  out[(size_t)(NS + 1) * Bp] = rz;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) out[(size_t)(NS + 2 + c) * Bp] = SAz[c];
+}
+
 }  // namespace sf

@@ -1,0 +1,57 @@
+// Instantiations + launchers of the scale-mode kernels (scale_target / scale_fit, final solve only).
+#include "common.cuh"
+#include "passes.cuh"
+
+namespace sf {
+
+#define SF_NS_SWITCH(NSV, CALL)                      \
+  switch (NSV) {                                     \
+    case 2: { constexpr int NS = 2; CALL; } break;   \
+    case 3: { constexpr int NS = 3; CALL; } break;   \
+    case 4: { constexpr int NS = 4; CALL; } break;   \
+    case 5: { constexpr int NS = 5; CALL; } break;   \
+    case 6: { constexpr int NS = 6; CALL; } break;   \
+    case 7: { constexpr int NS = 7; CALL; } break;   \
+    case 8: { constexpr int NS = 8; CALL; } break;   \
+    case 9: { constexpr int NS = 9; CALL; } break;   \
+    case 10: { constexpr int NS = 10; CALL; } break; \
+    case 11: { constexpr int NS = 11; CALL; } break; \
+    case 12: { constexpr int NS = 12; CALL; } break; \
+    case 13: { constexpr int NS = 13; CALL; } break; \
+    case 14: { constexpr int NS = 14; CALL; } break; \
+    case 15: { constexpr int NS = 15; CALL; } break; \
+    case 16: { constexpr int NS = 16; CALL; } break; \
+    case 17: { constexpr int NS = 17; CALL; } break; \
+    default: break;                                  \
+  }
+
+int scale_chunks(const smplfit_model_t* m) { return (m->num_vertices + 127) / 128; }
+
+template <int NS>
+static void scale_pass_t(const ShapeArgs& sa, int mode, int groups, cudaStream_t st) {
+  ShapeArgs a = sa;
+  a.chunk_len = 128;
+  a.n_chunks = (a.V + 127) / 128;
+  const long long warps = (long long)a.n_chunks * groups;
+  const int blocks = (int)((warps + 3) / 4);
+  if (mode == 1) SF_LAUNCH((k_scale_pass<NS, 1>), blocks, 128, 0, st, a);
+  else SF_LAUNCH((k_scale_pass<NS, 2>), blocks, 128, 0, st, a);
+}
+
+void launch_scale_pass(const ShapeArgs& a, int ns, int mode, int groups, cudaStream_t st) {
+  SF_NS_SWITCH(ns, (scale_pass_t<NS>(a, mode, groups, st)));
+}
+
+template <int NS>
+static void solve_scale_t(const SolveArgs& so, double* Gd, double* Zd, int groups, cudaStream_t st) {
+  SF_LAUNCH(k_gram_entries<NS>, dim3(groups, ShapeAcc<NS>::N), 32, 0, st, so, Gd);
+  SF_LAUNCH(k_scale_entries<NS>, dim3(groups, NS + 5), 32, 0, st, so, Zd);
+  SF_LAUNCH(k_shape_solve_scale<NS>, groups, 32, 0, st, so, (const double*)Gd, (const double*)Zd);
+  SF_LAUNCH(k_shape_out, dim3(groups, so.J), 32, 0, st, so, NS);
+}
+
+void launch_shape_solve_scale(const SolveArgs& a, double* Gd, double* Zd, int ns, int groups, cudaStream_t st) {
+  SF_NS_SWITCH(ns, (solve_scale_t<NS>(a, Gd, Zd, groups, st)));
+}
+
+}  // namespace sf

@@ -19,6 +19,10 @@ ShapePlan plan_shape_pass(const smplfit_model_t* m, int groups);
 int max_shape_partials(const smplfit_model_t* m);
 void launch_shape_pass(const ShapeArgs& a, int ns, int groups, const ShapePlan& p, cudaStream_t st);
 void launch_shape_solve(const SolveArgs& a, double* Gd, int ns, int groups, cudaStream_t st);
+// scale modes (final solve only): extra vertex pass + (NS+1)-unknown solve (pass_scale.cu)
+int scale_chunks(const smplfit_model_t* m);
+void launch_scale_pass(const ShapeArgs& a, int ns, int mode, int groups, cudaStream_t st);
+void launch_shape_solve_scale(const SolveArgs& a, double* Gd, double* Zd, int ns, int groups, cudaStream_t st);
 void launch_stats(const StatsArgs& legacy, const StatsRecArgs& rec, int ns, int ref_mode, bool weighted, bool use_rec,
                   int groups, cudaStream_t st);
 }  // namespace sf

@@ -47,7 +47,7 @@ __device__ __forceinline__ void load3_or_const(const float* p, const float* cst,
 //   sum w (t-ct)(a-ca)^T = M + st (ca0-ca)^T + (ct0-ct) sa^T + W (ct0-ct)(ca0-ca)^T
 __device__ inline void part_covariance(const float* partials, const int32_t* seg_begin, int part, int Bp, int b,
                                        const float* ct0, const float* ca0, const float* ct, const float* ca,
-                                       float* A) {
+                                       float* A, float mM = 1.f, float mst = 1.f, float msa = 1.f) {
   double acc[16];
 #pragma unroll
   for (int e = 0; e < 16; ++e) acc[e] = 0.0;
@@ -63,7 +63,8 @@ __device__ inline void part_covariance(const float* partials, const int32_t* seg
   for (int r = 0; r < 3; ++r)
 #pragma unroll
     for (int c = 0; c < 3; ++c)
-      A[r * 3 + c] = (float)acc[r * 3 + c] + (float)acc[9 + r] * da[c] + dt[r] * (float)acc[12 + c] + W * dt[r] * da[c];
+      A[r * 3 + c] = mM * (float)acc[r * 3 + c] + mst * (float)acc[9 + r] * da[c] + dt[r] * msa * (float)acc[12 + c] +
+                     W * dt[r] * da[c];
 }
 
 // ---------------------------------------------------------------------------------------
@@ -315,6 +316,11 @@ struct SolveArgs {
   const double* wsum;    // (J)      n_k = sum_v w_vk
   int n_chunks, J, S, Bp, B, V, weighted;
   int sa_closed_form;    // 1: partials hold only [G | r | Sb]; SA from (wS, wsum), W = V
+  int scale_mode;        // 0 none, 1 scale_target, 2 scale_fit (extra unknown, pt/bodyfitter.py:1171-1176)
+  const float* zpartials;  // [n_zchunks][NS+5][Bp] from k_scale_pass
+  int n_zchunks;
+  float scale_reg;
+  float* scale_out;      // [Bp] scale_corr
   float reg, reg2, kid_reg;
 };
 
@@ -433,6 +439,101 @@ __global__ void __launch_bounds__(32) k_shape_solve(const SolveArgs a, const dou
   }
 }
 
+// k_scale_entries<NS>: the NS+5 extra normal-equation entries of the scale column
+// [Gz(NS) | Gzz | rz | SAz(3)]: chunk partials of k_scale_pass + the joint block, in double.
+template <int NS>
+__global__ void __launch_bounds__(32) k_scale_entries(const SolveArgs a, double* __restrict__ Zd) {
+  constexpr int NZ = NS + 5;
+  constexpr int TW = 3 * (1 + NS);
+  const int b = blockIdx.x * 32 + threadIdx.x;
+  const int e = blockIdx.y;
+  if (b >= a.Bp) return;
+  const int Bp = a.Bp, J = a.J;
+  double acc = 0.0;
+  for (int q = 0; q < a.n_zchunks; ++q) acc += (double)a.zpartials[((size_t)q * NZ + e) * Bp + b];
+  if (a.tjT != nullptr) {
+    for (int j = 0; j < J; ++j) {
+      const double w = a.jwT ? (double)SF_IM(a.jwT, j, Bp, b) : 1.0;
+      for (int c = 0; c < 3; ++c) {
+        const float* prow = a.Pext + (size_t)(j * TW + c * (1 + NS)) * Bp + b;
+        const double tj = (double)SF_IM(a.tjT, j * 3 + c, Bp, b), pj = (double)prow[0];
+        const double z = (a.scale_mode == 1) ? -tj : pj;
+        if (e < NS) acc += w * z * (double)prow[(size_t)(1 + e) * Bp];
+        else if (e == NS) acc += w * z * z;
+        else if (e == NS + 1) acc += w * z * (tj - pj);
+        else if (e - NS - 2 == c) acc += w * z;
+      }
+    }
+  }
+  Zd[(size_t)e * Bp + b] = acc;
+}
+
+// k_shape_solve_scale<NS>: the (NS+1)-unknown variant of k_shape_solve (betas [+ kid] + scale
+// delta); outputs the *undivided* unknowns like the reference's result dict plus scale_corr = 1 + delta.
+template <int NS>
+__global__ void __launch_bounds__(32) k_shape_solve_scale(const SolveArgs a, const double* __restrict__ Gd,
+                                                          const double* __restrict__ Zd) {
+  constexpr int NG = NS * (NS + 1) / 2;
+  constexpr int N1 = NS + 1;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.Bp) return;
+  const int Bp = a.Bp;
+  double G[N1][N1], r[N1], SA[3][N1], Sb[3];
+  {
+    int o = 0;
+    for (int s = 0; s < NS; ++s)
+      for (int t = s; t < NS; ++t) {
+        const double v = Gd[(size_t)o * Bp + b];
+        G[s][t] = v;
+        G[t][s] = v;
+        ++o;
+      }
+    for (int s = 0; s < NS; ++s) r[s] = Gd[(size_t)(o++) * Bp + b];
+    for (int c = 0; c < 3; ++c) Sb[c] = Gd[(size_t)(o++) * Bp + b];
+    for (int c = 0; c < 3; ++c)
+      for (int s = 0; s < NS; ++s) SA[c][s] = Gd[(size_t)(o++) * Bp + b];
+  }
+  for (int s = 0; s < NS; ++s) {
+    G[s][NS] = Zd[(size_t)s * Bp + b];
+    G[NS][s] = G[s][NS];
+  }
+  G[NS][NS] = Zd[(size_t)NS * Bp + b];
+  r[NS] = Zd[(size_t)(NS + 1) * Bp + b];
+  for (int c = 0; c < 3; ++c) SA[c][NS] = Zd[(size_t)(NS + 2 + c) * Bp + b];
+  const double W = Gd[(size_t)(NG + NS + 3 + 3 * NS) * Bp + b];
+  const double Ws = (W == 0.0) ? 1.0 : W;
+  double rhs[N1];
+  for (int s = 0; s < N1; ++s) {
+    double rc = r[s];
+    for (int c = 0; c < 3; ++c) rc -= SA[c][s] * Sb[c] / Ws;
+    for (int t = 0; t < N1; ++t) {
+      double g = G[s][t];
+      for (int c = 0; c < 3; ++c) g -= SA[c][s] * SA[c][t] / Ws;
+      G[s][t] = g;
+    }
+    double lam = (s < 2) ? (double)a.reg2 : (double)a.reg;
+    double ref = 0.0;
+    if (s < a.S) {
+      if (a.beta_ref != nullptr && b < a.B) ref = (double)a.beta_ref[(size_t)b * a.S + s];
+    } else if (s < NS) {
+      lam = (double)a.kid_reg;
+      if (a.kid_ref != nullptr && b < a.B) ref = (double)a.kid_ref[b];
+    } else {
+      lam = (double)a.scale_reg;
+    }
+    G[s][s] += lam;
+    rhs[s] = rc + lam * ref;
+  }
+  chol_solve<N1>(G, rhs, N1);
+  for (int s = 0; s < NS; ++s) SF_IM(a.beta, s, Bp, b) = (float)rhs[s];
+  a.scale_out[b] = (float)rhs[NS] + 1.f;
+  for (int c = 0; c < 3; ++c) {
+    double m = Sb[c] / Ws;
+    for (int s = 0; s < N1; ++s) m -= SA[c][s] / Ws * rhs[s];
+    SF_IM(a.trans, c, Bp, b) = (float)m;
+  }
+}
+
 // k_shape_out: one thread per (instance, joint): reference joint (pt/bodyfitter.py:1093-1098)
 // and the skinning transform [R | T0 + T1 x + trans] the statistics pass consumes.
 static __global__ void __launch_bounds__(32) k_shape_out(const SolveArgs a, int NS) {
@@ -442,7 +543,8 @@ static __global__ void __launch_bounds__(32) k_shape_out(const SolveArgs a, int 
   const int Bp = a.Bp;
   const int TW = 3 * (1 + NS), RW = 12 + 3 * NS;
   float x[SMPLFIT_MAX_UNKNOWNS];
-  for (int s = 0; s < NS; ++s) x[s] = SF_IM(a.beta, s, Bp, b);
+  const float inv_sc = (a.scale_mode == 2) ? 1.f / a.scale_out[b] : 1.f;  // pt/bodyfitter.py:1293-1304
+  for (int s = 0; s < NS; ++s) x[s] = SF_IM(a.beta, s, Bp, b) * inv_sc;
 #pragma unroll
   for (int e = 0; e < 9; ++e) SF_IM(a.skin, j * 12 + e, Bp, b) = SF_IM(a.RT, j * RW + e, Bp, b);
   for (int c = 0; c < 3; ++c) {
@@ -473,6 +575,8 @@ struct AdjustArgs {
   const float* beta;      // [NS][Bp]
   const float* trans;     // [3][Bp]
   float* R_out;           // [9J][Bp]
+  const float* scale;     // [Bp] scale_corr or null
+  int scale_mode;         // 1: targets scaled (pt/bodyfitter.py:465-480), 2: reference scaled (:481-496)
   TreeTables t;
   int Bp;
 };
@@ -484,13 +588,18 @@ static __global__ void __launch_bounds__(32) k_adjust_solve(const AdjustArgs a) 
   const int TW = 3 * (1 + NS);
   float x[SMPLFIT_MAX_UNKNOWNS];
   for (int s = 0; s < NS; ++s) x[s] = SF_IM(a.beta, s, Bp, b);
+  const float sc = (a.scale != nullptr) ? a.scale[b] : 1.f;
+  const float st_t = (a.scale_mode == 1) ? sc : 1.f;  // scale of the target side
+  const float st_a = (a.scale_mode == 2) ? sc : 1.f;  // scale of the reference side
+  float trv[3];
+  for (int c = 0; c < 3; ++c) trv[c] = SF_IM(a.trans, c, Bp, b);
   float pos[SMPLFIT_MAX_JOINTS * 3], rest[SMPLFIT_MAX_JOINTS * 3];
   for (int j = 0; j < J; ++j)
     for (int c = 0; c < 3; ++c) {
       const float* Jt = a.t.Jt_ext + (size_t)j * TW + c * (1 + NS);
       float v = __ldg(Jt);
       for (int s = 0; s < NS; ++s) v = fmaf(__ldg(Jt + 1 + s), x[s], v);
-      rest[j * 3 + c] = v;
+      rest[j * 3 + c] = (a.scale_mode == 2) ? v * sc : v;  // j = j * scale_corr (pt/bodyfitter.py:1449-1450)
     }
   for (int i = 0; i < J; ++i) {
     const int par = a.t.parents[i];
@@ -515,16 +624,27 @@ static __global__ void __launch_bounds__(32) k_adjust_solve(const AdjustArgs a) 
 #pragma unroll
       for (int e = 0; e < 9; ++e) Rn[e] = SF_IM(a.R_prev, i * 9 + e, Bp, b);
     } else {
+      // the statistics were accumulated on the unscaled data about (ct0, ca0) = (tj_i, refj_i); they
+      // are bilinear, so scaling the targets (mode 1) or the reference about trans (mode 2) just
+      // rescales them: M' = sc M, st' = st_t st, sa' = st_a sa, centres scale alike.
       float ct0[3], ca[3], A[9];
       load3(a.tjT, i, Bp, b, ct0);
       load3(a.refj, i, Bp, b, ca);
-      part_covariance(a.partials, a.t.part_seg_begin, i, Bp, b, ct0, ca, pos + i * 3, ca, A);
+      for (int c = 0; c < 3; ++c) {
+        ct0[c] *= st_t;
+        ca[c] = st_a * ca[c] + (1.f - st_a) * trv[c];
+      }
+      part_covariance(a.partials, a.t.part_seg_begin, i, Bp, b, ct0, ca, pos + i * 3, ca, A, st_t * st_a, st_t, st_a);
       const int n = a.t.cas_count[i];
       const int32_t* cas = a.t.cas_table + i * a.t.max_cas;
       for (int k = 0; k < n; ++k) {
         float tj[3], aj[3];
         load3(a.tjT, cas[k], Bp, b, tj);
         load3(a.ajT, cas[k], Bp, b, aj);
+        for (int c = 0; c < 3; ++c) {
+          tj[c] *= st_t;
+          aj[c] = st_a * aj[c] + (1.f - st_a) * trv[c];
+        }
         const float w = a.jwT ? SF_IM(a.jwT, cas[k], Bp, b) : 1.f;
 #pragma unroll
         for (int r = 0; r < 3; ++r)
@@ -560,6 +680,9 @@ struct OutputArgs {
   float* orientations;   // (B,J,3,3)
   float* rel_orient;     // (B,J,3,3) or null
   float* kid;            // (B) or null
+  const float* scale;    // [Bp] or null
+  float* scale_corr;     // (B) or null
+  int scale_mode;
   int J, S, NS, B, Bp;
 };
 
@@ -569,7 +692,13 @@ static __global__ void __launch_bounds__(32) k_output(const OutputArgs a) {
   const int J = a.J, Bp = a.Bp;
   for (int s = 0; s < a.S; ++s) a.shape_betas[(size_t)b * a.S + s] = SF_IM(a.beta, s, Bp, b);
   if (a.kid != nullptr) a.kid[b] = SF_IM(a.beta, a.S, Bp, b);
-  for (int c = 0; c < 3; ++c) a.out_trans[(size_t)b * 3 + c] = SF_IM(a.trans, c, Bp, b) + SF_IM(a.mean, c, Bp, b);
+  {
+    // pt/bodyfitter.py:513-519: the target mean is added back (scaled in the scale modes)
+    const float sc = (a.scale != nullptr) ? a.scale[b] : 1.f;
+    const float f = (a.scale_mode == 1) ? sc : (a.scale_mode == 2 ? 1.f / sc : 1.f);
+    for (int c = 0; c < 3; ++c) a.out_trans[(size_t)b * 3 + c] = SF_IM(a.trans, c, Bp, b) + SF_IM(a.mean, c, Bp, b) * f;
+    if (a.scale_corr != nullptr) a.scale_corr[b] = sc;
+  }
   for (int j = 0; j < J; ++j) {
     float R[9];
 #pragma unroll

@@ -184,8 +184,7 @@ class BodyFitter(nn.Module):
             raise ValueError('Only one of estim_scale_target and estim_scale_fit can be True')
         if share_beta:
             raise NotImplementedError('share_beta is not implemented on the CUDA path (SURVEY.md 8f-2)')
-        if scale_target or scale_fit:
-            raise NotImplementedError('scale_target / scale_fit are not implemented on the CUDA path yet')
+        scale_mode = 1 if scale_target else (2 if scale_fit else 0)
         bm = self.body_model
         dev = bm.v_template.device
         _native.require_cuda(bm.v_template, 'the body model')
@@ -203,11 +202,14 @@ class BodyFitter(nn.Module):
                    relative_orientations=new(B, J, 3, 3))
         rotvecs = new(B, 3 * J) if 'pose_rotvecs' in requested_keys else None
         kid = new(B) if self.enable_kid else None
+        scale_corr = new(B) if scale_mode else None
         if B == 0:
             if rotvecs is not None:
                 out['pose_rotvecs'] = rotvecs
             if kid is not None:
                 out['kid_factor'] = kid
+            if scale_corr is not None:
+                out['scale_corr'] = scale_corr
             return out
         init_v = init_j = init_o = None
         if initial_pose_rotvecs is not None or initial_shape_betas is not None:
@@ -221,7 +223,7 @@ class BodyFitter(nn.Module):
             kid_ref = torch.as_tensor(initial_kid_factor, dtype=torch.float32, device=dev).reshape(-1).expand(B).contiguous()
         o = self._opts(num_iter, final_adjust_rots, requested_keys,
                        self._shape_weights_rule(tj, vw, jw), beta_regularizer, beta_regularizer2,
-                       kid_regularizer, 0, scale_regularizer)
+                       kid_regularizer, scale_mode, scale_regularizer)
         L = _native.lib()
         s = self._struct()
         ws_bytes = L.smplfit_fit_workspace_bytes(C.byref(s), B, C.byref(o), int(tj is not None),
@@ -234,14 +236,16 @@ class BodyFitter(nn.Module):
             _native.check(L.smplfit_fit(
                 C.byref(s), B, p(tv), p(tj), p(vw), p(jw), p(beta_ref), p(kid_ref), p(init_v), p(init_j),
                 p(init_o), C.byref(o), p(rotvecs), p(out['shape_betas']), p(out['trans']),
-                p(out['orientations']), p(out['relative_orientations']), p(kid), 0, ws.data_ptr(), ws_bytes,
-                _native.stream_ptr(dev),
+                p(out['orientations']), p(out['relative_orientations']), p(kid), p(scale_corr), ws.data_ptr(),
+                ws_bytes, _native.stream_ptr(dev),
             ))
         ws.record_stream(torch.cuda.current_stream(dev))
         if rotvecs is not None:
             out['pose_rotvecs'] = rotvecs
         if kid is not None:
             out['kid_factor'] = kid
+        if scale_corr is not None:
+            out['scale_corr'] = scale_corr
         return out
 
     # ------------------------------------------------------------------------------
@@ -266,8 +270,9 @@ class BodyFitter(nn.Module):
         """Shape and translation for a known pose (pt/bodyfitter.py:552-653)."""
         if scale_target and scale_fit:
             raise ValueError('Only one of estim_scale_target and estim_scale_fit can be True')
-        if share_beta or scale_target or scale_fit:
-            raise NotImplementedError('share_beta / scale options are not implemented on the CUDA path yet')
+        if share_beta:
+            raise NotImplementedError('share_beta is not implemented on the CUDA path (SURVEY.md 8f-2)')
+        scale_mode = 1 if scale_target else (2 if scale_fit else 0)
         bm = self.body_model
         dev = bm.v_template.device
         _native.require_cuda(bm.v_template, 'the body model')
@@ -280,12 +285,13 @@ class BodyFitter(nn.Module):
         new = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)  # noqa: E731
         out = dict(shape_betas=new(B, S), trans=new(B, 3), relative_orientations=new(B, J, 3, 3))
         kid = new(B) if self.enable_kid else None
+        scale_corr = new(B) if scale_mode else None
         beta_ref = self._pad_ref(beta_regularizer_reference, B, 'beta_regularizer_reference')
         kid_ref = None
         if kid_regularizer_reference is not None and self.enable_kid:
             kid_ref = kid_regularizer_reference.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
         o = self._opts(1, False, [], self._shape_weights_rule(tj, vw, jw), beta_regularizer, beta_regularizer2,
-                       kid_regularizer, 0, scale_regularizer)
+                       kid_regularizer, scale_mode, scale_regularizer)
         L = _native.lib()
         s = self._struct()
         ws_bytes = L.smplfit_fit_workspace_bytes(C.byref(s), B, C.byref(o), int(tj is not None),
@@ -295,12 +301,14 @@ class BodyFitter(nn.Module):
         with torch.cuda.device(dev):
             _native.check(L.smplfit_fit_known_pose(
                 C.byref(s), B, p(glob), p(tv), p(tj), p(vw), p(jw), p(beta_ref), p(kid_ref), C.byref(o),
-                p(out['shape_betas']), p(out['trans']), p(out['relative_orientations']), p(kid), 0,
+                p(out['shape_betas']), p(out['trans']), p(out['relative_orientations']), p(kid), p(scale_corr),
                 ws.data_ptr(), ws_bytes, _native.stream_ptr(dev),
             ))
         ws.record_stream(torch.cuda.current_stream(dev))
         if kid is not None:
             out['kid_factor'] = kid
+        if scale_corr is not None:
+            out['scale_corr'] = scale_corr
         return out
 
     def fit_with_known_shape(self, *args, **kwargs):

@@ -94,7 +94,7 @@ def test_forward_variants_vs_oracle():
         bm(pose_rotvecs=pose)
 
 
-UNSUPPORTED = {'fit_tiny_scale_target', 'fit_tiny_scale_fit'}
+UNSUPPORTED = set()
 
 
 @pytest.mark.parametrize('name', list(gc.FIT_CASES))
@@ -118,8 +118,9 @@ def test_fit_golden(name):
     # reference itself is noisier than that: SMPL-X finger parts)
     tol = max(1e-4, 4 * float(g['ref_noise_betas']))
     assert d_ref['shape_betas'] < tol and d_ref['trans'] < tol
-    if 'kid_factor' in out:
-        assert d_ref['kid_factor'] < tol
+    for extra in ('kid_factor', 'scale_corr'):
+        if extra in out:
+            assert d_ref[extra] < tol, extra
     # rotations: within the reference's own reproducibility ...
     d = np.abs(out['orientations'] - g['ref_orientations']).max(axis=(0, 2, 3))
     assert np.all(d <= gc.orient_tolerance(g)), (d, gc.orient_tolerance(g))
