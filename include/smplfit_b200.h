@@ -158,6 +158,19 @@ int smplfit_fit_known_pose(const smplfit_model_t* m, int64_t batch, const float*
                            float* out_rel_orientations, float* out_kid_factor, float* out_scale_corr,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+/* -- BodyFitter.fit_with_known_shape (pt/bodyfitter.py:656-838): pose and translation (and optionally a
+ * scale of the fitted mesh) for known betas.  shape_betas (B,n_betas) (first min(n,S) used), kid_factor (B)
+ * or NULL (requires a fitter built with enable_kid when given); init_* = forward of the initial pose with these
+ * betas (vertices (B,V,3), joints (B,J,3), orientations (B,J,3,3)), required.  opts: num_iter,
+ * final_adjust_rots, scale_mode (0 or 2 = scale_fit), want_*.  Workspace: smplfit_fit_workspace_bytes. */
+int smplfit_fit_known_shape(const smplfit_model_t* m, int64_t batch, const float* shape_betas, int n_betas,
+                            const float* kid_factor, const float* target_vertices, const float* target_joints,
+                            const float* vertex_weights, const float* joint_weights, const float* init_vertices,
+                            const float* init_joints, const float* init_orientations, const smplfit_fit_opts_t* opts,
+                            float* out_pose_rotvecs, float* out_trans, float* out_orientations,
+                            float* out_rel_orientations, float* out_scale_corr, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
 /* -- BodyConverter.convert_vertices (pt/bodyconverter.py:129-149): CSR (V_out x V_in) applied to
  * every instance: out (B,V_out,3) = M @ in (B,V_in,3). */
 int smplfit_convert_vertices(const int32_t* indptr, const int32_t* indices, const float* data,

@@ -629,6 +629,74 @@ class OracleFitter:
         return res
 
 
+def fit_scale_and_translation(t, a, tj, aj, vw=None, jw=None, scale=False):
+    """pt/bodyfitter.py:1628-1681."""
+    if tj is None or aj is None:
+        tb, ab = t, a
+        w = vw if vw is not None else np.ones(t.shape[:2], F32)
+    else:
+        tb, ab = np.concatenate([t, tj], 1), np.concatenate([a, aj], 1)
+        w = np.concatenate([vw, jw], 1) if (vw is not None and jw is not None) else np.ones(tb.shape[:2], F32)
+    w = w / w.sum(1, keepdims=True)
+    mt = (tb * w[..., None]).sum(1)
+    ma = (ab * w[..., None]).sum(1)
+    if scale:
+        sst = (((tb - mt[:, None]) ** 2) * w[..., None]).sum((1, 2))
+        ssa = (((ab - ma[:, None]) ** 2) * w[..., None]).sum((1, 2))
+        sc = np.sqrt(sst / ssa)
+        return sc, mt - sc[:, None] * ma
+    return None, mt - ma
+
+
+def fit_with_known_shape(fitter, shape_betas, target_vertices, target_joints=None, vertex_weights=None,
+                         joint_weights=None, kid_factor=None, num_iter=1, final_adjust_rots=True,
+                         initial_pose_rotvecs=None, scale_fit=False, requested_keys=None):
+    """pt/bodyfitter.py:656-838 (``fitter`` is an OracleFitter)."""
+    if requested_keys is None:
+        requested_keys = ['pose_rotvecs']
+    m = fitter.m
+    t = np.asarray(target_vertices, F32)
+    tj = None if target_joints is None else np.asarray(target_joints, F32)
+    vw, jw = vertex_weights, joint_weights
+    if tj is None:
+        mean = t.mean(1)
+        t = t - mean[:, None]
+    else:
+        mean = np.concatenate([t, tj], 1).mean(1)
+        t, tj = t - mean[:, None], tj - mean[:, None]
+    B = t.shape[0]
+    init = m.forward(shape_betas=shape_betas, kid_factor=kid_factor, pose_rotvecs=initial_pose_rotvecs)
+    bc = lambda x: np.broadcast_to(x, (B,) + x.shape[1:])  # noqa: E731
+    glob = fitter.fit_global_rotations(t, tj, bc(init['vertices']), bc(init['joints']), vw, jw) @ bc(init['orientations'])
+    for _ in range(num_iter - 1):
+        res = m.forward(glob_rotmats=glob, shape_betas=shape_betas, kid_factor=kid_factor)
+        glob = fitter.fit_global_rotations(t, tj, res['vertices'], res['joints'] if tj is not None else None, vw, jw) @ glob
+    res = m.forward(glob_rotmats=glob, shape_betas=shape_betas, kid_factor=kid_factor)
+    rv, rj = res['vertices'], res['joints']
+    sc, tr = fit_scale_and_translation(t, rv, tj, rj, vw, jw, scale=scale_fit)
+    if final_adjust_rots:
+        if scale_fit:
+            s3 = sc[:, None, None]
+            glob = fitter.fit_global_rotations_dependent(t, tj, s3 * rv + tr[:, None], s3 * rj + tr[:, None], vw, jw,
+                                                         glob, shape_betas, s3, tr, kid_factor)
+        else:
+            glob = fitter.fit_global_rotations_dependent(t, tj, rv + tr[:, None], rj + tr[:, None], vw, jw, glob,
+                                                         shape_betas, None, tr, kid_factor)
+    out = dict(trans=tr + mean, orientations=glob)
+    if scale_fit:
+        out['scale_corr'] = sc
+    if 'relative_orientations' in requested_keys or 'pose_rotvecs' in requested_keys:
+        par = m.parents
+        rel = np.empty_like(glob)
+        rel[:, 0] = glob[:, 0]
+        for i in range(1, m.num_joints):
+            rel[:, i] = np.swapaxes(glob[:, par[i]], -1, -2) @ glob[:, i]
+        out['relative_orientations'] = rel
+        if 'pose_rotvecs' in requested_keys:
+            out['pose_rotvecs'] = mat2rotvec(rel).reshape(B, -1)
+    return out
+
+
 def convert_vertices_csr(indptr, indices, data, verts):
     """CSR (V_out x V_in) applied to (B, V_in, 3): pt/bodyconverter.py:129-149."""
     verts = np.asarray(verts, F32)

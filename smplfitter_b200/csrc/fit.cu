@@ -19,12 +19,13 @@ std::vector<ProfRec> g_prof;
 struct FitWs {
   double* Gd;
   float *mean, *tT, *tjT, *vwT, *jwT, *vposedT, *R, *R2, *RT, *Pext, *feat, *gpart, *beta, *trans, *refj,
-      *skin, *spart, *aT, *ajT, *initjT, *RT4, *zpart, *scale;
+      *skin, *spart, *aT, *ajT, *initjT, *RT4, *zpart, *scale, *mpart;
   double* Zd;
   void* tc_scratch;
   size_t bytes;
 };
 
+static int moment_blocks(int V) { return (V + 255) / 256; }
 static int shape_nacc(int ns) { return ns * (ns + 1) / 2 + ns + 3 * ns + 3 + 1; }
 
 static FitWs carve(void* base, const smplfit_model_t* m, int64_t B, int has_joints, int has_vw, int has_jw,
@@ -54,13 +55,14 @@ static FitWs carve(void* base, const smplfit_model_t* m, int64_t B, int has_join
   w.refj = c.take<float>((size_t)3 * J * Bp);
   w.skin = c.take<float>((size_t)12 * J * Bp);
   w.spart = c.take<float>((size_t)m->n_segments * 16 * Bp);
-  const bool need_aT = !has_joints || has_init;
+  const bool need_aT = true;  // (fit_with_known_shape always materialises the reference)
   w.aT = need_aT ? c.take<float>((size_t)3 * V * Bp) : nullptr;
   w.ajT = need_aT ? c.take<float>((size_t)3 * J * Bp) : nullptr;
   w.initjT = has_init ? c.take<float>((size_t)3 * J * Bp) : nullptr;
   w.zpart = c.take<float>((size_t)scale_chunks(m) * (NS + 5) * Bp);
   w.Zd = c.take<double>((size_t)(NS + 5) * Bp);
   w.scale = c.take<float>(Bp);
+  w.mpart = c.take<float>((size_t)(moment_blocks(V) + 1) * 9 * Bp);
   w.tc_scratch = c.take<char>(vposed_tc_scratch_bytes(m, (int)Bp));
   w.bytes = c.off + 256;
   return w;
@@ -421,6 +423,125 @@ extern "C" int smplfit_debug_vposed(const smplfit_model_t* m, const float* feat,
     SF_LAUNCH(k_vposed_gemm_simt, grid, 256, 0, st, m->posedirs_fit, m->v_template_fit, feat, 3 * m->num_vertices,
               Kp, Bp, out);
   }
+  SF_CHECK_LAST();
+  return SMPLFIT_OK;
+}
+
+extern "C" int smplfit_fit_known_shape(const smplfit_model_t* m, int64_t batch, const float* shape_betas, int n_betas,
+                                       const float* kid_factor, const float* target_vertices,
+                                       const float* target_joints, const float* vertex_weights,
+                                       const float* joint_weights, const float* init_vertices,
+                                       const float* init_joints, const float* init_orientations,
+                                       const smplfit_fit_opts_t* o, float* out_pose_rotvecs, float* out_trans,
+                                       float* out_orientations, float* out_rel_orientations, float* out_scale_corr,
+                                       void* workspace, size_t workspace_bytes, void* stream) {
+  if (int e = check_model(m)) return e;
+  if (!o || !target_vertices || !init_vertices || !init_joints || !init_orientations || !out_trans || !out_orientations)
+    return fail(SMPLFIT_ERR_ARG, "missing required pointer");
+  if (batch <= 0 || batch > (1 << 24)) return fail(SMPLFIT_ERR_ARG, "batch out of range");
+  if (o->num_iter < 1) return fail(SMPLFIT_ERR_ARG, "num_iter must be >= 1");
+  if (o->scale_mode != 0 && o->scale_mode != 2) return fail(SMPLFIT_ERR_ARG, "fit_with_known_shape only knows scale_fit");
+  if (o->scale_mode != 0 && !out_scale_corr) return fail(SMPLFIT_ERR_ARG, "scale_corr output required");
+  if (kid_factor != nullptr && m->fit_ns != m->num_betas + 1)
+    return fail(SMPLFIT_ERR_UNSUPPORTED, "kid_factor needs a fitter built with enable_kid=True");
+  const bool has_joints = target_joints != nullptr;
+  FitCtx c;
+  c.m = m;
+  c.B = (int)batch;
+  c.Bp = roundup(c.B, 32);
+  c.groups = c.Bp / 32;
+  c.Kp = roundup(m->num_pose_feats, 16);
+  c.n_chunks = (m->num_vertices + m->chunk_len - 1) / m->chunk_len;
+  c.st = reinterpret_cast<cudaStream_t>(stream);
+  c.has_joints = has_joints;
+  c.plan = plan_shape_pass(m, c.groups);
+  c.use_rec = c.plan.use_rec;
+  c.w = carve(workspace, m, batch, has_joints, vertex_weights != nullptr, joint_weights != nullptr, 1);
+  if (!workspace || c.w.bytes > workspace_bytes) return fail(SMPLFIT_ERR_WORKSPACE, "workspace too small");
+  FitWs& w = c.w;
+  const int V = m->num_vertices, J = m->num_joints;
+  SF_LAUNCH(k_mean, (c.Bp * 32 + 255) / 256, 256, 0, c.st, target_vertices, target_joints, V, J, c.B, c.Bp, w.mean);
+  run_transpose<3>(c, target_vertices, V, m->inv_order, w.mean, w.tT);
+  if (vertex_weights) run_transpose<1>(c, vertex_weights, V, m->inv_order, nullptr, w.vwT);
+  if (joint_weights) run_transpose<1>(c, joint_weights, J, nullptr, nullptr, w.jwT);
+  if (has_joints) run_transpose<3>(c, target_joints, J, nullptr, w.mean, w.tjT);
+  else run_regress(c, w.tT, w.tjT);
+  c.vwT_shape = nullptr;
+  c.jwT_shape = nullptr;
+  SF_LAUNCH(k_set_shape, c.groups, 32, 0, c.st, shape_betas, n_betas, kid_factor, m->num_betas, m->fit_ns, c.B, c.Bp,
+            w.beta, w.trans);
+
+  // -- first rotation fit against the forward of the initial pose (pt/bodyfitter.py:721-737) --
+  run_transpose<3>(c, init_vertices, V, m->inv_order, nullptr, w.aT);
+  run_transpose<3>(c, init_joints, J, nullptr, nullptr, w.initjT);
+  run_transpose<1>(c, init_orientations, 9 * J, nullptr, nullptr, w.R2);
+  RotArgs ra;
+  ra.partials = w.spart; ra.tjT = w.tjT; ra.jwT = w.jwT; ra.R_new = w.R; ra.RT = w.RT; ra.Pext = w.Pext;
+  ra.feat = w.feat; ra.t = tables(m); ra.B = c.B; ra.Bp = c.Bp; ra.Kp = c.Kp; ra.RT4 = w.RT4;
+  run_stats(c, 2, w.initjT, w.aT, nullptr);
+  const float* aj = w.initjT;
+  if (!has_joints) {
+    run_regress(c, w.aT, w.ajT);
+    aj = w.ajT;
+  }
+  ra.ajT = aj; ra.aj_const = nullptr; ra.ca0T = w.initjT; ra.ca0_const = nullptr; ra.R_old = w.R2;
+  run_rot(c, ra, true);
+
+  // forward with the known betas for the current orientations = shape front + k_shape_out (trans = 0)
+  SolveArgs so;
+  so.partials = nullptr; so.Pext = w.Pext; so.RT = w.RT; so.tjT = nullptr; so.jwT = nullptr; so.beta_ref = nullptr;
+  so.kid_ref = nullptr; so.beta = w.beta; so.trans = w.trans; so.refj = w.refj; so.skin = w.skin; so.wS = nullptr;
+  so.wsum = nullptr; so.n_chunks = 0; so.J = J; so.S = m->num_betas; so.Bp = c.Bp; so.B = c.B; so.V = V;
+  so.weighted = 0; so.sa_closed_form = 0; so.scale_mode = 0; so.zpartials = nullptr; so.n_zchunks = 0;
+  so.scale_reg = 0.f; so.scale_out = w.scale; so.reg = so.reg2 = so.kid_reg = 0.f;
+  const float* R_final = w.R;
+  for (int it = 0; it < o->num_iter; ++it) {
+    const bool last = (it == o->num_iter - 1);
+    SF_LAUNCH(k_shape_out, dim3(c.groups, J), 32, 0, c.st, so, m->fit_ns);
+    run_gemm(c);
+    run_stats(c, 1, w.refj, nullptr, w.aT);  // reference vertices skinned on the fly, stored for the moments
+    aj = w.refj;
+    if (!has_joints) {
+      run_regress(c, w.aT, w.ajT);
+      aj = w.ajT;
+    }
+    if (!last) {
+      ra.ajT = aj; ra.aj_const = nullptr; ra.ca0T = w.refj; ra.ca0_const = nullptr; ra.R_old = w.R; ra.R_new = w.R;
+      run_rot(c, ra, true);
+      continue;
+    }
+    // fit_scale_and_translation (pt/bodyfitter.py:764-772, :1628-1681)
+    const bool vweights = has_joints ? (vertex_weights && joint_weights) : (vertex_weights != nullptr);
+    const int nvb = moment_blocks(V);
+    {
+      const long long warps = (long long)nvb * c.groups;
+      SF_LAUNCH(k_moments, (int)((warps + 3) / 4), 128, 0, c.st, w.tT, w.aT, vweights ? w.vwT : nullptr, V, 256, nvb,
+                c.Bp, w.mpart);
+      if (has_joints)
+        SF_LAUNCH(k_moments, (c.groups + 3) / 4, 128, 0, c.st, w.tjT, w.refj, vweights ? w.jwT : nullptr, J, J, 1, c.Bp,
+                  w.mpart + (size_t)nvb * 9 * c.Bp);
+    }
+    ScaleTransArgs sta;
+    sta.vpart = w.mpart; sta.jpart = has_joints ? w.mpart + (size_t)nvb * 9 * c.Bp : nullptr; sta.n_vblocks = nvb;
+    sta.Bp = c.Bp; sta.estimate_scale = o->scale_mode == 2; sta.scale = w.scale; sta.trans = w.trans;
+    SF_LAUNCH(k_scale_trans, c.groups, 32, 0, c.st, sta);
+    if (o->final_adjust_rots) {
+      AdjustArgs aa;
+      aa.partials = w.spart; aa.tjT = w.tjT; aa.ajT = aj; aa.refj = w.refj; aa.jwT = w.jwT; aa.R_prev = w.R;
+      aa.beta = w.beta; aa.trans = w.trans; aa.R_out = w.R2; aa.t = tables(m); aa.Bp = c.Bp;
+      aa.scale = w.scale; aa.scale_mode = 3;
+      SF_LAUNCH(k_adjust_solve, c.Bp / 32, 32, 0, c.st, aa);
+      R_final = w.R2;
+    }
+  }
+  OutputArgs oa;
+  oa.R_final = R_final; oa.R_rel_src = R_final; oa.beta = w.beta; oa.trans = w.trans; oa.mean = w.mean;
+  oa.parents = m->parents; oa.pose_rotvecs = o->want_pose_rotvecs ? out_pose_rotvecs : nullptr;
+  oa.shape_betas = nullptr; oa.out_trans = out_trans; oa.orientations = out_orientations;
+  oa.rel_orient = (o->want_pose_rotvecs || o->want_rel_orient) ? out_rel_orientations : nullptr; oa.kid = nullptr;
+  oa.scale = w.scale; oa.scale_corr = o->scale_mode ? out_scale_corr : nullptr; oa.scale_mode = 0;
+  oa.J = J; oa.S = m->num_betas; oa.NS = m->fit_ns; oa.B = c.B; oa.Bp = c.Bp;
+  SF_LAUNCH(k_output, c.Bp / 32, 32, 0, c.st, oa);
   SF_CHECK_LAST();
   return SMPLFIT_OK;
 }

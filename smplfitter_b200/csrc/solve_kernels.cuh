@@ -576,7 +576,8 @@ struct AdjustArgs {
   const float* trans;     // [3][Bp]
   float* R_out;           // [9J][Bp]
   const float* scale;     // [Bp] scale_corr or null
-  int scale_mode;         // 1: targets scaled (pt/bodyfitter.py:465-480), 2: reference scaled (:481-496)
+  int scale_mode;         // 1: targets scaled (pt/bodyfitter.py:465-480), 2: reference scaled about trans (:481-496),
+                          // 3: reference' = scale * reference + trans (fit_with_known_shape, :774-803)
   TreeTables t;
   int Bp;
 };
@@ -590,7 +591,8 @@ static __global__ void __launch_bounds__(32) k_adjust_solve(const AdjustArgs a) 
   for (int s = 0; s < NS; ++s) x[s] = SF_IM(a.beta, s, Bp, b);
   const float sc = (a.scale != nullptr) ? a.scale[b] : 1.f;
   const float st_t = (a.scale_mode == 1) ? sc : 1.f;  // scale of the target side
-  const float st_a = (a.scale_mode == 2) ? sc : 1.f;  // scale of the reference side
+  const float st_a = (a.scale_mode >= 2) ? sc : 1.f;  // scale of the reference side
+  const float tr_a = (a.scale_mode == 3) ? 1.f : (1.f - st_a);  // reference' = st_a * reference + tr_a * trans
   float trv[3];
   for (int c = 0; c < 3; ++c) trv[c] = SF_IM(a.trans, c, Bp, b);
   float pos[SMPLFIT_MAX_JOINTS * 3], rest[SMPLFIT_MAX_JOINTS * 3];
@@ -599,7 +601,7 @@ static __global__ void __launch_bounds__(32) k_adjust_solve(const AdjustArgs a) 
       const float* Jt = a.t.Jt_ext + (size_t)j * TW + c * (1 + NS);
       float v = __ldg(Jt);
       for (int s = 0; s < NS; ++s) v = fmaf(__ldg(Jt + 1 + s), x[s], v);
-      rest[j * 3 + c] = (a.scale_mode == 2) ? v * sc : v;  // j = j * scale_corr (pt/bodyfitter.py:1449-1450)
+      rest[j * 3 + c] = (a.scale_mode >= 2) ? v * sc : v;  // j = j * scale_corr (pt/bodyfitter.py:1449-1450)
     }
   for (int i = 0; i < J; ++i) {
     const int par = a.t.parents[i];
@@ -632,7 +634,7 @@ static __global__ void __launch_bounds__(32) k_adjust_solve(const AdjustArgs a) 
       load3(a.refj, i, Bp, b, ca);
       for (int c = 0; c < 3; ++c) {
         ct0[c] *= st_t;
-        ca[c] = st_a * ca[c] + (1.f - st_a) * trv[c];
+        ca[c] = st_a * ca[c] + tr_a * trv[c];
       }
       part_covariance(a.partials, a.t.part_seg_begin, i, Bp, b, ct0, ca, pos + i * 3, ca, A, st_t * st_a, st_t, st_a);
       const int n = a.t.cas_count[i];
@@ -643,7 +645,7 @@ static __global__ void __launch_bounds__(32) k_adjust_solve(const AdjustArgs a) 
         load3(a.ajT, cas[k], Bp, b, aj);
         for (int c = 0; c < 3; ++c) {
           tj[c] *= st_t;
-          aj[c] = st_a * aj[c] + (1.f - st_a) * trv[c];
+          aj[c] = st_a * aj[c] + tr_a * trv[c];
         }
         const float w = a.jwT ? SF_IM(a.jwT, cas[k], Bp, b) : 1.f;
 #pragma unroll
@@ -690,7 +692,8 @@ static __global__ void __launch_bounds__(32) k_output(const OutputArgs a) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= a.B) return;
   const int J = a.J, Bp = a.Bp;
-  for (int s = 0; s < a.S; ++s) a.shape_betas[(size_t)b * a.S + s] = SF_IM(a.beta, s, Bp, b);
+  if (a.shape_betas != nullptr)
+    for (int s = 0; s < a.S; ++s) a.shape_betas[(size_t)b * a.S + s] = SF_IM(a.beta, s, Bp, b);
   if (a.kid != nullptr) a.kid[b] = SF_IM(a.beta, a.S, Bp, b);
   {
     // pt/bodyfitter.py:513-519: the target mean is added back (scaled in the scale modes)
@@ -731,6 +734,86 @@ static __global__ void __launch_bounds__(32) k_output(const OutputArgs a) {
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// fit_scale_and_translation (pt/bodyfitter.py:1628-1681) for fit_with_known_shape: weighted
+// first / second moments of targets and reference over vertices (+ joints), reduced per
+// (vertex block, instance) then finalised per instance.
+// moments layout: [W, St(3), Sa(3), Stt, Saa]
+// ---------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(128) k_moments(const float* __restrict__ tT, const float* __restrict__ aT,
+                                                        const float* __restrict__ wT, int n_items, int items_per_warp,
+                                                        int n_blocks, int Bp, float* __restrict__ partials) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int blk = warp % n_blocks, g = warp / n_blocks;
+  if (g * 32 >= Bp) return;
+  const int b = g * 32 + lane;
+  float W = 0.f, St[3] = {0.f, 0.f, 0.f}, Sa[3] = {0.f, 0.f, 0.f}, Stt = 0.f, Saa = 0.f;
+  const int i0 = blk * items_per_warp, i1 = min(n_items, i0 + items_per_warp);
+  for (int i = i0; i < i1; ++i) {
+    const float w = wT ? SF_IM(wT, i, Bp, b) : 1.f;
+    W += w;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float t = SF_IM(tT, i * 3 + c, Bp, b), x = SF_IM(aT, i * 3 + c, Bp, b);
+      St[c] = fmaf(w, t, St[c]);
+      Sa[c] = fmaf(w, x, Sa[c]);
+      Stt = fmaf(w * t, t, Stt);
+      Saa = fmaf(w * x, x, Saa);
+    }
+  }
+  float* out = partials + (size_t)blk * 9 * Bp + b;
+  out[0] = W;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    out[(size_t)(1 + c) * Bp] = St[c];
+    out[(size_t)(4 + c) * Bp] = Sa[c];
+  }
+  out[(size_t)7 * Bp] = Stt;
+  out[(size_t)8 * Bp] = Saa;
+}
+
+struct ScaleTransArgs {
+  const float* vpart;  // [n_vblocks][9][Bp]
+  const float* jpart;  // [1][9][Bp] or null (no joints)
+  int n_vblocks, Bp, estimate_scale;
+  float* scale;  // [Bp]
+  float* trans;  // [3][Bp]
+};
+
+static __global__ void __launch_bounds__(32) k_scale_trans(const ScaleTransArgs a) {
+  const int b = blockIdx.x * 32 + threadIdx.x;
+  if (b >= a.Bp) return;
+  double m[9];
+  for (int e = 0; e < 9; ++e) m[e] = 0.0;
+  for (int q = 0; q < a.n_vblocks; ++q)
+    for (int e = 0; e < 9; ++e) m[e] += (double)a.vpart[((size_t)q * 9 + e) * a.Bp + b];
+  if (a.jpart != nullptr)
+    for (int e = 0; e < 9; ++e) m[e] += (double)a.jpart[(size_t)e * a.Bp + b];
+  const double W = m[0];
+  double mt[3], ma[3], sst = m[7], ssa = m[8];
+  for (int c = 0; c < 3; ++c) {
+    mt[c] = m[1 + c] / W;
+    ma[c] = m[4 + c] / W;
+    sst -= W * mt[c] * mt[c];
+    ssa -= W * ma[c] * ma[c];
+  }
+  const double sc = a.estimate_scale ? sqrt(sst / ssa) : 1.0;
+  a.scale[b] = (float)sc;
+  for (int c = 0; c < 3; ++c) SF_IM(a.trans, c, a.Bp, b) = (float)(mt[c] - sc * ma[c]);
+}
+
+// betas (B,n) / kid (B) given by the caller -> [NS][Bp] unknown vector (zero padded), zero trans
+static __global__ void __launch_bounds__(32) k_set_shape(const float* __restrict__ betas, int n_betas,
+                                                         const float* __restrict__ kid, int S, int NS, int B, int Bp,
+                                                         float* __restrict__ beta, float* __restrict__ trans) {
+  const int b = blockIdx.x * 32 + threadIdx.x;
+  if (b >= Bp) return;
+  const bool live = b < B;
+  for (int s = 0; s < S; ++s) SF_IM(beta, s, Bp, b) = (live && betas && s < n_betas) ? betas[(size_t)b * n_betas + s] : 0.f;
+  if (NS > S) SF_IM(beta, S, Bp, b) = (live && kid) ? kid[b] : 0.f;
+  for (int c = 0; c < 3; ++c) SF_IM(trans, c, Bp, b) = 0.f;
 }
 
 }  // namespace sf

@@ -311,6 +311,67 @@ class BodyFitter(nn.Module):
             out['scale_corr'] = scale_corr
         return out
 
-    def fit_with_known_shape(self, *args, **kwargs):
-        """pt/bodyfitter.py:656-838 -- pose-only variant; not on the CUDA path yet."""
-        raise NotImplementedError('fit_with_known_shape is not implemented on the CUDA path yet')
+    def fit_with_known_shape(
+        self,
+        shape_betas: torch.Tensor,
+        target_vertices: torch.Tensor,
+        target_joints: Optional[torch.Tensor] = None,
+        vertex_weights: Optional[torch.Tensor] = None,
+        joint_weights: Optional[torch.Tensor] = None,
+        kid_factor: Optional[torch.Tensor] = None,
+        num_iter: int = 1,
+        final_adjust_rots: bool = True,
+        initial_pose_rotvecs: Optional[torch.Tensor] = None,
+        scale_fit: bool = False,
+        requested_keys: Optional[list] = None,
+    ) -> dict[str, torch.Tensor]:
+        """Pose and translation for known betas (pt/bodyfitter.py:656-838)."""
+        if requested_keys is None:
+            requested_keys = ['pose_rotvecs']
+        bm = self.body_model
+        dev = bm.v_template.device
+        _native.require_cuda(bm.v_template, 'the body model')
+        B, V, J = target_vertices.shape[0], bm.num_vertices, bm.num_joints
+        tv = self._prep(target_vertices, (B, V, 3), 'target_vertices')
+        tj = self._prep(target_joints, (B, J, 3), 'target_joints')
+        vw = self._prep(vertex_weights, (B, V), 'vertex_weights')
+        jw = self._prep(joint_weights, (B, J), 'joint_weights')
+        if kid_factor is not None and not self.enable_kid:
+            raise NotImplementedError('kid_factor in fit_with_known_shape needs a fitter built with enable_kid=True')
+        betas = shape_betas.to(device=dev, dtype=torch.float32)
+        if betas.shape[0] != B:
+            betas = betas.expand(B, betas.shape[1])
+        betas = betas.contiguous()
+        kid = None
+        if kid_factor is not None:
+            kid = torch.as_tensor(kid_factor, dtype=torch.float32, device=dev).reshape(-1).expand(B).contiguous()
+        init = bm(shape_betas=betas, kid_factor=kid, pose_rotvecs=initial_pose_rotvecs)
+        expand = lambda x: x.expand(B, *x.shape[1:]).contiguous()  # noqa: E731
+        init_v, init_j, init_o = expand(init['vertices']), expand(init['joints']), expand(init['orientations'])
+        new = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)  # noqa: E731
+        out = dict(trans=new(B, 3), orientations=new(B, J, 3, 3))
+        want_rel = 'relative_orientations' in requested_keys or 'pose_rotvecs' in requested_keys
+        rel = new(B, J, 3, 3) if want_rel else None
+        rotvecs = new(B, 3 * J) if 'pose_rotvecs' in requested_keys else None
+        scale_corr = new(B) if scale_fit else None
+        o = self._opts(num_iter, final_adjust_rots, requested_keys, False, 0.0, 0.0, None, 2 if scale_fit else 0, 0.0)
+        L = _native.lib()
+        s = self._struct()
+        ws_bytes = L.smplfit_fit_workspace_bytes(C.byref(s), B, C.byref(o), int(tj is not None),
+                                                 int(vw is not None), int(jw is not None))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        p = _native.ptr
+        with torch.cuda.device(dev):
+            _native.check(L.smplfit_fit_known_shape(
+                C.byref(s), B, p(betas), betas.shape[1], p(kid), p(tv), p(tj), p(vw), p(jw), p(init_v), p(init_j),
+                p(init_o), C.byref(o), p(rotvecs), p(out['trans']), p(out['orientations']), p(rel), p(scale_corr),
+                ws.data_ptr(), ws_bytes, _native.stream_ptr(dev),
+            ))
+        ws.record_stream(torch.cuda.current_stream(dev))
+        if scale_corr is not None:
+            out['scale_corr'] = scale_corr
+        if rel is not None:
+            out['relative_orientations'] = rel
+        if rotvecs is not None:
+            out['pose_rotvecs'] = rotvecs
+        return out

@@ -212,6 +212,31 @@ def test_known_pose_vs_oracle():
     assert np.abs(out['shape_betas'].cpu().numpy() - betas).max() < 1e-3  # exact recovery on-manifold
 
 
+@pytest.mark.parametrize('joints,scale_fit,num_iter', [(True, False, 2), (True, True, 1), (False, False, 2)])
+def test_known_shape_vs_oracle(joints, scale_fit, num_iter):
+    mname = 'smpl_tiny'
+    bm, fitter = get_model(mname)
+    om = oracle_np.OracleModel(modeldata.initialize(mname), mname)
+    rs = np.random.RandomState(31)
+    B = 7
+    pose = (rs.randn(B, 72) * 0.25).astype(np.float32)
+    betas = rs.randn(B, 10).astype(np.float32)
+    trans = rs.randn(B, 3).astype(np.float32)
+    fw = om.forward(pose, betas, trans)
+    tv = (1.07 if scale_fit else 1.0) * fw['vertices'] + (rs.randn(B, om.num_vertices, 3) * 0.002).astype(np.float32)
+    tj = (1.07 if scale_fit else 1.0) * fw['joints']
+    kw = dict(num_iter=num_iter, final_adjust_rots=True, scale_fit=scale_fit,
+              requested_keys=['pose_rotvecs', 'relative_orientations'])
+    out = fitter.fit_with_known_shape(cuda(betas), cuda(tv), cuda(tj) if joints else None, **kw)
+    ora = oracle_np.fit_with_known_shape(oracle_np.OracleFitter(om), betas, tv, tj if joints else None, **kw)
+    assert set(out) == set(ora)
+    assert np.abs(out['trans'].cpu().numpy() - ora['trans']).max() < 1e-4
+    assert np.abs(out['orientations'].cpu().numpy() - ora['orientations']).max() < 1e-3  # oracle carries fp32 part-sum noise
+    if scale_fit:
+        assert np.abs(out['scale_corr'].cpu().numpy() - ora['scale_corr']).max() < 1e-4
+        assert np.abs(out['scale_corr'].cpu().numpy() - 1.07).max() < 5e-3
+
+
 def test_convert_vertices_vs_oracle():
     import scipy.sparse as sp
 
