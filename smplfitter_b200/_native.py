@@ -108,7 +108,7 @@ def lib():
     L.smplfit_debug_vposed.argtypes = [C.POINTER(ModelStruct), _F, C.c_int, C.c_int, _F, _F, _F]
     L.smplfit_fit_known_shape.restype = C.c_int
     L.smplfit_fit_known_shape.argtypes = (
-        [C.POINTER(ModelStruct), C.c_int64, _F, C.c_int] + [_F] * 9 + [C.POINTER(FitOpts)] + [_F] * 5
+        [C.POINTER(ModelStruct), C.c_int64, _F, C.c_int] + [_F] * 8 + [C.POINTER(FitOpts)] + [_F] * 5
         + [_F, C.c_size_t, _F]
     )
     L.smplfit_convert_vertices.restype = C.c_int
