@@ -213,12 +213,9 @@ def main():
         return fitter.fit(tv, tj, **FIT_KW)
 
     def step_e2e():
-        d_tv = h_tv.to(dev, non_blocking=True)
-        d_tj = h_tj.to(dev, non_blocking=True)
-        out = fitter.fit(d_tv, d_tj, **FIT_KW)
-        for k in h_out:
-            h_out[k].copy_(out[k], non_blocking=True)
-        return out
+        # public API for host-resident inputs: chunked H2D copies overlapped with the fits, results
+        # land in pinned host memory (BodyFitter.fit_from_host)
+        return fitter.fit_from_host(h_tv, h_tj, chunk_size=1024, **FIT_KW)
 
     def timed(fn, steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -266,6 +263,27 @@ def main():
     re = bm(out['pose_rotvecs'], out['shape_betas'], out['trans'])
     v2v_mm = float((re['vertices'] - tv).norm(dim=-1).mean().item() * 1000)
 
+    # secondary measurement: the forward LBS pass (store-bound; north_star's LBS roofline)
+    lbs = None
+    if rank == 0:
+        d_pose, d_betas, d_trans = (torch.from_numpy(x).to(dev) for x in (pose, betas, trans))
+        for _ in range(3):
+            bm(d_pose, d_betas, d_trans)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(args.steps):
+            bm(d_pose, d_betas, d_trans)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        t_fwd = e0.elapsed_time(e1) / args.steps / 1000
+        peak_hbm, _src = peaks()
+        fwd_bytes = B * (4 * 3 * V + 4 * (3 * J + S + 3))  # 83 020 B per forward (SMPL)
+        lbs = {'forwards_per_s': B / t_fwd, 'ms_per_call': t_fwd * 1000, 'achieved_gbs': fwd_bytes / t_fwd / 1e9,
+               'frac_of_hbm_peak': fwd_bytes / t_fwd / 1e9 / peak_hbm, 'bytes_per_forward': fwd_bytes // B}
+    if world > 1:
+        dist.barrier()
+
     if rank == 0:
         total_fits = B * world * args.steps
         value = total_fits / (ms / 1000)
@@ -279,8 +297,14 @@ def main():
             per_launch_ms = t / n
             alg_bytes = B * 2 * 4 * 3 * V  # target read + v_posed read per instance
             achieved = alg_bytes / (per_launch_ms / 1000) / 1e9
+            traffic = None
+            try:  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu capture
+                with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+                    traffic = json.load(f).get(dom)
+            except Exception:
+                pass
             roof = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                    'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                    'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                     'avg_launch_ms': per_launch_ms, 'share_of_step': t / tot,
                     'note': 'kernel is FP32-ALU bound by design (SURVEY.md 8d); HBM fraction reported as required',
                     'kernel_ms_per_step': {k: v[1] / min(args.steps, 5) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}}
@@ -301,7 +325,7 @@ def main():
             'e2e': {'value': e2e_value, 'unit': 'fits/s', 'h2d_bytes_per_step': int(B * (V + J) * 12),
                     'd2h_bytes_per_step': int(B * (3 * J + S + 3) * 4), 'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
-            'v2v_mm_roundtrip': v2v_mm,
+            'v2v_mm_roundtrip': v2v_mm, 'lbs_forward': lbs,
         }
         print(json.dumps(line))
     if world > 1:

@@ -249,6 +249,51 @@ class BodyFitter(nn.Module):
         return out
 
     # ------------------------------------------------------------------------------
+    def fit_from_host(self, target_vertices: torch.Tensor, target_joints: Optional[torch.Tensor] = None,
+                      chunk_size: int = 1024, pinned_out: bool = True, **fit_kwargs) -> dict[str, torch.Tensor]:
+        """``fit`` for HOST-resident inputs (ideally pinned): the batch is cut into chunks and the
+        host-to-device copy of chunk k+1 (on a side stream) overlaps the fit of chunk k, so the
+        end-to-end time approaches max(PCIe copy, compute) instead of their sum.  Results are
+        returned in (pinned) host tensors with the same keys as ``fit``."""
+        dev = self.body_model.v_template.device
+        _native.require_cuda(self.body_model.v_template, 'the body model')
+        B = target_vertices.shape[0]
+        compute = torch.cuda.current_stream(dev)
+        copy = getattr(self, '_copy_stream', None)
+        if copy is None:
+            copy = self._copy_stream = torch.cuda.Stream(dev)
+        outs: dict = {}
+        bounds = [(lo, min(B, lo + chunk_size)) for lo in range(0, B, chunk_size)]
+        staged = []
+
+        def stage(lo, hi):
+            with torch.cuda.stream(copy):
+                tv = target_vertices[lo:hi].to(dev, non_blocking=True)
+                tj = target_joints[lo:hi].to(dev, non_blocking=True) if target_joints is not None else None
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            return tv, tj, ev
+
+        copy.wait_stream(compute)
+        if bounds:
+            staged.append(stage(*bounds[0]))
+        for k, (lo, hi) in enumerate(bounds):
+            tv, tj, ev = staged[k]
+            if k + 1 < len(bounds):
+                staged.append(stage(*bounds[k + 1]))
+            compute.wait_event(ev)
+            tv.record_stream(compute)
+            if tj is not None:
+                tj.record_stream(compute)
+            res = self.fit(tv, tj, **fit_kwargs)
+            for key, val in res.items():
+                if key not in outs:
+                    outs[key] = torch.empty((B, *val.shape[1:]), dtype=val.dtype, pin_memory=pinned_out)
+                outs[key][lo:hi].copy_(val, non_blocking=True)
+            staged[k] = None
+        return outs
+
+    # ------------------------------------------------------------------------------
     def fit_with_known_pose(
         self,
         pose_rotvecs: torch.Tensor,
