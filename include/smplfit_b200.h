@@ -93,8 +93,10 @@ typedef struct smplfit_model {
                                    4 joint ids (int bits), shapedirs[3][NS]; NULL when skin_k > 4 */
   const double* fit_wS;         /* (J,3,NS) sum_v w_vk S_v  (closed-form SA of the unweighted shape solve) */
   const double* fit_wsum;       /* (J)      sum_v w_vk */
+  const float* fwd_rec;         /* (V, fwd_rec_len) forward records in MODEL order: 4 skin weights, 4 joint ids,
+                                   v_posed row (int) + 3 pad, shapedirs[3][SP], kid_shapedir[3]; NULL when skin_k > 4 */
   int32_t fit_rec_len;          /* floats per record = roundup(8 + 3 NSP, 4), NSP = NS rounded up to even; shapedirs[x][s] at 8 + x NSP + s */
-  int32_t fit_reserved2;
+  int32_t fwd_rec_len;          /* roundup(12 + 3 SP + 3, 4), SP = S rounded up to even */
   const void* reserved_ptr[4];
 } smplfit_model_t;
 

@@ -32,14 +32,14 @@ class ModelStruct(C.Structure):
     ]
     _ptr_fields_b = [
         'fit_shapedirs', 'fit_Jt_ext', 'template_joints_regressed', 'J_regressor_fit', 'posedirs_hi',
-        'posedirs_lo', 'template_mesh_fit', 'fit_rec', 'fit_wS', 'fit_wsum',
+        'posedirs_lo', 'template_mesh_fit', 'fit_rec', 'fit_wS', 'fit_wsum', 'fwd_rec',
     ]
     _fields_ = (
         [(n, C.c_int32) for n in _int_fields]
         + [(n, _F) for n in _ptr_fields_a]
         + [('fit_ns', C.c_int32), ('fit_reserved', C.c_int32)]
         + [(n, _F) for n in _ptr_fields_b]
-        + [('fit_rec_len', C.c_int32), ('fit_reserved2', C.c_int32)]
+        + [('fit_rec_len', C.c_int32), ('fwd_rec_len', C.c_int32)]
         + [('reserved_ptr', _F * 4)]
     )
 

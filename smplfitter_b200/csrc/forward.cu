@@ -171,6 +171,129 @@ __global__ void __launch_bounds__(96) k_fwd_skin(const FwdSkinArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// k_fwd_skin_rec: the skinning pass in the record style of the fit kernels.  CTA = 32 instances
+// (lane = instance) x 8 warps; the per-joint [R | t] rows of the group are staged in shared memory
+// with cp.async; each warp takes blocks of 32 consecutive model vertices, reads one packed record
+// per vertex (4 weights, 4 joint ids, v_posed row, shapedirs[3][SP], kid_shapedir[3]) with
+// warp-uniform 16-byte loads one vertex ahead, prefetches the v_posed values two ahead, and
+// writes the caller's (B,V,3) layout through a padded shared-memory transpose (coalesced rows).
+// ---------------------------------------------------------------------------------------
+struct FwdSkinRecArgs {
+  const float* vposedT;  // [3V][Bp], rows in internal order
+  const float* betaT;    // [S+1][Bp]
+  const float* skin;     // [12J][Bp]
+  const float* rec;      // [V][rec_len]: w4 | idx4 | row(int) pad3 | S[3][SP] | kid[3] pad
+  float* out;            // (B,V,3)
+  int V, J, S, SP, rec_len, B, Bp, nb, use_kid, blocks_per_warp;
+};
+
+template <int SPMAX>
+__global__ void __launch_bounds__(256) k_fwd_skin_rec(const FwdSkinRecArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  float* s_skin = sm;                               // [12J][32]
+  float* s_tile = sm + (size_t)a.J * 12 * 32;       // [8 warps][32][97]
+  const int g = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Bp = a.Bp, b = g * 32 + lane;
+  {
+    const int n16 = a.J * 12 * 8;
+    for (int q = threadIdx.x; q < n16; q += 256) {
+      const int r = q >> 3, part = q & 7;
+      const float* src = a.skin + (size_t)r * Bp + g * 32 + part * 4;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_skin + r * 32 + part * 4);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+  }
+  float beta[SPMAX];
+#pragma unroll
+  for (int s = 0; s < SPMAX; ++s) beta[s] = (s < a.nb) ? SF_IM(a.betaT, s, Bp, b) : 0.f;
+  const float kid = a.use_kid ? SF_IM(a.betaT, a.S, Bp, b) : 0.f;
+  float* tile = s_tile + (size_t)warp * 32 * 97;
+  const int n_blocks = (a.V + 31) / 32;
+  for (int q = 0; q < a.blocks_per_warp; ++q) {
+    const int blk = (blockIdx.x * a.blocks_per_warp + q) * 8 + warp;
+    if (blk >= n_blocks) break;
+    const int v0 = blk * 32, nv = min(32, a.V - v0);
+    const float* rec = a.rec + (size_t)v0 * a.rec_len;
+    float4 nw = __ldg(reinterpret_cast<const float4*>(rec));
+    int4 nj = __ldg(reinterpret_cast<const int4*>(rec + 4));
+    int nrow = __float_as_int(__ldg(rec + 8));
+    float nx[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) nx[c] = SF_IM(a.vposedT, nrow * 3 + c, Bp, b);
+    float Sc[12];
+    int cj = -1;
+    for (int k = 0; k < nv; ++k) {
+      const float4 w4 = nw;
+      const int4 j4 = nj;
+      float x[3] = {nx[0], nx[1], nx[2]};
+      const float* sd = rec + 12;
+      if (k + 1 < nv) {
+        rec += a.rec_len;
+        nw = __ldg(reinterpret_cast<const float4*>(rec));
+        nj = __ldg(reinterpret_cast<const int4*>(rec + 4));
+        nrow = __float_as_int(__ldg(rec + 8));
+#pragma unroll
+        for (int c = 0; c < 3; ++c) nx[c] = SF_IM(a.vposedT, nrow * 3 + c, Bp, b);
+      }
+      float vs[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float y = x[c];
+#pragma unroll
+        for (int s2 = 0; s2 < SPMAX; s2 += 2) {
+          if (s2 < a.SP) {
+            const float2 sv = __ldg(reinterpret_cast<const float2*>(sd + c * a.SP + s2));
+            y = fmaf(sv.x, beta[s2], y);
+            y = fmaf(sv.y, beta[s2 + 1], y);
+          }
+        }
+        if (a.use_kid) y = fmaf(__ldg(sd + 3 * a.SP + c), kid, y);
+        vs[c] = y;
+      }
+      if (j4.x != cj) {
+        cj = j4.x;
+        const float* p = s_skin + (size_t)(cj * 12) * 32 + lane;
+#pragma unroll
+        for (int e = 0; e < 12; ++e) Sc[e] = p[e * 32];
+      }
+      float o[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        o[c] = w4.x * fmaf(Sc[c * 3], vs[0], fmaf(Sc[c * 3 + 1], vs[1], fmaf(Sc[c * 3 + 2], vs[2], Sc[9 + c])));
+      const float wk[3] = {w4.y, w4.z, w4.w};
+      const int jk[3] = {j4.y, j4.z, j4.w};
+#pragma unroll
+      for (int kk = 0; kk < 3; ++kk) {
+        if (wk[kk] != 0.f) {
+          const float* p = s_skin + (size_t)(jk[kk] * 12) * 32 + lane;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float y = fmaf(p[(c * 3) * 32], vs[0], fmaf(p[(c * 3 + 1) * 32], vs[1], fmaf(p[(c * 3 + 2) * 32], vs[2], p[(9 + c) * 32])));
+            o[c] = fmaf(wk[kk], y, o[c]);
+          }
+        }
+      }
+      tile[lane * 97 + k * 3 + 0] = o[0];
+      tile[lane * 97 + k * 3 + 1] = o[1];
+      tile[lane * 97 + k * 3 + 2] = o[2];
+    }
+    __syncwarp();
+    const int width = nv * 3;
+    for (int r = 0; r < 32; ++r) {
+      const int bb = g * 32 + r;
+      if (bb >= a.B) break;
+      float* dst = a.out + ((size_t)bb * a.V + v0) * 3;
+      for (int e = lane; e < width; e += 32) dst[e] = tile[r * 97 + e];
+    }
+    __syncwarp();
+  }
+}
+
 // CSR SpMM of BodyConverter.convert_vertices: out[b][r][:] = sum_k data[k] in[b][indices[k]][:].
 // One thread per (instance, output vertex, coordinate); rows hold ~3 non-zeros (barycentric).
 __global__ void k_csr_apply(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
@@ -248,8 +371,20 @@ extern "C" int smplfit_forward(const smplfit_model_t* m, int64_t batch, int rot_
     s.kid_shapedir = m->kid_shapedir; s.skin_idx = m->skin_idx; s.skin_w = m->skin_w; s.inv_order = m->inv_order;
     s.out = out_vertices; s.V = m->num_vertices; s.S = m->num_betas; s.B = B; s.Bp = Bp; s.skin_k = m->skin_k;
     s.use_kid = kid != nullptr; s.nb = betas ? min(n_betas, m->num_betas) : 0;
-    dim3 grid(((m->num_vertices + 31) / 32 + 2) / 3, Bp / 32);
-    SF_LAUNCH(k_fwd_skin, grid, 96, 0, st, s);
+    if (m->fwd_rec != nullptr && m->skin_k <= 4 && m->num_betas <= 16) {
+      FwdSkinRecArgs r;
+      r.vposedT = w.vposedT; r.betaT = w.betaT; r.skin = w.skin; r.rec = m->fwd_rec; r.out = out_vertices;
+      r.V = m->num_vertices; r.J = m->num_joints; r.S = m->num_betas; r.SP = (m->num_betas + 1) / 2 * 2;
+      r.rec_len = m->fwd_rec_len; r.B = B; r.Bp = Bp; r.nb = s.nb; r.use_kid = s.use_kid; r.blocks_per_warp = 4;
+      const int n_blocks = (r.V + 31) / 32;
+      const size_t smem = ((size_t)r.J * 12 * 32 + (size_t)8 * 32 * 97) * sizeof(float);
+      dim3 grid2((n_blocks + 8 * r.blocks_per_warp - 1) / (8 * r.blocks_per_warp), Bp / 32);
+      cudaFuncSetAttribute(k_fwd_skin_rec<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      SF_LAUNCH(k_fwd_skin_rec<16>, grid2, 256, smem, st, r);
+    } else {
+      dim3 grid(((m->num_vertices + 31) / 32 + 2) / 3, Bp / 32);
+      SF_LAUNCH(k_fwd_skin, grid, 96, 0, st, s);
+    }
   }
   SF_CHECK_LAST();
   return SMPLFIT_OK;

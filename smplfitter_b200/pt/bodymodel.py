@@ -129,6 +129,27 @@ class BodyModel(nn.Module):
             'posedirs_hi': f32(pd_hi), 'posedirs_lo': f32(pd_lo),
             'template_mesh_fit': f32(template_mesh[order]),
         }
+        # forward records (model order): see csrc/forward.cu k_fwd_skin_rec
+        S = self.num_betas
+        SP = (S + 1) // 2 * 2
+        self._fwd_rec_len = (12 + 3 * SP + 3 + 3) // 4 * 4
+        if K <= 4:
+            idx4 = np.zeros((V, 4), np.int32)
+            w4 = np.zeros((V, 4), np.float32)
+            idx4[:, :K], w4[:, :K] = skin_idx, skin_w
+            idx4[:, K:] = skin_idx[:, :1]
+            srt = np.argsort(-w4, axis=1, kind='stable')
+            idx4 = np.take_along_axis(idx4, srt, axis=1)
+            w4 = np.take_along_axis(w4, srt, axis=1)
+            frec = np.zeros((V, self._fwd_rec_len), np.float32)
+            frec[:, 0:4] = w4
+            frec[:, 4:8] = idx4.view(np.float32)
+            frec[:, 8] = inv_order.astype(np.int32).view(np.float32)
+            sd_np = self.shapedirs.numpy()
+            for x in range(3):
+                frec[:, 12 + x * SP:12 + x * SP + S] = sd_np[:, x, :]
+            frec[:, 12 + 3 * SP:12 + 3 * SP + 3] = self.kid_shapedir.numpy()
+            t['fwd_rec'] = f32(frec)
         for k, v in t.items():
             self.register_buffer('_t_' + k, v, persistent=False)
         self._dims = dict(
@@ -163,6 +184,8 @@ class BodyModel(nn.Module):
             if not buf.is_contiguous():
                 raise RuntimeError(f'smplfitter_b200: buffer {name} must be contiguous')
         s.fit_ns = 0
+        s.fwd_rec = self._t_fwd_rec.data_ptr() if hasattr(self, '_t_fwd_rec') else 0
+        s.fwd_rec_len = self._fwd_rec_len
         if extra:
             for k, v in extra.items():
                 setattr(s, k, v)
