@@ -47,9 +47,14 @@ def fit_case(model, B, mkw=None, **fkw):
     re = bm(fit['pose_rotvecs'], fit['shape_betas'], fit['trans'])
     v2v = (re['vertices'] - fw['vertices']).norm(dim=-1).mean().item() * 1000
     fwd_ms = timed(lambda: bm(pose, betas, trans))
+    _native.profile(True)
+    bm(pose, betas, trans)
+    torch.cuda.synchronize()
+    _native.profile(False)
+    fprof = {k: round(v[1], 3) for k, v in _native.profile_report().items()}
     return {'model': model, 'B': B, 'V': bm.num_vertices, 'J': bm.num_joints, 'S': bm.num_betas, 'ms': ms,
             'fits_per_s': B / ms * 1000, 'roundtrip_v2v_mm': v2v, 'top_kernels_ms': prof,
-            'forward_ms': fwd_ms, 'forwards_per_s': B / fwd_ms * 1000}
+            'forward_ms': fwd_ms, 'forwards_per_s': B / fwd_ms * 1000, 'forward_kernels_ms': fprof}
 
 
 def converter_case(B):

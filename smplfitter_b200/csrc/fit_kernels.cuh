@@ -758,20 +758,13 @@ __global__ void __launch_bounds__(256, 1) k_shape_pass_v2(const ShapeArgs a) {
     const float* rec = a.rec + (size_t)i0 * REC;
     float4 nw = __ldg(reinterpret_cast<const float4*>(rec));
     int4 nj = __ldg(reinterpret_cast<const int4*>(rec + 4));
-    float nt[3], nvp[3], nvw = 1.f;   // vertex i + 1
-    float mt[3], mvp[3], mvw = 1.f;   // vertex i + 2 (streamed values are prefetched two ahead)
-    const int i0b = min(i0 + 1, i1 - 1);
+    float nt[3], nvp[3], nvw = 1.f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       nt[c] = SF_IM(a.tT, i0 * 3 + c, Bp, b);
       nvp[c] = SF_IM(a.vposedT, i0 * 3 + c, Bp, b);
-      mt[c] = SF_IM(a.tT, i0b * 3 + c, Bp, b);
-      mvp[c] = SF_IM(a.vposedT, i0b * 3 + c, Bp, b);
     }
-    if (WEIGHTED) {
-      nvw = SF_IM(a.vwT, i0, Bp, b);
-      mvw = SF_IM(a.vwT, i0b, Bp, b);
-    }
+    if (WEIGHTED) nvw = SF_IM(a.vwT, i0, Bp, b);
     float4 Cq[NQ];
     int cj = -1;
     for (int i = i0; i < i1; ++i) {
@@ -789,18 +782,12 @@ __global__ void __launch_bounds__(256, 1) k_shape_pass_v2(const ShapeArgs a) {
         rec += REC;
         nw = __ldg(reinterpret_cast<const float4*>(rec));
         nj = __ldg(reinterpret_cast<const int4*>(rec + 4));
-        const int i2 = min(i + 2, i1 - 1);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          nt[c] = mt[c];
-          nvp[c] = mvp[c];
-          mt[c] = SF_IM(a.tT, i2 * 3 + c, Bp, b);
-          mvp[c] = SF_IM(a.vposedT, i2 * 3 + c, Bp, b);
+          nt[c] = SF_IM(a.tT, (i + 1) * 3 + c, Bp, b);
+          nvp[c] = SF_IM(a.vposedT, (i + 1) * 3 + c, Bp, b);
         }
-        if (WEIGHTED) {
-          nvw = mvw;
-          mvw = SF_IM(a.vwT, i2, Bp, b);
-        }
+        if (WEIGHTED) nvw = SF_IM(a.vwT, i + 1, Bp, b);
       }
       if (j4.x != cj) {
         cj = j4.x;
@@ -1015,27 +1002,18 @@ __global__ void __launch_bounds__(256) k_stats_rec(const StatsRecArgs a) {
     const float* rec = a.rec + (size_t)i0 * REC;
     float4 nw = make_float4(0.f, 0.f, 0.f, 0.f);
     int4 nj = make_int4(0, 0, 0, 0);
-    // streamed per-lane values are prefetched two vertices ahead (DRAM latency ~ one iteration)
     float nt[3], nx[3], nvw = 1.f;  // nx: v_posed (REF 1), explicit reference (REF 2), template (REF 0)
-    float mt[3], mx[3], mvw = 1.f;  // vertex i + 2
     if (REF == 1) {
       nw = __ldg(reinterpret_cast<const float4*>(rec));
       nj = __ldg(reinterpret_cast<const int4*>(rec + 4));
     }
-    const int i0b = min(i0 + 1, i1 - 1);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       nt[c] = SF_IM(a.tT, i0 * 3 + c, Bp, b);
       nx[c] = (REF == 0) ? __ldg(a.template_fit + i0 * 3 + c)
                          : SF_IM((REF == 1 ? a.vposedT : a.aT_in), i0 * 3 + c, Bp, b);
-      mt[c] = SF_IM(a.tT, i0b * 3 + c, Bp, b);
-      mx[c] = (REF == 0) ? __ldg(a.template_fit + i0b * 3 + c)
-                         : SF_IM((REF == 1 ? a.vposedT : a.aT_in), i0b * 3 + c, Bp, b);
     }
-    if (WEIGHTED) {
-      nvw = SF_IM(a.vwT, i0, Bp, b);
-      mvw = SF_IM(a.vwT, i0b, Bp, b);
-    }
+    if (WEIGHTED) nvw = SF_IM(a.vwT, i0, Bp, b);
     float Sc[12];
     int cj = -1;
     for (int i = i0; i < i1; ++i) {
@@ -1063,19 +1041,13 @@ __global__ void __launch_bounds__(256) k_stats_rec(const StatsRecArgs a) {
           nw = __ldg(reinterpret_cast<const float4*>(rec));
           nj = __ldg(reinterpret_cast<const int4*>(rec + 4));
         }
-        const int i2 = min(i + 2, i1 - 1);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          nt[c] = mt[c];
-          nx[c] = mx[c];
-          mt[c] = SF_IM(a.tT, i2 * 3 + c, Bp, b);
-          mx[c] = (REF == 0) ? __ldg(a.template_fit + i2 * 3 + c)
-                             : SF_IM((REF == 1 ? a.vposedT : a.aT_in), i2 * 3 + c, Bp, b);
+          nt[c] = SF_IM(a.tT, (i + 1) * 3 + c, Bp, b);
+          nx[c] = (REF == 0) ? __ldg(a.template_fit + (i + 1) * 3 + c)
+                             : SF_IM((REF == 1 ? a.vposedT : a.aT_in), (i + 1) * 3 + c, Bp, b);
         }
-        if (WEIGHTED) {
-          nvw = mvw;
-          mvw = SF_IM(a.vwT, i2, Bp, b);
-        }
+        if (WEIGHTED) nvw = SF_IM(a.vwT, i + 1, Bp, b);
       }
       float ref[3];
       if (REF == 1) {

@@ -188,11 +188,11 @@ struct FwdSkinRecArgs {
   int V, J, S, SP, rec_len, B, Bp, nb, use_kid, blocks_per_warp;
 };
 
-template <int SPMAX>
-__global__ void __launch_bounds__(256) k_fwd_skin_rec(const FwdSkinRecArgs a) {
+template <int SP>
+__global__ void __launch_bounds__(256, 2) k_fwd_skin_rec(const FwdSkinRecArgs a) {
   extern __shared__ __align__(16) float sm[];
   float* s_skin = sm;                               // [12J][32]
-  float* s_tile = sm + (size_t)a.J * 12 * 32;       // [8 warps][32][97]
+  float* s_tile = sm + (size_t)a.J * 12 * 32;       // [8 warps][32][49]: 16 vertices x 3 + pad
   const int g = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Bp = a.Bp, b = g * 32 + lane;
@@ -208,16 +208,16 @@ __global__ void __launch_bounds__(256) k_fwd_skin_rec(const FwdSkinRecArgs a) {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
   }
-  float beta[SPMAX];
+  float beta[SP];
 #pragma unroll
-  for (int s = 0; s < SPMAX; ++s) beta[s] = (s < a.nb) ? SF_IM(a.betaT, s, Bp, b) : 0.f;
+  for (int s = 0; s < SP; ++s) beta[s] = (s < a.nb) ? SF_IM(a.betaT, s, Bp, b) : 0.f;
   const float kid = a.use_kid ? SF_IM(a.betaT, a.S, Bp, b) : 0.f;
-  float* tile = s_tile + (size_t)warp * 32 * 97;
-  const int n_blocks = (a.V + 31) / 32;
+  float* tile = s_tile + (size_t)warp * 32 * 49;
+  const int n_blocks = (a.V + 15) / 16;
   for (int q = 0; q < a.blocks_per_warp; ++q) {
     const int blk = (blockIdx.x * a.blocks_per_warp + q) * 8 + warp;
     if (blk >= n_blocks) break;
-    const int v0 = blk * 32, nv = min(32, a.V - v0);
+    const int v0 = blk * 16, nv = min(16, a.V - v0);
     const float* rec = a.rec + (size_t)v0 * a.rec_len;
     float4 nw = __ldg(reinterpret_cast<const float4*>(rec));
     int4 nj = __ldg(reinterpret_cast<const int4*>(rec + 4));
@@ -245,14 +245,12 @@ __global__ void __launch_bounds__(256) k_fwd_skin_rec(const FwdSkinRecArgs a) {
       for (int c = 0; c < 3; ++c) {
         float y = x[c];
 #pragma unroll
-        for (int s2 = 0; s2 < SPMAX; s2 += 2) {
-          if (s2 < a.SP) {
-            const float2 sv = __ldg(reinterpret_cast<const float2*>(sd + c * a.SP + s2));
-            y = fmaf(sv.x, beta[s2], y);
-            y = fmaf(sv.y, beta[s2 + 1], y);
-          }
+        for (int s2 = 0; s2 < SP; s2 += 2) {
+          const float2 sv = __ldg(reinterpret_cast<const float2*>(sd + c * SP + s2));
+          y = fmaf(sv.x, beta[s2], y);
+          y = fmaf(sv.y, beta[s2 + 1], y);
         }
-        if (a.use_kid) y = fmaf(__ldg(sd + 3 * a.SP + c), kid, y);
+        if (a.use_kid) y = fmaf(__ldg(sd + 3 * SP + c), kid, y);
         vs[c] = y;
       }
       if (j4.x != cj) {
@@ -278,9 +276,9 @@ __global__ void __launch_bounds__(256) k_fwd_skin_rec(const FwdSkinRecArgs a) {
           }
         }
       }
-      tile[lane * 97 + k * 3 + 0] = o[0];
-      tile[lane * 97 + k * 3 + 1] = o[1];
-      tile[lane * 97 + k * 3 + 2] = o[2];
+      tile[lane * 49 + k * 3 + 0] = o[0];
+      tile[lane * 49 + k * 3 + 1] = o[1];
+      tile[lane * 49 + k * 3 + 2] = o[2];
     }
     __syncwarp();
     const int width = nv * 3;
@@ -288,7 +286,7 @@ __global__ void __launch_bounds__(256) k_fwd_skin_rec(const FwdSkinRecArgs a) {
       const int bb = g * 32 + r;
       if (bb >= a.B) break;
       float* dst = a.out + ((size_t)bb * a.V + v0) * 3;
-      for (int e = lane; e < width; e += 32) dst[e] = tile[r * 97 + e];
+      for (int e = lane; e < width; e += 32) dst[e] = tile[r * 49 + e];
     }
     __syncwarp();
   }
@@ -375,12 +373,26 @@ extern "C" int smplfit_forward(const smplfit_model_t* m, int64_t batch, int rot_
       FwdSkinRecArgs r;
       r.vposedT = w.vposedT; r.betaT = w.betaT; r.skin = w.skin; r.rec = m->fwd_rec; r.out = out_vertices;
       r.V = m->num_vertices; r.J = m->num_joints; r.S = m->num_betas; r.SP = (m->num_betas + 1) / 2 * 2;
-      r.rec_len = m->fwd_rec_len; r.B = B; r.Bp = Bp; r.nb = s.nb; r.use_kid = s.use_kid; r.blocks_per_warp = 4;
-      const int n_blocks = (r.V + 31) / 32;
-      const size_t smem = ((size_t)r.J * 12 * 32 + (size_t)8 * 32 * 97) * sizeof(float);
+      r.rec_len = m->fwd_rec_len; r.B = B; r.Bp = Bp; r.nb = s.nb; r.use_kid = s.use_kid; r.blocks_per_warp = 8;
+      const int n_blocks = (r.V + 15) / 16;
+      const size_t smem = ((size_t)r.J * 12 * 32 + (size_t)8 * 32 * 49) * sizeof(float);
       dim3 grid2((n_blocks + 8 * r.blocks_per_warp - 1) / (8 * r.blocks_per_warp), Bp / 32);
-      cudaFuncSetAttribute(k_fwd_skin_rec<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      SF_LAUNCH(k_fwd_skin_rec<16>, grid2, 256, smem, st, r);
+#define SF_FWD_SKIN(SPV)                                                                                       \
+  do {                                                                                                         \
+    cudaFuncSetAttribute(k_fwd_skin_rec<SPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+    SF_LAUNCH(k_fwd_skin_rec<SPV>, grid2, 256, smem, st, r);                                                   \
+  } while (0)
+      switch (r.SP) {
+        case 2: SF_FWD_SKIN(2); break;
+        case 4: SF_FWD_SKIN(4); break;
+        case 6: SF_FWD_SKIN(6); break;
+        case 8: SF_FWD_SKIN(8); break;
+        case 10: SF_FWD_SKIN(10); break;
+        case 12: SF_FWD_SKIN(12); break;
+        case 14: SF_FWD_SKIN(14); break;
+        default: SF_FWD_SKIN(16); break;
+      }
+#undef SF_FWD_SKIN
     } else {
       dim3 grid(((m->num_vertices + 31) / 32 + 2) / 3, Bp / 32);
       SF_LAUNCH(k_fwd_skin, grid, 96, 0, st, s);
