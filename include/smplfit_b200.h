@@ -109,7 +109,7 @@ typedef struct smplfit_fit_opts {
   int32_t want_rel_orient;     /* ... or 'relative_orientations' */
   int32_t shape_weights;       /* 1: the shape stage honours vertex/joint weights (pt/bodyfitter.py:1018-1028) */
   int32_t scale_mode;          /* 0 none, 1 scale_target, 2 scale_fit (last solve only) */
-  int32_t reserved;
+  int32_t share_beta;          /* 1: one set of betas for the whole batch (pt/bodyfitter.py:1266-1274) */
   float beta_regularizer;
   float beta_regularizer2;
   float kid_regularizer;       /* resolved on the host (None -> beta_regularizer) */

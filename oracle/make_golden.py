@@ -58,6 +58,8 @@ FIT_CASES = {
                               dict(num_iter=2, beta_regularizer=1.0, scale_target=True), dict(joints=True)),
     'fit_tiny_scale_fit': ('smpl_tiny', {}, {}, 4, 0.3, 0.002,
                            dict(num_iter=2, beta_regularizer=1.0, scale_fit=True), dict(joints=True)),
+    'fit_tiny_share_beta': ('smpl_tiny', {}, {}, 5, 0.3, 0.002,
+                            dict(num_iter=2, beta_regularizer=1.0, share_beta=True), dict(joints=True, same_betas=True)),
     'fit_smplx_tiny_it3': ('smplx_tiny', {}, {}, 3, 0.2, 0.002,
                            dict(num_iter=3, beta_regularizer=1.0), dict(joints=True)),
     'fit_smplx_tiny_nojoints': ('smplx_tiny', {}, {}, 3, 0.2, 0.002,
@@ -80,6 +82,8 @@ def case_inputs(name, model_name, mkw, B, pose_scale, noise, flags, seed):
     rs = np.random.RandomState(seed)
     pose = (rs.randn(B, 3 * J) * pose_scale).astype(np.float32)
     betas = (rs.randn(B, S) * 0.5).astype(np.float32)
+    if flags.get('same_betas'):
+        betas = np.repeat(betas[:1], B, axis=0)
     trans = rs.randn(B, 3).astype(np.float32)
     inp = dict(pose=pose, betas=betas, trans=trans)
     if flags.get('vw'):

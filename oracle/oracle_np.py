@@ -348,11 +348,16 @@ class OracleFitter:
 
     # ---- split-Gramian solve: pt/bodyfitter.py:960-1102 ----
     def fit_shape(self, glob, t, tj, vw, jw, reg, reg2, scale_reg=0.0, kid_reg=None,
-                  scale_target=False, scale_fit=False, beta_ref=None, kid_ref=None):
+                  scale_target=False, scale_fit=False, beta_ref=None, kid_ref=None, share_beta=False):
         if scale_target and scale_fit:
             raise ValueError('Only one of estim_scale_target and estim_scale_fit can be True')
         glob = np.asarray(glob, F32)
         rel, P, T, v_posed = self._shape_front(glob)
+        if share_beta:
+            if scale_target or scale_fit:
+                raise NotImplementedError('share_beta + scale (lstsq_partial_share with independent columns)')
+            return self._fit_shape_general(glob, rel, P, T, v_posed, t, tj, vw, jw, reg, reg2, scale_reg,
+                                           kid_reg, False, False, beta_ref, kid_ref, share_beta=True)
         if self.gram_supported and not (scale_target or scale_fit):
             return self._fit_shape_gram(glob, rel, P, T, v_posed, t, tj, vw, jw, reg, reg2, beta_ref)
         return self._fit_shape_general(glob, rel, P, T, v_posed, t, tj, vw, jw, reg, reg2, scale_reg,
@@ -409,7 +414,7 @@ class OracleFitter:
 
     # ---- general solve (kid / scale unknowns, float32): pt/bodyfitter.py:1104-1319, pt/lstsq.py:7-29 ----
     def _fit_shape_general(self, glob, rel, P, T, v_posed, t, tj, vw, jw, reg, reg2, scale_reg,
-                           kid_reg, scale_target, scale_fit, beta_ref, kid_ref):
+                           kid_reg, scale_target, scale_fit, beta_ref, kid_ref, share_beta=False):
         m = self.m
         B, S = t.shape[0], self.S
         rot_blend = np.einsum('vj,bjCc->bvCc', m.weights, glob)
@@ -466,7 +471,14 @@ class OracleFitter:
         WA = w3[:, :, None] * A2
         G = np.einsum('bns,bnt->bst', WA, A2) + np.diag(lam)[None]
         rhs = np.einsum('bns,bn->bs', WA, b2) + lam * ref
-        x = np.linalg.solve(G.astype(F32), rhs.astype(F32)[..., None])[..., 0].astype(F32)
+        if share_beta:
+            # pt/lstsq.py:43-45 -> lstsq(..., shared=True): diag(lambda) is inside the per-instance
+            # Gramian that gets summed over the batch, and the regulariser-reference term is not passed
+            Gs = G.sum(0)
+            rs_ = np.einsum('bns,bn->bs', WA, b2).sum(0)
+            x = np.broadcast_to(np.linalg.solve(Gs.astype(F32), rs_.astype(F32)), (B, npar)).astype(F32)
+        else:
+            x = np.linalg.solve(G.astype(F32), rhs.astype(F32)[..., None])[..., 0].astype(F32)
         trans = (mean_b[:, 0] - np.einsum('bcs,bs->bc', mean_A[:, 0], x)).astype(F32)
         beta = x[:, :S]
         out = dict(shape_betas=beta, trans=trans, relative_orientations=rel)
@@ -534,8 +546,6 @@ class OracleFitter:
             kid_regularizer=None, share_beta=False, final_adjust_rots=True, scale_target=False,
             scale_fit=False, initial_pose_rotvecs=None, initial_shape_betas=None,
             initial_kid_factor=None, requested_keys=None):
-        if share_beta:
-            raise NotImplementedError('share_beta is outside the oracle (SURVEY.md section 8 f-2)')
         if requested_keys is None:
             requested_keys = ['pose_rotvecs']
         m = self.m
@@ -558,11 +568,11 @@ class OracleFitter:
             glob = self.fit_global_rotations(t, tj, self.template_mesh[None], m.J_template[None], vw, jw)
         for _ in range(num_iter - 1):
             res = self.fit_shape(glob, t, tj, vw, jw, beta_regularizer, beta_regularizer2, 0.0,
-                                 kid_regularizer, False, False, initial_shape_betas, initial_kid_factor)
+                                 kid_regularizer, False, False, initial_shape_betas, initial_kid_factor, share_beta)
             rj = res['joints'] if tj is not None else None
             glob = self.fit_global_rotations(t, tj, res['vertices'], rj, vw, jw) @ glob
         res = self.fit_shape(glob, t, tj, vw, jw, beta_regularizer, beta_regularizer2, scale_regularizer,
-                             kid_regularizer, scale_target, scale_fit, initial_shape_betas, initial_kid_factor)
+                             kid_regularizer, scale_target, scale_fit, initial_shape_betas, initial_kid_factor, share_beta)
         ref_v = res['vertices']
         ref_j = res['joints'] if (tj is not None or final_adjust_rots) else None
         kid = res['kid_factor'] if self.enable_kid else None

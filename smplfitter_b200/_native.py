@@ -50,7 +50,7 @@ class FitOpts(C.Structure):
     _fields_ = [
         ('num_iter', C.c_int32), ('final_adjust_rots', C.c_int32), ('enable_kid', C.c_int32),
         ('want_pose_rotvecs', C.c_int32), ('want_rel_orient', C.c_int32), ('shape_weights', C.c_int32),
-        ('scale_mode', C.c_int32), ('reserved', C.c_int32),
+        ('scale_mode', C.c_int32), ('share_beta', C.c_int32),
         ('beta_regularizer', C.c_float), ('beta_regularizer2', C.c_float),
         ('kid_regularizer', C.c_float), ('scale_regularizer', C.c_float),
     ]

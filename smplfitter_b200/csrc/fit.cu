@@ -20,7 +20,7 @@ struct FitWs {
   double* Gd;
   float *mean, *tT, *tjT, *vwT, *jwT, *vposedT, *R, *R2, *RT, *Pext, *feat, *gpart, *beta, *trans, *refj,
       *skin, *spart, *aT, *ajT, *initjT, *RT4, *zpart, *scale, *mpart;
-  double* Zd;
+  double *Zd, *Cd, *sums;
   void* tc_scratch;
   size_t bytes;
 };
@@ -61,6 +61,8 @@ static FitWs carve(void* base, const smplfit_model_t* m, int64_t B, int has_join
   w.initjT = has_init ? c.take<float>((size_t)3 * J * Bp) : nullptr;
   w.zpart = c.take<float>((size_t)scale_chunks(m) * (NS + 5) * Bp);
   w.Zd = c.take<double>((size_t)(NS + 5) * Bp);
+  w.Cd = c.take<double>((size_t)(NS * (NS + 1) / 2 + NS) * Bp);
+  w.sums = c.take<double>((size_t)(NS * (NS + 1) / 2 + 2 * NS + 8));
   w.scale = c.take<float>(Bp);
   w.mpart = c.take<float>((size_t)(moment_blocks(V) + 1) * 9 * Bp);
   w.tc_scratch = c.take<char>(vposed_tc_scratch_bytes(m, (int)Bp));
@@ -138,6 +140,9 @@ static void run_shape(FitCtx& c, int scale_mode, const float* beta_ref, const fl
     launch_scale_pass(sz, m->fit_ns, scale_mode, c.groups, c.st);
     // the scale pass writes its own partial layout: point the solve at it
     launch_shape_solve_scale(so, c.w.Gd, c.w.Zd, m->fit_ns, c.groups, c.st);
+  } else if (o->share_beta) {
+    const int ne = m->fit_ns * (m->fit_ns + 1) / 2 + m->fit_ns;
+    launch_shape_solve_shared(so, c.w.Gd, c.w.Cd, c.w.sums, c.w.sums + ne, m->fit_ns, c.groups, c.st);
   } else {
     launch_shape_solve(so, c.w.Gd, m->fit_ns, c.groups, c.st);
   }
@@ -250,6 +255,8 @@ extern "C" int smplfit_fit(const smplfit_model_t* m, int64_t batch, const float*
   if (o->num_iter < 1) return fail(SMPLFIT_ERR_ARG, "num_iter must be >= 1");
   if (o->scale_mode < 0 || o->scale_mode > 2) return fail(SMPLFIT_ERR_ARG, "bad scale_mode");
   if (o->scale_mode != 0 && !out_scale_corr) return fail(SMPLFIT_ERR_ARG, "scale_corr output required");
+  if (o->scale_mode != 0 && o->share_beta)
+    return fail(SMPLFIT_ERR_UNSUPPORTED, "share_beta together with scale estimation is not implemented");
   if ((o->enable_kid != 0) != (m->fit_ns == m->num_betas + 1))
     return fail(SMPLFIT_ERR_ARG, "enable_kid does not match the fitter tables");
   const bool has_init = init_vertices != nullptr;

@@ -54,4 +54,21 @@ void launch_shape_solve_scale(const SolveArgs& a, double* Gd, double* Zd, int ns
   SF_NS_SWITCH(ns, (solve_scale_t<NS>(a, Gd, Zd, groups, st)));
 }
 
+template <int NS>
+static void solve_shared_t(const SolveArgs& so, double* Gd, double* Cd, double* sums, double* x, int groups,
+                           cudaStream_t st) {
+  constexpr int NG = NS * (NS + 1) / 2;
+  SF_LAUNCH(k_gram_entries<NS>, dim3(groups, ShapeAcc<NS>::N), 32, 0, st, so, Gd);
+  SF_LAUNCH(k_center_entries<NS>, groups, 32, 0, st, so, (const double*)Gd, Cd);
+  SF_LAUNCH(k_batch_sum, NG + NS, 256, 0, st, (const double*)Cd, so.Bp, sums);
+  SF_LAUNCH(k_shared_solve<NS>, 1, 32, 0, st, so, (const double*)sums, x);
+  SF_LAUNCH(k_shared_apply<NS>, groups, 32, 0, st, so, (const double*)Gd, (const double*)x);
+  SF_LAUNCH(k_shape_out, dim3(groups, so.J), 32, 0, st, so, NS);
+}
+
+void launch_shape_solve_shared(const SolveArgs& a, double* Gd, double* Cd, double* sums, double* x, int ns, int groups,
+                               cudaStream_t st) {
+  SF_NS_SWITCH(ns, (solve_shared_t<NS>(a, Gd, Cd, sums, x, groups, st)));
+}
+
 }  // namespace sf

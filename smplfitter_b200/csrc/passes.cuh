@@ -23,6 +23,9 @@ void launch_shape_solve(const SolveArgs& a, double* Gd, int ns, int groups, cuda
 int scale_chunks(const smplfit_model_t* m);
 void launch_scale_pass(const ShapeArgs& a, int ns, int mode, int groups, cudaStream_t st);
 void launch_shape_solve_scale(const SolveArgs& a, double* Gd, double* Zd, int ns, int groups, cudaStream_t st);
+// share_beta: Cd = [NG+NS][Bp] doubles, sums = NG+NS doubles, x = NS doubles (device scratch)
+void launch_shape_solve_shared(const SolveArgs& a, double* Gd, double* Cd, double* sums, double* x, int ns, int groups,
+                               cudaStream_t st);
 void launch_stats(const StatsArgs& legacy, const StatsRecArgs& rec, int ns, int ref_mode, bool weighted, bool use_rec,
                   int groups, cudaStream_t st);
 }  // namespace sf

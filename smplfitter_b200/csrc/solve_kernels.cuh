@@ -816,4 +816,95 @@ static __global__ void __launch_bounds__(32) k_set_shape(const float* __restrict
   for (int c = 0; c < 3; ++c) SF_IM(trans, c, Bp, b) = 0.f;
 }
 
+// ---------------------------------------------------------------------------------------
+// share_beta (pt/bodyfitter.py:1266-1274, pt/lstsq.py:24-26, :43-45): the centred, regularised
+// normal equations of all instances are summed and solved once; the translation stays per
+// instance.  Mirrors the reference's shared branch exactly: the regulariser is added per instance
+// *before* the batch sum (i.e. B times) and the regulariser-reference term is not applied.
+//   k_center_entries : per instance  Gc = G - SA^T SA / W,  rc = r - SA^T Sb / W   (upper + rhs)
+//   k_batch_sum      : deterministic sum over the batch, one CTA per entry
+//   k_shared_solve   : one thread: + B * diag(lambda), Cholesky
+//   k_shared_apply   : per instance: beta = x, trans = (Sb - SA x) / W
+// ---------------------------------------------------------------------------------------
+template <int NS>
+__global__ void __launch_bounds__(32) k_center_entries(const SolveArgs a, const double* __restrict__ Gd,
+                                                       double* __restrict__ Cd) {
+  constexpr int NG = NS * (NS + 1) / 2;
+  const int b = blockIdx.x * 32 + threadIdx.x;
+  if (b >= a.Bp) return;
+  const int Bp = a.Bp;
+  const bool live = b < a.B;
+  double SA[3][NS], Sb[3];
+  for (int c = 0; c < 3; ++c) Sb[c] = Gd[(size_t)(NG + NS + c) * Bp + b];
+  for (int c = 0; c < 3; ++c)
+    for (int s = 0; s < NS; ++s) SA[c][s] = Gd[(size_t)(NG + NS + 3 + c * NS + s) * Bp + b];
+  const double W = Gd[(size_t)(NG + NS + 3 + 3 * NS) * Bp + b];
+  const double Ws = (W == 0.0) ? 1.0 : W;
+  int o = 0;
+  for (int s = 0; s < NS; ++s)
+    for (int t = s; t < NS; ++t) {
+      double g = Gd[(size_t)o * Bp + b];
+      for (int c = 0; c < 3; ++c) g -= SA[c][s] * SA[c][t] / Ws;
+      Cd[(size_t)o * Bp + b] = live ? g : 0.0;
+      ++o;
+    }
+  for (int s = 0; s < NS; ++s) {
+    double rc = Gd[(size_t)(NG + s) * Bp + b];
+    for (int c = 0; c < 3; ++c) rc -= SA[c][s] * Sb[c] / Ws;
+    Cd[(size_t)(NG + s) * Bp + b] = live ? rc : 0.0;
+  }
+}
+
+static __global__ void __launch_bounds__(256) k_batch_sum(const double* __restrict__ Cd, int Bp, double* __restrict__ out) {
+  __shared__ double red[256];
+  const int e = blockIdx.x;
+  double acc = 0.0;
+  for (int b = threadIdx.x; b < Bp; b += 256) acc += Cd[(size_t)e * Bp + b];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int h = 128; h > 0; h >>= 1) {
+    if (threadIdx.x < h) red[threadIdx.x] += red[threadIdx.x + h];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[e] = red[0];
+}
+
+template <int NS>
+__global__ void k_shared_solve(const SolveArgs a, const double* __restrict__ sums, double* __restrict__ x) {
+  constexpr int NG = NS * (NS + 1) / 2;
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double G[NS][NS], rhs[NS];
+  int o = 0;
+  for (int s = 0; s < NS; ++s)
+    for (int t = s; t < NS; ++t) {
+      G[s][t] = sums[o];
+      G[t][s] = sums[o];
+      ++o;
+    }
+  for (int s = 0; s < NS; ++s) {
+    const double lam = (s >= a.S) ? (double)a.kid_reg : ((s < 2) ? (double)a.reg2 : (double)a.reg);
+    G[s][s] += lam * (double)a.B;  // diag(lambda) added per instance, then summed (pt/lstsq.py:16-26)
+    rhs[s] = sums[NG + s];
+  }
+  chol_solve<NS>(G, rhs, NS);
+  for (int s = 0; s < NS; ++s) x[s] = rhs[s];
+}
+
+template <int NS>
+__global__ void __launch_bounds__(32) k_shared_apply(const SolveArgs a, const double* __restrict__ Gd,
+                                                     const double* __restrict__ x) {
+  constexpr int NG = NS * (NS + 1) / 2;
+  const int b = blockIdx.x * 32 + threadIdx.x;
+  if (b >= a.Bp) return;
+  const int Bp = a.Bp;
+  const double W = Gd[(size_t)(NG + NS + 3 + 3 * NS) * Bp + b];
+  const double Ws = (W == 0.0) ? 1.0 : W;
+  for (int s = 0; s < NS; ++s) SF_IM(a.beta, s, Bp, b) = (float)x[s];
+  for (int c = 0; c < 3; ++c) {
+    double m = Gd[(size_t)(NG + NS + c) * Bp + b] / Ws;
+    for (int s = 0; s < NS; ++s) m -= Gd[(size_t)(NG + NS + 3 + c * NS + s) * Bp + b] / Ws * x[s];
+    SF_IM(a.trans, c, Bp, b) = (float)m;
+  }
+}
+
 }  // namespace sf

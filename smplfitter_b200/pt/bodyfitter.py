@@ -182,9 +182,9 @@ class BodyFitter(nn.Module):
             requested_keys = ['pose_rotvecs']
         if scale_target and scale_fit:
             raise ValueError('Only one of estim_scale_target and estim_scale_fit can be True')
-        if share_beta:
-            raise NotImplementedError('share_beta is not implemented on the CUDA path (SURVEY.md 8f-2)')
         scale_mode = 1 if scale_target else (2 if scale_fit else 0)
+        if share_beta and scale_mode:
+            raise NotImplementedError('share_beta together with scale estimation is not implemented on the CUDA path')
         bm = self.body_model
         dev = bm.v_template.device
         _native.require_cuda(bm.v_template, 'the body model')
@@ -224,6 +224,7 @@ class BodyFitter(nn.Module):
         o = self._opts(num_iter, final_adjust_rots, requested_keys,
                        self._shape_weights_rule(tj, vw, jw), beta_regularizer, beta_regularizer2,
                        kid_regularizer, scale_mode, scale_regularizer)
+        o.share_beta = int(bool(share_beta))
         L = _native.lib()
         s = self._struct()
         ws_bytes = L.smplfit_fit_workspace_bytes(C.byref(s), B, C.byref(o), int(tj is not None),
