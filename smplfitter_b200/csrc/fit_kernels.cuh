@@ -956,15 +956,53 @@ struct StatsRecArgs {
   int n_segments, Bp, J, all_segments, segs_per_warp;
 };
 
+// 1-D bulk async copy global -> shared with mbarrier completion (TMA engine, UBLKCP)
+__device__ __forceinline__ void sf_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(dst)),
+               "l"(src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+__device__ __forceinline__ void sf_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void sf_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void sf_mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+constexpr int STATS_SEG_MAX = 32;  // must be >= the segment length of the model tables
+
 template <int NS, int REF, bool WEIGHTED>
 __global__ void __launch_bounds__(256) k_stats_rec(const StatsRecArgs a) {
-  extern __shared__ __align__(16) float s_skin[];  // [12J][32]
+  extern __shared__ __align__(16) float s_skin[];  // [12J][32], then per-warp record buffers + mbarriers (REF == 1)
   constexpr int REC = Rec<NS>::LEN;
   const int g = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Bp = a.Bp;
   const int b = g * 32 + lane;
+  float* s_rec = s_skin + (size_t)a.J * 12 * 32 + (size_t)warp * STATS_SEG_MAX * REC;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_skin + (size_t)a.J * 12 * 32 + (size_t)8 * STATS_SEG_MAX * REC) + warp;
+  uint32_t rec_phase = 0;
   if (REF == 1) {
+    if (lane == 0) sf_mbar_init(s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     const int n16 = a.J * 12 * 8;
     for (int q = threadIdx.x; q < n16; q += 256) {
       const int r = q >> 3, part = q & 7;
@@ -987,6 +1025,16 @@ __global__ void __launch_bounds__(256) k_stats_rec(const StatsRecArgs a) {
     const int part = a.seg_part[seg];
     const bool stat = (a.part_flags[part] & 1) != 0;
     if (!stat && !(REF == 1 && a.aT_out != nullptr && a.all_segments)) continue;
+    const int i0 = a.seg_start[seg], i1 = a.seg_start[seg + 1];
+    if (REF == 1) {
+      // stage this segment's records (one contiguous block) with a single bulk async copy
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t bytes = (uint32_t)(i1 - i0) * REC * 4;
+        sf_mbar_expect_tx(s_bar, bytes);
+        sf_bulk_g2s(s_rec, a.rec + (size_t)i0 * REC, bytes, s_bar);
+      }
+    }
     float ct[3], ca[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -998,15 +1046,7 @@ __global__ void __launch_bounds__(256) k_stats_rec(const StatsRecArgs a) {
     for (int e = 0; e < 9; ++e) M[e] = 0.f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) st[c] = sa[c] = 0.f;
-    const int i0 = a.seg_start[seg], i1 = a.seg_start[seg + 1];
-    const float* rec = a.rec + (size_t)i0 * REC;
-    float4 nw = make_float4(0.f, 0.f, 0.f, 0.f);
-    int4 nj = make_int4(0, 0, 0, 0);
     float nt[3], nx[3], nvw = 1.f;  // nx: v_posed (REF 1), explicit reference (REF 2), template (REF 0)
-    if (REF == 1) {
-      nw = __ldg(reinterpret_cast<const float4*>(rec));
-      nj = __ldg(reinterpret_cast<const int4*>(rec + 4));
-    }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       nt[c] = SF_IM(a.tT, i0 * 3 + c, Bp, b);
@@ -1014,11 +1054,13 @@ __global__ void __launch_bounds__(256) k_stats_rec(const StatsRecArgs a) {
                          : SF_IM((REF == 1 ? a.vposedT : a.aT_in), i0 * 3 + c, Bp, b);
     }
     if (WEIGHTED) nvw = SF_IM(a.vwT, i0, Bp, b);
+    if (REF == 1) {
+      sf_mbar_wait(s_bar, rec_phase);
+      rec_phase ^= 1;
+    }
     float Sc[12];
     int cj = -1;
     for (int i = i0; i < i1; ++i) {
-      const float4 w4 = nw;
-      const int4 j4 = nj;
       float t[3], x[3];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -1026,21 +1068,7 @@ __global__ void __launch_bounds__(256) k_stats_rec(const StatsRecArgs a) {
         x[c] = nx[c];
       }
       const float wv = nvw;
-      float S[3 * Rec<NS>::NSP];
-      if (REF == 1) {
-#pragma unroll
-        for (int qq = 0; qq < 3 * Rec<NS>::NSP / 2; ++qq) {
-          const float2 y = __ldg(reinterpret_cast<const float2*>(rec + 8) + qq);
-          S[2 * qq] = y.x;
-          S[2 * qq + 1] = y.y;
-        }
-      }
       if (i + 1 < i1) {
-        rec += REC;
-        if (REF == 1) {
-          nw = __ldg(reinterpret_cast<const float4*>(rec));
-          nj = __ldg(reinterpret_cast<const int4*>(rec + 4));
-        }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           nt[c] = SF_IM(a.tT, (i + 1) * 3 + c, Bp, b);
@@ -1051,12 +1079,19 @@ __global__ void __launch_bounds__(256) k_stats_rec(const StatsRecArgs a) {
       }
       float ref[3];
       if (REF == 1) {
+        const float* rec = s_rec + (size_t)(i - i0) * REC;  // shared-memory broadcasts
+        const float4 w4 = *reinterpret_cast<const float4*>(rec);
+        const int4 j4 = *reinterpret_cast<const int4*>(rec + 4);
         float vs[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           float y = x[c];
 #pragma unroll
-          for (int s = 0; s < NS; ++s) y = fmaf(S[c * Rec<NS>::NSP + s], beta[s], y);
+          for (int s2 = 0; s2 < Rec<NS>::NSP; s2 += 2) {
+            const float2 sv = *reinterpret_cast<const float2*>(rec + 8 + c * Rec<NS>::NSP + s2);
+            y = fmaf(sv.x, beta[s2], y);
+            if (s2 + 1 < NS) y = fmaf(sv.y, beta[s2 + 1], y);
+          }
           vs[c] = y;
         }
         if (j4.x != cj) {
