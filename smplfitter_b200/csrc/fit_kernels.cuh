@@ -700,6 +700,68 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_shape_pass_rec(const ShapeArg
 //    (one extra lower-triangle entry per odd row, dropped when the partials are written).
 // Same outputs and partial layout as k_shape_pass_rec.
 // ---------------------------------------------------------------------------------------
+// 1-D bulk async copy global -> shared with mbarrier completion (TMA engine, UBLKCP)
+__device__ __forceinline__ void sf_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(dst)),
+               "l"(src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+__device__ __forceinline__ void sf_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void sf_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void sf_mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+constexpr int REC_SUB = 16;  // vertices per staged record sub-block
+
+// Per-warp double-buffered staging of per-vertex records (contiguous in the internal order) with
+// 1-D bulk async copies: sub-block k lives in buffer k & 1; sub-block k+1 is in flight while k is
+// processed.  All calls are warp-uniform.
+template <int REC>
+struct RecStager {
+  float* buf;      // [2][REC_SUB * REC]
+  uint64_t* bar;   // [2]
+  const float* src;
+  int i0, i1;
+  uint32_t phase;
+  __device__ __forceinline__ void issue(int k, int lane) {  // stage sub-block k (if it exists)
+    const int first = i0 + k * REC_SUB;
+    __syncwarp();
+    if (first < i1 && lane == 0) {
+      const uint32_t bytes = (uint32_t)min(REC_SUB, i1 - first) * REC * 4;
+      sf_mbar_expect_tx(bar + (k & 1), bytes);
+      sf_bulk_g2s(buf + (size_t)(k & 1) * REC_SUB * REC, src + (size_t)first * REC, bytes, bar + (k & 1));
+    }
+  }
+  __device__ __forceinline__ void wait(int k) {
+    sf_mbar_wait(bar + (k & 1), (phase >> (k & 1)) & 1u);
+    phase ^= 1u << (k & 1);
+  }
+  __device__ __forceinline__ const float* rec(int i) const {
+    const int d = i - i0;
+    return buf + (size_t)((d / REC_SUB) & 1) * REC_SUB * REC + (size_t)(d % REC_SUB) * REC;
+  }
+};
+
 __device__ __forceinline__ float2 sf_fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ float2 sf_mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
 
@@ -726,6 +788,11 @@ __global__ void __launch_bounds__(256, 1) k_shape_pass_v2(const ShapeArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Bp = a.Bp;
   const int b = g * 32 + lane;
+  if (lane == 0) {
+    sf_mbar_init(reinterpret_cast<uint64_t*>(s_rt + (size_t)a.J * NQ * 128 + (size_t)8 * 2 * REC_SUB * REC) + 2 * warp, 1);
+    sf_mbar_init(reinterpret_cast<uint64_t*>(s_rt + (size_t)a.J * NQ * 128 + (size_t)8 * 2 * REC_SUB * REC) + 2 * warp + 1, 1);
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   {
     // RT4 is [J*NQ][Bp] float4: the CTA's slice of each (joint, quad) row is 32 x 16 B contiguous
     const int n = a.J * NQ * 32;
@@ -740,6 +807,11 @@ __global__ void __launch_bounds__(256, 1) k_shape_pass_v2(const ShapeArgs a) {
     __syncthreads();
   }
   const float4* sq = reinterpret_cast<const float4*>(s_rt);
+  RecStager<REC> rs;
+  rs.buf = s_rt + (size_t)a.J * NQ * 128 + (size_t)warp * 2 * REC_SUB * REC;
+  rs.bar = reinterpret_cast<uint64_t*>(s_rt + (size_t)a.J * NQ * 128 + (size_t)8 * 2 * REC_SUB * REC) + 2 * warp;
+  rs.src = a.rec;
+  rs.phase = 0;
   const int chunk = blockIdx.x * 8 + warp;
   const bool active = chunk < a.n_chunks;
   float2 G2[NP], r2[H], SA2[WEIGHTED ? 3 * H : 1];
@@ -755,9 +827,13 @@ __global__ void __launch_bounds__(256, 1) k_shape_pass_v2(const ShapeArgs a) {
   Sb[0] = Sb[1] = Sb[2] = 0.f;
   if (active) {
     const int i0 = chunk * a.chunk_len, i1 = min(a.V, i0 + a.chunk_len);
-    const float* rec = a.rec + (size_t)i0 * REC;
-    float4 nw = __ldg(reinterpret_cast<const float4*>(rec));
-    int4 nj = __ldg(reinterpret_cast<const int4*>(rec + 4));
+    rs.i0 = i0;
+    rs.i1 = i1;
+    rs.issue(0, lane);
+    rs.issue(1, lane);
+    rs.wait(0);
+    float4 nw = *reinterpret_cast<const float4*>(rs.rec(i0));
+    int4 nj = *reinterpret_cast<const int4*>(rs.rec(i0) + 4);
     float nt[3], nvp[3], nvw = 1.f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -777,11 +853,13 @@ __global__ void __launch_bounds__(256, 1) k_shape_pass_v2(const ShapeArgs a) {
         vp[c] = nvp[c];
       }
       const float wv = nvw;
-      const float2* sd2 = reinterpret_cast<const float2*>(rec + 8);  // shapedirs[x][sp] pairs, NSP/2 per x
+      if ((i - i0) % REC_SUB == 0 && i > i0) rs.issue((i - i0) / REC_SUB + 1, lane);  // buffer of the previous sub-block is free
+      const float2* sd2 = reinterpret_cast<const float2*>(rs.rec(i) + 8);  // shapedirs[x][sp] pairs (shared memory)
       if (i + 1 < i1) {
-        rec += REC;
-        nw = __ldg(reinterpret_cast<const float4*>(rec));
-        nj = __ldg(reinterpret_cast<const int4*>(rec + 4));
+        if ((i + 1 - i0) % REC_SUB == 0) rs.wait((i + 1 - i0) / REC_SUB);
+        const float* recn = rs.rec(i + 1);
+        nw = *reinterpret_cast<const float4*>(recn);
+        nj = *reinterpret_cast<const int4*>(recn + 4);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           nt[c] = SF_IM(a.tT, (i + 1) * 3 + c, Bp, b);
@@ -832,7 +910,7 @@ __global__ void __launch_bounds__(256, 1) k_shape_pass_v2(const ShapeArgs a) {
       for (int x = 0; x < 3; ++x) {
         float2 S2[H];
 #pragma unroll
-        for (int sp = 0; sp < H; ++sp) S2[sp] = __ldg(sd2 + x * H + sp);
+        for (int sp = 0; sp < H; ++sp) S2[sp] = sd2[x * H + sp];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const float r = rowv(c * 3 + x);
@@ -956,39 +1034,6 @@ struct StatsRecArgs {
   int n_segments, Bp, J, all_segments, segs_per_warp;
 };
 
-// 1-D bulk async copy global -> shared with mbarrier completion (TMA engine, UBLKCP)
-__device__ __forceinline__ void sf_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   (uint32_t)__cvta_generic_to_shared(dst)),
-               "l"(src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
-               : "memory");
-}
-__device__ __forceinline__ void sf_mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
-}
-__device__ __forceinline__ void sf_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void sf_mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-
-constexpr int STATS_SEG_MAX = 32;  // must be >= the segment length of the model tables
-
 template <int NS, int REF, bool WEIGHTED>
 __global__ void __launch_bounds__(256) k_stats_rec(const StatsRecArgs a) {
   extern __shared__ __align__(16) float s_skin[];  // [12J][32], then per-warp record buffers + mbarriers (REF == 1)
@@ -997,11 +1042,16 @@ __global__ void __launch_bounds__(256) k_stats_rec(const StatsRecArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Bp = a.Bp;
   const int b = g * 32 + lane;
-  float* s_rec = s_skin + (size_t)a.J * 12 * 32 + (size_t)warp * STATS_SEG_MAX * REC;
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_skin + (size_t)a.J * 12 * 32 + (size_t)8 * STATS_SEG_MAX * REC) + warp;
-  uint32_t rec_phase = 0;
+  RecStager<REC> rs;
+  rs.buf = s_skin + (size_t)a.J * 12 * 32 + (size_t)warp * 2 * REC_SUB * REC;
+  rs.bar = reinterpret_cast<uint64_t*>(s_skin + (size_t)a.J * 12 * 32 + (size_t)8 * 2 * REC_SUB * REC) + 2 * warp;
+  rs.src = a.rec;
+  rs.phase = 0;
   if (REF == 1) {
-    if (lane == 0) sf_mbar_init(s_bar, 1);
+    if (lane == 0) {
+      sf_mbar_init(rs.bar, 1);
+      sf_mbar_init(rs.bar + 1, 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     const int n16 = a.J * 12 * 8;
     for (int q = threadIdx.x; q < n16; q += 256) {
@@ -1026,14 +1076,11 @@ __global__ void __launch_bounds__(256) k_stats_rec(const StatsRecArgs a) {
     const bool stat = (a.part_flags[part] & 1) != 0;
     if (!stat && !(REF == 1 && a.aT_out != nullptr && a.all_segments)) continue;
     const int i0 = a.seg_start[seg], i1 = a.seg_start[seg + 1];
+    rs.i0 = i0;
+    rs.i1 = i1;
     if (REF == 1) {
-      // stage this segment's records (one contiguous block) with a single bulk async copy
-      __syncwarp();
-      if (lane == 0) {
-        const uint32_t bytes = (uint32_t)(i1 - i0) * REC * 4;
-        sf_mbar_expect_tx(s_bar, bytes);
-        sf_bulk_g2s(s_rec, a.rec + (size_t)i0 * REC, bytes, s_bar);
-      }
+      rs.issue(0, lane);
+      rs.issue(1, lane);
     }
     float ct[3], ca[3];
 #pragma unroll
@@ -1054,13 +1101,14 @@ __global__ void __launch_bounds__(256) k_stats_rec(const StatsRecArgs a) {
                          : SF_IM((REF == 1 ? a.vposedT : a.aT_in), i0 * 3 + c, Bp, b);
     }
     if (WEIGHTED) nvw = SF_IM(a.vwT, i0, Bp, b);
-    if (REF == 1) {
-      sf_mbar_wait(s_bar, rec_phase);
-      rec_phase ^= 1;
-    }
     float Sc[12];
     int cj = -1;
     for (int i = i0; i < i1; ++i) {
+      if (REF == 1 && (i - i0) % REC_SUB == 0) {  // entering sub-block k (warp-uniform)
+        const int k = (i - i0) / REC_SUB;
+        rs.wait(k);
+        if (k >= 1) rs.issue(k + 1, lane);  // the buffer of sub-block k-1 is free now
+      }
       float t[3], x[3];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -1079,7 +1127,7 @@ __global__ void __launch_bounds__(256) k_stats_rec(const StatsRecArgs a) {
       }
       float ref[3];
       if (REF == 1) {
-        const float* rec = s_rec + (size_t)(i - i0) * REC;  // shared-memory broadcasts
+        const float* rec = rs.rec(i);  // shared-memory broadcasts
         const float4 w4 = *reinterpret_cast<const float4*>(rec);
         const int4 j4 = *reinterpret_cast<const int4*>(rec + 4);
         float vs[3];

@@ -93,7 +93,7 @@ static void shape_rec_launch(const ShapeArgs& a, int groups, const ShapePlan& p,
 
 template <int NS, bool WEIGHTED>
 static void shape_v2_launch(const ShapeArgs& a, int groups, const ShapePlan& p, cudaStream_t st) {
-  const size_t smem_rt = (size_t)a.J * Quad<NS>::NQ * 32 * 16;
+  const size_t smem_rt = (size_t)a.J * Quad<NS>::NQ * 32 * 16 + (size_t)8 * 2 * REC_SUB * Rec<NS>::LEN * sizeof(float) + 16 * 8 + 16;
   const size_t smem_red = (size_t)4 * (2 * PackedG<NS>::NPAIRS + 8 * (Rec<NS>::NSP / 2) + 4) * 32 * sizeof(float);
   const size_t smem = smem_rt > smem_red ? smem_rt : smem_red;
   cudaFuncSetAttribute(k_shape_pass_v2<NS, WEIGHTED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -28,8 +28,8 @@ namespace sf {
 template <int NS, int REF, bool WEIGHTED>
 static void stats_rec_t(const StatsRecArgs& ra, int groups, cudaStream_t st) {
   StatsRecArgs a = ra;
-  a.segs_per_warp = 4;
-  const size_t smem = (REF == 1) ? ((size_t)a.J * 12 * 32 + (size_t)8 * STATS_SEG_MAX * Rec<NS>::LEN) * sizeof(float) + 8 * 8 + 16 : 0;
+  a.segs_per_warp = 2;
+  const size_t smem = (REF == 1) ? ((size_t)a.J * 12 * 32 + (size_t)8 * 2 * REC_SUB * Rec<NS>::LEN) * sizeof(float) + 16 * 8 + 16 : 0;
   dim3 grid((a.n_segments + 8 * a.segs_per_warp - 1) / (8 * a.segs_per_warp), groups);
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(k_stats_rec<NS, REF, WEIGHTED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -15,7 +15,7 @@ import torch.nn as nn
 
 from .. import _native, masks, modeldata
 
-SEG_LEN = 32  # vertices per statistics segment (csrc STATS_SEG_MAX)
+SEG_LEN = 64  # vertices per statistics segment
 CHUNK_LEN = 128  # vertices per shape-pass chunk
 
 

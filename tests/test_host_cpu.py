@@ -55,7 +55,7 @@ def test_device_tables(mname):
     assert seg_start[0] == 0 and seg_start[-1] == V
     for s in range(len(seg_part)):
         vs = order[seg_start[s]:seg_start[s + 1]]
-        assert 0 < len(vs) <= 32 and np.all(part[vs] == seg_part[s])
+        assert 0 < len(vs) <= 64 and np.all(part[vs] == seg_part[s])
     for p in range(J):
         assert np.all(seg_part[psb[p]:psb[p + 1]] == p)
         n = sum(seg_start[s + 1] - seg_start[s] for s in range(psb[p], psb[p + 1]))
