@@ -46,7 +46,7 @@ static FitWs carve(void* base, const smplfit_model_t* m, int64_t B, int has_join
   w.R2 = c.take<float>((size_t)9 * J * Bp);
   w.RT = c.take<float>((size_t)J * (12 + 3 * NS) * Bp);
   w.Pext = c.take<float>((size_t)J * 3 * (1 + NS) * Bp);
-  w.RT4 = c.take<float>((size_t)J * quad_rows_ns(NS) * Bp);
+  w.RT4 = c.take<float>(rt4_floats(m, (int)Bp));
   w.feat = c.take<float>((size_t)Bp * Kp);
   w.gpart = c.take<float>((size_t)max_shape_partials(m) * shape_nacc(NS) * Bp);
   w.Gd = c.take<double>((size_t)shape_nacc(NS) * Bp);
@@ -291,7 +291,7 @@ extern "C" int smplfit_fit(const smplfit_model_t* m, int64_t batch, const float*
 
   RotArgs ra;
   ra.partials = w.spart; ra.tjT = w.tjT; ra.jwT = w.jwT; ra.R_new = w.R; ra.RT = w.RT; ra.Pext = w.Pext;
-  ra.feat = w.feat; ra.t = tables(m); ra.B = c.B; ra.Bp = c.Bp; ra.Kp = c.Kp; ra.RT4 = w.RT4;
+  ra.feat = w.feat; ra.t = tables(m); ra.B = c.B; ra.Bp = c.Bp; ra.Kp = c.Kp; ra.RT4 = w.RT4; ra.rt4_clay = c.plan.kind == 3;
   // -- first rotation fit (pt/bodyfitter.py:363-394) --
   if (has_init) {
     run_transpose<3>(c, init_vertices, V, m->inv_order, nullptr, w.aT);
@@ -395,7 +395,7 @@ extern "C" int smplfit_fit_known_pose(const smplfit_model_t* m, int64_t batch, c
   RotArgs ra;
   ra.partials = nullptr; ra.tjT = nullptr; ra.ajT = nullptr; ra.aj_const = nullptr; ra.ca0T = nullptr;
   ra.ca0_const = nullptr; ra.jwT = nullptr; ra.R_old = nullptr; ra.R_new = w.R; ra.RT = w.RT; ra.Pext = w.Pext;
-  ra.feat = w.feat; ra.t = tables(m); ra.B = c.B; ra.Bp = c.Bp; ra.Kp = c.Kp; ra.RT4 = w.RT4;
+  ra.feat = w.feat; ra.t = tables(m); ra.B = c.B; ra.Bp = c.Bp; ra.Kp = c.Kp; ra.RT4 = w.RT4; ra.rt4_clay = c.plan.kind == 3;
   run_rot(c, ra, false);
   run_shape(c, o->scale_mode, beta_reg_reference, kid_reg_reference, o);
   // orientations output is not part of this method's result; reuse the scratch R2 for it
@@ -484,7 +484,7 @@ extern "C" int smplfit_fit_known_shape(const smplfit_model_t* m, int64_t batch, 
   run_transpose<1>(c, init_orientations, 9 * J, nullptr, nullptr, w.R2);
   RotArgs ra;
   ra.partials = w.spart; ra.tjT = w.tjT; ra.jwT = w.jwT; ra.R_new = w.R; ra.RT = w.RT; ra.Pext = w.Pext;
-  ra.feat = w.feat; ra.t = tables(m); ra.B = c.B; ra.Bp = c.Bp; ra.Kp = c.Kp; ra.RT4 = w.RT4;
+  ra.feat = w.feat; ra.t = tables(m); ra.B = c.B; ra.Bp = c.Bp; ra.Kp = c.Kp; ra.RT4 = w.RT4; ra.rt4_clay = c.plan.kind == 3;
   run_stats(c, 2, w.initjT, w.aT, nullptr);
   const float* aj = w.initjT;
   if (!has_joints) {

@@ -1010,6 +1010,305 @@ __global__ void __launch_bounds__(256, 1) k_shape_pass_v2(const ShapeArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
+// k_shape_pass_v3<NS, WEIGHTED, ROWSEL>: packed-math shape pass for models whose per-joint rows
+// of 32 instances do not fit in shared memory (SMPL-X: 55 joints) and / or many unknowns.
+//  * joint-subset staging: vertices are grouped by body part, so the CTA's vertices reference only
+//    a handful of joints; the CTA discovers them (bit mask over its records), stages just those
+//    joints' rows (cp.async) and reads any overflow joint straight from L2;
+//  * coordinate-major rows ("C layout", CLay<NS>): per joint and coordinate c the rows
+//    [R[c][0..2], T0[c], T[c][1..]] form QC quads, and the vertex loop handles one coordinate at a
+//    time (pos_c, jac_c, its Gram / rhs contribution), so only ~2 QC pairs are live at once;
+//  * ROWSEL splits the Gram rows over two launches when the accumulators would not fit in
+//    registers (NS >= 14): 1 = rows < SH plus r, Sb (SA, W when weighted), 2 = rows >= SH only.
+// Same partial layout as the other shape-pass kernels.
+// ---------------------------------------------------------------------------------------
+template <int NS>
+struct CLay {
+  static constexpr int NSP4 = (NS + 3) / 4 * 4;
+  static constexpr int RC = 4 + NSP4;   // rows per (joint, coordinate)
+  static constexpr int QC = RC / 4;     // quads per (joint, coordinate)
+  static constexpr int JQ = 3 * QC;     // quads per joint
+  static constexpr int H = Rec<NS>::NSP / 2;  // Jacobian pairs actually used
+  __host__ __device__ static constexpr int split_row() {  // first row of the second half
+    int s = 0;
+    while (s < NS && 2 * PackedG<NS>::row_off(s) < PackedG<NS>::NPAIRS) ++s;
+    return s;
+  }
+};
+__host__ __device__ inline int clay_rows_per_joint(int ns) { return 3 * (4 + (ns + 3) / 4 * 4); }
+
+struct ShapeV3Extra {
+  int cap_joints;  // joints that fit in the staging area
+};
+
+template <int NS, bool WEIGHTED, int ROWSEL>
+__global__ void __launch_bounds__(256, 1) k_shape_pass_v3(const ShapeArgs a, const ShapeV3Extra x3) {
+  extern __shared__ __align__(16) float s_rt[];
+  using L = CLay<NS>;
+  constexpr int H = L::H, QC = L::QC, JQ = L::JQ;
+  constexpr int REC = Rec<NS>::LEN;
+  constexpr int SH = L::split_row();
+  constexpr int P0 = (ROWSEL == 2) ? PackedG<NS>::row_off(SH) : 0;
+  constexpr int P1 = (ROWSEL == 1) ? PackedG<NS>::row_off(SH) : PackedG<NS>::NPAIRS;
+  constexpr int NPS = P1 - P0;  // Gram pairs accumulated by this launch
+  constexpr bool AUX = (ROWSEL != 2);  // r, Sb (SA, W) accumulated here
+  constexpr int NRED = 2 * NPS + (AUX ? 2 * H + 3 + (WEIGHTED ? 6 * H + 1 : 0) : 0);
+  const int g = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Bp = a.Bp;
+  const int b = g * 32 + lane;
+  const int cap = x3.cap_joints;
+  float4* sq = reinterpret_cast<float4*>(s_rt);                                   // [cap][JQ][32]
+  float* s_after = s_rt + (size_t)cap * JQ * 128;
+  RecStager<REC> rs;
+  rs.buf = s_after + (size_t)warp * 2 * REC_SUB * REC;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_after + (size_t)8 * 2 * REC_SUB * REC);
+  rs.bar = bars + 2 * warp;
+  rs.src = a.rec;
+  rs.phase = 0;
+  int* s_slot = reinterpret_cast<int*>(bars + 16);  // [64]
+  unsigned* s_mask = reinterpret_cast<unsigned*>(s_slot + 64);  // [2]
+  if (threadIdx.x < 2) s_mask[threadIdx.x] = 0u;
+  if (lane == 0) {
+    sf_mbar_init(rs.bar, 1);
+    sf_mbar_init(rs.bar + 1, 1);
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  const int chunk = blockIdx.x * 8 + warp;
+  const bool active = chunk < a.n_chunks;
+  const int i0 = chunk * a.chunk_len, i1 = active ? min(a.V, i0 + a.chunk_len) : i0;
+  {
+    // joints referenced (with non-zero weight) by this warp's vertices
+    unsigned m0 = 0u, m1 = 0u;
+    for (int i = i0 + lane; i < i1; i += 32) {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.rec + (size_t)i * REC));
+      const int4 j4 = __ldg(reinterpret_cast<const int4*>(a.rec + (size_t)i * REC + 4));
+      const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+      const int jv[4] = {j4.x, j4.y, j4.z, j4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (wv[k] != 0.f) {
+          if (jv[k] < 32) m0 |= 1u << jv[k]; else m1 |= 1u << (jv[k] - 32);
+        }
+    }
+    m0 = __reduce_or_sync(0xffffffffu, m0);
+    m1 = __reduce_or_sync(0xffffffffu, m1);
+    if (lane == 0) {
+      atomicOr(&s_mask[0], m0);
+      atomicOr(&s_mask[1], m1);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int j = threadIdx.x;
+    const unsigned lo = s_mask[0], hi = s_mask[1];
+    const bool used = j < 32 ? ((lo >> j) & 1u) : ((hi >> (j - 32)) & 1u);
+    const int before = j < 32 ? __popc(lo & ((1u << j) - 1u)) : __popc(lo) + __popc(hi & ((1u << (j - 32)) - 1u));
+    s_slot[j] = (used && before < cap) ? before : -1;
+  }
+  __syncthreads();
+  {
+    const float4* src = reinterpret_cast<const float4*>(a.RT4);
+    for (int j = 0; j < a.J; ++j) {
+      const int slot = s_slot[j];
+      if (slot < 0) continue;
+      for (int q = threadIdx.x; q < JQ * 32; q += 256) {
+        const int r = q >> 5, l = q & 31;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sq + (size_t)(slot * JQ + r) * 32 + l);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + (size_t)(j * JQ + r) * Bp + g * 32 + l) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+  }
+  float2 G2[NPS > 0 ? NPS : 1], r2[AUX ? H : 1], SA2[(AUX && WEIGHTED) ? 3 * H : 1];
+  float Sb[3] = {0.f, 0.f, 0.f}, Wsum = 0.f;
+#pragma unroll
+  for (int e = 0; e < NPS; ++e) G2[e] = make_float2(0.f, 0.f);
+  if (AUX) {
+#pragma unroll
+    for (int e = 0; e < H; ++e) r2[e] = make_float2(0.f, 0.f);
+    if (WEIGHTED) {
+#pragma unroll
+      for (int e = 0; e < 3 * H; ++e) SA2[e] = make_float2(0.f, 0.f);
+    }
+  }
+  if (active) {
+    rs.i0 = i0;
+    rs.i1 = i1;
+    rs.issue(0, lane);
+    rs.issue(1, lane);
+    rs.wait(0);
+    float nt[3], nvp[3], nvw = 1.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      nt[c] = SF_IM(a.tT, i0 * 3 + c, Bp, b);
+      nvp[c] = SF_IM(a.vposedT, i0 * 3 + c, Bp, b);
+    }
+    if (WEIGHTED) nvw = SF_IM(a.vwT, i0, Bp, b);
+    const float4* gsrc = reinterpret_cast<const float4*>(a.RT4);
+    for (int i = i0; i < i1; ++i) {
+      if ((i - i0) % REC_SUB == 0 && i > i0) {
+        rs.wait((i - i0) / REC_SUB);
+        rs.issue((i - i0) / REC_SUB + 1, lane);
+      }
+      const float* rec = rs.rec(i);
+      const float4 w4 = *reinterpret_cast<const float4*>(rec);
+      const int4 j4 = *reinterpret_cast<const int4*>(rec + 4);
+      const float2* sd2 = reinterpret_cast<const float2*>(rec + 8);
+      float t[3], vp[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        t[c] = nt[c];
+        vp[c] = nvp[c];
+      }
+      const float wv = nvw;
+      if (i + 1 < i1) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          nt[c] = SF_IM(a.tT, (i + 1) * 3 + c, Bp, b);
+          nvp[c] = SF_IM(a.vposedT, (i + 1) * 3 + c, Bp, b);
+        }
+        if (WEIGHTED) nvw = SF_IM(a.vwT, i + 1, Bp, b);
+      }
+      // row sources of the (up to) four joints: staged copy or global (overflow)
+      const float wk[4] = {w4.x, w4.y, w4.z, w4.w};
+      const int jk[4] = {j4.x, j4.y, j4.z, j4.w};
+      const float4* jp[4];
+      int jstride[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int slot = s_slot[jk[k]];
+        jp[k] = (slot >= 0) ? (sq + (size_t)slot * JQ * 32 + lane) : (gsrc + (size_t)jk[k] * JQ * Bp + b);
+        jstride[k] = (slot >= 0) ? 32 : Bp;
+      }
+      if (AUX && WEIGHTED) Wsum += wv;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float2 B2[2 * QC];
+#pragma unroll
+        for (int q = 0; q < 2 * QC; ++q) B2[q] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (wk[k] != 0.f) {
+            const float2 ww = make_float2(wk[k], wk[k]);
+#pragma unroll
+            for (int q = 0; q < QC; ++q) {
+              const float4 v = jp[k][(size_t)(c * QC + q) * jstride[k]];
+              B2[2 * q] = sf_fma2(ww, make_float2(v.x, v.y), B2[2 * q]);
+              B2[2 * q + 1] = sf_fma2(ww, make_float2(v.z, v.w), B2[2 * q + 1]);
+            }
+          }
+        }
+        // rows: B2[0] = (R[c][0], R[c][1]), B2[1] = (R[c][2], T0[c]), B2[2 + sp] = jac pair sp
+        const float pos = fmaf(B2[0].x, vp[0], fmaf(B2[0].y, vp[1], fmaf(B2[1].x, vp[2], B2[1].y)));
+        const float bv = t[c] - pos;
+        float2* J2 = B2 + 2;
+        const float rr3[3] = {B2[0].x, B2[0].y, B2[1].x};
+#pragma unroll
+        for (int xx = 0; xx < 3; ++xx) {
+          const float2 rr = make_float2(rr3[xx], rr3[xx]);
+#pragma unroll
+          for (int sp = 0; sp < H; ++sp) J2[sp] = sf_fma2(rr, sd2[xx * H + sp], J2[sp]);
+        }
+        if (AUX) {
+          const float wb = WEIGHTED ? wv * bv : bv;
+          Sb[c] += wb;
+          const float2 bb = make_float2(wb, wb);
+          if (WEIGHTED) {
+            const float2 w2 = make_float2(wv, wv);
+#pragma unroll
+            for (int sp = 0; sp < H; ++sp) SA2[c * H + sp] = sf_fma2(w2, J2[sp], SA2[c * H + sp]);
+          }
+#pragma unroll
+          for (int sp = 0; sp < H; ++sp) r2[sp] = sf_fma2(J2[sp], bb, r2[sp]);
+        }
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          if ((ROWSEL == 1 && s >= SH) || (ROWSEL == 2 && s < SH)) continue;
+          const float js = (s & 1) ? J2[s >> 1].y : J2[s >> 1].x;
+          const float wj = WEIGHTED ? wv * js : js;
+          const float2 jj = make_float2(wj, wj);
+#pragma unroll
+          for (int q = s / 2; q < H; ++q)
+            G2[PackedG<NS>::row_off(s) - P0 + q - s / 2] = sf_fma2(jj, J2[q], G2[PackedG<NS>::row_off(s) - P0 + q - s / 2]);
+        }
+      }
+    }
+  }
+  // ---- tree reduction over the 8 warps ----
+  float* red = s_rt;
+  auto fold = [&](bool write, int slot) {
+    float* base = red + (size_t)slot * NRED * 32 + lane;
+    int o = 0;
+#pragma unroll
+    for (int e = 0; e < NPS; ++e) {
+      if (write) { base[(o) * 32] = G2[e].x; base[(o + 1) * 32] = G2[e].y; }
+      else { G2[e].x += base[(o) * 32]; G2[e].y += base[(o + 1) * 32]; }
+      o += 2;
+    }
+    if (AUX) {
+#pragma unroll
+      for (int e = 0; e < H; ++e) {
+        if (write) { base[(o) * 32] = r2[e].x; base[(o + 1) * 32] = r2[e].y; }
+        else { r2[e].x += base[(o) * 32]; r2[e].y += base[(o + 1) * 32]; }
+        o += 2;
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (write) base[o * 32] = Sb[c]; else Sb[c] += base[o * 32];
+        ++o;
+      }
+      if (WEIGHTED) {
+#pragma unroll
+        for (int e = 0; e < 3 * H; ++e) {
+          if (write) { base[(o) * 32] = SA2[e].x; base[(o + 1) * 32] = SA2[e].y; }
+          else { SA2[e].x += base[(o) * 32]; SA2[e].y += base[(o + 1) * 32]; }
+          o += 2;
+        }
+        if (write) base[o * 32] = Wsum; else Wsum += base[o * 32];
+      }
+    }
+  };
+#pragma unroll 1
+  for (int half = 4; half >= 1; half >>= 1) {
+    __syncthreads();
+    if (warp >= half && warp < 2 * half) fold(true, warp - half);
+    __syncthreads();
+    if (warp < half) fold(false, warp);
+  }
+  if (warp == 0) {
+    float* out = a.partials + (size_t)blockIdx.x * ShapeAcc<NS>::N * Bp + b;
+    int o = 0;
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+      for (int t2 = s; t2 < NS; ++t2) {
+        if (!((ROWSEL == 1 && s >= SH) || (ROWSEL == 2 && s < SH))) {
+          const float2 gp = G2[PackedG<NS>::row_off(s) - P0 + t2 / 2 - s / 2];
+          out[(size_t)o * Bp] = (t2 & 1) ? gp.y : gp.x;
+        }
+        ++o;
+      }
+    if (AUX) {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) out[(size_t)(o++) * Bp] = (s & 1) ? r2[s >> 1].y : r2[s >> 1].x;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) out[(size_t)(o++) * Bp] = Sb[c];
+      if (WEIGHTED) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int s = 0; s < NS; ++s) out[(size_t)(o++) * Bp] = (s & 1) ? SA2[c * H + (s >> 1)].y : SA2[c * H + (s >> 1)].x;
+        out[(size_t)o * Bp] = Wsum;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // k_stats_rec<NS, REF, WEIGHTED>: the statistics pass in the same style (records, one-ahead
 // prefetch, per-joint skinning transforms of the CTA's 32 instances staged in shared memory,
 // dominant joint cached in registers).  8 warps per CTA, SEGS_PER_WARP segments per warp.

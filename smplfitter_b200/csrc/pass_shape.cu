@@ -44,22 +44,45 @@ static int num_sms() {
 }
 
 // variant of the record kernel (SMPLFIT_B200_SHAPE_VARIANT, for A/B runs): 4 = packed FFMA2 math (default),
-// 0 = scalar FFMA, 8 warps + register cache, 1 = scalar FFMA, 12 warps, no cache
+// 0 = scalar FFMA, 8 warps + register cache, 1 = scalar FFMA, 12 warps, no cache, 5 = force k_shape_pass_v3
 static int shape_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("SMPLFIT_B200_SHAPE_VARIANT");
     v = e ? atoi(e) : 4;
-    if (v < 0 || v > 4) v = 4;
+    if (v < 0 || v > 5) v = 4;
   }
   return v;
 }
 static int variant_warps(int v) { return v == 1 ? 12 : 8; }
 
+static size_t rec_stage_bytes(int ns) {
+  const int nsp = (ns + 1) / 2 * 2, rec = (8 + 3 * nsp + 3) / 4 * 4;
+  return (size_t)8 * 2 * REC_SUB * rec * sizeof(float) + 16 * 8 + 64 * 4 + 64;
+}
+
+size_t rt4_floats(const smplfit_model_t* m, int Bp) {
+  const size_t a = (size_t)m->num_joints * quad_rows_ns(m->fit_ns), b = (size_t)m->num_joints * clay_rows_per_joint(m->fit_ns);
+  return (a > b ? a : b) * (size_t)Bp;
+}
+
 ShapePlan plan_shape_pass(const smplfit_model_t* m, int groups) {
   ShapePlan p;
-  p.use_rec = shape_pass_uses_records(m);
-  p.warps = p.use_rec ? variant_warps(shape_variant()) : 8;
+  const bool rec_ok = m->fit_rec != nullptr && m->skin_k <= 4;
+  const size_t v2_smem = (size_t)m->num_joints * (quad_rows_ns(m->fit_ns) / 4) * 512 + rec_stage_bytes(m->fit_ns);
+  p.kind = 0;
+  p.cap_joints = 0;
+  if (rec_ok && v2_smem <= 210 * 1024 && m->fit_ns <= 12 && shape_variant() != 5) {
+    p.kind = 2;
+  } else if (rec_ok) {
+    p.kind = 3;
+    const size_t per_joint = (size_t)(clay_rows_per_joint(m->fit_ns) / 4) * 512;
+    const size_t budget = (size_t)200 * 1024 - rec_stage_bytes(m->fit_ns);
+    p.cap_joints = (int)(budget / per_joint);
+    if (p.cap_joints > m->num_joints) p.cap_joints = m->num_joints;
+  }
+  p.use_rec = p.kind != 0;
+  p.warps = (p.kind == 2) ? variant_warps(shape_variant()) : 8;
   // CTAs per instance group chosen so that the grid fills whole waves of the SM count
   const int V = m->num_vertices, sms = num_sms();
   const int c_min = (V + p.warps * 256 - 1) / (p.warps * 256), c_max = (V + p.warps * 32 - 1) / (p.warps * 32);
@@ -108,6 +131,10 @@ static void shape_pass_t(const ShapeArgs& sa, int groups, const ShapePlan& p, cu
   a.chunk_len = p.chunk_len;
   a.n_chunks = p.n_chunks;
   a.chunks_per_cta = p.warps;
+  if (p.kind == 3) {
+    launch_shape_pass_v3(a, NS, groups, p, st);
+    return;
+  }
   if (p.use_rec) {
     switch (shape_variant()) {
       case 1: shape_rec_launch<NS, WEIGHTED, 12, false>(a, groups, p, st); break;

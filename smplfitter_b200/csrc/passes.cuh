@@ -12,9 +12,13 @@ namespace sf {
 bool shape_pass_uses_records(const smplfit_model_t* m);
 // chunking of the shape pass for a given batch: balanced against the SM count at launch time
 struct ShapePlan {
-  bool use_rec;
+  bool use_rec;      // record-based kernels (v2 or v3)
+  int kind;          // 0 = generic k_shape_pass, 2 = k_shape_pass_v2 / rec (all joints staged), 3 = k_shape_pass_v3
+  int cap_joints;    // v3: joints that fit in the staging area
   int warps, chunk_len, n_chunks, n_partials;
 };
+size_t rt4_floats(const smplfit_model_t* m, int Bp);  // size of the quad-layout row buffer
+void launch_shape_pass_v3(const ShapeArgs& a, int ns, int groups, const ShapePlan& p, cudaStream_t st);
 ShapePlan plan_shape_pass(const smplfit_model_t* m, int groups);
 int max_shape_partials(const smplfit_model_t* m);
 void launch_shape_pass(const ShapeArgs& a, int ns, int groups, const ShapePlan& p, cudaStream_t st);

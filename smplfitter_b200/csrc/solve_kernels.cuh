@@ -84,7 +84,8 @@ struct RotArgs {
   const float* R_old;      // [9J][Bp] or null (identity)
   float* R_new;            // [9J][Bp]
   float* RT;               // [J*(12+3NS)][Bp] or null (skip the shape front)
-  float* RT4;              // optional quad layout of the same rows (fit_kernels.cuh Quad<NS>), or null
+  float* RT4;              // optional quad layout of the same rows (fit_kernels.cuh Quad<NS> / CLay<NS>), or null
+  int rt4_clay;            // 0: Quad<NS> row order (k_shape_pass_v2), 1: coordinate-major CLay<NS> (k_shape_pass_v3)
   float* Pext;             // [J*3*(1+NS)][Bp]
   float* feat;             // [Bp][Kp]
   TreeTables t;
@@ -223,7 +224,14 @@ static __global__ void __launch_bounds__(32) k_front_rel(const RotArgs a) {
     Rj[e] = SF_IM(a.R_new, j * 9 + e, Bp, b);
     SF_IM(a.RT, j * RW + e, Bp, b) = Rj[e];
   }
-  if (a.RT4 != nullptr) {
+  if (a.RT4 != nullptr && a.rt4_clay) {
+    const int nsp4 = (NS + 3) / 4 * 4, rc = 4 + nsp4, nq = 3 * rc / 4;
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int xx = 0; xx < 3; ++xx) rt4_store(a.RT4, j, nq, c * rc + xx, Bp, b, Rj[c * 3 + xx]);
+      for (int sx = NS; sx < nsp4; ++sx) rt4_store(a.RT4, j, nq, c * rc + 4 + sx, Bp, b, 0.f);
+    }
+  } else if (a.RT4 != nullptr) {
     const int rows = quad_rows_ns(NS), nq = rows / 4, nsp = (NS + 1) / 2 * 2;
 #pragma unroll
     for (int e = 0; e < 9; ++e) rt4_store(a.RT4, j, nq, e, Bp, b, Rj[e]);
@@ -279,7 +287,10 @@ static __global__ void __launch_bounds__(32) k_front_fk(const RotArgs a) {
       const float tv = P[j * 3 + c] - (Rj[c * 3] * j0 + Rj[c * 3 + 1] * j1 + Rj[c * 3 + 2] * j2);
       SF_IM(a.Pext, j * TW + c * (1 + NS) + s, Bp, b) = P[j * 3 + c];
       SF_IM(a.RT, j * RW + 9 + c * (1 + NS) + s, Bp, b) = tv;
-      if (a.RT4 != nullptr) {
+      if (a.RT4 != nullptr && a.rt4_clay) {
+        const int rc = 4 + (NS + 3) / 4 * 4;
+        rt4_store(a.RT4, j, 3 * rc / 4, c * rc + (s == 0 ? 3 : 4 + (s - 1)), Bp, b, tv);
+      } else if (a.RT4 != nullptr) {
         const int nsp = (NS + 1) / 2 * 2;
         rt4_store(a.RT4, j, quad_rows_ns(NS) / 4, s == 0 ? 10 + c : 14 + c * nsp + (s - 1), Bp, b, tv);
       }
