@@ -1,0 +1,99 @@
+"""``torch.library`` custom ops that make the modules scriptable (``torch.jit.script``) and
+traceable: TorchScript cannot see through ctypes, so the scripted ``forward`` / ``fit`` /
+``convert_vertices`` call these ops, whose bodies look the Python module up in a registry and run
+the regular host code (pointer marshalling into the C ABI).  Reference behaviour being matched:
+tests/conftest.py:38-39 and pt/__init__.py:90 script the fitter.
+"""
+
+from __future__ import annotations
+
+import weakref
+from typing import List, Optional
+
+import torch
+
+_registry: dict = {}
+_next_handle = [1]
+
+
+def register(module) -> int:
+    h = _next_handle[0]
+    _next_handle[0] += 1
+    _registry[h] = weakref.ref(module)
+    return h
+
+
+def _get(handle: int):
+    ref = _registry.get(handle)
+    mod = ref() if ref is not None else None
+    if mod is None:
+        raise RuntimeError(f'smplfitter_b200: module handle {handle} is no longer alive')
+    return mod
+
+
+def _empty_like_dev(t: torch.Tensor) -> torch.Tensor:
+    return torch.empty(0, device=t.device, dtype=torch.float32)
+
+
+@torch.library.custom_op('smplfit_b200::forward', mutates_args=())
+def forward_op(handle: int, anchor: torch.Tensor, pose_rotvecs: Optional[torch.Tensor],
+               shape_betas: Optional[torch.Tensor], trans: Optional[torch.Tensor],
+               kid_factor: Optional[torch.Tensor], rel_rotmats: Optional[torch.Tensor],
+               glob_rotmats: Optional[torch.Tensor], return_vertices: bool) -> List[torch.Tensor]:
+    res = _get(handle)._forward_impl(pose_rotvecs, shape_betas, trans, kid_factor, rel_rotmats, glob_rotmats,
+                                     return_vertices)
+    return [res['joints'], res['orientations'], res['vertices'] if return_vertices else _empty_like_dev(anchor)]
+
+
+@forward_op.register_fake
+def _(handle, anchor, pose_rotvecs, shape_betas, trans, kid_factor, rel_rotmats, glob_rotmats, return_vertices):
+    m = _get(handle)
+    B = 0
+    for a in (pose_rotvecs, shape_betas, trans, rel_rotmats, glob_rotmats):
+        if a is not None:
+            B = a.shape[0]
+            break
+    new = lambda *s: anchor.new_empty(s, dtype=torch.float32)  # noqa: E731
+    return [new(B, m.num_joints, 3), new(B, m.num_joints, 3, 3),
+            new(B, m.num_vertices, 3) if return_vertices else new(0)]
+
+
+@torch.library.custom_op('smplfit_b200::fit', mutates_args=())
+def fit_op(handle: int, target_vertices: torch.Tensor, target_joints: Optional[torch.Tensor],
+           vertex_weights: Optional[torch.Tensor], joint_weights: Optional[torch.Tensor], num_iter: int,
+           beta_regularizer: float, beta_regularizer2: float, scale_regularizer: float, kid_regularizer: float,
+           share_beta: bool, final_adjust_rots: bool, scale_target: bool, scale_fit: bool,
+           initial_pose_rotvecs: Optional[torch.Tensor], initial_shape_betas: Optional[torch.Tensor],
+           initial_kid_factor: Optional[torch.Tensor], want_pose_rotvecs: bool,
+           want_rel_orient: bool) -> List[torch.Tensor]:
+    keys = (['pose_rotvecs'] if want_pose_rotvecs else []) + (['relative_orientations'] if want_rel_orient else [])
+    res = _get(handle)._fit_impl(
+        target_vertices, target_joints, vertex_weights, joint_weights, num_iter, beta_regularizer, beta_regularizer2,
+        scale_regularizer, None if kid_regularizer != kid_regularizer else kid_regularizer, share_beta,
+        final_adjust_rots, scale_target, scale_fit, initial_pose_rotvecs, initial_shape_betas, initial_kid_factor, keys)
+    e = _empty_like_dev(target_vertices)
+    return [res['shape_betas'], res['trans'], res['orientations'], res['relative_orientations'],
+            res.get('pose_rotvecs', e), res.get('kid_factor', e), res.get('scale_corr', e)]
+
+
+@fit_op.register_fake
+def _(handle, target_vertices, target_joints, vertex_weights, joint_weights, num_iter, beta_regularizer,
+      beta_regularizer2, scale_regularizer, kid_regularizer, share_beta, final_adjust_rots, scale_target, scale_fit,
+      initial_pose_rotvecs, initial_shape_betas, initial_kid_factor, want_pose_rotvecs, want_rel_orient):
+    f = _get(handle)
+    B, J = target_vertices.shape[0], f.body_model.num_joints
+    new = lambda *s: target_vertices.new_empty(s, dtype=torch.float32)  # noqa: E731
+    return [new(B, f.n_betas), new(B, 3), new(B, J, 3, 3), new(B, J, 3, 3),
+            new(B, 3 * J) if want_pose_rotvecs else new(0), new(B) if f.enable_kid else new(0),
+            new(B) if (scale_target or scale_fit) else new(0)]
+
+
+@torch.library.custom_op('smplfit_b200::convert_vertices', mutates_args=())
+def convert_vertices_op(handle: int, inp_vertices: torch.Tensor) -> torch.Tensor:
+    return _get(handle)._convert_vertices_impl(inp_vertices)
+
+
+@convert_vertices_op.register_fake
+def _(handle, inp_vertices):
+    c = _get(handle)
+    return inp_vertices.new_empty((inp_vertices.shape[0], c.body_model_out.num_vertices, 3), dtype=torch.float32)

@@ -14,6 +14,7 @@ import torch
 import torch.nn as nn
 
 from .. import _native
+from . import _ops
 from .bodyfitter import BodyFitter
 
 
@@ -41,7 +42,9 @@ class BodyConverter(nn.Module):
             self.register_buffer('_csr_indptr', torch.tensor(m.indptr, dtype=torch.int32), persistent=False)
             self.register_buffer('_csr_indices', torch.tensor(m.indices, dtype=torch.int32), persistent=False)
             self.register_buffer('_csr_data', torch.tensor(m.data, dtype=torch.float32), persistent=False)
+        self._handle = _ops.register(self)
 
+    @torch.jit.unused
     def _load_default_csr(self):
         data_root = os.getenv('DATA_ROOT', '.')
         vin, vout = self.body_model_in.num_vertices, self.body_model_out.num_vertices
@@ -62,6 +65,7 @@ class BodyConverter(nn.Module):
             m = pickle.load(f, encoding='latin1')['mtx'].tocsr().astype(np.float32)
         return m[:, : m.shape[1] // 2]  # common.py:425-429
 
+    @torch.jit.unused
     def convert(
         self,
         pose_rotvecs: torch.Tensor,
@@ -100,10 +104,15 @@ class BodyConverter(nn.Module):
             fit_out['kid_factor'] = fit['kid_factor']
         return fit_out
 
+    @torch.jit.export
     def convert_vertices(self, inp_vertices: torch.Tensor) -> torch.Tensor:
         """Barycentric topology transfer (pt/bodyconverter.py:129-149)."""
         if not self.has_converter:
             return inp_vertices
+        return torch.ops.smplfit_b200.convert_vertices(self._handle, inp_vertices)
+
+    @torch.jit.unused
+    def _convert_vertices_impl(self, inp_vertices: torch.Tensor) -> torch.Tensor:
         _native.require_cuda(self._csr_data, 'the converter')
         dev = self._csr_data.device
         x = inp_vertices.to(device=dev, dtype=torch.float32).contiguous()

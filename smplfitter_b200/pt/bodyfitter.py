@@ -9,13 +9,14 @@ pointers.
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional
+from typing import Dict, List, Optional
 
 import numpy as np
 import torch
 import torch.nn as nn
 
 from .. import _native
+from . import _ops
 
 
 class BodyFitter(nn.Module):
@@ -98,8 +99,10 @@ class BodyFitter(nn.Module):
             self.register_buffer('_t_fit_rec', torch.tensor(np.ascontiguousarray(rec[order])), persistent=False)
         else:
             self._t_fit_rec = None
+        self._handle = _ops.register(self)
         self.to(body_model.v_template.device)
 
+    @torch.jit.unused
     def _struct(self) -> _native.ModelStruct:
         return self.body_model._struct(dict(
             fit_ns=self._ns,
@@ -112,6 +115,7 @@ class BodyFitter(nn.Module):
         ))
 
     # ------------------------------------------------------------------------------
+    @torch.jit.unused
     def _prep(self, x, shape, name):
         if x is None:
             return None
@@ -123,6 +127,7 @@ class BodyFitter(nn.Module):
             raise ValueError(f"'{name}' must have shape {tuple(shape)}, got {tuple(x.shape)}")
         return x.contiguous()
 
+    @torch.jit.unused
     def _opts(self, num_iter, final_adjust_rots, requested_keys, shape_weights, beta_regularizer,
               beta_regularizer2, kid_regularizer, scale_mode, scale_regularizer) -> _native.FitOpts:
         o = _native.FitOpts()
@@ -140,12 +145,14 @@ class BodyFitter(nn.Module):
         return o
 
     @staticmethod
+    @torch.jit.unused
     def _shape_weights_rule(target_joints, vertex_weights, joint_weights) -> bool:
         """pt/bodyfitter.py:1018-1028: weights enter the shape solve only as a complete set."""
         if target_joints is not None:
             return vertex_weights is not None and joint_weights is not None
         return vertex_weights is not None
 
+    @torch.jit.unused
     def _pad_ref(self, ref, B, name):
         if ref is None:
             return None
@@ -157,7 +164,57 @@ class BodyFitter(nn.Module):
         return out
 
     # ------------------------------------------------------------------------------
+    @torch.jit.export
     def fit(
+        self,
+        target_vertices: torch.Tensor,
+        target_joints: Optional[torch.Tensor] = None,
+        vertex_weights: Optional[torch.Tensor] = None,
+        joint_weights: Optional[torch.Tensor] = None,
+        num_iter: int = 1,
+        beta_regularizer: float = 1.0,
+        beta_regularizer2: float = 0.0,
+        scale_regularizer: float = 0.0,
+        kid_regularizer: Optional[float] = None,
+        share_beta: bool = False,
+        final_adjust_rots: bool = True,
+        scale_target: bool = False,
+        scale_fit: bool = False,
+        initial_pose_rotvecs: Optional[torch.Tensor] = None,
+        initial_shape_betas: Optional[torch.Tensor] = None,
+        initial_kid_factor: Optional[torch.Tensor] = None,
+        requested_keys: Optional[List[str]] = None,
+    ) -> Dict[str, torch.Tensor]:
+        """Fit pose, shape and translation (pt/bodyfitter.py:283-549; same arguments and result keys).
+
+        TorchScript-compatible: dispatches through the ``smplfit_b200::fit`` custom op."""
+        want_rv = True
+        want_rel = False
+        if requested_keys is not None:
+            want_rv = 'pose_rotvecs' in requested_keys
+            want_rel = 'relative_orientations' in requested_keys
+        if scale_target and scale_fit:
+            raise ValueError('Only one of estim_scale_target and estim_scale_fit can be True')
+        kid_reg = float('nan')
+        if kid_regularizer is not None:
+            kid_reg = float(kid_regularizer)
+        outs = torch.ops.smplfit_b200.fit(
+            self._handle, target_vertices, target_joints, vertex_weights, joint_weights, num_iter,
+            float(beta_regularizer), float(beta_regularizer2), float(scale_regularizer), kid_reg, share_beta,
+            final_adjust_rots, scale_target, scale_fit, initial_pose_rotvecs, initial_shape_betas,
+            initial_kid_factor, want_rv, want_rel)
+        result: Dict[str, torch.Tensor] = {
+            'shape_betas': outs[0], 'trans': outs[1], 'orientations': outs[2], 'relative_orientations': outs[3]}
+        if want_rv:
+            result['pose_rotvecs'] = outs[4]
+        if self.enable_kid:
+            result['kid_factor'] = outs[5]
+        if scale_target or scale_fit:
+            result['scale_corr'] = outs[6]
+        return result
+
+    @torch.jit.unused
+    def _fit_impl(
         self,
         target_vertices: torch.Tensor,
         target_joints: Optional[torch.Tensor] = None,
@@ -176,8 +233,7 @@ class BodyFitter(nn.Module):
         initial_shape_betas: Optional[torch.Tensor] = None,
         initial_kid_factor: Optional[torch.Tensor] = None,
         requested_keys: Optional[list] = None,
-    ) -> dict[str, torch.Tensor]:
-        """Fit pose, shape and translation (pt/bodyfitter.py:283-549; same arguments and result keys)."""
+    ) -> Dict[str, torch.Tensor]:
         if requested_keys is None:
             requested_keys = ['pose_rotvecs']
         if scale_target and scale_fit:
@@ -250,6 +306,7 @@ class BodyFitter(nn.Module):
         return out
 
     # ------------------------------------------------------------------------------
+    @torch.jit.unused
     def fit_from_host(self, target_vertices: torch.Tensor, target_joints: Optional[torch.Tensor] = None,
                       chunk_size: int = 1024, pinned_out: bool = True, **fit_kwargs) -> dict[str, torch.Tensor]:
         """``fit`` for HOST-resident inputs (ideally pinned): the batch is cut into chunks and the
@@ -295,6 +352,7 @@ class BodyFitter(nn.Module):
         return outs
 
     # ------------------------------------------------------------------------------
+    @torch.jit.unused
     def fit_with_known_pose(
         self,
         pose_rotvecs: torch.Tensor,
@@ -357,6 +415,7 @@ class BodyFitter(nn.Module):
             out['scale_corr'] = scale_corr
         return out
 
+    @torch.jit.unused
     def fit_with_known_shape(
         self,
         shape_betas: torch.Tensor,

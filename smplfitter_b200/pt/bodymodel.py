@@ -7,13 +7,14 @@ same result dictionaries, same error conventions (:164-200, :210-217).
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional
+from typing import Dict, Optional
 
 import numpy as np
 import torch
 import torch.nn as nn
 
 from .. import _native, masks, modeldata
+from . import _ops
 
 SEG_LEN = 64  # vertices per statistics segment
 CHUNK_LEN = 128  # vertices per shape-pass chunk
@@ -157,11 +158,13 @@ class BodyModel(nn.Module):
             is_smpl_family=int(plan.is_smpl_family), n_used=int(plan.part_is_stat[plan.part_assignment].sum()),
             n_segments=len(seg_part), chunk_len=CHUNK_LEN, max_cas=plan.cas_table.shape[1],
         )
+        self._handle = _ops.register(self)
         if device is not None:
             self.to(device)
 
     # ------------------------------------------------------------------------------
-    def _struct(self, extra: Optional[dict] = None) -> _native.ModelStruct:
+    @torch.jit.unused
+    def _struct(self, extra: Optional[dict] = None):
         """Fill the C struct with the current device addresses of the buffers."""
         _native.require_cuda(self.v_template, 'the body model')
         s = _native.ModelStruct()
@@ -201,8 +204,28 @@ class BodyModel(nn.Module):
         rel_rotmats: Optional[torch.Tensor] = None,
         glob_rotmats: Optional[torch.Tensor] = None,
         return_vertices: bool = True,
-    ) -> dict[str, torch.Tensor]:
-        """Vertices, joints and global orientations for a batch (pt/bodymodel.py:121-307)."""
+    ) -> Dict[str, torch.Tensor]:
+        """Vertices, joints and global orientations for a batch (pt/bodymodel.py:121-307).
+
+        TorchScript-compatible: dispatches through the ``smplfit_b200::forward`` custom op."""
+        outs = torch.ops.smplfit_b200.forward(self._handle, self.v_template, pose_rotvecs, shape_betas, trans,
+                                              kid_factor, rel_rotmats, glob_rotmats, return_vertices)
+        result: Dict[str, torch.Tensor] = {'joints': outs[0], 'orientations': outs[1]}
+        if return_vertices:
+            result['vertices'] = outs[2]
+        return result
+
+    @torch.jit.unused
+    def _forward_impl(
+        self,
+        pose_rotvecs: Optional[torch.Tensor] = None,
+        shape_betas: Optional[torch.Tensor] = None,
+        trans: Optional[torch.Tensor] = None,
+        kid_factor: Optional[torch.Tensor] = None,
+        rel_rotmats: Optional[torch.Tensor] = None,
+        glob_rotmats: Optional[torch.Tensor] = None,
+        return_vertices: bool = True,
+    ) -> Dict[str, torch.Tensor]:
         n_rot = sum(x is not None for x in (pose_rotvecs, rel_rotmats, glob_rotmats))
         if n_rot > 1:
             raise ValueError(
@@ -285,6 +308,7 @@ class BodyModel(nn.Module):
             result['vertices'] = verts
         return result
 
+    @torch.jit.unused
     def single(
         self,
         pose_rotvecs: Optional[torch.Tensor] = None,
@@ -307,6 +331,7 @@ class BodyModel(nn.Module):
         )
         return {k: v.squeeze(0) for k, v in result.items()}
 
+    @torch.jit.unused
     def rototranslate(
         self,
         R: torch.Tensor,

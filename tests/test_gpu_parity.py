@@ -255,3 +255,32 @@ def test_convert_vertices_vs_oracle():
     mc = m.tocsr()
     want = oracle_np.convert_vertices_csr(mc.indptr, mc.indices, mc.data, x)
     assert np.abs(got - want).max() < 1e-6
+
+
+def test_scripted_matches_eager():
+    """torch.jit.script(fitter).fit == eager fit, bit for bit (same kernels behind the custom op);
+    the reference's own tests run the scripted fitter (tests/conftest.py:38-39)."""
+    import warnings
+
+    bm, fitter = get_model('smpl_tiny', enable_kid=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        sm, sf = torch.jit.script(bm), torch.jit.script(fitter)
+    rng = np.random.default_rng(5)
+    B = 37
+    pose = cuda(rng.normal(0, 0.3, (B, bm.num_joints * 3)).astype(np.float32))
+    betas = cuda(rng.normal(0, 1, (B, 10)).astype(np.float32))
+    trans = cuda(rng.normal(0, 1, (B, 3)).astype(np.float32))
+    a, b = bm(pose, betas, trans), sm(pose, betas, trans)
+    for k in ('vertices', 'joints', 'orientations'):
+        assert torch.equal(a[k], b[k]), k
+    kw = dict(num_iter=2, beta_regularizer=0.5, kid_regularizer=1e3, scale_target=True,
+              requested_keys=['pose_rotvecs', 'relative_orientations'])
+    e = fitter.fit(a['vertices'], a['joints'], **kw)
+    s = sf.fit(a['vertices'], a['joints'], **kw)
+    assert set(e) == set(s) == {'pose_rotvecs', 'shape_betas', 'trans', 'orientations', 'relative_orientations',
+                                'kid_factor', 'scale_corr'}
+    for k in e:
+        assert torch.equal(e[k], s[k]), k
+    s2 = sf.fit(a['vertices'], requested_keys=['shape_betas'])
+    assert 'pose_rotvecs' not in s2 and 'scale_corr' not in s2

@@ -103,3 +103,25 @@ def test_product_never_imports_oracle():
             if f.endswith('.py'):
                 src = open(os.path.join(root, f)).read()
                 assert 'oracle' not in src.replace('no oracle', ''), os.path.join(root, f)
+
+
+def test_modules_are_scriptable():
+    """torch.jit.script over model / fitter / converter compiles (reference: tests/conftest.py:38-39,
+    pt/__init__.py:90 script the fitter); the scripted call still refuses to run without a GPU."""
+    import warnings
+
+    from smplfitter_b200.pt import BodyConverter, BodyFitter, BodyModel
+
+    bm = BodyModel('smpl_tiny')
+    fitter = BodyFitter(bm, enable_kid=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        sm = torch.jit.script(bm)
+        sf = torch.jit.script(fitter)
+        sc = torch.jit.script(BodyConverter(bm, bm))
+    assert 'requested_keys' in str(sf.fit.schema)
+    assert hasattr(sc, 'convert_vertices')
+    with pytest.raises(RuntimeError):
+        sm(shape_betas=torch.zeros(1, 10))
+    with pytest.raises(RuntimeError):
+        sf.fit(torch.zeros(2, bm.num_vertices, 3))
