@@ -7,6 +7,7 @@ import re
 
 import numpy as np
 import pytest
+import torch
 
 from smplfitter_b200 import masks, modeldata
 from tests import golden_cases as gc
