@@ -97,6 +97,23 @@ typedef struct smplfit_model {
                                    v_posed row (int) + 3 pad, shapedirs[3][SP], kid_shapedir[3]; NULL when skin_k > 4 */
   int32_t fit_rec_len;          /* floats per record = roundup(8 + 3 NSP, 4), NSP = NS rounded up to even; shapedirs[x][s] at 8 + x NSP + s */
   int32_t fwd_rec_len;          /* roundup(12 + 3 SP + 3, 4), SP = S rounded up to even */
+  /* ---- closed-form Gramian of the unweighted shape solve (k_shape_lite / k_gram_closed) ----
+   * With jac_v[:,s] = sum_k w_vk (R_k S_vs + T_ks) the normal matrix sum_v jac_v^T jac_v is a contraction of the
+   * per-instance joint transforms with model constants over the joint pairs (k,l) that share a vertex:
+   *   A_kl[a,b,s,t] = sum_v w_vk w_vl S_vs[a] S_vt[b],  Bm_kl[a,s] = sum_v w_vk w_vl S_vs[a],  W_kl = sum_v w_vk w_vl.
+   * All NULL / 0 disables the path (the per-vertex Gram kernels are used instead). */
+  const int32_t* seg_slots;     /* (n_segments, n_slots) joints whose skin weight is non-zero in the segment, -1 padded */
+  const int32_t* yj_start;      /* (J+1) CSR over joints of the (segment, slot) cells holding that joint */
+  const int32_t* yj_entry;      /* segment * n_slots + slot */
+  const int32_t* gcf_pairs;     /* (gcf_npairs, 2) off-diagonal pairs k < l */
+  const float* gcf_A;           /* (gcf_npairs, 9, NGP) A_kl[a,b,e] + A_kl[b,a,e], e = upper-triangle index of (s,t), NGP = roundup(NG, 4) */
+  const double* gcf_G0;         /* (NG) sum_k sum_a A_kk[a,a,e] (R_k^T R_k = I: instance independent) */
+  const int32_t* gcf_lstart;    /* (J+1) CSR over joints l of the partners k (k = l included) */
+  const int32_t* gcf_lk;        /* partner joint k of each CSR cell */
+  const float* gcf_Bm;          /* (cells, 3, roundup(NS, 4)) Bm_kl, zero padded */
+  const float* gcf_Wh;          /* (cells) W_kl / 2 */
+  int32_t n_slots;              /* slots per segment (12) */
+  int32_t gcf_npairs;
   const void* reserved_ptr[4];
 } smplfit_model_t;
 

@@ -40,6 +40,9 @@ class ModelStruct(C.Structure):
         + [('fit_ns', C.c_int32), ('fit_reserved', C.c_int32)]
         + [(n, _F) for n in _ptr_fields_b]
         + [('fit_rec_len', C.c_int32), ('fwd_rec_len', C.c_int32)]
+        + [(n, _F) for n in ('seg_slots', 'yj_start', 'yj_entry', 'gcf_pairs', 'gcf_A', 'gcf_G0', 'gcf_lstart',
+                             'gcf_lk', 'gcf_Bm', 'gcf_Wh')]
+        + [('n_slots', C.c_int32), ('gcf_npairs', C.c_int32)]
         + [('reserved_ptr', _F * 4)]
     )
 

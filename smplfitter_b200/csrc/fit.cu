@@ -5,6 +5,7 @@
 
 #include "common.cuh"
 #include "fit_kernels.cuh"
+#include "lite_kernels.cuh"
 #include "passes.cuh"
 #include "solve_kernels.cuh"
 #include "vposed_tc.cuh"
@@ -19,8 +20,8 @@ std::vector<ProfRec> g_prof;
 struct FitWs {
   double* Gd;
   float *mean, *tT, *tjT, *vwT, *jwT, *vposedT, *R, *R2, *RT, *Pext, *feat, *gpart, *beta, *trans, *refj,
-      *skin, *spart, *aT, *ajT, *initjT, *RT4, *zpart, *scale, *mpart;
-  double *Zd, *Cd, *sums;
+      *skin, *spart, *aT, *ajT, *initjT, *RT4, *zpart, *scale, *mpart, *RT12, *gcfpart, *skin4;
+  double *Zd, *Cd, *sums, *Yd;
   void* tc_scratch;
   size_t bytes;
 };
@@ -48,12 +49,20 @@ static FitWs carve(void* base, const smplfit_model_t* m, int64_t B, int has_join
   w.Pext = c.take<float>((size_t)J * 3 * (1 + NS) * Bp);
   w.RT4 = c.take<float>(rt4_floats(m, (int)Bp));
   w.feat = c.take<float>((size_t)Bp * Kp);
-  w.gpart = c.take<float>((size_t)max_shape_partials(m) * shape_nacc(NS) * Bp);
+  {
+    const size_t legacy = (size_t)max_shape_partials(m) * shape_nacc(NS);
+    const size_t lite = lite_available(m) ? (size_t)m->n_segments * lite_rows(NS) : 0;
+    w.gpart = c.take<float>((legacy > lite ? legacy : lite) * Bp);
+  }
+  w.RT12 = lite_available(m) ? c.take<float>((size_t)12 * J * Bp) : nullptr;
+  w.gcfpart = lite_available(m) ? c.take<float>((size_t)gram_closed_blocks(m) * (NS * (NS + 1) / 2) * Bp) : nullptr;
+  w.Yd = lite_available(m) ? c.take<double>((size_t)3 * J * Bp) : nullptr;
   w.Gd = c.take<double>((size_t)shape_nacc(NS) * Bp);
   w.beta = c.take<float>((size_t)NS * Bp);
   w.trans = c.take<float>(3 * Bp);
   w.refj = c.take<float>((size_t)3 * J * Bp);
   w.skin = c.take<float>((size_t)12 * J * Bp);
+  w.skin4 = c.take<float>((size_t)12 * J * Bp);
   w.spart = c.take<float>((size_t)m->n_segments * 16 * Bp);
   const bool need_aT = true;  // (fit_with_known_shape always materialises the reference)
   w.aT = need_aT ? c.take<float>((size_t)3 * V * Bp) : nullptr;
@@ -101,8 +110,17 @@ struct FitCtx {
   cudaStream_t st;
   const float *vwT_shape, *jwT_shape;  // shape-stage weights (pt/bodyfitter.py:1018-1028)
   bool has_joints, use_rec;
+  bool lite;  // closed-form Gramian + light vertex pass (unweighted shape stage)
   ShapePlan plan;
 };
+
+// decide the shape path once the weights are known; wires the matching row layouts into RotArgs
+static void choose_shape_path(FitCtx& c, RotArgs& ra) {
+  c.lite = lite_enabled(c.m) && c.vwT_shape == nullptr;
+  ra.RT12 = c.lite ? c.w.RT12 : nullptr;
+  ra.RT4 = c.lite ? nullptr : c.w.RT4;
+  ra.rt4_clay = c.plan.kind == 3;
+}
 
 static void run_gemm(FitCtx& c) {
   const smplfit_model_t* m = c.m;
@@ -121,16 +139,26 @@ static void run_shape(FitCtx& c, int scale_mode, const float* beta_ref, const fl
   sa.shapedirs = m->fit_shapedirs; sa.skin_idx = m->skin_idx; sa.skin_w = m->skin_w; sa.order = m->order;
   sa.partials = c.w.gpart; sa.rec = m->fit_rec; sa.RT4 = c.w.RT4; sa.V = m->num_vertices; sa.J = m->num_joints; sa.Bp = c.Bp;
   sa.skin_k = m->skin_k; sa.chunk_len = c.plan.chunk_len; sa.n_chunks = c.plan.n_chunks; sa.chunks_per_cta = c.plan.warps;
-  launch_shape_pass(sa, m->fit_ns, c.groups, c.plan, c.st);
-  SolveArgs so;
+  SolveArgs so{};
+  if (c.lite) {
+    LiteArgs la;
+    la.tT = c.w.tT; la.vposedT = c.w.vposedT; la.RT12 = c.w.RT12; la.rec = m->fit_rec; la.seg_start = m->seg_start;
+    la.seg_slots = m->seg_slots; la.partials = c.w.gpart; la.n_segments = m->n_segments; la.J = m->num_joints;
+    la.Bp = c.Bp; la.segs_per_warp = 1;
+    launch_shape_lite(la, m, c.groups, c.w.RT, c.w.gcfpart, c.w.Yd, c.st);
+    so.lite = 1; so.lite_nl = lite_rows(m->fit_ns); so.n_gcf = gram_closed_blocks(m); so.gcf_part = c.w.gcfpart;
+    so.G0 = m->gcf_G0; so.Yd = c.w.Yd;
+  } else {
+    launch_shape_pass(sa, m->fit_ns, c.groups, c.plan, c.st);
+  }
   so.partials = c.w.gpart; so.Pext = c.w.Pext; so.RT = c.w.RT;
   so.tjT = c.has_joints ? c.w.tjT : nullptr; so.jwT = c.jwT_shape;
   so.beta_ref = beta_ref; so.kid_ref = kid_ref;
-  so.beta = c.w.beta; so.trans = c.w.trans; so.refj = c.w.refj; so.skin = c.w.skin;
+  so.beta = c.w.beta; so.trans = c.w.trans; so.refj = c.w.refj; so.skin = c.w.skin; so.skin4 = c.w.skin4;
   so.wS = m->fit_wS; so.wsum = m->fit_wsum;
-  so.n_chunks = c.plan.n_partials; so.J = m->num_joints; so.S = m->num_betas; so.Bp = c.Bp; so.B = c.B;
+  so.n_chunks = c.lite ? m->n_segments : c.plan.n_partials; so.J = m->num_joints; so.S = m->num_betas; so.Bp = c.Bp; so.B = c.B;
   so.V = m->num_vertices; so.weighted = c.vwT_shape != nullptr;
-  so.sa_closed_form = (c.use_rec && c.vwT_shape == nullptr && m->fit_wS != nullptr) ? 1 : 0;
+  so.sa_closed_form = ((c.use_rec || c.lite) && c.vwT_shape == nullptr && m->fit_wS != nullptr) ? 1 : 0;
   so.reg = o->beta_regularizer; so.reg2 = o->beta_regularizer2; so.kid_reg = o->kid_regularizer;
   so.scale_mode = scale_mode; so.zpartials = c.w.zpart; so.n_zchunks = scale_chunks(m);
   so.scale_reg = o->scale_regularizer; so.scale_out = c.w.scale;
@@ -164,6 +192,15 @@ static void run_stats(FitCtx& c, int ref_mode, const float* ca0T, const float* a
   r.template_fit = m->template_mesh_fit; r.seg_start = s.seg_start; r.seg_part = s.seg_part;
   r.part_flags = s.part_flags; r.n_segments = s.n_segments; r.Bp = c.Bp; r.J = m->num_joints;
   r.all_segments = s.all_segments; r.segs_per_warp = 2;
+  if (ref_mode == 1 && stats_lite_enabled(m)) {
+    StatsLiteArgs l;
+    l.tT = c.w.tT; l.vwT = c.w.vwT; l.ct0 = c.w.tjT; l.ca0 = ca0T; l.vposedT = c.w.vposedT; l.beta = c.w.beta;
+    l.skin4 = c.w.skin4; l.aT_out = aT_out; l.partials = c.w.spart; l.rec = m->fit_rec; l.seg_start = m->seg_start;
+    l.seg_part = m->seg_part; l.part_flags = m->part_flags; l.n_segments = m->n_segments; l.Bp = c.Bp;
+    l.J = m->num_joints; l.all_segments = (aT_out != nullptr); l.segs_per_warp = 1;
+    launch_stats_lite(l, m, c.groups, c.st);
+    return;
+  }
   const bool use_rec = m->fit_rec != nullptr && m->skin_k <= 4 && m->template_mesh_fit != nullptr;
   launch_stats(s, r, m->fit_ns, ref_mode, c.w.vwT != nullptr, use_rec, c.groups, c.st);
 }
@@ -289,9 +326,10 @@ extern "C" int smplfit_fit(const smplfit_model_t* m, int64_t batch, const float*
   c.vwT_shape = o->shape_weights ? w.vwT : nullptr;
   c.jwT_shape = (o->shape_weights && has_joints) ? w.jwT : nullptr;
 
-  RotArgs ra;
+  RotArgs ra{};
   ra.partials = w.spart; ra.tjT = w.tjT; ra.jwT = w.jwT; ra.R_new = w.R; ra.RT = w.RT; ra.Pext = w.Pext;
-  ra.feat = w.feat; ra.t = tables(m); ra.B = c.B; ra.Bp = c.Bp; ra.Kp = c.Kp; ra.RT4 = w.RT4; ra.rt4_clay = c.plan.kind == 3;
+  ra.feat = w.feat; ra.t = tables(m); ra.B = c.B; ra.Bp = c.Bp; ra.Kp = c.Kp;
+  choose_shape_path(c, ra);
   // -- first rotation fit (pt/bodyfitter.py:363-394) --
   if (has_init) {
     run_transpose<3>(c, init_vertices, V, m->inv_order, nullptr, w.aT);
@@ -392,10 +430,11 @@ extern "C" int smplfit_fit_known_pose(const smplfit_model_t* m, int64_t batch, c
   c.vwT_shape = o->shape_weights ? w.vwT : nullptr;
   c.jwT_shape = (o->shape_weights && has_joints) ? w.jwT : nullptr;
   run_transpose<1>(c, glob_rotmats, 9 * J, nullptr, nullptr, w.R);
-  RotArgs ra;
+  RotArgs ra{};
   ra.partials = nullptr; ra.tjT = nullptr; ra.ajT = nullptr; ra.aj_const = nullptr; ra.ca0T = nullptr;
   ra.ca0_const = nullptr; ra.jwT = nullptr; ra.R_old = nullptr; ra.R_new = w.R; ra.RT = w.RT; ra.Pext = w.Pext;
-  ra.feat = w.feat; ra.t = tables(m); ra.B = c.B; ra.Bp = c.Bp; ra.Kp = c.Kp; ra.RT4 = w.RT4; ra.rt4_clay = c.plan.kind == 3;
+  ra.feat = w.feat; ra.t = tables(m); ra.B = c.B; ra.Bp = c.Bp; ra.Kp = c.Kp;
+  choose_shape_path(c, ra);
   run_rot(c, ra, false);
   run_shape(c, o->scale_mode, beta_reg_reference, kid_reg_reference, o);
   // orientations output is not part of this method's result; reuse the scratch R2 for it
@@ -482,9 +521,11 @@ extern "C" int smplfit_fit_known_shape(const smplfit_model_t* m, int64_t batch, 
   run_transpose<3>(c, init_vertices, V, m->inv_order, nullptr, w.aT);
   run_transpose<3>(c, init_joints, J, nullptr, nullptr, w.initjT);
   run_transpose<1>(c, init_orientations, 9 * J, nullptr, nullptr, w.R2);
-  RotArgs ra;
+  RotArgs ra{};
   ra.partials = w.spart; ra.tjT = w.tjT; ra.jwT = w.jwT; ra.R_new = w.R; ra.RT = w.RT; ra.Pext = w.Pext;
-  ra.feat = w.feat; ra.t = tables(m); ra.B = c.B; ra.Bp = c.Bp; ra.Kp = c.Kp; ra.RT4 = w.RT4; ra.rt4_clay = c.plan.kind == 3;
+  ra.feat = w.feat; ra.t = tables(m); ra.B = c.B; ra.Bp = c.Bp; ra.Kp = c.Kp;
+  c.lite = false;  // no shape solve in this entry point; keep the quad rows off too
+  ra.RT12 = nullptr; ra.RT4 = nullptr; ra.rt4_clay = 0;
   run_stats(c, 2, w.initjT, w.aT, nullptr);
   const float* aj = w.initjT;
   if (!has_joints) {
@@ -495,9 +536,9 @@ extern "C" int smplfit_fit_known_shape(const smplfit_model_t* m, int64_t batch, 
   run_rot(c, ra, true);
 
   // forward with the known betas for the current orientations = shape front + k_shape_out (trans = 0)
-  SolveArgs so;
+  SolveArgs so{};
   so.partials = nullptr; so.Pext = w.Pext; so.RT = w.RT; so.tjT = nullptr; so.jwT = nullptr; so.beta_ref = nullptr;
-  so.kid_ref = nullptr; so.beta = w.beta; so.trans = w.trans; so.refj = w.refj; so.skin = w.skin; so.wS = nullptr;
+  so.kid_ref = nullptr; so.beta = w.beta; so.trans = w.trans; so.refj = w.refj; so.skin = w.skin; so.skin4 = w.skin4; so.wS = nullptr;
   so.wsum = nullptr; so.n_chunks = 0; so.J = J; so.S = m->num_betas; so.Bp = c.Bp; so.B = c.B; so.V = V;
   so.weighted = 0; so.sa_closed_form = 0; so.scale_mode = 0; so.zpartials = nullptr; so.n_zchunks = 0;
   so.scale_reg = 0.f; so.scale_out = w.scale; so.reg = so.reg2 = so.kid_reg = 0.f;

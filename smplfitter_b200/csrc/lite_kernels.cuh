@@ -1,0 +1,627 @@
+// The unweighted shape pass in closed form ("lite" path).
+//
+// With  jac_v[:,s] = sum_k w_vk (R_k S_vs + T_ks)   and   b_v = t_v - (Rb_v vp_v + Tb_v0)
+// the normal equations of the shape solve (pt/bodyfitter.py:999-1048) need
+//   G[s,t] = sum_v jac_vs . jac_vt ,   r[s] = sum_v jac_vs . b_v ,   Sb = sum_v b_v .
+// Without per-vertex weights G does not depend on the targets: it is a contraction of the
+// per-instance joint transforms with model constants over the joint pairs that share a vertex
+// (k_gram_closed; constants gcf_* of include/smplfit_b200.h).  Only r and Sb need a pass over the
+// vertices, and that pass is light (k_shape_lite):
+//   r[s] = sum_v S_vs . z_v + sum_k T_ks . Y_k ,   z_v = Rb_v^T b_v ,   Y_k = sum_v w_vk b_v ,
+// i.e. per vertex a 12-row blend, one 3x3 transpose product, 3 NS FMAs, and a scatter of b_v into
+// the (few) joints the vertex is skinned to.  ~5x fewer FP32 operations than the per-vertex Gramian.
+#pragma once
+#include "fit_kernels.cuh"
+#include "solve_kernels.cuh"
+
+namespace sf {
+
+constexpr int LITE_NSLOT = 12;  // == N_SLOTS of pt/bodymodel.py
+constexpr int LITE_SUB = 8;     // vertices per staged record sub-block
+
+struct LiteArgs {
+  const float* tT;       // [3V][Bp]
+  const float* vposedT;  // [3V][Bp]
+  const float* RT12;     // [J*3][Bp] float4: (R[c][0], R[c][1], R[c][2], T0[c])
+  const float* rec;      // [V][Rec<NS>::LEN]
+  const int32_t* seg_start;
+  const int32_t* seg_slots;  // [n_segments][LITE_NSLOT]
+  float* partials;           // [n_segments][NS + 3 + 3*LITE_NSLOT][Bp]: r | Sb | Y per slot
+  int n_segments, J, Bp, segs_per_warp;
+};
+
+template <int REC>
+struct RecStagerLite {  // RecStager with LITE_SUB vertices per sub-block
+  float* buf;
+  uint64_t* bar;
+  const float* src;
+  int i0, i1;
+  uint32_t phase;
+  __device__ __forceinline__ void issue(int k, int lane) {
+    const int first = i0 + k * LITE_SUB;
+    __syncwarp();
+    if (first < i1 && lane == 0) {
+      const uint32_t bytes = (uint32_t)min(LITE_SUB, i1 - first) * REC * 4;
+      sf_mbar_expect_tx(bar + (k & 1), bytes);
+      sf_bulk_g2s(buf + (size_t)(k & 1) * LITE_SUB * REC, src + (size_t)first * REC, bytes, bar + (k & 1));
+    }
+  }
+  __device__ __forceinline__ void wait(int k) {
+    sf_mbar_wait(bar + (k & 1), (phase >> (k & 1)) & 1u);
+    phase ^= 1u << (k & 1);
+  }
+  __device__ __forceinline__ const float* rec(int i) const {
+    const int d = i - i0;
+    return buf + (size_t)((d / LITE_SUB) & 1) * LITE_SUB * REC + (size_t)(d % LITE_SUB) * REC;
+  }
+};
+
+__host__ __device__ inline size_t lite_smem_bytes(int J, int rec_len, int warps) {
+  return ((size_t)J * 3 * 128 + (size_t)warps * (2 * LITE_SUB * rec_len + LITE_NSLOT * 3 * 32)) * sizeof(float) +
+         (size_t)warps * (16 + 64) + 16;
+}
+
+// Joint rows in registers: the internal vertex order groups vertices by their tuple of skinning joints
+// (pt/bodymodel.py), so the four slots' rows change only ~0.1 times per vertex; they are reloaded from the
+// staged shared-memory copy on change (warp-uniform branch).  Slot k of a vertex with weight 0 is never loaded.
+struct JointCache {
+  float4 q[4][3];
+  int j[4];
+  __device__ __forceinline__ void reset() {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      j[k] = -1;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) q[k][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  // blended rows: B2[2c] = (row c .x, .y), B2[2c+1] = (row c .z, .w)
+  __device__ __forceinline__ void blend(const float w[4], float2* B2) const {
+    {
+      const float2 ww = make_float2(w[0], w[0]);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        B2[2 * c] = sf_mul2(ww, make_float2(q[0][c].x, q[0][c].y));
+        B2[2 * c + 1] = sf_mul2(ww, make_float2(q[0][c].z, q[0][c].w));
+      }
+    }
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      const float2 ww = make_float2(w[k], w[k]);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        B2[2 * c] = sf_fma2(ww, make_float2(q[k][c].x, q[k][c].y), B2[2 * c]);
+        B2[2 * c + 1] = sf_fma2(ww, make_float2(q[k][c].z, q[k][c].w), B2[2 * c + 1]);
+      }
+    }
+  }
+};
+
+template <int NS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_shape_lite(const LiteArgs a) {
+  extern __shared__ __align__(16) float s_lite[];
+  constexpr int NSP = Rec<NS>::NSP, H = NSP / 2, REC = Rec<NS>::LEN;
+  constexpr int NL = NS + 3 + 3 * LITE_NSLOT;
+  const int g = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Bp = a.Bp;
+  const int b = g * 32 + lane;
+  const float4* sq = reinterpret_cast<const float4*>(s_lite);  // [J*3][32]
+  float* wbase = s_lite + (size_t)a.J * 3 * 128;
+  float* yw = wbase + (size_t)WARPS * (2 * LITE_SUB * REC) + (size_t)warp * (LITE_NSLOT * 3 * 32);  // [slot*3+c][32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wbase + (size_t)WARPS * (2 * LITE_SUB * REC + LITE_NSLOT * 3 * 32));
+  unsigned char* lut = reinterpret_cast<unsigned char*>(bars + 2 * WARPS) + warp * 64;  // joint -> slot of the segment
+  RecStagerLite<REC> rs;
+  rs.buf = wbase + (size_t)warp * (2 * LITE_SUB * REC);
+  rs.bar = bars + 2 * warp;
+  rs.src = a.rec;
+  rs.phase = 0;
+  if (lane == 0) {
+    sf_mbar_init(rs.bar, 1);
+    sf_mbar_init(rs.bar + 1, 1);
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  {
+    // the CTA's 32-instance slice of every (joint, row) quad: 32 x 16 B contiguous per row
+    const int n = a.J * 3 * 32;
+    const float4* src = reinterpret_cast<const float4*>(a.RT12);
+    for (int q = threadIdx.x; q < n; q += WARPS * 32) {
+      const int r = q >> 5, l = q & 31;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_lite + (size_t)q * 4);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + (size_t)r * Bp + g * 32 + l) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+  }
+  for (int q = 0; q < a.segs_per_warp; ++q) {
+    const int seg = (blockIdx.x * a.segs_per_warp + q) * WARPS + warp;
+    if (seg >= a.n_segments) break;
+    const int i0 = a.seg_start[seg], i1 = a.seg_start[seg + 1];
+    const int sj = (lane < LITE_NSLOT) ? __ldg(a.seg_slots + seg * LITE_NSLOT + lane) : -1;
+    const int nslots = __popc(__ballot_sync(0xffffffffu, sj >= 0));
+    __syncwarp();
+    if (sj >= 0) lut[sj] = (unsigned char)lane;
+    for (int e = 0; e < nslots * 3; ++e) yw[e * 32 + lane] = 0.f;
+    __syncwarp();
+    rs.i0 = i0;
+    rs.i1 = i1;
+    rs.issue(0, lane);
+    rs.issue(1, lane);
+    float2 r2[H];
+#pragma unroll
+    for (int e = 0; e < H; ++e) r2[e] = make_float2(0.f, 0.f);
+    float Sb[3] = {0.f, 0.f, 0.f};
+    float Yr[4][3];  // Y of the cached joint of each slot, flushed to its shared-memory cell when the joint changes
+#pragma unroll
+    for (int k = 0; k < 4; ++k) Yr[k][0] = Yr[k][1] = Yr[k][2] = 0.f;
+    JointCache jc;
+    jc.reset();
+    // targets / posed template two vertices ahead in registers
+    float t0[3], p0[3], t1[3], p1[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      t0[c] = SF_IM(a.tT, i0 * 3 + c, Bp, b);
+      p0[c] = SF_IM(a.vposedT, i0 * 3 + c, Bp, b);
+      t1[c] = p1[c] = 0.f;
+    }
+    if (i0 + 1 < i1) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        t1[c] = SF_IM(a.tT, (i0 + 1) * 3 + c, Bp, b);
+        p1[c] = SF_IM(a.vposedT, (i0 + 1) * 3 + c, Bp, b);
+      }
+    }
+    for (int i = i0; i < i1; ++i) {
+      if ((i - i0) % LITE_SUB == 0) {  // entering sub-block k (warp-uniform)
+        const int k = (i - i0) / LITE_SUB;
+        rs.wait(k);
+        if (k >= 1) rs.issue(k + 1, lane);  // the buffer of sub-block k-1 is free now
+      }
+      float t[3], vp[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        t[c] = t0[c];
+        vp[c] = p0[c];
+        t0[c] = t1[c];
+        p0[c] = p1[c];
+      }
+      if (i + 2 < i1) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          t1[c] = SF_IM(a.tT, (i + 2) * 3 + c, Bp, b);
+          p1[c] = SF_IM(a.vposedT, (i + 2) * 3 + c, Bp, b);
+        }
+      }
+      const float* rec = rs.rec(i);
+      const float4 w4 = *reinterpret_cast<const float4*>(rec);
+      const int4 j4 = *reinterpret_cast<const int4*>(rec + 4);
+      const float wk[4] = {w4.x, w4.y, w4.z, w4.w};
+      const int jk[4] = {j4.x, j4.y, j4.z, j4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (wk[k] != 0.f && jk[k] != jc.j[k]) {  // warp-uniform, rare
+          if (jc.j[k] >= 0) {
+            float* yp = yw + (size_t)(lut[jc.j[k]] * 3) * 32 + lane;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              yp[c * 32] += Yr[k][c];
+              Yr[k][c] = 0.f;
+            }
+          }
+          jc.j[k] = jk[k];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) jc.q[k][c] = sq[(size_t)(jk[k] * 3 + c) * 32 + lane];
+        }
+      }
+      float2 B2[6];  // B2[2c] = (Rb[c][0], Rb[c][1]), B2[2c+1] = (Rb[c][2], Tb0[c])
+      jc.blend(wk, B2);
+      float bv[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float pos = fmaf(B2[2 * c].x, vp[0], fmaf(B2[2 * c].y, vp[1], fmaf(B2[2 * c + 1].x, vp[2], B2[2 * c + 1].y)));
+        bv[c] = t[c] - pos;
+        Sb[c] += bv[c];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Yr[k][c] = fmaf(wk[k], bv[c], Yr[k][c]);
+      float z[3];
+      z[0] = fmaf(B2[0].x, bv[0], fmaf(B2[2].x, bv[1], B2[4].x * bv[2]));
+      z[1] = fmaf(B2[0].y, bv[0], fmaf(B2[2].y, bv[1], B2[4].y * bv[2]));
+      z[2] = fmaf(B2[1].x, bv[0], fmaf(B2[3].x, bv[1], B2[5].x * bv[2]));
+      const float2* sd2 = reinterpret_cast<const float2*>(rec + 8);  // shapedirs[x][sp] pairs (shared memory)
+#pragma unroll
+      for (int x = 0; x < 3; ++x) {
+        const float2 zz = make_float2(z[x], z[x]);
+#pragma unroll
+        for (int sp = 0; sp < H; ++sp) r2[sp] = sf_fma2(sd2[x * H + sp], zz, r2[sp]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (jc.j[k] >= 0) {
+        float* yp = yw + (size_t)(lut[jc.j[k]] * 3) * 32 + lane;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) yp[c * 32] += Yr[k][c];
+      }
+    }
+    float* out = a.partials + (size_t)seg * NL * Bp + b;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) out[(size_t)s * Bp] = (s & 1) ? r2[s >> 1].y : r2[s >> 1].x;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[(size_t)(NS + c) * Bp] = Sb[c];
+    for (int e = 0; e < nslots * 3; ++e) out[(size_t)(NS + 3 + e) * Bp] = yw[e * 32 + lane];
+  }
+}
+
+// k_lite_reduce: one thread per (instance, joint): Y_k = sum over the (segment, slot) cells of joint k, in double.
+struct LiteReduceArgs {
+  const float* partials;
+  const int32_t* yj_start;
+  const int32_t* yj_entry;
+  double* Yd;  // [3J][Bp]
+  int NL, NS, Bp;
+};
+static __global__ void __launch_bounds__(32) k_lite_reduce(const LiteReduceArgs a) {
+  const int b = blockIdx.x * 32 + threadIdx.x;
+  const int j = blockIdx.y;
+  if (b >= a.Bp) return;
+  double y[3] = {0.0, 0.0, 0.0};
+  for (int q = a.yj_start[j]; q < a.yj_start[j + 1]; ++q) {
+    const int e = a.yj_entry[q];
+    const int seg = e / LITE_NSLOT, slot = e % LITE_NSLOT;
+    const float* p = a.partials + ((size_t)seg * a.NL + a.NS + 3 + slot * 3) * a.Bp + b;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) y[c] += (double)p[(size_t)c * a.Bp];
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) a.Yd[(size_t)(j * 3 + c) * a.Bp + b] = y[c];
+}
+
+// ---------------------------------------------------------------------------------------
+// The closed-form Gramian, two kernels (8 warps per CTA, lane = instance, in-CTA tree reduction so each CTA
+// writes one partial Gramian [NG][Bp]):
+//   k_gram_pairs<NS>: each warp takes LITE_PPW off-diagonal joint pairs k<l (rotation-rotation term)
+//        G[e] += sum_ab (R_k^T R_l)[a,b] * Asym_kl[a,b,e]           (constants: warp-uniform 16-byte loads)
+//   k_gram_trans<NS>: one CTA per coordinate c; the c-rows of every joint ([R_k[c][0..2] | T_k[c][1..NS]]) of the
+//        CTA's 32 instances are staged in shared memory; warps split the joints l
+//        Q_l[s] = sum_k (R_k[c] . Bm_kl[:,s] + W_kl/2 T_k[c][s]),   G[s,t] += T_l[c][t] Q_l[s] + T_l[c][s] Q_l[t]
+// (the diagonal rotation term sum_k sum_a A_kk[a,a,e] is the constant gcf_G0, added in k_gram_entries).
+// ---------------------------------------------------------------------------------------
+constexpr int LITE_PPW = 2;  // pairs per warp in k_gram_pairs
+
+struct GramClosedArgs {
+  const float* RT;  // [J*(12+3NS)][Bp]
+  const int32_t* pairs;
+  const float* A;
+  const int32_t* lstart;
+  const int32_t* lk;
+  const float* Bm;  // (cells, 3, NSP4)
+  const float* Wh;
+  float* out;  // [n_pair_ctas + 3][NG][Bp]
+  int npairs, J, Bp, n_pair_ctas;
+};
+
+// sum G over the CTA's 8 warps (fixed order); the result is valid in warp 0.  red: [4][N][32] floats.
+template <int N>
+__device__ __forceinline__ void cta_reduce8(float* G, float* red, int warp, int lane) {
+#pragma unroll
+  for (int half = 4; half >= 1; half >>= 1) {
+    __syncthreads();
+    if (warp >= half && warp < 2 * half) {
+#pragma unroll
+      for (int e = 0; e < N; ++e) red[((size_t)(warp - half) * N + e) * 32 + lane] = G[e];
+    }
+    __syncthreads();
+    if (warp < half) {
+#pragma unroll
+      for (int e = 0; e < N; ++e) G[e] += red[((size_t)warp * N + e) * 32 + lane];
+    }
+  }
+}
+
+template <int NS>
+__global__ void __launch_bounds__(256) k_gram_pairs(const GramClosedArgs a) {
+  extern __shared__ __align__(16) float s_red[];  // [4][NGP][32]
+  constexpr int NG = NS * (NS + 1) / 2, NGP = (NG + 3) / 4 * 4;
+  constexpr int RW = 12 + 3 * NS;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x * 32 + lane;
+  const int Bp = a.Bp;
+  float G[NGP];
+#pragma unroll
+  for (int e = 0; e < NGP; ++e) G[e] = 0.f;
+  const int p0 = (blockIdx.y * 8 + warp) * LITE_PPW, p1 = min(a.npairs, p0 + LITE_PPW);
+  for (int p = p0; p < p1; ++p) {
+    const int k = a.pairs[2 * p], l = a.pairs[2 * p + 1];
+    float Rk[9], Rl[9];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) {
+      Rk[e] = SF_IM(a.RT, k * RW + e, Bp, b);
+      Rl[e] = SF_IM(a.RT, l * RW + e, Bp, b);
+    }
+    const float4* A4 = reinterpret_cast<const float4*>(a.A) + (size_t)p * 9 * (NGP / 4);
+#pragma unroll
+    for (int aa = 0; aa < 3; ++aa)
+#pragma unroll
+      for (int bb = 0; bb < 3; ++bb) {
+        const float rkl = fmaf(Rk[aa], Rl[bb], fmaf(Rk[3 + aa], Rl[3 + bb], Rk[6 + aa] * Rl[6 + bb]));  // (R_k^T R_l)[aa][bb]
+#pragma unroll
+        for (int e4 = 0; e4 < NGP / 4; ++e4) {
+          const float4 c4 = __ldg(A4 + (aa * 3 + bb) * (NGP / 4) + e4);
+          G[4 * e4] = fmaf(rkl, c4.x, G[4 * e4]);
+          G[4 * e4 + 1] = fmaf(rkl, c4.y, G[4 * e4 + 1]);
+          G[4 * e4 + 2] = fmaf(rkl, c4.z, G[4 * e4 + 2]);
+          G[4 * e4 + 3] = fmaf(rkl, c4.w, G[4 * e4 + 3]);
+        }
+      }
+  }
+  cta_reduce8<NGP>(G, s_red, warp, lane);
+  if (warp == 0) {
+    float* out = a.out + (size_t)blockIdx.y * NG * Bp + b;
+#pragma unroll
+    for (int e = 0; e < NG; ++e) out[(size_t)e * Bp] = G[e];
+  }
+}
+
+template <int NS>
+__global__ void __launch_bounds__(256) k_gram_trans(const GramClosedArgs a) {
+  extern __shared__ __align__(16) float s_rows[];  // [J][3 + NS][32], then reused as the reduction scratch
+  constexpr int NG = NS * (NS + 1) / 2, NGP = (NG + 3) / 4 * 4, NSP4 = (NS + 3) / 4 * 4;
+  constexpr int RW = 12 + 3 * NS, CW = 3 + NS;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = blockIdx.x, c = blockIdx.y;
+  const int Bp = a.Bp;
+  const int b = g * 32 + lane;
+  {
+    const int n16 = a.J * CW * 8;  // 16-byte pieces: row = 128 B
+    for (int q = threadIdx.x; q < n16; q += 256) {
+      const int r = q >> 3, part = q & 7;
+      const int k = r / CW, e = r % CW;
+      const int row = (e < 3) ? k * RW + c * 3 + e : k * RW + 9 + c * (1 + NS) + 1 + (e - 3);
+      const float* src = a.RT + (size_t)row * Bp + g * 32 + part * 4;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_rows + r * 32 + part * 4);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+  }
+  float G[NGP];
+#pragma unroll
+  for (int e = 0; e < NGP; ++e) G[e] = 0.f;
+  for (int l = warp; l < a.J; l += 8) {
+    float Q[NSP4];
+#pragma unroll
+    for (int s = 0; s < NSP4; ++s) Q[s] = 0.f;
+    for (int q = a.lstart[l]; q < a.lstart[l + 1]; ++q) {
+      const int k = a.lk[q];
+      const float* rk = s_rows + (size_t)(k * CW) * 32 + lane;
+      const float r0 = rk[0], r1 = rk[32], r2 = rk[64];
+      const float wh = __ldg(a.Wh + q);
+      const float4* bm = reinterpret_cast<const float4*>(a.Bm + (size_t)q * 3 * NSP4);
+#pragma unroll
+      for (int s4 = 0; s4 < NSP4 / 4; ++s4) {
+        const float4 b0 = __ldg(bm + s4), b1 = __ldg(bm + NSP4 / 4 + s4), b2 = __ldg(bm + 2 * (NSP4 / 4) + s4);
+        const float bx[4][3] = {{b0.x, b1.x, b2.x}, {b0.y, b1.y, b2.y}, {b0.z, b1.z, b2.z}, {b0.w, b1.w, b2.w}};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int s = 4 * s4 + u;
+          if (s < NS) Q[s] += fmaf(r0, bx[u][0], fmaf(r1, bx[u][1], fmaf(r2, bx[u][2], wh * rk[(3 + s) * 32])));
+        }
+      }
+    }
+    float Tl[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) Tl[s] = s_rows[(size_t)(l * CW + 3 + s) * 32 + lane];
+    int e = 0;
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+      for (int t = s; t < NS; ++t) {
+        G[e] = fmaf(Tl[t], Q[s], fmaf(Tl[s], Q[t], G[e]));
+        ++e;
+      }
+  }
+  cta_reduce8<NGP>(G, s_rows, warp, lane);  // (its leading __syncthreads orders the reuse of s_rows)
+  if (warp == 0) {
+    float* out = a.out + (size_t)(a.n_pair_ctas + c) * NG * Bp + b;
+#pragma unroll
+    for (int e = 0; e < NG; ++e) out[(size_t)e * Bp] = G[e];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// k_stats_lite<NS, WEIGHTED>: the statistics pass against the skinned current fit (the hot REF == 1 mode of
+// k_stats_rec), restructured like k_shape_lite: joint rows as float4 quads (A[c][0..2], tau[c]) cached in
+// registers per slot, records staged per warp by bulk async copies, targets / posed template two vertices ahead.
+//   ref_v = (sum_k w_vk [A_k | tau_k]) [v_posed_v + S_v beta; 1];   per part: M += (t - ct)(ref - ca)^T, sums.
+// Same partial layout as k_stats ([segment][16][Bp]).
+// ---------------------------------------------------------------------------------------
+struct StatsLiteArgs {
+  const float* tT;
+  const float* vwT;
+  const float* ct0;      // [3J][Bp]
+  const float* ca0;      // [3J][Bp]
+  const float* vposedT;
+  const float* beta;     // [NS][Bp]
+  const float* skin4;    // [J*3][Bp] float4
+  float* aT_out;         // [3V][Bp] or null
+  float* partials;       // [n_segments][16][Bp]
+  const float* rec;
+  const int32_t* seg_start;
+  const int32_t* seg_part;
+  const int32_t* part_flags;
+  int n_segments, Bp, J, all_segments, segs_per_warp;
+};
+
+__host__ __device__ inline size_t stats_lite_smem_bytes(int J, int rec_len, int warps) {
+  return ((size_t)J * 3 * 128 + (size_t)warps * (2 * LITE_SUB * rec_len)) * sizeof(float) + (size_t)warps * 16 + 16;
+}
+
+template <int NS, bool WEIGHTED, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_stats_lite(const StatsLiteArgs a) {
+  extern __shared__ __align__(16) float s_st[];
+  constexpr int NSP = Rec<NS>::NSP, REC = Rec<NS>::LEN;
+  const int g = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Bp = a.Bp;
+  const int b = g * 32 + lane;
+  const float4* sq = reinterpret_cast<const float4*>(s_st);  // [J*3][32]
+  float* wbase = s_st + (size_t)a.J * 3 * 128;
+  RecStagerLite<REC> rs;
+  rs.buf = wbase + (size_t)warp * (2 * LITE_SUB * REC);
+  rs.bar = reinterpret_cast<uint64_t*>(wbase + (size_t)WARPS * (2 * LITE_SUB * REC)) + 2 * warp;
+  rs.src = a.rec;
+  rs.phase = 0;
+  if (lane == 0) {
+    sf_mbar_init(rs.bar, 1);
+    sf_mbar_init(rs.bar + 1, 1);
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  {
+    const int n = a.J * 3 * 32;
+    const float4* src = reinterpret_cast<const float4*>(a.skin4);
+    for (int q = threadIdx.x; q < n; q += WARPS * 32) {
+      const int r = q >> 5, l = q & 31;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_st + (size_t)q * 4);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + (size_t)r * Bp + g * 32 + l) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+  }
+  float beta[NS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) beta[s] = SF_IM(a.beta, s, Bp, b);
+  for (int q = 0; q < a.segs_per_warp; ++q) {
+    const int seg = (blockIdx.x * a.segs_per_warp + q) * WARPS + warp;
+    if (seg >= a.n_segments) break;
+    const int part = a.seg_part[seg];
+    const bool stat = (a.part_flags[part] & 1) != 0;
+    if (!stat && !(a.aT_out != nullptr && a.all_segments)) continue;
+    const int i0 = a.seg_start[seg], i1 = a.seg_start[seg + 1];
+    rs.i0 = i0;
+    rs.i1 = i1;
+    rs.issue(0, lane);
+    rs.issue(1, lane);
+    float ct[3], ca[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      ct[c] = SF_IM(a.ct0, part * 3 + c, Bp, b);
+      ca[c] = SF_IM(a.ca0, part * 3 + c, Bp, b);
+    }
+    float M[9], st[3], sa[3], W = 0.f;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) M[e] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) st[c] = sa[c] = 0.f;
+    JointCache jc;
+    jc.reset();
+    float t0[3], p0[3], t1[3], p1[3], w0 = 1.f, w1 = 1.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      t0[c] = SF_IM(a.tT, i0 * 3 + c, Bp, b);
+      p0[c] = SF_IM(a.vposedT, i0 * 3 + c, Bp, b);
+      t1[c] = p1[c] = 0.f;
+    }
+    if (WEIGHTED) w0 = SF_IM(a.vwT, i0, Bp, b);
+    if (i0 + 1 < i1) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        t1[c] = SF_IM(a.tT, (i0 + 1) * 3 + c, Bp, b);
+        p1[c] = SF_IM(a.vposedT, (i0 + 1) * 3 + c, Bp, b);
+      }
+      if (WEIGHTED) w1 = SF_IM(a.vwT, i0 + 1, Bp, b);
+    }
+    for (int i = i0; i < i1; ++i) {
+      if ((i - i0) % LITE_SUB == 0) {
+        const int k = (i - i0) / LITE_SUB;
+        rs.wait(k);
+        if (k >= 1) rs.issue(k + 1, lane);
+      }
+      float t[3], x[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        t[c] = t0[c];
+        x[c] = p0[c];
+        t0[c] = t1[c];
+        p0[c] = p1[c];
+      }
+      const float wv = w0;
+      w0 = w1;
+      if (i + 2 < i1) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          t1[c] = SF_IM(a.tT, (i + 2) * 3 + c, Bp, b);
+          p1[c] = SF_IM(a.vposedT, (i + 2) * 3 + c, Bp, b);
+        }
+        if (WEIGHTED) w1 = SF_IM(a.vwT, i + 2, Bp, b);
+      }
+      const float* rec = rs.rec(i);
+      const float4 w4 = *reinterpret_cast<const float4*>(rec);
+      const int4 j4 = *reinterpret_cast<const int4*>(rec + 4);
+      const float wk[4] = {w4.x, w4.y, w4.z, w4.w};
+      const int jk[4] = {j4.x, j4.y, j4.z, j4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (wk[k] != 0.f && jk[k] != jc.j[k]) {  // warp-uniform, rare
+          jc.j[k] = jk[k];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) jc.q[k][c] = sq[(size_t)(jk[k] * 3 + c) * 32 + lane];
+        }
+      }
+      float vs[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float2 y2 = make_float2(x[c], 0.f);
+#pragma unroll
+        for (int s2 = 0; s2 < NSP; s2 += 2) {
+          const float2 sv = *reinterpret_cast<const float2*>(rec + 8 + c * NSP + s2);
+          y2 = sf_fma2(sv, make_float2(beta[s2], (s2 + 1 < NS) ? beta[s2 + 1] : 0.f), y2);
+        }
+        vs[c] = y2.x + y2.y;
+      }
+      float2 B2[6];
+      jc.blend(wk, B2);
+      float ref[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        ref[c] = fmaf(B2[2 * c].x, vs[0], fmaf(B2[2 * c].y, vs[1], fmaf(B2[2 * c + 1].x, vs[2], B2[2 * c + 1].y)));
+      if (a.aT_out != nullptr) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) SF_IM(a.aT_out, i * 3 + c, Bp, b) = ref[c];
+      }
+      if (stat) {
+        float dt[3], wa[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          dt[c] = t[c] - ct[c];
+          wa[c] = WEIGHTED ? wv * (ref[c] - ca[c]) : (ref[c] - ca[c]);
+          st[c] = WEIGHTED ? fmaf(wv, dt[c], st[c]) : st[c] + dt[c];
+          sa[c] += wa[c];
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) M[r * 3 + c] = fmaf(dt[r], wa[c], M[r * 3 + c]);
+        W += wv;
+      }
+    }
+    if (stat) {
+      float* out = a.partials + (size_t)seg * 16 * Bp + b;
+#pragma unroll
+      for (int e = 0; e < 9; ++e) out[(size_t)e * Bp] = M[e];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        out[(size_t)(9 + c) * Bp] = st[c];
+        out[(size_t)(12 + c) * Bp] = sa[c];
+      }
+      out[(size_t)15 * Bp] = W;
+    }
+  }
+}
+
+}  // namespace sf

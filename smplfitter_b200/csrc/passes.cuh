@@ -23,6 +23,19 @@ ShapePlan plan_shape_pass(const smplfit_model_t* m, int groups);
 int max_shape_partials(const smplfit_model_t* m);
 void launch_shape_pass(const ShapeArgs& a, int ns, int groups, const ShapePlan& p, cudaStream_t st);
 void launch_shape_solve(const SolveArgs& a, double* Gd, int ns, int groups, cudaStream_t st);
+// closed-form ("lite") shape path (pass_lite.cu): availability = tables present; enabled = not switched off by
+// SMPLFIT_B200_SHAPE_VARIANT (6 = lite, the default; 4 / 5 / 0 / 1 select the per-vertex Gram kernels)
+struct LiteArgs;
+bool lite_available(const smplfit_model_t* m);
+bool lite_enabled(const smplfit_model_t* m);
+int lite_rows(int ns);                          // rows per segment of the lite partials
+int gram_closed_blocks(const smplfit_model_t* m);
+void launch_shape_lite(const LiteArgs& a, const smplfit_model_t* m, int groups, const float* RT, float* gcf_part,
+                       double* Yd, cudaStream_t st);
+// statistics pass against the skinned current fit in the same style (SMPLFIT_B200_STATS_VARIANT=0 selects k_stats_rec)
+struct StatsLiteArgs;
+bool stats_lite_enabled(const smplfit_model_t* m);
+void launch_stats_lite(const StatsLiteArgs& a, const smplfit_model_t* m, int groups, cudaStream_t st);
 // scale modes (final solve only): extra vertex pass + (NS+1)-unknown solve (pass_scale.cu)
 int scale_chunks(const smplfit_model_t* m);
 void launch_scale_pass(const ShapeArgs& a, int ns, int mode, int groups, cudaStream_t st);

@@ -86,6 +86,7 @@ struct RotArgs {
   float* RT;               // [J*(12+3NS)][Bp] or null (skip the shape front)
   float* RT4;              // optional quad layout of the same rows (fit_kernels.cuh Quad<NS> / CLay<NS>), or null
   int rt4_clay;            // 0: Quad<NS> row order (k_shape_pass_v2), 1: coordinate-major CLay<NS> (k_shape_pass_v3)
+  float* RT12;             // optional [J*3][Bp] float4 (R[c][0..2], T0[c]) for k_shape_lite, or null
   float* Pext;             // [J*3*(1+NS)][Bp]
   float* feat;             // [Bp][Kp]
   TreeTables t;
@@ -224,6 +225,12 @@ static __global__ void __launch_bounds__(32) k_front_rel(const RotArgs a) {
     Rj[e] = SF_IM(a.R_new, j * 9 + e, Bp, b);
     SF_IM(a.RT, j * RW + e, Bp, b) = Rj[e];
   }
+  if (a.RT12 != nullptr) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int xx = 0; xx < 3; ++xx) a.RT12[((size_t)(j * 3 + c) * Bp + b) * 4 + xx] = Rj[c * 3 + xx];
+  }
   if (a.RT4 != nullptr && a.rt4_clay) {
     const int nsp4 = (NS + 3) / 4 * 4, rc = 4 + nsp4, nq = 3 * rc / 4;
     for (int c = 0; c < 3; ++c) {
@@ -287,6 +294,7 @@ static __global__ void __launch_bounds__(32) k_front_fk(const RotArgs a) {
       const float tv = P[j * 3 + c] - (Rj[c * 3] * j0 + Rj[c * 3 + 1] * j1 + Rj[c * 3 + 2] * j2);
       SF_IM(a.Pext, j * TW + c * (1 + NS) + s, Bp, b) = P[j * 3 + c];
       SF_IM(a.RT, j * RW + 9 + c * (1 + NS) + s, Bp, b) = tv;
+      if (a.RT12 != nullptr && s == 0) a.RT12[((size_t)(j * 3 + c) * Bp + b) * 4 + 3] = tv;
       if (a.RT4 != nullptr && a.rt4_clay) {
         const int rc = 4 + (NS + 3) / 4 * 4;
         rt4_store(a.RT4, j, 3 * rc / 4, c * rc + (s == 0 ? 3 : 4 + (s - 1)), Bp, b, tv);
@@ -323,6 +331,7 @@ struct SolveArgs {
   float* trans;           // [3][Bp]
   float* refj;            // [3J][Bp]
   float* skin;            // [12J][Bp]
+  float* skin4;           // optional [J*3][Bp] float4 (A[c][0..2], tau[c]) copy of skin for k_stats_lite, or null
   const double* wS;      // (J,3,NS) D_k = sum_v w_vk S_v (closed-form SA), or null
   const double* wsum;    // (J)      n_k = sum_v w_vk
   int n_chunks, J, S, Bp, B, V, weighted;
@@ -333,6 +342,12 @@ struct SolveArgs {
   float scale_reg;
   float* scale_out;      // [Bp] scale_corr
   float reg, reg2, kid_reg;
+  // closed-form path (lite_kernels.cuh): partials = [n_chunks = n_segments][NS+3+3*slots][Bp] hold r | Sb | Y,
+  // G comes from gcf_part [n_gcf][NG][Bp] + G0, and r gets sum_k T_ks . Yd_k
+  int lite, lite_nl, n_gcf;
+  const float* gcf_part;
+  const double* G0;
+  const double* Yd;  // [3J][Bp]
 };
 
 // k_gram_entries<NS>: one thread per (instance, entry of [G | r | Sb | SA | W]): chunk partials
@@ -359,7 +374,21 @@ __global__ void __launch_bounds__(32) k_gram_entries(const SolveArgs a, double* 
   else kind = 4;
   double acc = 0.0;
   const bool from_partials = !(a.sa_closed_form && kind >= 3);
-  if (from_partials) {
+  if (a.lite && kind <= 2) {
+    if (kind == 0) {
+      acc = a.G0[e];
+      for (int q = 0; q < a.n_gcf; ++q) acc += (double)a.gcf_part[((size_t)q * NG + e) * Bp + b];
+    } else {
+      const int row = (kind == 1) ? s : NS + c;
+      for (int q = 0; q < a.n_chunks; ++q) acc += (double)a.partials[((size_t)q * a.lite_nl + row) * Bp + b];
+      if (kind == 1) {
+        for (int k = 0; k < J; ++k)
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc)
+            acc += (double)a.RT[(size_t)(k * RW + 9 + cc * (1 + NS) + 1 + s) * Bp + b] * a.Yd[(size_t)(k * 3 + cc) * Bp + b];
+      }
+    }
+  } else if (from_partials) {
     for (int q = 0; q < a.n_chunks; ++q) acc += (double)a.partials[((size_t)q * NACC + e) * Bp + b];
   } else if (kind == 4) {
     acc = (double)a.V;
@@ -569,6 +598,14 @@ static __global__ void __launch_bounds__(32) k_shape_out(const SolveArgs a, int 
     }
     SF_IM(a.refj, j * 3 + c, Bp, b) = prow[0] + pj + tr;
     SF_IM(a.skin, j * 12 + 9 + c, Bp, b) = trow[0] + tj + tr;
+    if (a.skin4 != nullptr) {
+      float4 q;
+      q.x = SF_IM(a.RT, j * RW + c * 3, Bp, b);
+      q.y = SF_IM(a.RT, j * RW + c * 3 + 1, Bp, b);
+      q.z = SF_IM(a.RT, j * RW + c * 3 + 2, Bp, b);
+      q.w = trow[0] + tj + tr;
+      reinterpret_cast<float4*>(a.skin4)[(size_t)(j * 3 + c) * Bp + b] = q;
+    }
   }
 }
 

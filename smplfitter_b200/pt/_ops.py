@@ -35,6 +35,20 @@ def _empty_like_dev(t: torch.Tensor) -> torch.Tensor:
     return torch.empty(0, device=t.device, dtype=torch.float32)
 
 
+def _distinct(tensors, inputs):
+    """Custom-op contract: returns may alias neither each other nor the inputs."""
+    seen = {x.untyped_storage().data_ptr() for x in inputs if x is not None and x.numel() > 0}
+    out = []
+    for t in tensors:
+        if t.numel() > 0:
+            p = t.untyped_storage().data_ptr()
+            if p in seen:
+                t = t.clone()
+            seen.add(t.untyped_storage().data_ptr())
+        out.append(t)
+    return out
+
+
 @torch.library.custom_op('smplfit_b200::forward', mutates_args=())
 def forward_op(handle: int, anchor: torch.Tensor, pose_rotvecs: Optional[torch.Tensor],
                shape_betas: Optional[torch.Tensor], trans: Optional[torch.Tensor],
@@ -42,7 +56,8 @@ def forward_op(handle: int, anchor: torch.Tensor, pose_rotvecs: Optional[torch.T
                glob_rotmats: Optional[torch.Tensor], return_vertices: bool) -> List[torch.Tensor]:
     res = _get(handle)._forward_impl(pose_rotvecs, shape_betas, trans, kid_factor, rel_rotmats, glob_rotmats,
                                      return_vertices)
-    return [res['joints'], res['orientations'], res['vertices'] if return_vertices else _empty_like_dev(anchor)]
+    return _distinct([res['joints'], res['orientations'], res['vertices'] if return_vertices else _empty_like_dev(anchor)],
+                     [pose_rotvecs, shape_betas, trans, kid_factor, rel_rotmats, glob_rotmats])
 
 
 @forward_op.register_fake
@@ -71,9 +86,13 @@ def fit_op(handle: int, target_vertices: torch.Tensor, target_joints: Optional[t
         target_vertices, target_joints, vertex_weights, joint_weights, num_iter, beta_regularizer, beta_regularizer2,
         scale_regularizer, None if kid_regularizer != kid_regularizer else kid_regularizer, share_beta,
         final_adjust_rots, scale_target, scale_fit, initial_pose_rotvecs, initial_shape_betas, initial_kid_factor, keys)
-    e = _empty_like_dev(target_vertices)
-    return [res['shape_betas'], res['trans'], res['orientations'], res['relative_orientations'],
-            res.get('pose_rotvecs', e), res.get('kid_factor', e), res.get('scale_corr', e)]
+    e = lambda: _empty_like_dev(target_vertices)  # noqa: E731
+    return _distinct(
+        [res['shape_betas'], res['trans'], res['orientations'], res['relative_orientations'],
+         res['pose_rotvecs'] if 'pose_rotvecs' in res else e(), res['kid_factor'] if 'kid_factor' in res else e(),
+         res['scale_corr'] if 'scale_corr' in res else e()],
+        [target_vertices, target_joints, vertex_weights, joint_weights, initial_pose_rotvecs, initial_shape_betas,
+         initial_kid_factor])
 
 
 @fit_op.register_fake
@@ -90,7 +109,7 @@ def _(handle, target_vertices, target_joints, vertex_weights, joint_weights, num
 
 @torch.library.custom_op('smplfit_b200::convert_vertices', mutates_args=())
 def convert_vertices_op(handle: int, inp_vertices: torch.Tensor) -> torch.Tensor:
-    return _get(handle)._convert_vertices_impl(inp_vertices)
+    return _distinct([_get(handle)._convert_vertices_impl(inp_vertices)], [inp_vertices])[0]
 
 
 @convert_vertices_op.register_fake

@@ -97,14 +97,79 @@ class BodyFitter(nn.Module):
             for x in range(3):
                 rec[:, 8 + x * nsp:8 + x * nsp + ns] = sd_np[:, x, :]
             self.register_buffer('_t_fit_rec', torch.tensor(np.ascontiguousarray(rec[order])), persistent=False)
+            self._build_pair_constants(idx4, w4, sd_np, J, ns)
         else:
             self._t_fit_rec = None
+            self._gcf_npairs = 0
         self._handle = _ops.register(self)
         self.to(body_model.v_template.device)
 
     @torch.jit.unused
+    def _build_pair_constants(self, idx4, w4, sd, J, ns):
+        """Model constants of the closed-form Gramian (include/smplfit_b200.h, ``gcf_*``), in float64:
+        over the joint pairs (k, l) sharing a vertex, A_kl[a,b,s,t] = sum_v w_vk w_vl S_vs[a] S_vt[b],
+        Bm_kl[a,s] = sum_v w_vk w_vl S_vs[a], W_kl = sum_v w_vk w_vl."""
+        V = idx4.shape[0]
+        iu, ju = np.triu_indices(ns)
+        ng = len(iu)
+        ngp = (ng + 3) // 4 * 4
+        # per pair: vertex lists and weight products (a vertex lists each joint once; padded slots have w = 0)
+        prods = {}
+        for a in range(4):
+            for b in range(4):
+                ww = w4[:, a].astype(np.float64) * w4[:, b].astype(np.float64)
+                nz = np.nonzero(ww)[0]
+                ka, kb = idx4[nz, a], idx4[nz, b]
+                for k, l, v, x in zip(ka.tolist(), kb.tolist(), nz.tolist(), ww[nz].tolist()):
+                    if k <= l and not (k == l and a != b):
+                        prods.setdefault((k, l), []).append((v, x))
+        S = sd.astype(np.float64)  # (V,3,ns)
+        off = sorted(p for p in prods if p[0] != p[1])
+        A = np.zeros((max(len(off), 1), 9, ngp), np.float32)
+        G0 = np.zeros(ng, np.float64)
+        Bm, Wkl = {}, {}
+        for p, lst in prods.items():
+            v = np.array([q[0] for q in lst])
+            x = np.array([q[1] for q in lst])
+            Sv = S[v]
+            Bm[p] = np.einsum('v,vas->as', x, Sv)
+            Wkl[p] = x.sum()
+            full = np.einsum('v,vae,vbe->abe', x, Sv[:, :, iu], Sv[:, :, ju])  # A[a,b,(s,t)]
+            if p[0] == p[1]:
+                G0 += np.einsum('aae->e', full)
+            else:
+                A[off.index(p), :, :ng] = (full + full.transpose(1, 0, 2)).reshape(9, ng)
+        lstart, lk, bm_cells, wh_cells = [0], [], [], []
+        for l in range(J):
+            for k in range(J):
+                p = (min(k, l), max(k, l))
+                if p in prods:
+                    lk.append(k)
+                    cell = np.zeros((3, (ns + 3) // 4 * 4))
+                    cell[:, :ns] = Bm[p]
+                    bm_cells.append(cell)
+                    wh_cells.append(0.5 * Wkl[p])
+            lstart.append(len(lk))
+        i32 = lambda x: torch.tensor(np.ascontiguousarray(x), dtype=torch.int32)  # noqa: E731
+        reg = lambda n, t: self.register_buffer(n, t, persistent=False)  # noqa: E731
+        reg('_t_gcf_pairs', i32(np.array(off or [(0, 0)], np.int32).reshape(-1, 2)))
+        reg('_t_gcf_A', torch.tensor(np.ascontiguousarray(A)))
+        reg('_t_gcf_G0', torch.tensor(G0))
+        reg('_t_gcf_lstart', i32(np.array(lstart)))
+        reg('_t_gcf_lk', i32(np.array(lk)))
+        reg('_t_gcf_Bm', torch.tensor(np.ascontiguousarray(np.stack(bm_cells).astype(np.float32))))
+        reg('_t_gcf_Wh', torch.tensor(np.array(wh_cells, np.float32)))
+        self._gcf_npairs = len(off)
+
+    @torch.jit.unused
     def _struct(self) -> _native.ModelStruct:
+        gcf = {}
+        if self._gcf_npairs > 0:
+            gcf = dict(gcf_npairs=self._gcf_npairs,
+                       **{n: getattr(self, '_t_' + n).data_ptr() for n in
+                          ('gcf_pairs', 'gcf_A', 'gcf_G0', 'gcf_lstart', 'gcf_lk', 'gcf_Bm', 'gcf_Wh')})
         return self.body_model._struct(dict(
+            **gcf,
             fit_ns=self._ns,
             fit_shapedirs=self._t_fit_shapedirs.data_ptr(),
             fit_Jt_ext=self.J_template_ext.data_ptr(),

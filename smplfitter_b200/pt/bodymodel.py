@@ -20,8 +20,12 @@ SEG_LEN = 64  # vertices per statistics segment
 CHUNK_LEN = 128  # vertices per shape-pass chunk
 
 
-def _segments(part_sorted: np.ndarray, num_joints: int):
-    """Split the part-grouped vertex order into segments of <= SEG_LEN vertices of one part."""
+N_SLOTS = 12  # distinct skinning joints a segment may touch (per-warp accumulator slots of k_shape_lite)
+
+
+def _segments(part_sorted: np.ndarray, num_joints: int, joint_sets=None):
+    """Split the part-grouped vertex order into segments of <= SEG_LEN vertices of one part that
+    touch at most N_SLOTS distinct skinning joints (``joint_sets[i]`` = joints of sorted vertex i)."""
     seg_start, seg_part = [0], []
     part_seg_begin = np.zeros(num_joints + 1, dtype=np.int32)
     V = len(part_sorted)
@@ -32,6 +36,14 @@ def _segments(part_sorted: np.ndarray, num_joints: int):
         done = 0
         while done < n:
             step = min(SEG_LEN, n - done)
+            if joint_sets is not None:
+                seen = set()
+                for q in range(step):
+                    nxt = seen | set(joint_sets[i + done + q])
+                    if len(nxt) > N_SLOTS:
+                        step = max(q, 1)
+                        break
+                    seen = nxt
             seg_part.append(p)
             seg_start.append(i + done + step)
             done += step
@@ -39,6 +51,23 @@ def _segments(part_sorted: np.ndarray, num_joints: int):
     part_seg_begin[num_joints] = len(seg_part)
     assert i == V
     return np.array(seg_start, np.int32), np.array(seg_part, np.int32), part_seg_begin
+
+
+def _slot_tables(seg_start, joint_sets, num_joints):
+    """Per segment the sorted list of joints it touches, and per joint the (segment, slot) cells."""
+    n_seg = len(seg_start) - 1
+    seg_slots = np.full((n_seg, N_SLOTS), -1, np.int32)
+    cells = [[] for _ in range(num_joints)]
+    for sgm in range(n_seg):
+        js = sorted(set().union(*[set(joint_sets[i]) for i in range(seg_start[sgm], seg_start[sgm + 1])]))
+        assert len(js) <= N_SLOTS
+        for slot, j in enumerate(js):
+            seg_slots[sgm, slot] = j
+            cells[j].append(sgm * N_SLOTS + slot)
+    yj_start = np.zeros(num_joints + 1, np.int32)
+    yj_start[1:] = np.cumsum([len(c) for c in cells])
+    yj_entry = np.array([e for c in cells for e in c] or [0], np.int32)
+    return seg_slots, yj_start, yj_entry
 
 
 class BodyModel(nn.Module):
@@ -98,11 +127,23 @@ class BodyModel(nn.Module):
         plan = self._plan
         V, J = self.num_vertices, self.num_joints
         P = 9 * (J - 1)
-        order = np.argsort(plan.part_assignment, kind='stable').astype(np.int32)
+        skin_idx, skin_w, K = masks.sparse_skin_table(w32)
+        if K <= 4:
+            # internal vertex order: by part, then by the tuple of skinning joints (weight-descending slots), so that
+            # consecutive vertices share their joints and the vertex kernels keep the joint rows in registers
+            key_idx = np.zeros((V, 4), np.int32)
+            key_w = np.zeros((V, 4), np.float32)
+            key_idx[:, :K], key_w[:, :K] = skin_idx, skin_w
+            key_idx[:, K:] = skin_idx[:, :1]
+            key_idx = np.take_along_axis(key_idx, np.argsort(-key_w, axis=1, kind='stable'), axis=1)
+            order = np.lexsort((np.arange(V), key_idx[:, 3], key_idx[:, 2], key_idx[:, 1], key_idx[:, 0],
+                                plan.part_assignment)).astype(np.int32)
+        else:
+            order = np.argsort(plan.part_assignment, kind='stable').astype(np.int32)
         inv_order = np.empty(V, np.int32)
         inv_order[order] = np.arange(V, dtype=np.int32)
-        seg_start, seg_part, part_seg_begin = _segments(plan.part_assignment[order], J)
-        skin_idx, skin_w, K = masks.sparse_skin_table(w32)
+        joint_sets = [tuple(int(j) for j, w in zip(skin_idx[v], skin_w[v]) if w != 0) for v in order]
+        seg_start, seg_part, part_seg_begin = _segments(plan.part_assignment[order], J, joint_sets if K <= 4 else None)
         Kp = (P + 15) // 16 * 16
         posedirs_fit = np.zeros((V * 3, Kp), np.float32)
         posedirs_fit[:, :P] = self.posedirs.numpy()[order].reshape(V * 3, P)
@@ -151,6 +192,9 @@ class BodyModel(nn.Module):
                 frec[:, 12 + x * SP:12 + x * SP + S] = sd_np[:, x, :]
             frec[:, 12 + 3 * SP:12 + 3 * SP + 3] = self.kid_shapedir.numpy()
             t['fwd_rec'] = f32(frec)
+        if K <= 4:
+            seg_slots, yj_start, yj_entry = _slot_tables(seg_start, joint_sets, J)
+            t['seg_slots'], t['yj_start'], t['yj_entry'] = i32(seg_slots), i32(yj_start), i32(yj_entry)
         for k, v in t.items():
             self.register_buffer('_t_' + k, v, persistent=False)
         self._dims = dict(
@@ -189,6 +233,10 @@ class BodyModel(nn.Module):
         s.fit_ns = 0
         s.fwd_rec = self._t_fwd_rec.data_ptr() if hasattr(self, '_t_fwd_rec') else 0
         s.fwd_rec_len = self._fwd_rec_len
+        if hasattr(self, '_t_seg_slots'):
+            s.seg_slots, s.yj_start, s.yj_entry = (self._t_seg_slots.data_ptr(), self._t_yj_start.data_ptr(),
+                                                    self._t_yj_entry.data_ptr())
+            s.n_slots = N_SLOTS
         if extra:
             for k, v in extra.items():
                 setattr(s, k, v)

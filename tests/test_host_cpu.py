@@ -126,3 +126,69 @@ def test_modules_are_scriptable():
         sm(shape_betas=torch.zeros(1, 10))
     with pytest.raises(RuntimeError):
         sf.fit(torch.zeros(2, bm.num_vertices, 3))
+
+
+@pytest.mark.parametrize('mname,kid', [('smpl_tiny', False), ('smplx_tiny', True)])
+def test_closed_form_gram_tables(mname, kid):
+    """The model constants behind k_gram_closed / k_shape_lite (include/smplfit_b200.h gcf_*, seg_slots, yj_*):
+    a float64 emulation of the two kernels from the device tables reproduces the per-vertex normal equations
+    G = sum_v jac^T jac, r = sum_v jac^T b of pt/bodyfitter.py:999-1048."""
+    from scipy.spatial.transform import Rotation
+
+    from smplfitter_b200.pt import BodyFitter, BodyModel
+    from smplfitter_b200.pt.bodymodel import N_SLOTS
+
+    bm = BodyModel(mname)
+    f = BodyFitter(bm, enable_kid=kid)
+    J, V, ns = bm.num_joints, bm.num_vertices, f._ns
+    rng = np.random.default_rng(0)
+    R = Rotation.random(J, random_state=1).as_matrix()
+    T = rng.normal(size=(J, 3, 1 + ns))            # T_ext[k][c][0 | 1+s]
+    t, vp = rng.normal(size=(V, 3)), rng.normal(size=(V, 3))  # internal vertex order
+    rec = f._t_fit_rec.numpy().astype(np.float64)
+    nsp = (ns + 1) // 2 * 2
+    w4 = rec[:, 0:4]
+    j4 = f._t_fit_rec.numpy()[:, 4:8].copy().view(np.int32)
+    S = np.stack([rec[:, 8 + x * nsp:8 + x * nsp + ns] for x in range(3)], axis=1)  # (V,3,ns)
+    # brute force
+    Rb = np.einsum('vk,vkab->vab', w4, R[j4])
+    Tb = np.einsum('vk,vkas->vas', w4, T[j4])
+    jac = np.einsum('vab,vbs->vas', Rb, S) + Tb[:, :, 1:]
+    b = t - (np.einsum('vab,vb->va', Rb, vp) + Tb[:, :, 0])
+    G_ref, r_ref = np.einsum('vas,vat->st', jac, jac), np.einsum('vas,va->s', jac, b)
+    # k_gram_closed
+    iu, ju = np.triu_indices(ns)
+    ng = len(iu)
+    G = f._t_gcf_G0.numpy().copy()
+    A = f._t_gcf_A.numpy().astype(np.float64)
+    for p, (k, l) in enumerate(f._t_gcf_pairs.numpy()[:f._gcf_npairs]):
+        G += np.einsum('ab,abe->e', R[k].T @ R[l], A[p, :, :ng].reshape(3, 3, ng))
+    lstart, lk = f._t_gcf_lstart.numpy(), f._t_gcf_lk.numpy()
+    Bm, Wh = f._t_gcf_Bm.numpy().astype(np.float64)[:, :, :ns], f._t_gcf_Wh.numpy().astype(np.float64)
+    for l in range(J):
+        Q = np.zeros((3, ns))
+        for q in range(lstart[l], lstart[l + 1]):
+            Q += R[lk[q]] @ Bm[q] + Wh[q] * T[lk[q]][:, 1:]
+        Tl = T[l][:, 1:]
+        G += np.einsum('ce,ce->e', Tl[:, ju], Q[:, iu]) + np.einsum('ce,ce->e', Tl[:, iu], Q[:, ju])
+    Gm = np.zeros((ns, ns))
+    Gm[iu, ju] = G
+    Gm[ju, iu] = G
+    assert np.abs(Gm - G_ref).max() <= 2e-6 * np.abs(G_ref).max()  # constants are stored in float32
+    # k_shape_lite + k_lite_reduce
+    seg_start, seg_slots = bm._t_seg_start.numpy(), bm._t_seg_slots.numpy()
+    n_seg = len(seg_start) - 1
+    z = np.einsum('vca,vc->va', Rb, b)
+    r = np.einsum('vas,va->s', S, z)
+    cells = np.zeros((n_seg * N_SLOTS, 3))
+    for sgm in range(n_seg):
+        lut = {int(j): sl for sl, j in enumerate(seg_slots[sgm]) if j >= 0}
+        for i in range(seg_start[sgm], seg_start[sgm + 1]):
+            for k in range(4):
+                if w4[i, k] != 0:
+                    cells[sgm * N_SLOTS + lut[int(j4[i, k])]] += w4[i, k] * b[i]
+    yj_start, yj_entry = bm._t_yj_start.numpy(), bm._t_yj_entry.numpy()
+    for k in range(J):
+        Yk = cells[yj_entry[yj_start[k]:yj_start[k + 1]]].sum(axis=0)
+        r += T[k][:, 1:].T @ Yk
+    assert np.abs(r - r_ref).max() <= 1e-9 * np.abs(r_ref).max()
