@@ -256,12 +256,40 @@ class BodyModel(nn.Module):
         """Vertices, joints and global orientations for a batch (pt/bodymodel.py:121-307).
 
         TorchScript-compatible: dispatches through the ``smplfit_b200::forward`` custom op."""
+        if not torch.jit.is_scripting():
+            # eager callers get the reference's TypeError / ValueError before the op schema sees the arguments
+            self._check_forward_inputs(pose_rotvecs, shape_betas, trans, kid_factor, rel_rotmats, glob_rotmats)
         outs = torch.ops.smplfit_b200.forward(self._handle, self.v_template, pose_rotvecs, shape_betas, trans,
                                               kid_factor, rel_rotmats, glob_rotmats, return_vertices)
         result: Dict[str, torch.Tensor] = {'joints': outs[0], 'orientations': outs[1]}
         if return_vertices:
             result['vertices'] = outs[2]
         return result
+
+    @torch.jit.unused
+    def _check_forward_inputs(self, pose_rotvecs, shape_betas, trans, kid_factor, rel_rotmats, glob_rotmats):
+        """Argument checks of pt/bodymodel.py:173-200 (skipped under TorchScript, as in the reference)."""
+        n_rot = sum(x is not None for x in (pose_rotvecs, rel_rotmats, glob_rotmats))
+        if n_rot > 1:
+            raise ValueError(
+                'Only one rotation input may be provided (pose_rotvecs, rel_rotmats, or glob_rotmats).'
+            )
+        for name, arg, min_ndim in [
+            ('pose_rotvecs', pose_rotvecs, 2), ('shape_betas', shape_betas, 2), ('trans', trans, 2),
+            ('kid_factor', kid_factor, 1), ('rel_rotmats', rel_rotmats, 4), ('glob_rotmats', glob_rotmats, 4),
+        ]:
+            if arg is not None:
+                if isinstance(arg, np.ndarray):
+                    raise TypeError(
+                        f"Expected torch.Tensor for '{name}', got numpy.ndarray. "
+                        f'Convert with torch.from_numpy() or torch.as_tensor().'
+                    )
+                if arg.ndim < min_ndim:
+                    raise ValueError(
+                        f"Expected batched input for '{name}' with at least {min_ndim} dimensions, but "
+                        f'got shape {tuple(arg.shape)}. For single (unbatched) inputs, use model.single() '
+                        f'instead.'
+                    )
 
     @torch.jit.unused
     def _forward_impl(
