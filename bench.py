@@ -37,6 +37,7 @@ sys.path.insert(0, ROOT)
 
 BATCH = 4096
 NUM_ITER = 3
+E2E_CHUNK = 512
 MODEL = 'smpl'
 FIT_KW = dict(num_iter=NUM_ITER, beta_regularizer=1.0, final_adjust_rots=True,
               requested_keys=['pose_rotvecs', 'shape_betas'])
@@ -202,7 +203,8 @@ def main():
     h_tv = torch.empty(tv.shape, dtype=torch.float32, pin_memory=True).copy_(tv.cpu())
     h_tj = torch.empty(tj.shape, dtype=torch.float32, pin_memory=True).copy_(tj.cpu())
     h_out = {k: torch.empty(s, dtype=torch.float32, pin_memory=True)
-             for k, s in (('pose_rotvecs', (B, 3 * J)), ('shape_betas', (B, S)), ('trans', (B, 3)))}
+             for k, s in (('pose_rotvecs', (B, 3 * J)), ('shape_betas', (B, S)), ('trans', (B, 3)),
+                          ('orientations', (B, J, 3, 3)), ('relative_orientations', (B, J, 3, 3)))}
 
     def barrier():
         if world > 1:
@@ -213,9 +215,10 @@ def main():
         return fitter.fit(tv, tj, **FIT_KW)
 
     def step_e2e():
-        # public API for host-resident inputs: chunked H2D copies overlapped with the fits, results
-        # land in pinned host memory (BodyFitter.fit_from_host)
-        return fitter.fit_from_host(h_tv, h_tj, chunk_size=1024, **FIT_KW)
+        # public API for host-resident inputs (BodyFitter.fit_from_host -> smplfit_fit_host): chunked H2D
+        # copies overlapped with the fits, every result key of fit() copied back into pinned host memory,
+        # stream synchronised before it returns
+        return fitter.fit_from_host(h_tv, h_tj, chunk_size=E2E_CHUNK, out=h_out, **FIT_KW)
 
     def timed(fn, steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -323,7 +326,12 @@ def main():
                        'vs_baseline_note': 'published 9481 fits/s is the reference on an RTX 3090 (README.md:15)',
                        'parallelism': f'batch-sharded x{world}, no data-path collective'},
             'e2e': {'value': e2e_value, 'unit': 'fits/s', 'h2d_bytes_per_step': int(B * (V + J) * 12),
-                    'd2h_bytes_per_step': int(B * (3 * J + S + 3) * 4), 'ms_per_step': ms_e2e / args.steps},
+                    'd2h_bytes_per_step': int(sum(t.numel() for t in h_out.values()) * 4),
+                    'ms_per_step': ms_e2e / args.steps, 'chunk': E2E_CHUNK,
+                    'pcie_floor_ms': B * (V + J) * 12 / 54e9 * 1000,
+                    'note': 'BodyFitter.fit_from_host: pinned host targets -> pinned host results, stream '
+                            'synchronised every step; pcie_floor_ms = H2D bytes / 54 GB/s (measured pinned H2D '
+                            'rate of the box, scripts/e2e_diag.py)'},
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
             'v2v_mm_roundtrip': v2v_mm, 'lbs_forward': lbs,
         }

@@ -11,7 +11,9 @@
  *                                   _part_sums :235, _fit_shape :840, _fit_shape_gram :960,
  *                                   _fit_shape_general :1104, _fit_global_rotations :1321,
  *                                   _fit_global_rotations_dependent :1418) and pt/rotation.py
+ *   smplfit_fit_host           <- the same fit() for host-resident inputs (chunked H2D / fit overlap)
  *   smplfit_fit_known_pose     <- pt/bodyfitter.py:552-653    BodyFitter.fit_with_known_pose
+ *   smplfit_fit_known_shape    <- pt/bodyfitter.py:656-838    BodyFitter.fit_with_known_shape
  *   smplfit_convert_vertices   <- pt/bodyconverter.py:129-149 BodyConverter.convert_vertices
  *
  * Conventions: plain pointers and sizes only (no torch types).  All pointers are DEVICE
@@ -114,7 +116,10 @@ typedef struct smplfit_model {
   const float* gcf_Wh;          /* (cells) W_kl / 2 */
   int32_t n_slots;              /* slots per segment (12) */
   int32_t gcf_npairs;
-  const void* reserved_ptr[4];
+  const float* gcf_AT_hi;       /* (roundup(NG, 256), roundup(9 gcf_npairs, 32)) gcf_A transposed to [e][pair*9 + a*3 + b], zero
+                                   padded, tf32-exact high part: the pair term as a tcgen05 GEMM against (R_k^T R_l) features */
+  const float* gcf_AT_lo;       /* same shape, gcf_A^T - gcf_AT_hi */
+  const void* reserved_ptr[2];
 } smplfit_model_t;
 
 /* Options of BodyFitter.fit (pt/bodyfitter.py:283-302). */
@@ -166,6 +171,22 @@ int smplfit_fit(const smplfit_model_t* m, int64_t batch, const float* target_ver
                 float* out_trans, float* out_orientations, float* out_rel_orientations,
                 float* out_kid_factor, float* out_scale_corr, void* workspace,
                 size_t workspace_bytes, void* stream);
+
+/* -- BodyFitter.fit for HOST-resident targets (the end-to-end form of pt/bodyfitter.py:283-549: what a caller holding
+ * numpy / CPU tensors pays for `fitter.fit(torch.as_tensor(x).cuda(), ...)` followed by `.cpu()` on the results).
+ * host_* pointers are HOST memory (page-locked for the copies to overlap the fits; pageable memory works but
+ * serialises); `workspace` is DEVICE memory of smplfit_fit_host_workspace_bytes.  The batch is processed in
+ * chunks of `chunk` instances: the H2D copy of chunk k+1 runs on a library-owned copy stream while chunk k is
+ * fitted on `stream`; the results are copied back on `stream` and are valid once `stream` has been synchronised.
+ * No vertex/joint weights, initial guesses or share_beta here (per-instance options go through smplfit_fit).
+ * host_orientations / host_rel_orientations / host_kid_factor / host_scale_corr may be NULL. */
+size_t smplfit_fit_host_workspace_bytes(const smplfit_model_t* m, int64_t batch, int64_t chunk,
+                                        const smplfit_fit_opts_t* opts, int has_joints);
+int smplfit_fit_host(const smplfit_model_t* m, int64_t batch, int64_t chunk, const float* host_target_vertices,
+                     const float* host_target_joints, const smplfit_fit_opts_t* opts, float* host_pose_rotvecs,
+                     float* host_shape_betas, float* host_trans, float* host_orientations,
+                     float* host_rel_orientations, float* host_kid_factor, float* host_scale_corr,
+                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* -- BodyFitter.fit_with_known_pose (pt/bodyfitter.py:552-653): shape/translation only.
  * glob_rotmats (B,J,3,3) are the global orientations of the known pose. */

@@ -51,7 +51,7 @@ ms, _ = timed(lambda: hb.copy_(d, non_blocking=True))
 out['d2h_gbs'] = h_tv.numel() * 4 / ms / 1e6
 ms, iss = timed(lambda: fitter.fit(tv, tj, **kw))
 out['resident_ms'], out['resident_issue_ms'] = ms, iss
-for cs in (256, 512, 1024, 2048, 4096):
+for cs in (128, 256, 512, 1024, 2048, 4096):
     ms, iss = timed(lambda: fitter.fit_from_host(h_tv, h_tj, chunk_size=cs, **kw))
     out[f'from_host_{cs}_ms'], out[f'from_host_{cs}_issue_ms'] = ms, iss
 for bs in (32, 256, 1024):

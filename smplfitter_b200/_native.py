@@ -43,7 +43,7 @@ class ModelStruct(C.Structure):
         + [(n, _F) for n in ('seg_slots', 'yj_start', 'yj_entry', 'gcf_pairs', 'gcf_A', 'gcf_G0', 'gcf_lstart',
                              'gcf_lk', 'gcf_Bm', 'gcf_Wh')]
         + [('n_slots', C.c_int32), ('gcf_npairs', C.c_int32)]
-        + [('reserved_ptr', _F * 4)]
+        + [('gcf_AT_hi', _F), ('gcf_AT_lo', _F), ('reserved_ptr', _F * 2)]
     )
 
 
@@ -94,6 +94,15 @@ def lib():
     L.smplfit_fit.restype = C.c_int
     L.smplfit_fit.argtypes = (
         [C.POINTER(ModelStruct), C.c_int64] + [_F] * 9 + [C.POINTER(FitOpts)] + [_F] * 7
+        + [_F, C.c_size_t, _F]
+    )
+    L.smplfit_fit_host_workspace_bytes.restype = C.c_size_t
+    L.smplfit_fit_host_workspace_bytes.argtypes = [
+        C.POINTER(ModelStruct), C.c_int64, C.c_int64, C.POINTER(FitOpts), C.c_int,
+    ]
+    L.smplfit_fit_host.restype = C.c_int
+    L.smplfit_fit_host.argtypes = (
+        [C.POINTER(ModelStruct), C.c_int64, C.c_int64, _F, _F, C.POINTER(FitOpts)] + [_F] * 7
         + [_F, C.c_size_t, _F]
     )
     L.smplfit_fit_known_pose.restype = C.c_int

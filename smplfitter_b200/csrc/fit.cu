@@ -20,7 +20,7 @@ std::vector<ProfRec> g_prof;
 struct FitWs {
   double* Gd;
   float *mean, *tT, *tjT, *vwT, *jwT, *vposedT, *R, *R2, *RT, *Pext, *feat, *gpart, *beta, *trans, *refj,
-      *skin, *spart, *aT, *ajT, *initjT, *RT4, *zpart, *scale, *mpart, *RT12, *gcfpart, *skin4;
+      *skin, *spart, *aT, *ajT, *initjT, *RT4, *zpart, *scale, *mpart, *RT12, *gcfpart, *skin4, *pairfeat;
   double *Zd, *Cd, *sums, *Yd;
   void* tc_scratch;
   size_t bytes;
@@ -57,6 +57,7 @@ static FitWs carve(void* base, const smplfit_model_t* m, int64_t B, int has_join
   w.RT12 = lite_available(m) ? c.take<float>((size_t)12 * J * Bp) : nullptr;
   w.gcfpart = lite_available(m) ? c.take<float>((size_t)gram_closed_blocks(m) * (NS * (NS + 1) / 2) * Bp) : nullptr;
   w.Yd = lite_available(m) ? c.take<double>((size_t)3 * J * Bp) : nullptr;
+  w.pairfeat = (lite_available(m) && gram_pairs_scratch_floats(m, (int)Bp) > 0) ? c.take<float>(gram_pairs_scratch_floats(m, (int)Bp)) : nullptr;
   w.Gd = c.take<double>((size_t)shape_nacc(NS) * Bp);
   w.beta = c.take<float>((size_t)NS * Bp);
   w.trans = c.take<float>(3 * Bp);
@@ -145,7 +146,7 @@ static void run_shape(FitCtx& c, int scale_mode, const float* beta_ref, const fl
     la.tT = c.w.tT; la.vposedT = c.w.vposedT; la.RT12 = c.w.RT12; la.rec = m->fit_rec; la.seg_start = m->seg_start;
     la.seg_slots = m->seg_slots; la.partials = c.w.gpart; la.n_segments = m->n_segments; la.J = m->num_joints;
     la.Bp = c.Bp; la.segs_per_warp = 1;
-    launch_shape_lite(la, m, c.groups, c.w.RT, c.w.gcfpart, c.w.Yd, c.st);
+    launch_shape_lite(la, m, c.groups, c.w.RT, c.w.gcfpart, c.w.Yd, c.w.pairfeat, c.st);
     so.lite = 1; so.lite_nl = lite_rows(m->fit_ns); so.n_gcf = gram_closed_blocks(m); so.gcf_part = c.w.gcfpart;
     so.G0 = m->gcf_G0; so.Yd = c.w.Yd;
   } else {

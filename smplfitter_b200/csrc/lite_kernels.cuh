@@ -366,6 +366,60 @@ __global__ void __launch_bounds__(256) k_gram_pairs(const GramClosedArgs a) {
   }
 }
 
+// k_pair_feat: the features of the pair term for the tensor-core path (vposed_tc.cu tc_gemm_run):
+//   X[b][p*9 + a*3 + c] = (R_k^T R_l)[a][c]   for pair p = (k, l),
+// written pre-split into tf32-exact hi / lo parts, [Bt][Kt] row-major (columns >= 9 npairs and rows >= Bp are zero).
+// One CTA per 32 instances: the rotations are staged in shared memory transposed to [instance][J*9] (odd stride),
+// warp w handles instances 4w..4w+3, lanes run over the pairs so a warp's stores cover 1152 contiguous bytes.
+struct PairFeatArgs {
+  const float* RT;  // [J*RW][Bp]
+  const int32_t* pairs;
+  float *hi, *lo;   // [Bt][Kt]
+  int npairs, J, RW, Bp, Kt;
+};
+
+static __global__ void __launch_bounds__(256) k_pair_feat(const PairFeatArgs a) {
+  extern __shared__ __align__(16) float s_R[];  // [32][stride]
+  const int g = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int J9 = a.J * 9, stride = J9 | 1;
+  const bool valid = g * 32 < a.Bp;  // Bp % 32 == 0: a group is entirely inside or outside the batch
+  if (valid) {
+    for (int q = threadIdx.x; q < J9 * 32; q += 256) {
+      const int row = q >> 5, l = q & 31;
+      const int k = row / 9, e = row % 9;
+      s_R[l * stride + row] = a.RT[(size_t)(k * a.RW + e) * a.Bp + g * 32 + l];
+    }
+  }
+  __syncthreads();
+  const int K9 = a.npairs * 9;
+  for (int ii = 0; ii < 4; ++ii) {
+    const int i = warp * 4 + ii;
+    float* hi = a.hi + (size_t)(g * 32 + i) * a.Kt;
+    float* lo = a.lo + (size_t)(g * 32 + i) * a.Kt;
+    if (valid) {
+      const float* R = s_R + i * stride;
+      for (int p = lane; p < a.npairs; p += 32) {
+        const int k = __ldg(a.pairs + 2 * p), l = __ldg(a.pairs + 2 * p + 1);
+        const float* Rk = R + k * 9;
+        const float* Rl = R + l * 9;
+#pragma unroll
+        for (int aa = 0; aa < 3; ++aa)
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc) {
+            const float x = fmaf(Rk[aa], Rl[cc], fmaf(Rk[3 + aa], Rl[3 + cc], Rk[6 + aa] * Rl[6 + cc]));
+            const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+            hi[p * 9 + aa * 3 + cc] = h;
+            lo[p * 9 + aa * 3 + cc] = x - h;
+          }
+      }
+      for (int q = K9 + lane; q < a.Kt; q += 32) hi[q] = lo[q] = 0.f;
+    } else {
+      for (int q = lane; q < a.Kt; q += 32) hi[q] = lo[q] = 0.f;
+    }
+  }
+}
+
 template <int NS>
 __global__ void __launch_bounds__(256) k_gram_trans(const GramClosedArgs a) {
   extern __shared__ __align__(16) float s_rows[];  // [J][3 + NS][32], then reused as the reduction scratch

@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "lite_kernels.cuh"
 #include "passes.cuh"
+#include "vposed_tc.cuh"
 
 namespace sf {
 
@@ -74,8 +75,17 @@ bool stats_lite_enabled(const smplfit_model_t* m) {
 
 int lite_rows(int ns) { return ns + 3 + 3 * LITE_NSLOT; }
 
-static int pair_ctas(const smplfit_model_t* m) { return (m->gcf_npairs + 8 * LITE_PPW - 1) / (8 * LITE_PPW); }
+// partial Gramians of the pair term: one (the tcgen05 GEMM) or one per CTA of the SIMT fallback k_gram_pairs
+static int pair_ctas(const smplfit_model_t* m) {
+  if (gram_pairs_tc_available(m)) return 1;
+  return (m->gcf_npairs + 8 * LITE_PPW - 1) / (8 * LITE_PPW);
+}
 int gram_closed_blocks(const smplfit_model_t* m) { return pair_ctas(m) + 3; }
+// hi / lo pair features [Bt][Kt] of the tensor-core path
+size_t gram_pairs_scratch_floats(const smplfit_model_t* m, int Bp) {
+  if (!gram_pairs_tc_available(m)) return 0;
+  return (size_t)2 * roundup(Bp, tc_tile_m()) * roundup(9 * m->gcf_npairs, tc_tile_k()) + 64;
+}
 
 // segments per warp that fills whole waves of the SM count best (one CTA per SM)
 static int pick_spw(int n_segments, int warps, int groups) {
@@ -102,7 +112,7 @@ static void lite_launch_t(LiteArgs a, int groups, cudaStream_t st) {
 
 template <int NS>
 static void lite_t(const LiteArgs& a, const smplfit_model_t* m, int groups, const float* RT, float* gcf_part, double* Yd,
-                   cudaStream_t st) {
+                   float* pair_scratch, cudaStream_t st) {
   constexpr int NG = NS * (NS + 1) / 2, NGP = (NG + 3) / 4 * 4;
   GramClosedArgs ga;
   ga.RT = RT; ga.pairs = m->gcf_pairs; ga.A = m->gcf_A; ga.lstart = m->gcf_lstart; ga.lk = m->gcf_lk; ga.Bm = m->gcf_Bm;
@@ -113,7 +123,27 @@ static void lite_t(const LiteArgs& a, const smplfit_model_t* m, int groups, cons
   const size_t smem_t = rows > red ? rows : red;
   if (red > 48 * 1024) cudaFuncSetAttribute(k_gram_pairs<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)red);
   if (smem_t > 48 * 1024) cudaFuncSetAttribute(k_gram_trans<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
-  if (ga.n_pair_ctas > 0) SF_LAUNCH(k_gram_pairs<NS>, dim3(groups, ga.n_pair_ctas), 256, red, st, ga);
+  bool pairs_done = false;
+  if (gram_pairs_tc_available(m) && pair_scratch != nullptr) {
+    // pair term on the tensor cores: features (R_k^T R_l) x constants A^T, 3xTF32 (vposed_tc.cu)
+    const int Kt = roundup(9 * m->gcf_npairs, tc_tile_k()), Bt = roundup(a.Bp, tc_tile_m());
+    PairFeatArgs pf;
+    pf.RT = RT; pf.pairs = m->gcf_pairs; pf.hi = pair_scratch; pf.lo = pair_scratch + (size_t)Bt * Kt;
+    pf.npairs = m->gcf_npairs; pf.J = m->num_joints; pf.RW = 12 + 3 * NS; pf.Bp = a.Bp; pf.Kt = Kt;
+    const size_t smem_f = (size_t)32 * ((m->num_joints * 9) | 1) * sizeof(float);
+    if (smem_f > 48 * 1024) cudaFuncSetAttribute(k_pair_feat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
+    SF_LAUNCH(k_pair_feat, Bt / 32, 256, smem_f, st, pf);
+    pairs_done = tc_gemm_run(m->gcf_AT_hi, m->gcf_AT_lo, NG, roundup(NG, tc_tile_n()), Kt, nullptr, pf.hi, pf.lo, Bt,
+                             gcf_part, a.Bp, st);
+  }
+  if (!pairs_done && ga.n_pair_ctas > 0) {
+    if (gram_pairs_tc_available(m)) {
+      // the workspace holds one pair block on this path: the SIMT kernel cannot take over
+      fprintf(stderr, "smplfit_b200: tcgen05 pair GEMM failed to launch\n");
+    } else {
+      SF_LAUNCH(k_gram_pairs<NS>, dim3(groups, ga.n_pair_ctas), 256, red, st, ga);
+    }
+  }
   SF_LAUNCH(k_gram_trans<NS>, dim3(groups, 3), 256, smem_t, st, ga);
   if (lite_warps(m) == 12) lite_launch_t<NS, 12>(a, groups, st);
   else lite_launch_t<NS, 8>(a, groups, st);
@@ -124,8 +154,8 @@ static void lite_t(const LiteArgs& a, const smplfit_model_t* m, int groups, cons
 }
 
 void launch_shape_lite(const LiteArgs& a, const smplfit_model_t* m, int groups, const float* RT, float* gcf_part,
-                       double* Yd, cudaStream_t st) {
-  SF_NS_SWITCH(m->fit_ns, (lite_t<NS>(a, m, groups, RT, gcf_part, Yd, st)));
+                       double* Yd, float* pair_scratch, cudaStream_t st) {
+  SF_NS_SWITCH(m->fit_ns, (lite_t<NS>(a, m, groups, RT, gcf_part, Yd, pair_scratch, st)));
 }
 
 template <int NS, bool WEIGHTED, int WARPS>

@@ -110,6 +110,7 @@ struct TcMaps {
   CUtensorMap f_hi, f_lo, p_hi, p_lo;
 };
 
+template <bool BIAS>
 __global__ void __launch_bounds__(THREADS, 1)
 k_vposed_tc(const __grid_constant__ TcMaps maps, const float* __restrict__ vt, float* __restrict__ out, int M_rows,
             int Bp, int k_blocks, int tiles_m, int total_tiles) {
@@ -232,7 +233,7 @@ k_vposed_tc(const __grid_constant__ TcMaps maps, const float* __restrict__ vt, f
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int n = n0 + c0 + j;
-          if (n < M_rows && b < Bp) out[(size_t)n * Bp + b] = __uint_as_float(r[j]) + __ldg(vt + n);
+          if (n < M_rows && b < Bp) out[(size_t)n * Bp + b] = BIAS ? __uint_as_float(r[j]) + __ldg(vt + n) : __uint_as_float(r[j]);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -293,6 +294,54 @@ int g_tc_mode = -1;  // -1: read SMPLFIT_B200_GEMM env on first use; 0 = SIMT, 1
 
 }  // namespace
 
+static bool tc_enabled() {
+  if (g_tc_mode < 0) {
+    const char* e = getenv("SMPLFIT_B200_GEMM");
+    g_tc_mode = (e && strcmp(e, "simt") == 0) ? 0 : 1;
+  }
+  return g_tc_mode == 1;
+}
+
+static int sm_count_tc() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+int tc_tile_k() { return TILE_K; }
+int tc_tile_m() { return TILE_M; }
+int tc_tile_n() { return TILE_N; }
+
+// out[n][b] = bias[n] + sum_k (p_hi + p_lo)[n][k] (f_hi + f_lo)[b][k]   (3xTF32, fp32 accumulate in TMEM)
+// p_*: [rows_alloc][Kt] (rows_alloc >= rows), f_*: [Bt][Kt] (Bt = roundup(Bp, 128)), out: [rows][Bp]
+bool tc_gemm_run(const float* p_hi, const float* p_lo, int rows, int rows_alloc, int Kt, const float* bias,
+                 const float* f_hi, const float* f_lo, int Bt, float* out, int Bp, cudaStream_t st) {
+  if (!tc_enabled() || !p_hi || !p_lo || !f_hi || !f_lo || Kt % TILE_K != 0 || Bt % TILE_M != 0) return false;
+  TcMaps maps;
+  if (!make_map(&maps.f_hi, f_hi, Bt, Kt, TILE_M) || !make_map(&maps.f_lo, f_lo, Bt, Kt, TILE_M) ||
+      !make_map(&maps.p_hi, p_hi, rows_alloc, Kt, TILE_N) || !make_map(&maps.p_lo, p_lo, rows_alloc, Kt, TILE_N))
+    return false;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(k_vposed_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_vposed_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    attr_set = true;
+  }
+  const int tiles_m = Bt / TILE_M, tiles_n = (rows + TILE_N - 1) / TILE_N, total = tiles_m * tiles_n;
+  const int sms = sm_count_tc();
+  const int grid = total < sms ? total : sms;
+  if (bias) SF_LAUNCH(k_vposed_tc<true>, grid, THREADS, SMEM_BYTES, st, maps, bias, out, rows, Bp, Kt / TILE_K, tiles_m, total);
+  else SF_LAUNCH(k_vposed_tc<false>, grid, THREADS, SMEM_BYTES, st, maps, bias, out, rows, Bp, Kt / TILE_K, tiles_m, total);
+  return true;
+}
+
 size_t vposed_tc_scratch_bytes(const smplfit_model_t* m, int Bp) {
   const int Kt = roundup(m->num_pose_feats, TILE_K);
   const int Bt = roundup(Bp, TILE_M);
@@ -301,42 +350,22 @@ size_t vposed_tc_scratch_bytes(const smplfit_model_t* m, int Bp) {
 
 bool vposed_tc_run(const smplfit_model_t* m, const float* feat, float* vposedT, int Bp, int Kp, void* scratch,
                    cudaStream_t st) {
-  if (g_tc_mode < 0) {
-    const char* e = getenv("SMPLFIT_B200_GEMM");
-    g_tc_mode = (e && strcmp(e, "simt") == 0) ? 0 : 1;
-  }
-  if (g_tc_mode == 0 || m->posedirs_hi == nullptr || m->posedirs_lo == nullptr || scratch == nullptr) return false;
+  if (!tc_enabled() || m->posedirs_hi == nullptr || m->posedirs_lo == nullptr || scratch == nullptr) return false;
+  if (encode_fn() == nullptr) return false;
   const int Kt = roundup(m->num_pose_feats, TILE_K);
   const int Bt = roundup(Bp, TILE_M);
   const int rows = 3 * m->num_vertices;
   float* hi = reinterpret_cast<float*>(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
   float* lo = hi + (size_t)Bt * Kt;
-  TcMaps maps;
-  if (!make_map(&maps.f_hi, hi, Bt, Kt, TILE_M) || !make_map(&maps.f_lo, lo, Bt, Kt, TILE_M) ||
-      !make_map(&maps.p_hi, m->posedirs_hi, rows, Kt, TILE_N) || !make_map(&maps.p_lo, m->posedirs_lo, rows, Kt, TILE_N))
-    return false;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(k_vposed_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
-      cudaGetLastError();
-      return false;
-    }
-    attr_set = true;
-  }
   const size_t n = (size_t)Bt * Kt;
-  // rows [Bp, Bt) of the split features are never written by k_split_feat's bound: clear via the kernel itself
+  // rows [Bp, Bt) and columns [Kp, Kt) of the split features are written as zeros by the kernel's bound checks
   SF_LAUNCH(k_split_feat, (unsigned)((n + 255) / 256), 256, 0, st, feat, Bp, Kp, Kt, hi, lo);
-  const int tiles_m = Bt / TILE_M, tiles_n = (rows + TILE_N - 1) / TILE_N, total = tiles_m * tiles_n;
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-  }
-  const int grid = total < sms ? total : sms;
-  SF_LAUNCH(k_vposed_tc, grid, THREADS, SMEM_BYTES, st, maps, m->v_template_fit, vposedT, rows, Bp, Kt / TILE_K, tiles_m,
-            total);
-  return true;
+  return tc_gemm_run(m->posedirs_hi, m->posedirs_lo, rows, rows, Kt, m->v_template_fit, hi, lo, Bt, vposedT, Bp, st);
+}
+
+// the closed-form Gramian's pair term as the same GEMM (pass_lite.cu): available when the constants are present
+bool gram_pairs_tc_available(const smplfit_model_t* m) {
+  return tc_enabled() && m->gcf_AT_hi != nullptr && m->gcf_AT_lo != nullptr && m->gcf_npairs > 0 && encode_fn() != nullptr;
 }
 
 }  // namespace sf

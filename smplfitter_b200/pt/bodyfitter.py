@@ -154,6 +154,13 @@ class BodyFitter(nn.Module):
         reg = lambda n, t: self.register_buffer(n, t, persistent=False)  # noqa: E731
         reg('_t_gcf_pairs', i32(np.array(off or [(0, 0)], np.int32).reshape(-1, 2)))
         reg('_t_gcf_A', torch.tensor(np.ascontiguousarray(A)))
+        # the same constants as a GEMM operand: AT[e][p*9 + ab], rows padded to the 256-row tile, K to 32, hi/lo split
+        kt = (9 * max(len(off), 1) + 31) // 32 * 32
+        AT = np.zeros(((ng + 255) // 256 * 256, kt), np.float32)
+        AT[:ng, :9 * A.shape[0]] = A[:, :, :ng].reshape(-1, ng).T
+        at_hi = (AT.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+        reg('_t_gcf_AT_hi', torch.tensor(np.ascontiguousarray(at_hi)))
+        reg('_t_gcf_AT_lo', torch.tensor(np.ascontiguousarray(AT - at_hi)))
         reg('_t_gcf_G0', torch.tensor(G0))
         reg('_t_gcf_lstart', i32(np.array(lstart)))
         reg('_t_gcf_lk', i32(np.array(lk)))
@@ -167,7 +174,8 @@ class BodyFitter(nn.Module):
         if self._gcf_npairs > 0:
             gcf = dict(gcf_npairs=self._gcf_npairs,
                        **{n: getattr(self, '_t_' + n).data_ptr() for n in
-                          ('gcf_pairs', 'gcf_A', 'gcf_G0', 'gcf_lstart', 'gcf_lk', 'gcf_Bm', 'gcf_Wh')})
+                          ('gcf_pairs', 'gcf_A', 'gcf_G0', 'gcf_lstart', 'gcf_lk', 'gcf_Bm', 'gcf_Wh', 'gcf_AT_hi',
+                           'gcf_AT_lo')})
         return self.body_model._struct(dict(
             **gcf,
             fit_ns=self._ns,
@@ -373,48 +381,78 @@ class BodyFitter(nn.Module):
     # ------------------------------------------------------------------------------
     @torch.jit.unused
     def fit_from_host(self, target_vertices: torch.Tensor, target_joints: Optional[torch.Tensor] = None,
-                      chunk_size: int = 1024, pinned_out: bool = True, **fit_kwargs) -> dict[str, torch.Tensor]:
-        """``fit`` for HOST-resident inputs (ideally pinned): the batch is cut into chunks and the
-        host-to-device copy of chunk k+1 (on a side stream) overlaps the fit of chunk k, so the
-        end-to-end time approaches max(PCIe copy, compute) instead of their sum.  Results are
-        returned in (pinned) host tensors with the same keys as ``fit``."""
-        dev = self.body_model.v_template.device
-        _native.require_cuda(self.body_model.v_template, 'the body model')
-        B = target_vertices.shape[0]
-        compute = torch.cuda.current_stream(dev)
-        copy = getattr(self, '_copy_stream', None)
-        if copy is None:
-            copy = self._copy_stream = torch.cuda.Stream(dev)
-        outs: dict = {}
-        bounds = [(lo, min(B, lo + chunk_size)) for lo in range(0, B, chunk_size)]
-        staged = []
+                      chunk_size: int = 512, out: Optional[dict] = None, num_iter: int = 1,
+                      beta_regularizer: float = 1.0, beta_regularizer2: float = 0.0, scale_regularizer: float = 0.0,
+                      kid_regularizer: Optional[float] = None, final_adjust_rots: bool = True,
+                      scale_target: bool = False, scale_fit: bool = False,
+                      requested_keys: Optional[list] = None) -> dict[str, torch.Tensor]:
+        """``fit`` for HOST-resident float32 inputs (CPU tensors, ideally pinned) -> HOST results.
 
-        def stage(lo, hi):
-            with torch.cuda.stream(copy):
-                tv = target_vertices[lo:hi].to(dev, non_blocking=True)
-                tj = target_joints[lo:hi].to(dev, non_blocking=True) if target_joints is not None else None
-                ev = torch.cuda.Event()
-                ev.record(copy)
-            return tv, tj, ev
+        One C-ABI call (``smplfit_fit_host``): the batch is cut into chunks of ``chunk_size`` instances, the
+        host-to-device copy of chunk k+1 (library-owned copy stream) overlaps the fit of chunk k (current
+        stream), and the results are copied back into pinned host tensors, so the end-to-end time approaches
+        max(PCIe copy, compute) instead of their sum.  ``out`` may carry preallocated pinned result tensors
+        (keys of ``fit``'s result) to reuse across calls.  The results are valid after the current stream has
+        been synchronised (this method does that before returning).  Per-instance options (weights, initial
+        guesses) and ``share_beta`` are not available here: use ``fit`` on device tensors."""
+        if requested_keys is None:
+            requested_keys = ['pose_rotvecs']
+        if scale_target and scale_fit:
+            raise ValueError('Only one of estim_scale_target and estim_scale_fit can be True')
+        scale_mode = 1 if scale_target else (2 if scale_fit else 0)
+        bm = self.body_model
+        dev = bm.v_template.device
+        _native.require_cuda(bm.v_template, 'the body model')
+        B, V, J, S = target_vertices.shape[0], bm.num_vertices, bm.num_joints, self.n_betas
 
-        copy.wait_stream(compute)
-        if bounds:
-            staged.append(stage(*bounds[0]))
-        for k, (lo, hi) in enumerate(bounds):
-            tv, tj, ev = staged[k]
-            if k + 1 < len(bounds):
-                staged.append(stage(*bounds[k + 1]))
-            compute.wait_event(ev)
-            tv.record_stream(compute)
-            if tj is not None:
-                tj.record_stream(compute)
-            res = self.fit(tv, tj, **fit_kwargs)
-            for key, val in res.items():
-                if key not in outs:
-                    outs[key] = torch.empty((B, *val.shape[1:]), dtype=val.dtype, pin_memory=pinned_out)
-                outs[key][lo:hi].copy_(val, non_blocking=True)
-            staged[k] = None
-        return outs
+        def host(x, shape, name):
+            if x is None:
+                return None
+            if isinstance(x, np.ndarray):
+                raise TypeError(f"Expected torch.Tensor for '{name}', got numpy.ndarray.")
+            if x.is_cuda:
+                raise ValueError(f"'{name}' must be a CPU tensor here (use fit() for device tensors)")
+            if tuple(x.shape) != tuple(shape):
+                raise ValueError(f"'{name}' must have shape {tuple(shape)}, got {tuple(x.shape)}")
+            return x.to(dtype=torch.float32).contiguous()
+
+        tv = host(target_vertices, (B, V, 3), 'target_vertices')
+        tj = host(target_joints, (B, J, 3), 'target_joints')
+        shapes = dict(shape_betas=(B, S), trans=(B, 3), orientations=(B, J, 3, 3), relative_orientations=(B, J, 3, 3))
+        if 'pose_rotvecs' in requested_keys:
+            shapes['pose_rotvecs'] = (B, 3 * J)
+        if self.enable_kid:
+            shapes['kid_factor'] = (B,)
+        if scale_mode:
+            shapes['scale_corr'] = (B,)
+        res = {}
+        for key, shape in shapes.items():
+            t = None if out is None else out.get(key)
+            if t is None:
+                t = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+            elif tuple(t.shape) != shape or t.dtype != torch.float32 or t.is_cuda or not t.is_contiguous():
+                raise ValueError(f"out['{key}'] must be a contiguous float32 CPU tensor of shape {shape}")
+            res[key] = t
+        if B == 0:
+            return res
+        o = self._opts(num_iter, final_adjust_rots, requested_keys, False, beta_regularizer, beta_regularizer2,
+                       kid_regularizer, scale_mode, scale_regularizer)
+        L = _native.lib()
+        s = self._struct()
+        chunk = max(1, min(int(chunk_size), B))
+        ws_bytes = L.smplfit_fit_host_workspace_bytes(C.byref(s), B, chunk, C.byref(o), int(tj is not None))
+        if ws_bytes == 0:
+            _native.check(-2 if self._ns > 17 else -1)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        hp = lambda k: res[k].data_ptr() if k in res else 0  # noqa: E731
+        with torch.cuda.device(dev):
+            _native.check(L.smplfit_fit_host(
+                C.byref(s), B, chunk, tv.data_ptr(), 0 if tj is None else tj.data_ptr(), C.byref(o),
+                hp('pose_rotvecs'), hp('shape_betas'), hp('trans'), hp('orientations'), hp('relative_orientations'),
+                hp('kid_factor'), hp('scale_corr'), ws.data_ptr(), ws_bytes, _native.stream_ptr(dev),
+            ))
+            torch.cuda.current_stream(dev).synchronize()  # the host tensors are the result: make them valid
+        return res
 
     # ------------------------------------------------------------------------------
     @torch.jit.unused

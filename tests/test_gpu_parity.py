@@ -195,6 +195,39 @@ def test_fit_roundtrip_full_batch():
         assert torch.equal(again[k], fit[k]), k
 
 
+@pytest.mark.parametrize('joints', [True, False])
+def test_fit_from_host_matches_fit(joints):
+    """smplfit_fit_host (chunked H2D / fit overlap, host results) against fit() on the same inputs: the chunks are
+    independent fits, so the results agree to fp32 rounding; ragged last chunk, pageable and pinned inputs."""
+    bm, fitter = get_model('smpl_tiny')
+    g = torch.Generator(device='cuda').manual_seed(11)
+    B = 77
+    pose = torch.randn(B, 72, device='cuda', generator=g) * 0.2
+    betas = torch.randn(B, 10, device='cuda', generator=g) * 0.5
+    trans = torch.randn(B, 3, device='cuda', generator=g)
+    fw = bm(pose, betas, trans)
+    tj = fw['joints'] if joints else None
+    kw = dict(num_iter=2, beta_regularizer=1.0, requested_keys=['pose_rotvecs', 'shape_betas'])
+    ref = fitter.fit(fw['vertices'], tj, **kw)
+    h_tv = fw['vertices'].cpu()
+    h_tj = tj.cpu() if joints else None
+    for chunk, pinned in ((32, False), (16, True), (4096, True)):
+        tv_in = h_tv.pin_memory() if pinned else h_tv
+        tj_in = (h_tj.pin_memory() if pinned else h_tj) if joints else None
+        out = fitter.fit_from_host(tv_in, tj_in, chunk_size=chunk, **kw)
+        assert set(out) == set(ref)
+        for k in ref:
+            assert not out[k].is_cuda
+            assert (out[k] - ref[k].cpu()).abs().max().item() < 1e-5, (k, chunk)
+    # preallocated result buffers are filled in place
+    bufs = {k: torch.empty(v.shape, pin_memory=True) for k, v in ref.items()}
+    out = fitter.fit_from_host(h_tv.pin_memory(), h_tj.pin_memory() if joints else None, chunk_size=40, out=bufs, **kw)
+    assert all(out[k].data_ptr() == bufs[k].data_ptr() for k in ref)
+    assert (bufs['shape_betas'] - ref['shape_betas'].cpu()).abs().max().item() < 1e-5
+    with pytest.raises(ValueError):
+        fitter.fit_from_host(fw['vertices'], tj, **kw)  # device tensors belong to fit()
+
+
 def test_known_pose_vs_oracle():
     mname = 'smpl_tiny'
     bm, fitter = get_model(mname)
