@@ -11,17 +11,19 @@
 // i.e. per vertex a 12-row blend, one 3x3 transpose product, 3 NS FMAs, and a scatter of b_v into
 // the (few) joints the vertex is skinned to.  ~5x fewer FP32 operations than the per-vertex Gramian.
 #pragma once
+#include <cuda.h>
+
 #include "fit_kernels.cuh"
 #include "solve_kernels.cuh"
 
 namespace sf {
 
 constexpr int LITE_NSLOT = 12;  // == N_SLOTS of pt/bodymodel.py
-constexpr int LITE_SUB = 8;     // vertices per staged record sub-block
+constexpr int LITE_VS = 4;      // vertices per staged sub-block
 
 struct LiteArgs {
-  const float* tT;       // [3V][Bp]
-  const float* vposedT;  // [3V][Bp]
+  const float* tT;       // [3V][Bp]   (read through the tensor map)
+  const float* vposedT;  // [3V][Bp]   (read through the tensor map)
   const float* RT12;     // [J*3][Bp] float4: (R[c][0], R[c][1], R[c][2], T0[c])
   const float* rec;      // [V][Rec<NS>::LEN]
   const int32_t* seg_start;
@@ -30,34 +32,54 @@ struct LiteArgs {
   int n_segments, J, Bp, segs_per_warp;
 };
 
+__device__ __forceinline__ void sf_tma_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          (uint32_t)__cvta_generic_to_shared(dst)),
+      "l"(map), "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// Per-warp two-stage shared-memory ring of the three streams a vertex pass consumes: the warp's 32-instance
+// column of the targets and of the posed template (one 2D TMA box {32 instances, 3 LITE_VS rows} each, from the
+// instance-minor [3V][Bp] arrays) and the LITE_VS per-vertex records (one bulk copy), all signalling one mbarrier
+// per stage.  Stage k + 1 is in flight while stage k is consumed: the global-memory latency is taken off the
+// per-vertex critical path (the register-prefetch version stalled on its own rotation moves, profiles/).
+// Stage layout (floats): [t: 3 VS x 32][vp: 3 VS x 32][records: VS x REC], padded to a 128-byte multiple.
 template <int REC>
-struct RecStagerLite {  // RecStager with LITE_SUB vertices per sub-block
-  float* buf;
-  uint64_t* bar;
-  const float* src;
-  int i0, i1;
+struct VertStager {
+  static constexpr int BOX = 3 * LITE_VS * 32;
+  static constexpr int STAGE = (2 * BOX + LITE_VS * REC + 31) / 32 * 32;
+  float* buf;     // [2][STAGE], 128-byte aligned
+  uint64_t* bar;  // [2]
+  const float* rec_src;
+  const CUtensorMap *mt, *mv;
+  int i0, i1, col;
   uint32_t phase;
   __device__ __forceinline__ void issue(int k, int lane) {
-    const int first = i0 + k * LITE_SUB;
-    __syncwarp();
+    const int first = i0 + k * LITE_VS;
+    __syncwarp();  // every lane is done reading the stage that is refilled
     if (first < i1 && lane == 0) {
-      const uint32_t bytes = (uint32_t)min(LITE_SUB, i1 - first) * REC * 4;
-      sf_mbar_expect_tx(bar + (k & 1), bytes);
-      sf_bulk_g2s(buf + (size_t)(k & 1) * LITE_SUB * REC, src + (size_t)first * REC, bytes, bar + (k & 1));
+      float* dst = buf + (size_t)(k & 1) * STAGE;
+      const uint32_t rec_bytes = (uint32_t)min(LITE_VS, i1 - first) * REC * 4;
+      // a TMA box always delivers its full byte count (rows past the tensor are zero-filled)
+      sf_mbar_expect_tx(bar + (k & 1), 2u * BOX * 4u + rec_bytes);
+      sf_tma_2d(dst, mt, bar + (k & 1), col, first * 3);
+      sf_tma_2d(dst + BOX, mv, bar + (k & 1), col, first * 3);
+      sf_bulk_g2s(dst + 2 * BOX, rec_src + (size_t)first * REC, rec_bytes, bar + (k & 1));
     }
   }
   __device__ __forceinline__ void wait(int k) {
     sf_mbar_wait(bar + (k & 1), (phase >> (k & 1)) & 1u);
     phase ^= 1u << (k & 1);
   }
-  __device__ __forceinline__ const float* rec(int i) const {
-    const int d = i - i0;
-    return buf + (size_t)((d / LITE_SUB) & 1) * LITE_SUB * REC + (size_t)(d % LITE_SUB) * REC;
-  }
+  __device__ __forceinline__ const float* stage(int k) const { return buf + (size_t)(k & 1) * STAGE; }
 };
 
+__host__ __device__ inline int lite_stage_floats(int rec_len) { return (2 * 3 * LITE_VS * 32 + LITE_VS * rec_len + 31) / 32 * 32; }
+
 __host__ __device__ inline size_t lite_smem_bytes(int J, int rec_len, int warps) {
-  return ((size_t)J * 3 * 128 + (size_t)warps * (2 * LITE_SUB * rec_len + LITE_NSLOT * 3 * 32)) * sizeof(float) +
+  return ((size_t)J * 3 * 128 + (size_t)warps * (2 * lite_stage_floats(rec_len) + LITE_NSLOT * 3 * 32)) * sizeof(float) +
          (size_t)warps * (16 + 64) + 16;
 }
 
@@ -98,23 +120,29 @@ struct JointCache {
 };
 
 template <int NS, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 1) k_shape_lite(const LiteArgs a) {
-  extern __shared__ __align__(16) float s_lite[];
+__global__ void __launch_bounds__(WARPS * 32, 1)
+k_shape_lite(const LiteArgs a, const __grid_constant__ CUtensorMap map_t, const __grid_constant__ CUtensorMap map_vp) {
+  extern __shared__ __align__(128) float s_lite[];
   constexpr int NSP = Rec<NS>::NSP, H = NSP / 2, REC = Rec<NS>::LEN;
   constexpr int NL = NS + 3 + 3 * LITE_NSLOT;
+  using Stager = VertStager<REC>;
+  constexpr int BOX = Stager::BOX, STAGE = Stager::STAGE;
   const int g = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Bp = a.Bp;
   const int b = g * 32 + lane;
   const float4* sq = reinterpret_cast<const float4*>(s_lite);  // [J*3][32]
   float* wbase = s_lite + (size_t)a.J * 3 * 128;
-  float* yw = wbase + (size_t)WARPS * (2 * LITE_SUB * REC) + (size_t)warp * (LITE_NSLOT * 3 * 32);  // [slot*3+c][32]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(wbase + (size_t)WARPS * (2 * LITE_SUB * REC + LITE_NSLOT * 3 * 32));
+  float* yw = wbase + (size_t)WARPS * (2 * STAGE) + (size_t)warp * (LITE_NSLOT * 3 * 32);  // [slot*3+c][32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wbase + (size_t)WARPS * (2 * STAGE + LITE_NSLOT * 3 * 32));
   unsigned char* lut = reinterpret_cast<unsigned char*>(bars + 2 * WARPS) + warp * 64;  // joint -> slot of the segment
-  RecStagerLite<REC> rs;
-  rs.buf = wbase + (size_t)warp * (2 * LITE_SUB * REC);
+  Stager rs;
+  rs.buf = wbase + (size_t)warp * (2 * STAGE);
   rs.bar = bars + 2 * warp;
-  rs.src = a.rec;
+  rs.rec_src = a.rec;
+  rs.mt = &map_t;
+  rs.mv = &map_vp;
+  rs.col = g * 32;
   rs.phase = 0;
   if (lane == 0) {
     sf_mbar_init(rs.bar, 1);
@@ -138,16 +166,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_shape_lite(const LiteArgs a) 
     const int seg = (blockIdx.x * a.segs_per_warp + q) * WARPS + warp;
     if (seg >= a.n_segments) break;
     const int i0 = a.seg_start[seg], i1 = a.seg_start[seg + 1];
-    const int sj = (lane < LITE_NSLOT) ? __ldg(a.seg_slots + seg * LITE_NSLOT + lane) : -1;
-    const int nslots = __popc(__ballot_sync(0xffffffffu, sj >= 0));
-    __syncwarp();
-    if (sj >= 0) lut[sj] = (unsigned char)lane;
-    for (int e = 0; e < nslots * 3; ++e) yw[e * 32 + lane] = 0.f;
-    __syncwarp();
     rs.i0 = i0;
     rs.i1 = i1;
     rs.issue(0, lane);
     rs.issue(1, lane);
+    const int sj = (lane < LITE_NSLOT) ? __ldg(a.seg_slots + seg * LITE_NSLOT + lane) : -1;
+    const int nslots = __popc(__ballot_sync(0xffffffffu, sj >= 0));
+    if (sj >= 0) lut[sj] = (unsigned char)lane;
+    for (int e = 0; e < nslots * 3; ++e) yw[e * 32 + lane] = 0.f;
+    __syncwarp();
     float2 r2[H];
 #pragma unroll
     for (int e = 0; e < H; ++e) r2[e] = make_float2(0.f, 0.f);
@@ -157,86 +184,65 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_shape_lite(const LiteArgs a) 
     for (int k = 0; k < 4; ++k) Yr[k][0] = Yr[k][1] = Yr[k][2] = 0.f;
     JointCache jc;
     jc.reset();
-    // targets / posed template two vertices ahead in registers
-    float t0[3], p0[3], t1[3], p1[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      t0[c] = SF_IM(a.tT, i0 * 3 + c, Bp, b);
-      p0[c] = SF_IM(a.vposedT, i0 * 3 + c, Bp, b);
-      t1[c] = p1[c] = 0.f;
-    }
-    if (i0 + 1 < i1) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        t1[c] = SF_IM(a.tT, (i0 + 1) * 3 + c, Bp, b);
-        p1[c] = SF_IM(a.vposedT, (i0 + 1) * 3 + c, Bp, b);
-      }
-    }
-    for (int i = i0; i < i1; ++i) {
-      if ((i - i0) % LITE_SUB == 0) {  // entering sub-block k (warp-uniform)
-        const int k = (i - i0) / LITE_SUB;
-        rs.wait(k);
-        if (k >= 1) rs.issue(k + 1, lane);  // the buffer of sub-block k-1 is free now
-      }
-      float t[3], vp[3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        t[c] = t0[c];
-        vp[c] = p0[c];
-        t0[c] = t1[c];
-        p0[c] = p1[c];
-      }
-      if (i + 2 < i1) {
+    const int nsub = (i1 - i0 + LITE_VS - 1) / LITE_VS;
+    for (int k = 0; k < nsub; ++k) {
+      rs.wait(k);
+      if (k >= 1) rs.issue(k + 1, lane);  // the stage of sub-block k-1 is free now
+      const float* st = rs.stage(k);
+      const int nv = min(LITE_VS, i1 - (i0 + k * LITE_VS));
+#pragma unroll 1
+      for (int u = 0; u < nv; ++u) {
+        float t[3], vp[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          t1[c] = SF_IM(a.tT, (i + 2) * 3 + c, Bp, b);
-          p1[c] = SF_IM(a.vposedT, (i + 2) * 3 + c, Bp, b);
+          t[c] = st[(u * 3 + c) * 32 + lane];
+          vp[c] = st[BOX + (u * 3 + c) * 32 + lane];
         }
-      }
-      const float* rec = rs.rec(i);
-      const float4 w4 = *reinterpret_cast<const float4*>(rec);
-      const int4 j4 = *reinterpret_cast<const int4*>(rec + 4);
-      const float wk[4] = {w4.x, w4.y, w4.z, w4.w};
-      const int jk[4] = {j4.x, j4.y, j4.z, j4.w};
+        const float* rec = st + 2 * BOX + u * REC;
+        const float4 w4 = *reinterpret_cast<const float4*>(rec);
+        const int4 j4 = *reinterpret_cast<const int4*>(rec + 4);
+        const float wk[4] = {w4.x, w4.y, w4.z, w4.w};
+        const int jk[4] = {j4.x, j4.y, j4.z, j4.w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (wk[k] != 0.f && jk[k] != jc.j[k]) {  // warp-uniform, rare
-          if (jc.j[k] >= 0) {
-            float* yp = yw + (size_t)(lut[jc.j[k]] * 3) * 32 + lane;
+        for (int kk = 0; kk < 4; ++kk) {
+          if (wk[kk] != 0.f && jk[kk] != jc.j[kk]) {  // warp-uniform, rare
+            if (jc.j[kk] >= 0) {
+              float* yp = yw + (size_t)(lut[jc.j[kk]] * 3) * 32 + lane;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              yp[c * 32] += Yr[k][c];
-              Yr[k][c] = 0.f;
+              for (int c = 0; c < 3; ++c) {
+                yp[c * 32] += Yr[kk][c];
+                Yr[kk][c] = 0.f;
+              }
             }
+            jc.j[kk] = jk[kk];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) jc.q[kk][c] = sq[(size_t)(jk[kk] * 3 + c) * 32 + lane];
           }
-          jc.j[k] = jk[k];
-#pragma unroll
-          for (int c = 0; c < 3; ++c) jc.q[k][c] = sq[(size_t)(jk[k] * 3 + c) * 32 + lane];
         }
-      }
-      float2 B2[6];  // B2[2c] = (Rb[c][0], Rb[c][1]), B2[2c+1] = (Rb[c][2], Tb0[c])
-      jc.blend(wk, B2);
-      float bv[3];
+        float2 B2[6];  // B2[2c] = (Rb[c][0], Rb[c][1]), B2[2c+1] = (Rb[c][2], Tb0[c])
+        jc.blend(wk, B2);
+        float bv[3];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float pos = fmaf(B2[2 * c].x, vp[0], fmaf(B2[2 * c].y, vp[1], fmaf(B2[2 * c + 1].x, vp[2], B2[2 * c + 1].y)));
-        bv[c] = t[c] - pos;
-        Sb[c] += bv[c];
-      }
+        for (int c = 0; c < 3; ++c) {
+          const float pos = fmaf(B2[2 * c].x, vp[0], fmaf(B2[2 * c].y, vp[1], fmaf(B2[2 * c + 1].x, vp[2], B2[2 * c + 1].y)));
+          bv[c] = t[c] - pos;
+          Sb[c] += bv[c];
+        }
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
+        for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) Yr[k][c] = fmaf(wk[k], bv[c], Yr[k][c]);
-      float z[3];
-      z[0] = fmaf(B2[0].x, bv[0], fmaf(B2[2].x, bv[1], B2[4].x * bv[2]));
-      z[1] = fmaf(B2[0].y, bv[0], fmaf(B2[2].y, bv[1], B2[4].y * bv[2]));
-      z[2] = fmaf(B2[1].x, bv[0], fmaf(B2[3].x, bv[1], B2[5].x * bv[2]));
-      const float2* sd2 = reinterpret_cast<const float2*>(rec + 8);  // shapedirs[x][sp] pairs (shared memory)
+          for (int c = 0; c < 3; ++c) Yr[kk][c] = fmaf(wk[kk], bv[c], Yr[kk][c]);
+        float z[3];
+        z[0] = fmaf(B2[0].x, bv[0], fmaf(B2[2].x, bv[1], B2[4].x * bv[2]));
+        z[1] = fmaf(B2[0].y, bv[0], fmaf(B2[2].y, bv[1], B2[4].y * bv[2]));
+        z[2] = fmaf(B2[1].x, bv[0], fmaf(B2[3].x, bv[1], B2[5].x * bv[2]));
+        const float2* sd2 = reinterpret_cast<const float2*>(rec + 8);  // shapedirs[x][sp] pairs (shared memory)
 #pragma unroll
-      for (int x = 0; x < 3; ++x) {
-        const float2 zz = make_float2(z[x], z[x]);
+        for (int x = 0; x < 3; ++x) {
+          const float2 zz = make_float2(z[x], z[x]);
 #pragma unroll
-        for (int sp = 0; sp < H; ++sp) r2[sp] = sf_fma2(sd2[x * H + sp], zz, r2[sp]);
+          for (int sp = 0; sp < H; ++sp) r2[sp] = sf_fma2(sd2[x * H + sp], zz, r2[sp]);
+        }
       }
     }
 #pragma unroll
@@ -253,6 +259,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_shape_lite(const LiteArgs a) 
 #pragma unroll
     for (int c = 0; c < 3; ++c) out[(size_t)(NS + c) * Bp] = Sb[c];
     for (int e = 0; e < nslots * 3; ++e) out[(size_t)(NS + 3 + e) * Bp] = yw[e * 32 + lane];
+    __syncwarp();  // lut / yw are rewritten by the next segment
   }
 }
 
@@ -512,23 +519,29 @@ struct StatsLiteArgs {
 };
 
 __host__ __device__ inline size_t stats_lite_smem_bytes(int J, int rec_len, int warps) {
-  return ((size_t)J * 3 * 128 + (size_t)warps * (2 * LITE_SUB * rec_len)) * sizeof(float) + (size_t)warps * 16 + 16;
+  return ((size_t)J * 3 * 128 + (size_t)warps * (2 * lite_stage_floats(rec_len))) * sizeof(float) + (size_t)warps * 16 + 16;
 }
 
 template <int NS, bool WEIGHTED, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 1) k_stats_lite(const StatsLiteArgs a) {
-  extern __shared__ __align__(16) float s_st[];
+__global__ void __launch_bounds__(WARPS * 32, 1)
+k_stats_lite(const StatsLiteArgs a, const __grid_constant__ CUtensorMap map_t, const __grid_constant__ CUtensorMap map_vp) {
+  extern __shared__ __align__(128) float s_st[];
   constexpr int NSP = Rec<NS>::NSP, REC = Rec<NS>::LEN;
+  using Stager = VertStager<REC>;
+  constexpr int BOX = Stager::BOX, STAGE = Stager::STAGE;
   const int g = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Bp = a.Bp;
   const int b = g * 32 + lane;
   const float4* sq = reinterpret_cast<const float4*>(s_st);  // [J*3][32]
   float* wbase = s_st + (size_t)a.J * 3 * 128;
-  RecStagerLite<REC> rs;
-  rs.buf = wbase + (size_t)warp * (2 * LITE_SUB * REC);
-  rs.bar = reinterpret_cast<uint64_t*>(wbase + (size_t)WARPS * (2 * LITE_SUB * REC)) + 2 * warp;
-  rs.src = a.rec;
+  Stager rs;
+  rs.buf = wbase + (size_t)warp * (2 * STAGE);
+  rs.bar = reinterpret_cast<uint64_t*>(wbase + (size_t)WARPS * (2 * STAGE)) + 2 * warp;
+  rs.rec_src = a.rec;
+  rs.mt = &map_t;
+  rs.mv = &map_vp;
+  rs.col = g * 32;
   rs.phase = 0;
   if (lane == 0) {
     sf_mbar_init(rs.bar, 1);
@@ -574,94 +587,77 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_stats_lite(const StatsLiteArg
     for (int c = 0; c < 3; ++c) st[c] = sa[c] = 0.f;
     JointCache jc;
     jc.reset();
-    float t0[3], p0[3], t1[3], p1[3], w0 = 1.f, w1 = 1.f;
+    const int nsub = (i1 - i0 + LITE_VS - 1) / LITE_VS;
+    for (int k = 0; k < nsub; ++k) {
+      const int first = i0 + k * LITE_VS;
+      const int nv = min(LITE_VS, i1 - first);
+      // the (rare) per-vertex weights stay on a plain coalesced load, issued before the stage wait
+      float wnext = WEIGHTED ? SF_IM(a.vwT, first, Bp, b) : 1.f;
+      rs.wait(k);
+      if (k >= 1) rs.issue(k + 1, lane);
+      const float* sg = rs.stage(k);
+#pragma unroll 1
+      for (int u = 0; u < nv; ++u) {
+        {
+          const int i = first + u;
+          float t[3], x[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      t0[c] = SF_IM(a.tT, i0 * 3 + c, Bp, b);
-      p0[c] = SF_IM(a.vposedT, i0 * 3 + c, Bp, b);
-      t1[c] = p1[c] = 0.f;
-    }
-    if (WEIGHTED) w0 = SF_IM(a.vwT, i0, Bp, b);
-    if (i0 + 1 < i1) {
+          for (int c = 0; c < 3; ++c) {
+            t[c] = sg[(u * 3 + c) * 32 + lane];
+            x[c] = sg[BOX + (u * 3 + c) * 32 + lane];
+          }
+          const float wv = wnext;
+          if (WEIGHTED && u + 1 < nv) wnext = SF_IM(a.vwT, i + 1, Bp, b);
+          const float* rec = sg + 2 * BOX + u * REC;
+          const float4 w4 = *reinterpret_cast<const float4*>(rec);
+          const int4 j4 = *reinterpret_cast<const int4*>(rec + 4);
+          const float wk[4] = {w4.x, w4.y, w4.z, w4.w};
+          const int jk[4] = {j4.x, j4.y, j4.z, j4.w};
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        t1[c] = SF_IM(a.tT, (i0 + 1) * 3 + c, Bp, b);
-        p1[c] = SF_IM(a.vposedT, (i0 + 1) * 3 + c, Bp, b);
-      }
-      if (WEIGHTED) w1 = SF_IM(a.vwT, i0 + 1, Bp, b);
-    }
-    for (int i = i0; i < i1; ++i) {
-      if ((i - i0) % LITE_SUB == 0) {
-        const int k = (i - i0) / LITE_SUB;
-        rs.wait(k);
-        if (k >= 1) rs.issue(k + 1, lane);
-      }
-      float t[3], x[3];
+          for (int kk = 0; kk < 4; ++kk) {
+            if (wk[kk] != 0.f && jk[kk] != jc.j[kk]) {  // warp-uniform, rare
+              jc.j[kk] = jk[kk];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        t[c] = t0[c];
-        x[c] = p0[c];
-        t0[c] = t1[c];
-        p0[c] = p1[c];
-      }
-      const float wv = w0;
-      w0 = w1;
-      if (i + 2 < i1) {
+              for (int c = 0; c < 3; ++c) jc.q[kk][c] = sq[(size_t)(jk[kk] * 3 + c) * 32 + lane];
+            }
+          }
+          float vs[3];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          t1[c] = SF_IM(a.tT, (i + 2) * 3 + c, Bp, b);
-          p1[c] = SF_IM(a.vposedT, (i + 2) * 3 + c, Bp, b);
+          for (int c = 0; c < 3; ++c) {
+            float2 y2 = make_float2(x[c], 0.f);
+#pragma unroll
+            for (int s2 = 0; s2 < NSP; s2 += 2) {
+              const float2 sv = *reinterpret_cast<const float2*>(rec + 8 + c * NSP + s2);
+              y2 = sf_fma2(sv, make_float2(beta[s2], (s2 + 1 < NS) ? beta[s2 + 1] : 0.f), y2);
+            }
+            vs[c] = y2.x + y2.y;
+          }
+          float2 B2[6];
+          jc.blend(wk, B2);
+          float ref[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            ref[c] = fmaf(B2[2 * c].x, vs[0], fmaf(B2[2 * c].y, vs[1], fmaf(B2[2 * c + 1].x, vs[2], B2[2 * c + 1].y)));
+          if (a.aT_out != nullptr) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) SF_IM(a.aT_out, i * 3 + c, Bp, b) = ref[c];
+          }
+          if (stat) {
+            float dt[3], wa[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              dt[c] = t[c] - ct[c];
+              wa[c] = WEIGHTED ? wv * (ref[c] - ca[c]) : (ref[c] - ca[c]);
+              st[c] = WEIGHTED ? fmaf(wv, dt[c], st[c]) : st[c] + dt[c];
+              sa[c] += wa[c];
+            }
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+              for (int c = 0; c < 3; ++c) M[r * 3 + c] = fmaf(dt[r], wa[c], M[r * 3 + c]);
+            W += wv;
+          }
         }
-        if (WEIGHTED) w1 = SF_IM(a.vwT, i + 2, Bp, b);
-      }
-      const float* rec = rs.rec(i);
-      const float4 w4 = *reinterpret_cast<const float4*>(rec);
-      const int4 j4 = *reinterpret_cast<const int4*>(rec + 4);
-      const float wk[4] = {w4.x, w4.y, w4.z, w4.w};
-      const int jk[4] = {j4.x, j4.y, j4.z, j4.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (wk[k] != 0.f && jk[k] != jc.j[k]) {  // warp-uniform, rare
-          jc.j[k] = jk[k];
-#pragma unroll
-          for (int c = 0; c < 3; ++c) jc.q[k][c] = sq[(size_t)(jk[k] * 3 + c) * 32 + lane];
-        }
-      }
-      float vs[3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float2 y2 = make_float2(x[c], 0.f);
-#pragma unroll
-        for (int s2 = 0; s2 < NSP; s2 += 2) {
-          const float2 sv = *reinterpret_cast<const float2*>(rec + 8 + c * NSP + s2);
-          y2 = sf_fma2(sv, make_float2(beta[s2], (s2 + 1 < NS) ? beta[s2 + 1] : 0.f), y2);
-        }
-        vs[c] = y2.x + y2.y;
-      }
-      float2 B2[6];
-      jc.blend(wk, B2);
-      float ref[3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c)
-        ref[c] = fmaf(B2[2 * c].x, vs[0], fmaf(B2[2 * c].y, vs[1], fmaf(B2[2 * c + 1].x, vs[2], B2[2 * c + 1].y)));
-      if (a.aT_out != nullptr) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) SF_IM(a.aT_out, i * 3 + c, Bp, b) = ref[c];
-      }
-      if (stat) {
-        float dt[3], wa[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          dt[c] = t[c] - ct[c];
-          wa[c] = WEIGHTED ? wv * (ref[c] - ca[c]) : (ref[c] - ca[c]);
-          st[c] = WEIGHTED ? fmaf(wv, dt[c], st[c]) : st[c] + dt[c];
-          sa[c] += wa[c];
-        }
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-          for (int c = 0; c < 3; ++c) M[r * 3 + c] = fmaf(dt[r], wa[c], M[r * 3 + c]);
-        W += wv;
       }
     }
     if (stat) {

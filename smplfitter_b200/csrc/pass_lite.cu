@@ -57,7 +57,7 @@ static int env_int(const char* name, int dflt) {
 bool lite_available(const smplfit_model_t* m) {
   return m->fit_rec != nullptr && m->skin_k <= 4 && m->seg_slots != nullptr && m->yj_start != nullptr &&
          m->gcf_A != nullptr && m->gcf_lstart != nullptr && m->gcf_G0 != nullptr && m->n_slots == LITE_NSLOT &&
-         m->fit_wS != nullptr && lite_warps(m) != 0;
+         m->fit_wS != nullptr && lite_warps(m) != 0 && tensor_maps_available();
 }
 
 bool lite_enabled(const smplfit_model_t* m) {
@@ -69,7 +69,7 @@ bool lite_enabled(const smplfit_model_t* m) {
 bool stats_lite_enabled(const smplfit_model_t* m) {
   static int v = -1;
   if (v < 0) v = env_int("SMPLFIT_B200_STATS_VARIANT", 1) == 1 ? 1 : 0;
-  return v == 1 && m->fit_rec != nullptr && m->skin_k <= 4 &&
+  return v == 1 && m->fit_rec != nullptr && m->skin_k <= 4 && tensor_maps_available() &&
          stats_lite_smem_bytes(m->num_joints, m->fit_rec_len, 8) <= kSmemMax;
 }
 
@@ -101,13 +101,23 @@ static int pick_spw(int n_segments, int warps, int groups) {
   return best_spw;
 }
 
+// tensor maps of the two instance-minor [3V][Bp] streams: box = {32 instances, 3 LITE_VS rows}
+static bool stream_maps(const float* tT, const float* vposedT, int V, int Bp, CUtensorMap* mt, CUtensorMap* mv) {
+  return make_im_map(mt, tT, (uint64_t)3 * V, (uint64_t)Bp, 3 * LITE_VS) && make_im_map(mv, vposedT, (uint64_t)3 * V, (uint64_t)Bp, 3 * LITE_VS);
+}
+
 template <int NS, int WARPS>
-static void lite_launch_t(LiteArgs a, int groups, cudaStream_t st) {
+static void lite_launch_t(LiteArgs a, int V, int groups, cudaStream_t st) {
+  CUtensorMap mt, mv;
+  if (!stream_maps(a.tT, a.vposedT, V, a.Bp, &mt, &mv)) {
+    fprintf(stderr, "smplfit_b200: cuTensorMapEncodeTiled failed for the vertex streams\n");
+    return;
+  }
   const size_t smem = lite_smem_bytes(a.J, Rec<NS>::LEN, WARPS);
   a.segs_per_warp = pick_spw(a.n_segments, WARPS, groups);
   cudaFuncSetAttribute(k_shape_lite<NS, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid((a.n_segments + WARPS * a.segs_per_warp - 1) / (WARPS * a.segs_per_warp), groups);
-  SF_LAUNCH((k_shape_lite<NS, WARPS>), grid, WARPS * 32, smem, st, a);
+  SF_LAUNCH((k_shape_lite<NS, WARPS>), grid, WARPS * 32, smem, st, a, mt, mv);
 }
 
 template <int NS>
@@ -145,8 +155,8 @@ static void lite_t(const LiteArgs& a, const smplfit_model_t* m, int groups, cons
     }
   }
   SF_LAUNCH(k_gram_trans<NS>, dim3(groups, 3), 256, smem_t, st, ga);
-  if (lite_warps(m) == 12) lite_launch_t<NS, 12>(a, groups, st);
-  else lite_launch_t<NS, 8>(a, groups, st);
+  if (lite_warps(m) == 12) lite_launch_t<NS, 12>(a, m->num_vertices, groups, st);
+  else lite_launch_t<NS, 8>(a, m->num_vertices, groups, st);
   LiteReduceArgs ra;
   ra.partials = a.partials; ra.yj_start = m->yj_start; ra.yj_entry = m->yj_entry; ra.Yd = Yd; ra.NL = lite_rows(NS);
   ra.NS = NS; ra.Bp = a.Bp;
@@ -159,21 +169,26 @@ void launch_shape_lite(const LiteArgs& a, const smplfit_model_t* m, int groups, 
 }
 
 template <int NS, bool WEIGHTED, int WARPS>
-static void stats_lite_launch_t(StatsLiteArgs a, int groups, cudaStream_t st) {
+static void stats_lite_launch_t(StatsLiteArgs a, int V, int groups, cudaStream_t st) {
+  CUtensorMap mt, mv;
+  if (!stream_maps(a.tT, a.vposedT, V, a.Bp, &mt, &mv)) {
+    fprintf(stderr, "smplfit_b200: cuTensorMapEncodeTiled failed for the vertex streams\n");
+    return;
+  }
   const size_t smem = stats_lite_smem_bytes(a.J, Rec<NS>::LEN, WARPS);
   a.segs_per_warp = pick_spw(a.n_segments, WARPS, groups);
   cudaFuncSetAttribute(k_stats_lite<NS, WEIGHTED, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid((a.n_segments + WARPS * a.segs_per_warp - 1) / (WARPS * a.segs_per_warp), groups);
-  SF_LAUNCH((k_stats_lite<NS, WEIGHTED, WARPS>), grid, WARPS * 32, smem, st, a);
+  SF_LAUNCH((k_stats_lite<NS, WEIGHTED, WARPS>), grid, WARPS * 32, smem, st, a, mt, mv);
 }
 
 template <int NS>
 static void stats_lite_t(const StatsLiteArgs& a, const smplfit_model_t* m, int groups, cudaStream_t st) {
   const bool w12 = stats_lite_smem_bytes(m->num_joints, m->fit_rec_len, 12) <= kSmemMax;
   if (a.vwT != nullptr) {
-    if (w12) stats_lite_launch_t<NS, true, 12>(a, groups, st); else stats_lite_launch_t<NS, true, 8>(a, groups, st);
+    if (w12) stats_lite_launch_t<NS, true, 12>(a, m->num_vertices, groups, st); else stats_lite_launch_t<NS, true, 8>(a, m->num_vertices, groups, st);
   } else {
-    if (w12) stats_lite_launch_t<NS, false, 12>(a, groups, st); else stats_lite_launch_t<NS, false, 8>(a, groups, st);
+    if (w12) stats_lite_launch_t<NS, false, 12>(a, m->num_vertices, groups, st); else stats_lite_launch_t<NS, false, 8>(a, m->num_vertices, groups, st);
   }
 }
 

@@ -363,6 +363,21 @@ bool vposed_tc_run(const smplfit_model_t* m, const float* feat, float* vposedT, 
   return tc_gemm_run(m->posedirs_hi, m->posedirs_lo, rows, rows, Kt, m->v_template_fit, hi, lo, Bt, vposedT, Bp, st);
 }
 
+bool tensor_maps_available() { return encode_fn() != nullptr; }
+
+// [rows][Bp] instance-minor array, box = {32 instances, box_rows rows}, no swizzle (the vertex streams of pass_lite.cu)
+bool make_im_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t Bp, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {Bp, rows};
+  cuuint64_t strides[1] = {Bp * sizeof(float)};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t elem[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, elem,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // the closed-form Gramian's pair term as the same GEMM (pass_lite.cu): available when the constants are present
 bool gram_pairs_tc_available(const smplfit_model_t* m) {
   return tc_enabled() && m->gcf_AT_hi != nullptr && m->gcf_AT_lo != nullptr && m->gcf_npairs > 0 && encode_fn() != nullptr;

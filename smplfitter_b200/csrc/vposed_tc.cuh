@@ -2,6 +2,7 @@
 // vposed_tc.cu.  Returns false when the path is unavailable for the given shapes so the
 // caller falls back to the FP32 SIMT GEMM of fit_kernels.cuh.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "../../include/smplfit_b200.h"
@@ -18,4 +19,6 @@ int tc_tile_k();
 int tc_tile_m();
 int tc_tile_n();
 bool gram_pairs_tc_available(const smplfit_model_t* m);
+bool tensor_maps_available();
+bool make_im_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t Bp, uint32_t box_rows);
 }  // namespace sf
