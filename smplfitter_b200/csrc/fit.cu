@@ -1,7 +1,10 @@
 // C-ABI entry points of BodyFitter.fit / fit_with_known_pose: workspace carving and the
 // launch sequence.  Kernels live in fit_kernels.cuh (vertex passes) and solve_kernels.cuh
 // (per-instance solves).  Reference: /root/reference/src/smplfitter/pt/bodyfitter.py:283-549.
+#include <stdlib.h>
 #include <string.h>
+
+#include <mutex>
 
 #include "common.cuh"
 #include "fit_kernels.cuh"
@@ -25,6 +28,64 @@ struct FitWs {
   void* tc_scratch;
   size_t bytes;
 };
+
+// Side streams for the stages of one fit that do not depend on each other (the closed-form Gramian's pair / translation
+// terms against the pose-blend GEMM + vertex pass).  A small per-device ring; the slot is picked from the caller's
+// stream handle, so concurrent fits on different streams (smplfit_fit_host) usually get different side streams.
+// Sharing a slot is still correct: every fork / join records its event right before the matching wait is enqueued.
+struct SideSlot {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  bool ok = false;
+};
+constexpr int kSideSlots = 4, kSideDevices = 64;
+static SideSlot g_side[kSideDevices][kSideSlots];
+static std::mutex g_side_mutex;
+
+static int side_stream_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("SMPLFIT_B200_SIDE_STREAM");
+    mode = e ? atoi(e) : 0;
+  }
+  return mode;
+}
+
+static SideSlot* side_slot(cudaStream_t st) {
+  if (g_prof_on) return nullptr;  // per-kernel timing wants the stages back to back
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kSideDevices) return nullptr;
+  const int slot = (int)((reinterpret_cast<uintptr_t>(st) >> 4) % kSideSlots);
+  std::lock_guard<std::mutex> lock(g_side_mutex);
+  SideSlot& s = g_side[dev][slot];
+  if (!s.ok) {
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    s.ok = true;
+  }
+  return &s;
+}
+
+// final adjustment: level-parallel kernel unless switched off (SMPLFIT_B200_ADJUST=seq) or a copy part's source is not
+// an ancestor-side joint of lower depth (never the case for the SMPL family, where toes copy their parent foot)
+static void launch_adjust(const AdjustArgs& aa, int groups, cudaStream_t st) {
+  static int par = -1;
+  if (par < 0) {
+    const char* e = getenv("SMPLFIT_B200_ADJUST");
+    par = (e && strcmp(e, "seq") == 0) ? 0 : 1;
+  }
+  const size_t smem = adjust_par_smem_bytes(aa.t.J);
+  if (par && smem <= 200 * 1024) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_adjust_par, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    SF_LAUNCH(k_adjust_par, groups, ADJ_WARPS * 32, smem, st, aa);
+  } else {
+    SF_LAUNCH(k_adjust_solve, groups, 32, 0, st, aa);
+  }
+}
 
 static int moment_blocks(int V) { return (V + 255) / 256; }
 static int shape_nacc(int ns) { return ns * (ns + 1) / 2 + ns + 3 * ns + 3 + 1; }
@@ -134,7 +195,24 @@ static void run_gemm(FitCtx& c) {
 static void run_shape(FitCtx& c, int scale_mode, const float* beta_ref, const float* kid_ref,
                       const smplfit_fit_opts_t* o) {
   const smplfit_model_t* m = c.m;
+  // The closed-form Gramian needs only the joint transforms.  Forked onto a side stream it can overlap the vertex
+  // pass; it must not overlap the persistent tcgen05 GEMM (whose static tile schedule suffers when its CTAs do not all
+  // start together: measured 3.62 -> 3.82 ms per step), so the fork point is after the GEMM.
+  // SMPLFIT_B200_SIDE_STREAM: 0 = off (default), 1 = fork before the GEMM, 2 = fork after the GEMM.
+  const int side_mode = side_stream_mode();
+  SideSlot* side = (c.lite && side_mode != 0) ? side_slot(c.st) : nullptr;
+  auto gram = [&]() {
+    cudaStream_t gs = c.st;
+    if (side && cudaEventRecord(side->fork, c.st) == cudaSuccess && cudaStreamWaitEvent(side->stream, side->fork, 0) == cudaSuccess)
+      gs = side->stream;
+    else
+      side = nullptr;
+    launch_gram_closed(m, c.groups, c.Bp, c.w.RT, c.w.gcfpart, c.w.pairfeat, gs);
+    if (side) cudaEventRecord(side->join, side->stream);
+  };
+  if (c.lite && side_mode != 2) gram();
   run_gemm(c);
+  if (c.lite && side_mode == 2) gram();
   ShapeArgs sa;
   sa.tT = c.w.tT; sa.vwT = c.vwT_shape; sa.vposedT = c.w.vposedT; sa.RT = c.w.RT;
   sa.shapedirs = m->fit_shapedirs; sa.skin_idx = m->skin_idx; sa.skin_w = m->skin_w; sa.order = m->order;
@@ -146,7 +224,8 @@ static void run_shape(FitCtx& c, int scale_mode, const float* beta_ref, const fl
     la.tT = c.w.tT; la.vposedT = c.w.vposedT; la.RT12 = c.w.RT12; la.rec = m->fit_rec; la.seg_start = m->seg_start;
     la.seg_slots = m->seg_slots; la.partials = c.w.gpart; la.n_segments = m->n_segments; la.J = m->num_joints;
     la.Bp = c.Bp; la.segs_per_warp = 1;
-    launch_shape_lite(la, m, c.groups, c.w.RT, c.w.gcfpart, c.w.Yd, c.w.pairfeat, c.st);
+    launch_shape_lite(la, m, c.groups, c.w.Yd, c.st);
+    if (side) cudaStreamWaitEvent(c.st, side->join, 0);
     so.lite = 1; so.lite_nl = lite_rows(m->fit_ns); so.n_gcf = gram_closed_blocks(m); so.gcf_part = c.w.gcfpart;
     so.G0 = m->gcf_G0; so.Yd = c.w.Yd;
   } else {
@@ -373,7 +452,7 @@ extern "C" int smplfit_fit(const smplfit_model_t* m, int64_t batch, const float*
       aa.partials = w.spart; aa.tjT = w.tjT; aa.ajT = aj; aa.refj = w.refj; aa.jwT = w.jwT; aa.R_prev = w.R;
       aa.beta = w.beta; aa.trans = w.trans; aa.R_out = w.R2; aa.t = tables(m); aa.Bp = c.Bp;
       aa.scale = o->scale_mode ? w.scale : nullptr; aa.scale_mode = o->scale_mode;
-      SF_LAUNCH(k_adjust_solve, c.Bp / 32, 32, 0, c.st, aa);
+      launch_adjust(aa, c.Bp / 32, c.st);
       R_final = w.R2;
     }
   }
@@ -387,7 +466,7 @@ extern "C" int smplfit_fit(const smplfit_model_t* m, int64_t batch, const float*
   oa.scale = o->scale_mode ? w.scale : nullptr; oa.scale_corr = o->scale_mode ? out_scale_corr : nullptr;
   oa.scale_mode = o->scale_mode;
   oa.J = J; oa.S = m->num_betas; oa.NS = m->fit_ns; oa.B = c.B; oa.Bp = c.Bp;
-  SF_LAUNCH(k_output, c.Bp / 32, 32, 0, c.st, oa);
+  SF_LAUNCH(k_output, dim3(c.Bp / 32, J), 32, 0, c.st, oa);
   SF_CHECK_LAST();
   return SMPLFIT_OK;
 }
@@ -448,7 +527,7 @@ extern "C" int smplfit_fit_known_pose(const smplfit_model_t* m, int64_t batch, c
   oa.scale = o->scale_mode ? w.scale : nullptr; oa.scale_corr = o->scale_mode ? out_scale_corr : nullptr;
   oa.scale_mode = 0;
   oa.J = J; oa.S = m->num_betas; oa.NS = m->fit_ns; oa.B = c.B; oa.Bp = c.Bp;
-  SF_LAUNCH(k_output, c.Bp / 32, 32, 0, c.st, oa);
+  SF_LAUNCH(k_output, dim3(c.Bp / 32, J), 32, 0, c.st, oa);
   SF_CHECK_LAST();
   return SMPLFIT_OK;
 }
@@ -579,7 +658,7 @@ extern "C" int smplfit_fit_known_shape(const smplfit_model_t* m, int64_t batch, 
       aa.partials = w.spart; aa.tjT = w.tjT; aa.ajT = aj; aa.refj = w.refj; aa.jwT = w.jwT; aa.R_prev = w.R;
       aa.beta = w.beta; aa.trans = w.trans; aa.R_out = w.R2; aa.t = tables(m); aa.Bp = c.Bp;
       aa.scale = w.scale; aa.scale_mode = 3;
-      SF_LAUNCH(k_adjust_solve, c.Bp / 32, 32, 0, c.st, aa);
+      launch_adjust(aa, c.Bp / 32, c.st);
       R_final = w.R2;
     }
   }
@@ -590,7 +669,7 @@ extern "C" int smplfit_fit_known_shape(const smplfit_model_t* m, int64_t batch, 
   oa.rel_orient = (o->want_pose_rotvecs || o->want_rel_orient) ? out_rel_orientations : nullptr; oa.kid = nullptr;
   oa.scale = w.scale; oa.scale_corr = o->scale_mode ? out_scale_corr : nullptr; oa.scale_mode = 0;
   oa.J = J; oa.S = m->num_betas; oa.NS = m->fit_ns; oa.B = c.B; oa.Bp = c.Bp;
-  SF_LAUNCH(k_output, c.Bp / 32, 32, 0, c.st, oa);
+  SF_LAUNCH(k_output, dim3(c.Bp / 32, J), 32, 0, c.st, oa);
   SF_CHECK_LAST();
   return SMPLFIT_OK;
 }

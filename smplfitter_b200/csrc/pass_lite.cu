@@ -121,9 +121,10 @@ static void lite_launch_t(LiteArgs a, int V, int groups, cudaStream_t st) {
 }
 
 template <int NS>
-static void lite_t(const LiteArgs& a, const smplfit_model_t* m, int groups, const float* RT, float* gcf_part, double* Yd,
-                   float* pair_scratch, cudaStream_t st) {
+static void gram_closed_t(const smplfit_model_t* m, int groups, int Bp, const float* RT, float* gcf_part,
+                          float* pair_scratch, cudaStream_t st) {
   constexpr int NG = NS * (NS + 1) / 2, NGP = (NG + 3) / 4 * 4;
+  struct { int Bp; } a{Bp};
   GramClosedArgs ga;
   ga.RT = RT; ga.pairs = m->gcf_pairs; ga.A = m->gcf_A; ga.lstart = m->gcf_lstart; ga.lk = m->gcf_lk; ga.Bm = m->gcf_Bm;
   ga.Wh = m->gcf_Wh; ga.out = gcf_part; ga.npairs = m->gcf_npairs; ga.J = m->num_joints; ga.Bp = a.Bp;
@@ -155,6 +156,10 @@ static void lite_t(const LiteArgs& a, const smplfit_model_t* m, int groups, cons
     }
   }
   SF_LAUNCH(k_gram_trans<NS>, dim3(groups, 3), 256, smem_t, st, ga);
+}
+
+template <int NS>
+static void lite_t(const LiteArgs& a, const smplfit_model_t* m, int groups, double* Yd, cudaStream_t st) {
   if (lite_warps(m) == 12) lite_launch_t<NS, 12>(a, m->num_vertices, groups, st);
   else lite_launch_t<NS, 8>(a, m->num_vertices, groups, st);
   LiteReduceArgs ra;
@@ -163,9 +168,13 @@ static void lite_t(const LiteArgs& a, const smplfit_model_t* m, int groups, cons
   SF_LAUNCH(k_lite_reduce, dim3(groups, m->num_joints), 32, 0, st, ra);
 }
 
-void launch_shape_lite(const LiteArgs& a, const smplfit_model_t* m, int groups, const float* RT, float* gcf_part,
-                       double* Yd, float* pair_scratch, cudaStream_t st) {
-  SF_NS_SWITCH(m->fit_ns, (lite_t<NS>(a, m, groups, RT, gcf_part, Yd, pair_scratch, st)));
+void launch_shape_lite(const LiteArgs& a, const smplfit_model_t* m, int groups, double* Yd, cudaStream_t st) {
+  SF_NS_SWITCH(m->fit_ns, (lite_t<NS>(a, m, groups, Yd, st)));
+}
+
+void launch_gram_closed(const smplfit_model_t* m, int groups, int Bp, const float* RT, float* gcf_part, float* pair_scratch,
+                        cudaStream_t st) {
+  SF_NS_SWITCH(m->fit_ns, (gram_closed_t<NS>(m, groups, Bp, RT, gcf_part, pair_scratch, st)));
 }
 
 template <int NS, bool WEIGHTED, int WARPS>

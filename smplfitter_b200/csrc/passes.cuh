@@ -31,8 +31,11 @@ bool lite_enabled(const smplfit_model_t* m);
 int lite_rows(int ns);                          // rows per segment of the lite partials
 int gram_closed_blocks(const smplfit_model_t* m);
 size_t gram_pairs_scratch_floats(const smplfit_model_t* m, int Bp);  // pair features of the tensor-core pair term
-void launch_shape_lite(const LiteArgs& a, const smplfit_model_t* m, int groups, const float* RT, float* gcf_part,
-                       double* Yd, float* pair_scratch, cudaStream_t st);
+// the vertex pass (r, Sb, Y) + its per-joint reduction, and -- independent of it -- the Gramian from the joint
+// transforms (pair term on tcgen05 + translation terms); fit.cu runs the latter on a side stream
+void launch_shape_lite(const LiteArgs& a, const smplfit_model_t* m, int groups, double* Yd, cudaStream_t st);
+void launch_gram_closed(const smplfit_model_t* m, int groups, int Bp, const float* RT, float* gcf_part, float* pair_scratch,
+                        cudaStream_t st);
 // statistics pass against the skinned current fit in the same style (SMPLFIT_B200_STATS_VARIANT=0 selects k_stats_rec)
 struct StatsLiteArgs;
 bool stats_lite_enabled(const smplfit_model_t* m);

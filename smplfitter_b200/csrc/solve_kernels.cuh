@@ -713,6 +713,118 @@ static __global__ void __launch_bounds__(32) k_adjust_solve(const AdjustArgs a) 
   }
 }
 
+// k_adjust_par: the same walk, level-synchronous.  One CTA (ADJ_WARPS warps) per 32 instances, lane = instance;
+// joint positions, rest joints and the output orientations live in shared memory; the joints of one tree depth are
+// independent given their parents, so each depth is processed in parallel (warp per joint) between two CTA barriers.
+// The dependent chain shrinks from J joints / all adjustable parts to the tree depth / adjustable parts per branch.
+constexpr int ADJ_WARPS = 8;
+__host__ __device__ inline size_t adjust_par_smem_bytes(int J) { return (size_t)J * 15 * 32 * sizeof(float) + (size_t)(J + 1) * sizeof(int); }
+
+static __global__ void __launch_bounds__(ADJ_WARPS * 32) k_adjust_par(const AdjustArgs a) {
+  extern __shared__ __align__(16) float s_adj[];
+  const int J = a.t.J, NS = a.t.NS, Bp = a.Bp;
+  const int TW = 3 * (1 + NS);
+  float* pos = s_adj;             // [J*3][32]
+  float* rest = pos + J * 96;     // [J*3][32]
+  float* Ro = rest + J * 96;      // [J*9][32]
+  int* depth = reinterpret_cast<int*>(Ro + J * 288);  // [J], then max depth
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x * 32 + lane;
+  if (threadIdx.x < J) {
+    int d = 0;
+    for (int p = threadIdx.x; p > 0; p = a.t.parents[p]) ++d;
+    depth[threadIdx.x] = d;
+  }
+  float x[SMPLFIT_MAX_UNKNOWNS];
+  for (int s = 0; s < NS; ++s) x[s] = SF_IM(a.beta, s, Bp, b);
+  const float sc = (a.scale != nullptr) ? a.scale[b] : 1.f;
+  const float st_t = (a.scale_mode == 1) ? sc : 1.f;  // scale of the target side
+  const float st_a = (a.scale_mode >= 2) ? sc : 1.f;  // scale of the reference side
+  const float tr_a = (a.scale_mode == 3) ? 1.f : (1.f - st_a);  // reference' = st_a * reference + tr_a * trans
+  float trv[3];
+  for (int c = 0; c < 3; ++c) trv[c] = SF_IM(a.trans, c, Bp, b);
+  // phase 0: rest joints (pt/bodyfitter.py:1441-1450) and the orientations that are simply kept
+  for (int i = warp; i < J; i += ADJ_WARPS) {
+    for (int c = 0; c < 3; ++c) {
+      const float* Jt = a.t.Jt_ext + (size_t)i * TW + c * (1 + NS);
+      float v = __ldg(Jt);
+      for (int s = 0; s < NS; ++s) v = fmaf(__ldg(Jt + 1 + s), x[s], v);
+      rest[(i * 3 + c) * 32 + lane] = (a.scale_mode >= 2) ? v * sc : v;
+    }
+    if (a.t.part_kind[i] != 4 && (a.t.part_flags[i] & 2) == 0) {
+#pragma unroll
+      for (int e = 0; e < 9; ++e) Ro[(i * 9 + e) * 32 + lane] = SF_IM(a.R_prev, i * 9 + e, Bp, b);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int md = 0;
+    for (int j = 0; j < J; ++j) md = max(md, depth[j]);
+    depth[J] = md;
+  }
+  __syncthreads();
+  const int max_depth = depth[J];
+  for (int d = 0; d <= max_depth; ++d) {
+    for (int i = warp; i < J; i += ADJ_WARPS) {
+      if (depth[i] != d) continue;
+      float pi[3];
+      if (i == 0) {
+        for (int c = 0; c < 3; ++c) pi[c] = rest[c * 32 + lane] + trv[c];
+      } else {
+        const int par = a.t.parents[i];
+        float Rp[9], bone[3];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) Rp[e] = Ro[(par * 9 + e) * 32 + lane];
+        for (int c = 0; c < 3; ++c) bone[c] = rest[(i * 3 + c) * 32 + lane] - rest[(par * 3 + c) * 32 + lane];
+        float rb[3];
+        mat3_vec(Rp, bone, rb);
+        for (int c = 0; c < 3; ++c) pi[c] = pos[(par * 3 + c) * 32 + lane] + rb[c];
+      }
+      for (int c = 0; c < 3; ++c) pos[(i * 3 + c) * 32 + lane] = pi[c];
+      const int kind = a.t.part_kind[i];
+      if (kind == 4) {  // toes copy the (already adjusted) feet: the source is an ancestor (pt/bodyfitter.py:1414-1416)
+        const int src = a.t.part_copy_src[i];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) Ro[(i * 9 + e) * 32 + lane] = Ro[(src * 9 + e) * 32 + lane];
+      } else if ((a.t.part_flags[i] & 2) != 0) {
+        float ct0[3], ca[3], A[9];
+        load3(a.tjT, i, Bp, b, ct0);
+        load3(a.refj, i, Bp, b, ca);
+        for (int c = 0; c < 3; ++c) {
+          ct0[c] *= st_t;
+          ca[c] = st_a * ca[c] + tr_a * trv[c];
+        }
+        part_covariance(a.partials, a.t.part_seg_begin, i, Bp, b, ct0, ca, pi, ca, A, st_t * st_a, st_t, st_a);
+        const int n = a.t.cas_count[i];
+        const int32_t* cas = a.t.cas_table + i * a.t.max_cas;
+        for (int k = 0; k < n; ++k) {
+          float tj[3], aj[3];
+          load3(a.tjT, cas[k], Bp, b, tj);
+          load3(a.ajT, cas[k], Bp, b, aj);
+          for (int c = 0; c < 3; ++c) {
+            tj[c] *= st_t;
+            aj[c] = st_a * aj[c] + tr_a * trv[c];
+          }
+          const float w = a.jwT ? SF_IM(a.jwT, cas[k], Bp, b) : 1.f;
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) A[r * 3 + c] = fmaf(tj[r] - pi[r], w * (aj[c] - ca[c]), A[r * 3 + c]);
+        }
+        float Rf[9], Rold[9], Rn[9];
+        proj_so3(A, Rf);
+#pragma unroll
+        for (int e = 0; e < 9; ++e) Rold[e] = SF_IM(a.R_prev, i * 9 + e, Bp, b);
+        mat3_mul(Rf, Rold, Rn);
+#pragma unroll
+        for (int e = 0; e < 9; ++e) Ro[(i * 9 + e) * 32 + lane] = Rn[e];
+      }
+    }
+    __syncthreads();
+  }
+  for (int q = threadIdx.x; q < J * 9 * 32; q += ADJ_WARPS * 32) a.R_out[(size_t)(q >> 5) * Bp + blockIdx.x * 32 + (q & 31)] = Ro[q];
+}
+
 // ---------------------------------------------------------------------------------------
 // k_output: caller-facing results in the reference layouts (pt/bodyfitter.py:513-549):
 // trans + target mean, orientations, relative orientations, pose rotation vectors.
@@ -736,50 +848,48 @@ struct OutputArgs {
   int J, S, NS, B, Bp;
 };
 
+// one thread per (instance, joint); the joint-0 thread also writes the per-instance scalars
 static __global__ void __launch_bounds__(32) k_output(const OutputArgs a) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
   if (b >= a.B) return;
   const int J = a.J, Bp = a.Bp;
-  if (a.shape_betas != nullptr)
-    for (int s = 0; s < a.S; ++s) a.shape_betas[(size_t)b * a.S + s] = SF_IM(a.beta, s, Bp, b);
-  if (a.kid != nullptr) a.kid[b] = SF_IM(a.beta, a.S, Bp, b);
-  {
+  if (j == 0) {
+    if (a.shape_betas != nullptr)
+      for (int s = 0; s < a.S; ++s) a.shape_betas[(size_t)b * a.S + s] = SF_IM(a.beta, s, Bp, b);
+    if (a.kid != nullptr) a.kid[b] = SF_IM(a.beta, a.S, Bp, b);
     // pt/bodyfitter.py:513-519: the target mean is added back (scaled in the scale modes)
     const float sc = (a.scale != nullptr) ? a.scale[b] : 1.f;
     const float f = (a.scale_mode == 1) ? sc : (a.scale_mode == 2 ? 1.f / sc : 1.f);
     for (int c = 0; c < 3; ++c) a.out_trans[(size_t)b * 3 + c] = SF_IM(a.trans, c, Bp, b) + SF_IM(a.mean, c, Bp, b) * f;
     if (a.scale_corr != nullptr) a.scale_corr[b] = sc;
   }
-  for (int j = 0; j < J; ++j) {
-    float R[9];
+  if (a.orientations != nullptr) {
 #pragma unroll
-    for (int e = 0; e < 9; ++e) {
-      R[e] = SF_IM(a.R_final, j * 9 + e, Bp, b);
-      if (a.orientations != nullptr) a.orientations[((size_t)b * J + j) * 9 + e] = R[e];
+    for (int e = 0; e < 9; ++e) a.orientations[((size_t)b * J + j) * 9 + e] = SF_IM(a.R_final, j * 9 + e, Bp, b);
+  }
+  if (a.rel_orient != nullptr || a.pose_rotvecs != nullptr) {
+    float Rs[9], rel[9];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) Rs[e] = SF_IM(a.R_rel_src, j * 9 + e, Bp, b);
+    if (j == 0) {
+#pragma unroll
+      for (int e = 0; e < 9; ++e) rel[e] = Rs[e];
+    } else {
+      float Rp[9];
+      const int par = a.parents[j];
+#pragma unroll
+      for (int e = 0; e < 9; ++e) Rp[e] = SF_IM(a.R_rel_src, par * 9 + e, Bp, b);
+      mat3_tmul(Rp, Rs, rel);
     }
-    if (a.rel_orient != nullptr || a.pose_rotvecs != nullptr) {
-      float Rs[9], rel[9];
+    if (a.rel_orient != nullptr) {
 #pragma unroll
-      for (int e = 0; e < 9; ++e) Rs[e] = SF_IM(a.R_rel_src, j * 9 + e, Bp, b);
-      if (j == 0) {
-#pragma unroll
-        for (int e = 0; e < 9; ++e) rel[e] = Rs[e];
-      } else {
-        float Rp[9];
-        const int par = a.parents[j];
-#pragma unroll
-        for (int e = 0; e < 9; ++e) Rp[e] = SF_IM(a.R_rel_src, par * 9 + e, Bp, b);
-        mat3_tmul(Rp, Rs, rel);
-      }
-      if (a.rel_orient != nullptr) {
-#pragma unroll
-        for (int e = 0; e < 9; ++e) a.rel_orient[((size_t)b * J + j) * 9 + e] = rel[e];
-      }
-      if (a.pose_rotvecs != nullptr) {
-        float rv[3];
-        mat2rotvec(rel, rv);
-        for (int c = 0; c < 3; ++c) a.pose_rotvecs[(size_t)b * 3 * J + j * 3 + c] = rv[c];
-      }
+      for (int e = 0; e < 9; ++e) a.rel_orient[((size_t)b * J + j) * 9 + e] = rel[e];
+    }
+    if (a.pose_rotvecs != nullptr) {
+      float rv[3];
+      mat2rotvec(rel, rv);
+      for (int c = 0; c < 3; ++c) a.pose_rotvecs[(size_t)b * 3 * J + j * 3 + c] = rv[c];
     }
   }
 }
