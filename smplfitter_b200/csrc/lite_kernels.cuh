@@ -276,6 +276,7 @@ static __global__ void __launch_bounds__(32) k_lite_reduce(const LiteReduceArgs 
   const int j = blockIdx.y;
   if (b >= a.Bp) return;
   double y[3] = {0.0, 0.0, 0.0};
+#pragma unroll 8
   for (int q = a.yj_start[j]; q < a.yj_start[j + 1]; ++q) {
     const int e = a.yj_entry[q];
     const int seg = e / LITE_NSLOT, slot = e % LITE_NSLOT;
@@ -400,13 +401,18 @@ static __global__ void __launch_bounds__(256) k_pair_feat(const PairFeatArgs a) 
   }
   __syncthreads();
   const int K9 = a.npairs * 9;
+  // blockIdx.y splits the pair range (each CTA re-stages the rotations: a few KB from L2) so that several CTAs
+  // per SM hide the store latency
+  const int per = (a.npairs + gridDim.y - 1) / gridDim.y;
+  const int p_lo = blockIdx.y * per, p_hi = min(a.npairs, p_lo + per);
+  const bool last = blockIdx.y == gridDim.y - 1;
   for (int ii = 0; ii < 4; ++ii) {
     const int i = warp * 4 + ii;
     float* hi = a.hi + (size_t)(g * 32 + i) * a.Kt;
     float* lo = a.lo + (size_t)(g * 32 + i) * a.Kt;
     if (valid) {
       const float* R = s_R + i * stride;
-      for (int p = lane; p < a.npairs; p += 32) {
+      for (int p = p_lo + lane; p < p_hi; p += 32) {
         const int k = __ldg(a.pairs + 2 * p), l = __ldg(a.pairs + 2 * p + 1);
         const float* Rk = R + k * 9;
         const float* Rl = R + l * 9;
@@ -420,9 +426,11 @@ static __global__ void __launch_bounds__(256) k_pair_feat(const PairFeatArgs a) 
             lo[p * 9 + aa * 3 + cc] = x - h;
           }
       }
-      for (int q = K9 + lane; q < a.Kt; q += 32) hi[q] = lo[q] = 0.f;
+      if (last)
+        for (int q = K9 + lane; q < a.Kt; q += 32) hi[q] = lo[q] = 0.f;
     } else {
-      for (int q = lane; q < a.Kt; q += 32) hi[q] = lo[q] = 0.f;
+      const int q_lo = p_lo * 9, q_hi = last ? a.Kt : p_hi * 9;
+      for (int q = q_lo + lane; q < q_hi; q += 32) hi[q] = lo[q] = 0.f;
     }
   }
 }

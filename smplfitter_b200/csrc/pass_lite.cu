@@ -143,7 +143,7 @@ static void gram_closed_t(const smplfit_model_t* m, int groups, int Bp, const fl
     pf.npairs = m->gcf_npairs; pf.J = m->num_joints; pf.RW = 12 + 3 * NS; pf.Bp = a.Bp; pf.Kt = Kt;
     const size_t smem_f = (size_t)32 * ((m->num_joints * 9) | 1) * sizeof(float);
     if (smem_f > 48 * 1024) cudaFuncSetAttribute(k_pair_feat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
-    SF_LAUNCH(k_pair_feat, Bt / 32, 256, smem_f, st, pf);
+    SF_LAUNCH(k_pair_feat, dim3(Bt / 32, 4), 256, smem_f, st, pf);
     pairs_done = tc_gemm_run(m->gcf_AT_hi, m->gcf_AT_lo, NG, roundup(NG, tc_tile_n()), Kt, nullptr, pf.hi, pf.lo, Bt,
                              gcf_part, a.Bp, st);
   }

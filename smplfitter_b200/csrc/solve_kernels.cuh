@@ -51,7 +51,8 @@ __device__ inline void part_covariance(const float* partials, const int32_t* seg
   double acc[16];
 #pragma unroll
   for (int e = 0; e < 16; ++e) acc[e] = 0.0;
-  for (int s = seg_begin[part]; s < seg_begin[part + 1]; ++s) {
+#pragma unroll 4
+  for (int s = seg_begin[part]; s < seg_begin[part + 1]; ++s) {  // unrolled: the loads of 4 segments are in flight together
     const float* p = partials + (size_t)s * 16 * Bp + b;
 #pragma unroll
     for (int e = 0; e < 16; ++e) acc[e] += (double)p[(size_t)e * Bp];
@@ -377,11 +378,14 @@ __global__ void __launch_bounds__(32) k_gram_entries(const SolveArgs a, double* 
   if (a.lite && kind <= 2) {
     if (kind == 0) {
       acc = a.G0[e];
+#pragma unroll 4
       for (int q = 0; q < a.n_gcf; ++q) acc += (double)a.gcf_part[((size_t)q * NG + e) * Bp + b];
     } else {
       const int row = (kind == 1) ? s : NS + c;
+#pragma unroll 8
       for (int q = 0; q < a.n_chunks; ++q) acc += (double)a.partials[((size_t)q * a.lite_nl + row) * Bp + b];
       if (kind == 1) {
+#pragma unroll 4
         for (int k = 0; k < J; ++k)
 #pragma unroll
           for (int cc = 0; cc < 3; ++cc)
@@ -389,10 +393,12 @@ __global__ void __launch_bounds__(32) k_gram_entries(const SolveArgs a, double* 
       }
     }
   } else if (from_partials) {
+#pragma unroll 8
     for (int q = 0; q < a.n_chunks; ++q) acc += (double)a.partials[((size_t)q * NACC + e) * Bp + b];
   } else if (kind == 4) {
     acc = (double)a.V;
   } else {  // SA(c,s) = sum_k (R_k D_k + n_k T_k[:,1:])
+#pragma unroll 4
     for (int k = 0; k < J; ++k) {
       const double nk = a.wsum[k];
       if (nk == 0.0) continue;
@@ -403,6 +409,7 @@ __global__ void __launch_bounds__(32) k_gram_entries(const SolveArgs a, double* 
     }
   }
   if (a.tjT != nullptr) {  // joint block (pt/bodyfitter.py:1050-1058, _gram_block :1598)
+#pragma unroll 4
     for (int j = 0; j < J; ++j) {
       const double w = a.jwT ? (double)SF_IM(a.jwT, j, Bp, b) : 1.0;
       if (kind == 4) { acc += w; continue; }

@@ -62,7 +62,10 @@ def scatter_fit_gather(fit_fn: Callable[..., dict], total: int, target_vertices:
                        has_joints: bool = True, src: int = 0, group=None, device=None, **fit_kwargs) -> Optional[dict]:
     """Shard a batch held by rank ``src`` over the group, run ``fit_fn(verts, joints, **kw)`` on
     each shard (``BodyFitter.fit`` of the rank-local fitter) and gather the result dictionary
-    on ``src``."""
+    on ``src``.  ``share_beta`` couples the instances of the whole batch (one all-reduce of the normal
+    equations per shape solve would be needed) and is rejected here."""
+    if fit_kwargs.get('share_beta'):
+        raise NotImplementedError('share_beta couples all instances: fit it on one rank (BodyFitter.fit)')
     tv = scatter_rows(target_vertices, total, src, group, device, (num_vertices, 3))
     tj = scatter_rows(target_joints, total, src, group, device, (num_joints, 3)) if has_joints else None
     local = fit_fn(tv, tj, **fit_kwargs)
