@@ -119,7 +119,8 @@ typedef struct smplfit_model {
   const float* gcf_AT_hi;       /* (roundup(NG, 256), roundup(9 gcf_npairs, 32)) gcf_A transposed to [e][pair*9 + a*3 + b], zero
                                    padded, tf32-exact high part: the pair term as a tcgen05 GEMM against (R_k^T R_l) features */
   const float* gcf_AT_lo;       /* same shape, gcf_A^T - gcf_AT_hi */
-  const void* reserved_ptr[2];
+  const float* posedirs_model_hi; /* (3V, Kt) posedirs rows in MODEL vertex order, tf32-exact high part (forward LBS) */
+  const float* posedirs_model_lo; /* (3V, Kt) remainder */
 } smplfit_model_t;
 
 /* Options of BodyFitter.fit (pt/bodyfitter.py:283-302). */

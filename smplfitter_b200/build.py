@@ -41,7 +41,11 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = True) -> str:
+def build(force: bool = False, verbose: bool = True, out: str | None = None, extra: list | None = None) -> str:
+    """Default: the in-tree library.  ``out`` / ``extra`` build a variant (extra nvcc flags, e.g. a -D tuning
+    macro) into another file for A/B runs (load it with SMPLFIT_B200_LIB=...)."""
+    if out or extra:
+        return _build_variant(out or LIB, list(extra or []), verbose)
     stamp = LIB + '.stamp'
     digest = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
@@ -71,5 +75,31 @@ def build(force: bool = False, verbose: bool = True) -> str:
     return LIB
 
 
+def _build_variant(out: str, extra: list, verbose: bool) -> str:
+    tag = hashlib.sha256((' '.join(extra) + out).encode()).hexdigest()[:10]
+    objdir = os.path.join(HERE, 'build', 'variant_' + tag)
+    os.makedirs(objdir, exist_ok=True)
+    nvcc = _nvcc()
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src.replace('.cu', '.o'))
+        r = subprocess.run([nvcc, *NVCC_FLAGS, *extra, '-I', INCLUDE, '-c', os.path.join(CSRC, src), '-o', obj],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f'nvcc failed on {src}:\n{r.stdout}\n{r.stderr}')
+        return obj
+
+    with cf.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    r = subprocess.run([nvcc, '-shared', '-o', out, *objs, '-lcuda'], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f'link failed:\n{r.stdout}\n{r.stderr}')
+    if verbose:
+        print(f'built {out} with {extra}')
+    return out
+
+
 if __name__ == '__main__':
-    build(force='--force' in sys.argv)
+    _out = sys.argv[sys.argv.index('--out') + 1] if '--out' in sys.argv else None
+    _extra = sys.argv[sys.argv.index('--extra') + 1].split() if '--extra' in sys.argv else None
+    build(force='--force' in sys.argv, out=_out, extra=_extra)

@@ -8,8 +8,11 @@
 //           (3) k_fwd_skin: lane = instance; adds the shape/kid blend shapes, blends the
 //               <= K skinning transforms per vertex and writes the caller's (B,V,3) layout
 //               through a shared-memory transpose so both sides stay coalesced.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "fit_kernels.cuh"
+#include "lite_kernels.cuh"
 #include "solve_kernels.cuh"
 #include "vposed_tc.cuh"
 
@@ -25,6 +28,7 @@ struct FwdPrepArgs {
   const float* J_shapedirs;     // (J,3,S)
   const float* kid_J_shapedir;  // (J,3)
   float* skin;   // [12J][Bp]
+  float* skin4;  // optional [J*3][Bp] float4 (G[c][0..2], t[c]): the same rows as quads for k_fwd_skin_tma
   float* feat;   // [Bp][Kp]
   float* betaT;  // [S+1][Bp] (betas zero-padded to S, then kid)
   float* out_joints;        // (B,J,3)
@@ -94,6 +98,11 @@ __global__ void __launch_bounds__(32) k_fwd_prep(const FwdPrepArgs a) {
     mat3_vec(G, rest + j * 3, rj);
     for (int e = 0; e < 9; ++e) SF_IM(a.skin, j * 12 + e, Bp, b) = G[e];
     for (int c = 0; c < 3; ++c) SF_IM(a.skin, j * 12 + 9 + c, Bp, b) = (pos[j * 3 + c] - rj[c]) + tr[c];
+    if (a.skin4 != nullptr) {
+      for (int c = 0; c < 3; ++c)
+        reinterpret_cast<float4*>(a.skin4)[(size_t)(j * 3 + c) * Bp + b] =
+            make_float4(G[c * 3], G[c * 3 + 1], G[c * 3 + 2], (pos[j * 3 + c] - rj[c]) + tr[c]);
+    }
     if (live) {
       for (int e = 0; e < 9; ++e) a.out_orientations[((size_t)b * J + j) * 9 + e] = G[e];
       for (int c = 0; c < 3; ++c) a.out_joints[((size_t)b * J + j) * 3 + c] = pos[j * 3 + c] + tr[c];
@@ -292,6 +301,148 @@ __global__ void __launch_bounds__(256, 2) k_fwd_skin_rec(const FwdSkinRecArgs a)
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// k_fwd_skin_tma: the skinning pass with the streams staged by TMA (same scheme as k_stats_lite).  v_posed^T comes
+// from the forward GEMM in MODEL vertex order (posedirs_model_hi / lo), so a warp's block of FWD_BLK consecutive
+// model vertices is FWD_BLK * 3 contiguous rows: per-warp two-stage ring, one 2D tensor-map box {32 instances,
+// 3 LITE_VS rows} + one bulk copy of LITE_VS records per stage on one mbarrier.  Joint rows as float4 quads in shared
+// memory, cached in registers per skinning slot; results go through a padded shared-memory tile so that the
+// caller's (B,V,3) rows are written in 192-byte contiguous pieces.
+// ---------------------------------------------------------------------------------------
+constexpr int FWD_BLK = 16;  // model vertices per output tile
+struct FwdSkinTmaArgs {
+  const float* betaT;    // [S+1][Bp]
+  const float* skin4;    // [J*3][Bp] float4
+  const float* rec;      // [V][rec_len]: w4 | idx4 | (unused) | S[3][SP] | kid[3] pad
+  float* out;            // (B,V,3)
+  int V, J, S, rec_len, B, Bp, nb, use_kid, blocks_per_warp;
+};
+
+__host__ __device__ inline int fwd_stage_floats(int rec_len) { return (3 * LITE_VS * 32 + LITE_VS * rec_len + 31) / 32 * 32; }
+__host__ __device__ inline size_t fwd_tma_smem_bytes(int J, int rec_len, int warps) {
+  return ((size_t)J * 3 * 128 + (size_t)warps * (2 * fwd_stage_floats(rec_len) + 32 * (FWD_BLK * 3 + 1))) * sizeof(float) +
+         (size_t)warps * 16 + 16;
+}
+
+template <int SP, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_fwd_skin_tma(const FwdSkinTmaArgs a, const __grid_constant__ CUtensorMap map_vp) {
+  extern __shared__ __align__(128) float s_fw[];
+  constexpr int BOX = 3 * LITE_VS * 32, TW = FWD_BLK * 3 + 1;
+  const int STAGE = fwd_stage_floats(a.rec_len);
+  const int g = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Bp = a.Bp, b = g * 32 + lane;
+  const float4* sq = reinterpret_cast<const float4*>(s_fw);  // [J*3][32]
+  float* wbase = s_fw + (size_t)a.J * 3 * 128;
+  float* stage_buf = wbase + (size_t)warp * (2 * STAGE);
+  float* tile = wbase + (size_t)WARPS * (2 * STAGE) + (size_t)warp * (32 * TW);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(wbase + (size_t)WARPS * (2 * STAGE + 32 * TW)) + 2 * warp;
+  if (lane == 0) {
+    sf_mbar_init(bar, 1);
+    sf_mbar_init(bar + 1, 1);
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  {
+    const int n = a.J * 3 * 32;
+    const float4* src = reinterpret_cast<const float4*>(a.skin4);
+    for (int q = threadIdx.x; q < n; q += WARPS * 32) {
+      const int r = q >> 5, l = q & 31;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_fw + (size_t)q * 4);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + (size_t)r * Bp + g * 32 + l) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+  }
+  float beta[SP];
+#pragma unroll
+  for (int s = 0; s < SP; ++s) beta[s] = (s < a.nb) ? SF_IM(a.betaT, s, Bp, b) : 0.f;
+  const float kid = a.use_kid ? SF_IM(a.betaT, a.S, Bp, b) : 0.f;
+  const int n_blocks = (a.V + FWD_BLK - 1) / FWD_BLK;
+  uint32_t phase = 0;
+  auto issue = [&](int first, int i1, int k) {
+    __syncwarp();
+    if (first < i1 && lane == 0) {
+      float* dst = stage_buf + (size_t)(k & 1) * STAGE;
+      const uint32_t rec_bytes = (uint32_t)min(LITE_VS, i1 - first) * a.rec_len * 4;
+      sf_mbar_expect_tx(bar + (k & 1), (uint32_t)BOX * 4u + rec_bytes);
+      sf_tma_2d(dst, &map_vp, bar + (k & 1), g * 32, first * 3);
+      sf_bulk_g2s(dst + BOX, a.rec + (size_t)first * a.rec_len, rec_bytes, bar + (k & 1));
+    }
+  };
+  JointCache jc;
+  jc.reset();
+  for (int q = 0; q < a.blocks_per_warp; ++q) {
+    const int blk = (blockIdx.x * a.blocks_per_warp + q) * WARPS + warp;
+    if (blk >= n_blocks) break;
+    const int v0 = blk * FWD_BLK, v1 = min(a.V, v0 + FWD_BLK);
+    const int nsub = (v1 - v0 + LITE_VS - 1) / LITE_VS;
+    issue(v0, v1, 0);
+    issue(v0 + LITE_VS, v1, 1);
+    for (int k = 0; k < nsub; ++k) {
+      sf_mbar_wait(bar + (k & 1), (phase >> (k & 1)) & 1u);
+      phase ^= 1u << (k & 1);
+      if (k >= 1) issue(v0 + (k + 1) * LITE_VS, v1, k + 1);
+      const float* sg = stage_buf + (size_t)(k & 1) * STAGE;
+      const int nv = min(LITE_VS, v1 - (v0 + k * LITE_VS));
+#pragma unroll 1
+      for (int u = 0; u < nv; ++u) {
+        const float* rec = sg + BOX + u * a.rec_len;
+        const float4 w4 = *reinterpret_cast<const float4*>(rec);
+        const int4 j4 = *reinterpret_cast<const int4*>(rec + 4);
+        const float wk[4] = {w4.x, w4.y, w4.z, w4.w};
+        const int jk[4] = {j4.x, j4.y, j4.z, j4.w};
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          if (wk[kk] != 0.f && jk[kk] != jc.j[kk]) {  // warp-uniform
+            jc.j[kk] = jk[kk];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) jc.q[kk][c] = sq[(size_t)(jk[kk] * 3 + c) * 32 + lane];
+          }
+        }
+        float vs[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float2 y2 = make_float2(sg[(u * 3 + c) * 32 + lane], 0.f);
+#pragma unroll
+          for (int s2 = 0; s2 < SP; s2 += 2) {
+            const float2 sv = *reinterpret_cast<const float2*>(rec + 12 + c * SP + s2);
+            y2 = sf_fma2(sv, make_float2(beta[s2], beta[s2 + 1]), y2);
+          }
+          float y = y2.x + y2.y;
+          if (a.use_kid) y = fmaf(rec[12 + 3 * SP + c], kid, y);
+          vs[c] = y;
+        }
+        float2 B2[6];
+        jc.blend(wk, B2);
+        const int col = (k * LITE_VS + u) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          tile[lane * TW + col + c] =
+              fmaf(B2[2 * c].x, vs[0], fmaf(B2[2 * c].y, vs[1], fmaf(B2[2 * c + 1].x, vs[2], B2[2 * c + 1].y)));
+      }
+    }
+    __syncwarp();
+    const int width = (v1 - v0) * 3;
+    float* obase = a.out + (size_t)v0 * 3;
+    if (width == FWD_BLK * 3) {  // full tile: compile-time row length
+#pragma unroll 4
+      for (int idx = lane; idx < 32 * FWD_BLK * 3; idx += 32) {
+        const int r = idx / (FWD_BLK * 3), e = idx - r * (FWD_BLK * 3);
+        const int bb = g * 32 + r;
+        if (bb < a.B) obase[(size_t)bb * a.V * 3 + e] = tile[r * TW + e];
+      }
+    } else {
+      for (int idx = lane; idx < 32 * width; idx += 32) {
+        const int r = idx / width, e = idx - r * width;
+        const int bb = g * 32 + r;
+        if (bb < a.B) obase[(size_t)bb * a.V * 3 + e] = tile[r * TW + e];
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // CSR SpMM of BodyConverter.convert_vertices: out[b][r][:] = sum_k data[k] in[b][indices[k]][:].
 // One thread per (instance, output vertex, coordinate); rows hold ~3 non-zeros (barycentric).
 __global__ void k_csr_apply(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
@@ -309,8 +460,17 @@ __global__ void k_csr_apply(const int32_t* __restrict__ indptr, const int32_t* _
   out[idx] = acc;
 }
 
+static bool fwd_tma_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SMPLFIT_B200_FWD_VARIANT");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
 struct FwdWs {
-  float *vposedT, *feat, *skin, *betaT;
+  float *vposedT, *feat, *skin, *skin4, *betaT;
   void* tc_scratch;
   size_t bytes;
 };
@@ -323,6 +483,7 @@ static FwdWs carve_fwd(void* base, const smplfit_model_t* m, int64_t B) {
   w.vposedT = c.take<float>((size_t)3 * m->num_vertices * Bp);
   w.feat = c.take<float>(Bp * Kp);
   w.skin = c.take<float>((size_t)12 * m->num_joints * Bp);
+  w.skin4 = c.take<float>((size_t)12 * m->num_joints * Bp);
   w.betaT = c.take<float>((size_t)(m->num_betas + 1) * Bp);
   w.tc_scratch = c.take<char>(vposed_tc_scratch_bytes(m, (int)Bp));
   w.bytes = c.off + 256;
@@ -354,11 +515,53 @@ extern "C" int smplfit_forward(const smplfit_model_t* m, int64_t batch, int rot_
   FwdPrepArgs p;
   p.rot = rot; p.betas = betas; p.trans = trans; p.kid = kid; p.parents = m->parents;
   p.J_template = m->J_template; p.J_shapedirs = m->J_shapedirs; p.kid_J_shapedir = m->kid_J_shapedir;
-  p.skin = w.skin; p.feat = w.feat; p.betaT = w.betaT; p.out_joints = out_joints;
+  p.skin = w.skin; p.skin4 = w.skin4; p.feat = w.feat; p.betaT = w.betaT; p.out_joints = out_joints;
   p.out_orientations = out_orientations; p.rot_mode = rot_mode; p.n_betas = betas ? n_betas : 0;
   p.J = m->num_joints; p.S = m->num_betas; p.B = B; p.Bp = Bp; p.Kp = Kp;
   SF_LAUNCH(k_fwd_prep, Bp / 32, 32, 0, st, p);
   if (out_vertices != nullptr) {
+    // fast path: GEMM with the MODEL-order posedirs copy, then the TMA-staged skinning kernel
+    const int SPf = (m->num_betas + 1) / 2 * 2;
+    const bool tma_ok = fwd_tma_enabled() && m->posedirs_model_hi != nullptr && m->posedirs_model_lo != nullptr &&
+                        m->fwd_rec != nullptr && m->skin_k <= 4 && m->num_betas <= 16 && tensor_maps_available();
+    if (tma_ok) {
+      const int warps = fwd_tma_smem_bytes(m->num_joints, m->fwd_rec_len, 12) <= 227 * 1024 ? 12 : 8;
+      CUtensorMap mv;
+      if (fwd_tma_smem_bytes(m->num_joints, m->fwd_rec_len, warps) <= 227 * 1024 &&
+          make_im_map(&mv, w.vposedT, (uint64_t)3 * m->num_vertices, (uint64_t)Bp, 3 * LITE_VS) &&
+          vposed_tc_run_model(m, w.feat, w.vposedT, Bp, Kp, w.tc_scratch, st)) {
+        FwdSkinTmaArgs r;
+        r.betaT = w.betaT; r.skin4 = w.skin4; r.rec = m->fwd_rec; r.out = out_vertices; r.V = m->num_vertices;
+        r.J = m->num_joints; r.S = m->num_betas; r.rec_len = m->fwd_rec_len; r.B = B; r.Bp = Bp;
+        r.nb = betas ? min(n_betas, m->num_betas) : 0; r.use_kid = kid != nullptr; r.blocks_per_warp = 4;
+        const int n_blocks = (r.V + FWD_BLK - 1) / FWD_BLK;
+        const size_t smem = fwd_tma_smem_bytes(r.J, r.rec_len, warps);
+        dim3 grid2((n_blocks + warps * r.blocks_per_warp - 1) / (warps * r.blocks_per_warp), Bp / 32);
+#define SF_FWD_TMA(SPV)                                                                                              \
+  do {                                                                                                               \
+    if (warps == 12) {                                                                                               \
+      cudaFuncSetAttribute(k_fwd_skin_tma<SPV, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+      SF_LAUNCH((k_fwd_skin_tma<SPV, 12>), grid2, 12 * 32, smem, st, r, mv);                                         \
+    } else {                                                                                                         \
+      cudaFuncSetAttribute(k_fwd_skin_tma<SPV, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+      SF_LAUNCH((k_fwd_skin_tma<SPV, 8>), grid2, 8 * 32, smem, st, r, mv);                                           \
+    }                                                                                                                \
+  } while (0)
+        switch (SPf) {
+          case 2: SF_FWD_TMA(2); break;
+          case 4: SF_FWD_TMA(4); break;
+          case 6: SF_FWD_TMA(6); break;
+          case 8: SF_FWD_TMA(8); break;
+          case 10: SF_FWD_TMA(10); break;
+          case 12: SF_FWD_TMA(12); break;
+          case 14: SF_FWD_TMA(14); break;
+          default: SF_FWD_TMA(16); break;
+        }
+#undef SF_FWD_TMA
+        SF_CHECK_LAST();
+        return SMPLFIT_OK;
+      }
+    }
     if (!vposed_tc_run(m, w.feat, w.vposedT, Bp, Kp, w.tc_scratch, st)) {
       dim3 grid((3 * m->num_vertices + 127) / 128, (Bp + 63) / 64);
       SF_LAUNCH(k_vposed_gemm_simt, grid, 256, 0, st, m->posedirs_fit, m->v_template_fit, w.feat,

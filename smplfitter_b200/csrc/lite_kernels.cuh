@@ -20,6 +20,10 @@ namespace sf {
 
 constexpr int LITE_NSLOT = 12;  // == N_SLOTS of pt/bodymodel.py
 constexpr int LITE_VS = 4;      // vertices per staged sub-block
+#ifndef SF_LITE_UNROLL
+#define SF_LITE_UNROLL 1
+#endif
+constexpr int LITE_UNROLL = SF_LITE_UNROLL;  // vertices of a sub-block processed per loop iteration (ILP vs registers)
 
 struct LiteArgs {
   const float* tT;       // [3V][Bp]   (read through the tensor map)
@@ -190,7 +194,7 @@ k_shape_lite(const LiteArgs a, const __grid_constant__ CUtensorMap map_t, const 
       if (k >= 1) rs.issue(k + 1, lane);  // the stage of sub-block k-1 is free now
       const float* st = rs.stage(k);
       const int nv = min(LITE_VS, i1 - (i0 + k * LITE_VS));
-#pragma unroll 1
+#pragma unroll LITE_UNROLL
       for (int u = 0; u < nv; ++u) {
         float t[3], vp[3];
 #pragma unroll
@@ -604,7 +608,7 @@ k_stats_lite(const StatsLiteArgs a, const __grid_constant__ CUtensorMap map_t, c
       rs.wait(k);
       if (k >= 1) rs.issue(k + 1, lane);
       const float* sg = rs.stage(k);
-#pragma unroll 1
+#pragma unroll LITE_UNROLL
       for (int u = 0; u < nv; ++u) {
         {
           const int i = first + u;

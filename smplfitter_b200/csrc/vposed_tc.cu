@@ -348,9 +348,23 @@ size_t vposed_tc_scratch_bytes(const smplfit_model_t* m, int Bp) {
   return (size_t)2 * Bt * Kt * sizeof(float) + 512;
 }
 
+static bool vposed_tc_run_with(const smplfit_model_t* m, const float* p_hi, const float* p_lo, const float* bias,
+                               const float* feat, float* vposedT, int Bp, int Kp, void* scratch, cudaStream_t st);
+
 bool vposed_tc_run(const smplfit_model_t* m, const float* feat, float* vposedT, int Bp, int Kp, void* scratch,
                    cudaStream_t st) {
-  if (!tc_enabled() || m->posedirs_hi == nullptr || m->posedirs_lo == nullptr || scratch == nullptr) return false;
+  return vposed_tc_run_with(m, m->posedirs_hi, m->posedirs_lo, m->v_template_fit, feat, vposedT, Bp, Kp, scratch, st);
+}
+
+// rows in MODEL vertex order (forward LBS): v_posed^T[v*3+c] = v_template[v][c] + posedirs[v][c] . feat
+bool vposed_tc_run_model(const smplfit_model_t* m, const float* feat, float* vposedT, int Bp, int Kp, void* scratch,
+                         cudaStream_t st) {
+  return vposed_tc_run_with(m, m->posedirs_model_hi, m->posedirs_model_lo, m->v_template, feat, vposedT, Bp, Kp, scratch, st);
+}
+
+static bool vposed_tc_run_with(const smplfit_model_t* m, const float* p_hi, const float* p_lo, const float* bias,
+                               const float* feat, float* vposedT, int Bp, int Kp, void* scratch, cudaStream_t st) {
+  if (!tc_enabled() || p_hi == nullptr || p_lo == nullptr || scratch == nullptr) return false;
   if (encode_fn() == nullptr) return false;
   const int Kt = roundup(m->num_pose_feats, TILE_K);
   const int Bt = roundup(Bp, TILE_M);
@@ -360,7 +374,7 @@ bool vposed_tc_run(const smplfit_model_t* m, const float* feat, float* vposedT, 
   const size_t n = (size_t)Bt * Kt;
   // rows [Bp, Bt) and columns [Kp, Kt) of the split features are written as zeros by the kernel's bound checks
   SF_LAUNCH(k_split_feat, (unsigned)((n + 255) / 256), 256, 0, st, feat, Bp, Kp, Kt, hi, lo);
-  return tc_gemm_run(m->posedirs_hi, m->posedirs_lo, rows, rows, Kt, m->v_template_fit, hi, lo, Bt, vposedT, Bp, st);
+  return tc_gemm_run(p_hi, p_lo, rows, rows, Kt, bias, hi, lo, Bt, vposedT, Bp, st);
 }
 
 bool tensor_maps_available() { return encode_fn() != nullptr; }

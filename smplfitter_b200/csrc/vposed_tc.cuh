@@ -11,6 +11,8 @@ namespace sf {
 size_t vposed_tc_scratch_bytes(const smplfit_model_t* m, int Bp);
 bool vposed_tc_run(const smplfit_model_t* m, const float* feat, float* vposedT, int Bp, int Kp, void* scratch,
                    cudaStream_t st);
+bool vposed_tc_run_model(const smplfit_model_t* m, const float* feat, float* vposedT, int Bp, int Kp, void* scratch,
+                         cudaStream_t st);
 // the generic kernel behind it: out[n][b] = bias[n] (nullable) + sum_k p[n][k] f[b][k] with both operands pre-split into
 // tf32-exact hi / lo parts; p_*: [rows_alloc >= rows][Kt], f_*: [Bt][Kt], Kt % tc_tile_k() == 0, Bt % tc_tile_m() == 0
 bool tc_gemm_run(const float* p_hi, const float* p_lo, int rows, int rows_alloc, int Kt, const float* bias,

@@ -152,6 +152,10 @@ class BodyModel(nn.Module):
         pd[:, :P] = posedirs_fit[:, :P]
         pd_hi = (pd.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)  # tf32-exact part
         pd_lo = pd - pd_hi
+        pdm = np.zeros((V * 3, Kt), np.float32)  # the same rows in MODEL order, for the forward pass
+        pdm[:, :P] = self.posedirs.numpy().reshape(V * 3, P)
+        pdm_hi = (pdm.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+        pdm_lo = pdm - pdm_hi
         eye_feat = np.tile(np.eye(3, dtype=np.float32), [J - 1, 1]).reshape(-1)
         v_posed0 = self.v_template.numpy() + np.einsum('vcp,p->vc', self.posedirs.numpy(), eye_feat)
         template_mesh = (v_posed0 * w32.sum(axis=1, keepdims=True)).astype(np.float32)  # pt/bodyfitter.py:49
@@ -169,6 +173,7 @@ class BodyModel(nn.Module):
             'template_joints_regressed': f32(jreg @ template_mesh),
             'J_regressor_fit': f32(jreg[:, order]),
             'posedirs_hi': f32(pd_hi), 'posedirs_lo': f32(pd_lo),
+            'posedirs_model_hi': f32(pdm_hi), 'posedirs_model_lo': f32(pdm_lo),
             'template_mesh_fit': f32(template_mesh[order]),
         }
         # forward records (model order): see csrc/forward.cu k_fwd_skin_rec
@@ -225,7 +230,8 @@ class BodyModel(nn.Module):
         for name in ('parents', 'skin_idx', 'skin_w', 'order', 'inv_order', 'seg_start', 'seg_part',
                      'part_seg_begin', 'part_kind', 'part_copy_src', 'part_flags', 'cas_table', 'cas_count',
                      'posedirs_fit', 'v_template_fit', 'template_mesh', 'template_joints_regressed',
-                     'J_regressor_fit', 'posedirs_hi', 'posedirs_lo', 'template_mesh_fit'):
+                     'J_regressor_fit', 'posedirs_hi', 'posedirs_lo', 'template_mesh_fit', 'posedirs_model_hi',
+                     'posedirs_model_lo'):
             setattr(s, name, getattr(self, '_t_' + name).data_ptr())
         for name, buf in self.named_buffers():
             if not buf.is_contiguous():
