@@ -272,6 +272,14 @@ static void run_stats(FitCtx& c, int ref_mode, const float* ca0T, const float* a
   r.template_fit = m->template_mesh_fit; r.seg_start = s.seg_start; r.seg_part = s.seg_part;
   r.part_flags = s.part_flags; r.n_segments = s.n_segments; r.Bp = c.Bp; r.J = m->num_joints;
   r.all_segments = s.all_segments; r.segs_per_warp = 2;
+  if (ref_mode == 0 && stats_lite_enabled(m) && m->template_mesh_fit != nullptr) {
+    StatsLiteArgs l{};
+    l.tT = c.w.tT; l.vwT = c.w.vwT; l.ct0 = c.w.tjT; l.partials = c.w.spart; l.seg_start = m->seg_start;
+    l.seg_part = m->seg_part; l.part_flags = m->part_flags; l.n_segments = m->n_segments; l.Bp = c.Bp;
+    l.J = m->num_joints;
+    launch_stats_tmpl(l, m, m->template_mesh_fit, m->J_template, c.groups, c.st);
+    return;
+  }
   if (ref_mode == 1 && stats_lite_enabled(m)) {
     StatsLiteArgs l;
     l.tT = c.w.tT; l.vwT = c.w.vwT; l.ct0 = c.w.tjT; l.ca0 = ca0T; l.vposedT = c.w.vposedT; l.beta = c.w.beta;

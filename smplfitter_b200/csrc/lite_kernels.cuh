@@ -686,4 +686,108 @@ k_stats_lite(const StatsLiteArgs a, const __grid_constant__ CUtensorMap map_t, c
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// k_stats_tmpl<WEIGHTED, WARPS>: the statistics pass of the FIRST rotation fit, against the constant template mesh
+// (pt/bodyfitter.py:384-394; REF == 0 of k_stats_rec).  Only the targets stream from HBM: per-warp ring of
+// TMPL_NST stages of TMPL_VS vertices (one 2D TMA box each); the template coordinates of a stage are one coalesced
+// load per lane, broadcast by shuffles.  9 FMAs per vertex: the pass is bandwidth-bound.
+// ---------------------------------------------------------------------------------------
+constexpr int TMPL_VS = 8, TMPL_NST = 3;
+__host__ __device__ inline size_t stats_tmpl_smem_bytes(int warps) {
+  return (size_t)warps * TMPL_NST * (3 * TMPL_VS * 32) * sizeof(float) + (size_t)warps * TMPL_NST * 8 + 16;
+}
+
+template <bool WEIGHTED, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+k_stats_tmpl(const StatsLiteArgs a, const float* __restrict__ template_fit, const float* __restrict__ ca0_const,
+             const __grid_constant__ CUtensorMap map_t) {
+  extern __shared__ __align__(128) float s_tm[];
+  constexpr int BOX = 3 * TMPL_VS * 32;
+  const int g = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Bp = a.Bp;
+  const int b = g * 32 + lane;
+  float* buf = s_tm + (size_t)warp * TMPL_NST * BOX;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_tm + (size_t)WARPS * TMPL_NST * BOX) + TMPL_NST * warp;
+  if (lane == 0)
+    for (int s = 0; s < TMPL_NST; ++s) sf_mbar_init(bar + s, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  uint32_t phase = 0;
+  for (int q = 0; q < a.segs_per_warp; ++q) {
+    const int seg = (blockIdx.x * a.segs_per_warp + q) * WARPS + warp;
+    if (seg >= a.n_segments) break;
+    const int part = a.seg_part[seg];
+    if ((a.part_flags[part] & 1) == 0) continue;
+    const int i0 = a.seg_start[seg], i1 = a.seg_start[seg + 1];
+    const int nsub = (i1 - i0 + TMPL_VS - 1) / TMPL_VS;
+    auto issue = [&](int k) {
+      __syncwarp();
+      if (k < nsub && lane == 0) {
+        const int s = k % TMPL_NST;
+        sf_mbar_expect_tx(bar + s, (uint32_t)BOX * 4u);
+        sf_tma_2d(buf + (size_t)s * BOX, &map_t, bar + s, g * 32, (i0 + k * TMPL_VS) * 3);
+      }
+    };
+    for (int k = 0; k < TMPL_NST - 1; ++k) issue(k);
+    float ct[3], ca[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      ct[c] = SF_IM(a.ct0, part * 3 + c, Bp, b);
+      ca[c] = __ldg(ca0_const + part * 3 + c);
+    }
+    float M[9], st[3], sa[3], W = 0.f;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) M[e] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) st[c] = sa[c] = 0.f;
+    for (int k = 0; k < nsub; ++k) {
+      const int first = i0 + k * TMPL_VS;
+      const int nv = min(TMPL_VS, i1 - first);
+      const float tm = (lane < nv * 3) ? __ldg(template_fit + (size_t)first * 3 + lane) : 0.f;
+      float wv8[TMPL_VS];
+      if (WEIGHTED) {
+#pragma unroll
+        for (int u = 0; u < TMPL_VS; ++u) wv8[u] = (u < nv) ? SF_IM(a.vwT, first + u, Bp, b) : 0.f;
+      }
+      issue(k + TMPL_NST - 1);
+      const int s = k % TMPL_NST;
+      sf_mbar_wait(bar + s, (phase >> s) & 1u);
+      phase ^= 1u << s;
+      const float* sg = buf + (size_t)s * BOX;
+#pragma unroll
+      for (int u = 0; u < TMPL_VS; ++u) {
+        float x[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) x[c] = __shfl_sync(0xffffffffu, tm, u * 3 + c);
+        if (u < nv) {
+          const float wv = WEIGHTED ? wv8[u] : 1.f;
+          float dt[3], wa[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            dt[c] = sg[(u * 3 + c) * 32 + lane] - ct[c];
+            wa[c] = WEIGHTED ? wv * (x[c] - ca[c]) : (x[c] - ca[c]);
+            st[c] = WEIGHTED ? fmaf(wv, dt[c], st[c]) : st[c] + dt[c];
+            sa[c] += wa[c];
+          }
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) M[r * 3 + c] = fmaf(dt[r], wa[c], M[r * 3 + c]);
+          W += wv;
+        }
+      }
+    }
+    float* out = a.partials + (size_t)seg * 16 * Bp + b;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) out[(size_t)e * Bp] = M[e];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      out[(size_t)(9 + c) * Bp] = st[c];
+      out[(size_t)(12 + c) * Bp] = sa[c];
+    }
+    out[(size_t)15 * Bp] = W;
+  }
+}
+
 }  // namespace sf

@@ -205,4 +205,26 @@ void launch_stats_lite(const StatsLiteArgs& a, const smplfit_model_t* m, int gro
   SF_NS_SWITCH(m->fit_ns, (stats_lite_t<NS>(a, m, groups, st)));
 }
 
+// first rotation fit: statistics against the constant template (REF == 0), TMA-staged
+void launch_stats_tmpl(const StatsLiteArgs& a0, const smplfit_model_t* m, const float* template_fit, const float* ca0_const,
+                       int groups, cudaStream_t st) {
+  StatsLiteArgs a = a0;
+  CUtensorMap mt;
+  if (!make_im_map(&mt, a.tT, (uint64_t)3 * m->num_vertices, (uint64_t)a.Bp, 3 * TMPL_VS)) {
+    fprintf(stderr, "smplfit_b200: cuTensorMapEncodeTiled failed for the target stream\n");
+    return;
+  }
+  constexpr int WARPS = 16;
+  const size_t smem = stats_tmpl_smem_bytes(WARPS);
+  a.segs_per_warp = pick_spw(a.n_segments, WARPS, groups);
+  dim3 grid((a.n_segments + WARPS * a.segs_per_warp - 1) / (WARPS * a.segs_per_warp), groups);
+  if (a.vwT != nullptr) {
+    cudaFuncSetAttribute(k_stats_tmpl<true, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    SF_LAUNCH((k_stats_tmpl<true, WARPS>), grid, WARPS * 32, smem, st, a, template_fit, ca0_const, mt);
+  } else {
+    cudaFuncSetAttribute(k_stats_tmpl<false, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    SF_LAUNCH((k_stats_tmpl<false, WARPS>), grid, WARPS * 32, smem, st, a, template_fit, ca0_const, mt);
+  }
+}
+
 }  // namespace sf

@@ -40,6 +40,8 @@ void launch_gram_closed(const smplfit_model_t* m, int groups, int Bp, const floa
 struct StatsLiteArgs;
 bool stats_lite_enabled(const smplfit_model_t* m);
 void launch_stats_lite(const StatsLiteArgs& a, const smplfit_model_t* m, int groups, cudaStream_t st);
+void launch_stats_tmpl(const StatsLiteArgs& a, const smplfit_model_t* m, const float* template_fit, const float* ca0_const,
+                       int groups, cudaStream_t st);
 // scale modes (final solve only): extra vertex pass + (NS+1)-unknown solve (pass_scale.cu)
 int scale_chunks(const smplfit_model_t* m);
 void launch_scale_pass(const ShapeArgs& a, int ns, int mode, int groups, cudaStream_t st);
