@@ -169,6 +169,8 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=BATCH, help='fits per GPU per step (default: BASELINE config)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--resident-only', action='store_true',
+                    help='profiling aid: only the resident timed steps (no e2e / forward / instrumented legs)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
 
@@ -243,6 +245,13 @@ def main():
     launches = _native.launch_count()
     clocks = sampler.stop() if rank == 0 else None
 
+    if args.resident_only:
+        if rank == 0:
+            print(json.dumps({'resident_only': True, 'ms_per_step': ms / args.steps, 'gpu_launches': int(launches),
+                              'note': 'profiling run, not a bench line'}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)

@@ -271,25 +271,33 @@ static __global__ void __launch_bounds__(32) k_front_fk(const RotArgs a) {
   if (b >= a.Bp) return;
   const int Bp = a.Bp, NS = a.t.NS, J = a.t.J;
   const int TW = 3 * (1 + NS), RW = 12 + 3 * NS;
+  // phase 1: the chain P_j = P_parent + R_parent (J_j - J_parent).  No global stores in this loop, so the loads of
+  // the next joints' rotations are issued ahead of the dependent adds (the loop is unrolled).
   float P[SMPLFIT_MAX_JOINTS * 3];
+  {
+    const float* Jt = a.t.Jt_ext;
+    P[0] = __ldg(Jt + s); P[1] = __ldg(Jt + (1 + NS) + s); P[2] = __ldg(Jt + 2 * (1 + NS) + s);
+  }
+#pragma unroll 4
+  for (int j = 1; j < J; ++j) {
+    const int par = a.t.parents[j];
+    const float* Jt = a.t.Jt_ext + (size_t)j * TW;
+    const float* Jp = a.t.Jt_ext + (size_t)par * TW;
+    const float d0 = __ldg(Jt + s) - __ldg(Jp + s), d1 = __ldg(Jt + (1 + NS) + s) - __ldg(Jp + (1 + NS) + s),
+                d2 = __ldg(Jt + 2 * (1 + NS) + s) - __ldg(Jp + 2 * (1 + NS) + s);
+    float Rp[9];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) Rp[e] = SF_IM(a.R_new, par * 9 + e, Bp, b);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) P[j * 3 + c] = P[par * 3 + c] + (Rp[c * 3] * d0 + Rp[c * 3 + 1] * d1 + Rp[c * 3 + 2] * d2);
+  }
+  // phase 2: per-joint outputs (independent of each other)
   for (int j = 0; j < J; ++j) {
     const float* Jt = a.t.Jt_ext + (size_t)j * TW;
     const float j0 = __ldg(Jt + s), j1 = __ldg(Jt + (1 + NS) + s), j2 = __ldg(Jt + 2 * (1 + NS) + s);
     float Rj[9];
 #pragma unroll
     for (int e = 0; e < 9; ++e) Rj[e] = SF_IM(a.R_new, j * 9 + e, Bp, b);
-    if (j == 0) {
-      P[0] = j0; P[1] = j1; P[2] = j2;
-    } else {
-      const int par = a.t.parents[j];
-      const float* Jp = a.t.Jt_ext + (size_t)par * TW;
-      const float d0 = j0 - __ldg(Jp + s), d1 = j1 - __ldg(Jp + (1 + NS) + s), d2 = j2 - __ldg(Jp + 2 * (1 + NS) + s);
-      float Rp[9];
-#pragma unroll
-      for (int e = 0; e < 9; ++e) Rp[e] = SF_IM(a.R_new, par * 9 + e, Bp, b);
-#pragma unroll
-      for (int c = 0; c < 3; ++c) P[j * 3 + c] = P[par * 3 + c] + (Rp[c * 3] * d0 + Rp[c * 3 + 1] * d1 + Rp[c * 3 + 2] * d2);
-    }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float tv = P[j * 3 + c] - (Rj[c * 3] * j0 + Rj[c * 3 + 1] * j1 + Rj[c * 3 + 2] * j2);
