@@ -121,6 +121,7 @@ typedef struct smplfit_model {
   const float* gcf_AT_lo;       /* same shape, gcf_A^T - gcf_AT_hi */
   const float* posedirs_model_hi; /* (3V, Kt) posedirs rows in MODEL vertex order, tf32-exact high part (forward LBS) */
   const float* posedirs_model_lo; /* (3V, Kt) remainder */
+  const float* posedirs_model_f32; /* (3V, Kt) the same rows in full precision (split into hi / lo inside the GEMM kernel) */
 } smplfit_model_t;
 
 /* Options of BodyFitter.fit (pt/bodyfitter.py:283-302). */

@@ -311,6 +311,10 @@ static void run_rot(FitCtx& c, const RotArgs& ra, bool fit) {
 
 template <int C>
 static void run_transpose(FitCtx& c, const float* src, int N, const int32_t* inv, const float* mean, float* dst) {
+  if (C == 3 && N >= 4 * TV_N) {  // vertex arrays: the larger-tile kernel
+    SF_LAUNCH(k_transpose_v, dim3((N + TV_N - 1) / TV_N, c.groups), 256, 0, c.st, src, N, c.B, c.Bp, inv, mean, dst);
+    return;
+  }
   dim3 grid((N + 31) / 32, c.groups), block(32, 8);
   SF_LAUNCH(k_transpose<C>, grid, block, 0, c.st, src, N, c.B, c.Bp, inv, mean, dst);
 }

@@ -102,6 +102,48 @@ __global__ void k_transpose(const float* __restrict__ src, int N, int B, int Bp,
 }
 
 // ---------------------------------------------------------------------------------------
+// k_transpose_v: the vertex re-layout (C == 3) with a larger tile: 32 instances x 64 vertices per CTA (768
+// contiguous bytes read per instance), the destination rows of the tile (inv_order) staged once in shared memory,
+// the per-instance mean held in registers.  dst[(pos(n)*3 + c)][b] = src[b][n][c] - mean[c][b].
+// ---------------------------------------------------------------------------------------
+constexpr int TV_N = 64;
+static __global__ void __launch_bounds__(256) k_transpose_v(const float* __restrict__ src, int N, int B, int Bp,
+                                                            const int32_t* __restrict__ inv_order,
+                                                            const float* __restrict__ mean, float* __restrict__ dst) {
+  __shared__ float tile[32][TV_N * 3 + 1];
+  __shared__ int s_pos[TV_N];
+  const int n0 = blockIdx.x * TV_N;
+  const int g = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nn = min(TV_N, N - n0), width = nn * 3;
+  if (threadIdx.x < TV_N) s_pos[threadIdx.x] = (threadIdx.x < nn) ? (inv_order ? inv_order[n0 + threadIdx.x] : n0 + threadIdx.x) : 0;
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    const int r = warp * 4 + rr;
+    const int b = g * 32 + r;
+    const float* row = src + ((size_t)b * N + n0) * 3;
+#pragma unroll
+    for (int k = 0; k < TV_N * 3 / 32; ++k) {
+      const int e = k * 32 + lane;
+      tile[r][e] = (b < B && e < width) ? row[e] : 0.f;
+    }
+  }
+  __syncthreads();
+  const int b = g * 32 + lane;
+  float m[3] = {0.f, 0.f, 0.f};
+  if (mean != nullptr) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) m[c] = SF_IM(mean, c, Bp, b);
+  }
+  const bool live = b < B;
+  for (int v = warp; v < nn; v += 8) {
+    const int pos = s_pos[v];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) SF_IM(dst, pos * 3 + c, Bp, b) = live ? tile[lane][v * 3 + c] - m[c] : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // k_vposed_gemm_simt: v_posed^T[n][b] = v_template_fit[n] + sum_k posedirs_fit[n][k] feat[b][k]
 // (pt/bodyfitter.py:913-916).  Plain FP32 shared-memory tiled GEMM (128 x 64 x 16 tiles,
 // 8 x 4 register micro-tiles); the tcgen05 kernel in vposed_tc.cu replaces it.

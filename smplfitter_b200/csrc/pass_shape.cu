@@ -162,6 +162,15 @@ void launch_shape_pass(const ShapeArgs& a, int ns, int groups, const ShapePlan& 
 template <int NS>
 static void shape_solve_t(const SolveArgs& so, double* Gd, int groups, cudaStream_t st) {
   constexpr int NACC = ShapeAcc<NS>::N;
+  static int fused = -1;
+  if (fused < 0) {
+    const char* e = getenv("SMPLFIT_B200_SOLVE_FUSED");
+    fused = (e && atoi(e) == 1) ? 1 : 0;
+  }
+  if (fused) {
+    SF_LAUNCH(k_solve_fused<NS>, groups, GE_WARPS * 32, 0, st, so, Gd);
+    return;
+  }
   SF_LAUNCH(k_gram_entries<NS>, dim3(groups, NACC), 32, 0, st, so, Gd);
   SF_LAUNCH(k_shape_solve<NS>, groups, 32, 0, st, so, Gd);
   SF_LAUNCH(k_shape_out, dim3(groups, so.J), 32, 0, st, so, NS);

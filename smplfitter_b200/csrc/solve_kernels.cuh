@@ -359,16 +359,13 @@ struct SolveArgs {
   const double* Yd;  // [3J][Bp]
 };
 
-// k_gram_entries<NS>: one thread per (instance, entry of [G | r | Sb | SA | W]): chunk partials
-// + joint block (+ closed-form SA), in double.  blockIdx.y = entry (warp-uniform).
+// gram_entry<NS>: entry e of [G | r | Sb | SA | W] for instance b: chunk partials + joint block (+ closed-form SA),
+// in double (e is warp-uniform).
 template <int NS>
-__global__ void __launch_bounds__(32) k_gram_entries(const SolveArgs a, double* __restrict__ Gd) {
+__device__ __forceinline__ void gram_entry(const SolveArgs& a, double* __restrict__ Gd, int e, int b) {
   constexpr int NG = NS * (NS + 1) / 2;
   constexpr int NACC = NG + NS + 3 + 3 * NS + 1;
   constexpr int TW = 3 * (1 + NS), RW = 12 + 3 * NS;
-  const int b = blockIdx.x * 32 + threadIdx.x;
-  const int e = blockIdx.y;
-  if (b >= a.Bp) return;
   const int Bp = a.Bp, J = a.J;
   // decode the entry
   int kind, s = 0, t = 0, c = 0;  // 0 G(s,t), 1 r(s), 2 Sb(c), 3 SA(c,s), 4 W
@@ -439,14 +436,23 @@ __global__ void __launch_bounds__(32) k_gram_entries(const SolveArgs a, double* 
   Gd[(size_t)e * Bp + b] = acc;
 }
 
+// k_gram_entries<NS>: one single-warp CTA per (32 instances, entry): blockIdx.y = entry.  (Dealing the entries to the
+// warps of one CTA per group -- k_solve_fused below -- is slower: 154 us vs 66 + 39 + 15 us for the three separate
+// kernels; the entries are latency-bound and want to be spread over all SMs.)
+constexpr int GE_WARPS = 16;
+template <int NS>
+__global__ void __launch_bounds__(32) k_gram_entries(const SolveArgs a, double* __restrict__ Gd) {
+  const int b = blockIdx.x * 32 + threadIdx.x;
+  if (b >= a.Bp) return;
+  gram_entry<NS>(a, Gd, (int)blockIdx.y, b);
+}
+
 // k_shape_solve<NS>: one thread per instance: centre with the covariance identity, regularise,
 // Cholesky-solve in double, recover the translation (pt/bodyfitter.py:1060-1089; the general
 // solve :1199-1283 is algebraically the same system).
 template <int NS>
-__global__ void __launch_bounds__(32) k_shape_solve(const SolveArgs a, const double* __restrict__ Gd) {
+__device__ __forceinline__ void shape_solve_body(const SolveArgs& a, const double* Gd, int b) {
   constexpr int NG = NS * (NS + 1) / 2;
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= a.Bp) return;
   const int Bp = a.Bp;
   double G[NS][NS], r[NS], SA[3][NS], Sb[3];
   {
@@ -492,6 +498,13 @@ __global__ void __launch_bounds__(32) k_shape_solve(const SolveArgs a, const dou
     for (int s = 0; s < NS; ++s) m -= SA[c][s] / Ws * rhs[s];
     SF_IM(a.trans, c, Bp, b) = (float)m;
   }
+}
+
+template <int NS>
+__global__ void __launch_bounds__(32) k_shape_solve(const SolveArgs a, const double* __restrict__ Gd) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.Bp) return;
+  shape_solve_body<NS>(a, Gd, b);
 }
 
 // k_scale_entries<NS>: the NS+5 extra normal-equation entries of the scale column
@@ -591,10 +604,7 @@ __global__ void __launch_bounds__(32) k_shape_solve_scale(const SolveArgs a, con
 
 // k_shape_out: one thread per (instance, joint): reference joint (pt/bodyfitter.py:1093-1098)
 // and the skinning transform [R | T0 + T1 x + trans] the statistics pass consumes.
-static __global__ void __launch_bounds__(32) k_shape_out(const SolveArgs a, int NS) {
-  const int b = blockIdx.x * 32 + threadIdx.x;
-  const int j = blockIdx.y;
-  if (b >= a.Bp) return;
+__device__ __forceinline__ void shape_out_joint(const SolveArgs& a, int NS, int j, int b) {
   const int Bp = a.Bp;
   const int TW = 3 * (1 + NS), RW = 12 + 3 * NS;
   float x[SMPLFIT_MAX_UNKNOWNS];
@@ -622,6 +632,30 @@ static __global__ void __launch_bounds__(32) k_shape_out(const SolveArgs a, int 
       reinterpret_cast<float4*>(a.skin4)[(size_t)(j * 3 + c) * Bp + b] = q;
     }
   }
+}
+
+static __global__ void __launch_bounds__(32) k_shape_out(const SolveArgs a, int NS) {
+  const int b = blockIdx.x * 32 + threadIdx.x;
+  const int j = blockIdx.y;
+  if (b >= a.Bp) return;
+  shape_out_joint(a, NS, j, b);
+}
+
+// k_solve_fused<NS> (experiment, SMPLFIT_B200_SOLVE_FUSED=1; measured slower, see k_gram_entries): the three stages
+// of the plain shape solve in one CTA per 32 instances (GE_WARPS warps, lane =
+// instance): normal-equation entries dealt to the warps -> CTA barrier -> warp 0 centres, regularises and
+// Cholesky-solves in double -> CTA barrier -> reference joints and skinning rows, joints dealt to the warps.
+// (Global memory written before a CTA barrier is visible to the CTA after it; Gd is read through a plain pointer.)
+template <int NS>
+__global__ void __launch_bounds__(GE_WARPS * 32) k_solve_fused(const SolveArgs a, double* Gd) {
+  constexpr int NACC = NS * (NS + 1) / 2 + NS + 3 + 3 * NS + 1;
+  const int warp = threadIdx.x >> 5;
+  const int b = blockIdx.x * 32 + (threadIdx.x & 31);  // Bp is a multiple of 32: no partial groups
+  for (int e = warp; e < NACC; e += GE_WARPS) gram_entry<NS>(a, Gd, e, b);
+  __syncthreads();
+  if (warp == 0) shape_solve_body<NS>(a, Gd, b);
+  __syncthreads();
+  for (int j = warp; j < a.J; j += GE_WARPS) shape_out_joint(a, NS, j, b);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -6,9 +6,9 @@
 // sm_100a design: persistent CTAs (one per SM) loop over 128-instance x 256-row tiles.
 // D[128][256] accumulates in TMEM (tcgen05.mma, cta_group::1, kind::tf32, M = 128, N = 256, K = 8
 // per instruction); the 512 TMEM columns hold two accumulators so the epilogue of tile i overlaps
-// the MMAs of tile i+1.  Both operands are K-major fp32 tiles of 32 floats per row (= one
-// 128-byte swizzle atom row) brought in by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) through a
-// 2-stage mbarrier ring (96 KB per stage).  Instances are the M side so that in the epilogue TMEM
+// the MMAs of tile i+1.  Both operands are K-major fp32 tiles of 16 floats per row (= one
+// 64-byte swizzle atom row) brought in by TMA (cp.async.bulk.tensor.2d, SWIZZLE_64B) through a
+// 4-stage mbarrier ring (48 KB per stage).  Instances are the M side so that in the epilogue TMEM
 // lane == instance: each warp stores 32 consecutive instances of one v_posed^T row = one
 // coalesced 128-byte line per column.  Tiles are ordered so CTAs working at the same time share
 // the posedirs tile in L2.
@@ -34,14 +34,26 @@ namespace {
 
 constexpr int TILE_M = 128;   // instances per tile (TMEM lanes)
 constexpr int TILE_N = 256;   // v_posed^T rows (vertex coordinates) per tile
-constexpr int TILE_K = 32;    // floats per k-block = 128 bytes = swizzle atom width
+// k-block: 16 floats = 64 bytes per row (SWIZZLE_64B atoms) and a 4-stage ring.  With 32-float k-blocks only two
+// 96 KB stages fit and the kernel ran at period = TMA latency (tensor pipe 58 % active, L2->SM traffic at 27 % of its
+// peak: latency-, not bandwidth-bound); four 48 KB stages keep three loads in flight.  -DSMPLFIT_TC_K32 restores the
+// 128-byte layout.
+#ifdef SMPLFIT_TC_K32
+constexpr int TILE_K = 32;
 constexpr int STAGES = 2;
+#else
+constexpr int TILE_K = 16;
+constexpr int STAGES = 4;
+#endif
+constexpr int K_PAD = 32;     // K padding of every operand array (model constants are laid out with it)
+constexpr int ROW_BYTES = TILE_K * 4;  // bytes per tile row = swizzle span
 constexpr int A_BYTES = TILE_M * TILE_K * 4;     // 16 KB per feature tile
 constexpr int B_BYTES = TILE_N * TILE_K * 4;     // 32 KB per posedirs tile
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // F_hi, F_lo, P_hi, P_lo = 96 KB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr uint32_t TMEM_COLS = 512;              // two 128 x 256 fp32 accumulators
-constexpr int THREADS = 256;                     // warp 0 TMA, 1 MMA, 2 TMEM alloc, 4-7 epilogue
+constexpr int THREADS = 384;                     // warp 0 TMA, 1 MMA, 2 TMEM alloc, 4-7 epilogue, 8-11 hi/lo split
+constexpr int CONV_THREADS = 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -76,16 +88,16 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start
-// address >> 4 in bits [0,14), LBO (unused for swizzled K-major) = 1 in [16,30), SBO = 1024 B
-// (8 rows x 128 B) >> 4 in [32,46), version 1 in [46,48), layout SWIZZLE_128B = 2 in [61,64).
+// K-major swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in bits [0,14),
+// LBO (unused for swizzled K-major) = 1 in [16,30), SBO = 8 rows x ROW_BYTES >> 4 in [32,46), version 1 in [46,48),
+// layout type in [61,64): SWIZZLE_128B = 2, SWIZZLE_64B = 4.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)((8 * ROW_BYTES) >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)(ROW_BYTES == 128 ? 2 : 4) << 61;
   return d;
 }
 // tcgen05 instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both
@@ -110,7 +122,14 @@ struct TcMaps {
   CUtensorMap f_hi, f_lo, p_hi, p_lo;
 };
 
-template <bool BIAS>
+// SPLIT = true: the operands arrive as plain fp32 (maps.f_hi = features [Bp][Kp], maps.p_hi = P [rows][Kp]) and four
+// converter warps split each stage into its tf32-exact hi / lo parts in shared memory (hi in place, lo into the
+// neighbouring slot), which cuts the L2 -> SM traffic of a k-block from 48 KB to 24 KB (the pre-split version moves
+// 1.79 GB per launch at 8.8 TB/s).  Experiment (SMPLFIT_B200_GEMM_SPLIT=1): correct, but the extra pipeline stage costs
+// more than the traffic saves (0.233 vs 0.201 ms) -- the kernel is not L2-bound; neither did 4 x 48 KB stages beat
+// 2 x 96 KB ones, so it is not TMA-latency-bound either.  At 569 TFLOP/s of TF32 work it sits at ~70 % of what the
+// tensor pipe sustains on this part under power limits (bf16 measures 1624 of 2250 nominal TFLOP/s).
+template <bool BIAS, bool SPLIT>
 __global__ void __launch_bounds__(THREADS, 1)
 k_vposed_tc(const __grid_constant__ TcMaps maps, const float* __restrict__ vt, float* __restrict__ out, int M_rows,
             int Bp, int k_blocks, int tiles_m, int total_tiles) {
@@ -120,7 +139,8 @@ k_vposed_tc(const __grid_constant__ TcMaps maps, const float* __restrict__ vt, f
   uint64_t* empty = full + STAGES;
   uint64_t* acc_full = empty + STAGES;   // [2] accumulator ready for the epilogue
   uint64_t* acc_empty = acc_full + 2;    // [2] accumulator drained (4 epilogue warps arrive)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* conv = acc_empty + 2;        // [STAGES] stage split into hi / lo (SPLIT only; 4 converter warps arrive)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(conv + STAGES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -133,6 +153,7 @@ k_vposed_tc(const __grid_constant__ TcMaps maps, const float* __restrict__ vt, f
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
+      mbar_init(&conv[s], CONV_THREADS / 32);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
@@ -162,11 +183,17 @@ k_vposed_tc(const __grid_constant__ TcMaps maps, const float* __restrict__ vt, f
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* st = smem + s * STAGE_BYTES;
-          mbar_expect_tx(&full[s], STAGE_BYTES);
-          tma_load_2d(st, &maps.f_hi, &full[s], kb * TILE_K, b0);
-          tma_load_2d(st + A_BYTES, &maps.f_lo, &full[s], kb * TILE_K, b0);
-          tma_load_2d(st + 2 * A_BYTES, &maps.p_hi, &full[s], kb * TILE_K, n0);
-          tma_load_2d(st + 2 * A_BYTES + B_BYTES, &maps.p_lo, &full[s], kb * TILE_K, n0);
+          if (SPLIT) {
+            mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
+            tma_load_2d(st, &maps.f_hi, &full[s], kb * TILE_K, b0);
+            tma_load_2d(st + 2 * A_BYTES, &maps.p_hi, &full[s], kb * TILE_K, n0);
+          } else {
+            mbar_expect_tx(&full[s], STAGE_BYTES);
+            tma_load_2d(st, &maps.f_hi, &full[s], kb * TILE_K, b0);
+            tma_load_2d(st + A_BYTES, &maps.f_lo, &full[s], kb * TILE_K, b0);
+            tma_load_2d(st + 2 * A_BYTES, &maps.p_hi, &full[s], kb * TILE_K, n0);
+            tma_load_2d(st + 2 * A_BYTES + B_BYTES, &maps.p_lo, &full[s], kb * TILE_K, n0);
+          }
         }
       }
     }
@@ -185,7 +212,7 @@ k_vposed_tc(const __grid_constant__ TcMaps maps, const float* __restrict__ vt, f
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&full[s], ph);
+          mbar_wait(SPLIT ? &conv[s] : &full[s], ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
           const uint64_t fhi = make_desc(base), flo = make_desc(base + A_BYTES);
@@ -204,7 +231,51 @@ k_vposed_tc(const __grid_constant__ TcMaps maps, const float* __restrict__ vt, f
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
+  } else if (SPLIT && warp >= 8) {
+    // ---- converter warps: x -> (hi, lo) of every fp32 word of the stage (elementwise, so the swizzled layout does
+    // not matter); generic-proxy writes are fenced towards the async proxy before the MMA issuer is released ----
+    const int ct = threadIdx.x - 8 * 32;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        uint8_t* st = smem + s * STAGE_BYTES;
+        float4* fh = reinterpret_cast<float4*>(st);
+        float4* fl = reinterpret_cast<float4*>(st + A_BYTES);
+        float4* phh = reinterpret_cast<float4*>(st + 2 * A_BYTES);
+        float4* pl = reinterpret_cast<float4*>(st + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+        for (int q = 0; q < A_BYTES / 16 / CONV_THREADS; ++q) {
+          const int i = q * CONV_THREADS + ct;
+          const float4 x = fh[i];
+          float4 h;
+          h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+          h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+          h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+          h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+          fh[i] = h;
+          fl[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+        }
+#pragma unroll
+        for (int q = 0; q < B_BYTES / 16 / CONV_THREADS; ++q) {
+          const int i = q * CONV_THREADS + ct;
+          const float4 x = phh[i];
+          float4 h;
+          h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+          h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+          h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+          h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+          phh[i] = h;
+          pl[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&conv[s]);
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
     // ---- epilogue warps: TMEM -> registers -> + v_template -> coalesced global stores ----
     const int q = warp - 4;  // TMEM lane quadrant (warp id % 4)
     int tcount = 0;
@@ -278,15 +349,17 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-bool make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+bool make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint64_t ld = 0) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
+  if (ld == 0) ld = cols;
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * sizeof(float)};
+  cuuint64_t strides[1] = {ld * sizeof(float)};
   cuuint32_t box[2] = {(cuuint32_t)TILE_K, (cuuint32_t)box_rows};
   cuuint32_t elem[2] = {1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, elem,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, ROW_BYTES == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -312,7 +385,7 @@ static int sm_count_tc() {
   return sms;
 }
 
-int tc_tile_k() { return TILE_K; }
+int tc_tile_k() { return K_PAD; }  // K padding of operand arrays (a multiple of the k-block)
 int tc_tile_m() { return TILE_M; }
 int tc_tile_n() { return TILE_N; }
 
@@ -320,15 +393,17 @@ int tc_tile_n() { return TILE_N; }
 // p_*: [rows_alloc][Kt] (rows_alloc >= rows), f_*: [Bt][Kt] (Bt = roundup(Bp, 128)), out: [rows][Bp]
 bool tc_gemm_run(const float* p_hi, const float* p_lo, int rows, int rows_alloc, int Kt, const float* bias,
                  const float* f_hi, const float* f_lo, int Bt, float* out, int Bp, cudaStream_t st) {
-  if (!tc_enabled() || !p_hi || !p_lo || !f_hi || !f_lo || Kt % TILE_K != 0 || Bt % TILE_M != 0) return false;
+  if (!tc_enabled() || !p_hi || !p_lo || !f_hi || !f_lo || Kt % K_PAD != 0 || Bt % TILE_M != 0) return false;
   TcMaps maps;
   if (!make_map(&maps.f_hi, f_hi, Bt, Kt, TILE_M) || !make_map(&maps.f_lo, f_lo, Bt, Kt, TILE_M) ||
       !make_map(&maps.p_hi, p_hi, rows_alloc, Kt, TILE_N) || !make_map(&maps.p_lo, p_lo, rows_alloc, Kt, TILE_N))
     return false;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(k_vposed_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(k_vposed_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
+    if (cudaFuncSetAttribute(k_vposed_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_vposed_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_vposed_tc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_vposed_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
       cudaGetLastError();
       return false;
     }
@@ -337,13 +412,52 @@ bool tc_gemm_run(const float* p_hi, const float* p_lo, int rows, int rows_alloc,
   const int tiles_m = Bt / TILE_M, tiles_n = (rows + TILE_N - 1) / TILE_N, total = tiles_m * tiles_n;
   const int sms = sm_count_tc();
   const int grid = total < sms ? total : sms;
-  if (bias) SF_LAUNCH(k_vposed_tc<true>, grid, THREADS, SMEM_BYTES, st, maps, bias, out, rows, Bp, Kt / TILE_K, tiles_m, total);
-  else SF_LAUNCH(k_vposed_tc<false>, grid, THREADS, SMEM_BYTES, st, maps, bias, out, rows, Bp, Kt / TILE_K, tiles_m, total);
+  if (bias) SF_LAUNCH((k_vposed_tc<true, false>), grid, THREADS, SMEM_BYTES, st, maps, bias, out, rows, Bp, Kt / TILE_K, tiles_m, total);
+  else SF_LAUNCH((k_vposed_tc<false, false>), grid, THREADS, SMEM_BYTES, st, maps, bias, out, rows, Bp, Kt / TILE_K, tiles_m, total);
+  return true;
+}
+
+static bool split_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SMPLFIT_B200_GEMM_SPLIT");
+    v = (e && atoi(e) == 1) ? 1 : 0;  // measured: 0.233 ms vs 0.201 ms per launch with pre-split operands -> off by default
+  }
+  return v == 1;
+}
+
+// Same product from plain fp32 operands (hi / lo split inside the kernel): p [rows][p_ld] and f [Bp][f_ld], K valid
+// columns each (both leading dimensions multiples of 4 floats; columns / rows past the arrays are zero-filled by TMA).
+bool tc_gemm_run_f32(const float* p, int rows, int p_ld, const float* bias, const float* f, int f_rows, int f_ld, int K,
+                     float* out, int Bp, cudaStream_t st) {
+  if (!tc_enabled() || !split_enabled() || !p || !f || p_ld % 4 != 0 || f_ld % 4 != 0 || K > p_ld || K > f_ld) return false;
+  TcMaps maps;
+  if (!make_map(&maps.f_hi, f, (uint64_t)f_rows, (uint64_t)K, TILE_M, (uint64_t)f_ld) ||
+      !make_map(&maps.p_hi, p, (uint64_t)rows, (uint64_t)K, TILE_N, (uint64_t)p_ld))
+    return false;
+  maps.f_lo = maps.f_hi;
+  maps.p_lo = maps.p_hi;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(k_vposed_tc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_vposed_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    attr_set = true;
+  }
+  const int Bt = roundup(Bp, TILE_M);
+  const int tiles_m = Bt / TILE_M, tiles_n = (rows + TILE_N - 1) / TILE_N, total = tiles_m * tiles_n;
+  const int sms = sm_count_tc();
+  const int grid = total < sms ? total : sms;
+  const int k_blocks = (K + TILE_K - 1) / TILE_K;
+  if (bias) SF_LAUNCH((k_vposed_tc<true, true>), grid, THREADS, SMEM_BYTES, st, maps, bias, out, rows, Bp, k_blocks, tiles_m, total);
+  else SF_LAUNCH((k_vposed_tc<false, true>), grid, THREADS, SMEM_BYTES, st, maps, bias, out, rows, Bp, k_blocks, tiles_m, total);
   return true;
 }
 
 size_t vposed_tc_scratch_bytes(const smplfit_model_t* m, int Bp) {
-  const int Kt = roundup(m->num_pose_feats, TILE_K);
+  const int Kt = roundup(m->num_pose_feats, K_PAD);
   const int Bt = roundup(Bp, TILE_M);
   return (size_t)2 * Bt * Kt * sizeof(float) + 512;
 }
@@ -353,12 +467,21 @@ static bool vposed_tc_run_with(const smplfit_model_t* m, const float* p_hi, cons
 
 bool vposed_tc_run(const smplfit_model_t* m, const float* feat, float* vposedT, int Bp, int Kp, void* scratch,
                    cudaStream_t st) {
+  // fp32 operands, split in shared memory: posedirs_fit is [3V][Kp], feat [Bp][Kp]
+  if (m->posedirs_fit != nullptr && encode_fn() != nullptr &&
+      tc_gemm_run_f32(m->posedirs_fit, 3 * m->num_vertices, Kp, m->v_template_fit, feat, Bp, Kp, m->num_pose_feats, vposedT,
+                      Bp, st))
+    return true;
   return vposed_tc_run_with(m, m->posedirs_hi, m->posedirs_lo, m->v_template_fit, feat, vposedT, Bp, Kp, scratch, st);
 }
 
 // rows in MODEL vertex order (forward LBS): v_posed^T[v*3+c] = v_template[v][c] + posedirs[v][c] . feat
 bool vposed_tc_run_model(const smplfit_model_t* m, const float* feat, float* vposedT, int Bp, int Kp, void* scratch,
                          cudaStream_t st) {
+  if (m->posedirs_model_f32 != nullptr && encode_fn() != nullptr &&
+      tc_gemm_run_f32(m->posedirs_model_f32, 3 * m->num_vertices, roundup(m->num_pose_feats, K_PAD), m->v_template, feat, Bp,
+                      Kp, m->num_pose_feats, vposedT, Bp, st))
+    return true;
   return vposed_tc_run_with(m, m->posedirs_model_hi, m->posedirs_model_lo, m->v_template, feat, vposedT, Bp, Kp, scratch, st);
 }
 
@@ -366,7 +489,7 @@ static bool vposed_tc_run_with(const smplfit_model_t* m, const float* p_hi, cons
                                const float* feat, float* vposedT, int Bp, int Kp, void* scratch, cudaStream_t st) {
   if (!tc_enabled() || p_hi == nullptr || p_lo == nullptr || scratch == nullptr) return false;
   if (encode_fn() == nullptr) return false;
-  const int Kt = roundup(m->num_pose_feats, TILE_K);
+  const int Kt = roundup(m->num_pose_feats, K_PAD);
   const int Bt = roundup(Bp, TILE_M);
   const int rows = 3 * m->num_vertices;
   float* hi = reinterpret_cast<float*>(((uintptr_t)scratch + 255) & ~(uintptr_t)255);

@@ -173,7 +173,7 @@ class BodyModel(nn.Module):
             'template_joints_regressed': f32(jreg @ template_mesh),
             'J_regressor_fit': f32(jreg[:, order]),
             'posedirs_hi': f32(pd_hi), 'posedirs_lo': f32(pd_lo),
-            'posedirs_model_hi': f32(pdm_hi), 'posedirs_model_lo': f32(pdm_lo),
+            'posedirs_model_hi': f32(pdm_hi), 'posedirs_model_lo': f32(pdm_lo), 'posedirs_model_f32': f32(pdm),
             'template_mesh_fit': f32(template_mesh[order]),
         }
         # forward records (model order): see csrc/forward.cu k_fwd_skin_rec
@@ -231,7 +231,7 @@ class BodyModel(nn.Module):
                      'part_seg_begin', 'part_kind', 'part_copy_src', 'part_flags', 'cas_table', 'cas_count',
                      'posedirs_fit', 'v_template_fit', 'template_mesh', 'template_joints_regressed',
                      'J_regressor_fit', 'posedirs_hi', 'posedirs_lo', 'template_mesh_fit', 'posedirs_model_hi',
-                     'posedirs_model_lo'):
+                     'posedirs_model_lo', 'posedirs_model_f32'):
             setattr(s, name, getattr(self, '_t_' + name).data_ptr())
         for name, buf in self.named_buffers():
             if not buf.is_contiguous():
