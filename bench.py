@@ -54,7 +54,7 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 20 ms while the timed regions (resident and end-to-end) run."""
 
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
@@ -68,7 +68,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '200',
+                ['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '20',
                  '-i', str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -243,10 +243,11 @@ def main():
     _native.launch_count(reset=True)
     ms = timed(step_resident, args.steps)
     launches = _native.launch_count()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = None
 
     if args.resident_only:
         if rank == 0:
+            sampler.stop()
             print(json.dumps({'resident_only': True, 'ms_per_step': ms / args.steps, 'gpu_launches': int(launches),
                               'note': 'profiling run, not a bench line'}))
         if world > 1:
@@ -255,6 +256,7 @@ def main():
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
 
     # instrumented repeat: per-kernel device time with CUDA events on the launching stream
     prof = {}
