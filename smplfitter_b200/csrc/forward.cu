@@ -400,17 +400,22 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_fwd_skin_tma(const FwdSkinTma
             for (int c = 0; c < 3; ++c) jc.q[kk][c] = sq[(size_t)(jk[kk] * 3 + c) * 32 + lane];
           }
         }
+        constexpr int NV4 = (3 * SP + 3 + 3) / 4;
+        float sdv[NV4 * 4];  // shapedirs[c][s] then kid_shapedir[c] of the record, read as 16-byte words
+#pragma unroll
+        for (int q4 = 0; q4 < NV4; ++q4) {
+          const float4 v4 = *reinterpret_cast<const float4*>(rec + 12 + 4 * q4);
+          sdv[4 * q4] = v4.x; sdv[4 * q4 + 1] = v4.y; sdv[4 * q4 + 2] = v4.z; sdv[4 * q4 + 3] = v4.w;
+        }
         float vs[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           float2 y2 = make_float2(sg[(u * 3 + c) * 32 + lane], 0.f);
 #pragma unroll
-          for (int s2 = 0; s2 < SP; s2 += 2) {
-            const float2 sv = *reinterpret_cast<const float2*>(rec + 12 + c * SP + s2);
-            y2 = sf_fma2(sv, make_float2(beta[s2], beta[s2 + 1]), y2);
-          }
+          for (int s2 = 0; s2 < SP; s2 += 2)
+            y2 = sf_fma2(make_float2(sdv[c * SP + s2], sdv[c * SP + s2 + 1]), make_float2(beta[s2], beta[s2 + 1]), y2);
           float y = y2.x + y2.y;
-          if (a.use_kid) y = fmaf(rec[12 + 3 * SP + c], kid, y);
+          if (a.use_kid) y = fmaf(sdv[3 * SP + c], kid, y);
           vs[c] = y;
         }
         float2 B2[6];

@@ -240,12 +240,21 @@ k_shape_lite(const LiteArgs a, const __grid_constant__ CUtensorMap map_t, const 
         z[0] = fmaf(B2[0].x, bv[0], fmaf(B2[2].x, bv[1], B2[4].x * bv[2]));
         z[1] = fmaf(B2[0].y, bv[0], fmaf(B2[2].y, bv[1], B2[4].y * bv[2]));
         z[2] = fmaf(B2[1].x, bv[0], fmaf(B2[3].x, bv[1], B2[5].x * bv[2]));
-        const float2* sd2 = reinterpret_cast<const float2*>(rec + 8);  // shapedirs[x][sp] pairs (shared memory)
+        // shapedirs[x][s] of the record: 3 NSP floats read as 16-byte words (the record is padded to a 16-byte
+        // multiple past them), used as (s, s+1) pairs
+        constexpr int NV4 = (3 * NSP + 3) / 4;
+        float sdv[NV4 * 4];
+#pragma unroll
+        for (int q = 0; q < NV4; ++q) {
+          const float4 v4 = *reinterpret_cast<const float4*>(rec + 8 + 4 * q);
+          sdv[4 * q] = v4.x; sdv[4 * q + 1] = v4.y; sdv[4 * q + 2] = v4.z; sdv[4 * q + 3] = v4.w;
+        }
 #pragma unroll
         for (int x = 0; x < 3; ++x) {
           const float2 zz = make_float2(z[x], z[x]);
 #pragma unroll
-          for (int sp = 0; sp < H; ++sp) r2[sp] = sf_fma2(sd2[x * H + sp], zz, r2[sp]);
+          for (int sp = 0; sp < H; ++sp)
+            r2[sp] = sf_fma2(make_float2(sdv[x * NSP + 2 * sp], sdv[x * NSP + 2 * sp + 1]), zz, r2[sp]);
         }
       }
     }
@@ -633,15 +642,21 @@ k_stats_lite(const StatsLiteArgs a, const __grid_constant__ CUtensorMap map_t, c
               for (int c = 0; c < 3; ++c) jc.q[kk][c] = sq[(size_t)(jk[kk] * 3 + c) * 32 + lane];
             }
           }
+          constexpr int NV4 = (3 * NSP + 3) / 4;
+          float sdv[NV4 * 4];  // shapedirs[c][s] of the record as 16-byte words
+#pragma unroll
+          for (int q4 = 0; q4 < NV4; ++q4) {
+            const float4 v4 = *reinterpret_cast<const float4*>(rec + 8 + 4 * q4);
+            sdv[4 * q4] = v4.x; sdv[4 * q4 + 1] = v4.y; sdv[4 * q4 + 2] = v4.z; sdv[4 * q4 + 3] = v4.w;
+          }
           float vs[3];
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             float2 y2 = make_float2(x[c], 0.f);
 #pragma unroll
-            for (int s2 = 0; s2 < NSP; s2 += 2) {
-              const float2 sv = *reinterpret_cast<const float2*>(rec + 8 + c * NSP + s2);
-              y2 = sf_fma2(sv, make_float2(beta[s2], (s2 + 1 < NS) ? beta[s2 + 1] : 0.f), y2);
-            }
+            for (int s2 = 0; s2 < NSP; s2 += 2)
+              y2 = sf_fma2(make_float2(sdv[c * NSP + s2], sdv[c * NSP + s2 + 1]),
+                           make_float2(beta[s2], (s2 + 1 < NS) ? beta[s2 + 1] : 0.f), y2);
             vs[c] = y2.x + y2.y;
           }
           float2 B2[6];
