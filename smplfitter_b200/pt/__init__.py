@@ -6,9 +6,10 @@ import functools
 
 from .bodyconverter import BodyConverter
 from .bodyfitter import BodyFitter
+from .bodyflipper import BodyFlipper
 from .bodymodel import BodyModel
 
-__all__ = ['BodyModel', 'BodyFitter', 'BodyConverter', 'get_cached_body_model', 'get_cached_fit_fn']
+__all__ = ['BodyModel', 'BodyFitter', 'BodyConverter', 'BodyFlipper', 'get_cached_body_model', 'get_cached_fit_fn']
 
 
 @functools.lru_cache()

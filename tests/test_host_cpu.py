@@ -192,3 +192,26 @@ def test_closed_form_gram_tables(mname, kid):
         Yk = cells[yj_entry[yj_start[k]:yj_start[k + 1]]].sum(axis=0)
         r += T[k][:, 1:].T @ Yk
     assert np.abs(r - r_ref).max() <= 1e-9 * np.abs(r_ref).max()
+
+
+def test_body_flipper_host_logic():
+    """BodyFlipper's host side (pt/bodyflipper.py:112-137): mirror assignment and the naive rotation-vector flip."""
+    from smplfitter_b200.pt import BodyFlipper, BodyModel
+    from smplfitter_b200.pt.bodyflipper import get_mirror_mapping, nearest_mirror_csr
+
+    rs = np.random.RandomState(0)
+    half = rs.randn(7, 3) + [2.0, 0, 0]
+    pts = np.concatenate([half, half * [-1, 1, 1], [[0.0, 1.0, 2.0]]])  # 7 mirrored pairs + one point on the plane
+    m = get_mirror_mapping(pts)
+    assert np.array_equal(m, np.concatenate([np.arange(7, 14), np.arange(0, 7), [14]]))
+    csr = nearest_mirror_csr(pts)
+    assert np.allclose(csr @ pts * [-1, 1, 1], pts)  # mirror transfer + x flip maps a symmetric set onto itself
+    bm = BodyModel('smpl_tiny')
+    fl = BodyFlipper(bm)
+    J = bm.num_joints
+    rv = torch.from_numpy(rs.randn(5, 3 * J).astype(np.float32))
+    got = fl.naive_flip_rotvecs(rv).numpy().reshape(5, J, 3)
+    want = rv.numpy().reshape(5, J, 3)[:, fl.mirror_inds_joints.numpy()] * [1, -1, -1]
+    assert np.array_equal(got, want.astype(np.float32))
+    with pytest.raises(RuntimeError):
+        fl.flip_vertices(torch.zeros(1, bm.num_vertices, 3))  # CPU module: no fallback
