@@ -127,10 +127,21 @@ def cpu_port_fits_per_s(sample_B, reps, seed=42):
 
 
 def host_cores():
+    """Threads the numpy port can actually use: the BLAS pool size (its matmul / einsum calls are the only threaded
+    part), capped by the scheduler affinity."""
     try:
-        return len(os.sched_getaffinity(0))
+        avail = len(os.sched_getaffinity(0))
     except Exception:
-        return os.cpu_count() or 1
+        avail = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_info
+
+        blas = [p.get('num_threads', 1) for p in threadpool_info() if p.get('user_api') == 'blas']
+        if blas:
+            return int(min(avail, max(blas)))
+    except Exception:
+        pass
+    return avail
 
 
 def run_reference_arm(args, rank):

@@ -5,6 +5,7 @@ for v in $VALS; do
   python - <<PY
 import json
 d=json.loads(open('gpurun_out/ab_$v.log').read().strip().splitlines()[-1])
-print('$VAR=$v: fits/s=%.0f ms/step=%.3f e2e_ms=%.3f' % (d['value'], d['ms_per_step'], d['e2e']['ms_per_step']))
+k=d['roofline']['kernel_ms_per_step']
+print('$VAR=$v: fits/s=%.0f ms/step=%.3f e2e_ms=%.3f' % (d['value'], d['ms_per_step'], d['e2e']['ms_per_step']), {a: round(b,3) for a,b in list(k.items())[:4]})
 PY
 done
