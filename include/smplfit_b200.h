@@ -122,6 +122,9 @@ typedef struct smplfit_model {
   const float* posedirs_model_hi; /* (3V, Kt) posedirs rows in MODEL vertex order, tf32-exact high part (forward LBS) */
   const float* posedirs_model_lo; /* (3V, Kt) remainder */
   const float* posedirs_model_f32; /* (3V, Kt) the same rows in full precision (split into hi / lo inside the GEMM kernel) */
+  const uint8_t* fit_slot_mask; /* (V) internal order: bit k = skinning slot k of this vertex (fit_rec) has a non-zero weight and a
+                                   joint other than the previous one of that slot within the statistics segment, i.e. the
+                                   kernels' per-slot register cache of joint rows must reload; NULL = compare at run time */
 } smplfit_model_t;
 
 /* Options of BodyFitter.fit (pt/bodyfitter.py:283-302). */

@@ -43,7 +43,7 @@ class ModelStruct(C.Structure):
         + [(n, _F) for n in ('seg_slots', 'yj_start', 'yj_entry', 'gcf_pairs', 'gcf_A', 'gcf_G0', 'gcf_lstart',
                              'gcf_lk', 'gcf_Bm', 'gcf_Wh')]
         + [('n_slots', C.c_int32), ('gcf_npairs', C.c_int32)]
-        + [('gcf_AT_hi', _F), ('gcf_AT_lo', _F), ('posedirs_model_hi', _F), ('posedirs_model_lo', _F), ('posedirs_model_f32', _F)]
+        + [('gcf_AT_hi', _F), ('gcf_AT_lo', _F), ('posedirs_model_hi', _F), ('posedirs_model_lo', _F), ('posedirs_model_f32', _F), ('fit_slot_mask', _F)]
     )
 
 

@@ -87,6 +87,16 @@ static void launch_adjust(const AdjustArgs& aa, int groups, cudaStream_t st) {
   }
 }
 
+// SMPLFIT_B200_SLOT_MASK=0: the vertex kernels compare joint ids at run time instead of using fit_slot_mask
+static bool slot_mask_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SMPLFIT_B200_SLOT_MASK");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static int moment_blocks(int V) { return (V + 255) / 256; }
 static int shape_nacc(int ns) { return ns * (ns + 1) / 2 + ns + 3 * ns + 3 + 1; }
 
@@ -223,7 +233,7 @@ static void run_shape(FitCtx& c, int scale_mode, const float* beta_ref, const fl
     LiteArgs la;
     la.tT = c.w.tT; la.vposedT = c.w.vposedT; la.RT12 = c.w.RT12; la.rec = m->fit_rec; la.seg_start = m->seg_start;
     la.seg_slots = m->seg_slots; la.partials = c.w.gpart; la.n_segments = m->n_segments; la.J = m->num_joints;
-    la.Bp = c.Bp; la.segs_per_warp = 1;
+    la.Bp = c.Bp; la.segs_per_warp = 1; la.slot_mask = slot_mask_enabled() ? m->fit_slot_mask : nullptr;
     launch_shape_lite(la, m, c.groups, c.w.Yd, c.st);
     if (side) cudaStreamWaitEvent(c.st, side->join, 0);
     so.lite = 1; so.lite_nl = lite_rows(m->fit_ns); so.n_gcf = gram_closed_blocks(m); so.gcf_part = c.w.gcfpart;
@@ -286,6 +296,7 @@ static void run_stats(FitCtx& c, int ref_mode, const float* ca0T, const float* a
     l.skin4 = c.w.skin4; l.aT_out = aT_out; l.partials = c.w.spart; l.rec = m->fit_rec; l.seg_start = m->seg_start;
     l.seg_part = m->seg_part; l.part_flags = m->part_flags; l.n_segments = m->n_segments; l.Bp = c.Bp;
     l.J = m->num_joints; l.all_segments = (aT_out != nullptr); l.segs_per_warp = 1;
+    l.slot_mask = slot_mask_enabled() ? m->fit_slot_mask : nullptr;
     launch_stats_lite(l, m, c.groups, c.st);
     return;
   }

@@ -33,6 +33,7 @@ struct LiteArgs {
   const int32_t* seg_start;
   const int32_t* seg_slots;  // [n_segments][LITE_NSLOT]
   float* partials;           // [n_segments][NS + 3 + 3*LITE_NSLOT][Bp]: r | Sb | Y per slot
+  const uint8_t* slot_mask;  // [V] precomputed "slot k must reload its joint rows" bits (smplfit_b200.h), or null
   int n_segments, J, Bp, segs_per_warp;
 };
 
@@ -135,6 +136,7 @@ k_shape_lite(const LiteArgs a, const __grid_constant__ CUtensorMap map_t, const 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Bp = a.Bp;
   const int b = g * 32 + lane;
+  const bool has_mask = a.slot_mask != nullptr;
   const float4* sq = reinterpret_cast<const float4*>(s_lite);  // [J*3][32]
   float* wbase = s_lite + (size_t)a.J * 3 * 128;
   float* yw = wbase + (size_t)WARPS * (2 * STAGE) + (size_t)warp * (LITE_NSLOT * 3 * 32);  // [slot*3+c][32]
@@ -190,10 +192,13 @@ k_shape_lite(const LiteArgs a, const __grid_constant__ CUtensorMap map_t, const 
     jc.reset();
     const int nsub = (i1 - i0 + LITE_VS - 1) / LITE_VS;
     for (int k = 0; k < nsub; ++k) {
+      const int nv = min(LITE_VS, i1 - (i0 + k * LITE_VS));
+      // precomputed reload bits of the sub-block's vertices (one byte per lane, broadcast by shuffle below)
+      unsigned mk = 0u;
+      if (has_mask && lane < nv) mk = __ldg(a.slot_mask + i0 + k * LITE_VS + lane);
       rs.wait(k);
       if (k >= 1) rs.issue(k + 1, lane);  // the stage of sub-block k-1 is free now
       const float* st = rs.stage(k);
-      const int nv = min(LITE_VS, i1 - (i0 + k * LITE_VS));
 #pragma unroll LITE_UNROLL
       for (int u = 0; u < nv; ++u) {
         float t[3], vp[3];
@@ -204,12 +209,22 @@ k_shape_lite(const LiteArgs a, const __grid_constant__ CUtensorMap map_t, const 
         }
         const float* rec = st + 2 * BOX + u * REC;
         const float4 w4 = *reinterpret_cast<const float4*>(rec);
-        const int4 j4 = *reinterpret_cast<const int4*>(rec + 4);
         const float wk[4] = {w4.x, w4.y, w4.z, w4.w};
+        unsigned m;
+        int4 j4 = make_int4(0, 0, 0, 0);
+        if (has_mask) {
+          m = __shfl_sync(0xffffffffu, mk, u);
+          if (m) j4 = *reinterpret_cast<const int4*>(rec + 4);
+        } else {
+          j4 = *reinterpret_cast<const int4*>(rec + 4);
+          m = (wk[0] != 0.f && j4.x != jc.j[0] ? 1u : 0u) | (wk[1] != 0.f && j4.y != jc.j[1] ? 2u : 0u) |
+              (wk[2] != 0.f && j4.z != jc.j[2] ? 4u : 0u) | (wk[3] != 0.f && j4.w != jc.j[3] ? 8u : 0u);
+        }
         const int jk[4] = {j4.x, j4.y, j4.z, j4.w};
+        if (m) {  // warp-uniform, ~4 % of the vertices
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
-          if (wk[kk] != 0.f && jk[kk] != jc.j[kk]) {  // warp-uniform, rare
+          if (m & (1u << kk)) {
             if (jc.j[kk] >= 0) {
               float* yp = yw + (size_t)(lut[jc.j[kk]] * 3) * 32 + lane;
 #pragma unroll
@@ -222,6 +237,7 @@ k_shape_lite(const LiteArgs a, const __grid_constant__ CUtensorMap map_t, const 
 #pragma unroll
             for (int c = 0; c < 3; ++c) jc.q[kk][c] = sq[(size_t)(jk[kk] * 3 + c) * 32 + lane];
           }
+        }
         }
         float2 B2[6];  // B2[2c] = (Rb[c][0], Rb[c][1]), B2[2c+1] = (Rb[c][2], Tb0[c])
         jc.blend(wk, B2);
@@ -536,6 +552,7 @@ struct StatsLiteArgs {
   const int32_t* seg_start;
   const int32_t* seg_part;
   const int32_t* part_flags;
+  const uint8_t* slot_mask;  // as in LiteArgs, or null
   int n_segments, Bp, J, all_segments, segs_per_warp;
 };
 
@@ -554,6 +571,7 @@ k_stats_lite(const StatsLiteArgs a, const __grid_constant__ CUtensorMap map_t, c
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Bp = a.Bp;
   const int b = g * 32 + lane;
+  const bool has_mask = a.slot_mask != nullptr;
   const float4* sq = reinterpret_cast<const float4*>(s_st);  // [J*3][32]
   float* wbase = s_st + (size_t)a.J * 3 * 128;
   Stager rs;
@@ -614,6 +632,8 @@ k_stats_lite(const StatsLiteArgs a, const __grid_constant__ CUtensorMap map_t, c
       const int nv = min(LITE_VS, i1 - first);
       // the (rare) per-vertex weights stay on a plain coalesced load, issued before the stage wait
       float wnext = WEIGHTED ? SF_IM(a.vwT, first, Bp, b) : 1.f;
+      unsigned mk = 0u;  // precomputed reload bits of the sub-block's vertices
+      if (has_mask && lane < nv) mk = __ldg(a.slot_mask + first + lane);
       rs.wait(k);
       if (k >= 1) rs.issue(k + 1, lane);
       const float* sg = rs.stage(k);
@@ -631,15 +651,26 @@ k_stats_lite(const StatsLiteArgs a, const __grid_constant__ CUtensorMap map_t, c
           if (WEIGHTED && u + 1 < nv) wnext = SF_IM(a.vwT, i + 1, Bp, b);
           const float* rec = sg + 2 * BOX + u * REC;
           const float4 w4 = *reinterpret_cast<const float4*>(rec);
-          const int4 j4 = *reinterpret_cast<const int4*>(rec + 4);
           const float wk[4] = {w4.x, w4.y, w4.z, w4.w};
-          const int jk[4] = {j4.x, j4.y, j4.z, j4.w};
+          unsigned m;
+          int4 j4 = make_int4(0, 0, 0, 0);
+          if (has_mask) {
+            m = __shfl_sync(0xffffffffu, mk, u);
+            if (m) j4 = *reinterpret_cast<const int4*>(rec + 4);
+          } else {
+            j4 = *reinterpret_cast<const int4*>(rec + 4);
+            m = (wk[0] != 0.f && j4.x != jc.j[0] ? 1u : 0u) | (wk[1] != 0.f && j4.y != jc.j[1] ? 2u : 0u) |
+                (wk[2] != 0.f && j4.z != jc.j[2] ? 4u : 0u) | (wk[3] != 0.f && j4.w != jc.j[3] ? 8u : 0u);
+          }
+          if (m) {  // warp-uniform, ~4 % of the vertices
+            const int jk[4] = {j4.x, j4.y, j4.z, j4.w};
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            if (wk[kk] != 0.f && jk[kk] != jc.j[kk]) {  // warp-uniform, rare
-              jc.j[kk] = jk[kk];
+            for (int kk = 0; kk < 4; ++kk) {
+              if (m & (1u << kk)) {
+                jc.j[kk] = jk[kk];
 #pragma unroll
-              for (int c = 0; c < 3; ++c) jc.q[kk][c] = sq[(size_t)(jk[kk] * 3 + c) * 32 + lane];
+                for (int c = 0; c < 3; ++c) jc.q[kk][c] = sq[(size_t)(jk[kk] * 3 + c) * 32 + lane];
+              }
             }
           }
           constexpr int NV4 = (3 * NSP + 3) / 4;

@@ -97,6 +97,22 @@ class BodyFitter(nn.Module):
             for x in range(3):
                 rec[:, 8 + x * nsp:8 + x * nsp + ns] = sd_np[:, x, :]
             self.register_buffer('_t_fit_rec', torch.tensor(np.ascontiguousarray(rec[order])), persistent=False)
+            # per vertex (internal order): bit k set when skinning slot k must (re)load its joint rows, i.e. its weight
+            # is non-zero and its joint differs from the last one loaded for that slot in the same segment -- the
+            # kernels' register cache of joint rows (lite_kernels.cuh JointCache) replayed on the host
+            seg_start = body_model._t_seg_start.cpu().numpy()
+            idx_o, w_o = idx4[order], w4[order]
+            mask = np.zeros(V, np.uint8)
+            for a, b in zip(seg_start[:-1], seg_start[1:]):
+                cached = [-1, -1, -1, -1]
+                for i in range(int(a), int(b)):
+                    m = 0
+                    for k in range(4):
+                        if w_o[i, k] != 0 and idx_o[i, k] != cached[k]:
+                            cached[k] = int(idx_o[i, k])
+                            m |= 1 << k
+                    mask[i] = m
+            self.register_buffer('_t_fit_slot_mask', torch.tensor(mask), persistent=False)
             self._build_pair_constants(idx4, w4, sd_np, J, ns)
         else:
             self._t_fit_rec = None
@@ -182,6 +198,7 @@ class BodyFitter(nn.Module):
             fit_shapedirs=self._t_fit_shapedirs.data_ptr(),
             fit_Jt_ext=self.J_template_ext.data_ptr(),
             fit_rec=0 if self._t_fit_rec is None else self._t_fit_rec.data_ptr(),
+            fit_slot_mask=0 if self._t_fit_rec is None else self._t_fit_slot_mask.data_ptr(),
             fit_rec_len=self._rec_len,
             fit_wS=self._t_fit_wS.data_ptr(),
             fit_wsum=self._t_fit_wsum.data_ptr(),
