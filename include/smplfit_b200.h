@@ -182,7 +182,9 @@ int smplfit_fit(const smplfit_model_t* m, int64_t batch, const float* target_ver
  * host_* pointers are HOST memory (page-locked for the copies to overlap the fits; pageable memory works but
  * serialises); `workspace` is DEVICE memory of smplfit_fit_host_workspace_bytes.  The batch is processed in
  * chunks of `chunk` instances: the H2D copy of chunk k+1 runs on a library-owned copy stream while chunk k is
- * fitted on `stream`; the results are copied back on `stream` and are valid once `stream` has been synchronised.
+ * fitted on library-owned compute streams; each chunk's results are copied back right after its fit (page-locked
+ * output buffers keep these copies asynchronous) and everything is joined into `stream`: the host buffers are valid
+ * once `stream` has been synchronised.
  * No vertex/joint weights, initial guesses or share_beta here (per-instance options go through smplfit_fit).
  * host_orientations / host_rel_orientations / host_kid_factor / host_scale_corr may be NULL. */
 size_t smplfit_fit_host_workspace_bytes(const smplfit_model_t* m, int64_t batch, int64_t chunk,

@@ -216,21 +216,24 @@ extern "C" int smplfit_fit_host(const smplfit_model_t* m, int64_t batch, int64_t
                                w.kid + lo, w.scale + lo, w.fit_ws[slot], w.fit_ws_bytes, cs);
     if (rc != SMPLFIT_OK) return rc;
     if (trace) cudaEventRecord(tr_fit[k], cs);
+    // results of this chunk: a few hundred bytes per instance, copied back on the chunk's stream (the D2H engine is
+    // otherwise idle), so that only the last chunk's copy is exposed at the end
+    auto back = [&](float* host, const float* dev, size_t per_instance) -> cudaError_t {
+      if (!host) return cudaSuccess;
+      return cudaMemcpyAsync(host + (size_t)lo * per_instance, dev + (size_t)lo * per_instance,
+                             (size_t)n * per_instance * sizeof(float), cudaMemcpyDeviceToHost, cs);
+    };
+    if (o->want_pose_rotvecs) SF_CU(back(host_pose_rotvecs, w.pose, J * 3));
+    SF_CU(back(host_shape_betas, w.betas, S));
+    SF_CU(back(host_trans, w.trans, 3));
+    SF_CU(back(host_orientations, w.orient, J * 9));
+    SF_CU(back(host_rel_orientations, w.rel, J * 9));
+    if (o->enable_kid) SF_CU(back(host_kid_factor, w.kid, 1));
+    if (o->scale_mode != 0) SF_CU(back(host_scale_corr, w.scale, 1));
     SF_CU(cudaEventRecord(p->done[slot], cs));
   }
+  // every chunk's results were copied back on its own stream right after its fit: join the ring
   for (int i = 0; i < kSlots && i < n_chunks; ++i) SF_CU(cudaStreamWaitEvent(st, p->done[i], 0));
-  // results: a few hundred bytes per instance, one copy per output for the whole batch
-  auto back = [&](float* host, const float* dev, size_t per_instance) -> cudaError_t {
-    if (!host) return cudaSuccess;
-    return cudaMemcpyAsync(host, dev, (size_t)batch * per_instance * sizeof(float), cudaMemcpyDeviceToHost, st);
-  };
-  if (o->want_pose_rotvecs) SF_CU(back(host_pose_rotvecs, w.pose, J * 3));
-  SF_CU(back(host_shape_betas, w.betas, S));
-  SF_CU(back(host_trans, w.trans, 3));
-  SF_CU(back(host_orientations, w.orient, J * 9));
-  SF_CU(back(host_rel_orientations, w.rel, J * 9));
-  if (o->enable_kid) SF_CU(back(host_kid_factor, w.kid, 1));
-  if (o->scale_mode != 0) SF_CU(back(host_scale_corr, w.scale, 1));
   if (trace) {
     cudaEventRecord(tr_end, st);
     cudaEventSynchronize(tr_end);
