@@ -13,6 +13,9 @@
 namespace sf {
 
 extern thread_local char g_err[512];
+// set by a launcher that could not enqueue its kernel (e.g. a tensor-map encode failure); the C-ABI entry point that
+// called it turns it into SMPLFIT_ERR_CUDA instead of returning results computed from garbage
+extern thread_local const char* g_launch_failure;
 extern std::atomic<long long> g_launches;
 
 inline int fail(int code, const char* fmt, const char* detail = "") {
@@ -47,6 +50,11 @@ extern std::vector<ProfRec> g_prof;
 
 #define SF_CHECK_LAST()                                                            \
   do {                                                                             \
+    if (sf::g_launch_failure != nullptr) {                                         \
+      const char* m__ = sf::g_launch_failure;                                      \
+      sf::g_launch_failure = nullptr;                                              \
+      return sf::fail(SMPLFIT_ERR_CUDA, "launch failed: %s", m__);                 \
+    }                                                                              \
     cudaError_t e__ = cudaGetLastError();                                          \
     if (e__ != cudaSuccess) return sf::fail(SMPLFIT_ERR_CUDA, "CUDA error: %s", cudaGetErrorString(e__)); \
   } while (0)

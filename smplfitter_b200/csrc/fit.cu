@@ -16,6 +16,7 @@
 namespace sf {
 
 thread_local char g_err[512] = "";
+thread_local const char* g_launch_failure = nullptr;
 std::atomic<long long> g_launches{0};
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;

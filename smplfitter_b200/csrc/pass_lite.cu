@@ -117,7 +117,7 @@ template <int NS, int WARPS>
 static void lite_launch_t(LiteArgs a, int V, int groups, cudaStream_t st) {
   CUtensorMap mt, mv;
   if (!stream_maps(a.tT, a.vposedT, V, a.Bp, &mt, &mv)) {
-    fprintf(stderr, "smplfit_b200: cuTensorMapEncodeTiled failed for the vertex streams\n");
+    g_launch_failure = "cuTensorMapEncodeTiled failed for the vertex streams";
     return;
   }
   const size_t smem = lite_smem_bytes(a.J, Rec<NS>::LEN, WARPS);
@@ -157,7 +157,7 @@ static void gram_closed_t(const smplfit_model_t* m, int groups, int Bp, const fl
   if (!pairs_done && ga.n_pair_ctas > 0) {
     if (gram_pairs_tc_available(m)) {
       // the workspace holds one pair block on this path: the SIMT kernel cannot take over
-      fprintf(stderr, "smplfit_b200: tcgen05 pair GEMM failed to launch\n");
+      g_launch_failure = "tcgen05 pair GEMM could not be launched";
     } else {
       SF_LAUNCH(k_gram_pairs<NS>, dim3(groups, ga.n_pair_ctas), 256, red, st, ga);
     }
@@ -191,7 +191,7 @@ template <int NS, bool WEIGHTED, int WARPS>
 static void stats_lite_launch_t(StatsLiteArgs a, int V, int groups, cudaStream_t st) {
   CUtensorMap mt, mv;
   if (!stream_maps(a.tT, a.vposedT, V, a.Bp, &mt, &mv)) {
-    fprintf(stderr, "smplfit_b200: cuTensorMapEncodeTiled failed for the vertex streams\n");
+    g_launch_failure = "cuTensorMapEncodeTiled failed for the vertex streams";
     return;
   }
   const size_t smem = stats_lite_smem_bytes(a.J, Rec<NS>::LEN, WARPS);
@@ -224,7 +224,7 @@ void launch_stats_tmpl(const StatsLiteArgs& a0, const smplfit_model_t* m, const 
   StatsLiteArgs a = a0;
   CUtensorMap mt;
   if (!make_im_map(&mt, a.tT, (uint64_t)3 * m->num_vertices, (uint64_t)a.Bp, 3 * TMPL_VS)) {
-    fprintf(stderr, "smplfit_b200: cuTensorMapEncodeTiled failed for the target stream\n");
+    g_launch_failure = "cuTensorMapEncodeTiled failed for the target stream";
     return;
   }
   constexpr int WARPS = 16;

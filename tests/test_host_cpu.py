@@ -215,3 +215,40 @@ def test_body_flipper_host_logic():
     assert np.array_equal(got, want.astype(np.float32))
     with pytest.raises(RuntimeError):
         fl.flip_vertices(torch.zeros(1, bm.num_vertices, 3))  # CPU module: no fallback
+
+
+@pytest.mark.parametrize('mname', ['smpl_tiny', 'smplx_tiny'])
+def test_slot_mask_and_gemm_operands(mname):
+    """Host tables added for the TMA-staged kernels: fit_slot_mask replays the kernels' per-slot register cache
+    (reset at every segment start, skipping zero weights), and gcf_AT_hi + gcf_AT_lo is the transposed, padded gcf_A."""
+    from smplfitter_b200.pt import BodyFitter, BodyModel
+
+    bm = BodyModel(mname)
+    ft = BodyFitter(bm)
+    rec = ft._t_fit_rec.numpy()
+    w = rec[:, 0:4]
+    idx = rec[:, 4:8].view(np.int32)
+    seg = bm._t_seg_start.numpy()
+    mask = ft._t_fit_slot_mask.numpy()
+    assert mask.shape == (bm.num_vertices,) and mask.dtype == np.uint8
+    for a, b in zip(seg[:-1], seg[1:]):
+        # first vertex of a segment: every slot with a non-zero weight loads
+        assert mask[a] == sum(1 << k for k in range(4) if w[a, k] != 0)
+        for k in range(4):
+            last = -1
+            for i in range(a, b):
+                need = w[i, k] != 0 and idx[i, k] != last
+                assert bool(mask[i] >> k & 1) == bool(need), (i, k)
+                if need:
+                    last = idx[i, k]
+    # the records past the last segment (unused vertices, if any) carry no bits that matter; segments tile [0, V)
+    assert seg[0] == 0 and seg[-1] == bm.num_vertices
+    A = ft._t_gcf_A.numpy()                      # (npairs, 9, NGP)
+    AT = ft._t_gcf_AT_hi.numpy() + ft._t_gcf_AT_lo.numpy()
+    ns = ft._ns
+    ng = ns * (ns + 1) // 2
+    assert AT.shape[0] % 256 == 0 and AT.shape[1] % 32 == 0
+    assert np.array_equal(AT[:ng, :9 * A.shape[0]], A[:, :, :ng].reshape(-1, ng).T)
+    assert not AT[ng:].any() and not AT[:, 9 * A.shape[0]:].any()
+    hi = ft._t_gcf_AT_hi.numpy()
+    assert not (hi.view(np.uint32) & np.uint32(0x1FFF)).any()  # tf32-exact high parts
