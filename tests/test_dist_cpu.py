@@ -62,3 +62,11 @@ def test_scatter_fit_gather_world2():
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=10) is True
+
+
+def test_scatter_fit_gather_rejects_share_beta():
+    """share_beta couples every instance of the batch: the sharded helper refuses it before any communication."""
+    import pytest
+
+    with pytest.raises(NotImplementedError):
+        sdist.scatter_fit_gather(_fake_fit, 4, None, None, 11, 5, share_beta=True)
