@@ -252,3 +252,25 @@ def test_slot_mask_and_gemm_operands(mname):
     assert not AT[ng:].any() and not AT[:, 9 * A.shape[0]:].any()
     hi = ft._t_gcf_AT_hi.numpy()
     assert not (hi.view(np.uint32) & np.uint32(0x1FFF)).any()  # tf32-exact high parts
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/smplfit_b200.h is a C header (what a cgo / JNI / ctypes-free binding would include): it must compile
+    as C11 on its own and declare every entry point the library exports."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        pytest.skip('no gcc')
+    src = tmp_path / 'use_header.c'
+    src.write_text(
+        '#include "smplfit_b200.h"\n'
+        'int probe(const smplfit_model_t* m, const smplfit_fit_opts_t* o) {\n'
+        '  size_t a = smplfit_fit_workspace_bytes(m, 1, o, 1, 0, 0) + smplfit_forward_workspace_bytes(m, 1) +\n'
+        '             smplfit_fit_host_workspace_bytes(m, 1, 1, o, 1) + smplfit_struct_size(0);\n'
+        '  return (int)a + (smplfit_version() != 0) + (int)smplfit_launch_count(0);\n'
+        '}\n')
+    r = subprocess.run([gcc, '-std=c11', '-Wall', '-Werror', '-fsyntax-only', '-I', os.path.join(ROOT, 'include'), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
