@@ -431,10 +431,15 @@ static __global__ void __launch_bounds__(256) k_pair_feat(const PairFeatArgs a) 
   __syncthreads();
   const int K9 = a.npairs * 9;
   // blockIdx.y splits the pair range (each CTA re-stages the rotations: a few KB from L2) so that several CTAs
-  // per SM hide the store latency
+  // per SM hide the latency.  Each warp builds one instance's slice of the feature row in shared memory (stride-9
+  // writes are bank-conflict free) and copies it out with coalesced stores: writing the 9 values of a pair
+  // straight to global memory touched every 32-byte sector once per value (226 MB of partial-sector writes for
+  // 23 MB of data).
   const int per = (a.npairs + gridDim.y - 1) / gridDim.y;
   const int p_lo = blockIdx.y * per, p_hi = min(a.npairs, p_lo + per);
   const bool last = blockIdx.y == gridDim.y - 1;
+  const int n9 = max(0, p_hi - p_lo) * 9;
+  float* sbuf = s_R + 32 * stride + (size_t)warp * (2 * per * 9);  // [hi: per*9][lo: per*9]
   for (int ii = 0; ii < 4; ++ii) {
     const int i = warp * 4 + ii;
     float* hi = a.hi + (size_t)(g * 32 + i) * a.Kt;
@@ -445,22 +450,27 @@ static __global__ void __launch_bounds__(256) k_pair_feat(const PairFeatArgs a) 
         const int k = __ldg(a.pairs + 2 * p), l = __ldg(a.pairs + 2 * p + 1);
         const float* Rk = R + k * 9;
         const float* Rl = R + l * 9;
+        float* oh = sbuf + (p - p_lo) * 9;
+        float* ol = oh + per * 9;
 #pragma unroll
         for (int aa = 0; aa < 3; ++aa)
 #pragma unroll
           for (int cc = 0; cc < 3; ++cc) {
             const float x = fmaf(Rk[aa], Rl[cc], fmaf(Rk[3 + aa], Rl[3 + cc], Rk[6 + aa] * Rl[6 + cc]));
             const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-            hi[p * 9 + aa * 3 + cc] = h;
-            lo[p * 9 + aa * 3 + cc] = x - h;
+            oh[aa * 3 + cc] = h;
+            ol[aa * 3 + cc] = x - h;
           }
       }
-      if (last)
-        for (int q = K9 + lane; q < a.Kt; q += 32) hi[q] = lo[q] = 0.f;
-    } else {
-      const int q_lo = p_lo * 9, q_hi = last ? a.Kt : p_hi * 9;
-      for (int q = q_lo + lane; q < q_hi; q += 32) hi[q] = lo[q] = 0.f;
     }
+    __syncwarp();
+    for (int q = lane; q < n9; q += 32) {
+      hi[p_lo * 9 + q] = valid ? sbuf[q] : 0.f;
+      lo[p_lo * 9 + q] = valid ? sbuf[per * 9 + q] : 0.f;
+    }
+    if (last)
+      for (int q = K9 + lane; q < a.Kt; q += 32) hi[q] = lo[q] = 0.f;
+    __syncwarp();
   }
 }
 

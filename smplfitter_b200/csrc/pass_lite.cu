@@ -148,9 +148,11 @@ static void gram_closed_t(const smplfit_model_t* m, int groups, int Bp, const fl
     PairFeatArgs pf;
     pf.RT = RT; pf.pairs = m->gcf_pairs; pf.hi = pair_scratch; pf.lo = pair_scratch + (size_t)Bt * Kt;
     pf.npairs = m->gcf_npairs; pf.J = m->num_joints; pf.RW = 12 + 3 * NS; pf.Bp = a.Bp; pf.Kt = Kt;
-    const size_t smem_f = (size_t)32 * ((m->num_joints * 9) | 1) * sizeof(float);
+    constexpr int PF_SPLIT = 4;  // CTAs per instance group (pair ranges)
+    const int pf_per = (m->gcf_npairs + PF_SPLIT - 1) / PF_SPLIT;
+    const size_t smem_f = ((size_t)32 * ((m->num_joints * 9) | 1) + (size_t)8 * 2 * pf_per * 9) * sizeof(float);
     if (smem_f > 48 * 1024) cudaFuncSetAttribute(k_pair_feat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
-    SF_LAUNCH(k_pair_feat, dim3(Bt / 32, 4), 256, smem_f, st, pf);
+    SF_LAUNCH(k_pair_feat, dim3(Bt / 32, PF_SPLIT), 256, smem_f, st, pf);
     pairs_done = tc_gemm_run(m->gcf_AT_hi, m->gcf_AT_lo, NG, roundup(NG, tc_tile_n()), Kt, nullptr, pf.hi, pf.lo, Bt,
                              gcf_part, a.Bp, st);
   }
