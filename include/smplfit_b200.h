@@ -125,6 +125,19 @@ typedef struct smplfit_model {
   const uint8_t* fit_slot_mask; /* (V) internal order: bit k = skinning slot k of this vertex (fit_rec) has a non-zero weight and a
                                    joint other than the previous one of that slot within the statistics segment, i.e. the
                                    kernels' per-slot register cache of joint rows must reload; NULL = compare at run time */
+  /* ---- fused forward LBS (k_fwd_fused: blend-shape GEMM with the skinning in its epilogue) ----
+   * Constants of the GEMM  D[b][3p+c] = sum_k F[b][k] P[3p+c][k]:  P = 2^fwd_scale_log2 [posedirs | shapedirs | kid_shapedir]
+   * with rows in PROCESSING order p (64-vertex tiles of 16-vertex chunks; a chunk holds 16 consecutive model vertices,
+   * re-ordered so that consecutive vertices share skinning joints), split into fp16 hi / lo parts (raw IEEE half bits).
+   * All NULL / 0 disables the path (the GEMM + k_fwd_skin kernels are used instead). */
+  const uint16_t* fwd_P_hi;     /* (roundup(V,64)*3, fwd_kf) */
+  const uint16_t* fwd_P_lo;     /* same shape: P - hi */
+  const uint32_t* fwd_vrec;     /* (roundup(V,64), 8) per processed vertex: 4 slot weights (float bits) | pack | v_rest[3] (float
+                                   bits; zero-pose zero-shape position = v_template + posedirs vec(I)); pack = 4 x 6-bit joint of
+                                   slot k (bits 6k..6k+5) | reload mask (bits 24-27: slot k takes another joint here) |
+                                   model-local vertex index inside the chunk (bits 28-31) */
+  int32_t fwd_kf;               /* K of the GEMM: roundup(P + S + 1, 32); feature order [pose | betas | kid] */
+  int32_t fwd_scale_log2;       /* s: the constants are scaled by 2^s into fp16's normal range */
 } smplfit_model_t;
 
 /* Options of BodyFitter.fit (pt/bodyfitter.py:283-302). */

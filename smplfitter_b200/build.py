@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 LIB = os.path.join(HERE, 'libsmplfit_b200.so')
-SOURCES = ['fit.cu', 'fit_host.cu', 'pass_shape.cu', 'pass_shape_v3.cu', 'pass_lite.cu', 'pass_stats.cu', 'pass_scale.cu', 'forward.cu', 'vposed_tc.cu']
+SOURCES = ['fit.cu', 'fit_host.cu', 'pass_shape.cu', 'pass_shape_v3.cu', 'pass_lite.cu', 'pass_stats.cu', 'pass_scale.cu', 'forward.cu', 'fwd_fused.cu', 'vposed_tc.cu']
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
     '-Xcompiler', '-fPIC', '--use_fast_math=false' if False else '-DSMPLFIT_BUILD',

@@ -248,6 +248,24 @@ SYNTHETIC_SPECS = {
 
 _provider: Optional[Callable[..., ModelData]] = None
 _cache: dict = {}
+_synthetic_enabled: Optional[bool] = None  # None: follow $SMPLFITTER_B200_SYNTHETIC (default off)
+
+
+def use_synthetic_models(enable: bool = True) -> None:
+    """Opt in to (or out of) the synthetic stand-ins for model names without a provider.
+
+    Off by default: like the reference (common.py:219-260), ``BodyModel('smpl')`` raises
+    ``FileNotFoundError`` when the licensed files cannot be loaded.  Tests, ``bench.py`` and
+    ``smoke()`` call this explicitly; ``SMPLFITTER_B200_SYNTHETIC=1`` does the same from the
+    environment."""
+    global _synthetic_enabled
+    _synthetic_enabled = bool(enable)
+
+
+def synthetic_models_enabled() -> bool:
+    if _synthetic_enabled is not None:
+        return _synthetic_enabled
+    return os.environ.get('SMPLFITTER_B200_SYNTHETIC', '0') == '1'
 
 
 def set_model_provider(fn: Optional[Callable[..., ModelData]]) -> None:
@@ -277,20 +295,23 @@ def initialize(
 ) -> ModelData:
     """Same call signature as the reference seam (common.py:219-228).
 
-    Resolution order: an installed provider; else, if ``SMPLFITTER_B200_SYNTHETIC`` is not
-    ``0``, the synthetic stand-in of that name.  Reading the licensed files is delegated to
-    a provider on purpose (file parsing is out of scope).
+    Resolution order: an installed provider; else, only after an explicit opt-in
+    (``use_synthetic_models()`` or ``SMPLFITTER_B200_SYNTHETIC=1``), the synthetic stand-in of
+    that name; else ``FileNotFoundError`` as in the reference.  Reading the licensed files is
+    delegated to a provider on purpose (file parsing is out of scope).
     """
     if _provider is not None:
         return _provider(
             model_name, gender, model_root, num_betas, vertex_subset_size, vertex_subset,
             faces, joint_regressor_post_lbs,
         )
-    if os.environ.get('SMPLFITTER_B200_SYNTHETIC', '1') == '0' or model_name not in SYNTHETIC_SPECS:
+    if not synthetic_models_enabled() or model_name not in SYNTHETIC_SPECS:
         raise FileNotFoundError(
             f"No model provider installed for '{model_name}'. Call "
             'smplfitter_b200.modeldata.set_model_provider(smplfitter.common.initialize) to load '
-            'the licensed files, or use a synthetic model name: ' + ', '.join(SYNTHETIC_SPECS)
+            'the licensed files; synthetic stand-ins (' + ', '.join(SYNTHETIC_SPECS) + ') are only '
+            'served after smplfitter_b200.modeldata.use_synthetic_models() or with '
+            'SMPLFITTER_B200_SYNTHETIC=1'
         )
     data = synthetic_model(model_name)
     if vertex_subset_size is not None and vertex_subset is None:

@@ -46,7 +46,9 @@ class BodyFlipper(nn.Module):
 
     ``mirror_csr`` may be given explicitly (scipy CSR, (V, V)).  Otherwise, as in the reference (:140-156), the
     SMPL-X flip correspondences (and, for SMPL, the two transfer matrices) are read from
-    ``$DATA_ROOT/body_models`` when present; without those licensed files the nearest-mirror-vertex stand-in is used.
+    ``$DATA_ROOT/body_models``; without those licensed files the constructor raises ``FileNotFoundError`` like the
+    reference, unless synthetic models were opted into (``modeldata.use_synthetic_models()``), in which case the
+    nearest-mirror-vertex stand-in is used.
     """
 
     def __init__(self, body_model, mirror_csr=None):
@@ -57,6 +59,12 @@ class BodyFlipper(nn.Module):
         if mirror_csr is None:
             mirror_csr = self._load_default_csr(body_model.num_vertices)
         if mirror_csr is None:
+            from .. import modeldata
+
+            if not modeldata.synthetic_models_enabled():
+                raise FileNotFoundError(
+                    'smplx_flip_correspondences.npz not found under $DATA_ROOT/body_models/smplx; pass mirror_csr= '
+                    'explicitly (the nearest-mirror stand-in is only used with synthetic models)')
             mirror_csr = nearest_mirror_csr(res['vertices'])
         m = mirror_csr.tocsr().astype(np.float32)
         V = body_model.num_vertices

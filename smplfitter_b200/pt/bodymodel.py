@@ -152,10 +152,6 @@ class BodyModel(nn.Module):
         pd[:, :P] = posedirs_fit[:, :P]
         pd_hi = (pd.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)  # tf32-exact part
         pd_lo = pd - pd_hi
-        pdm = np.zeros((V * 3, Kt), np.float32)  # the same rows in MODEL order, for the forward pass
-        pdm[:, :P] = self.posedirs.numpy().reshape(V * 3, P)
-        pdm_hi = (pdm.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
-        pdm_lo = pdm - pdm_hi
         eye_feat = np.tile(np.eye(3, dtype=np.float32), [J - 1, 1]).reshape(-1)
         v_posed0 = self.v_template.numpy() + np.einsum('vcp,p->vc', self.posedirs.numpy(), eye_feat)
         template_mesh = (v_posed0 * w32.sum(axis=1, keepdims=True)).astype(np.float32)  # pt/bodyfitter.py:49
@@ -173,30 +169,12 @@ class BodyModel(nn.Module):
             'template_joints_regressed': f32(jreg @ template_mesh),
             'J_regressor_fit': f32(jreg[:, order]),
             'posedirs_hi': f32(pd_hi), 'posedirs_lo': f32(pd_lo),
-            'posedirs_model_hi': f32(pdm_hi), 'posedirs_model_lo': f32(pdm_lo), 'posedirs_model_f32': f32(pdm),
             'template_mesh_fit': f32(template_mesh[order]),
         }
-        # forward records (model order): see csrc/forward.cu k_fwd_skin_rec
-        S = self.num_betas
-        SP = (S + 1) // 2 * 2
-        self._fwd_rec_len = (12 + 3 * SP + 3 + 3) // 4 * 4
-        if K <= 4:
-            idx4 = np.zeros((V, 4), np.int32)
-            w4 = np.zeros((V, 4), np.float32)
-            idx4[:, :K], w4[:, :K] = skin_idx, skin_w
-            idx4[:, K:] = skin_idx[:, :1]
-            srt = np.argsort(-w4, axis=1, kind='stable')
-            idx4 = np.take_along_axis(idx4, srt, axis=1)
-            w4 = np.take_along_axis(w4, srt, axis=1)
-            frec = np.zeros((V, self._fwd_rec_len), np.float32)
-            frec[:, 0:4] = w4
-            frec[:, 4:8] = idx4.view(np.float32)
-            frec[:, 8] = inv_order.astype(np.int32).view(np.float32)
-            sd_np = self.shapedirs.numpy()
-            for x in range(3):
-                frec[:, 12 + x * SP:12 + x * SP + S] = sd_np[:, x, :]
-            frec[:, 12 + 3 * SP:12 + 3 * SP + 3] = self.kid_shapedir.numpy()
-            t['fwd_rec'] = f32(frec)
+        if K <= 4 and J <= 64:
+            v_rest = self.v_template.numpy().astype(np.float64) + np.einsum(
+                'vcp,p->vc', self.posedirs.numpy().astype(np.float64), eye_feat.astype(np.float64))
+            self._build_forward_tables(skin_idx, skin_w, v_rest, t)
         if K <= 4:
             seg_slots, yj_start, yj_entry = _slot_tables(seg_start, joint_sets, J)
             t['seg_slots'], t['yj_start'], t['yj_entry'] = i32(seg_slots), i32(yj_start), i32(yj_entry)
@@ -210,6 +188,79 @@ class BodyModel(nn.Module):
         self._handle = _ops.register(self)
         if device is not None:
             self.to(device)
+
+    @torch.jit.unused
+    def _build_forward_tables(self, skin_idx, skin_w, v_rest, t):
+        """Constants of the fused forward kernel (include/smplfit_b200.h ``fwd_*``; csrc/fwd_fused.cu).
+
+        Processing order: 64-vertex tiles of 16-vertex chunks; a chunk is 16 consecutive model vertices (so a chunk's
+        results are one contiguous 192-byte piece of the caller's row), visited in the order and with the joint -> slot
+        assignment that makes the kernel's four register-cached joint rows change as rarely as possible (greedy: next
+        the vertex needing the fewest new joints; a new joint evicts the slot whose joint is needed latest)."""
+        V, J, S = self.num_vertices, self.num_joints, self.num_betas
+        P = 9 * (J - 1)
+        CH, TILE, CPW = 16, 64, 2  # FWD_CHUNK, TILE_V and chunks per epilogue warp of csrc/fwd_fused.cu
+        Vp = (V + TILE - 1) // TILE * TILE
+        joints_of = [[(int(j), float(w)) for j, w in zip(skin_idx[v], skin_w[v]) if w != 0] for v in range(V)]
+        rec = np.zeros((Vp, 8), np.uint32)
+        proc = np.full(Vp, -1, np.int64)  # processing position -> model vertex (-1: padding)
+        for c0 in range(0, Vp, CH):
+            todo = [v for v in range(c0, min(c0 + CH, V))]
+            pos = c0
+            first = (c0 // CH) % CPW == 0  # a warp keeps its cache over the CPW consecutive chunks it takes from a tile
+            if first:
+                cache = [-1, -1, -1, -1]
+            while todo:
+                # fewest joints missing from the cache; ties: lowest vertex index
+                v = min(todo, key=lambda u: (sum(1 for j, _ in joints_of[u] if j not in cache), u))
+                todo.remove(v)
+                need = [j for j, _ in joints_of[v]]
+                reload = 0
+                for j in need:
+                    if j in cache:
+                        continue
+                    free = [k for k in range(4) if cache[k] not in need]
+                    # evict an empty slot, else the slot whose joint the fewest remaining vertices of the chunk need
+                    k = min(free, key=lambda kk: (cache[kk] != -1,
+                                                  sum(1 for u in todo for jj, _ in joints_of[u] if jj == cache[kk]), kk))
+                    cache[k] = j
+                    reload |= 1 << k
+                if first:  # nothing is cached across tiles (the next tile belongs to other instances)
+                    reload = 0
+                    for k in range(4):
+                        if cache[k] in need:
+                            reload |= 1 << k
+                    first = False
+                w = np.zeros(4, np.float32)
+                for j, ww in joints_of[v]:
+                    w[cache.index(j)] = ww
+                pack = 0
+                for k in range(4):
+                    pack |= (max(cache[k], 0) & 63) << (6 * k)
+                pack |= reload << 24
+                pack |= (v - c0) << 28
+                rec[pos, 0:4] = w.view(np.uint32)
+                rec[pos, 4] = pack
+                rec[pos, 5:8] = v_rest[v].astype(np.float32).view(np.uint32)
+                proc[pos] = v
+                pos += 1
+            for q in range(pos, c0 + CH):  # padding of the last chunk(s): zero weights, distinct local indices
+                rec[q, 4] = (q - c0) << 28
+        Kf = (P + S + 1 + 31) // 32 * 32
+        pm = np.zeros((Vp * 3, Kf), np.float64)
+        live = proc >= 0
+        rows = np.concatenate([self.posedirs.numpy().astype(np.float64), self.shapedirs.numpy().astype(np.float64),
+                               self.kid_shapedir.numpy().astype(np.float64)[:, :, None]], axis=2)  # (V,3,P+S+1)
+        pm.reshape(Vp, 3, Kf)[live, :, :P + S + 1] = rows[proc[live]]
+        amax = float(np.abs(pm).max())
+        self._fwd_scale_log2 = int(np.clip(np.floor(np.log2(16384.0 / amax)) if amax > 0 else 0, 0, 14))
+        pm *= 2.0 ** self._fwd_scale_log2
+        hi = pm.astype(np.float16)
+        lo = (pm - hi.astype(np.float64)).astype(np.float16)
+        self._fwd_kf = Kf
+        t['fwd_P_hi'] = torch.from_numpy(hi)
+        t['fwd_P_lo'] = torch.from_numpy(lo)
+        t['fwd_vrec'] = torch.from_numpy(rec.view(np.int32))
 
     # ------------------------------------------------------------------------------
     @torch.jit.unused
@@ -230,15 +281,16 @@ class BodyModel(nn.Module):
         for name in ('parents', 'skin_idx', 'skin_w', 'order', 'inv_order', 'seg_start', 'seg_part',
                      'part_seg_begin', 'part_kind', 'part_copy_src', 'part_flags', 'cas_table', 'cas_count',
                      'posedirs_fit', 'v_template_fit', 'template_mesh', 'template_joints_regressed',
-                     'J_regressor_fit', 'posedirs_hi', 'posedirs_lo', 'template_mesh_fit', 'posedirs_model_hi',
-                     'posedirs_model_lo', 'posedirs_model_f32'):
+                     'J_regressor_fit', 'posedirs_hi', 'posedirs_lo', 'template_mesh_fit'):
             setattr(s, name, getattr(self, '_t_' + name).data_ptr())
         for name, buf in self.named_buffers():
             if not buf.is_contiguous():
                 raise RuntimeError(f'smplfitter_b200: buffer {name} must be contiguous')
         s.fit_ns = 0
-        s.fwd_rec = self._t_fwd_rec.data_ptr() if hasattr(self, '_t_fwd_rec') else 0
-        s.fwd_rec_len = self._fwd_rec_len
+        if hasattr(self, '_t_fwd_P_hi'):
+            s.fwd_P_hi, s.fwd_P_lo, s.fwd_vrec = (self._t_fwd_P_hi.data_ptr(), self._t_fwd_P_lo.data_ptr(),
+                                                  self._t_fwd_vrec.data_ptr())
+            s.fwd_kf, s.fwd_scale_log2 = self._fwd_kf, self._fwd_scale_log2
         if hasattr(self, '_t_seg_slots'):
             s.seg_slots, s.yj_start, s.yj_entry = (self._t_seg_slots.data_ptr(), self._t_yj_start.data_ptr(),
                                                     self._t_yj_entry.data_ptr())

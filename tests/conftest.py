@@ -9,6 +9,12 @@ if ROOT not in sys.path:
 
 GOLDEN_DIR = os.path.join(ROOT, 'tests', 'golden')
 
+# the licensed SMPL files are absent: every test runs on the synthetic stand-ins (explicit opt-in;
+# without it BodyModel('smpl') raises FileNotFoundError like the reference)
+from smplfitter_b200 import modeldata  # noqa: E402
+
+modeldata.use_synthetic_models(True)
+
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')

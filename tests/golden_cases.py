@@ -4,7 +4,8 @@ import os
 
 import numpy as np
 
-from oracle.make_golden import FIT_CASES, FORWARD_CASES, MASK_CASES  # noqa: F401  (test-side import)
+from oracle.make_golden import (CONVERT_CASES, FIT_CASES, FORWARD_CASES, KNOWN_POSE_CASES,  # noqa: F401
+                                KNOWN_SHAPE_CASES, MASK_CASES, aux_call_kwargs)
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
@@ -38,5 +39,27 @@ def orient_tolerance(g, floor=1e-4, k=6.0):
     return np.maximum(floor, np.maximum(k * n, n.max()))
 
 
-def rotvec_tolerance(g, floor=1e-4, k=6.0):
-    return np.repeat(orient_tolerance(g, floor, k) * 1.5, 3)
+def relative_tolerance(g, parents, floor=1e-4, k=6.0):
+    """Relative rotation R_parent^T R_j: carries the noise of both joints."""
+    t = orient_tolerance(g, floor, k)
+    par = np.asarray(parents).copy()
+    par[0] = 0
+    rel = t + t[par]
+    rel[0] = t[0]
+    return rel
+
+
+def rotvec_tolerance(g, parents, floor=1e-4, k=6.0):
+    """Rotation-vector entries of the relative rotations (|d rotvec| <= ~sqrt(2) |d R| entrywise near small angles)."""
+    return np.repeat(relative_tolerance(g, parents, floor, k) * 1.5, 3)
+
+
+def csr_of(g):
+    """scipy CSR transfer matrix stored in a converter fixture (None: same topology)."""
+    if 'csr_data' not in g:
+        return None
+    import scipy.sparse as sp
+
+    n_out = len(g['csr_indptr']) - 1
+    return sp.csr_matrix((g['csr_data'], g['csr_indices'], g['csr_indptr']),
+                         shape=(n_out, int(g['csr_indices'].max()) + 1))

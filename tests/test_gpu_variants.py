@@ -18,7 +18,6 @@ VARIANTS = {
     'stats_rec': {'SMPLFIT_B200_STATS_VARIANT': '0'},
     'adjust_seq': {'SMPLFIT_B200_ADJUST': 'seq'},
     'slot_mask_off': {'SMPLFIT_B200_SLOT_MASK': '0'},
-    'fwd_rec': {'SMPLFIT_B200_FWD_VARIANT': '0'},
     'side_stream': {'SMPLFIT_B200_SIDE_STREAM': '2'},
 }
 

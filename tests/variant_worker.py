@@ -5,7 +5,10 @@ import sys
 import numpy as np
 import torch
 
+from smplfitter_b200 import modeldata
 from smplfitter_b200.pt import BodyFitter, BodyModel
+
+modeldata.use_synthetic_models(True)
 
 out = {}
 for mname, B in (('smpl_tiny', 45), ('smplx_tiny', 33)):
