@@ -138,6 +138,12 @@ typedef struct smplfit_model {
                                    model-local vertex index inside the chunk (bits 28-31) */
   int32_t fwd_kf;               /* K of the GEMM: roundup(P + S + 1, 32); feature order [pose | betas | kid] */
   int32_t fwd_scale_log2;       /* s: the constants are scaled by 2^s into fp16's normal range */
+  /* ---- the fit's pose-blend contraction v_posed^T = v_template_fit + posedirs_fit . vec(R_rel) on the same fp16-split
+   * tensor-core main loop: 2^fit_scale_log2 posedirs_fit as fp16 hi / lo (raw half bits), rows in internal order ---- */
+  const uint16_t* fit_P_hi;     /* (roundup(3V,192), fit_kf) */
+  const uint16_t* fit_P_lo;
+  int32_t fit_kf;               /* roundup(P, 32) */
+  int32_t fit_scale_log2;
 } smplfit_model_t;
 
 /* Options of BodyFitter.fit (pt/bodyfitter.py:283-302). */

@@ -45,6 +45,7 @@ class ModelStruct(C.Structure):
         + [('n_slots', C.c_int32), ('gcf_npairs', C.c_int32)]
         + [('gcf_AT_hi', _F), ('gcf_AT_lo', _F), ('posedirs_model_hi', _F), ('posedirs_model_lo', _F), ('posedirs_model_f32', _F), ('fit_slot_mask', _F)]
         + [('fwd_P_hi', _F), ('fwd_P_lo', _F), ('fwd_vrec', _F), ('fwd_kf', C.c_int32), ('fwd_scale_log2', C.c_int32)]
+        + [('fit_P_hi', _F), ('fit_P_lo', _F), ('fit_kf', C.c_int32), ('fit_scale_log2', C.c_int32)]
     )
 
 

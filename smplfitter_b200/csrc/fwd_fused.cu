@@ -39,16 +39,21 @@ constexpr int ROW_BYTES = KB * 2;
 constexpr int A_BYTES = TILE_M * ROW_BYTES;   // 8 KB per feature tile
 constexpr int B_BYTES = TILE_N * ROW_BYTES;   // 12 KB per constant tile
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // F_hi, F_lo, P_hi, P_lo = 40 KB
-constexpr int STAGES = 4;
-constexpr int EPI_WARPS = 8;
-constexpr int CPW = NCH * 4 / EPI_WARPS;      // chunks per epilogue warp and tile (2)
-constexpr int THREADS = 128 + EPI_WARPS * 32;
 constexpr int PITCH = 3 * CH + 2;             // staging row pitch in floats (even: 8-byte aligned rows)
 constexpr int STG_FLOATS = 32 * PITCH;
 constexpr int REC_WORDS = 8;                  // per-vertex record: w[4] | pack | v_rest[3]
-constexpr int WARP_SMEM = STG_FLOATS * 4 + CPW * CH * REC_WORDS * 4 + 16;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * WARP_SMEM + 256 + 1024;
+constexpr int WARP_SMEM = STG_FLOATS * 4;     // per epilogue warp: the staging tile
+constexpr int REC_TILE_BYTES = TILE_V * REC_WORDS * 4;  // the records of one tile (2 KB), double buffered per CTA
 constexpr uint32_t TMEM_COLS = 512;
+// Epilogue width: 8 warps (two per TMEM lane quadrant), 2 chunks per warp and tile.  Measured alternative: 16 warps
+// (one chunk each, 640 threads, register file re-divided with setmaxnreg) ran 0.188 vs 0.177 ms -- not kept.
+template <int EW>
+struct Cfg {
+  static constexpr int STAGES = 4;
+  static constexpr int CPW = NCH * 4 / EW;
+  static constexpr int THREADS = 128 + EW * 32;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EW * WARP_SMEM + 2 * REC_TILE_BYTES + 256 + 1024;
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -72,6 +77,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "}\n"
         : "=r"(ok)
         : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// the single-thread producer / MMA loops wait most of the time (the epilogue sets the pace): try_wait with a
+// suspend-time hint parks the thread in hardware instead of polling, so the wait does not take issue slots from the
+// epilogue warps of the same scheduler
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity), "r"(0x989680u)
         : "memory");
   } while (!ok);
 }
@@ -124,27 +147,43 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
                  "=r"(r[o + 12]), "=r"(r[o + 13]), "=r"(r[o + 14]), "=r"(r[o + 15])                                       \
                : "r"(taddr))
 
+#define SF_TMEM_LD8(r, o, taddr)                                                                                \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"                  \
+               : "=r"(r[o + 0]), "=r"(r[o + 1]), "=r"(r[o + 2]), "=r"(r[o + 3]), "=r"(r[o + 4]), "=r"(r[o + 5]), \
+                 "=r"(r[o + 6]), "=r"(r[o + 7])                                                                 \
+               : "r"(taddr))
+
 struct FusedMaps {
   CUtensorMap f_hi, f_lo, p_hi, p_lo;
 };
 
 struct FusedArgs {
-  const float4* quads;     // [J*3][Bt] skinning rows (G[c][0..2], t[c]) per instance
+  const float4* quads;     // [J*3][Bt] skinning rows per instance, pair layout (see k_fwd_prep2)
   const uint32_t* vrec;    // [tiles_n * TILE_V][REC_WORDS] per-vertex records in processing order
-  float* out;              // (B,V,3)
+  float* out;              // MODE 0: (B,V,3);  MODE 1: [rows][Bp] instance-minor
+  const float* bias;       // MODE 1: [rows] added to every column of the row
   float inv_scale;         // 2^-s
   int V, B, Bt, k_blocks, tiles_m, total_tiles, aligned8;
+  int rows, Bp;            // MODE 1
 };
 
-__global__ void __launch_bounds__(THREADS, 1) k_fwd_fused(const __grid_constant__ FusedMaps maps, const FusedArgs a) {
+// MODE 0: forward LBS (skinning epilogue).  MODE 1: the same GEMM with a plain epilogue, out[n][b] = bias[n] + 2^-s D[b][n]
+// (the fit's posed template v_posed^T = v_template + posedirs . vec(R_rel), pt/bodyfitter.py:913-916).
+template <int MODE, int EW>
+__global__ void __launch_bounds__(Cfg<EW>::THREADS, 1) k_fwd_fused(const __grid_constant__ FusedMaps maps, const FusedArgs a) {
+  constexpr int STAGES = Cfg<EW>::STAGES, CPW = Cfg<EW>::CPW, EPI_WARPS = EW;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by pointer arithmetic on the shared array (keeps the shared address space: LDS / STS, not
+  // generic LD / ST, for everything derived from it)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* warp_area = smem + STAGES * STAGE_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(warp_area + EPI_WARPS * WARP_SMEM);
+  uint8_t* rec_area = warp_area + EPI_WARPS * WARP_SMEM;  // [2][TILE_V][REC_WORDS] (MODE 0)
+  uint64_t* full = reinterpret_cast<uint64_t*>(rec_area + 2 * REC_TILE_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* acc_full = empty + STAGES;  // [2] accumulator ready for the epilogue
   uint64_t* acc_empty = acc_full + 2;   // [2] accumulator drained (EPI_WARPS arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* rec_full = acc_empty + 2;   // [2] the tile's records have landed (MODE 0)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rec_full + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -161,12 +200,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_fwd_fused(const __grid_constant_
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], EPI_WARPS);
+      mbar_init(&rec_full[s], 1);
     }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp >= 4 && lane == 0) {
-    uint64_t* rbar = reinterpret_cast<uint64_t*>(warp_area + (warp - 4) * WARP_SMEM + STG_FLOATS * 4 + CPW * CH * REC_WORDS * 4);
-    mbar_init(rbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -179,16 +214,26 @@ __global__ void __launch_bounds__(THREADS, 1) k_fwd_fused(const __grid_constant_
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp < 4) {
   if (warp == 0) {
     if (lane == 0) {
       // ---- TMA producer ----
-      int it = 0;
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      int it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tcount) {
         const int b0 = (tile % a.tiles_m) * TILE_M, n0 = (tile / a.tiles_m) * TILE_N;
+        if (MODE == 0) {
+          // the tile's per-vertex records, into the buffer that goes with its accumulator (free once the epilogue of
+          // two tiles ago has released it)
+          const int as = tcount & 1;
+          mbar_wait_parked(&acc_empty[as], ((tcount >> 1) & 1) ^ 1);
+          mbar_expect_tx(&rec_full[as], REC_TILE_BYTES);
+          bulk_g2s(rec_area + as * REC_TILE_BYTES, a.vrec + (size_t)(tile / a.tiles_m) * TILE_V * REC_WORDS, REC_TILE_BYTES,
+                   &rec_full[as]);
+        }
         for (int kb = 0; kb < a.k_blocks; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
+          mbar_wait_parked(&empty[s], ph ^ 1);
           uint8_t* st = smem + s * STAGE_BYTES;
           mbar_expect_tx(&full[s], STAGE_BYTES);
           tma_load_2d(st, &maps.f_hi, &full[s], kb * KB, b0);
@@ -206,14 +251,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_fwd_fused(const __grid_constant_
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tcount) {
         const int as = tcount & 1;
         const uint32_t aph = (tcount >> 1) & 1;
-        mbar_wait(&acc_empty[as], aph ^ 1);
+        mbar_wait_parked(&acc_empty[as], aph ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * TILE_N);
         uint32_t acc = 0;
         for (int kb = 0; kb < a.k_blocks; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&full[s], ph);
+          mbar_wait_parked(&full[s], ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
           const uint64_t fhi = make_desc(base), flo = make_desc(base + A_BYTES);
@@ -232,120 +277,185 @@ __global__ void __launch_bounds__(THREADS, 1) k_fwd_fused(const __grid_constant_
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
+  }
+  } else if (MODE == 1) {
+    // ---- epilogue warps: TMEM -> + bias -> coalesced stores (lane == instance: 128-byte lines) ----
+    const int e = warp - 4, q = warp & 3, h = e >> 2;
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tcount) {
+      const int as = tcount & 1;
+      const uint32_t aph = (tcount >> 1) & 1;
+      const int tm = tile % a.tiles_m, tn = tile / a.tiles_m;
+      const int b = tm * TILE_M + q * 32 + lane;
+      mbar_wait(&acc_full[as], aph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int ch = 0; ch < CPW; ++ch) {
+        const int c0 = (h * CPW + ch) * 3 * CH;
+        const int n0 = tn * TILE_N + c0;
+        if (n0 >= a.rows) break;
+        uint32_t r[3 * CH];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TILE_N + c0);
+        SF_TMEM_LD16(r, 0, taddr);
+        SF_TMEM_LD16(r, 16, taddr + 16);
+        SF_TMEM_LD16(r, 32, taddr + 32);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (b < a.Bp) {
+          float* dst = a.out + (size_t)n0 * a.Bp + b;
+#pragma unroll
+          for (int i = 0; i < 3 * CH; ++i)
+            if (n0 + i < a.rows) dst[(size_t)i * a.Bp] = fmaf(__uint_as_float(r[i]), a.inv_scale, __ldg(a.bias + n0 + i));
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
+    }
+  } else {
     // ---- epilogue warps: skinning out of TMEM ----
     const int e = warp - 4;
     const int q = warp & 3;    // TMEM lane quadrant this warp may read (warp id % 4)
     const int h = e >> 2;      // which CPW chunks of the tile
     float* stg = reinterpret_cast<float*>(warp_area + e * WARP_SMEM);
-    uint32_t* recs = reinterpret_cast<uint32_t*>(stg + STG_FLOATS);
-    uint64_t* rbar = reinterpret_cast<uint64_t*>(recs + CPW * CH * REC_WORDS);
-    // write-out mapping: 4 rows x 24 float2 = 96 float2 = 3 warp-wide 8-byte accesses
-    int wo_row[3], wo_e[3];
+    // write-out mappings (a chunk row = 3 CH contiguous floats of one instance):
+    //   8-byte form: 4 rows x 24 float2 = 3 warp-wide accesses;  4-byte form (odd V): 2 rows x 48 floats = 3 accesses
+    int wo8_s[3], wo8_g[3], wo4_s[3], wo4_g[3], wo8_r[3], wo4_r[3];
 #pragma unroll
     for (int t = 0; t < 3; ++t) {
       const int n = t * 32 + lane;
-      wo_row[t] = n / (3 * CH / 2);
-      wo_e[t] = n - wo_row[t] * (3 * CH / 2);
+      wo8_r[t] = n / (3 * CH / 2);
+      const int e8 = n - wo8_r[t] * (3 * CH / 2);
+      wo8_s[t] = wo8_r[t] * PITCH + 2 * e8;
+      wo8_g[t] = wo8_r[t] * a.V * 3 + 2 * e8;
+      wo4_r[t] = n / (3 * CH);
+      const int e4 = n - wo4_r[t] * (3 * CH);
+      wo4_s[t] = wo4_r[t] * PITCH + e4;
+      wo4_g[t] = wo4_r[t] * a.V * 3 + e4;
     }
-    float4 cq[4][3];  // cached joint rows per skinning slot
+    // cached joint rows per skinning slot, as the pairs the blend / apply steps consume:
+    //   cq[k][0..3] = (G00,G10) (G01,G11) (G02,G12) (t0,t1);  cq[k][4..5] = (G20,G21) (G22,t2)
+    float2 cq[4][6];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) cq[k][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < 6; ++i) cq[k][i] = make_float2(0.f, 0.f);
     int tcount = 0;
-    uint32_t rphase = 0;
     const float inv_scale = a.inv_scale;
+    float* const my_row = stg + lane * PITCH;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tcount) {
       const int as = tcount & 1;
       const uint32_t aph = (tcount >> 1) & 1;
       const int tm = tile % a.tiles_m, tn = tile / a.tiles_m;
       const int b = tm * TILE_M + q * 32 + lane;  // this lane's instance (< Bt)
-      const int vfirst = tn * TILE_V + h * CPW * CH;  // first vertex (processing order == model order per chunk)
-      // this warp's records of the tile: one bulk copy, hidden behind the wait for the accumulator
-      if (lane == 0) {
-        mbar_expect_tx(rbar, CPW * CH * REC_WORDS * 4);
-        bulk_g2s(recs, a.vrec + (size_t)vfirst * REC_WORDS, CPW * CH * REC_WORDS * 4, rbar);
-      }
+      const int vfirst = tn * TILE_V + h * CPW * CH;  // first vertex of this warp's chunks
+      // per-vertex records of this warp's share of the tile (shared memory, warp-uniform 16-byte reads one vertex
+      // ahead of their use)
+      const uint4* rc = reinterpret_cast<const uint4*>(rec_area + as * REC_TILE_BYTES) + (h * CPW * CH) * 2;
+      mbar_wait(&rec_full[as], aph);
+      uint4 nw4 = rc[0], nm4 = rc[1];
       mbar_wait(&acc_full[as], aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      mbar_wait(rbar, rphase);
-      rphase ^= 1u;
       const float4* qb = a.quads + b;
+      const int b_row0 = tm * TILE_M + q * 32;
 #pragma unroll 1
       for (int ch = 0; ch < CPW; ++ch) {
         const int v0 = vfirst + ch * CH;
         if (v0 >= a.V) break;
-        uint32_t r[3 * CH];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TILE_N + (h * CPW + ch) * 3 * CH);
-        SF_TMEM_LD16(r, 0, taddr);
-        SF_TMEM_LD16(r, 16, taddr + 16);
-        SF_TMEM_LD16(r, 32, taddr + 32);
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {  // 8 vertices = 24 accumulator columns at a time (register budget)
+        uint32_t r[3 * CH / 2];
+        SF_TMEM_LD16(r, 0, taddr + half * (3 * CH / 2));
+        SF_TMEM_LD8(r, 16, taddr + half * (3 * CH / 2) + 16);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const uint4* rc = reinterpret_cast<const uint4*>(recs + ch * CH * REC_WORDS);
 #pragma unroll
-        for (int u = 0; u < CH; ++u) {
-          const uint4 w4 = rc[2 * u];
-          const uint4 m4 = rc[2 * u + 1];
+        for (int uu = 0; uu < CH / 2; ++uu) {
+          const int u = half * (CH / 2) + uu;
+          const uint4 w4 = nw4, m4 = nm4;
+          if (u + 1 < CH || ch + 1 < CPW) {
+            nw4 = rc[2 * (ch * CH + u) + 2];
+            nm4 = rc[2 * (ch * CH + u) + 3];
+          }
           const uint32_t pack = m4.x;
+          // slots that take another joint at this vertex (host-replayed cache, warp-uniform, rare); at the first vertex
+          // of the warp's share of a tile every slot is (re)loaded: the previous tile belonged to other instances
+          const uint32_t rl = (u == 0 && ch == 0) ? 0xFu : ((pack >> 24) & 0xFu);
+          if (rl) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (pack & (1u << (24 + k))) {  // warp-uniform: slot k takes another joint at this vertex
-              const int j = (pack >> (6 * k)) & 63;
-#pragma unroll
-              for (int c = 0; c < 3; ++c) cq[k][c] = __ldg(qb + (size_t)(j * 3 + c) * a.Bt);
+            for (int k = 0; k < 4; ++k) {
+              if (rl & (1u << k)) {
+                const float4* src = qb + (size_t)(((pack >> (6 * k)) & 63) * 3) * a.Bt;
+                const float4 A = __ldg(src), Bq = __ldg(src + a.Bt), C = __ldg(src + 2 * (size_t)a.Bt);
+                cq[k][0] = make_float2(A.x, A.y); cq[k][1] = make_float2(A.z, A.w);
+                cq[k][2] = make_float2(Bq.x, Bq.y); cq[k][3] = make_float2(Bq.z, Bq.w);
+                cq[k][4] = make_float2(C.x, C.y); cq[k][5] = make_float2(C.z, C.w);
+              }
             }
           }
-          const float x0 = fmaf(__uint_as_float(r[3 * u]), inv_scale, __uint_as_float(m4.y));
-          const float x1 = fmaf(__uint_as_float(r[3 * u + 1]), inv_scale, __uint_as_float(m4.z));
-          const float x2 = fmaf(__uint_as_float(r[3 * u + 2]), inv_scale, __uint_as_float(m4.w));
+          const float x0 = fmaf(__uint_as_float(r[3 * uu]), inv_scale, __uint_as_float(m4.y));
+          const float x1 = fmaf(__uint_as_float(r[3 * uu + 1]), inv_scale, __uint_as_float(m4.z));
+          const float x2 = fmaf(__uint_as_float(r[3 * uu + 2]), inv_scale, __uint_as_float(m4.w));
           float2 B2[6];
           {
             const float w = __uint_as_float(w4.x);
             const float2 ww = make_float2(w, w);
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              B2[2 * c] = __fmul2_rn(ww, make_float2(cq[0][c].x, cq[0][c].y));
-              B2[2 * c + 1] = __fmul2_rn(ww, make_float2(cq[0][c].z, cq[0][c].w));
-            }
+            for (int i = 0; i < 6; ++i) B2[i] = __fmul2_rn(ww, cq[0][i]);
           }
           const float wk[3] = {__uint_as_float(w4.y), __uint_as_float(w4.z), __uint_as_float(w4.w)};
 #pragma unroll
-          for (int k = 1; k < 4; ++k) {
-            if (wk[k - 1] != 0.f) {  // warp-uniform
-              const float2 ww = make_float2(wk[k - 1], wk[k - 1]);
+          for (int k = 1; k < 4; ++k) {  // unused slots carry weight 0 (and finite stale rows)
+            const float2 ww = make_float2(wk[k - 1], wk[k - 1]);
 #pragma unroll
-              for (int c = 0; c < 3; ++c) {
-                B2[2 * c] = __ffma2_rn(ww, make_float2(cq[k][c].x, cq[k][c].y), B2[2 * c]);
-                B2[2 * c + 1] = __ffma2_rn(ww, make_float2(cq[k][c].z, cq[k][c].w), B2[2 * c + 1]);
-              }
-            }
+            for (int i = 0; i < 6; ++i) B2[i] = __ffma2_rn(ww, cq[k][i], B2[i]);
           }
-          float* dst = stg + lane * PITCH + 3 * (pack >> 28);
-#pragma unroll
-          for (int c = 0; c < 3; ++c)
-            dst[c] = fmaf(B2[2 * c].x, x0, fmaf(B2[2 * c].y, x1, fmaf(B2[2 * c + 1].x, x2, B2[2 * c + 1].y)));
+          const float2 o01 = __ffma2_rn(B2[0], make_float2(x0, x0),
+                                        __ffma2_rn(B2[1], make_float2(x1, x1), __ffma2_rn(B2[2], make_float2(x2, x2), B2[3])));
+          const float o2 = fmaf(B2[4].x, x0, fmaf(B2[4].y, x1, fmaf(B2[5].x, x2, B2[5].y)));
+          float* dst = my_row + 3 * (pack >> 28);
+          dst[0] = o01.x;
+          dst[1] = o01.y;
+          dst[2] = o2;
+        }
         }
         __syncwarp();
-        // write-out: rows = instances tm*128 + q*32 + r, 3*CH contiguous floats each at vertex v0
-        const int b_row0 = tm * TILE_M + q * 32;
-        if (a.aligned8 && v0 + CH <= a.V) {
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
+        // write-out: rows = instances b_row0 + r, 3*CH contiguous floats each at vertex v0
+        float* gbase = a.out + ((size_t)b_row0 * a.V + v0) * 3;
+        const int nrows = a.B - b_row0;  // valid rows of this 32-instance block
+        if (v0 + CH <= a.V) {
+          if (a.aligned8) {
+            const size_t gstep = (size_t)4 * a.V * 3;
 #pragma unroll
             for (int t = 0; t < 3; ++t) {
-              const int rr = 4 * g + wo_row[t];
-              const int bb = b_row0 + rr;
-              const float2 v = *reinterpret_cast<const float2*>(stg + rr * PITCH + 2 * wo_e[t]);
-              if (bb < a.B) *reinterpret_cast<float2*>(a.out + ((size_t)bb * a.V + v0) * 3 + 2 * wo_e[t]) = v;
+              float* gp = gbase + wo8_g[t];
+              const float* sp = stg + wo8_s[t];
+              if (nrows >= 32) {
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                  *reinterpret_cast<float2*>(gp + g * gstep) = *reinterpret_cast<const float2*>(sp + 4 * g * PITCH);
+              } else {
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                  if (4 * g + wo8_r[t] < nrows)
+                    *reinterpret_cast<float2*>(gp + g * gstep) = *reinterpret_cast<const float2*>(sp + 4 * g * PITCH);
+              }
+            }
+          } else {
+            const size_t gstep = (size_t)2 * a.V * 3;
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+              float* gp = gbase + wo4_g[t];
+              const float* sp = stg + wo4_s[t];
+#pragma unroll
+              for (int g = 0; g < 16; ++g)
+                if (2 * g + wo4_r[t] < nrows) gp[g * gstep] = sp[2 * g * PITCH];
             }
           }
-        } else {
-          const int width = 3 * min(CH, a.V - v0);
+        } else {  // last, partial chunk of the model
+          const int width = 3 * (a.V - v0);
           for (int idx = lane; idx < 32 * width; idx += 32) {
             const int rr = idx / width, ee = idx - rr * width;
-            const int bb = b_row0 + rr;
-            if (bb < a.B) a.out[((size_t)bb * a.V + v0) * 3 + ee] = stg[rr * PITCH + ee];
+            if (b_row0 + rr < a.B) gbase[(size_t)rr * a.V * 3 + ee] = stg[rr * PITCH + ee];
           }
         }
         __syncwarp();
@@ -469,10 +579,11 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) k_fwd_prep2(const Prep2Args a
     float rj[3];
     mat3_vec(G, rest + j * 3, rj);
     if (a.quads != nullptr) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c)
-        a.quads[(size_t)(j * 3 + c) * a.Bt + b] =
-            make_float4(G[c * 3], G[c * 3 + 1], G[c * 3 + 2], (pos[j * 3 + c] - rj[c]) + tr[c]);
+      // pair layout of the fused epilogue: (G00,G10,G01,G11) (G02,G12,t0,t1) (G20,G21,G22,t2)
+      const float t0 = (pos[j * 3] - rj[0]) + tr[0], t1 = (pos[j * 3 + 1] - rj[1]) + tr[1], t2 = (pos[j * 3 + 2] - rj[2]) + tr[2];
+      a.quads[(size_t)(j * 3) * a.Bt + b] = make_float4(G[0], G[3], G[1], G[4]);
+      a.quads[(size_t)(j * 3 + 1) * a.Bt + b] = make_float4(G[2], G[5], t0, t1);
+      a.quads[(size_t)(j * 3 + 2) * a.Bt + b] = make_float4(G[6], G[7], G[8], t2);
     }
     if (live) {
       for (int e = 0; e < 9; ++e) a.out_orientations[((size_t)b * J + j) * 9 + e] = G[e];
@@ -593,19 +704,84 @@ int fwd_fused_run(const smplfit_model_t* m, int B, int rot_mode, const float* ro
     return fail(SMPLFIT_ERR_CUDA, "tensor map encode failed (forward)");
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(k_fwd_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
+    if (cudaFuncSetAttribute(k_fwd_fused<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<8>::SMEM_BYTES) != cudaSuccess) {
       cudaGetLastError();
       return fail(SMPLFIT_ERR_CUDA, "cannot reserve shared memory for k_fwd_fused");
     }
     attr_set = true;
   }
-  FusedArgs fa;
+  FusedArgs fa{};
   fa.quads = w.quads; fa.vrec = m->fwd_vrec; fa.out = out_vertices; fa.inv_scale = ldexpf(1.f, -m->fwd_scale_log2);
   fa.V = V; fa.B = B; fa.Bt = w.Bt; fa.k_blocks = m->fwd_kf / KB; fa.tiles_m = tiles_m; fa.total_tiles = tiles_m * tiles_n;
   fa.aligned8 = (V % 2 == 0) && ((reinterpret_cast<uintptr_t>(out_vertices) & 7) == 0);
   const int grid = fa.total_tiles < sm_count() ? fa.total_tiles : sm_count();
-  SF_LAUNCH(k_fwd_fused, grid, THREADS, SMEM_BYTES, st, maps, fa);
+  SF_LAUNCH((k_fwd_fused<0, 8>), grid, Cfg<8>::THREADS, Cfg<8>::SMEM_BYTES, st, maps, fa);
   return SMPLFIT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The fit's pose-blend contraction on the same main loop: v_posed^T [3V][Bp] = v_template_fit + posedirs_fit . vec(R_rel)
+// with the constants of smplfit_model_t::fit_P_* (rows in the fit's internal vertex order).
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+// feat [Bp][Kp] fp32 -> fp16 hi / lo [Bt][Kf], zero padded (rows >= Bp, columns >= Kp)
+__global__ void k_split_feat_h(const float* __restrict__ feat, int Bp, int Kp, int Kf, size_t n2, __half2* __restrict__ hi,
+                               __half2* __restrict__ lo) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n2) return;
+  const int k2 = (int)(idx % (Kf / 2));
+  const size_t b = idx / (Kf / 2);
+  float x[2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int k = 2 * k2 + t;
+    x[t] = (k < Kp && b < (size_t)Bp) ? feat[b * Kp + k] : 0.f;
+  }
+  const __half h0 = __float2half_rn(x[0]), h1 = __float2half_rn(x[1]);
+  hi[idx] = __halves2half2(h0, h1);
+  lo[idx] = __halves2half2(__float2half_rn(x[0] - __half2float(h0)), __float2half_rn(x[1] - __half2float(h1)));
+}
+}  // namespace
+
+bool vposed_f16_available(const smplfit_model_t* m) {
+  return m->fit_P_hi != nullptr && m->fit_P_lo != nullptr && m->fit_kf > 0 && m->fit_kf % KB == 0 && encode_fn() != nullptr;
+}
+
+size_t vposed_f16_scratch_bytes(const smplfit_model_t* m, int Bp) {
+  if (!m->fit_P_hi || m->fit_kf <= 0) return 0;
+  return (size_t)2 * roundup(Bp, TILE_M) * m->fit_kf * sizeof(__half) + 512;
+}
+
+bool vposed_f16_run(const smplfit_model_t* m, const float* feat, float* vposedT, int Bp, int Kp, void* scratch,
+                    cudaStream_t st) {
+  if (!vposed_f16_available(m) || scratch == nullptr) return false;
+  const int Bt = roundup(Bp, TILE_M), Kf = m->fit_kf, rows = 3 * m->num_vertices;
+  __half* hi = reinterpret_cast<__half*>(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
+  __half* lo = hi + (size_t)Bt * Kf;
+  const int tiles_n = (rows + TILE_N - 1) / TILE_N, tiles_m = Bt / TILE_M;
+  FusedMaps maps;
+  if (!make_h_map(&maps.f_hi, hi, (uint64_t)Bt, (uint64_t)Kf, TILE_M) || !make_h_map(&maps.f_lo, lo, (uint64_t)Bt, (uint64_t)Kf, TILE_M) ||
+      !make_h_map(&maps.p_hi, m->fit_P_hi, (uint64_t)tiles_n * TILE_N, (uint64_t)Kf, TILE_N) ||
+      !make_h_map(&maps.p_lo, m->fit_P_lo, (uint64_t)tiles_n * TILE_N, (uint64_t)Kf, TILE_N))
+    return false;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(k_fwd_fused<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<8>::SMEM_BYTES) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    attr_set = true;
+  }
+  const size_t n2 = (size_t)Bt * (Kf / 2);
+  SF_LAUNCH(k_split_feat_h, (unsigned)((n2 + 255) / 256), 256, 0, st, feat, Bp, Kp, Kf, n2, reinterpret_cast<__half2*>(hi),
+            reinterpret_cast<__half2*>(lo));
+  FusedArgs fa{};
+  fa.out = vposedT; fa.bias = m->v_template_fit; fa.inv_scale = ldexpf(1.f, -m->fit_scale_log2);
+  fa.V = m->num_vertices; fa.B = Bp; fa.Bt = Bt; fa.k_blocks = Kf / KB; fa.tiles_m = tiles_m; fa.total_tiles = tiles_m * tiles_n;
+  fa.rows = rows; fa.Bp = Bp;
+  const int grid = fa.total_tiles < sm_count() ? fa.total_tiles : sm_count();
+  SF_LAUNCH((k_fwd_fused<1, 8>), grid, Cfg<8>::THREADS, Cfg<8>::SMEM_BYTES, st, maps, fa);
+  return true;
 }
 
 }  // namespace sf

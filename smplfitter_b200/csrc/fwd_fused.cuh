@@ -23,4 +23,9 @@ int fwd_fused_run(const smplfit_model_t* m, int B, int rot_mode, const float* ro
                   const float* trans, const float* kid, float* out_vertices, float* out_joints, float* out_orientations,
                   const FwdFusedWs& w, cudaStream_t st);
 
+// the fit's v_posed^T GEMM on the same fp16-split main loop (feat: [Bp][Kp] fp32 rows vec(R_rel[1:]))
+bool vposed_f16_available(const smplfit_model_t* m);
+size_t vposed_f16_scratch_bytes(const smplfit_model_t* m, int Bp);
+bool vposed_f16_run(const smplfit_model_t* m, const float* feat, float* vposedT, int Bp, int Kp, void* scratch, cudaStream_t st);
+
 }  // namespace sf

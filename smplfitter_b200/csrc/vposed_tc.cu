@@ -26,6 +26,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "fwd_fused.cuh"
 #include "vposed_tc.cuh"
 
 namespace sf {
@@ -459,7 +460,18 @@ bool tc_gemm_run_f32(const float* p, int rows, int p_ld, const float* bias, cons
 size_t vposed_tc_scratch_bytes(const smplfit_model_t* m, int Bp) {
   const int Kt = roundup(m->num_pose_feats, K_PAD);
   const int Bt = roundup(Bp, TILE_M);
-  return (size_t)2 * Bt * Kt * sizeof(float) + 512;
+  const size_t tf32 = (size_t)2 * Bt * Kt * sizeof(float) + 512, f16 = vposed_f16_scratch_bytes(m, Bp);
+  return tf32 > f16 ? tf32 : f16;
+}
+
+// SMPLFIT_B200_GEMM=tf32: the 3xTF32 kernel of this file instead of the fp16-split main loop of fwd_fused.cu (A/B runs)
+static bool tf32_forced() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SMPLFIT_B200_GEMM");
+    v = (e && strcmp(e, "tf32") == 0) ? 1 : 0;
+  }
+  return v == 1;
 }
 
 static bool vposed_tc_run_with(const smplfit_model_t* m, const float* p_hi, const float* p_lo, const float* bias,
@@ -467,6 +479,7 @@ static bool vposed_tc_run_with(const smplfit_model_t* m, const float* p_hi, cons
 
 bool vposed_tc_run(const smplfit_model_t* m, const float* feat, float* vposedT, int Bp, int Kp, void* scratch,
                    cudaStream_t st) {
+  if (tc_enabled() && !tf32_forced() && vposed_f16_run(m, feat, vposedT, Bp, Kp, scratch, st)) return true;
   // fp32 operands, split in shared memory: posedirs_fit is [3V][Kp], feat [Bp][Kp]
   if (m->posedirs_fit != nullptr && encode_fn() != nullptr &&
       tc_gemm_run_f32(m->posedirs_fit, 3 * m->num_vertices, Kp, m->v_template_fit, feat, Bp, Kp, m->num_pose_feats, vposedT,

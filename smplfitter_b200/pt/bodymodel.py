@@ -152,6 +152,17 @@ class BodyModel(nn.Module):
         pd[:, :P] = posedirs_fit[:, :P]
         pd_hi = (pd.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)  # tf32-exact part
         pd_lo = pd - pd_hi
+        # the same rows for the fp16-split tensor-core GEMM (csrc/fwd_fused.cu, MODE 1): scaled into fp16's normal
+        # range, hi = fp16(x), lo = fp16(x - hi); rows padded to the 192-row tile
+        kf = (P + 31) // 32 * 32
+        pf = np.zeros(((V * 3 + 191) // 192 * 192, kf), np.float64)
+        pf[:V * 3, :P] = posedirs_fit[:, :P]
+        amax = float(np.abs(pf).max())
+        self._fit_scale_log2 = int(np.clip(np.floor(np.log2(16384.0 / amax)) if amax > 0 else 0, 0, 14))
+        pf *= 2.0 ** self._fit_scale_log2
+        pf_hi = pf.astype(np.float16)
+        pf_lo = (pf - pf_hi.astype(np.float64)).astype(np.float16)
+        self._fit_kf = kf
         eye_feat = np.tile(np.eye(3, dtype=np.float32), [J - 1, 1]).reshape(-1)
         v_posed0 = self.v_template.numpy() + np.einsum('vcp,p->vc', self.posedirs.numpy(), eye_feat)
         template_mesh = (v_posed0 * w32.sum(axis=1, keepdims=True)).astype(np.float32)  # pt/bodyfitter.py:49
@@ -169,6 +180,7 @@ class BodyModel(nn.Module):
             'template_joints_regressed': f32(jreg @ template_mesh),
             'J_regressor_fit': f32(jreg[:, order]),
             'posedirs_hi': f32(pd_hi), 'posedirs_lo': f32(pd_lo),
+            'fit_P_hi': torch.from_numpy(pf_hi), 'fit_P_lo': torch.from_numpy(pf_lo),
             'template_mesh_fit': f32(template_mesh[order]),
         }
         if K <= 4 and J <= 64:
@@ -199,17 +211,18 @@ class BodyModel(nn.Module):
         the vertex needing the fewest new joints; a new joint evicts the slot whose joint is needed latest)."""
         V, J, S = self.num_vertices, self.num_joints, self.num_betas
         P = 9 * (J - 1)
-        CH, TILE, CPW = 16, 64, 2  # FWD_CHUNK, TILE_V and chunks per epilogue warp of csrc/fwd_fused.cu
+        CH, TILE = 16, 64  # FWD_CHUNK and TILE_V of csrc/fwd_fused.cu
         Vp = (V + TILE - 1) // TILE * TILE
         joints_of = [[(int(j), float(w)) for j, w in zip(skin_idx[v], skin_w[v]) if w != 0] for v in range(V)]
         rec = np.zeros((Vp, 8), np.uint32)
         proc = np.full(Vp, -1, np.int64)  # processing position -> model vertex (-1: padding)
+        # one sequential replay of the cache over the whole processing order: every record carries the cache content
+        # AFTER its vertex (the joint of each slot), so a warp entering the order anywhere loads all four slots from the
+        # record of its first vertex (the kernel does that at the start of its share of every tile)
+        cache = [-1, -1, -1, -1]
         for c0 in range(0, Vp, CH):
             todo = [v for v in range(c0, min(c0 + CH, V))]
             pos = c0
-            first = (c0 // CH) % CPW == 0  # a warp keeps its cache over the CPW consecutive chunks it takes from a tile
-            if first:
-                cache = [-1, -1, -1, -1]
             while todo:
                 # fewest joints missing from the cache; ties: lowest vertex index
                 v = min(todo, key=lambda u: (sum(1 for j, _ in joints_of[u] if j not in cache), u))
@@ -225,12 +238,6 @@ class BodyModel(nn.Module):
                                                   sum(1 for u in todo for jj, _ in joints_of[u] if jj == cache[kk]), kk))
                     cache[k] = j
                     reload |= 1 << k
-                if first:  # nothing is cached across tiles (the next tile belongs to other instances)
-                    reload = 0
-                    for k in range(4):
-                        if cache[k] in need:
-                            reload |= 1 << k
-                    first = False
                 w = np.zeros(4, np.float32)
                 for j, ww in joints_of[v]:
                     w[cache.index(j)] = ww
@@ -245,7 +252,10 @@ class BodyModel(nn.Module):
                 proc[pos] = v
                 pos += 1
             for q in range(pos, c0 + CH):  # padding of the last chunk(s): zero weights, distinct local indices
-                rec[q, 4] = (q - c0) << 28
+                pack = 0
+                for k in range(4):
+                    pack |= (max(cache[k], 0) & 63) << (6 * k)
+                rec[q, 4] = pack | ((q - c0) << 28)
         Kf = (P + S + 1 + 31) // 32 * 32
         pm = np.zeros((Vp * 3, Kf), np.float64)
         live = proc >= 0
@@ -281,12 +291,13 @@ class BodyModel(nn.Module):
         for name in ('parents', 'skin_idx', 'skin_w', 'order', 'inv_order', 'seg_start', 'seg_part',
                      'part_seg_begin', 'part_kind', 'part_copy_src', 'part_flags', 'cas_table', 'cas_count',
                      'posedirs_fit', 'v_template_fit', 'template_mesh', 'template_joints_regressed',
-                     'J_regressor_fit', 'posedirs_hi', 'posedirs_lo', 'template_mesh_fit'):
+                     'J_regressor_fit', 'posedirs_hi', 'posedirs_lo', 'template_mesh_fit', 'fit_P_hi', 'fit_P_lo'):
             setattr(s, name, getattr(self, '_t_' + name).data_ptr())
         for name, buf in self.named_buffers():
             if not buf.is_contiguous():
                 raise RuntimeError(f'smplfitter_b200: buffer {name} must be contiguous')
         s.fit_ns = 0
+        s.fit_kf, s.fit_scale_log2 = self._fit_kf, self._fit_scale_log2
         if hasattr(self, '_t_fwd_P_hi'):
             s.fwd_P_hi, s.fwd_P_lo, s.fwd_vrec = (self._t_fwd_P_hi.data_ptr(), self._t_fwd_P_lo.data_ptr(),
                                                   self._t_fwd_vrec.data_ptr())
