@@ -469,7 +469,15 @@ def main():
     if args.resident_only:
         if rank == 0:
             sampler.stop()
+            _native.profile(True)
+            torch.cuda.synchronize(dev)
+            for _ in range(3):
+                step_resident()
+            torch.cuda.synchronize(dev)
+            _native.profile(False)
+            kprof = _native.profile_report()
             print(json.dumps({'resident_only': True, 'ms_per_step': ms / args.steps, 'gpu_launches': int(launches),
+                              'kernel_ms_per_step': {k: round(v[1] / 3, 5) for k, v in sorted(kprof.items(), key=lambda kv: -kv[1][1])},
                               'note': 'profiling run, not a bench line'}))
         if world > 1:
             dist.destroy_process_group()

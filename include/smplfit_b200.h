@@ -144,6 +144,20 @@ typedef struct smplfit_model {
   const uint16_t* fit_P_lo;
   int32_t fit_kf;               /* roundup(P, 32) */
   int32_t fit_scale_log2;
+  /* ---- fused fit passes (k_fit_fused, csrc/fit_fused.cu): the blend-shape GEMM with the shape-stage / statistics
+   * vertex pass in its epilogue, so that the posed template never exists in HBM.  Statistics segment q (<= 32 vertices,
+   * seg_start / seg_part above) owns the padded vertex slots [32 q, 32 q + 32); a GEMM tile is two segments.
+   * Fitter-level tables (they depend on NS).  All NULL / 0 disables the path. */
+  const uint16_t* fq_P_hi;      /* (fq_nseg_pad * 96, fq_kf) 2^fq_scale_log2 [posedirs | fit_shapedirs] rows in slot order, fp16 high part */
+  const uint16_t* fq_P_lo;      /* same shape: remainder */
+  const uint32_t* fq_rec;       /* (fq_nseg_pad * 32, 8) per slot: 4 skin weights (float bits, descending) | pack | v_rest[3];
+                                   pack = 4 x 6-bit joint of slot k | reload mask (bits 24-27: slot k takes another joint here,
+                                   along the chain of segments of the same parity) | valid (bit 28) */
+  const float* fq_sd;           /* (fq_nseg_pad * 32, fq_sdl) shapedirs[x][s] at x * NSP + s, NSP = NS rounded up to even */
+  int32_t fq_kf;                /* K of the GEMM: roundup(P + NS, 32); feature order [vec(R_rel[1:] - I) | unknowns] */
+  int32_t fq_scale_log2;
+  int32_t fq_sdl;               /* roundup(3 NSP, 4) */
+  int32_t fq_nseg_pad;          /* n_segments rounded up to even */
 } smplfit_model_t;
 
 /* Options of BodyFitter.fit (pt/bodyfitter.py:283-302). */

@@ -83,6 +83,7 @@ KNOWN_POSE_CASES = {
     'kpose_tiny_kid_nojoints': ('smpl_tiny', dict(enable_kid=True), 3,
                                 dict(beta_regularizer=0.0, kid_regularizer=1e9), dict(joints=False)),
     'kpose_tiny_scale_target': ('smpl_tiny', {}, 3, dict(beta_regularizer=1.0, scale_target=True), dict(joints=True)),
+    'kpose_tiny_share_beta': ('smpl_tiny', {}, 4, dict(beta_regularizer=1.0, share_beta=True), dict(joints=True, same_betas=True)),
 }
 KNOWN_SHAPE_CASES = {
     'kshape_tiny': ('smpl_tiny', {}, 4, dict(num_iter=2, final_adjust_rots=True), dict(joints=True)),
@@ -119,6 +120,8 @@ def case_inputs(name, model_name, mkw, B, pose_scale, noise, flags, seed):
         betas = np.repeat(betas[:1], B, axis=0)
     trans = rs.randn(B, 3).astype(np.float32)
     inp = dict(pose=pose, betas=betas, trans=trans)
+    if flags.get('same_betas'):
+        inp['betas'][:] = inp['betas'][:1]
     if flags.get('vw'):
         inp['vw'] = rs.uniform(0.2, 1.5, size=(B, V)).astype(np.float32)
     if flags.get('jw'):
@@ -165,6 +168,8 @@ def aux_inputs(mname, B, flags, seed):
     rs = np.random.RandomState(seed)
     inp = dict(pose=(rs.randn(B, 3 * J) * 0.3).astype(np.float32), betas=(rs.randn(B, S) * 0.7).astype(np.float32),
                trans=rs.randn(B, 3).astype(np.float32))
+    if flags.get('same_betas'):
+        inp['betas'][:] = inp['betas'][:1]
     if flags.get('vw'):
         inp['vw'] = rs.uniform(0.2, 1.5, size=(B, V)).astype(np.float32)
     if flags.get('jw'):

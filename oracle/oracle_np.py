@@ -619,7 +619,7 @@ class OracleFitter:
                             joint_weights=None, beta_regularizer=1, beta_regularizer2=0,
                             scale_regularizer=0, kid_regularizer=None, scale_target=False,
                             scale_fit=False, beta_regularizer_reference=None,
-                            kid_regularizer_reference=None):
+                            kid_regularizer_reference=None, share_beta=False):
         m = self.m
         t = np.asarray(target_vertices, F32)
         tj = None if target_joints is None else np.asarray(target_joints, F32)
@@ -632,7 +632,7 @@ class OracleFitter:
         glob = m.forward(pose_rotvecs=pose_rotvecs, return_vertices=False)['orientations']
         res = self.fit_shape(glob, t, tj, vertex_weights, joint_weights, beta_regularizer,
                              beta_regularizer2, scale_regularizer, kid_regularizer, scale_target,
-                             scale_fit, beta_regularizer_reference, kid_regularizer_reference)
+                             scale_fit, beta_regularizer_reference, kid_regularizer_reference, share_beta)
         res['trans'] = res['trans'] + mean
         res.pop('vertices')
         res.pop('joints')

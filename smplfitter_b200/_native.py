@@ -46,6 +46,8 @@ class ModelStruct(C.Structure):
         + [('gcf_AT_hi', _F), ('gcf_AT_lo', _F), ('posedirs_model_hi', _F), ('posedirs_model_lo', _F), ('posedirs_model_f32', _F), ('fit_slot_mask', _F)]
         + [('fwd_P_hi', _F), ('fwd_P_lo', _F), ('fwd_vrec', _F), ('fwd_kf', C.c_int32), ('fwd_scale_log2', C.c_int32)]
         + [('fit_P_hi', _F), ('fit_P_lo', _F), ('fit_kf', C.c_int32), ('fit_scale_log2', C.c_int32)]
+        + [('fq_P_hi', _F), ('fq_P_lo', _F), ('fq_rec', _F), ('fq_sd', _F), ('fq_kf', C.c_int32),
+           ('fq_scale_log2', C.c_int32), ('fq_sdl', C.c_int32), ('fq_nseg_pad', C.c_int32)]
     )
 
 

@@ -7,6 +7,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "fit_fused.cuh"
 #include "fit_kernels.cuh"
 #include "lite_kernels.cuh"
 #include "passes.cuh"
@@ -27,6 +28,7 @@ struct FitWs {
       *skin, *spart, *aT, *ajT, *initjT, *RT4, *zpart, *scale, *mpart, *RT12, *gcfpart, *skin4, *pairfeat;
   double *Zd, *Cd, *sums, *Yd;
   void* tc_scratch;
+  void* fq_scratch;
   size_t bytes;
 };
 
@@ -148,6 +150,7 @@ static FitWs carve(void* base, const smplfit_model_t* m, int64_t B, int has_join
   w.scale = c.take<float>(Bp);
   w.mpart = c.take<float>((size_t)(moment_blocks(V) + 1) * 9 * Bp);
   w.tc_scratch = c.take<char>(vposed_tc_scratch_bytes(m, (int)Bp));
+  w.fq_scratch = fit_fused_available(m) ? c.take<char>(fit_fused_scratch_bytes(m, (int)Bp)) : nullptr;
   w.bytes = c.off + 256;
   return w;
 }
@@ -184,6 +187,8 @@ struct FitCtx {
   const float *vwT_shape, *jwT_shape;  // shape-stage weights (pt/bodyfitter.py:1018-1028)
   bool has_joints, use_rec;
   bool lite;  // closed-form Gramian + light vertex pass (unweighted shape stage)
+  bool fused;         // vertex passes in the epilogue of the blend-shape GEMM (fit_fused.cu): no v_posed^T in HBM
+  bool vposed_valid;  // w.vposedT holds the posed template of the current orientations (non-fused consumers)
   ShapePlan plan;
 };
 
@@ -197,6 +202,7 @@ static void choose_shape_path(FitCtx& c, RotArgs& ra) {
 
 static void run_gemm(FitCtx& c) {
   const smplfit_model_t* m = c.m;
+  c.vposed_valid = true;
   if (vposed_tc_run(m, c.w.feat, c.w.vposedT, c.Bp, c.Kp, c.w.tc_scratch, c.st)) return;
   dim3 grid((3 * m->num_vertices + 127) / 128, (c.Bp + 63) / 64);
   SF_LAUNCH(k_vposed_gemm_simt, grid, 256, 0, c.st, m->posedirs_fit, m->v_template_fit, c.w.feat,
@@ -222,7 +228,11 @@ static void run_shape(FitCtx& c, int scale_mode, const float* beta_ref, const fl
     if (side) cudaEventRecord(side->join, side->stream);
   };
   if (c.lite && side_mode != 2) gram();
-  run_gemm(c);
+  bool shape_fused = false;
+  if (c.lite && c.fused && scale_mode == 0)  // (the scale pass of the final solve reads v_posed^T)
+    shape_fused = fit_fused_run(m, 2, c.B, c.Bp, c.w.feat, c.Kp, nullptr, c.w.tT, nullptr, c.w.RT12, nullptr, nullptr, nullptr, 0,
+                                c.w.gpart, c.w.fq_scratch, c.st);
+  if (!shape_fused) run_gemm(c);
   if (c.lite && side_mode == 2) gram();
   ShapeArgs sa;
   sa.tT = c.w.tT; sa.vwT = c.vwT_shape; sa.vposedT = c.w.vposedT; sa.RT = c.w.RT;
@@ -235,7 +245,8 @@ static void run_shape(FitCtx& c, int scale_mode, const float* beta_ref, const fl
     la.tT = c.w.tT; la.vposedT = c.w.vposedT; la.RT12 = c.w.RT12; la.rec = m->fit_rec; la.seg_start = m->seg_start;
     la.seg_slots = m->seg_slots; la.partials = c.w.gpart; la.n_segments = m->n_segments; la.J = m->num_joints;
     la.Bp = c.Bp; la.segs_per_warp = 1; la.slot_mask = slot_mask_enabled() ? m->fit_slot_mask : nullptr;
-    launch_shape_lite(la, m, c.groups, c.w.Yd, c.st);
+    if (shape_fused) launch_lite_reduce(la, m, c.groups, c.w.Yd, c.st);
+    else launch_shape_lite(la, m, c.groups, c.w.Yd, c.st);
     if (side) cudaStreamWaitEvent(c.st, side->join, 0);
     so.lite = 1; so.lite_nl = lite_rows(m->fit_ns); so.n_gcf = gram_closed_blocks(m); so.gcf_part = c.w.gcfpart;
     so.G0 = m->gcf_G0; so.Yd = c.w.Yd;
@@ -291,6 +302,11 @@ static void run_stats(FitCtx& c, int ref_mode, const float* ca0T, const float* a
     launch_stats_tmpl(l, m, m->template_mesh_fit, m->J_template, c.groups, c.st);
     return;
   }
+  if (ref_mode == 1 && c.fused &&
+      fit_fused_run(m, 3, c.B, c.Bp, c.w.feat, c.Kp, c.w.beta, c.w.tT, c.w.vwT, c.w.skin4, c.w.tjT, ca0T, aT_out,
+                    aT_out != nullptr, c.w.spart, c.w.fq_scratch, c.st))
+    return;
+  if (ref_mode == 1 && !c.vposed_valid) run_gemm(c);
   if (ref_mode == 1 && stats_lite_enabled(m)) {
     StatsLiteArgs l;
     l.tT = c.w.tT; l.vwT = c.w.vwT; l.ct0 = c.w.tjT; l.ca0 = ca0T; l.vposedT = c.w.vposedT; l.beta = c.w.beta;
@@ -316,6 +332,7 @@ static void run_regress(FitCtx& c, const float* X, float* out) {
 // rotation fit per (instance, part), then the pose-dependent front of the next shape solve
 static void run_rot(FitCtx& c, const RotArgs& ra, bool fit) {
   const int J = c.m->num_joints;
+  c.vposed_valid = false;
   if (fit) SF_LAUNCH(k_rot_fit, dim3(c.groups, J), 32, 0, c.st, ra);
   SF_LAUNCH(k_front_rel, dim3(c.groups, J), 32, 0, c.st, ra);
   SF_LAUNCH(k_front_fk, dim3(c.groups, c.m->fit_ns + 1), 32, 0, c.st, ra);
@@ -414,6 +431,8 @@ extern "C" int smplfit_fit(const smplfit_model_t* m, int64_t batch, const float*
   c.has_joints = has_joints;
   c.plan = plan_shape_pass(m, c.groups);
   c.use_rec = c.plan.use_rec;
+  c.fused = fit_fused_available(m);
+  c.vposed_valid = false;
   c.w = carve(workspace, m, batch, has_joints, vertex_weights != nullptr, joint_weights != nullptr, has_init);
   if (!workspace || c.w.bytes > workspace_bytes) return fail(SMPLFIT_ERR_WORKSPACE, "workspace too small");
   FitWs& w = c.w;
@@ -508,6 +527,8 @@ extern "C" int smplfit_fit_known_pose(const smplfit_model_t* m, int64_t batch, c
   if (batch <= 0 || batch > (1 << 24)) return fail(SMPLFIT_ERR_ARG, "batch out of range");
   if (o->scale_mode < 0 || o->scale_mode > 2) return fail(SMPLFIT_ERR_ARG, "bad scale_mode");
   if (o->scale_mode != 0 && !out_scale_corr) return fail(SMPLFIT_ERR_ARG, "scale_corr output required");
+  if (o->scale_mode != 0 && o->share_beta)
+    return fail(SMPLFIT_ERR_UNSUPPORTED, "share_beta together with scale estimation is not implemented");
   if ((o->enable_kid != 0) != (m->fit_ns == m->num_betas + 1))
     return fail(SMPLFIT_ERR_ARG, "enable_kid does not match the fitter tables");
   const bool has_joints = target_joints != nullptr;
@@ -522,6 +543,8 @@ extern "C" int smplfit_fit_known_pose(const smplfit_model_t* m, int64_t batch, c
   c.has_joints = has_joints;
   c.plan = plan_shape_pass(m, c.groups);
   c.use_rec = c.plan.use_rec;
+  c.fused = fit_fused_available(m);
+  c.vposed_valid = false;
   c.w = carve(workspace, m, batch, has_joints, vertex_weights != nullptr, joint_weights != nullptr, 1);
   if (!workspace || c.w.bytes > workspace_bytes) return fail(SMPLFIT_ERR_WORKSPACE, "workspace too small");
   FitWs& w = c.w;
@@ -606,6 +629,8 @@ extern "C" int smplfit_fit_known_shape(const smplfit_model_t* m, int64_t batch, 
   c.has_joints = has_joints;
   c.plan = plan_shape_pass(m, c.groups);
   c.use_rec = c.plan.use_rec;
+  c.fused = fit_fused_available(m);
+  c.vposed_valid = false;
   c.w = carve(workspace, m, batch, has_joints, vertex_weights != nullptr, joint_weights != nullptr, 1);
   if (!workspace || c.w.bytes > workspace_bytes) return fail(SMPLFIT_ERR_WORKSPACE, "workspace too small");
   FitWs& w = c.w;
@@ -650,7 +675,6 @@ extern "C" int smplfit_fit_known_shape(const smplfit_model_t* m, int64_t batch, 
   for (int it = 0; it < o->num_iter; ++it) {
     const bool last = (it == o->num_iter - 1);
     SF_LAUNCH(k_shape_out, dim3(c.groups, J), 32, 0, c.st, so, m->fit_ns);
-    run_gemm(c);
     run_stats(c, 1, w.refj, nullptr, w.aT);  // reference vertices skinned on the fly, stored for the moments
     aj = w.refj;
     if (!has_joints) {

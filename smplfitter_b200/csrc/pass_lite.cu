@@ -180,6 +180,13 @@ static void lite_t(const LiteArgs& a, const smplfit_model_t* m, int groups, doub
   SF_LAUNCH(k_lite_reduce, dim3(groups, m->num_joints), 32, 0, st, ra);
 }
 
+void launch_lite_reduce(const LiteArgs& a, const smplfit_model_t* m, int groups, double* Yd, cudaStream_t st) {
+  LiteReduceArgs ra;
+  ra.partials = a.partials; ra.yj_start = m->yj_start; ra.yj_entry = m->yj_entry; ra.Yd = Yd; ra.NL = lite_rows(m->fit_ns);
+  ra.NS = m->fit_ns; ra.Bp = a.Bp;
+  SF_LAUNCH(k_lite_reduce, dim3(groups, m->num_joints), 32, 0, st, ra);
+}
+
 void launch_shape_lite(const LiteArgs& a, const smplfit_model_t* m, int groups, double* Yd, cudaStream_t st) {
   SF_NS_SWITCH(m->fit_ns, (lite_t<NS>(a, m, groups, Yd, st)));
 }

@@ -34,6 +34,8 @@ size_t gram_pairs_scratch_floats(const smplfit_model_t* m, int Bp);  // pair fea
 // the vertex pass (r, Sb, Y) + its per-joint reduction, and -- independent of it -- the Gramian from the joint
 // transforms (pair term on tcgen05 + translation terms); fit.cu runs the latter on a side stream
 void launch_shape_lite(const LiteArgs& a, const smplfit_model_t* m, int groups, double* Yd, cudaStream_t st);
+// the per-joint reduction alone (the fused pass of fit_fused.cu has written the partials)
+void launch_lite_reduce(const LiteArgs& a, const smplfit_model_t* m, int groups, double* Yd, cudaStream_t st);
 void launch_gram_closed(const smplfit_model_t* m, int groups, int Bp, const float* RT, float* gcf_part, float* pair_scratch,
                         cudaStream_t st);
 // statistics pass against the skinned current fit in the same style (SMPLFIT_B200_STATS_VARIANT=0 selects k_stats_rec)

@@ -70,6 +70,12 @@ class BodyFitter(nn.Module):
         self.register_buffer('_t_fit_shapedirs', sd.contiguous().clone(), persistent=False)
         self.J_template_ext = nn.Buffer(torch.cat(jt, dim=2).contiguous())
         self._ns = S + (1 if enable_kid else 0)
+        if self._ns > 17:
+            raise NotImplementedError(
+                f'smplfitter_b200.BodyFitter solves for at most 17 shape unknowns (betas + kid); this body model has '
+                f'{S} betas{" + kid" if enable_kid else ""}. Construct the BodyModel with num_betas<=16 '
+                f"(e.g. BodyModel('{body_model.model_name}', num_betas=16)); the reference solves all {S}, so a "
+                'truncated model is a different (smaller) least-squares problem, not an approximation made silently.')
         # packed per-vertex records (internal order) and the closed-form SA constants
         ns = self._ns
         order = body_model._t_order.cpu().numpy()
@@ -114,9 +120,11 @@ class BodyFitter(nn.Module):
                     mask[i] = m
             self.register_buffer('_t_fit_slot_mask', torch.tensor(mask), persistent=False)
             self._build_pair_constants(idx4, w4, sd_np, J, ns)
+            self._build_fused_tables(idx_o, w_o, sd_np[order], order, seg_start, ns)
         else:
             self._t_fit_rec = None
             self._gcf_npairs = 0
+            self._fq = None
         self._handle = _ops.register(self)
         self.to(body_model.v_template.device)
 
@@ -185,6 +193,68 @@ class BodyFitter(nn.Module):
         self._gcf_npairs = len(off)
 
     @torch.jit.unused
+    def _build_fused_tables(self, idx_o, w_o, sd_o, order, seg_start, ns):
+        """Constants of the fused fit passes (include/smplfit_b200.h ``fq_*``; csrc/fit_fused.cu): segment q owns the
+        padded vertex slots [32 q, 32 q + 32); the GEMM constants are [posedirs | shapedirs (+ kid)] rows in slot order,
+        scaled into fp16's normal range and split hi / lo; the slot records carry the skinning weights, the joints of the
+        four register-cached slots and the bits saying which slots reload -- replayed here along the chain of segments
+        one epilogue warp walks (every second segment)."""
+        bm = self.body_model
+        J, V = bm.num_joints, bm.num_vertices
+        if J > 64 or int(np.max(np.diff(seg_start))) > 32:
+            self._fq = None
+            return
+        P = 9 * (J - 1)
+        nseg = len(seg_start) - 1
+        nseg_pad = (nseg + 1) // 2 * 2
+        slot_of = np.full(nseg_pad * 32, -1, np.int64)  # slot -> internal vertex position
+        for q in range(nseg):
+            a, b = int(seg_start[q]), int(seg_start[q + 1])
+            slot_of[32 * q:32 * q + (b - a)] = np.arange(a, b)
+        live = slot_of >= 0
+        eye_feat = np.tile(np.eye(3), [J - 1, 1]).reshape(-1)
+        pd = bm.posedirs.cpu().numpy().astype(np.float64)[order]  # (V,3,P) internal order
+        v_rest = bm.v_template.cpu().numpy().astype(np.float64)[order] + np.einsum('vcp,p->vc', pd, eye_feat)
+        rec = np.zeros((nseg_pad * 32, 8), np.uint32)
+        for h in range(2):
+            cached = [-1, -1, -1, -1]
+            for q in range(h, nseg, 2):
+                for i in range(int(seg_start[q]), int(seg_start[q + 1])):
+                    m = 0
+                    for k in range(4):
+                        if w_o[i, k] != 0 and idx_o[i, k] != cached[k]:
+                            cached[k] = int(idx_o[i, k])
+                            m |= 1 << k
+                    pack = (m << 24) | (1 << 28)
+                    for k in range(4):
+                        pack |= (max(cached[k], 0) & 63) << (6 * k)
+                    s_ = 32 * q + (i - int(seg_start[q]))
+                    rec[s_, 0:4] = w_o[i].astype(np.float32).view(np.uint32)
+                    rec[s_, 4] = pack
+                    rec[s_, 5:8] = v_rest[i].astype(np.float32).view(np.uint32)
+        nsp = (ns + 1) // 2 * 2
+        sdl = (3 * nsp + 3) // 4 * 4
+        sd = np.zeros((nseg_pad * 32, sdl), np.float32)
+        for x in range(3):
+            sd[live, x * nsp:x * nsp + ns] = sd_o[slot_of[live], x, :]
+        kf = (P + ns + 31) // 32 * 32
+        pm = np.zeros((nseg_pad * 32, 3, kf), np.float64)
+        pm[live, :, :P] = pd[slot_of[live]]
+        pm[live, :, P:P + ns] = sd_o[slot_of[live]].astype(np.float64)
+        pm = pm.reshape(nseg_pad * 96, kf)
+        amax = float(np.abs(pm).max())
+        scale_log2 = int(np.clip(np.floor(np.log2(16384.0 / amax)) if amax > 0 else 0, 0, 14))
+        pm *= 2.0 ** scale_log2
+        hi = pm.astype(np.float16)
+        lo = (pm - hi.astype(np.float64)).astype(np.float16)
+        reg = lambda n, t: self.register_buffer(n, t, persistent=False)  # noqa: E731
+        reg('_t_fq_P_hi', torch.from_numpy(hi))
+        reg('_t_fq_P_lo', torch.from_numpy(lo))
+        reg('_t_fq_rec', torch.from_numpy(rec.view(np.int32)))
+        reg('_t_fq_sd', torch.from_numpy(sd))
+        self._fq = dict(fq_kf=kf, fq_scale_log2=scale_log2, fq_sdl=sdl, fq_nseg_pad=nseg_pad)
+
+    @torch.jit.unused
     def _struct(self) -> _native.ModelStruct:
         gcf = {}
         if self._gcf_npairs > 0:
@@ -192,8 +262,11 @@ class BodyFitter(nn.Module):
                        **{n: getattr(self, '_t_' + n).data_ptr() for n in
                           ('gcf_pairs', 'gcf_A', 'gcf_G0', 'gcf_lstart', 'gcf_lk', 'gcf_Bm', 'gcf_Wh', 'gcf_AT_hi',
                            'gcf_AT_lo')})
+        fq = {}
+        if self._fq is not None:
+            fq = dict(**self._fq, **{n: getattr(self, '_t_' + n).data_ptr() for n in ('fq_P_hi', 'fq_P_lo', 'fq_rec', 'fq_sd')})
         return self.body_model._struct(dict(
-            **gcf,
+            **gcf, **fq,
             fit_ns=self._ns,
             fit_shapedirs=self._t_fit_shapedirs.data_ptr(),
             fit_Jt_ext=self.J_template_ext.data_ptr(),
@@ -494,32 +567,49 @@ class BodyFitter(nn.Module):
         """Shape and translation for a known pose (pt/bodyfitter.py:552-653)."""
         if scale_target and scale_fit:
             raise ValueError('Only one of estim_scale_target and estim_scale_fit can be True')
-        if share_beta:
-            raise NotImplementedError('share_beta is not implemented on the CUDA path (SURVEY.md 8f-2)')
         scale_mode = 1 if scale_target else (2 if scale_fit else 0)
+        if share_beta and scale_mode:
+            raise NotImplementedError('share_beta together with scale estimation is not implemented on the CUDA path')
         bm = self.body_model
         dev = bm.v_template.device
         _native.require_cuda(bm.v_template, 'the body model')
+        if target_vertices.ndim != 3:
+            raise ValueError(f'target_vertices must be (batch, {bm.num_vertices}, 3)')
         B, V, J, S = target_vertices.shape[0], bm.num_vertices, bm.num_joints, self.n_betas
         tv = self._prep(target_vertices, (B, V, 3), 'target_vertices')
         tj = self._prep(target_joints, (B, J, 3), 'target_joints')
         vw = self._prep(vertex_weights, (B, V), 'vertex_weights')
         jw = self._prep(joint_weights, (B, J), 'joint_weights')
-        glob = bm(pose_rotvecs=pose_rotvecs, return_vertices=False)['orientations']
+        if pose_rotvecs.shape[0] not in (1, B):
+            raise ValueError(f"'pose_rotvecs' must have batch size {B} (or 1), got {tuple(pose_rotvecs.shape)}")
         new = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)  # noqa: E731
         out = dict(shape_betas=new(B, S), trans=new(B, 3), relative_orientations=new(B, J, 3, 3))
         kid = new(B) if self.enable_kid else None
         scale_corr = new(B) if scale_mode else None
+        if B == 0:
+            if kid is not None:
+                out['kid_factor'] = kid
+            if scale_corr is not None:
+                out['scale_corr'] = scale_corr
+            return out
+        glob = bm(pose_rotvecs=pose_rotvecs, return_vertices=False)['orientations']
+        glob = glob.expand(B, J, 3, 3).contiguous()
         beta_ref = self._pad_ref(beta_regularizer_reference, B, 'beta_regularizer_reference')
         kid_ref = None
         if kid_regularizer_reference is not None and self.enable_kid:
-            kid_ref = kid_regularizer_reference.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+            kid_ref = torch.as_tensor(kid_regularizer_reference, dtype=torch.float32, device=dev).reshape(-1)
+            if kid_ref.numel() not in (1, B):
+                raise ValueError(f"'kid_regularizer_reference' must have {B} (or 1) elements, got {kid_ref.numel()}")
+            kid_ref = kid_ref.expand(B).contiguous()
         o = self._opts(1, False, [], self._shape_weights_rule(tj, vw, jw), beta_regularizer, beta_regularizer2,
                        kid_regularizer, scale_mode, scale_regularizer)
+        o.share_beta = int(bool(share_beta))
         L = _native.lib()
         s = self._struct()
         ws_bytes = L.smplfit_fit_workspace_bytes(C.byref(s), B, C.byref(o), int(tj is not None),
                                                  int(vw is not None), int(jw is not None))
+        if ws_bytes == 0:
+            _native.check(-2 if self._ns > 17 else -1)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         p = _native.ptr
         with torch.cuda.device(dev):
@@ -564,6 +654,17 @@ class BodyFitter(nn.Module):
         if kid_factor is not None and not self.enable_kid:
             raise NotImplementedError('kid_factor in fit_with_known_shape needs a fitter built with enable_kid=True')
         betas = shape_betas.to(device=dev, dtype=torch.float32)
+        if betas.ndim != 2 or betas.shape[0] not in (1, B):
+            raise ValueError(f"'shape_betas' must be ({B} or 1, n_betas), got {tuple(betas.shape)}")
+        if B == 0:
+            out = dict(trans=betas.new_empty(0, 3), orientations=betas.new_empty(0, J, 3, 3))
+            if scale_fit:
+                out['scale_corr'] = betas.new_empty(0)
+            if 'relative_orientations' in requested_keys or 'pose_rotvecs' in requested_keys:
+                out['relative_orientations'] = betas.new_empty(0, J, 3, 3)
+            if 'pose_rotvecs' in requested_keys:
+                out['pose_rotvecs'] = betas.new_empty(0, 3 * J)
+            return out
         if betas.shape[0] != B:
             betas = betas.expand(B, betas.shape[1])
         betas = betas.contiguous()
@@ -584,6 +685,8 @@ class BodyFitter(nn.Module):
         s = self._struct()
         ws_bytes = L.smplfit_fit_workspace_bytes(C.byref(s), B, C.byref(o), int(tj is not None),
                                                  int(vw is not None), int(jw is not None))
+        if ws_bytes == 0:
+            _native.check(-2 if self._ns > 17 else -1)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         p = _native.ptr
         with torch.cuda.device(dev):

@@ -16,7 +16,7 @@ import torch.nn as nn
 from .. import _native, masks, modeldata
 from . import _ops
 
-SEG_LEN = 64  # vertices per statistics segment
+SEG_LEN = 32  # vertices per statistics segment (== the padded slot block of one segment in csrc/fit_fused.cu)
 CHUNK_LEN = 128  # vertices per shape-pass chunk
 
 
