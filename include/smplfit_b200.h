@@ -152,11 +152,12 @@ typedef struct smplfit_model {
   const uint16_t* fq_P_lo;      /* same shape: remainder */
   const uint32_t* fq_rec;       /* (fq_nseg_pad * 32, 8) per slot: 4 skin weights (float bits, descending) | pack | v_rest[3];
                                    pack = 4 x 6-bit joint of slot k | reload mask (bits 24-27: slot k takes another joint here,
-                                   along the chain of segments of the same parity) | valid (bit 28) */
-  const float* fq_sd;           /* (fq_nseg_pad * 32, fq_sdl) shapedirs[x][s] at x * NSP + s, NSP = NS rounded up to even */
+                                   along the chain of segments of the same parity) | valid (bit 28) | bits 29 / 30, first slot of every 8-slot
+                                   block only: some slot reloads within the first / second four slots of the block */
+  const float* fq_sd;           /* (fq_nseg_pad * 32, fq_sdl) shapedirs[x][s] at x * NSP4 + s, NSP4 = NS rounded up to a multiple of 4 */
   int32_t fq_kf;                /* K of the GEMM: roundup(P + NS, 32); feature order [vec(R_rel[1:] - I) | unknowns] */
   int32_t fq_scale_log2;
-  int32_t fq_sdl;               /* roundup(3 NSP, 4) */
+  int32_t fq_sdl;               /* 3 NSP4 */
   int32_t fq_nseg_pad;          /* n_segments rounded up to even */
 } smplfit_model_t;
 
@@ -209,6 +210,16 @@ int smplfit_fit(const smplfit_model_t* m, int64_t batch, const float* target_ver
                 float* out_trans, float* out_orientations, float* out_rel_orientations,
                 float* out_kid_factor, float* out_scale_corr, void* workspace,
                 size_t workspace_bytes, void* stream);
+
+/* -- share_beta across ranks: with one process per GPU and the batch sharded over the ranks, the only
+ * cross-instance term of the fit is the batch sum of the centred normal equations of every shape solve
+ * (pt/lstsq.py:24-26).  When a hook is installed, every share_beta solve calls it between its local batch sum and the
+ * shared Cholesky solve: `device_buf` holds `count` doubles (upper triangle + right-hand side) that the hook must
+ * replace by their sum over all ranks, enqueued on `stream` (e.g. one ncclAllReduce; the Python host passes a ctypes
+ * callback around torch.distributed.all_reduce).  `global_batch` = instances over all ranks (the regulariser is added
+ * once per instance before the sum).  fn = NULL removes the hook.  Process-wide; install it before the fits. */
+typedef void (*smplfit_allreduce_fn)(double* device_buf, int64_t count, void* stream, void* user);
+int smplfit_set_share_beta_allreduce(smplfit_allreduce_fn fn, void* user, int64_t global_batch);
 
 /* -- BodyFitter.fit for HOST-resident targets (the end-to-end form of pt/bodyfitter.py:283-549: what a caller holding
  * numpy / CPU tensors pays for `fitter.fit(torch.as_tensor(x).cuda(), ...)` followed by `.cpu()` on the results).

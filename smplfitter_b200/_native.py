@@ -63,6 +63,9 @@ class FitOpts(C.Structure):
     ]
 
 
+ALLREDUCE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p)
+
+
 def lib_path() -> str:
     return os.environ.get('SMPLFIT_B200_LIB', os.path.join(_HERE, 'libsmplfit_b200.so'))
 
@@ -127,6 +130,8 @@ def lib():
         [C.POINTER(ModelStruct), C.c_int64, _F, C.c_int] + [_F] * 8 + [C.POINTER(FitOpts)] + [_F] * 5
         + [_F, C.c_size_t, _F]
     )
+    L.smplfit_set_share_beta_allreduce.restype = C.c_int
+    L.smplfit_set_share_beta_allreduce.argtypes = [ALLREDUCE_FN, C.c_void_p, C.c_int64]
     L.smplfit_convert_vertices.restype = C.c_int
     L.smplfit_convert_vertices.argtypes = [_F, _F, _F, C.c_int32, C.c_int32, C.c_int64, _F, _F, _F]
     if L.smplfit_struct_size(0) != C.sizeof(ModelStruct) or L.smplfit_struct_size(1) != C.sizeof(FitOpts):

@@ -4,8 +4,6 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include <mutex>
-
 #include "common.cuh"
 #include "fit_fused.cuh"
 #include "fit_kernels.cuh"
@@ -32,47 +30,6 @@ struct FitWs {
   size_t bytes;
 };
 
-// Side streams for the stages of one fit that do not depend on each other (the closed-form Gramian's pair / translation
-// terms against the pose-blend GEMM + vertex pass).  A small per-device ring; the slot is picked from the caller's
-// stream handle, so concurrent fits on different streams (smplfit_fit_host) usually get different side streams.
-// Sharing a slot is still correct: every fork / join records its event right before the matching wait is enqueued.
-struct SideSlot {
-  cudaStream_t stream = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
-  bool ok = false;
-};
-constexpr int kSideSlots = 4, kSideDevices = 64;
-static SideSlot g_side[kSideDevices][kSideSlots];
-static std::mutex g_side_mutex;
-
-static int side_stream_mode() {
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = getenv("SMPLFIT_B200_SIDE_STREAM");
-    mode = e ? atoi(e) : 0;
-  }
-  return mode;
-}
-
-static SideSlot* side_slot(cudaStream_t st) {
-  if (g_prof_on) return nullptr;  // per-kernel timing wants the stages back to back
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kSideDevices) return nullptr;
-  const int slot = (int)((reinterpret_cast<uintptr_t>(st) >> 4) % kSideSlots);
-  std::lock_guard<std::mutex> lock(g_side_mutex);
-  SideSlot& s = g_side[dev][slot];
-  if (!s.ok) {
-    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
-      cudaGetLastError();
-      return nullptr;
-    }
-    s.ok = true;
-  }
-  return &s;
-}
-
 // final adjustment: level-parallel kernel unless switched off (SMPLFIT_B200_ADJUST=seq) or a copy part's source is not
 // an ancestor-side joint of lower depth (never the case for the SMPL family, where toes copy their parent foot)
 static void launch_adjust(const AdjustArgs& aa, int groups, cudaStream_t st) {
@@ -88,16 +45,6 @@ static void launch_adjust(const AdjustArgs& aa, int groups, cudaStream_t st) {
   } else {
     SF_LAUNCH(k_adjust_solve, groups, 32, 0, st, aa);
   }
-}
-
-// SMPLFIT_B200_SLOT_MASK=0: the vertex kernels compare joint ids at run time instead of using fit_slot_mask
-static bool slot_mask_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SMPLFIT_B200_SLOT_MASK");
-    v = (e && atoi(e) == 0) ? 0 : 1;
-  }
-  return v == 1;
 }
 
 static int moment_blocks(int V) { return (V + 255) / 256; }
@@ -212,28 +159,13 @@ static void run_gemm(FitCtx& c) {
 static void run_shape(FitCtx& c, int scale_mode, const float* beta_ref, const float* kid_ref,
                       const smplfit_fit_opts_t* o) {
   const smplfit_model_t* m = c.m;
-  // The closed-form Gramian needs only the joint transforms.  Forked onto a side stream it can overlap the vertex
-  // pass; it must not overlap the persistent tcgen05 GEMM (whose static tile schedule suffers when its CTAs do not all
-  // start together: measured 3.62 -> 3.82 ms per step), so the fork point is after the GEMM.
-  // SMPLFIT_B200_SIDE_STREAM: 0 = off (default), 1 = fork before the GEMM, 2 = fork after the GEMM.
-  const int side_mode = side_stream_mode();
-  SideSlot* side = (c.lite && side_mode != 0) ? side_slot(c.st) : nullptr;
-  auto gram = [&]() {
-    cudaStream_t gs = c.st;
-    if (side && cudaEventRecord(side->fork, c.st) == cudaSuccess && cudaStreamWaitEvent(side->stream, side->fork, 0) == cudaSuccess)
-      gs = side->stream;
-    else
-      side = nullptr;
-    launch_gram_closed(m, c.groups, c.Bp, c.w.RT, c.w.gcfpart, c.w.pairfeat, gs);
-    if (side) cudaEventRecord(side->join, side->stream);
-  };
-  if (c.lite && side_mode != 2) gram();
+  // the closed-form Gramian needs only the joint transforms (not the vertices)
+  if (c.lite) launch_gram_closed(m, c.groups, c.Bp, c.w.RT, c.w.gcfpart, c.w.pairfeat, c.st);
   bool shape_fused = false;
   if (c.lite && c.fused && scale_mode == 0)  // (the scale pass of the final solve reads v_posed^T)
     shape_fused = fit_fused_run(m, 2, c.B, c.Bp, c.w.feat, c.Kp, nullptr, c.w.tT, nullptr, c.w.RT12, nullptr, nullptr, nullptr, 0,
                                 c.w.gpart, c.w.fq_scratch, c.st);
   if (!shape_fused) run_gemm(c);
-  if (c.lite && side_mode == 2) gram();
   ShapeArgs sa;
   sa.tT = c.w.tT; sa.vwT = c.vwT_shape; sa.vposedT = c.w.vposedT; sa.RT = c.w.RT;
   sa.shapedirs = m->fit_shapedirs; sa.skin_idx = m->skin_idx; sa.skin_w = m->skin_w; sa.order = m->order;
@@ -244,10 +176,9 @@ static void run_shape(FitCtx& c, int scale_mode, const float* beta_ref, const fl
     LiteArgs la;
     la.tT = c.w.tT; la.vposedT = c.w.vposedT; la.RT12 = c.w.RT12; la.rec = m->fit_rec; la.seg_start = m->seg_start;
     la.seg_slots = m->seg_slots; la.partials = c.w.gpart; la.n_segments = m->n_segments; la.J = m->num_joints;
-    la.Bp = c.Bp; la.segs_per_warp = 1; la.slot_mask = slot_mask_enabled() ? m->fit_slot_mask : nullptr;
+    la.Bp = c.Bp; la.segs_per_warp = 1; la.slot_mask = m->fit_slot_mask;
     if (shape_fused) launch_lite_reduce(la, m, c.groups, c.w.Yd, c.st);
     else launch_shape_lite(la, m, c.groups, c.w.Yd, c.st);
-    if (side) cudaStreamWaitEvent(c.st, side->join, 0);
     so.lite = 1; so.lite_nl = lite_rows(m->fit_ns); so.n_gcf = gram_closed_blocks(m); so.gcf_part = c.w.gcfpart;
     so.G0 = m->gcf_G0; so.Yd = c.w.Yd;
   } else {
@@ -313,7 +244,7 @@ static void run_stats(FitCtx& c, int ref_mode, const float* ca0T, const float* a
     l.skin4 = c.w.skin4; l.aT_out = aT_out; l.partials = c.w.spart; l.rec = m->fit_rec; l.seg_start = m->seg_start;
     l.seg_part = m->seg_part; l.part_flags = m->part_flags; l.n_segments = m->n_segments; l.Bp = c.Bp;
     l.J = m->num_joints; l.all_segments = (aT_out != nullptr); l.segs_per_warp = 1;
-    l.slot_mask = slot_mask_enabled() ? m->fit_slot_mask : nullptr;
+    l.slot_mask = m->fit_slot_mask;
     launch_stats_lite(l, m, c.groups, c.st);
     return;
   }
@@ -389,6 +320,12 @@ extern "C" size_t smplfit_struct_size(int which) {
 extern "C" int64_t smplfit_launch_count(int reset) {
   const long long v = reset ? g_launches.exchange(0) : g_launches.load();
   return (int64_t)v;
+}
+
+extern "C" int smplfit_set_share_beta_allreduce(smplfit_allreduce_fn fn, void* user, int64_t global_batch) {
+  if (fn != nullptr && global_batch <= 0) return fail(SMPLFIT_ERR_ARG, "global_batch must be positive");
+  set_share_beta_allreduce(fn, user, global_batch);
+  return SMPLFIT_OK;
 }
 
 extern "C" size_t smplfit_fit_workspace_bytes(const smplfit_model_t* m, int64_t batch, const smplfit_fit_opts_t* o,

@@ -215,8 +215,9 @@ __device__ __forceinline__ bool seg_active(const FitFusedArgs& a, int mode, int 
   return true;
 }
 
-// H = NSP / 2 (float2 accumulators of r) for MODE 2; unused for MODE 3
-template <int MODE, int H, bool WEIGHTED>
+// H = NSP / 2 (float2 accumulators of r) for MODE 2; unused for MODE 3.  AOUT (MODE 3): the reference vertices are also
+// written out (fits without target joints regress the joints from them) and segments without statistics take part.
+template <int MODE, int H, bool WEIGHTED, bool AOUT>
 __global__ void __launch_bounds__(THREADS, 1) k_fit_fused(const __grid_constant__ FusedMaps maps, const FitFusedArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -375,6 +376,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_fit_fused(const __grid_constant_
     if (MODE == 2) {
       lut[lane] = 0;
       lut[32 + lane] = 0;
+#pragma unroll
+      for (int r = 0; r < NSLOT * 3; ++r) yw[r * 32 + lane] = 0.f;
       __syncwarp();
     }
     RowCache rc;
@@ -383,7 +386,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_fit_fused(const __grid_constant_
 #pragma unroll
       for (int c = 0; c < 3; ++c) rc.q[k][c] = make_float4(0.f, 0.f, 0.f, 0.f);
     int jcur[4] = {0, 0, 0, 0};
-    int cur_tm = -1, tcount = 0, tcnt = 0;
+    int cur_tm = -1, cur_part = -1, tcount = 0, tcnt = 0;
+    float ct[3] = {0.f, 0.f, 0.f}, ca[3] = {0.f, 0.f, 0.f};  // provisional centres of the current part (MODE 3)
     for (int L = L0; L < L1; ++L, ++tcount) {
       const int as = tcount & 1;
       const uint32_t aph = (tcount >> 1) & 1;
@@ -397,11 +401,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_fit_fused(const __grid_constant_
       // full reload of the four slots at the first vertex when the cached rows belong to other instances or the chain of
       // segments the host replayed (every second segment, in order) was left (skipped segment)
       const bool fresh = tm != cur_tm;
+      if (fresh) {
+        cur_part = -1;
+        if (MODE == 2) {  // (a NaN instance may have left NaNs in Y rows that are never handed out)
+#pragma unroll
+          for (int r = 0; r < NSLOT * 3; ++r) yw[r * 32 + lane] = 0.f;
+        }
+      }
       cur_tm = live ? tm : -1;
       // per-segment state
       float2 r2[H > 0 ? H : 1];
       float Sb[3] = {0.f, 0.f, 0.f}, Yr[4][3];
-      float M[9], st[3] = {0.f, 0.f, 0.f}, sa[3] = {0.f, 0.f, 0.f}, W = 0.f, ct[3] = {0.f, 0.f, 0.f}, ca[3] = {0.f, 0.f, 0.f};
+      float M[9], st[3] = {0.f, 0.f, 0.f}, sa[3] = {0.f, 0.f, 0.f}, W = 0.f;
       int nslots = 0;
       if (MODE == 2) {
 #pragma unroll
@@ -412,14 +423,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_fit_fused(const __grid_constant_
           const int sj = (lane < NSLOT) ? __ldg(a.seg_slots + seg * NSLOT + lane) : -1;
           nslots = __popc(__ballot_sync(0xffffffffu, sj >= 0));
           if (sj >= 0) lut[sj] = (unsigned char)lane;
-#pragma unroll
-          for (int r = 0; r < NSLOT * 3; ++r) yw[r * 32 + lane] = 0.f;
           __syncwarp();
         }
       } else {
 #pragma unroll
         for (int r = 0; r < 9; ++r) M[r] = 0.f;
-        if (live) {
+        if (live && part != cur_part) {  // consecutive segments of a chain mostly belong to the same part
+          cur_part = part;
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             ct[c] = a.ct0[(size_t)(part * 3 + c) * Bp + b];
@@ -447,90 +457,137 @@ __global__ void __launch_bounds__(THREADS, 1) k_fit_fused(const __grid_constant_
           if (live) {
             const float* tq = reinterpret_cast<const float*>(t_area + (size_t)(h * TRING + ts) * TSLOT_BYTES) + q * 3 * GV * 32 + lane;
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            // per-vertex work on x = GEMM column triple (scaled, rest position added), t = target
+            auto vertex = [&](const float wk[4], const float x[3], const float t[3], int vi) {
+              float2 B2[6];
+              rc.blend(wk, B2);
+              float p[3];
 #pragma unroll
-            for (int u = 0; u < GV; ++u) {
-              const int vi = g * GV + u;
-              if (vi < len) {
-                const uint4 w4 = recs[2 * vi], m4 = recs[2 * vi + 1];
-                const uint32_t pack = m4.x;
-                const float wk[4] = {__uint_as_float(w4.x), __uint_as_float(w4.y), __uint_as_float(w4.z), __uint_as_float(w4.w)};
-                const uint32_t rl = (fresh && vi == 0) ? 0xFu : ((pack >> 24) & 0xFu);
-                if (rl) {  // warp-uniform, rare
+              for (int c = 0; c < 3; ++c)
+                p[c] = fmaf(B2[2 * c].x, x[0], fmaf(B2[2 * c].y, x[1], fmaf(B2[2 * c + 1].x, x[2], B2[2 * c + 1].y)));
+              if (MODE == 2) {
+                float bv[3];
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    if (rl & (1u << k)) {
-                      const int jn = (int)((pack >> (6 * k)) & 63u);
-                      if (MODE == 2) {
-                        float* yp = yw + (size_t)(lut[jcur[k]] * 3) * 32 + lane;
+                for (int c = 0; c < 3; ++c) {
+                  bv[c] = t[c] - p[c];
+                  Sb[c] += bv[c];
+                }
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                          yp[c * 32] += Yr[k][c];
-                          Yr[k][c] = 0.f;
-                        }
-                      }
-                      jcur[k] = jn;
-                      rc.load(k, qb + (size_t)(jn * 3) * Bp, Bp);
-                    }
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                  for (int c = 0; c < 3; ++c) Yr[k][c] = fmaf(wk[k], bv[c], Yr[k][c]);
+                float z[3];
+                z[0] = fmaf(B2[0].x, bv[0], fmaf(B2[2].x, bv[1], B2[4].x * bv[2]));
+                z[1] = fmaf(B2[0].y, bv[0], fmaf(B2[2].y, bv[1], B2[4].y * bv[2]));
+                z[2] = fmaf(B2[1].x, bv[0], fmaf(B2[3].x, bv[1], B2[5].x * bv[2]));
+                // shapedirs[x][s] at x * NSP4 + s (rows padded to 16-byte multiples: read as 16-byte words)
+                constexpr int NSP4 = (2 * H + 3) / 4 * 4;
+                const float4* sdv = reinterpret_cast<const float4*>(sds + (size_t)vi * a.sdl);
+#pragma unroll
+                for (int xx = 0; xx < 3; ++xx) {
+                  const float2 zz = make_float2(z[xx], z[xx]);
+#pragma unroll
+                  for (int q4 = 0; q4 < NSP4 / 4; ++q4) {
+                    const float4 s4 = sdv[xx * (NSP4 / 4) + q4];
+                    r2[2 * q4] = __ffma2_rn(make_float2(s4.x, s4.y), zz, r2[2 * q4]);
+                    if (2 * q4 + 1 < H) r2[2 * q4 + 1] = __ffma2_rn(make_float2(s4.z, s4.w), zz, r2[2 * q4 + 1]);
                   }
                 }
+              } else {
+                if (AOUT) {
+                  float* ao = a.aT_out + (size_t)((i0 + vi) * 3) * Bp + b;
+                  ao[0] = p[0];
+                  ao[Bp] = p[1];
+                  ao[2 * (size_t)Bp] = p[2];
+                }
+                if (!AOUT || stat) {  // (without AOUT only segments with statistics are active)
+                  const float wv = WEIGHTED ? a.vwT[(size_t)(i0 + vi) * Bp + b] : 1.f;
+                  float dt[3], wa[3];
+#pragma unroll
+                  for (int c = 0; c < 3; ++c) {
+                    dt[c] = t[c] - ct[c];
+                    wa[c] = WEIGHTED ? wv * (p[c] - ca[c]) : (p[c] - ca[c]);
+                    st[c] = WEIGHTED ? fmaf(wv, dt[c], st[c]) : st[c] + dt[c];
+                    sa[c] += wa[c];
+                  }
+#pragma unroll
+                  for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) M[rr * 3 + c] = fmaf(dt[rr], wa[c], M[rr * 3 + c]);
+                  W += wv;
+                }
+              }
+            };
+            // GV / 2 vertices without a slot reload: one branch-free stretch, so the per-vertex chains interleave
+            auto fast_half = [&](int u0) {
+#pragma unroll
+              for (int uu = 0; uu < GV / 2; ++uu) {
+                const int u = u0 + uu;  // compile-time after inlining (u0 is a literal at both call sites)
+                const int vi = g * GV + u;
+                const uint4 w4 = recs[2 * vi], m4 = recs[2 * vi + 1];
+                const float wk[4] = {__uint_as_float(w4.x), __uint_as_float(w4.y), __uint_as_float(w4.z), __uint_as_float(w4.w)};
                 float t[3], x[3];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                   t[c] = tq[(u * 3 + c) * 32];
                   x[c] = fmaf(__uint_as_float(r[3 * u + c]), inv_scale, __uint_as_float(c == 0 ? m4.y : (c == 1 ? m4.z : m4.w)));
                 }
-                float2 B2[6];
-                rc.blend(wk, B2);
-                float p[3];
+                vertex(wk, x, t, vi);
+              }
+            };
+            const uint32_t pack0 = recs[2 * g * GV + 1].x;
+            const int nv = min(GV, len - g * GV);
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+              const int u_lo = half * (GV / 2), u_hi = min(nv, u_lo + GV / 2);
+              if (u_lo >= u_hi) break;
+              const bool fast = u_hi - u_lo == GV / 2 && !(fresh && g == 0 && half == 0) && (pack0 & (1u << (29 + half))) == 0;
+              if (fast) {
+                if (half == 0) fast_half(0);
+                else fast_half(GV / 2);
+              } else {
+                // general vertices (a slot reloads, first vertices of a fresh chain, or a partial half): rolled loop;
+                // the accumulator columns go through a small per-thread array so that they can be indexed at run time
+                float xs[3 * GV / 2];
+                if (half == 0) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c)
-                  p[c] = fmaf(B2[2 * c].x, x[0], fmaf(B2[2 * c].y, x[1], fmaf(B2[2 * c + 1].x, x[2], B2[2 * c + 1].y)));
-                if (MODE == 2) {
-                  float bv[3];
+                  for (int i = 0; i < 3 * GV / 2; ++i) xs[i] = __uint_as_float(r[i]);
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 3 * GV / 2; ++i) xs[i] = __uint_as_float(r[3 * GV / 2 + i]);
+                }
+#pragma unroll 1
+                for (int u = u_lo; u < u_hi; ++u) {
+                  const int vi = g * GV + u;
+                  const uint4 w4 = recs[2 * vi], m4 = recs[2 * vi + 1];
+                  const uint32_t pack = m4.x;
+                  const float wk[4] = {__uint_as_float(w4.x), __uint_as_float(w4.y), __uint_as_float(w4.z), __uint_as_float(w4.w)};
+                  const uint32_t rl = (fresh && vi == 0) ? 0xFu : ((pack >> 24) & 0xFu);
+                  if (rl) {  // warp-uniform
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                      if (rl & (1u << k)) {
+                        const int jn = (int)((pack >> (6 * k)) & 63u);
+                        if (MODE == 2) {
+                          float* yp = yw + (size_t)(lut[jcur[k]] * 3) * 32 + lane;
+#pragma unroll
+                          for (int c = 0; c < 3; ++c) {
+                            yp[c * 32] += Yr[k][c];
+                            Yr[k][c] = 0.f;
+                          }
+                        }
+                        jcur[k] = jn;
+                        rc.load(k, qb + (size_t)(jn * 3) * Bp, Bp);
+                      }
+                    }
+                  }
+                  float t[3], x[3];
 #pragma unroll
                   for (int c = 0; c < 3; ++c) {
-                    bv[c] = t[c] - p[c];
-                    Sb[c] += bv[c];
+                    t[c] = tq[(u * 3 + c) * 32];
+                    x[c] = fmaf(xs[3 * (u - u_lo) + c], inv_scale, __uint_as_float(c == 0 ? m4.y : (c == 1 ? m4.z : m4.w)));
                   }
-#pragma unroll
-                  for (int k = 0; k < 4; ++k)
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) Yr[k][c] = fmaf(wk[k], bv[c], Yr[k][c]);
-                  float z[3];
-                  z[0] = fmaf(B2[0].x, bv[0], fmaf(B2[2].x, bv[1], B2[4].x * bv[2]));
-                  z[1] = fmaf(B2[0].y, bv[0], fmaf(B2[2].y, bv[1], B2[4].y * bv[2]));
-                  z[2] = fmaf(B2[1].x, bv[0], fmaf(B2[3].x, bv[1], B2[5].x * bv[2]));
-                  const float* sdv = sds + (size_t)vi * a.sdl;  // shapedirs[x][s] at x * 2H + s
-#pragma unroll
-                  for (int xx = 0; xx < 3; ++xx) {
-                    const float2 zz = make_float2(z[xx], z[xx]);
-#pragma unroll
-                    for (int sp = 0; sp < H; ++sp) {
-                      const float2 s2 = *reinterpret_cast<const float2*>(sdv + xx * 2 * H + 2 * sp);
-                      r2[sp] = __ffma2_rn(s2, zz, r2[sp]);
-                    }
-                  }
-                } else {
-                  if (a.aT_out != nullptr) {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) a.aT_out[(size_t)((i0 + vi) * 3 + c) * Bp + b] = p[c];
-                  }
-                  if (stat) {
-                    const float wv = WEIGHTED ? a.vwT[(size_t)(i0 + vi) * Bp + b] : 1.f;
-                    float dt[3], wa[3];
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                      dt[c] = t[c] - ct[c];
-                      wa[c] = WEIGHTED ? wv * (p[c] - ca[c]) : (p[c] - ca[c]);
-                      st[c] = WEIGHTED ? fmaf(wv, dt[c], st[c]) : st[c] + dt[c];
-                      sa[c] += wa[c];
-                    }
-#pragma unroll
-                    for (int rr = 0; rr < 3; ++rr)
-#pragma unroll
-                      for (int c = 0; c < 3; ++c) M[rr * 3 + c] = fmaf(dt[rr], wa[c], M[rr * 3 + c]);
-                    W += wv;
-                  }
+                  vertex(wk, x, t, vi);
                 }
               }
             }
@@ -549,21 +606,26 @@ __global__ void __launch_bounds__(THREADS, 1) k_fit_fused(const __grid_constant_
           for (int k = 0; k < 4; ++k) {
             float* yp = yw + (size_t)(lut[jcur[k]] * 3) * 32 + lane;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              yp[c * 32] += Yr[k][c];
-              Yr[k][c] = 0.f;
-            }
+            for (int c = 0; c < 3; ++c) yp[c * 32] += Yr[k][c];
           }
           const int NL = a.ns + 3 + 3 * NSLOT;
           float* out = a.partials + (size_t)seg * NL * Bp + b;
 #pragma unroll
           for (int s = 0; s < 2 * H; ++s)
             if (s < a.ns) out[(size_t)s * Bp] = (s & 1) ? r2[s >> 1].y : r2[s >> 1].x;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) out[(size_t)(a.ns + c) * Bp] = Sb[c];
-          for (int r = 0; r < nslots * 3; ++r) out[(size_t)(a.ns + 3 + r) * Bp] = yw[r * 32 + lane];
+          out += (size_t)a.ns * Bp;
+          out[0] = Sb[0];
+          out[Bp] = Sb[1];
+          out[2 * (size_t)Bp] = Sb[2];
+          out += (size_t)3 * Bp;
+          for (int r = 0; r < nslots * 3; ++r) {  // hand the Y rows out and leave them zeroed for the next segment
+            out[(size_t)r * Bp] = yw[r * 32 + lane];
+            yw[r * 32 + lane] = 0.f;
+          }
+          // a stale slot (weight 0 in this segment) may have been flushed (adding 0) into a row past nslots: those rows
+          // only ever receive zeros, so they stay zero
           __syncwarp();
-        } else if (stat) {
+        } else if (!AOUT || stat) {
           float* out = a.partials + (size_t)seg * 16 * Bp + b;
 #pragma unroll
           for (int r = 0; r < 9; ++r) out[(size_t)r * Bp] = M[r];
@@ -661,17 +723,17 @@ int sm_count() {
   return sms;
 }
 
-template <int MODE, int H, bool WEIGHTED>
+template <int MODE, int H, bool WEIGHTED, bool AOUT = false>
 bool launch_t(const FusedMaps& maps, const FitFusedArgs& fa, int grid, int smem, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(k_fit_fused<MODE, H, WEIGHTED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+    if (cudaFuncSetAttribute(k_fit_fused<MODE, H, WEIGHTED, AOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
       cudaGetLastError();
       return false;
     }
     attr_set = true;
   }
-  SF_LAUNCH((k_fit_fused<MODE, H, WEIGHTED>), grid, THREADS, smem, st, maps, fa);
+  SF_LAUNCH((k_fit_fused<MODE, H, WEIGHTED, AOUT>), grid, THREADS, smem, st, maps, fa);
   return true;
 }
 
@@ -720,6 +782,8 @@ bool fit_fused_run(const smplfit_model_t* m, int mode, int B, int Bp, const floa
   const int grid = fa.total_tiles < sm_count() ? fa.total_tiles : sm_count();
   const int smem = fused_smem_bytes(mode, m->fq_sdl);
   if (mode == 3) {
+    if (aT_out != nullptr)
+      return vwT ? launch_t<3, 0, true, true>(maps, fa, grid, smem, st) : launch_t<3, 0, false, true>(maps, fa, grid, smem, st);
     return vwT ? launch_t<3, 0, true>(maps, fa, grid, smem, st) : launch_t<3, 0, false>(maps, fa, grid, smem, st);
   }
   switch ((m->fit_ns + 1) / 2) {

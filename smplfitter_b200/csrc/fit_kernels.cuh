@@ -550,189 +550,6 @@ __host__ __device__ inline int quad_row_T(int ns, int c, int col) {
 }
 
 // ---------------------------------------------------------------------------------------
-// k_shape_pass_rec<NS>: the shape pass for models with <= 4 influences per vertex whose
-// per-joint rows fit in shared memory (SMPL-size).  Same math as k_shape_pass; differences:
-//  * records instead of indexed tables; the next vertex's skin words and its streamed
-//    t / v_posed values are prefetched one iteration ahead (the pass was long-scoreboard bound);
-//  * the dominant joint's [R | T_ext] rows are cached in registers -- vertices are grouped by
-//    part, so they change only at part boundaries -- cutting shared-memory reads by ~25 %;
-//  * zero-weight slots are skipped (warp-uniform branch);
-//  * without per-vertex weights SA = sum_v jac_v is not accumulated: it has the closed form
-//    sum_k (R_k D_k + n_k T_k[:,1:]) with model constants D_k = sum_v w_vk S_v, n_k = sum_v w_vk,
-//    evaluated in k_shape_solve.
-// ---------------------------------------------------------------------------------------
-template <int NS, bool WEIGHTED, int WARPS, bool CACHE>
-__global__ void __launch_bounds__(WARPS * 32, 1) k_shape_pass_rec(const ShapeArgs a) {
-  extern __shared__ __align__(16) float s_rt[];
-  constexpr int RW = 12 + 3 * NS;
-  constexpr int TW = 3 * (1 + NS);
-  constexpr int REC = Rec<NS>::LEN;
-  constexpr int NUSED = WEIGHTED ? ShapeAcc<NS>::N : ShapeAcc<NS>::N_UNWEIGHTED;
-  constexpr int OG = 0, OR = ShapeAcc<NS>::NG, OSB = OR + NS, OSA = OSB + 3, OW = OSA + 3 * NS;
-  static_assert(WARPS == 8 || WARPS == 12 || WARPS == 16, "tree reduction expects 8, 12 or 16 warps");
-  const int g = blockIdx.y;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int Bp = a.Bp;
-  const int b = g * 32 + lane;
-  {
-    const int n16 = a.J * RW * 8;
-    for (int q = threadIdx.x; q < n16; q += WARPS * 32) {
-      const int r = q >> 3, part = q & 7;
-      const float* src = a.RT + (size_t)r * Bp + g * 32 + part * 4;
-      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_rt + r * 32 + part * 4);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-  }
-  const int chunk = blockIdx.x * WARPS + warp;
-  const bool active = chunk < a.n_chunks;
-  float acc[NUSED];
-#pragma unroll
-  for (int e = 0; e < NUSED; ++e) acc[e] = 0.f;
-  if (active) {
-    const int i0 = chunk * a.chunk_len, i1 = min(a.V, i0 + a.chunk_len);
-    const float* rec = a.rec + (size_t)i0 * REC;
-    float4 nw = __ldg(reinterpret_cast<const float4*>(rec));
-    int4 nj = __ldg(reinterpret_cast<const int4*>(rec + 4));
-    float nt[3], nvp[3], nvw = 1.f;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      nt[c] = SF_IM(a.tT, i0 * 3 + c, Bp, b);
-      nvp[c] = SF_IM(a.vposedT, i0 * 3 + c, Bp, b);
-    }
-    if (WEIGHTED) nvw = SF_IM(a.vwT, i0, Bp, b);
-    float Rc[CACHE ? 9 : 1], Tc[CACHE ? TW : 1];
-    int cj = -1;
-    for (int i = i0; i < i1; ++i) {
-      const float4 w4 = nw;
-      const int4 j4 = nj;
-      float t[3], vp[3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        t[c] = nt[c];
-        vp[c] = nvp[c];
-      }
-      const float wv = nvw;
-      const float* sd = rec + 8;  // this vertex's shapedirs (warp-uniform loads at the point of use)
-      if (i + 1 < i1) {  // prefetch the next vertex
-        rec += REC;
-        nw = __ldg(reinterpret_cast<const float4*>(rec));
-        nj = __ldg(reinterpret_cast<const int4*>(rec + 4));
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          nt[c] = SF_IM(a.tT, (i + 1) * 3 + c, Bp, b);
-          nvp[c] = SF_IM(a.vposedT, (i + 1) * 3 + c, Bp, b);
-        }
-        if (WEIGHTED) nvw = SF_IM(a.vwT, i + 1, Bp, b);
-      }
-      float Rb[9], Tb[TW];
-      if (CACHE) {
-        if (j4.x != cj) {  // part boundary: refresh the register copy of the dominant joint's rows
-          cj = j4.x;
-          const float* p = s_rt + (size_t)(cj * RW) * 32 + lane;
-#pragma unroll
-          for (int e = 0; e < 9; ++e) Rc[e] = p[e * 32];
-#pragma unroll
-          for (int e = 0; e < TW; ++e) Tc[e] = p[(9 + e) * 32];
-        }
-#pragma unroll
-        for (int e = 0; e < 9; ++e) Rb[e] = w4.x * Rc[e];
-#pragma unroll
-        for (int e = 0; e < TW; ++e) Tb[e] = w4.x * Tc[e];
-      } else {
-        const float* p = s_rt + (size_t)(j4.x * RW) * 32 + lane;
-#pragma unroll
-        for (int e = 0; e < 9; ++e) Rb[e] = w4.x * p[e * 32];
-#pragma unroll
-        for (int e = 0; e < TW; ++e) Tb[e] = w4.x * p[(9 + e) * 32];
-      }
-      const float wk[3] = {w4.y, w4.z, w4.w};
-      const int jk[3] = {j4.y, j4.z, j4.w};
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        if (wk[k] != 0.f) {
-          const float* p = s_rt + (size_t)(jk[k] * RW) * 32 + lane;
-#pragma unroll
-          for (int e = 0; e < 9; ++e) Rb[e] = fmaf(wk[k], p[e * 32], Rb[e]);
-#pragma unroll
-          for (int e = 0; e < TW; ++e) Tb[e] = fmaf(wk[k], p[(9 + e) * 32], Tb[e]);
-        }
-      }
-      float bv[3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float pos = fmaf(Rb[c * 3], vp[0], fmaf(Rb[c * 3 + 1], vp[1], fmaf(Rb[c * 3 + 2], vp[2], Tb[c * (1 + NS)])));
-        bv[c] = t[c] - pos;
-      }
-#pragma unroll
-      for (int s = 0; s < NS; ++s) {
-        const float s0 = __ldg(sd + s), s1 = __ldg(sd + Rec<NS>::NSP + s), s2 = __ldg(sd + 2 * Rec<NS>::NSP + s);
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-          Tb[c * (1 + NS) + 1 + s] =
-              fmaf(Rb[c * 3], s0, fmaf(Rb[c * 3 + 1], s1, fmaf(Rb[c * 3 + 2], s2, Tb[c * (1 + NS) + 1 + s])));
-      }
-      if (WEIGHTED) acc[OW] += wv;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        acc[OSB + c] += WEIGHTED ? wv * bv[c] : bv[c];
-        int e = OG;
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-          const float js = Tb[c * (1 + NS) + 1 + s];
-          const float wj = WEIGHTED ? wv * js : js;
-          if (WEIGHTED) acc[OSA + c * NS + s] += wj;
-          acc[OR + s] = fmaf(wj, bv[c], acc[OR + s]);
-#pragma unroll
-          for (int t2 = s; t2 < NS; ++t2) {
-            acc[e] = fmaf(wj, Tb[c * (1 + NS) + 1 + t2], acc[e]);
-            ++e;
-          }
-        }
-      }
-    }
-  }
-  // deterministic tree reduction over the CTA's warps through shared memory ([8][NUSED][32] max)
-  float* red = s_rt;
-  if (WARPS > 8) {  // fold warps 8.. onto warps 0..WARPS-9
-    __syncthreads();
-    if (warp >= 8) {
-      float* dst = red + (size_t)(warp - 8) * NUSED * 32 + lane;
-#pragma unroll
-      for (int e = 0; e < NUSED; ++e) dst[e * 32] = acc[e];
-    }
-    __syncthreads();
-    if (warp < WARPS - 8) {
-      const float* src = red + (size_t)warp * NUSED * 32 + lane;
-#pragma unroll
-      for (int e = 0; e < NUSED; ++e) acc[e] += src[e * 32];
-    }
-  }
-#pragma unroll 1
-  for (int half = 4; half >= 1; half >>= 1) {
-    __syncthreads();
-    if (warp >= half && warp < 2 * half) {
-      float* dst = red + (size_t)(warp - half) * NUSED * 32 + lane;
-#pragma unroll
-      for (int e = 0; e < NUSED; ++e) dst[e * 32] = acc[e];
-    }
-    __syncthreads();
-    if (warp < half) {
-      const float* src = red + (size_t)warp * NUSED * 32 + lane;
-#pragma unroll
-      for (int e = 0; e < NUSED; ++e) acc[e] += src[e * 32];
-    }
-  }
-  if (warp == 0) {
-    float* out = a.partials + (size_t)blockIdx.x * ShapeAcc<NS>::N * Bp + b;
-#pragma unroll
-    for (int e = 0; e < NUSED; ++e) out[(size_t)e * Bp] = acc[e];
-  }
-}
-
-// ---------------------------------------------------------------------------------------
 // k_shape_pass_v2<NS>: packed-math shape pass (Blackwell FFMA2, two FP32 FMAs per issue slot).
 // The pass is issue-bound, so the arithmetic is arranged in float2 pairs along the shape index:
 //  * per-joint rows live in shared memory as float4 quads per instance (Quad<NS> order):
@@ -740,7 +557,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_shape_pass_rec(const ShapeArg
 //  * jac[c][s,s+1] += (R[c][x], R[c][x]) * shapedirs[x][s,s+1]   (uniform 8-byte record loads);
 //  * G[s][t,t+1] += (jac[c][s], jac[c][s]) * jac[c][t,t+1] for pairs t >= s & ~1
 //    (one extra lower-triangle entry per odd row, dropped when the partials are written).
-// Same outputs and partial layout as k_shape_pass_rec.
+// Same outputs and partial layout as k_shape_pass (without per-vertex weights SA = sum_v jac_v is not accumulated: it has the
+// closed form sum_k (R_k D_k + n_k T_k[:,1:]) with D_k = sum_v w_vk S_v, n_k = sum_v w_vk, evaluated in k_gram_entries).
 // ---------------------------------------------------------------------------------------
 // 1-D bulk async copy global -> shared with mbarrier completion (TMA engine, UBLKCP)
 __device__ __forceinline__ void sf_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {

@@ -44,12 +44,6 @@ static int sm_count() {
 
 // warps per CTA of the vertex kernels (one CTA per SM): 12 when the staging fits, else 8, else unavailable
 static int env_int(const char* name, int dflt);
-// SMPLFIT_B200_LITE_WARPS=14 / 16: experiment with more warps per CTA for the unweighted kernels (default 12)
-static int lite_warps_override() {
-  static int v = -1;
-  if (v < 0) v = env_int("SMPLFIT_B200_LITE_WARPS", 0);
-  return v;
-}
 static int lite_warps(const smplfit_model_t* m) {
   if (lite_smem_bytes(m->num_joints, m->fit_rec_len, 12) <= kSmemMax) return 12;
   if (lite_smem_bytes(m->num_joints, m->fit_rec_len, 8) <= kSmemMax) return 8;
@@ -169,10 +163,7 @@ static void gram_closed_t(const smplfit_model_t* m, int groups, int Bp, const fl
 
 template <int NS>
 static void lite_t(const LiteArgs& a, const smplfit_model_t* m, int groups, double* Yd, cudaStream_t st) {
-  const int wo = lite_warps_override();
-  if (wo == 14 && lite_smem_bytes(m->num_joints, m->fit_rec_len, 14) <= kSmemMax) lite_launch_t<NS, 14>(a, m->num_vertices, groups, st);
-  else if (wo == 16 && lite_smem_bytes(m->num_joints, m->fit_rec_len, 16) <= kSmemMax) lite_launch_t<NS, 16>(a, m->num_vertices, groups, st);
-  else if (lite_warps(m) == 12) lite_launch_t<NS, 12>(a, m->num_vertices, groups, st);
+  if (lite_warps(m) == 12) lite_launch_t<NS, 12>(a, m->num_vertices, groups, st);
   else lite_launch_t<NS, 8>(a, m->num_vertices, groups, st);
   LiteReduceArgs ra;
   ra.partials = a.partials; ra.yj_start = m->yj_start; ra.yj_entry = m->yj_entry; ra.Yd = Yd; ra.NL = lite_rows(NS);
@@ -216,10 +207,7 @@ static void stats_lite_t(const StatsLiteArgs& a, const smplfit_model_t* m, int g
   if (a.vwT != nullptr) {
     if (w12) stats_lite_launch_t<NS, true, 12>(a, m->num_vertices, groups, st); else stats_lite_launch_t<NS, true, 8>(a, m->num_vertices, groups, st);
   } else {
-    const int wo = lite_warps_override();
-    if (wo == 14 && stats_lite_smem_bytes(m->num_joints, m->fit_rec_len, 14) <= kSmemMax) stats_lite_launch_t<NS, false, 14>(a, m->num_vertices, groups, st);
-    else if (wo == 16 && stats_lite_smem_bytes(m->num_joints, m->fit_rec_len, 16) <= kSmemMax) stats_lite_launch_t<NS, false, 16>(a, m->num_vertices, groups, st);
-    else if (w12) stats_lite_launch_t<NS, false, 12>(a, m->num_vertices, groups, st); else stats_lite_launch_t<NS, false, 8>(a, m->num_vertices, groups, st);
+    if (w12) stats_lite_launch_t<NS, false, 12>(a, m->num_vertices, groups, st); else stats_lite_launch_t<NS, false, 8>(a, m->num_vertices, groups, st);
   }
 }
 

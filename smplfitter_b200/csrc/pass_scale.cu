@@ -54,6 +54,16 @@ void launch_shape_solve_scale(const SolveArgs& a, double* Gd, double* Zd, int ns
   SF_NS_SWITCH(ns, (solve_scale_t<NS>(a, Gd, Zd, groups, st)));
 }
 
+// share_beta over several ranks: hook called on the local batch sums before the shared solve (smplfit_b200.h)
+static smplfit_allreduce_fn g_ar_fn = nullptr;
+static void* g_ar_user = nullptr;
+static int64_t g_ar_total = 0;
+void set_share_beta_allreduce(smplfit_allreduce_fn fn, void* user, int64_t global_batch) {
+  g_ar_fn = fn;
+  g_ar_user = user;
+  g_ar_total = global_batch;
+}
+
 template <int NS>
 static void solve_shared_t(const SolveArgs& so, double* Gd, double* Cd, double* sums, double* x, int groups,
                            cudaStream_t st) {
@@ -61,7 +71,12 @@ static void solve_shared_t(const SolveArgs& so, double* Gd, double* Cd, double* 
   SF_LAUNCH(k_gram_entries<NS>, dim3(groups, ShapeAcc<NS>::N), 32, 0, st, so, Gd);
   SF_LAUNCH(k_center_entries<NS>, groups, 32, 0, st, so, (const double*)Gd, Cd);
   SF_LAUNCH(k_batch_sum, NG + NS, 256, 0, st, (const double*)Cd, so.Bp, sums);
-  SF_LAUNCH(k_shared_solve<NS>, 1, 32, 0, st, so, (const double*)sums, x);
+  SolveArgs sg = so;
+  if (g_ar_fn != nullptr) {
+    g_ar_fn(sums, NG + NS, reinterpret_cast<void*>(st), g_ar_user);
+    sg.B = (int)g_ar_total;  // diag(lambda) is added once per instance of the WHOLE batch
+  }
+  SF_LAUNCH(k_shared_solve<NS>, 1, 32, 0, st, sg, (const double*)sums, x);
   SF_LAUNCH(k_shared_apply<NS>, groups, 32, 0, st, so, (const double*)Gd, (const double*)x);
   SF_LAUNCH(k_shape_out, dim3(groups, so.J), 32, 0, st, so, NS);
 }

@@ -43,19 +43,6 @@ static int num_sms() {
   return n;
 }
 
-// variant of the record kernel (SMPLFIT_B200_SHAPE_VARIANT, for A/B runs): 4 = packed FFMA2 math (default),
-// 0 = scalar FFMA, 8 warps + register cache, 1 = scalar FFMA, 12 warps, no cache, 5 = force k_shape_pass_v3
-static int shape_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SMPLFIT_B200_SHAPE_VARIANT");
-    v = e ? atoi(e) : 4;
-    if (v < 0 || v > 5) v = 4;
-  }
-  return v;
-}
-static int variant_warps(int v) { return v == 1 ? 12 : 8; }
-
 static size_t rec_stage_bytes(int ns) {
   const int nsp = (ns + 1) / 2 * 2, rec = (8 + 3 * nsp + 3) / 4 * 4;
   return (size_t)8 * 2 * REC_SUB * rec * sizeof(float) + 16 * 8 + 64 * 4 + 64;
@@ -72,7 +59,7 @@ ShapePlan plan_shape_pass(const smplfit_model_t* m, int groups) {
   const size_t v2_smem = (size_t)m->num_joints * (quad_rows_ns(m->fit_ns) / 4) * 512 + rec_stage_bytes(m->fit_ns);
   p.kind = 0;
   p.cap_joints = 0;
-  if (rec_ok && v2_smem <= 210 * 1024 && m->fit_ns <= 12 && shape_variant() != 5) {
+  if (rec_ok && v2_smem <= 210 * 1024 && m->fit_ns <= 12) {
     p.kind = 2;
   } else if (rec_ok) {
     p.kind = 3;
@@ -82,7 +69,7 @@ ShapePlan plan_shape_pass(const smplfit_model_t* m, int groups) {
     if (p.cap_joints > m->num_joints) p.cap_joints = m->num_joints;
   }
   p.use_rec = p.kind != 0;
-  p.warps = (p.kind == 2) ? variant_warps(shape_variant()) : 8;
+  p.warps = 8;
   // CTAs per instance group chosen so that the grid fills whole waves of the SM count
   const int V = m->num_vertices, sms = num_sms();
   const int c_min = (V + p.warps * 256 - 1) / (p.warps * 256), c_max = (V + p.warps * 32 - 1) / (p.warps * 32);
@@ -103,15 +90,6 @@ ShapePlan plan_shape_pass(const smplfit_model_t* m, int groups) {
 int max_shape_partials(const smplfit_model_t* m) {
   const int V = m->num_vertices;
   return (V + 8 * 32 - 1) / (8 * 32) + 1;
-}
-
-template <int NS, bool WEIGHTED, int WARPS, bool CACHE>
-static void shape_rec_launch(const ShapeArgs& a, int groups, const ShapePlan& p, cudaStream_t st) {
-  const size_t smem_rt = rt_smem_bytes(a.J, NS);
-  const size_t smem_red = (size_t)8 * ShapeAcc<NS>::N * 32 * sizeof(float);
-  const size_t smem = smem_rt > smem_red ? smem_rt : smem_red;
-  cudaFuncSetAttribute(k_shape_pass_rec<NS, WEIGHTED, WARPS, CACHE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  SF_LAUNCH((k_shape_pass_rec<NS, WEIGHTED, WARPS, CACHE>), dim3(p.n_partials, groups), WARPS * 32, smem, st, a);
 }
 
 template <int NS, bool WEIGHTED>
@@ -136,11 +114,7 @@ static void shape_pass_t(const ShapeArgs& sa, int groups, const ShapePlan& p, cu
     return;
   }
   if (p.use_rec) {
-    switch (shape_variant()) {
-      case 1: shape_rec_launch<NS, WEIGHTED, 12, false>(a, groups, p, st); break;
-      case 4: shape_v2_launch<NS, WEIGHTED>(a, groups, p, st); break;
-      default: shape_rec_launch<NS, WEIGHTED, 8, true>(a, groups, p, st); break;
-    }
+    shape_v2_launch<NS, WEIGHTED>(a, groups, p, st);
     return;
   }
   dim3 grid(p.n_partials, groups);
@@ -162,15 +136,6 @@ void launch_shape_pass(const ShapeArgs& a, int ns, int groups, const ShapePlan& 
 template <int NS>
 static void shape_solve_t(const SolveArgs& so, double* Gd, int groups, cudaStream_t st) {
   constexpr int NACC = ShapeAcc<NS>::N;
-  static int fused = -1;
-  if (fused < 0) {
-    const char* e = getenv("SMPLFIT_B200_SOLVE_FUSED");
-    fused = (e && atoi(e) == 1) ? 1 : 0;
-  }
-  if (fused) {
-    SF_LAUNCH(k_solve_fused<NS>, groups, GE_WARPS * 32, 0, st, so, Gd);
-    return;
-  }
   SF_LAUNCH(k_gram_entries<NS>, dim3(groups, NACC), 32, 0, st, so, Gd);
   SF_LAUNCH(k_shape_solve<NS>, groups, 32, 0, st, so, Gd);
   SF_LAUNCH(k_shape_out, dim3(groups, so.J), 32, 0, st, so, NS);

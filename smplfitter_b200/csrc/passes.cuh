@@ -51,6 +51,7 @@ void launch_shape_solve_scale(const SolveArgs& a, double* Gd, double* Zd, int ns
 // share_beta: Cd = [NG+NS][Bp] doubles, sums = NG+NS doubles, x = NS doubles (device scratch)
 void launch_shape_solve_shared(const SolveArgs& a, double* Gd, double* Cd, double* sums, double* x, int ns, int groups,
                                cudaStream_t st);
+void set_share_beta_allreduce(smplfit_allreduce_fn fn, void* user, int64_t global_batch);
 void launch_stats(const StatsArgs& legacy, const StatsRecArgs& rec, int ns, int ref_mode, bool weighted, bool use_rec,
                   int groups, cudaStream_t st);
 }  // namespace sf

@@ -437,9 +437,8 @@ __device__ __forceinline__ void gram_entry(const SolveArgs& a, double* __restric
 }
 
 // k_gram_entries<NS>: one single-warp CTA per (32 instances, entry): blockIdx.y = entry.  (Dealing the entries to the
-// warps of one CTA per group -- k_solve_fused below -- is slower: 154 us vs 66 + 39 + 15 us for the three separate
-// kernels; the entries are latency-bound and want to be spread over all SMs.)
-constexpr int GE_WARPS = 16;
+// warps of one CTA per group, with the solve and the output rows behind CTA barriers, measured slower: 154 us vs
+// 66 + 39 + 15 us for the three separate kernels; the entries are latency-bound and want to be spread over all SMs.)
 template <int NS>
 __global__ void __launch_bounds__(32) k_gram_entries(const SolveArgs a, double* __restrict__ Gd) {
   const int b = blockIdx.x * 32 + threadIdx.x;
@@ -639,23 +638,6 @@ static __global__ void __launch_bounds__(32) k_shape_out(const SolveArgs a, int 
   const int j = blockIdx.y;
   if (b >= a.Bp) return;
   shape_out_joint(a, NS, j, b);
-}
-
-// k_solve_fused<NS> (experiment, SMPLFIT_B200_SOLVE_FUSED=1; measured slower, see k_gram_entries): the three stages
-// of the plain shape solve in one CTA per 32 instances (GE_WARPS warps, lane =
-// instance): normal-equation entries dealt to the warps -> CTA barrier -> warp 0 centres, regularises and
-// Cholesky-solves in double -> CTA barrier -> reference joints and skinning rows, joints dealt to the warps.
-// (Global memory written before a CTA barrier is visible to the CTA after it; Gd is read through a plain pointer.)
-template <int NS>
-__global__ void __launch_bounds__(GE_WARPS * 32) k_solve_fused(const SolveArgs a, double* Gd) {
-  constexpr int NACC = NS * (NS + 1) / 2 + NS + 3 + 3 * NS + 1;
-  const int warp = threadIdx.x >> 5;
-  const int b = blockIdx.x * 32 + (threadIdx.x & 31);  // Bp is a multiple of 32: no partial groups
-  for (int e = warp; e < NACC; e += GE_WARPS) gram_entry<NS>(a, Gd, e, b);
-  __syncthreads();
-  if (warp == 0) shape_solve_body<NS>(a, Gd, b);
-  __syncthreads();
-  for (int j = warp; j < a.J; j += GE_WARPS) shape_out_joint(a, NS, j, b);
 }
 
 // ---------------------------------------------------------------------------------------

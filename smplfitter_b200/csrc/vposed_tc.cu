@@ -402,9 +402,7 @@ bool tc_gemm_run(const float* p_hi, const float* p_lo, int rows, int rows_alloc,
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(k_vposed_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(k_vposed_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(k_vposed_tc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(k_vposed_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
+        cudaFuncSetAttribute(k_vposed_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
       cudaGetLastError();
       return false;
     }
@@ -415,45 +413,6 @@ bool tc_gemm_run(const float* p_hi, const float* p_lo, int rows, int rows_alloc,
   const int grid = total < sms ? total : sms;
   if (bias) SF_LAUNCH((k_vposed_tc<true, false>), grid, THREADS, SMEM_BYTES, st, maps, bias, out, rows, Bp, Kt / TILE_K, tiles_m, total);
   else SF_LAUNCH((k_vposed_tc<false, false>), grid, THREADS, SMEM_BYTES, st, maps, bias, out, rows, Bp, Kt / TILE_K, tiles_m, total);
-  return true;
-}
-
-static bool split_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SMPLFIT_B200_GEMM_SPLIT");
-    v = (e && atoi(e) == 1) ? 1 : 0;  // measured: 0.233 ms vs 0.201 ms per launch with pre-split operands -> off by default
-  }
-  return v == 1;
-}
-
-// Same product from plain fp32 operands (hi / lo split inside the kernel): p [rows][p_ld] and f [Bp][f_ld], K valid
-// columns each (both leading dimensions multiples of 4 floats; columns / rows past the arrays are zero-filled by TMA).
-bool tc_gemm_run_f32(const float* p, int rows, int p_ld, const float* bias, const float* f, int f_rows, int f_ld, int K,
-                     float* out, int Bp, cudaStream_t st) {
-  if (!tc_enabled() || !split_enabled() || !p || !f || p_ld % 4 != 0 || f_ld % 4 != 0 || K > p_ld || K > f_ld) return false;
-  TcMaps maps;
-  if (!make_map(&maps.f_hi, f, (uint64_t)f_rows, (uint64_t)K, TILE_M, (uint64_t)f_ld) ||
-      !make_map(&maps.p_hi, p, (uint64_t)rows, (uint64_t)K, TILE_N, (uint64_t)p_ld))
-    return false;
-  maps.f_lo = maps.f_hi;
-  maps.p_lo = maps.p_hi;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(k_vposed_tc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(k_vposed_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
-      cudaGetLastError();
-      return false;
-    }
-    attr_set = true;
-  }
-  const int Bt = roundup(Bp, TILE_M);
-  const int tiles_m = Bt / TILE_M, tiles_n = (rows + TILE_N - 1) / TILE_N, total = tiles_m * tiles_n;
-  const int sms = sm_count_tc();
-  const int grid = total < sms ? total : sms;
-  const int k_blocks = (K + TILE_K - 1) / TILE_K;
-  if (bias) SF_LAUNCH((k_vposed_tc<true, true>), grid, THREADS, SMEM_BYTES, st, maps, bias, out, rows, Bp, k_blocks, tiles_m, total);
-  else SF_LAUNCH((k_vposed_tc<false, true>), grid, THREADS, SMEM_BYTES, st, maps, bias, out, rows, Bp, k_blocks, tiles_m, total);
   return true;
 }
 
@@ -480,21 +439,12 @@ static bool vposed_tc_run_with(const smplfit_model_t* m, const float* p_hi, cons
 bool vposed_tc_run(const smplfit_model_t* m, const float* feat, float* vposedT, int Bp, int Kp, void* scratch,
                    cudaStream_t st) {
   if (tc_enabled() && !tf32_forced() && vposed_f16_run(m, feat, vposedT, Bp, Kp, scratch, st)) return true;
-  // fp32 operands, split in shared memory: posedirs_fit is [3V][Kp], feat [Bp][Kp]
-  if (m->posedirs_fit != nullptr && encode_fn() != nullptr &&
-      tc_gemm_run_f32(m->posedirs_fit, 3 * m->num_vertices, Kp, m->v_template_fit, feat, Bp, Kp, m->num_pose_feats, vposedT,
-                      Bp, st))
-    return true;
   return vposed_tc_run_with(m, m->posedirs_hi, m->posedirs_lo, m->v_template_fit, feat, vposedT, Bp, Kp, scratch, st);
 }
 
 // rows in MODEL vertex order (forward LBS): v_posed^T[v*3+c] = v_template[v][c] + posedirs[v][c] . feat
 bool vposed_tc_run_model(const smplfit_model_t* m, const float* feat, float* vposedT, int Bp, int Kp, void* scratch,
                          cudaStream_t st) {
-  if (m->posedirs_model_f32 != nullptr && encode_fn() != nullptr &&
-      tc_gemm_run_f32(m->posedirs_model_f32, 3 * m->num_vertices, roundup(m->num_pose_feats, K_PAD), m->v_template, feat, Bp,
-                      Kp, m->num_pose_feats, vposedT, Bp, st))
-    return true;
   return vposed_tc_run_with(m, m->posedirs_model_hi, m->posedirs_model_lo, m->v_template, feat, vposedT, Bp, Kp, scratch, st);
 }
 

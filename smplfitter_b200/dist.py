@@ -12,6 +12,7 @@ row block per rank.
 
 from __future__ import annotations
 
+import contextlib
 import os
 from typing import Callable, Optional
 
@@ -104,6 +105,47 @@ def gather_rows(x: torch.Tensor, total: int, dst: int = 0, group=None) -> Option
     return None
 
 
+class _RawDoubles:
+    """Zero-copy view of `count` device doubles at `ptr` for torch.as_tensor (CUDA array interface)."""
+
+    def __init__(self, ptr: int, count: int):
+        self.__cuda_array_interface__ = {'data': (int(ptr), False), 'shape': (int(count),), 'typestr': '<f8',
+                                         'version': 2, 'strides': None}
+
+
+class share_beta_across_ranks:
+    """Context manager: while active, every ``share_beta=True`` shape solve of this process sums its centred normal
+    equations over the ranks of ``group`` (ONE all-reduce of S(S+1)/2 + S doubles per solve -- the only cross-instance
+    term of the fit, pt/lstsq.py:24-26), so the batch shards of all ranks share one set of betas.  Every rank must run
+    the same number of solves (same ``num_iter``, one ``fit`` call each).  ``global_batch`` = instances over all ranks."""
+
+    def __init__(self, global_batch: int, group=None, device=None):
+        from . import _native
+
+        self._native = _native
+        self.total, self.group, self.device = int(global_batch), group, device
+        self.error = None
+
+        def hook(ptr, count, stream, user):
+            try:
+                t = torch.as_tensor(_RawDoubles(ptr, count), device=self.device)
+                dist.all_reduce(t, group=self.group)
+            except BaseException as e:  # an exception cannot cross the C frame: keep it for __exit__
+                self.error = e
+
+        self._cb = _native.ALLREDUCE_FN(hook)  # keep the callback object alive while installed
+
+    def __enter__(self):
+        self._native.check(self._native.lib().smplfit_set_share_beta_allreduce(self._cb, None, self.total))
+        return self
+
+    def __exit__(self, *exc):
+        self._native.lib().smplfit_set_share_beta_allreduce(self._native.ALLREDUCE_FN(0), None, 0)
+        if self.error is not None and exc[0] is None:
+            raise self.error
+        return False
+
+
 def _pack(res: dict, keys: list, n: int) -> torch.Tensor:
     return torch.cat([res[k].reshape(n, -1) for k in keys], dim=1) if keys else torch.empty((n, 0))
 
@@ -115,13 +157,17 @@ def scatter_fit_gather(fit_fn: Callable[..., dict], total: int, target_vertices:
     """Shard a batch held by group rank ``src`` over the group, run ``fit_fn(verts, joints, **kw)`` on
     each shard (``BodyFitter.fit`` of the rank-local fitter) and gather the result dictionary
     on ``src``.  Every shard travels in ``n_chunks`` pieces; a rank fits piece *c* while piece *c + 1* is still
-    arriving.  ``share_beta`` couples the instances of the whole batch (one all-reduce of the normal
-    equations per shape solve would be needed) and is rejected here."""
-    if fit_kwargs.get('share_beta'):
-        raise NotImplementedError('share_beta couples all instances: fit it on one rank (BodyFitter.fit)')
+    arriving.  ``share_beta=True`` couples the instances of the whole batch: the shards are then fitted in one
+    piece each under ``share_beta_across_ranks`` (one all-reduce of the normal equations per shape solve); it needs
+    a CUDA fitter (the hook lives in the C library) and at least one instance per rank."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     lo, hi = shard_bounds(total, world, rank)
     n = hi - lo
+    shared = bool(fit_kwargs.get('share_beta'))
+    if shared:
+        if total < world:
+            raise ValueError('share_beta over ranks needs at least one instance per rank')
+        n_chunks = 1
     n_chunks = max(1, min(int(n_chunks), max(n, 1)))
     V, J = num_vertices, num_joints
 
@@ -156,10 +202,12 @@ def scatter_fit_gather(fit_fn: Callable[..., dict], total: int, target_vertices:
                 w.append(dist.irecv(tj_loc[a - lo:b - lo], _peer(group, src), group=group))
             waits.append(w)
     parts = []
-    for (a, b), w in zip(mine, waits):
-        for q in w:
-            q.wait()  # NCCL: orders the current stream after the transfer, does not block the host
-        parts.append(fit_fn(tv_loc[a - lo:b - lo], tj_loc[a - lo:b - lo] if has_joints else None, **fit_kwargs))
+    ctx = share_beta_across_ranks(total, group, device) if shared else contextlib.nullcontext()
+    with ctx:
+        for (a, b), w in zip(mine, waits):
+            for q in w:
+                q.wait()  # NCCL: orders the current stream after the transfer, does not block the host
+            parts.append(fit_fn(tv_loc[a - lo:b - lo], tj_loc[a - lo:b - lo] if has_joints else None, **fit_kwargs))
     if not parts:  # empty shard: the result keys / shapes still come from the fit function
         parts.append(fit_fn(tv_loc, tj_loc, **fit_kwargs))
     keys = sorted(parts[0])

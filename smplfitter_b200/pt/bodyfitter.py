@@ -232,11 +232,15 @@ class BodyFitter(nn.Module):
                     rec[s_, 0:4] = w_o[i].astype(np.float32).view(np.uint32)
                     rec[s_, 4] = pack
                     rec[s_, 5:8] = v_rest[i].astype(np.float32).view(np.uint32)
-        nsp = (ns + 1) // 2 * 2
-        sdl = (3 * nsp + 3) // 4 * 4
+        # bits 29 / 30 of the first record of every 8-slot block: some slot reloads within the first / second four slots
+        # of the block (the kernel's branch-free fast path needs four vertices without reloads)
+        any_rl = ((rec[:, 4] >> 24) & 0xF).reshape(-1, 2, 4).max(axis=2) != 0
+        rec[::8, 4] |= (any_rl[:, 0].astype(np.uint32) << 29) | (any_rl[:, 1].astype(np.uint32) << 30)
+        nsp4 = (ns + 3) // 4 * 4  # rows padded to 16-byte multiples
+        sdl = 3 * nsp4
         sd = np.zeros((nseg_pad * 32, sdl), np.float32)
         for x in range(3):
-            sd[live, x * nsp:x * nsp + ns] = sd_o[slot_of[live], x, :]
+            sd[live, x * nsp4:x * nsp4 + ns] = sd_o[slot_of[live], x, :]
         kf = (P + ns + 31) // 32 * 32
         pm = np.zeros((nseg_pad * 32, 3, kf), np.float64)
         pm[live, :, :P] = pd[slot_of[live]]

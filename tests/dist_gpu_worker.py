@@ -42,10 +42,19 @@ def main():
         res['diff'] = {k: float((out[k] - want[k]).abs().max().item()) for k in want}
         # instances are independent and every rank runs the same kernels: the sharded result is the single-GPU one
         res['ok'] = res['keys'] and all(v <= 1e-6 for v in res['diff'].values())
-        # share_beta over the ranks: one all-reduce of the centred normal equations per shape solve
-        print('DIST_RESULT ' + json.dumps(res), flush=True)
     else:
         assert out is None
+    # share_beta over the ranks: one all-reduce of the centred normal equations per shape solve
+    if total >= world:
+        kws = dict(kw, share_beta=True)
+        outs = sdist.scatter_fit_gather(fitter.fit, total, tv, tj, V, J, device=dev, **kws)
+        if rank == 0:
+            wants = fitter.fit(tv, tj, **kws)
+            res['diff_shared'] = {k: float((outs[k] - wants[k]).abs().max().item()) for k in wants}
+            res['betas_equal'] = bool((outs['shape_betas'] - outs['shape_betas'][:1]).abs().max().item() == 0.0)
+            res['ok'] = res['ok'] and res['betas_equal'] and all(v <= 2e-5 for v in res['diff_shared'].values())
+    if rank == 0:
+        print('DIST_RESULT ' + json.dumps(res), flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -64,9 +64,16 @@ def test_scatter_fit_gather_world2():
     assert q.get(timeout=10) is True
 
 
-def test_scatter_fit_gather_rejects_share_beta():
-    """share_beta couples every instance of the batch: the sharded helper refuses it before any communication."""
-    import pytest
+def test_share_beta_hook_symbol_and_view():
+    """share_beta over ranks: the C library exports the hook setter, and the zero-copy view class describes the
+    buffer the way torch's CUDA array interface expects (the all-reduce itself runs in tests/test_gpu_dist.py)."""
+    from smplfitter_b200 import _native
 
-    with pytest.raises(NotImplementedError):
-        sdist.scatter_fit_gather(_fake_fit, 4, None, None, 11, 5, share_beta=True)
+    L = _native.lib()
+    assert L.smplfit_set_share_beta_allreduce(_native.ALLREDUCE_FN(0), None, 0) == 0
+    cb = _native.ALLREDUCE_FN(lambda p, n, s, u: None)
+    assert L.smplfit_set_share_beta_allreduce(cb, None, 0) != 0  # a hook needs the global batch size
+    assert L.smplfit_set_share_beta_allreduce(cb, None, 8) == 0
+    assert L.smplfit_set_share_beta_allreduce(_native.ALLREDUCE_FN(0), None, 0) == 0
+    v = sdist._RawDoubles(0x1000, 65)
+    assert v.__cuda_array_interface__['shape'] == (65,) and v.__cuda_array_interface__['typestr'] == '<f8'

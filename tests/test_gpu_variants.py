@@ -1,7 +1,8 @@
-"""Every kernel variant behind an environment switch computes the same forward / fit as the default path
-(the switches are read once per process, so each variant runs in its own subprocess): tcgen05 vs SIMT GEMMs
-(posedirs contraction and the pair term of the closed-form Gramian), closed-form vs per-vertex Gramian shape pass,
-TMA-staged vs register-prefetch statistics / forward skinning, level-parallel vs sequential final adjustment."""
+"""The fallback kernels that back a product path (models / options the default kernels do not cover) compute the same
+forward / fit as the default path.  Each is forced through an environment switch (read once per process, so every
+variant runs in its own subprocess): SIMT instead of tcgen05 GEMMs, the unfused GEMM + vertex passes instead of the
+fused epilogue kernels, the per-vertex Gramian (weighted-fit) shape pass, the register-prefetch statistics pass, the
+sequential final adjustment."""
 import os
 import subprocess
 import sys
@@ -11,14 +12,11 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARIANTS = {
-    'gemm_simt': {'SMPLFIT_B200_GEMM': 'simt'},
-    'gemm_split_in_smem': {'SMPLFIT_B200_GEMM_SPLIT': '1'},
-    'solve_fused': {'SMPLFIT_B200_SOLVE_FUSED': '1'},
-    'per_vertex_gram': {'SMPLFIT_B200_SHAPE_VARIANT': '4'},
-    'stats_rec': {'SMPLFIT_B200_STATS_VARIANT': '0'},
-    'adjust_seq': {'SMPLFIT_B200_ADJUST': 'seq'},
-    'slot_mask_off': {'SMPLFIT_B200_SLOT_MASK': '0'},
-    'side_stream': {'SMPLFIT_B200_SIDE_STREAM': '2'},
+    'gemm_simt': {'SMPLFIT_B200_GEMM': 'simt'},                 # FP32 SIMT GEMMs (posedirs contraction, pair term)
+    'fit_unfused': {'SMPLFIT_B200_FIT_FUSED': '0'},             # GEMM -> HBM -> TMA-staged vertex passes
+    'per_vertex_gram': {'SMPLFIT_B200_SHAPE_VARIANT': '4', 'SMPLFIT_B200_FIT_FUSED': '0'},  # weighted-path kernels, unweighted
+    'stats_rec': {'SMPLFIT_B200_STATS_VARIANT': '0', 'SMPLFIT_B200_FIT_FUSED': '0'},        # register-prefetch statistics
+    'adjust_seq': {'SMPLFIT_B200_ADJUST': 'seq'},               # sequential final adjustment
 }
 
 
