@@ -17,7 +17,8 @@ kind of line for their own workload and are not the headline.
             timed region.
 `roofline`: the dominant kernel of the step, timed live with CUDA events on its stream in an
             instrumented repeat of the timed steps; algorithmic bytes per instance are stated in
-            DESIGN.md.
+            DESIGN.md.  Since round 2 the dominant kernel is k_fit_fused (blend-shape GEMM with the vertex pass in its
+            epilogue): its algorithmic HBM bytes are the targets alone, and `roofline.tensor` adds the tensor-core rate.
 `cpu_baseline` / `--impl reference`: the UNMODIFIED reference's own numpy backend
             (smplfitter.np.BodyFitter.fit from oracle/_ref, staged by build()) on the box's host cores on a
             bounded sample of the same workload; falls back to the numpy port (oracle/oracle_np.py,
@@ -151,6 +152,9 @@ def algorithmic_bytes(kernel, B, V, J, S):
     """ALGORITHMIC HBM bytes of one launch of ``kernel`` over B instances (DESIGN.md section 4 states them per
     instance): what the kernel must read / write once, not what it happens to move."""
     v = B * 4 * 3 * V
+    if 'k_fit_fused' in kernel:
+        return v, ('fused blend-shape GEMM + vertex pass: the targets are read once (12 V bytes per instance), the posed '
+                   'template stays in TMEM (average over the shape-stage and statistics launches)')
     if 'k_fwd_fused' in kernel:
         return v + B * 4 * (12 * J + S), 'forward LBS: (B,V,3) written once + joint rows / betas read'
     if 'k_vposed' in kernel:
@@ -162,6 +166,26 @@ def algorithmic_bytes(kernel, B, V, J, S):
     if 'k_fwd_skin' in kernel:
         return 2 * v, 'v_posed^T read once + (B,V,3) written once'
     return 2 * v, 'vertex pass: targets + v_posed^T read once (2 x 12 V bytes per instance)'
+
+
+def fused_tensor_rate(kernel, fitter, B, per_launch_ms):
+    """Tensor-core work of one k_fit_fused launch: 2 x 128-instance tiles x padded rows x K flops per product, three fp16
+    products per K step (hi*hi + hi*lo + lo*hi).  Reported next to the HBM figure; None for other kernels."""
+    if 'k_fit_fused' not in kernel or fitter is None or getattr(fitter, '_fq', None) is None:
+        return None
+    rows = fitter._fq['fq_nseg_pad'] * 96
+    bt = (B + 127) // 128 * 128
+    useful = 2.0 * bt * rows * fitter._fq['fq_kf']
+    peak = None
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            peak = float(json.load(f)['bf16_tflops'])
+    except Exception:
+        pass
+    issued = 3 * useful / (per_launch_ms / 1000) / 1e12
+    return {'issued_tflops_fp16': issued, 'useful_tflops': issued / 3, 'peak_bf16_tflops': peak,
+            'frac_issued': issued / peak if peak else None,
+            'note': 'fp16-split GEMM: 3 products per K step give fp32-grade accuracy; issued = 3 x useful'}
 
 
 def host_cores():
@@ -486,6 +510,16 @@ def main():
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
+    # the node's ceiling for the end-to-end leg: every rank copying its pinned targets to its GPU AT THE SAME TIME
+    # (one host memory system / PCIe root feeds all GPUs), nothing else running
+    ms_copy = None
+    if is_fit:
+        def step_copy():
+            tv.copy_(h_tv, non_blocking=True)
+            tj.copy_(h_tj, non_blocking=True)
+
+        step_copy()
+        ms_copy = timed(step_copy, 5) / 5
 
     # N > 1: the north_star's data movement -- the global batch on rank 0's GPU, NCCL scatter -> fit -> gather
     scatter_gather = None
@@ -571,7 +605,8 @@ def main():
             traffic = None
             try:  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu capture
                 with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
-                    traffic = json.load(f).get(args.config, {}).get(dom)
+                    tj_ = json.load(f)
+                traffic = tj_.get(dom) if args.config == 'smpl' else None
             except Exception:
                 pass
             roof = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
@@ -579,6 +614,7 @@ def main():
                     'avg_launch_ms': per_launch_ms, 'share_of_step': t / tot, 'algorithmic_bytes': alg_bytes,
                     'note': alg_note + '; the fit is FP32-issue bound by design (SURVEY.md 8d), the HBM fraction is '
                                        'reported as required',
+                    'tensor': fused_tensor_rate(dom, fitter if is_fit else None, B, per_launch_ms),
                     'kernel_ms_per_step': {k: v[1] / n_prof for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
                     'launches_per_step': {k: v[0] / n_prof for k, v in prof.items()}}
         cpu = None
@@ -608,10 +644,15 @@ def main():
                     'ms_per_step': ms_e2e / args.steps, 'chunk': E2E_CHUNK if is_fit else None,
                     'pcie_floor_ms': h2d / 54e9 * 1000,
                     'aggregate_h2d_gbs': h2d * world / (ms_e2e / args.steps / 1000) / 1e9,
+                    'concurrent_copy_ms': ms_copy,
+                    'concurrent_copy_gbs': (h2d * world / (ms_copy / 1000) / 1e9) if ms_copy else None,
+                    'frac_of_copy_ceiling': (ms_copy / (ms_e2e / args.steps)) if ms_copy else None,
                     'note': ('BodyFitter.fit_from_host: pinned host targets -> pinned host results, stream synchronised '
                              'every step' if is_fit else 'pinned host parameters -> BodyConverter.convert -> pinned host results')
                             + '; pcie_floor_ms = H2D bytes / 54 GB/s (measured pinned H2D rate of one GPU of the box, '
-                              'scripts/e2e_diag.py); aggregate_h2d_gbs = all ranks\' H2D bytes / step time'},
+                              'scripts/e2e_diag.py); aggregate_h2d_gbs = all ranks\' H2D bytes / step time; '
+                              'concurrent_copy_* = the same pinned buffers copied by all ranks at once with nothing else '
+                              'running (the node\'s measured ceiling for this leg), frac_of_copy_ceiling = that time / e2e time'},
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
             'v2v_mm_roundtrip': v2v_mm, 'v2v_mm_vs_reference': v2v_ref_mm, 'reference_pt_b200': ref_gpu,
             'lbs_forward': lbs, 'scatter_gather': scatter_gather,

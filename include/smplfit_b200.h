@@ -159,6 +159,11 @@ typedef struct smplfit_model {
   int32_t fq_scale_log2;
   int32_t fq_sdl;               /* 3 NSP4 */
   int32_t fq_nseg_pad;          /* n_segments rounded up to even */
+  /* ---- the post-LBS joint regressor in CSR form over the internal vertex order (fits without target joints regress
+   * them from the vertices, pt/bodyfitter.py:1342-1344; the licensed regressors have ~1 % non-zeros).  NULL: dense. */
+  const int32_t* jreg_ptr;      /* (J+1) */
+  const int32_t* jreg_idx;      /* (nnz) internal vertex positions */
+  const float* jreg_val;        /* (nnz) */
 } smplfit_model_t;
 
 /* Options of BodyFitter.fit (pt/bodyfitter.py:283-302). */

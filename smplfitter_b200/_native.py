@@ -48,6 +48,7 @@ class ModelStruct(C.Structure):
         + [('fit_P_hi', _F), ('fit_P_lo', _F), ('fit_kf', C.c_int32), ('fit_scale_log2', C.c_int32)]
         + [('fq_P_hi', _F), ('fq_P_lo', _F), ('fq_rec', _F), ('fq_sd', _F), ('fq_kf', C.c_int32),
            ('fq_scale_log2', C.c_int32), ('fq_sdl', C.c_int32), ('fq_nseg_pad', C.c_int32)]
+        + [('jreg_ptr', _F), ('jreg_idx', _F), ('jreg_val', _F)]
     )
 
 

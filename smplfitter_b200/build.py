@@ -18,7 +18,8 @@ LIB = os.path.join(HERE, 'libsmplfit_b200.so')
 SOURCES = ['fit.cu', 'fit_host.cu', 'pass_shape.cu', 'pass_shape_v3.cu', 'pass_lite.cu', 'pass_stats.cu', 'pass_scale.cu', 'forward.cu', 'fwd_fused.cu', 'fit_fused.cu', 'vposed_tc.cu']
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-    '-Xcompiler', '-fPIC', '--use_fast_math=false' if False else '-DSMPLFIT_BUILD',
+    '-Xcompiler', '-fPIC', '-DSMPLFIT_BUILD',
+    '-Xfatbin=-compress-all',  # (file size only: the device code is compressed in the fat binary, decompressed at load)
 ]
 
 

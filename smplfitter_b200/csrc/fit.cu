@@ -254,6 +254,11 @@ static void run_stats(FitCtx& c, int ref_mode, const float* ca0T, const float* a
 
 static void run_regress(FitCtx& c, const float* X, float* out) {
   const smplfit_model_t* m = c.m;
+  if (m->jreg_ptr != nullptr && m->jreg_idx != nullptr && m->jreg_val != nullptr) {
+    const long long nw = (long long)c.groups * m->num_joints;
+    SF_LAUNCH(k_regress_csr, (int)((nw + 3) / 4), 128, 0, c.st, m->jreg_ptr, m->jreg_idx, m->jreg_val, X, m->num_joints, c.Bp, out);
+    return;
+  }
   const int jblocks = (m->num_joints + 7) / 8;
   const long long warps = (long long)c.groups * jblocks;
   SF_LAUNCH(k_regress, (int)((warps + 3) / 4), 128, 0, c.st, m->J_regressor_fit, X, m->num_vertices,

@@ -203,6 +203,48 @@ static __global__ void __launch_bounds__(256) k_vposed_gemm_simt(const float* __
 }
 
 // ---------------------------------------------------------------------------------------
+// k_regress_csr: the same regression from the regressor's non-zeros (CSR over the internal vertex order): one warp per
+// (32 instances, joint); the three coordinate rows of every referenced vertex are coalesced 128-byte loads, four
+// non-zeros in flight per step.
+// ---------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(128) k_regress_csr(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                                                            const float* __restrict__ val, const float* __restrict__ X, int J,
+                                                            int Bp, float* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int g = warp / J, j = warp - g * J;
+  if (g * 32 >= Bp) return;
+  const int b = g * 32 + lane;
+  const int e0 = __ldg(ptr + j), e1 = __ldg(ptr + j + 1);
+  float acc[3] = {0.f, 0.f, 0.f};
+  int e = e0;
+  for (; e + 4 <= e1; e += 4) {
+    int i[4];
+    float w[4], x[4][3];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      i[u] = __ldg(idx + e + u);
+      w[u] = __ldg(val + e + u);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) x[u][c] = SF_IM(X, i[u] * 3 + c, Bp, b);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc[c] = fmaf(w[u], x[u][c], acc[c]);
+  }
+  for (; e < e1; ++e) {
+    const int i = __ldg(idx + e);
+    const float w = __ldg(val + e);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc[c] = fmaf(w, SF_IM(X, i * 3 + c, Bp, b), acc[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) SF_IM(out, j * 3 + c, Bp, b) = acc[c];
+}
+
+// ---------------------------------------------------------------------------------------
 // k_regress: joints^T[j*3+c][b] = sum_i Jreg_fit[j][i] X^T[i*3+c][b]
 // (pt/bodyfitter.py:1342-1344).  One warp per (instance group, block of 8 joints).
 // ---------------------------------------------------------------------------------------

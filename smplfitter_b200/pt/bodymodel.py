@@ -183,6 +183,12 @@ class BodyModel(nn.Module):
             'fit_P_hi': torch.from_numpy(pf_hi), 'fit_P_lo': torch.from_numpy(pf_lo),
             'template_mesh_fit': f32(template_mesh[order]),
         }
+        jr = jreg[:, order]
+        nzr, nzc = np.nonzero(jr)  # row-major: grouped by joint, ascending internal position
+        jptr = np.zeros(J + 1, np.int32)
+        jptr[1:] = np.cumsum(np.bincount(nzr, minlength=J))
+        t['jreg_ptr'], t['jreg_idx'] = i32(jptr), i32(nzc if len(nzc) else np.zeros(1, np.int32))
+        t['jreg_val'] = f32(jr[nzr, nzc] if len(nzc) else np.zeros(1, np.float32))
         if K <= 4 and J <= 64:
             v_rest = self.v_template.numpy().astype(np.float64) + np.einsum(
                 'vcp,p->vc', self.posedirs.numpy().astype(np.float64), eye_feat.astype(np.float64))
@@ -291,7 +297,8 @@ class BodyModel(nn.Module):
         for name in ('parents', 'skin_idx', 'skin_w', 'order', 'inv_order', 'seg_start', 'seg_part',
                      'part_seg_begin', 'part_kind', 'part_copy_src', 'part_flags', 'cas_table', 'cas_count',
                      'posedirs_fit', 'v_template_fit', 'template_mesh', 'template_joints_regressed',
-                     'J_regressor_fit', 'posedirs_hi', 'posedirs_lo', 'template_mesh_fit', 'fit_P_hi', 'fit_P_lo'):
+                     'J_regressor_fit', 'posedirs_hi', 'posedirs_lo', 'template_mesh_fit', 'fit_P_hi', 'fit_P_lo',
+                     'jreg_ptr', 'jreg_idx', 'jreg_val'):
             setattr(s, name, getattr(self, '_t_' + name).data_ptr())
         for name, buf in self.named_buffers():
             if not buf.is_contiguous():
