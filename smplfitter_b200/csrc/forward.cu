@@ -195,6 +195,42 @@ __global__ void k_csr_apply(const int32_t* __restrict__ indptr, const int32_t* _
   out[idx] = acc;
 }
 
+// The same SpMM with the instance's input vertices staged in shared memory (one CTA per instance): the (B,V_in,3) array
+// is read once with coalesced 16-byte loads, the ~3 gathers per output element hit shared memory, the output row is
+// written coalesced.  Used when V_in * 12 bytes fit (SMPL -> SMPL-X: 82.7 KB).
+__global__ void __launch_bounds__(512) k_csr_apply_smem(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                                        const float* __restrict__ data, int v_out, int v_in,
+                                                        const float* __restrict__ in, float* __restrict__ out) {
+  extern __shared__ __align__(16) float s_in[];  // [v_in][3]
+  const size_t b = blockIdx.x;
+  const float* src = in + b * (size_t)v_in * 3;
+  const int n = v_in * 3;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    for (int i = threadIdx.x; i < n / 4; i += blockDim.x) reinterpret_cast<float4*>(s_in)[i] = __ldg(s4 + i);
+    for (int i = (n / 4) * 4 + threadIdx.x; i < n; i += blockDim.x) s_in[i] = __ldg(src + i);
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s_in[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  float* dst = out + b * (size_t)v_out * 3;
+  // a thread per output vertex: the row's indices / weights are fetched once for its three coordinates
+  for (int r = threadIdx.x; r < v_out; r += blockDim.x) {
+    const int k0 = __ldg(indptr + r), k1 = __ldg(indptr + r + 1);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int k = k0; k < k1; ++k) {
+      const float w = __ldg(data + k);
+      const float* v = s_in + __ldg(indices + k) * 3;
+      a0 = fmaf(w, v[0], a0);
+      a1 = fmaf(w, v[1], a1);
+      a2 = fmaf(w, v[2], a2);
+    }
+    dst[r * 3] = a0;
+    dst[r * 3 + 1] = a1;
+    dst[r * 3 + 2] = a2;
+  }
+}
+
 struct FwdWs {
   float *vposedT, *feat, *skin, *betaT;
   void* tc_scratch;
@@ -282,8 +318,14 @@ extern "C" int smplfit_convert_vertices(const int32_t* indptr, const int32_t* in
   if (batch <= 0) return SMPLFIT_OK;
   const long long total = (long long)batch * v_out * 3;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  SF_LAUNCH(k_csr_apply, (unsigned)((total + 255) / 256), 256, 0, st, indptr, indices, data, v_out, v_in, total,
-            in_vertices, out_vertices);
+  const size_t smem = (size_t)v_in * 3 * sizeof(float);
+  if (smem <= 200 * 1024 && batch <= 0x7fffffffLL) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_csr_apply_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    SF_LAUNCH(k_csr_apply_smem, (unsigned)batch, 512, smem, st, indptr, indices, data, v_out, v_in, in_vertices, out_vertices);
+  } else {
+    SF_LAUNCH(k_csr_apply, (unsigned)((total + 255) / 256), 256, 0, st, indptr, indices, data, v_out, v_in, total,
+              in_vertices, out_vertices);
+  }
   SF_CHECK_LAST();
   return SMPLFIT_OK;
 }

@@ -27,8 +27,30 @@ def _get(handle: int):
     ref = _registry.get(handle)
     mod = ref() if ref is not None else None
     if mod is None:
-        raise RuntimeError(f'smplfitter_b200: module handle {handle} is no longer alive')
+        raise RuntimeError(
+            f'smplfitter_b200: module handle {handle} is not alive in this process. A scripted smplfitter_b200 module '
+            'dispatches to the Python module it was scripted from: keep that module alive, and do not torch.jit.save / '
+            'load it into another process (script the module again there).')
     return mod
+
+
+class RegisteredModule:
+    """Mixin of the nn.Modules that dispatch through the ops below: a copy (``copy.deepcopy``, pickling) gets its OWN
+    handle, so it never runs on the buffers of the module it was copied from."""
+
+    def __deepcopy__(self, memo):
+        import copy
+
+        new = type(self).__new__(type(self))
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        new.__dict__['_handle'] = register(new)
+        return new
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self.__dict__['_handle'] = register(self)
 
 
 def _empty_like_dev(t: torch.Tensor) -> torch.Tensor:

@@ -18,7 +18,7 @@ from . import _ops
 from .bodyfitter import BodyFitter
 
 
-class BodyConverter(nn.Module):
+class BodyConverter(_ops.RegisteredModule, nn.Module):
     """Converts between SMPL-family parametrisations.
 
     ``vertex_converter_csr`` may be passed explicitly as a ``scipy.sparse`` CSR matrix of

@@ -19,7 +19,7 @@ from .. import _native
 from . import _ops
 
 
-class BodyFitter(nn.Module):
+class BodyFitter(_ops.RegisteredModule, nn.Module):
     """Fits body-model parameters to target vertices (and optionally joints).
 
     Parameters:

@@ -70,7 +70,7 @@ def _slot_tables(seg_start, joint_sets, num_joints):
     return seg_slots, yj_start, yj_entry
 
 
-class BodyModel(nn.Module):
+class BodyModel(_ops.RegisteredModule, nn.Module):
     """Statistical body model of the SMPL family (forward linear blend skinning).
 
     Parameters are those of the reference (pt/bodymodel.py:53-64).  Model data comes from

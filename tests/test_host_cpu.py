@@ -274,3 +274,19 @@ def test_header_is_plain_c(tmp_path):
     r = subprocess.run([gcc, '-std=c11', '-Wall', '-Werror', '-fsyntax-only', '-I', os.path.join(ROOT, 'include'), str(src)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_copies_get_their_own_handle():
+    """A deep copy / unpickled copy of a module dispatches to ITS buffers (own registry handle), not to the original's."""
+    import copy
+    import pickle
+
+    from smplfitter_b200.pt import BodyFitter, BodyModel, _ops
+
+    bm = BodyModel('smpl_tiny')
+    fitter = BodyFitter(bm)
+    f2 = copy.deepcopy(fitter)
+    assert f2._handle != fitter._handle and f2.body_model._handle != bm._handle
+    assert _ops._get(f2._handle) is f2 and _ops._get(f2.body_model._handle) is f2.body_model
+    bm3 = pickle.loads(pickle.dumps(bm))
+    assert bm3._handle != bm._handle and _ops._get(bm3._handle) is bm3
