@@ -558,6 +558,22 @@ def main():
         dist.barrier()
 
     out = step_resident()
+    # latency of one small fit (the launch chain is what bounds it): median of 20 calls at batch 32, device time
+    lat32 = None
+    if is_fit and rank == 0:
+        tv32, tj32 = tv[:32].contiguous(), tj[:32].contiguous()
+        for _ in range(3):
+            fitter.fit(tv32, tj32, **FIT_KW)
+        ts = []
+        for _ in range(20):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev)
+            a0.record()
+            fitter.fit(tv32, tj32, **FIT_KW)
+            a1.record()
+            torch.cuda.synchronize(dev)
+            ts.append(a0.elapsed_time(a1))
+        lat32 = sorted(ts)[len(ts) // 2]
     v2v_mm = ref_gpu = v2v_ref_mm = lbs = None
     if is_fit:
         # parity spot check inside the bench run (not timed): v2v of the re-posed fit against the targets
@@ -655,7 +671,7 @@ def main():
                               'running (the node\'s measured ceiling for this leg), frac_of_copy_ceiling = that time / e2e time'},
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
             'v2v_mm_roundtrip': v2v_mm, 'v2v_mm_vs_reference': v2v_ref_mm, 'reference_pt_b200': ref_gpu,
-            'lbs_forward': lbs, 'scatter_gather': scatter_gather,
+            'lbs_forward': lbs, 'scatter_gather': scatter_gather, 'latency_batch32_ms': lat32,
         }
         print(json.dumps(line))
     if world > 1:

@@ -275,18 +275,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_fit_fused(const __grid_constant_
   if (warp < 4) {
     if (warp == 0) {
       if (lane == 0) {
-        // ---- TMA producer: GEMM operands + the tile's slot records ----
-        int it = 0, tcount = 0;
-        for (int L = L0; L < L1; ++L, ++tcount) {
+        // ---- TMA producer: GEMM operands ----
+        int it = 0;
+        for (int L = L0; L < L1; ++L) {
           const int tm = L / a.tiles_n, tn = L - tm * a.tiles_n;
           const int b0 = tm * TILE_M, n0 = tn * TILE_N;
-          const int as = tcount & 1;
-          // the tile's slot records (+ shape directions), into the buffer that goes with its accumulator
-          mbar_wait_parked(&acc_empty[as], ((tcount >> 1) & 1) ^ 1);
-          mbar_expect_tx(&rec_full[as], (uint32_t)(REC_TILE_BYTES + sd_tile));
-          bulk_g2s(rec_area + as * REC_TILE_BYTES, a.rec + (size_t)tn * TILE_V * REC_WORDS, REC_TILE_BYTES, &rec_full[as]);
-          if (MODE == 2)
-            bulk_g2s(sd_area + as * sd_tile, a.sd + (size_t)tn * TILE_V * a.sdl, (uint32_t)sd_tile, &rec_full[as]);
+          // (only the smem stages gate these loads: the operands of the next tile are fetched while the epilogue of
+          // the current one still owns both accumulators; the MMA issuer waits for the accumulator)
           for (int kb = 0; kb < a.k_blocks; ++kb, ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
@@ -336,12 +331,22 @@ __global__ void __launch_bounds__(THREADS, 1) k_fit_fused(const __grid_constant_
       __syncwarp();
     } else if (warp == 2) {
       if (lane == 0) {
-        // ---- target producer: per half h a ring of TRING blocks of GV vertices x 128 instances, filled as far ahead
+        // ---- record + target producer: per half h a ring of TRING blocks of GV vertices x 128 instances, filled as far ahead
         // of the epilogue warps as the ring allows (the HBM latency of the targets is off their critical path) ----
-        int cnt[2] = {0, 0};
-        for (int L = L0; L < L1; ++L) {
+        int cnt[2] = {0, 0}, tcount = 0;
+        for (int L = L0; L < L1; ++L, ++tcount) {
           const int tm = L / a.tiles_n, tn = L - tm * a.tiles_n;
           const int b0 = tm * TILE_M;
+          {
+            // the tile's slot records (+ shape directions), into the buffer that goes with its accumulator (free once
+            // the epilogue of two tiles ago has released it)
+            const int as = tcount & 1;
+            mbar_wait_parked(&acc_empty[as], ((tcount >> 1) & 1) ^ 1);
+            mbar_expect_tx(&rec_full[as], (uint32_t)(REC_TILE_BYTES + sd_tile));
+            bulk_g2s(rec_area + as * REC_TILE_BYTES, a.rec + (size_t)tn * TILE_V * REC_WORDS, REC_TILE_BYTES, &rec_full[as]);
+            if (MODE == 2)
+              bulk_g2s(sd_area + as * sd_tile, a.sd + (size_t)tn * TILE_V * a.sdl, (uint32_t)sd_tile, &rec_full[as]);
+          }
           int i0[2], len[2], part;
           bool stat, act[2];
 #pragma unroll

@@ -137,7 +137,13 @@ template <int NS>
 static void shape_solve_t(const SolveArgs& so, double* Gd, int groups, cudaStream_t st) {
   constexpr int NACC = ShapeAcc<NS>::N;
   SF_LAUNCH(k_gram_entries<NS>, dim3(groups, NACC), 32, 0, st, so, Gd);
-  SF_LAUNCH(k_shape_solve<NS>, groups, 32, 0, st, so, Gd);
+  if constexpr (NS >= 3) {  // (trans is written by rows 0..2)
+    const size_t smem = shape_solve_par_smem(NS);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_shape_solve_par<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    SF_LAUNCH(k_shape_solve_par<NS>, groups, NS * 32, smem, st, so, (const double*)Gd);
+  } else {
+    SF_LAUNCH(k_shape_solve<NS>, groups, 32, 0, st, so, Gd);
+  }
   SF_LAUNCH(k_shape_out, dim3(groups, so.J), 32, 0, st, so, NS);
 }
 

@@ -414,22 +414,40 @@ __device__ __forceinline__ void gram_entry(const SolveArgs& a, double* __restric
     }
   }
   if (a.tjT != nullptr) {  // joint block (pt/bodyfitter.py:1050-1058, _gram_block :1598)
+    // per joint the three-coordinate dot product is formed in fp32 (the reference forms the whole block in an fp32
+    // GEMM and casts to f64 afterwards, :1034-1062); the sum over joints is accumulated in double.  Conversions and
+    // FP64 arithmetic are what bounds this kernel: one F2F + one DFMA per joint instead of six + four.
+    if (kind == 4) {
+      for (int j = 0; j < J; ++j) acc += a.jwT ? (double)SF_IM(a.jwT, j, Bp, b) : 1.0;
+    } else if (kind == 0) {
 #pragma unroll 4
-    for (int j = 0; j < J; ++j) {
-      const double w = a.jwT ? (double)SF_IM(a.jwT, j, Bp, b) : 1.0;
-      if (kind == 4) { acc += w; continue; }
-      if (kind == 0 || kind == 1) {
-        for (int cc = 0; cc < 3; ++cc) {
-          const float* prow = a.Pext + (size_t)(j * TW + cc * (1 + NS)) * Bp + b;
-          const double js = (double)prow[(size_t)(1 + s) * Bp];
-          const double other = (kind == 0) ? (double)prow[(size_t)(1 + t) * Bp]
-                                           : (double)SF_IM(a.tjT, j * 3 + cc, Bp, b) - (double)prow[0];
-          acc += w * js * other;
-        }
-      } else {
+      for (int j = 0; j < J; ++j) {
+        const float* prow = a.Pext + (size_t)(j * TW) * Bp + b;
+        float d = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc)
+          d = fmaf(prow[(size_t)(cc * (1 + NS) + 1 + s) * Bp], prow[(size_t)(cc * (1 + NS) + 1 + t) * Bp], d);
+        if (a.jwT) d *= SF_IM(a.jwT, j, Bp, b);
+        acc += (double)d;
+      }
+    } else if (kind == 1) {
+#pragma unroll 4
+      for (int j = 0; j < J; ++j) {
+        const float* prow = a.Pext + (size_t)(j * TW) * Bp + b;
+        float d = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc)
+          d = fmaf(prow[(size_t)(cc * (1 + NS) + 1 + s) * Bp], SF_IM(a.tjT, j * 3 + cc, Bp, b) - prow[(size_t)(cc * (1 + NS)) * Bp], d);
+        if (a.jwT) d *= SF_IM(a.jwT, j, Bp, b);
+        acc += (double)d;
+      }
+    } else {
+#pragma unroll 4
+      for (int j = 0; j < J; ++j) {
         const float* prow = a.Pext + (size_t)(j * TW + c * (1 + NS)) * Bp + b;
-        acc += (kind == 2) ? w * ((double)SF_IM(a.tjT, j * 3 + c, Bp, b) - (double)prow[0])
-                           : w * (double)prow[(size_t)(1 + s) * Bp];
+        float d = (kind == 2) ? SF_IM(a.tjT, j * 3 + c, Bp, b) - prow[0] : prow[(size_t)(1 + s) * Bp];
+        if (a.jwT) d *= SF_IM(a.jwT, j, Bp, b);
+        acc += (double)d;
       }
     }
   }
@@ -498,6 +516,89 @@ __device__ __forceinline__ void shape_solve_body(const SolveArgs& a, const doubl
     SF_IM(a.trans, c, Bp, b) = (float)m;
   }
 }
+
+// k_shape_solve_par<NS>: the same solve with the rows of the normal matrix dealt to the warps of a CTA (lane = instance,
+// warp = row, the matrix in shared memory as [row][col][32 lanes] doubles): centring and regularisation per row, a
+// right-looking Cholesky with three CTA barriers per column, column-oriented forward / backward substitution.  The
+// dependent chain shrinks from ~NS^3/3 to ~NS^2 FP64 operations per instance and NS times more warps are in flight
+// (the thread-per-instance kernel ran one warp per SM: 39 us for 4096 instances at NS = 10).
+template <int NS>
+__global__ void __launch_bounds__(NS * 32) k_shape_solve_par(const SolveArgs a, const double* __restrict__ Gd) {
+  extern __shared__ __align__(16) double s_g[];  // G [NS][NS][32] | rhs [NS][32] | SA [3][NS][32] | Sb [3][32]
+  constexpr int NG = NS * (NS + 1) / 2;
+  const int lane = threadIdx.x & 31, r = threadIdx.x >> 5;
+  const int b = blockIdx.x * 32 + lane;
+  const int Bp = a.Bp;
+  double* G = s_g;
+  double* rhs = G + NS * NS * 32;
+  double* SA = rhs + NS * 32;
+  double* Sb = SA + 3 * NS * 32;
+#define SG(i, j) G[((i) * NS + (j)) * 32 + lane]
+  // stage SA, Sb (every row needs them)
+  for (int q = r; q < 3 * NS + 3; q += NS) {
+    if (q < 3 * NS) SA[q * 32 + lane] = Gd[(size_t)(NG + NS + 3 + q) * Bp + b];
+    else Sb[(q - 3 * NS) * 32 + lane] = Gd[(size_t)(NG + NS + (q - 3 * NS)) * Bp + b];
+  }
+  const double W = Gd[(size_t)(NG + NS + 3 + 3 * NS) * Bp + b];
+  const double Ws = (W == 0.0) ? 1.0 : W;
+  __syncthreads();
+  {
+    // row r: centre with the covariance identity, regularise (pt/bodyfitter.py:1060-1081)
+    const double sa0 = SA[(0 * NS + r) * 32 + lane], sa1 = SA[(1 * NS + r) * 32 + lane], sa2 = SA[(2 * NS + r) * 32 + lane];
+    for (int t = 0; t <= r; ++t) {  // lower triangle: entry (t, r) of the upper-triangle list, t <= r
+      const int o = t * NS - t * (t - 1) / 2 + (r - t);
+      double g = Gd[(size_t)o * Bp + b];
+      g -= (sa0 * SA[(0 * NS + t) * 32 + lane] + sa1 * SA[(1 * NS + t) * 32 + lane] + sa2 * SA[(2 * NS + t) * 32 + lane]) / Ws;
+      SG(r, t) = g;
+    }
+    double rc = Gd[(size_t)(NG + r) * Bp + b] - (sa0 * Sb[lane] + sa1 * Sb[32 + lane] + sa2 * Sb[64 + lane]) / Ws;
+    double lam = (r < 2) ? (double)a.reg2 : (double)a.reg;
+    double ref = 0.0;
+    if (r < a.S) {
+      if (a.beta_ref != nullptr && b < a.B) ref = (double)a.beta_ref[(size_t)b * a.S + r];
+    } else {  // kid unknown
+      lam = (double)a.kid_reg;
+      if (a.kid_ref != nullptr && b < a.B) ref = (double)a.kid_ref[b];
+    }
+    SG(r, r) += lam;
+    rhs[r * 32 + lane] = rc + lam * ref;
+  }
+  // Cholesky, lower triangle in place (no pivoting; failures surface as NaN like torch.linalg.cholesky_ex)
+  for (int j = 0; j < NS; ++j) {
+    __syncthreads();
+    if (r == j) SG(j, j) = sqrt(SG(j, j));
+    __syncthreads();
+    if (r > j) SG(r, j) = SG(r, j) / SG(j, j);
+    __syncthreads();
+    if (r > j) {
+      const double lrj = SG(r, j);
+      for (int k = j + 1; k <= r; ++k) SG(r, k) -= lrj * SG(k, j);
+    }
+  }
+  // forward substitution L y = rhs (column oriented: once y_i is final every later row subtracts its share)
+  for (int i = 0; i < NS; ++i) {
+    __syncthreads();
+    if (r == i) rhs[i * 32 + lane] = rhs[i * 32 + lane] / SG(i, i);
+    __syncthreads();
+    if (r > i) rhs[r * 32 + lane] -= SG(r, i) * rhs[i * 32 + lane];
+  }
+  // backward substitution L^T x = y
+  for (int i = NS - 1; i >= 0; --i) {
+    __syncthreads();
+    if (r == i) rhs[i * 32 + lane] = rhs[i * 32 + lane] / SG(i, i);
+    __syncthreads();
+    if (r < i) rhs[r * 32 + lane] -= SG(i, r) * rhs[i * 32 + lane];
+  }
+  __syncthreads();
+  SF_IM(a.beta, r, Bp, b) = (float)rhs[r * 32 + lane];
+  if (r < 3) {
+    double m = Sb[r * 32 + lane] / Ws;
+    for (int s = 0; s < NS; ++s) m -= SA[(r * NS + s) * 32 + lane] / Ws * rhs[s * 32 + lane];
+    SF_IM(a.trans, r, Bp, b) = (float)m;
+  }
+#undef SG
+}
+inline size_t shape_solve_par_smem(int ns) { return (size_t)(ns * ns + ns + 3 * ns + 3) * 32 * sizeof(double); }
 
 template <int NS>
 __global__ void __launch_bounds__(32) k_shape_solve(const SolveArgs a, const double* __restrict__ Gd) {
