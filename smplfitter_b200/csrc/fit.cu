@@ -136,6 +136,7 @@ struct FitCtx {
   bool lite;  // closed-form Gramian + light vertex pass (unweighted shape stage)
   bool fused;         // vertex passes in the epilogue of the blend-shape GEMM (fit_fused.cu): no v_posed^T in HBM
   bool vposed_valid;  // w.vposedT holds the posed template of the current orientations (non-fused consumers)
+  bool feats_ready;   // the fused passes' feature rows are maintained by k_front_fused / k_shape_out
   ShapePlan plan;
 };
 
@@ -146,6 +147,8 @@ static void choose_shape_path(FitCtx& c, RotArgs& ra) {
   ra.RT4 = c.lite ? nullptr : c.w.RT4;
   ra.rt4_clay = c.plan.kind == 3;
 }
+
+static void set_feature_rows(FitCtx& c, SolveArgs& so);
 
 static void run_gemm(FitCtx& c) {
   const smplfit_model_t* m = c.m;
@@ -164,7 +167,7 @@ static void run_shape(FitCtx& c, int scale_mode, const float* beta_ref, const fl
   bool shape_fused = false;
   if (c.lite && c.fused && scale_mode == 0)  // (the scale pass of the final solve reads v_posed^T)
     shape_fused = fit_fused_run(m, 2, c.B, c.Bp, c.w.feat, c.Kp, nullptr, c.w.tT, nullptr, c.w.RT12, nullptr, nullptr, nullptr, 0,
-                                c.w.gpart, c.w.fq_scratch, c.st);
+                                c.w.gpart, c.w.fq_scratch, c.feats_ready, c.st);
   if (!shape_fused) run_gemm(c);
   ShapeArgs sa;
   sa.tT = c.w.tT; sa.vwT = c.vwT_shape; sa.vposedT = c.w.vposedT; sa.RT = c.w.RT;
@@ -184,6 +187,7 @@ static void run_shape(FitCtx& c, int scale_mode, const float* beta_ref, const fl
   } else {
     launch_shape_pass(sa, m->fit_ns, c.groups, c.plan, c.st);
   }
+  set_feature_rows(c, so);
   so.partials = c.w.gpart; so.Pext = c.w.Pext; so.RT = c.w.RT;
   so.tjT = c.has_joints ? c.w.tjT : nullptr; so.jwT = c.jwT_shape;
   so.beta_ref = beta_ref; so.kid_ref = kid_ref;
@@ -235,7 +239,7 @@ static void run_stats(FitCtx& c, int ref_mode, const float* ca0T, const float* a
   }
   if (ref_mode == 1 && c.fused &&
       fit_fused_run(m, 3, c.B, c.Bp, c.w.feat, c.Kp, c.w.beta, c.w.tT, c.w.vwT, c.w.skin4, c.w.tjT, ca0T, aT_out,
-                    aT_out != nullptr, c.w.spart, c.w.fq_scratch, c.st))
+                    aT_out != nullptr, c.w.spart, c.w.fq_scratch, c.feats_ready, c.st))
     return;
   if (ref_mode == 1 && !c.vposed_valid) run_gemm(c);
   if (ref_mode == 1 && stats_lite_enabled(m)) {
@@ -266,10 +270,40 @@ static void run_regress(FitCtx& c, const float* X, float* out) {
 }
 
 // rotation fit per (instance, part), then the pose-dependent front of the next shape solve
+// feature-row pointers of the fused passes into a SolveArgs (k_shape_out writes the unknowns' columns)
+static void set_feature_rows(FitCtx& c, SolveArgs& so) {
+  so.fq_hi = so.fq_lo = nullptr;
+  so.fq_kf = so.fq_p = 0;
+  if (!c.feats_ready) return;
+  void *hi, *lo;
+  fit_fused_feature_rows(c.m, c.Bp, c.w.fq_scratch, &hi, &lo);
+  so.fq_hi = reinterpret_cast<__half*>(hi); so.fq_lo = reinterpret_cast<__half*>(lo);
+  so.fq_kf = c.m->fq_kf; so.fq_p = c.m->num_pose_feats;
+}
+
 static void run_rot(FitCtx& c, const RotArgs& ra, bool fit) {
   const int J = c.m->num_joints;
   c.vposed_valid = false;
   if (fit) SF_LAUNCH(k_rot_fit, dim3(c.groups, J), 32, 0, c.st, ra);
+  c.feats_ready = false;
+  if (c.fused && ra.RT4 == nullptr && c.w.fq_scratch != nullptr) {
+    // closed-form path: relative rotations, row tables, kinematic-chain columns and the fused passes' feature rows in
+    // one kernel
+    int fkw = FF_WARPS;
+    while (fkw > 1 && front_fused_smem_bytes(J, c.m->fq_kf, fkw) > 200 * 1024) --fkw;
+    const size_t smem = front_fused_smem_bytes(J, c.m->fq_kf, fkw);
+    if (smem <= 200 * 1024) {
+      RotArgs rf = ra;
+      void *hi, *lo;
+      fit_fused_feature_rows(c.m, c.Bp, c.w.fq_scratch, &hi, &lo);
+      rf.fq_hi = reinterpret_cast<__half*>(hi); rf.fq_lo = reinterpret_cast<__half*>(lo);
+      rf.fq_kf = c.m->fq_kf; rf.fk_warps = fkw;
+      if (smem > 48 * 1024) cudaFuncSetAttribute(k_front_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      SF_LAUNCH(k_front_fused, c.groups, FF_WARPS * 32, smem, c.st, rf);
+      c.feats_ready = true;
+      return;
+    }
+  }
   SF_LAUNCH(k_front_rel, dim3(c.groups, J), 32, 0, c.st, ra);
   SF_LAUNCH(k_front_fk, dim3(c.groups, c.m->fit_ns + 1), 32, 0, c.st, ra);
 }
@@ -375,6 +409,7 @@ extern "C" int smplfit_fit(const smplfit_model_t* m, int64_t batch, const float*
   c.use_rec = c.plan.use_rec;
   c.fused = fit_fused_available(m);
   c.vposed_valid = false;
+  c.feats_ready = false;
   c.w = carve(workspace, m, batch, has_joints, vertex_weights != nullptr, joint_weights != nullptr, has_init);
   if (!workspace || c.w.bytes > workspace_bytes) return fail(SMPLFIT_ERR_WORKSPACE, "workspace too small");
   FitWs& w = c.w;
@@ -487,6 +522,7 @@ extern "C" int smplfit_fit_known_pose(const smplfit_model_t* m, int64_t batch, c
   c.use_rec = c.plan.use_rec;
   c.fused = fit_fused_available(m);
   c.vposed_valid = false;
+  c.feats_ready = false;
   c.w = carve(workspace, m, batch, has_joints, vertex_weights != nullptr, joint_weights != nullptr, 1);
   if (!workspace || c.w.bytes > workspace_bytes) return fail(SMPLFIT_ERR_WORKSPACE, "workspace too small");
   FitWs& w = c.w;
@@ -573,6 +609,7 @@ extern "C" int smplfit_fit_known_shape(const smplfit_model_t* m, int64_t batch, 
   c.use_rec = c.plan.use_rec;
   c.fused = fit_fused_available(m);
   c.vposed_valid = false;
+  c.feats_ready = false;
   c.w = carve(workspace, m, batch, has_joints, vertex_weights != nullptr, joint_weights != nullptr, 1);
   if (!workspace || c.w.bytes > workspace_bytes) return fail(SMPLFIT_ERR_WORKSPACE, "workspace too small");
   FitWs& w = c.w;
@@ -616,6 +653,7 @@ extern "C" int smplfit_fit_known_shape(const smplfit_model_t* m, int64_t batch, 
   const float* R_final = w.R;
   for (int it = 0; it < o->num_iter; ++it) {
     const bool last = (it == o->num_iter - 1);
+    set_feature_rows(c, so);
     SF_LAUNCH(k_shape_out, dim3(c.groups, J), 32, 0, c.st, so, m->fit_ns);
     run_stats(c, 1, w.refj, nullptr, w.aT);  // reference vertices skinned on the fly, stored for the moments
     aj = w.refj;

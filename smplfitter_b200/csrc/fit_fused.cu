@@ -761,9 +761,16 @@ size_t fit_fused_scratch_bytes(const smplfit_model_t* m, int Bp) {
   return (size_t)2 * roundup(Bp, TILE_M) * m->fq_kf * sizeof(__half) + 512;
 }
 
+void fit_fused_feature_rows(const smplfit_model_t* m, int Bp, void* scratch, void** hi, void** lo) {
+  const int Bt = roundup(Bp, TILE_M);
+  __half* h = reinterpret_cast<__half*>(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
+  *hi = h;
+  *lo = h + (size_t)Bt * m->fq_kf;
+}
+
 bool fit_fused_run(const smplfit_model_t* m, int mode, int B, int Bp, const float* feat, int Kp, const float* beta,
                    const float* tT, const float* vwT, const float* quads, const float* ct0, const float* ca0, float* aT_out,
-                   int all_segments, float* partials, void* scratch, cudaStream_t st) {
+                   int all_segments, float* partials, void* scratch, bool feats_ready, cudaStream_t st) {
   if (!fit_fused_available(m) || scratch == nullptr) return false;
   const int Bt = roundup(Bp, TILE_M), Kf = m->fq_kf;
   __half* hi = reinterpret_cast<__half*>(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
@@ -775,9 +782,11 @@ bool fit_fused_run(const smplfit_model_t* m, int mode, int B, int Bp, const floa
       !make_h_map(&maps.p_hi, m->fq_P_hi, p_rows, (uint64_t)Kf, TILE_N) || !make_h_map(&maps.p_lo, m->fq_P_lo, p_rows, (uint64_t)Kf, TILE_N) ||
       !make_t_map(&maps.t, tT, (uint64_t)3 * m->num_vertices, (uint64_t)Bp))
     return false;
-  const size_t n2 = (size_t)Bt * (Kf / 2);
-  SF_LAUNCH(k_fq_feat, (unsigned)((n2 + 255) / 256), 256, 0, st, feat, beta, B, Bp, Kp, m->num_pose_feats, m->fit_ns, Kf, n2,
-            reinterpret_cast<__half2*>(hi), reinterpret_cast<__half2*>(lo));
+  if (!feats_ready) {  // (k_front_fused / k_shape_out write the rows themselves on the closed-form path)
+    const size_t n2 = (size_t)Bt * (Kf / 2);
+    SF_LAUNCH(k_fq_feat, (unsigned)((n2 + 255) / 256), 256, 0, st, feat, beta, B, Bp, Kp, m->num_pose_feats, m->fit_ns, Kf, n2,
+              reinterpret_cast<__half2*>(hi), reinterpret_cast<__half2*>(lo));
+  }
   FitFusedArgs fa{};
   fa.tT = tT; fa.vwT = vwT; fa.quads = reinterpret_cast<const float4*>(quads); fa.rec = m->fq_rec; fa.sd = m->fq_sd;
   fa.seg_start = m->seg_start; fa.seg_part = m->seg_part; fa.part_flags = m->part_flags; fa.seg_slots = m->seg_slots;

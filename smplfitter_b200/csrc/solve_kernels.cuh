@@ -2,6 +2,7 @@
 // arrays ([row][Bp]) so every access is coalesced across the warp.  All 3x3 / SxS algebra is
 // register- or local-resident; nothing here touches per-vertex data.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -92,6 +93,11 @@ struct RotArgs {
   float* feat;             // [Bp][Kp]
   TreeTables t;
   int B, Bp, Kp;
+  // k_front_fused only: the fp16 hi / lo feature rows [vec(R_rel[1:] - I) | 0 ...] of the fused passes (fit_fused.cu),
+  // [>= Bp][fq_kf] row-major, and the number of warps that run kinematic-chain columns at a time (shared-memory budget)
+  __half* fq_hi;
+  __half* fq_lo;
+  int fq_kf, fk_warps;
 };
 
 // Rotation fit of one body part (device function shared by the kernels below).
@@ -316,6 +322,120 @@ static __global__ void __launch_bounds__(32) k_front_fk(const RotArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
+// k_front_fused: k_front_rel + k_front_fk + the feature rows of the fused passes in one kernel (the closed-form path:
+// no RT4 layouts).  One CTA (FF_WARPS warps, lane = instance) per 32 instances: the orientations are staged in shared
+// memory once (the per-column kinematic chains re-read every parent rotation: 11 x from L2 in k_front_fk), joints are
+// dealt to the warps for the relative rotations / row tables, the feature rows [vec(R_rel[1:] - I) | 0 ...] are built
+// as fp16 hi / lo in a shared-memory tile and copied out with coalesced stores, then the (1 + NS) chain columns are
+// dealt to the warps with their joint positions in shared memory.
+// ---------------------------------------------------------------------------------------
+constexpr int FF_WARPS = 8;
+__host__ __device__ inline size_t front_fused_smem_bytes(int J, int kf, int fk_warps) {
+  const size_t tile = (size_t)2 * 32 * (kf + 2) * sizeof(__half);
+  const size_t chains = (size_t)fk_warps * J * 3 * 32 * sizeof(float);
+  return (size_t)J * 9 * 32 * sizeof(float) + (tile > chains ? tile : chains);
+}
+
+static __global__ void __launch_bounds__(FF_WARPS * 32) k_front_fused(const RotArgs a) {
+  extern __shared__ __align__(16) float s_ff[];
+  const int J = a.t.J, NS = a.t.NS, Bp = a.Bp, Kf = a.fq_kf;
+  const int RW = 12 + 3 * NS, TW = 3 * (1 + NS), P = 9 * (J - 1);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = blockIdx.x, b = g * 32 + lane;
+  float* sR = s_ff;            // [J*9][32]
+  float* sX = sR + J * 9 * 32; // feature tile (phase 1), then the chains' joint positions (phase 2)
+  for (int row = warp; row < J * 9; row += FF_WARPS) sR[row * 32 + lane] = a.R_new[(size_t)row * Bp + b];
+  const int KS = Kf + 2;  // tile row stride in halves: an odd number of 4-byte words, so a warp's 32 rows hit 32 banks
+  __half* th = reinterpret_cast<__half*>(sX);
+  __half* tl = th + 32 * KS;
+  for (int q = threadIdx.x; q < 32 * (Kf - P); q += FF_WARPS * 32) {
+    const int i = q / (Kf - P), k = P + q % (Kf - P);
+    th[i * KS + k] = __float2half_rn(0.f);
+    tl[i * KS + k] = __float2half_rn(0.f);
+  }
+  __syncthreads();
+  // ---- phase 1: per joint (pt/bodyfitter.py:869-876, :913) ----
+  for (int j = warp; j < J; j += FF_WARPS) {
+    float Rj[9];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) {
+      Rj[e] = sR[(j * 9 + e) * 32 + lane];
+      SF_IM(a.RT, j * RW + e, Bp, b) = Rj[e];
+    }
+    if (a.RT12 != nullptr) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int xx = 0; xx < 3; ++xx) a.RT12[((size_t)(j * 3 + c) * Bp + b) * 4 + xx] = Rj[c * 3 + xx];
+    }
+    if (j > 0) {
+      const int par = a.t.parents[j];
+      float Rp[9], rel[9];
+#pragma unroll
+      for (int e = 0; e < 9; ++e) Rp[e] = sR[(par * 9 + e) * 32 + lane];
+      mat3_tmul(Rp, Rj, rel);
+#pragma unroll
+      for (int e = 0; e < 9; ++e) {
+        a.feat[(size_t)b * a.Kp + (j - 1) * 9 + e] = rel[e];
+        const float v = rel[e] - ((e % 4 == 0) ? 1.f : 0.f);
+        const __half hv = __float2half_rn(v);
+        th[lane * KS + (j - 1) * 9 + e] = hv;
+        tl[lane * KS + (j - 1) * 9 + e] = __float2half_rn(v - __half2float(hv));
+      }
+    } else {
+      for (int k = 9 * (J - 1); k < a.Kp; ++k) a.feat[(size_t)b * a.Kp + k] = 0.f;
+    }
+  }
+  __syncthreads();
+  for (int i = warp; i < 32; i += FF_WARPS) {  // coalesced copy-out of the feature rows (zero rows past the batch)
+    const size_t row = (size_t)(g * 32 + i) * Kf;
+    const bool live = g * 32 + i < a.B;
+    for (int k = lane; k < Kf; k += 32) {
+      a.fq_hi[row + k] = live ? th[i * KS + k] : __float2half_rn(0.f);
+      a.fq_lo[row + k] = live ? tl[i * KS + k] : __float2half_rn(0.f);
+    }
+  }
+  __syncthreads();  // the tile region becomes the chains' scratch
+  // ---- phase 2: forward kinematics of column s of [position | shape Jacobian] (pt/bodyfitter.py:880-911) ----
+  if (warp < a.fk_warps) {
+    float* sP = sX + (size_t)warp * J * 3 * 32;  // [J*3][32]
+    for (int s = warp; s <= NS; s += a.fk_warps) {
+      {
+        const float* Jt = a.t.Jt_ext;
+        sP[0 * 32 + lane] = __ldg(Jt + s);
+        sP[1 * 32 + lane] = __ldg(Jt + (1 + NS) + s);
+        sP[2 * 32 + lane] = __ldg(Jt + 2 * (1 + NS) + s);
+      }
+      for (int j = 1; j < J; ++j) {
+        const int par = a.t.parents[j];
+        const float* Jt = a.t.Jt_ext + (size_t)j * TW;
+        const float* Jp = a.t.Jt_ext + (size_t)par * TW;
+        const float d0 = __ldg(Jt + s) - __ldg(Jp + s), d1 = __ldg(Jt + (1 + NS) + s) - __ldg(Jp + (1 + NS) + s),
+                    d2 = __ldg(Jt + 2 * (1 + NS) + s) - __ldg(Jp + 2 * (1 + NS) + s);
+        const float* Rp = sR + (size_t)(par * 9) * 32 + lane;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          sP[(j * 3 + c) * 32 + lane] = sP[(par * 3 + c) * 32 + lane] + (Rp[(c * 3) * 32] * d0 + Rp[(c * 3 + 1) * 32] * d1 + Rp[(c * 3 + 2) * 32] * d2);
+      }
+      for (int j = 0; j < J; ++j) {
+        const float* Jt = a.t.Jt_ext + (size_t)j * TW;
+        const float j0 = __ldg(Jt + s), j1 = __ldg(Jt + (1 + NS) + s), j2 = __ldg(Jt + 2 * (1 + NS) + s);
+        const float* Rj = sR + (size_t)(j * 9) * 32 + lane;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float pj = sP[(j * 3 + c) * 32 + lane];
+          const float tv = pj - (Rj[(c * 3) * 32] * j0 + Rj[(c * 3 + 1) * 32] * j1 + Rj[(c * 3 + 2) * 32] * j2);
+          SF_IM(a.Pext, j * TW + c * (1 + NS) + s, Bp, b) = pj;
+          SF_IM(a.RT, j * RW + 9 + c * (1 + NS) + s, Bp, b) = tv;
+          if (a.RT12 != nullptr && s == 0) a.RT12[((size_t)(j * 3 + c) * Bp + b) * 4 + 3] = tv;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // k_front_from_R: the shape front alone, for orientations given by the caller
 // (fit_with_known_pose, pt/bodyfitter.py:617-639).  Reuses k_rot_solve's tail by running it
 // with every part marked "none" and R_old = the given orientations.
@@ -357,6 +477,11 @@ struct SolveArgs {
   const float* gcf_part;
   const double* G0;
   const double* Yd;  // [3J][Bp]
+  // feature rows of the fused statistics pass (fit_fused.cu): k_shape_out writes the solved unknowns into columns
+  // [fq_p, fq_p + NS) as fp16 hi / lo; null = the caller builds the rows itself
+  __half* fq_hi;
+  __half* fq_lo;
+  int fq_kf, fq_p;
 };
 
 // gram_entry<NS>: entry e of [G | r | Sb | SA | W] for instance b: chunk partials + joint block (+ closed-form SA),
@@ -739,6 +864,14 @@ static __global__ void __launch_bounds__(32) k_shape_out(const SolveArgs a, int 
   const int j = blockIdx.y;
   if (b >= a.Bp) return;
   shape_out_joint(a, NS, j, b);
+  if (j == 0 && a.fq_hi != nullptr) {  // the unknowns as GEMM features of the statistics pass (x = ... + S beta)
+    for (int s = 0; s < NS; ++s) {
+      const float v = (b < a.B) ? SF_IM(a.beta, s, a.Bp, b) : 0.f;
+      const __half hv = __float2half_rn(v);
+      a.fq_hi[(size_t)b * a.fq_kf + a.fq_p + s] = hv;
+      a.fq_lo[(size_t)b * a.fq_kf + a.fq_p + s] = __float2half_rn(v - __half2float(hv));
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------
