@@ -221,15 +221,8 @@ __global__ void __launch_bounds__(Cfg<EW>::THREADS, 1) k_fwd_fused(const __grid_
       int it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tcount) {
         const int b0 = (tile % a.tiles_m) * TILE_M, n0 = (tile / a.tiles_m) * TILE_N;
-        if (MODE == 0) {
-          // the tile's per-vertex records, into the buffer that goes with its accumulator (free once the epilogue of
-          // two tiles ago has released it)
-          const int as = tcount & 1;
-          mbar_wait_parked(&acc_empty[as], ((tcount >> 1) & 1) ^ 1);
-          mbar_expect_tx(&rec_full[as], REC_TILE_BYTES);
-          bulk_g2s(rec_area + as * REC_TILE_BYTES, a.vrec + (size_t)(tile / a.tiles_m) * TILE_V * REC_WORDS, REC_TILE_BYTES,
-                   &rec_full[as]);
-        }
+        // (only the smem stages gate these loads: the operands of the next tile are fetched while the epilogue still
+        // owns both accumulators; the MMA issuer waits for the accumulator, warp 2 copies the tile's records)
         for (int kb = 0; kb < a.k_blocks; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
@@ -274,6 +267,20 @@ __global__ void __launch_bounds__(Cfg<EW>::THREADS, 1) k_fwd_fused(const __grid_
           mma_commit(&empty[s]);  // frees the smem stage when these MMAs retire
         }
         mma_commit(&acc_full[as]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 2 && MODE == 0) {
+    if (lane == 0) {
+      // ---- record producer: the tile's per-vertex records, into the buffer that goes with its accumulator (free once
+      // the epilogue of two tiles ago has released it) ----
+      int tcount = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tcount) {
+        const int as = tcount & 1;
+        mbar_wait_parked(&acc_empty[as], ((tcount >> 1) & 1) ^ 1);
+        mbar_expect_tx(&rec_full[as], REC_TILE_BYTES);
+        bulk_g2s(rec_area + as * REC_TILE_BYTES, a.vrec + (size_t)(tile / a.tiles_m) * TILE_V * REC_WORDS, REC_TILE_BYTES,
+                 &rec_full[as]);
       }
     }
     __syncwarp();
