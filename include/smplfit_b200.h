@@ -273,6 +273,14 @@ int smplfit_convert_vertices(const int32_t* indptr, const int32_t* indices, cons
                              int32_t v_out, int32_t v_in, int64_t batch, const float* in_vertices,
                              float* out_vertices, void* stream);
 
+/* smplfit_fit captures a call whose arguments repeat (same model tables, options, batch, pointers, workspace) into a
+ * CUDA graph on its second occurrence and replays it afterwards (one cudaGraphLaunch instead of ~40 kernel launches:
+ * what bounds small batches is the host's launch rate).  Number of graph launches since the last reset; the kernels
+ * inside a replayed graph are counted by smplfit_launch_count as usual.  SMPLFIT_B200_GRAPH=0 disables the cache. */
+int64_t smplfit_graph_replays(int reset);
+/* diagnostics: {calls seen for the first time, captures started, captures that failed, graphs instantiated} */
+void smplfit_graph_stats(int64_t* out4);
+
 /* Number of kernels launched by this library on the calling thread since the last reset
  * (bench.py reports it as gpu_launches). */
 int64_t smplfit_launch_count(int reset);

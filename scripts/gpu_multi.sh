@@ -3,7 +3,9 @@
 # (default config weak + strong scaling, and the BASELINE configs that are quoted per GPU on several GPUs)
 N=${NGPUS:-2}
 mkdir -p gpurun_out
+if [ -z "${SKIP_DIST}" ]; then
 timeout 600 python -m pytest tests/test_gpu_dist.py -m gpu -q -x --timeout 500 > gpurun_out/pytest_dist.log 2>&1; echo "pytest_dist rc=$?" | tee -a gpurun_out/pytest_dist.log
+fi
 run() { # name, extra args
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 200)) \
     bench.py --gpus $N --steps ${STEPS:-10} --warmup 3 --no-cpu-baseline --no-reference-gpu $2 > gpurun_out/multi_${N}_$1.json 2>> gpurun_out/multi.err
@@ -24,4 +26,4 @@ for c in ${EXTRA:-strong}; do
     *) run $c "--config $c";;
   esac
 done
-tail -3 gpurun_out/pytest_dist.log; tail -5 gpurun_out/multi.err
+tail -3 gpurun_out/pytest_dist.log 2>/dev/null; grep -v Warning gpurun_out/multi.err | tail -5

@@ -89,6 +89,10 @@ def lib():
     L.smplfit_struct_size.argtypes = [C.c_int]
     L.smplfit_launch_count.restype = C.c_int64
     L.smplfit_launch_count.argtypes = [C.c_int]
+    L.smplfit_graph_replays.restype = C.c_int64
+    L.smplfit_graph_replays.argtypes = [C.c_int]
+    L.smplfit_graph_stats.restype = None
+    L.smplfit_graph_stats.argtypes = [C.POINTER(C.c_int64)]
     L.smplfit_forward_workspace_bytes.restype = C.c_size_t
     L.smplfit_forward_workspace_bytes.argtypes = [C.POINTER(ModelStruct), C.c_int64]
     L.smplfit_forward.restype = C.c_int
@@ -160,6 +164,17 @@ def stream_ptr(device) -> int:
 
 def launch_count(reset: bool = False) -> int:
     return int(lib().smplfit_launch_count(1 if reset else 0))
+
+
+def graph_replays(reset: bool = False) -> int:
+    """Fits served by replaying a captured CUDA graph since the last reset."""
+    return int(lib().smplfit_graph_replays(1 if reset else 0))
+
+
+def graph_stats() -> dict:
+    buf = (C.c_int64 * 4)()
+    lib().smplfit_graph_stats(buf)
+    return dict(zip(('first_sights', 'captures', 'capture_failures', 'instantiated'), [int(x) for x in buf]))
 
 
 def require_cuda(t: torch.Tensor, what: str) -> None:

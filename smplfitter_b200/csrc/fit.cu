@@ -4,6 +4,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "fit_fused.cuh"
 #include "fit_kernels.cuh"
@@ -374,14 +376,15 @@ extern "C" size_t smplfit_fit_workspace_bytes(const smplfit_model_t* m, int64_t 
   return carve(nullptr, m, batch, has_joints, has_vw, has_jw, /*has_init=*/1).bytes;
 }
 
-extern "C" int smplfit_fit(const smplfit_model_t* m, int64_t batch, const float* target_vertices,
-                           const float* target_joints, const float* vertex_weights, const float* joint_weights,
-                           const float* beta_reg_reference, const float* kid_reg_reference,
-                           const float* init_vertices, const float* init_joints, const float* init_orientations,
-                           const smplfit_fit_opts_t* o, float* out_pose_rotvecs, float* out_shape_betas,
-                           float* out_trans, float* out_orientations, float* out_rel_orientations,
-                           float* out_kid_factor, float* out_scale_corr, void* workspace, size_t workspace_bytes,
-                           void* stream) {
+// the launch sequence of one fit, enqueued kernel by kernel on `stream`
+static int fit_direct(const smplfit_model_t* m, int64_t batch, const float* target_vertices,
+                      const float* target_joints, const float* vertex_weights, const float* joint_weights,
+                      const float* beta_reg_reference, const float* kid_reg_reference,
+                      const float* init_vertices, const float* init_joints, const float* init_orientations,
+                      const smplfit_fit_opts_t* o, float* out_pose_rotvecs, float* out_shape_betas,
+                      float* out_trans, float* out_orientations, float* out_rel_orientations,
+                      float* out_kid_factor, float* out_scale_corr, void* workspace, size_t workspace_bytes,
+                      void* stream) {
   if (int e = check_model(m)) return e;
   if (!o || !target_vertices || !out_shape_betas || !out_trans || !out_orientations)
     return fail(SMPLFIT_ERR_ARG, "missing required pointer");
@@ -488,6 +491,171 @@ extern "C" int smplfit_fit(const smplfit_model_t* m, int64_t batch, const float*
   oa.J = J; oa.S = m->num_betas; oa.NS = m->fit_ns; oa.B = c.B; oa.Bp = c.Bp;
   SF_LAUNCH(k_output, dim3(c.Bp / 32, J), 32, 0, c.st, oa);
   SF_CHECK_LAST();
+  return SMPLFIT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// CUDA-graph replay of repeated fits.  A fit is ~40 dependent launches; at small batches the host cannot enqueue them
+// as fast as the GPU runs them.  A call whose arguments (model tables, options, batch, every pointer, workspace) were
+// seen before is captured once into a graph and replayed from then on with a single cudaGraphLaunch (the kernels, their
+// tensor maps and pointers are baked into the nodes; the data they point to is read at run time as usual).  Calls that
+// do not repeat pay one hash.  Not used while profiling, inside a caller's own capture, with the share_beta
+// all-reduce hook installed, or when SMPLFIT_B200_GRAPH=0.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+struct GraphEntry {
+  uint64_t key = 0;
+  cudaGraphExec_t exec = nullptr;
+  long long kernels = 0;
+  unsigned long long last_use = 0;
+  int seen = 0;
+};
+constexpr int kGraphSlots = 32;
+GraphEntry g_graphs[kGraphSlots];
+unsigned long long g_graph_clock = 0;
+std::atomic<long long> g_graph_replays{0};
+std::atomic<long long> g_graph_stat[4];  // first sights, captures started, captures failed, instantiated
+std::mutex g_graph_mutex;
+
+inline void fnv(uint64_t& h, const void* p, size_t n) {
+  const unsigned char* b = reinterpret_cast<const unsigned char*>(p);
+  for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+}
+bool graphs_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SMPLFIT_B200_GRAPH");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+}  // namespace
+
+extern "C" int64_t smplfit_graph_replays(int reset) {
+  const long long v = reset ? g_graph_replays.exchange(0) : g_graph_replays.load();
+  return (int64_t)v;
+}
+extern "C" void smplfit_graph_stats(int64_t* out4) {
+  for (int i = 0; i < 4; ++i) out4[i] = (int64_t)g_graph_stat[i].load();
+}
+
+extern "C" int smplfit_fit(const smplfit_model_t* m, int64_t batch, const float* target_vertices,
+                           const float* target_joints, const float* vertex_weights, const float* joint_weights,
+                           const float* beta_reg_reference, const float* kid_reg_reference,
+                           const float* init_vertices, const float* init_joints, const float* init_orientations,
+                           const smplfit_fit_opts_t* o, float* out_pose_rotvecs, float* out_shape_betas,
+                           float* out_trans, float* out_orientations, float* out_rel_orientations,
+                           float* out_kid_factor, float* out_scale_corr, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  auto direct_on = [&](void* s) {
+    return fit_direct(m, batch, target_vertices, target_joints, vertex_weights, joint_weights, beta_reg_reference,
+                      kid_reg_reference, init_vertices, init_joints, init_orientations, o, out_pose_rotvecs, out_shape_betas,
+                      out_trans, out_orientations, out_rel_orientations, out_kid_factor, out_scale_corr, workspace,
+                      workspace_bytes, s);
+  };
+  auto direct = [&]() { return direct_on(stream); };
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (!m || !o || !graphs_enabled() || g_prof_on || share_beta_allreduce_installed() ||
+      cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone)
+    return direct();
+  uint64_t key = 1469598103934665603ull;
+  fnv(key, m, sizeof(*m));
+  fnv(key, o, sizeof(*o));
+  const void* ptrs[] = {target_vertices, target_joints, vertex_weights, joint_weights, beta_reg_reference, kid_reg_reference,
+                        init_vertices, init_joints, init_orientations, out_pose_rotvecs, out_shape_betas, out_trans,
+                        out_orientations, out_rel_orientations, out_kid_factor, out_scale_corr, workspace};
+  fnv(key, ptrs, sizeof(ptrs));
+  fnv(key, &batch, sizeof(batch));
+  fnv(key, &workspace_bytes, sizeof(workspace_bytes));
+  int dev = 0;
+  cudaGetDevice(&dev);
+  fnv(key, &dev, sizeof(dev));
+  if (key == 0) key = 1;
+  std::lock_guard<std::mutex> lock(g_graph_mutex);
+  GraphEntry* hit = nullptr;
+  GraphEntry* victim = &g_graphs[0];
+  for (auto& e : g_graphs) {
+    if (e.key == key) { hit = &e; break; }
+    if (e.last_use < victim->last_use) victim = &e;
+  }
+  ++g_graph_clock;
+  if (hit && hit->exec) {
+    hit->last_use = g_graph_clock;
+    if (cudaGraphLaunch(hit->exec, st) == cudaSuccess) {
+      g_launches.fetch_add(hit->kernels, std::memory_order_relaxed);
+      g_graph_replays.fetch_add(1, std::memory_order_relaxed);
+      return SMPLFIT_OK;
+    }
+    cudaGetLastError();
+    cudaGraphExecDestroy(hit->exec);
+    *hit = GraphEntry{};
+    return direct();
+  }
+  if (!hit) {  // first sight: remember the call, run it directly
+    g_graph_stat[0]++;
+    if (victim->exec) cudaGraphExecDestroy(victim->exec);
+    *victim = GraphEntry{};
+    victim->key = key;
+    victim->seen = 1;
+    victim->last_use = g_graph_clock;
+    return direct();
+  }
+  // second sight: capture the launch sequence, instantiate, launch
+  hit->last_use = g_graph_clock;
+  hit->seen++;
+  const long long before = g_launches.load();
+  g_graph_stat[1]++;
+  // the sequence is captured on a private stream (the caller's may be the legacy default stream, which cannot capture);
+  // the instantiated graph is then launched on the caller's stream
+  static thread_local cudaStream_t cap = nullptr;
+  static thread_local int cap_dev = -1;
+  if (cap == nullptr || cap_dev != dev) {
+    if (cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaGetLastError();
+      cap = nullptr;
+      return direct();
+    }
+    cap_dev = dev;
+  }
+  if (cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    return direct();
+  }
+  const int rc = direct_on(cap);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(cap, &graph);
+  const long long kernels = g_launches.load() - before;
+  if (rc != SMPLFIT_OK || ce != cudaSuccess || graph == nullptr) {
+    g_graph_stat[2]++;
+    if (getenv("SMPLFIT_B200_GRAPH_TRACE"))
+      fprintf(stderr, "smplfit graph capture failed: rc=%d (%s) end=%s\n", rc, g_err, cudaGetErrorString(ce));
+    cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    g_launches.store(before);
+    *hit = GraphEntry{};
+    return rc != SMPLFIT_OK ? rc : direct();  // (nothing was executed by the failed capture)
+  }
+  cudaGraphExec_t exec = nullptr;
+  if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess || exec == nullptr) {
+    cudaGetLastError();
+    cudaGraphDestroy(graph);
+    g_launches.store(before);
+    *hit = GraphEntry{};
+    return direct();
+  }
+  cudaGraphDestroy(graph);
+  g_graph_stat[3]++;
+  hit->exec = exec;
+  hit->kernels = kernels;
+  if (cudaGraphLaunch(exec, st) != cudaSuccess) {
+    cudaGetLastError();
+    cudaGraphExecDestroy(exec);
+    g_launches.store(before);
+    *hit = GraphEntry{};
+    return direct();
+  }
+  g_graph_replays.fetch_add(1, std::memory_order_relaxed);
   return SMPLFIT_OK;
 }
 

@@ -64,6 +64,8 @@ void set_share_beta_allreduce(smplfit_allreduce_fn fn, void* user, int64_t globa
   g_ar_total = global_batch;
 }
 
+bool share_beta_allreduce_installed() { return g_ar_fn != nullptr; }
+
 template <int NS>
 static void solve_shared_t(const SolveArgs& so, double* Gd, double* Cd, double* sums, double* x, int groups,
                            cudaStream_t st) {

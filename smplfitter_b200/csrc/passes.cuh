@@ -52,6 +52,7 @@ void launch_shape_solve_scale(const SolveArgs& a, double* Gd, double* Zd, int ns
 void launch_shape_solve_shared(const SolveArgs& a, double* Gd, double* Cd, double* sums, double* x, int ns, int groups,
                                cudaStream_t st);
 void set_share_beta_allreduce(smplfit_allreduce_fn fn, void* user, int64_t global_batch);
+bool share_beta_allreduce_installed();
 void launch_stats(const StatsArgs& legacy, const StatsRecArgs& rec, int ns, int ref_mode, bool weighted, bool use_rec,
                   int groups, cudaStream_t st);
 }  // namespace sf

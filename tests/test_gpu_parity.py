@@ -488,3 +488,28 @@ def test_body_flipper():
     # (the synthetic model is not mirror-symmetric, so how well the flipped mesh can be represented says nothing
     # about the code; the reference's own flipper tests need the licensed symmetric models)
     assert all(torch.isfinite(out[k]).all().item() for k in ('pose_rotvecs', 'shape_betas', 'trans'))
+
+
+@pytest.mark.gpu
+def test_graph_replay_matches_direct():
+    """Repeated fits with identical arguments are served by replaying a captured CUDA graph (smplfit_fit): same bits as
+    the kernel-by-kernel launches, and the replays actually happen."""
+    from smplfitter_b200 import _native
+
+    bm, fitter = get_model('smpl_tiny', (), False)
+    rs = np.random.RandomState(11)
+    B = 37
+    pose = cuda((rs.randn(B, 3 * bm.num_joints) * 0.2).astype(np.float32))
+    betas = cuda((rs.randn(B, bm.num_betas) * 0.5).astype(np.float32))
+    trans = cuda(rs.randn(B, 3).astype(np.float32))
+    fw = bm(pose, betas, trans)
+    kw = dict(num_iter=2, beta_regularizer=1.0, requested_keys=['pose_rotvecs', 'shape_betas'])
+    first = {k: v.clone() for k, v in fitter.fit(fw['vertices'], fw['joints'], **kw).items()}
+    _native.graph_replays(reset=True)
+    out = None
+    for _ in range(8):  # rebinding `out` makes the allocator alternate between two sets of blocks: the argument tuple
+        out = fitter.fit(fw['vertices'], fw['joints'], **kw)  # of every second call repeats
+        torch.cuda.synchronize()
+    assert _native.graph_replays() >= 1, ('no fit was served from a graph', _native.graph_stats())
+    for k in first:
+        assert torch.equal(out[k], first[k]), k
