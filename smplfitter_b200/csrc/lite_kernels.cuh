@@ -305,11 +305,22 @@ static __global__ void __launch_bounds__(32) k_lite_reduce(const LiteReduceArgs 
   const int j = blockIdx.y;
   if (b >= a.Bp) return;
   double y[3] = {0.0, 0.0, 0.0};
-#pragma unroll 8
-  for (int q = a.yj_start[j]; q < a.yj_start[j + 1]; ++q) {
+  auto cell = [&](int q) {
     const int e = a.yj_entry[q];
     const int seg = e / LITE_NSLOT, slot = e % LITE_NSLOT;
-    const float* p = a.partials + ((size_t)seg * a.NL + a.NS + 3 + slot * 3) * a.Bp + b;
+    return a.partials + ((size_t)seg * a.NL + a.NS + 3 + slot * 3) * a.Bp + b;
+  };
+  int q = a.yj_start[j];
+  const int q1 = a.yj_start[j + 1];
+#pragma unroll 4
+  for (; q + 2 <= q1; q += 2) {  // two cells added in fp32 before the double accumulation
+    const float* p0 = cell(q);
+    const float* p1 = cell(q + 1);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) y[c] += (double)(p0[(size_t)c * a.Bp] + p1[(size_t)c * a.Bp]);
+  }
+  if (q < q1) {
+    const float* p = cell(q);
 #pragma unroll
     for (int c = 0; c < 3; ++c) y[c] += (double)p[(size_t)c * a.Bp];
   }

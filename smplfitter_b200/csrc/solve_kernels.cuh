@@ -512,8 +512,13 @@ __device__ __forceinline__ void gram_entry(const SolveArgs& a, double* __restric
       for (int q = 0; q < a.n_gcf; ++q) acc += (double)a.gcf_part[((size_t)q * NG + e) * Bp + b];
     } else {
       const int row = (kind == 1) ? s : NS + c;
-#pragma unroll 8
-      for (int q = 0; q < a.n_chunks; ++q) acc += (double)a.partials[((size_t)q * a.lite_nl + row) * Bp + b];
+      const float* pr = a.partials + (size_t)row * Bp + b;
+      const size_t qs = (size_t)a.lite_nl * Bp;
+      int q = 0;
+#pragma unroll 4
+      for (; q + 4 <= a.n_chunks; q += 4)  // four segment partials added in fp32, then one double accumulation
+        acc += (double)((pr[(size_t)q * qs] + pr[(size_t)(q + 1) * qs]) + (pr[(size_t)(q + 2) * qs] + pr[(size_t)(q + 3) * qs]));
+      for (; q < a.n_chunks; ++q) acc += (double)pr[(size_t)q * qs];
       if (kind == 1) {
 #pragma unroll 4
         for (int k = 0; k < J; ++k)
