@@ -71,6 +71,10 @@ FIT_CASES = {
     # BASELINE.json configs[2]: full-size SMPL-X shape (10475 vertices, 55 joints, 16 betas)
     'fit_smplx_it3': ('smplx', {}, {}, 2, 0.15, 0.002,
                       dict(num_iter=3, beta_regularizer=1.0), dict(joints=True)),
+    # (appended last: the case index seeds the inputs of every case)
+    'fit_tiny_share_beta_scale': ('smpl_tiny', {}, {}, 5, 0.3, 0.002,
+                                  dict(num_iter=2, beta_regularizer=1.0, share_beta=True, scale_target=True,
+                                       scale_regularizer=0.5), dict(joints=True, same_betas=True)),
 }
 FORWARD_CASES = {'fwd_smpl': ('smpl', 3), 'fwd_tiny': ('smpl_tiny', 4), 'fwd_smplx_tiny': ('smplx_tiny', 3),
                  'fwd_smplx': ('smplx', 2)}

@@ -354,10 +354,8 @@ class OracleFitter:
         glob = np.asarray(glob, F32)
         rel, P, T, v_posed = self._shape_front(glob)
         if share_beta:
-            if scale_target or scale_fit:
-                raise NotImplementedError('share_beta + scale (lstsq_partial_share with independent columns)')
             return self._fit_shape_general(glob, rel, P, T, v_posed, t, tj, vw, jw, reg, reg2, scale_reg,
-                                           kid_reg, False, False, beta_ref, kid_ref, share_beta=True)
+                                           kid_reg, scale_target, scale_fit, beta_ref, kid_ref, share_beta=True)
         if self.gram_supported and not (scale_target or scale_fit):
             return self._fit_shape_gram(glob, rel, P, T, v_posed, t, tj, vw, jw, reg, reg2, beta_ref)
         return self._fit_shape_general(glob, rel, P, T, v_posed, t, tj, vw, jw, reg, reg2, scale_reg,
@@ -471,7 +469,22 @@ class OracleFitter:
         WA = w3[:, :, None] * A2
         G = np.einsum('bns,bnt->bst', WA, A2) + np.diag(lam)[None]
         rhs = np.einsum('bns,bn->bs', WA, b2) + lam * ref
-        if share_beta:
+        n_sh = S + (1 if self.enable_kid else 0)
+        if share_beta and npar > n_sh:
+            # pt/lstsq.py:32-90 lstsq_partial_share: betas (+ kid) shared over the batch, the scale column per instance.
+            # The regulariser enters as extra rows (row e_i, weight lambda_i, right-hand side lambda_i ref_i), so its
+            # reference term is lambda_i^2 ref_i here; the independent column is eliminated per instance (Schur
+            # complement), the shared system is summed over the batch, then the independent unknown is recovered.
+            rp = np.einsum('bns,bn->bs', WA, b2) + (lam ** 2) * ref
+            Gss, Gsz, Gzz = G[:, :n_sh, :n_sh], G[:, :n_sh, n_sh:], G[:, n_sh:, n_sh:]
+            c_s = np.linalg.solve(Gzz, np.swapaxes(Gsz, 1, 2))            # (B, n_indep, n_sh)
+            c_r = np.linalg.solve(Gzz, rp[:, n_sh:, None])                  # (B, n_indep, 1)
+            Sb_ = (Gss - Gsz @ c_s).sum(0)
+            tb_ = (rp[:, :n_sh, None] - Gsz @ c_r).sum(0)
+            x_s = np.linalg.solve(Sb_.astype(F32), tb_.astype(F32))       # (n_sh, 1)
+            x_z = c_r - c_s @ x_s[None]
+            x = np.concatenate([np.broadcast_to(x_s[None, :, 0], (B, n_sh)), x_z[:, :, 0]], 1).astype(F32)
+        elif share_beta:
             # pt/lstsq.py:43-45 -> lstsq(..., shared=True): diag(lambda) is inside the per-instance
             # Gramian that gets summed over the batch, and the regulariser-reference term is not passed
             Gs = G.sum(0)

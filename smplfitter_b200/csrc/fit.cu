@@ -206,7 +206,12 @@ static void run_shape(FitCtx& c, int scale_mode, const float* beta_ref, const fl
     sz.partials = c.w.zpart;
     launch_scale_pass(sz, m->fit_ns, scale_mode, c.groups, c.st);
     // the scale pass writes its own partial layout: point the solve at it
-    launch_shape_solve_scale(so, c.w.Gd, c.w.Zd, m->fit_ns, c.groups, c.st);
+    if (o->share_beta) {
+      const int ne = m->fit_ns * (m->fit_ns + 1) / 2 + m->fit_ns;
+      launch_shape_solve_shared_scale(so, c.w.Gd, c.w.Zd, c.w.Cd, c.w.sums, c.w.sums + ne, m->fit_ns, c.groups, c.st);
+    } else {
+      launch_shape_solve_scale(so, c.w.Gd, c.w.Zd, m->fit_ns, c.groups, c.st);
+    }
   } else if (o->share_beta) {
     const int ne = m->fit_ns * (m->fit_ns + 1) / 2 + m->fit_ns;
     launch_shape_solve_shared(so, c.w.Gd, c.w.Cd, c.w.sums, c.w.sums + ne, m->fit_ns, c.groups, c.st);
@@ -392,8 +397,6 @@ static int fit_direct(const smplfit_model_t* m, int64_t batch, const float* targ
   if (o->num_iter < 1) return fail(SMPLFIT_ERR_ARG, "num_iter must be >= 1");
   if (o->scale_mode < 0 || o->scale_mode > 2) return fail(SMPLFIT_ERR_ARG, "bad scale_mode");
   if (o->scale_mode != 0 && !out_scale_corr) return fail(SMPLFIT_ERR_ARG, "scale_corr output required");
-  if (o->scale_mode != 0 && o->share_beta)
-    return fail(SMPLFIT_ERR_UNSUPPORTED, "share_beta together with scale estimation is not implemented");
   if ((o->enable_kid != 0) != (m->fit_ns == m->num_betas + 1))
     return fail(SMPLFIT_ERR_ARG, "enable_kid does not match the fitter tables");
   const bool has_init = init_vertices != nullptr;
@@ -672,8 +675,6 @@ extern "C" int smplfit_fit_known_pose(const smplfit_model_t* m, int64_t batch, c
   if (batch <= 0 || batch > (1 << 24)) return fail(SMPLFIT_ERR_ARG, "batch out of range");
   if (o->scale_mode < 0 || o->scale_mode > 2) return fail(SMPLFIT_ERR_ARG, "bad scale_mode");
   if (o->scale_mode != 0 && !out_scale_corr) return fail(SMPLFIT_ERR_ARG, "scale_corr output required");
-  if (o->scale_mode != 0 && o->share_beta)
-    return fail(SMPLFIT_ERR_UNSUPPORTED, "share_beta together with scale estimation is not implemented");
   if ((o->enable_kid != 0) != (m->fit_ns == m->num_betas + 1))
     return fail(SMPLFIT_ERR_ARG, "enable_kid does not match the fitter tables");
   const bool has_joints = target_joints != nullptr;

@@ -83,6 +83,27 @@ static void solve_shared_t(const SolveArgs& so, double* Gd, double* Cd, double* 
   SF_LAUNCH(k_shape_out, dim3(groups, so.J), 32, 0, st, so, NS);
 }
 
+template <int NS>
+static void solve_shared_scale_t(const SolveArgs& so, double* Gd, double* Zd, double* Cd, double* sums, double* x, int groups,
+                                 cudaStream_t st) {
+  constexpr int NG = NS * (NS + 1) / 2;
+  SF_LAUNCH(k_gram_entries<NS>, dim3(groups, ShapeAcc<NS>::N), 32, 0, st, so, Gd);
+  SF_LAUNCH(k_scale_entries<NS>, dim3(groups, NS + 5), 32, 0, st, so, Zd);
+  SF_LAUNCH(k_center_entries_scale<NS>, groups, 32, 0, st, so, (const double*)Gd, Zd, Cd);
+  SF_LAUNCH(k_batch_sum, NG + NS, 256, 0, st, (const double*)Cd, so.Bp, sums);
+  if (g_ar_fn != nullptr) g_ar_fn(sums, NG + NS, reinterpret_cast<void*>(st), g_ar_user);
+  SolveArgs sg = so;
+  sg.shared_noreg = 1;  // the regulariser rows are inside the per-instance Schur complements
+  SF_LAUNCH(k_shared_solve<NS>, 1, 32, 0, st, sg, (const double*)sums, x);
+  SF_LAUNCH(k_shared_apply_scale<NS>, groups, 32, 0, st, so, (const double*)Gd, (const double*)Zd, (const double*)x);
+  SF_LAUNCH(k_shape_out, dim3(groups, so.J), 32, 0, st, so, NS);
+}
+
+void launch_shape_solve_shared_scale(const SolveArgs& a, double* Gd, double* Zd, double* Cd, double* sums, double* x, int ns,
+                                     int groups, cudaStream_t st) {
+  SF_NS_SWITCH(ns, (solve_shared_scale_t<NS>(a, Gd, Zd, Cd, sums, x, groups, st)));
+}
+
 void launch_shape_solve_shared(const SolveArgs& a, double* Gd, double* Cd, double* sums, double* x, int ns, int groups,
                                cudaStream_t st) {
   SF_NS_SWITCH(ns, (solve_shared_t<NS>(a, Gd, Cd, sums, x, groups, st)));

@@ -51,6 +51,9 @@ void launch_shape_solve_scale(const SolveArgs& a, double* Gd, double* Zd, int ns
 // share_beta: Cd = [NG+NS][Bp] doubles, sums = NG+NS doubles, x = NS doubles (device scratch)
 void launch_shape_solve_shared(const SolveArgs& a, double* Gd, double* Cd, double* sums, double* x, int ns, int groups,
                                cudaStream_t st);
+// share_beta together with scale estimation (partial share: the scale unknown stays per instance)
+void launch_shape_solve_shared_scale(const SolveArgs& a, double* Gd, double* Zd, double* Cd, double* sums, double* x, int ns,
+                                     int groups, cudaStream_t st);
 void set_share_beta_allreduce(smplfit_allreduce_fn fn, void* user, int64_t global_batch);
 bool share_beta_allreduce_installed();
 void launch_stats(const StatsArgs& legacy, const StatsRecArgs& rec, int ns, int ref_mode, bool weighted, bool use_rec,

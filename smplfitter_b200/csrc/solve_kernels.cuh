@@ -466,6 +466,7 @@ struct SolveArgs {
   int n_chunks, J, S, Bp, B, V, weighted;
   int sa_closed_form;    // 1: partials hold only [G | r | Sb]; SA from (wS, wsum), W = V
   int scale_mode;        // 0 none, 1 scale_target, 2 scale_fit (extra unknown, pt/bodyfitter.py:1171-1176)
+  int shared_noreg;      // k_shared_solve: the summed system already contains the regulariser (partial-share path)
   const float* zpartials;  // [n_zchunks][NS+5][Bp] from k_scale_pass
   int n_zchunks;
   float scale_reg;
@@ -1311,7 +1312,7 @@ __global__ void k_shared_solve(const SolveArgs a, const double* __restrict__ sum
     }
   for (int s = 0; s < NS; ++s) {
     const double lam = (s >= a.S) ? (double)a.kid_reg : ((s < 2) ? (double)a.reg2 : (double)a.reg);
-    G[s][s] += lam * (double)a.B;  // diag(lambda) added per instance, then summed (pt/lstsq.py:16-26)
+    if (!a.shared_noreg) G[s][s] += lam * (double)a.B;  // diag(lambda) added per instance, then summed (pt/lstsq.py:16-26)
     rhs[s] = sums[NG + s];
   }
   chol_solve<NS>(G, rhs, NS);
@@ -1331,6 +1332,110 @@ __global__ void __launch_bounds__(32) k_shared_apply(const SolveArgs a, const do
   for (int c = 0; c < 3; ++c) {
     double m = Gd[(size_t)(NG + NS + c) * Bp + b] / Ws;
     for (int s = 0; s < NS; ++s) m -= Gd[(size_t)(NG + NS + 3 + c * NS + s) * Bp + b] / Ws * x[s];
+    SF_IM(a.trans, c, Bp, b) = (float)m;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// share_beta together with scale estimation (pt/lstsq.py:32-90 lstsq_partial_share): the betas (+ kid) are shared over
+// the batch, the scale column stays per instance.  The regulariser enters as extra rows (row e_i, weight lambda_i,
+// right-hand side lambda_i ref_i -- so its reference term is lambda_i^2 ref_i on this path).  Per instance the scale
+// column is eliminated from the centred, regularised normal equations (Schur complement):
+//   c_s = G_sz / G_zz',  c_r = r_z / G_zz',  S_b = G_ss' - G_sz c_s^T,  t_b = r_s' - G_sz c_r        (k_center_entries_scale)
+// S_b, t_b are summed over the batch (k_batch_sum, all-reduce hook), solved once (k_shared_solve, no extra regulariser),
+// and every instance recovers its own scale unknown delta_b = c_r - c_s . x and translation (k_shared_apply_scale).
+// Zd rows [0, NS] are overwritten with c_s, c_r.
+// ---------------------------------------------------------------------------------------
+template <int NS>
+__global__ void __launch_bounds__(32) k_center_entries_scale(const SolveArgs a, const double* __restrict__ Gd,
+                                                             double* __restrict__ Zd, double* __restrict__ Cd) {
+  constexpr int NG = NS * (NS + 1) / 2;
+  constexpr int N1 = NS + 1;
+  const int b = blockIdx.x * 32 + threadIdx.x;
+  if (b >= a.Bp) return;
+  const int Bp = a.Bp;
+  const bool live = b < a.B;
+  double G[N1][N1], r[N1], SA[3][N1], Sb[3];
+  {
+    int o = 0;
+    for (int s = 0; s < NS; ++s)
+      for (int t = s; t < NS; ++t) {
+        const double v = Gd[(size_t)o * Bp + b];
+        G[s][t] = v;
+        G[t][s] = v;
+        ++o;
+      }
+    for (int s = 0; s < NS; ++s) r[s] = Gd[(size_t)(o++) * Bp + b];
+    for (int c = 0; c < 3; ++c) Sb[c] = Gd[(size_t)(o++) * Bp + b];
+    for (int c = 0; c < 3; ++c)
+      for (int s = 0; s < NS; ++s) SA[c][s] = Gd[(size_t)(o++) * Bp + b];
+  }
+  for (int s = 0; s < NS; ++s) {
+    G[s][NS] = Zd[(size_t)s * Bp + b];
+    G[NS][s] = G[s][NS];
+  }
+  G[NS][NS] = Zd[(size_t)NS * Bp + b];
+  r[NS] = Zd[(size_t)(NS + 1) * Bp + b];
+  for (int c = 0; c < 3; ++c) SA[c][NS] = Zd[(size_t)(NS + 2 + c) * Bp + b];
+  const double W = Gd[(size_t)(NG + NS + 3 + 3 * NS) * Bp + b];
+  const double Ws = (W == 0.0) ? 1.0 : W;
+  double rc[N1], lam[N1], ref[N1];
+  for (int s = 0; s < N1; ++s) {
+    double v = r[s];
+    for (int c = 0; c < 3; ++c) v -= SA[c][s] * Sb[c] / Ws;
+    rc[s] = v;
+    for (int t = 0; t < N1; ++t) {
+      double g = G[s][t];
+      for (int c = 0; c < 3; ++c) g -= SA[c][s] * SA[c][t] / Ws;
+      G[s][t] = g;
+    }
+    lam[s] = (s < 2) ? (double)a.reg2 : (double)a.reg;
+    ref[s] = 0.0;
+    if (s < a.S) {
+      if (a.beta_ref != nullptr && live) ref[s] = (double)a.beta_ref[(size_t)b * a.S + s];
+    } else if (s < NS) {
+      lam[s] = (double)a.kid_reg;
+      if (a.kid_ref != nullptr && live) ref[s] = (double)a.kid_ref[b];
+    } else {
+      lam[s] = (double)a.scale_reg;
+    }
+  }
+  const double gzz = G[NS][NS] + lam[NS];
+  const double c_r = rc[NS] / gzz;
+  double c_s[NS];
+  for (int s = 0; s < NS; ++s) c_s[s] = G[s][NS] / gzz;
+  int o = 0;
+  for (int s = 0; s < NS; ++s)
+    for (int t = s; t < NS; ++t) {
+      const double v = G[s][t] + ((s == t) ? lam[s] : 0.0) - G[s][NS] * c_s[t];
+      Cd[(size_t)o * Bp + b] = live ? v : 0.0;
+      ++o;
+    }
+  for (int s = 0; s < NS; ++s) {
+    const double v = rc[s] + lam[s] * lam[s] * ref[s] - G[s][NS] * c_r;
+    Cd[(size_t)(NG + s) * Bp + b] = live ? v : 0.0;
+  }
+  for (int s = 0; s < NS; ++s) Zd[(size_t)s * Bp + b] = c_s[s];
+  Zd[(size_t)NS * Bp + b] = c_r;
+}
+
+template <int NS>
+__global__ void __launch_bounds__(32) k_shared_apply_scale(const SolveArgs a, const double* __restrict__ Gd,
+                                                           const double* __restrict__ Zd, const double* __restrict__ x) {
+  constexpr int NG = NS * (NS + 1) / 2;
+  const int b = blockIdx.x * 32 + threadIdx.x;
+  if (b >= a.Bp) return;
+  const int Bp = a.Bp;
+  const double W = Gd[(size_t)(NG + NS + 3 + 3 * NS) * Bp + b];
+  const double Ws = (W == 0.0) ? 1.0 : W;
+  double delta = Zd[(size_t)NS * Bp + b];
+  for (int s = 0; s < NS; ++s) delta -= Zd[(size_t)s * Bp + b] * x[s];
+  for (int s = 0; s < NS; ++s) SF_IM(a.beta, s, Bp, b) = (float)x[s];
+  a.scale_out[b] = (float)delta + 1.f;
+  for (int c = 0; c < 3; ++c) {
+    double m = Gd[(size_t)(NG + NS + c) * Bp + b] / Ws;
+    for (int s = 0; s < NS; ++s) m -= Gd[(size_t)(NG + NS + 3 + c * NS + s) * Bp + b] / Ws * x[s];
+    m -= Zd[(size_t)(NS + 2 + c) * Bp + b] / Ws * delta;
     SF_IM(a.trans, c, Bp, b) = (float)m;
   }
 }

@@ -406,8 +406,6 @@ class BodyFitter(_ops.RegisteredModule, nn.Module):
         if scale_target and scale_fit:
             raise ValueError('Only one of estim_scale_target and estim_scale_fit can be True')
         scale_mode = 1 if scale_target else (2 if scale_fit else 0)
-        if share_beta and scale_mode:
-            raise NotImplementedError('share_beta together with scale estimation is not implemented on the CUDA path')
         bm = self.body_model
         dev = bm.v_template.device
         _native.require_cuda(bm.v_template, 'the body model')
@@ -572,8 +570,6 @@ class BodyFitter(_ops.RegisteredModule, nn.Module):
         if scale_target and scale_fit:
             raise ValueError('Only one of estim_scale_target and estim_scale_fit can be True')
         scale_mode = 1 if scale_target else (2 if scale_fit else 0)
-        if share_beta and scale_mode:
-            raise NotImplementedError('share_beta together with scale estimation is not implemented on the CUDA path')
         bm = self.body_model
         dev = bm.v_template.device
         _native.require_cuda(bm.v_template, 'the body model')
