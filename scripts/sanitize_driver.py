@@ -51,6 +51,9 @@ def fit_options():
     fitter.fit(fw['vertices'], fw['joints'], vw, jw, num_iter=2)                       # weighted (general shape pass)
     fitter.fit(fw['vertices'], fw['joints'], num_iter=2, scale_target=True)            # scale pass of the final solve
     fitter.fit(fw['vertices'], fw['joints'], num_iter=2, share_beta=True)
+    fitter.fit(fw['vertices'], fw['joints'], num_iter=2, share_beta=True, scale_fit=True)  # partial share
+    for _ in range(3):  # repeated identical call: captured into a CUDA graph, then replayed
+        fitter.fit(fw['vertices'], fw['joints'], num_iter=2)
     fitter.fit(fw['vertices'], fw['joints'], num_iter=1, initial_pose_rotvecs=p, initial_shape_betas=b)
     fitter.fit_with_known_pose(p, fw['vertices'], fw['joints'])
     fitter.fit_with_known_shape(b, fw['vertices'], fw['joints'], num_iter=2)
