@@ -56,7 +56,8 @@ typedef struct smplfit_model {
   int32_t n_segments;   /* statistics segments (<= seg_len vertices of one part each) */
   int32_t chunk_len;    /* vertices per shape-pass chunk */
   int32_t max_cas;      /* row length of cas_table */
-  int32_t reserved0, reserved1;
+  int32_t n_adjustable; /* parts re-fitted by the final adjustment (part_flags bit 1); 0 = unknown (use J) */
+  int32_t reserved1;
   const float* v_template;     /* (V,3) pose-corrected template */
   const float* shapedirs;      /* (V,3,S) */
   const float* posedirs;       /* (V,3,P) */

@@ -22,7 +22,7 @@ class ModelStruct(C.Structure):
 
     _int_fields = [
         'num_vertices', 'num_joints', 'num_betas', 'num_pose_feats', 'skin_k', 'is_smpl_family',
-        'n_used', 'n_segments', 'chunk_len', 'max_cas', 'reserved0', 'reserved1',
+        'n_used', 'n_segments', 'chunk_len', 'max_cas', 'n_adjustable', 'reserved1',
     ]
     _ptr_fields_a = [
         'v_template', 'shapedirs', 'posedirs', 'kid_shapedir', 'J_template', 'J_shapedirs',

@@ -40,7 +40,7 @@ static void launch_adjust(const AdjustArgs& aa, int groups, cudaStream_t st) {
     const char* e = getenv("SMPLFIT_B200_ADJUST");
     par = (e && strcmp(e, "seq") == 0) ? 0 : 1;
   }
-  const size_t smem = adjust_par_smem_bytes(aa.t.J);
+  const size_t smem = adjust_par_smem_bytes(aa.t.J, aa.n_adj);
   if (par && smem <= 200 * 1024) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_adjust_par, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     SF_LAUNCH(k_adjust_par, groups, ADJ_WARPS * 32, smem, st, aa);
@@ -291,12 +291,28 @@ static void set_feature_rows(FitCtx& c, SolveArgs& so) {
 static void run_rot(FitCtx& c, const RotArgs& ra, bool fit) {
   const int J = c.m->num_joints;
   c.vposed_valid = false;
-  if (fit) SF_LAUNCH(k_rot_fit, dim3(c.groups, J), 32, 0, c.st, ra);
+  if (fit) {
+    // warps per (instance group, part): the segment partials of a part are summed by several warps when parts are long
+    const int spp = c.m->n_segments / (J > 0 ? J : 1);
+    if (spp >= 8) SF_LAUNCH(k_rot_fit<4>, dim3(c.groups, J), 128, 0, c.st, ra);
+    else if (spp >= 4) SF_LAUNCH(k_rot_fit<2>, dim3(c.groups, J), 64, 0, c.st, ra);
+    else SF_LAUNCH(k_rot_fit<1>, dim3(c.groups, J), 32, 0, c.st, ra);
+  }
   c.feats_ready = false;
   if (c.fused && ra.RT4 == nullptr && c.w.fq_scratch != nullptr) {
     // closed-form path: relative rotations, row tables, kinematic-chain columns and the fused passes' feature rows in
     // one kernel
-    int fkw = FF_WARPS;
+    // 12 warps (one kinematic-chain column each for SMPL) when the grid is a single wave, 8 (smaller CTAs, two per SM)
+    // when there are more instance groups than SMs
+    static int sms = 0;
+    if (sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    int ffw = (c.groups <= sms && c.m->fit_ns + 1 > 8) ? 12 : 8;
+    if (ffw == 12 && front_fused_smem_bytes(J, c.m->fq_kf, 12) > 200 * 1024) ffw = 8;  // (measured: only pays when all 12 chains fit)
+    int fkw = ffw;
     while (fkw > 1 && front_fused_smem_bytes(J, c.m->fq_kf, fkw) > 200 * 1024) --fkw;
     const size_t smem = front_fused_smem_bytes(J, c.m->fq_kf, fkw);
     if (smem <= 200 * 1024) {
@@ -305,8 +321,13 @@ static void run_rot(FitCtx& c, const RotArgs& ra, bool fit) {
       fit_fused_feature_rows(c.m, c.Bp, c.w.fq_scratch, &hi, &lo);
       rf.fq_hi = reinterpret_cast<__half*>(hi); rf.fq_lo = reinterpret_cast<__half*>(lo);
       rf.fq_kf = c.m->fq_kf; rf.fk_warps = fkw;
-      if (smem > 48 * 1024) cudaFuncSetAttribute(k_front_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      SF_LAUNCH(k_front_fused, c.groups, FF_WARPS * 32, smem, c.st, rf);
+      if (ffw == 12) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_front_fused<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        SF_LAUNCH(k_front_fused<12>, c.groups, 12 * 32, smem, c.st, rf);
+      } else {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_front_fused<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        SF_LAUNCH(k_front_fused<8>, c.groups, 8 * 32, smem, c.st, rf);
+      }
       c.feats_ready = true;
       return;
     }
@@ -476,7 +497,7 @@ static int fit_direct(const smplfit_model_t* m, int64_t batch, const float* targ
     } else {
       AdjustArgs aa;
       aa.partials = w.spart; aa.tjT = w.tjT; aa.ajT = aj; aa.refj = w.refj; aa.jwT = w.jwT; aa.R_prev = w.R;
-      aa.beta = w.beta; aa.trans = w.trans; aa.R_out = w.R2; aa.t = tables(m); aa.Bp = c.Bp;
+      aa.beta = w.beta; aa.trans = w.trans; aa.R_out = w.R2; aa.t = tables(m); aa.Bp = c.Bp; aa.n_adj = (m->n_adjustable > 0 && m->n_adjustable <= J) ? m->n_adjustable : J;
       aa.scale = o->scale_mode ? w.scale : nullptr; aa.scale_mode = o->scale_mode;
       launch_adjust(aa, c.Bp / 32, c.st);
       R_final = w.R2;
@@ -853,7 +874,7 @@ extern "C" int smplfit_fit_known_shape(const smplfit_model_t* m, int64_t batch, 
     if (o->final_adjust_rots) {
       AdjustArgs aa;
       aa.partials = w.spart; aa.tjT = w.tjT; aa.ajT = aj; aa.refj = w.refj; aa.jwT = w.jwT; aa.R_prev = w.R;
-      aa.beta = w.beta; aa.trans = w.trans; aa.R_out = w.R2; aa.t = tables(m); aa.Bp = c.Bp;
+      aa.beta = w.beta; aa.trans = w.trans; aa.R_out = w.R2; aa.t = tables(m); aa.Bp = c.Bp; aa.n_adj = (m->n_adjustable > 0 && m->n_adjustable <= J) ? m->n_adjustable : J;
       aa.scale = w.scale; aa.scale_mode = 3;
       launch_adjust(aa, c.Bp / 32, c.st);
       R_final = w.R2;

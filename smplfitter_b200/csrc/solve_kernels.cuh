@@ -46,27 +46,39 @@ __device__ __forceinline__ void load3_or_const(const float* p, const float* cst,
 
 // Segment partials of one part -> centred cross-covariance about (ct, ca):
 //   sum w (t-ct)(a-ca)^T = M + st (ca0-ca)^T + (ct0-ct) sa^T + W (ct0-ct)(ca0-ca)^T
-__device__ inline void part_covariance(const float* partials, const int32_t* seg_begin, int part, int Bp, int b,
-                                       const float* ct0, const float* ca0, const float* ct, const float* ca,
-                                       float* A, float mM = 1.f, float mst = 1.f, float msa = 1.f) {
-  double acc[16];
+// the 16 statistics of a part: its segment partials (every `step`-th segment starting at `first`) summed in double
+__device__ inline void part_sums(const float* partials, const int32_t* seg_begin, int part, int Bp, int b, double* acc,
+                                 int first = 0, int step = 1) {
 #pragma unroll
   for (int e = 0; e < 16; ++e) acc[e] = 0.0;
 #pragma unroll 4
-  for (int s = seg_begin[part]; s < seg_begin[part + 1]; ++s) {  // unrolled: the loads of 4 segments are in flight together
+  for (int s = seg_begin[part] + first; s < seg_begin[part + 1]; s += step) {  // unrolled: 4 segments' loads in flight
     const float* p = partials + (size_t)s * 16 * Bp + b;
 #pragma unroll
     for (int e = 0; e < 16; ++e) acc[e] += (double)p[(size_t)e * Bp];
   }
+}
+// sums (as float) -> centred cross-covariance about (ct, ca)
+__device__ inline void covariance_from_sums(const float* sm, const float* ct0, const float* ca0, const float* ct, const float* ca,
+                                            float* A, float mM = 1.f, float mst = 1.f, float msa = 1.f) {
   const float dt[3] = {ct0[0] - ct[0], ct0[1] - ct[1], ct0[2] - ct[2]};
   const float da[3] = {ca0[0] - ca[0], ca0[1] - ca[1], ca0[2] - ca[2]};
-  const float W = (float)acc[15];
+  const float W = sm[15];
 #pragma unroll
   for (int r = 0; r < 3; ++r)
 #pragma unroll
     for (int c = 0; c < 3; ++c)
-      A[r * 3 + c] = mM * (float)acc[r * 3 + c] + mst * (float)acc[9 + r] * da[c] + dt[r] * msa * (float)acc[12 + c] +
-                     W * dt[r] * da[c];
+      A[r * 3 + c] = mM * sm[r * 3 + c] + mst * sm[9 + r] * da[c] + dt[r] * msa * sm[12 + c] + W * dt[r] * da[c];
+}
+__device__ inline void part_covariance(const float* partials, const int32_t* seg_begin, int part, int Bp, int b,
+                                       const float* ct0, const float* ca0, const float* ct, const float* ca,
+                                       float* A, float mM = 1.f, float mst = 1.f, float msa = 1.f) {
+  double acc[16];
+  part_sums(partials, seg_begin, part, Bp, b, acc);
+  float sm[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) sm[e] = (float)acc[e];
+  covariance_from_sums(sm, ct0, ca0, ct, ca, A, mM, mst, msa);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -101,7 +113,7 @@ struct RotArgs {
 };
 
 // Rotation fit of one body part (device function shared by the kernels below).
-__device__ inline void fit_part(const RotArgs& a, int i, int b, float* R) {
+__device__ inline void fit_part(const RotArgs& a, int i, int b, float* R, const float* sums = nullptr) {
   const int Bp = a.Bp;
   const int kind = a.t.part_kind[i];
   if (kind == 0 || kind == 4) {
@@ -150,7 +162,8 @@ __device__ inline void fit_part(const RotArgs& a, int i, int b, float* R) {
   float ct0[3], ca0[3];
   load3(a.tjT, i, Bp, b, ct0);
   load3_or_const(a.ca0T, a.ca0_const, i, Bp, b, ca0);
-  part_covariance(a.partials, a.t.part_seg_begin, i, Bp, b, ct0, ca0, mt, ma, A);
+  if (sums != nullptr) covariance_from_sums(sums, ct0, ca0, mt, ma, A);
+  else part_covariance(a.partials, a.t.part_seg_begin, i, Bp, b, ct0, ca0, mt, ma, A);
   if (kind == 3) {  // leaf part: Kabsch on its vertices
     proj_so3(A, R);
     return;
@@ -193,14 +206,38 @@ __device__ inline void fit_part(const RotArgs& a, int i, int b, float* R) {
 // k_rot_fit: one thread per (instance, part).  Fits the part's rotation (toe parts re-fit their
 // foot, pt/bodyfitter.py:1414-1416) and left-multiplies it onto the running orientation
 // (:422-433).  In-place safe: thread (b, i) only touches R[i][b].
-static __global__ void __launch_bounds__(32) k_rot_fit(const RotArgs a) {
-  const int b = blockIdx.x * 32 + threadIdx.x;
+template <int RF_WARPS>
+__global__ void __launch_bounds__(RF_WARPS * 32) k_rot_fit(const RotArgs a) {
+  // the part's segment partials are summed by RF_WARPS warps (every RF_WARPS-th segment each: the dependent chain of
+  // DRAM / L2 round trips is what bounds this kernel), combined in a fixed order, then warp 0 fits the rotation
+  __shared__ double s_acc[RF_WARPS][16][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x * 32 + lane;
   const int i = blockIdx.y;
-  if (b >= a.Bp) return;
   const int Bp = a.Bp;
   const int src = (a.t.part_kind[i] == 4) ? a.t.part_copy_src[i] : i;
+  const int kind = a.t.part_kind[src];
+  const bool vertex_stats = (kind == 2 || kind == 3);  // block-uniform
+  if (vertex_stats) {
+    double acc[16];
+    part_sums(a.partials, a.t.part_seg_begin, src, Bp, b, acc, warp, RF_WARPS);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) s_acc[warp][e][lane] = acc[e];
+  }
+  __syncthreads();
+  if (warp != 0) return;
+  float sums[16];
+  if (vertex_stats) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      double v = s_acc[0][e][lane];
+#pragma unroll
+      for (int w = 1; w < RF_WARPS; ++w) v += s_acc[w][e][lane];
+      sums[e] = (float)v;
+    }
+  }
   float Rf[9], Rn[9];
-  fit_part(a, src, b, Rf);
+  fit_part(a, src, b, Rf, vertex_stats ? sums : nullptr);
   if (a.R_old != nullptr) {
     float Ro[9];
 #pragma unroll
@@ -329,14 +366,14 @@ static __global__ void __launch_bounds__(32) k_front_fk(const RotArgs a) {
 // as fp16 hi / lo in a shared-memory tile and copied out with coalesced stores, then the (1 + NS) chain columns are
 // dealt to the warps with their joint positions in shared memory.
 // ---------------------------------------------------------------------------------------
-constexpr int FF_WARPS = 8;
 __host__ __device__ inline size_t front_fused_smem_bytes(int J, int kf, int fk_warps) {
   const size_t tile = (size_t)2 * 32 * (kf + 2) * sizeof(__half);
   const size_t chains = (size_t)fk_warps * J * 3 * 32 * sizeof(float);
   return (size_t)J * 9 * 32 * sizeof(float) + (tile > chains ? tile : chains);
 }
 
-static __global__ void __launch_bounds__(FF_WARPS * 32) k_front_fused(const RotArgs a) {
+template <int FF_WARPS>
+__global__ void __launch_bounds__(FF_WARPS * 32) k_front_fused(const RotArgs a) {
   extern __shared__ __align__(16) float s_ff[];
   const int J = a.t.J, NS = a.t.NS, Bp = a.Bp, Kf = a.fq_kf;
   const int RW = 12 + 3 * NS, TW = 3 * (1 + NS), P = 9 * (J - 1);
@@ -899,6 +936,7 @@ struct AdjustArgs {
                           // 3: reference' = scale * reference + trans (fit_with_known_shape, :774-803)
   TreeTables t;
   int Bp;
+  int n_adj;              // upper bound of the adjustable parts (shared-memory sizing of k_adjust_par)
 };
 
 static __global__ void __launch_bounds__(32) k_adjust_solve(const AdjustArgs a) {
@@ -989,7 +1027,9 @@ static __global__ void __launch_bounds__(32) k_adjust_solve(const AdjustArgs a) 
 // independent given their parents, so each depth is processed in parallel (warp per joint) between two CTA barriers.
 // The dependent chain shrinks from J joints / all adjustable parts to the tree depth / adjustable parts per branch.
 constexpr int ADJ_WARPS = 8;
-__host__ __device__ inline size_t adjust_par_smem_bytes(int J) { return (size_t)J * 15 * 32 * sizeof(float) + (size_t)(J + 1) * sizeof(int); }
+__host__ __device__ inline size_t adjust_par_smem_bytes(int J, int n_adj) {
+  return (size_t)J * 15 * 32 * sizeof(float) + (size_t)n_adj * 16 * 32 * sizeof(float) + (size_t)(2 * J + 2) * sizeof(int);
+}
 
 static __global__ void __launch_bounds__(ADJ_WARPS * 32) k_adjust_par(const AdjustArgs a) {
   extern __shared__ __align__(16) float s_adj[];
@@ -998,13 +1038,32 @@ static __global__ void __launch_bounds__(ADJ_WARPS * 32) k_adjust_par(const Adju
   float* pos = s_adj;             // [J*3][32]
   float* rest = pos + J * 96;     // [J*3][32]
   float* Ro = rest + J * 96;      // [J*9][32]
-  int* depth = reinterpret_cast<int*>(Ro + J * 288);  // [J], then max depth
+  float* ssum = Ro + J * 288;     // [n_adj][16][32] statistics of the adjustable parts (summed once, off the level loop)
+  int* depth = reinterpret_cast<int*>(ssum + (size_t)a.n_adj * 512);  // [J], then max depth
+  int* slot = depth + J + 1;      // [J] index of an adjustable part into ssum, else -1
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.x * 32 + lane;
   if (threadIdx.x < J) {
     int d = 0;
     for (int p = threadIdx.x; p > 0; p = a.t.parents[p]) ++d;
     depth[threadIdx.x] = d;
+  }
+  if (threadIdx.x == 32) {  // (another warp than the one that scans the depths below)
+    int n = 0;
+    for (int j = 0; j < J; ++j) {
+      const bool adj = a.t.part_kind[j] != 4 && (a.t.part_flags[j] & 2) != 0;
+      slot[j] = (adj && n < a.n_adj) ? n++ : -1;
+    }
+  }
+  __syncthreads();
+  // the segment partials of every adjustable part, all warps at once: the level loop below then has no dependent
+  // DRAM / L2 round trips left on its critical path (they were ~2/3 of this kernel's 147 us)
+  for (int i = warp; i < J; i += ADJ_WARPS) {
+    if (slot[i] < 0) continue;
+    double acc[16];
+    part_sums(a.partials, a.t.part_seg_begin, i, Bp, b, acc);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) ssum[((size_t)slot[i] * 16 + e) * 32 + lane] = (float)acc[e];
   }
   float x[SMPLFIT_MAX_UNKNOWNS];
   for (int s = 0; s < NS; ++s) x[s] = SF_IM(a.beta, s, Bp, b);
@@ -1065,7 +1124,14 @@ static __global__ void __launch_bounds__(ADJ_WARPS * 32) k_adjust_par(const Adju
           ct0[c] *= st_t;
           ca[c] = st_a * ca[c] + tr_a * trv[c];
         }
-        part_covariance(a.partials, a.t.part_seg_begin, i, Bp, b, ct0, ca, pi, ca, A, st_t * st_a, st_t, st_a);
+        if (slot[i] >= 0) {
+          float sm[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) sm[e] = ssum[((size_t)slot[i] * 16 + e) * 32 + lane];
+          covariance_from_sums(sm, ct0, ca, pi, ca, A, st_t * st_a, st_t, st_a);
+        } else {
+          part_covariance(a.partials, a.t.part_seg_begin, i, Bp, b, ct0, ca, pi, ca, A, st_t * st_a, st_t, st_a);
+        }
         const int n = a.t.cas_count[i];
         const int32_t* cas = a.t.cas_table + i * a.t.max_cas;
         for (int k = 0; k < n; ++k) {

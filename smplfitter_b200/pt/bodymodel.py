@@ -202,6 +202,7 @@ class BodyModel(_ops.RegisteredModule, nn.Module):
             num_vertices=V, num_joints=J, num_betas=self.num_betas, num_pose_feats=P, skin_k=K,
             is_smpl_family=int(plan.is_smpl_family), n_used=int(plan.part_is_stat[plan.part_assignment].sum()),
             n_segments=len(seg_part), chunk_len=CHUNK_LEN, max_cas=plan.cas_table.shape[1],
+            n_adjustable=int(np.asarray(plan.part_is_adjustable).astype(bool).sum()),
         )
         self._handle = _ops.register(self)
         if device is not None:
