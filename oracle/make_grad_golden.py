@@ -1,0 +1,104 @@
+"""TEST INFRASTRUCTURE -- gradient fixtures from the UNMODIFIED reference (pt backend, CPU, torch autograd).
+
+For a subset of the golden fit / forward cases (same inputs as ``tests/golden/<case>.npz``) this script draws seeded
+cotangents for every output, back-propagates ``sum_k <cot_k, out_k>`` through the reference
+(``smplfitter.pt.BodyFitter.fit`` / ``BodyModel.forward``) and stores the input gradients:
+
+    tests/golden/grad_<case>.npz:  cot_<output>, ref_grad_<input>
+
+``tests/test_adjoint_cpu.py`` holds the gradient evaluation of this repo (``smplfitter_b200/pt/_adjoint.py``) against
+them on the CPU; ``tests/test_gpu_grad.py`` does the same through the CUDA ops' registered backward on the B200.
+
+Run in the build container (needs /root/reference or oracle/_ref):  python -m oracle.make_grad_golden
+"""
+
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import refload  # noqa: E402
+from oracle.make_golden import FIT_CASES  # noqa: E402
+
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+
+# fit cases whose options the gradient path supports, and the inputs differentiated in each
+GRAD_FIT_CASES = {
+    'fit_tiny_it1': ('target_vertices', 'target_joints'),
+    'fit_tiny_it3': ('target_vertices', 'target_joints'),
+    'fit_tiny_nojoints': ('target_vertices',),
+    'fit_tiny_weights': ('target_vertices', 'target_joints', 'vertex_weights', 'joint_weights'),
+    'fit_tiny_initial': ('target_vertices', 'target_joints', 'initial_pose_rotvecs', 'initial_shape_betas'),
+    'fit_tiny_it4_noadjust': ('target_vertices', 'target_joints'),
+    'fit_tiny_nojoints_vw': ('target_vertices', 'vertex_weights'),
+    'fit_smplx_tiny_it3': ('target_vertices', 'target_joints'),
+}
+GRAD_FORWARD_CASES = {'fwd_tiny': 'smpl_tiny', 'fwd_smplx_tiny': 'smplx_tiny'}
+FIT_OUTPUTS = ('shape_betas', 'trans', 'orientations', 'relative_orientations', 'pose_rotvecs')
+FWD_OUTPUTS = ('joints', 'orientations', 'vertices')
+
+
+def fit_inputs(name, g):
+    """fit() kwargs of a golden fit case as float32 numpy arrays (tensor arguments) + plain options."""
+    _, _, _, _, _, _, fkw, flags = FIT_CASES[name]
+    tens = dict(target_vertices=g['target_vertices'])
+    if flags.get('joints'):
+        tens['target_joints'] = g['target_joints']
+    if 'in_vw' in g:
+        tens['vertex_weights'] = g['in_vw']
+    if 'in_jw' in g:
+        tens['joint_weights'] = g['in_jw']
+    if 'in_init_pose' in g:
+        tens['initial_pose_rotvecs'] = g['in_init_pose']
+        tens['initial_shape_betas'] = g['in_init_betas']
+    return tens, dict(fkw)
+
+
+def cotangents(shapes: dict, seed: int):
+    rs = np.random.RandomState(seed)
+    return {k: rs.randn(*s).astype(np.float32) for k, s in shapes.items()}
+
+
+def main():
+    ref = refload.load()
+    rpt = ref.pt
+    for idx, (name, wrt) in enumerate(GRAD_FIT_CASES.items()):
+        g = dict(np.load(os.path.join(GOLD, name + '.npz')))
+        mname, mkw, fitkw = FIT_CASES[name][0], FIT_CASES[name][1], FIT_CASES[name][2]
+        bm = rpt.BodyModel(mname, 'neutral', **mkw)
+        fitter = rpt.BodyFitter(bm, **fitkw)
+        tens, opts = fit_inputs(name, g)
+        tt = {k: torch.from_numpy(v).clone().requires_grad_(k in wrt) for k, v in tens.items()}
+        out = fitter.fit(**tt, **opts, requested_keys=['pose_rotvecs', 'shape_betas', 'relative_orientations'])
+        cot = cotangents({k: tuple(out[k].shape) for k in FIT_OUTPUTS}, seed=900 + idx)
+        sum((out[k] * torch.from_numpy(cot[k])).sum() for k in FIT_OUTPUTS).backward()
+        rec = {('cot_' + k): v for k, v in cot.items()}
+        for k in wrt:
+            gr = tt[k].grad.numpy()
+            assert np.isfinite(gr).all() and np.abs(gr).max() > 0, (name, k)
+            rec['ref_grad_' + k] = gr
+        np.savez_compressed(os.path.join(GOLD, 'grad_' + name + '.npz'), **rec)
+        print(f'[grad] {name}: ' + ' '.join(f"{k}={np.abs(rec['ref_grad_' + k]).max():.2e}" for k in wrt))
+    for idx, (name, mname) in enumerate(GRAD_FORWARD_CASES.items()):
+        g = dict(np.load(os.path.join(GOLD, name + '.npz')))
+        bm = rpt.BodyModel(mname, 'neutral')
+        tt = {k: torch.from_numpy(g[k]).clone().requires_grad_(True) for k in ('pose', 'betas', 'trans')}
+        out = bm(tt['pose'], tt['betas'], tt['trans'])
+        cot = cotangents({k: tuple(out[k].shape) for k in FWD_OUTPUTS}, seed=950 + idx)
+        sum((out[k] * torch.from_numpy(cot[k])).sum() for k in FWD_OUTPUTS).backward()
+        rec = {('cot_' + k): v for k, v in cot.items()}
+        rec.update({('ref_grad_' + k): tt[k].grad.numpy() for k in tt})
+        np.savez_compressed(os.path.join(GOLD, 'grad_' + name + '.npz'), **rec)
+        print(f'[grad] {name}: ' + ' '.join(f"{k}={np.abs(tt[k].grad.numpy()).max():.2e}" for k in tt))
+
+
+if __name__ == '__main__':
+    main()

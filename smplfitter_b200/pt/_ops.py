@@ -95,6 +95,27 @@ def _(handle, anchor, pose_rotvecs, shape_betas, trans, kid_factor, rel_rotmats,
             new(B, m.num_vertices, 3) if return_vertices else new(0)]
 
 
+def _needs(xs):
+    return [x is not None and x.requires_grad for x in xs]
+
+
+def _forward_setup(ctx, inputs, output):
+    handle, _anchor, *tensors, return_vertices = inputs
+    ctx.handle, ctx.return_vertices, ctx.needs = handle, return_vertices, _needs(tensors)
+    ctx.save_for_backward(*tensors)
+
+
+def _forward_backward(ctx, grads):
+    """Gradient of the forward pass: see ``_adjoint`` (values from CUDA, gradient by a sliced re-evaluation)."""
+    from . import _adjoint
+
+    g = _adjoint.forward_backward(_get(ctx.handle), list(ctx.saved_tensors), ctx.needs, ctx.return_vertices, grads)
+    return (None, None, *g, None)
+
+
+forward_op.register_autograd(_forward_backward, setup_context=_forward_setup)
+
+
 @torch.library.custom_op('smplfit_b200::fit', mutates_args=())
 def fit_op(handle: int, target_vertices: torch.Tensor, target_joints: Optional[torch.Tensor],
            vertex_weights: Optional[torch.Tensor], joint_weights: Optional[torch.Tensor], num_iter: int,
@@ -127,6 +148,32 @@ def _(handle, target_vertices, target_joints, vertex_weights, joint_weights, num
     return [new(B, f.n_betas), new(B, 3), new(B, J, 3, 3), new(B, J, 3, 3),
             new(B, 3 * J) if want_pose_rotvecs else new(0), new(B) if f.enable_kid else new(0),
             new(B) if (scale_target or scale_fit) else new(0)]
+
+
+def _fit_setup(ctx, inputs, output):
+    (handle, tv, tj, vw, jw, num_iter, reg, reg2, _scale_reg, _kid_reg, share_beta, final_adjust_rots, scale_target,
+     scale_fit, init_pose, init_betas, init_kid, want_rv, want_rel) = inputs
+    if _get(handle).enable_kid or share_beta or scale_target or scale_fit or init_kid is not None:
+        raise NotImplementedError(
+            'smplfitter_b200: gradients through fit() are available for the closed-form gram path only (no enable_kid, '
+            'share_beta, scale_target / scale_fit, initial_kid_factor); detach the inputs or drop those options')
+    tensors = [tv, tj, vw, jw, init_pose, init_betas]
+    ctx.handle, ctx.needs = handle, _needs(tensors)
+    ctx.opts = dict(num_iter=num_iter, beta_regularizer=reg, beta_regularizer2=reg2, final_adjust_rots=final_adjust_rots,
+                    want_pose_rotvecs=want_rv, want_rel_orient=want_rel)
+    ctx.save_for_backward(*tensors)
+
+
+def _fit_backward(ctx, grads):
+    """Gradient of the fit with respect to targets, weights and initial guesses: see ``_adjoint``."""
+    from . import _adjoint
+
+    g = _adjoint.fit_backward(_get(ctx.handle), list(ctx.saved_tensors), ctx.needs, ctx.opts, grads[:5])
+    return (None, g[0], g[1], g[2], g[3], None, None, None, None, None, None, None, None, None, g[4], g[5], None, None,
+            None)
+
+
+fit_op.register_autograd(_fit_backward, setup_context=_fit_setup)
 
 
 @torch.library.custom_op('smplfit_b200::convert_vertices', mutates_args=())

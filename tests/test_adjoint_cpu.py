@@ -1,0 +1,174 @@
+"""Gradient path (smplfitter_b200/pt/_adjoint.py) on the CPU: the differentiable evaluation that the CUDA ops'
+backward replays is held (a) against the float64 oracle values of the golden fit cases (it must be the same function),
+(b) against gradients back-propagated through the UNMODIFIED reference (tests/golden/grad_*.npz, written by
+oracle/make_grad_golden.py), (c) against central finite differences in float64, and (d) the hand-derived proj_so3
+pull-back against torch.autograd.gradcheck, including a reflection case and equal singular values."""
+
+import numpy as np
+import pytest
+import torch
+
+from tests import golden_cases as gc
+import smplfitter_b200.pt as pt
+from oracle.make_golden import FIT_CASES
+from oracle.make_grad_golden import FIT_OUTPUTS, FWD_OUTPUTS, GRAD_FIT_CASES, GRAD_FORWARD_CASES, fit_inputs
+from smplfitter_b200.pt import _adjoint
+
+ADJ_OPTS = ('num_iter', 'beta_regularizer', 'beta_regularizer2', 'final_adjust_rots')
+
+
+def _model(name):
+    mname, mkw = FIT_CASES[name][0], FIT_CASES[name][1]
+    return pt.BodyModel(mname, **mkw)
+
+
+def _run(bm, tens, opts, want_rel=True):
+    kw = {k: v for k, v in opts.items() if k in ADJ_OPTS}
+    return _adjoint.fit(bm, bm.num_betas, want_pose_rotvecs=True, want_rel_orient=want_rel, **tens, **kw)
+
+
+@pytest.mark.parametrize('name', sorted(GRAD_FIT_CASES))
+def test_adjoint_evaluation_is_the_fit(name):
+    """float64 evaluation == float64 oracle of the same case (1e-9), i.e. the function differentiated is the fit."""
+    g = gc.load(name)
+    tens, opts = fit_inputs(name, g)
+    out = _run(_model(name), {k: torch.from_numpy(v).double() for k, v in tens.items()}, opts)
+    for k, o in zip(FIT_OUTPUTS, out):
+        assert np.abs(o.numpy() - g['exact_' + k]).max() < 1e-9, k
+
+
+@pytest.mark.parametrize('dtype,tol', [(torch.float64, 2e-3), (torch.float32, 1e-2)])
+@pytest.mark.parametrize('name', sorted(GRAD_FIT_CASES))
+def test_fit_gradients_match_reference_autograd(name, dtype, tol):
+    """The reference back-propagates in float32, so its gradient carries its own rounding; the float64 evaluation is
+    expected within 2e-3 of it (relative to the gradient's scale), the float32 one within 1e-2 (x 5 on the SMPL-X
+    stand-in, whose 55 small parts make the float32 gradient of either implementation that much noisier: the float64
+    finite-difference test below is the exact check)."""
+    if 'smplx' in name:
+        tol *= 5
+    g, gg = gc.load(name), gc.load('grad_' + name)
+    tens, opts = fit_inputs(name, g)
+    wrt = GRAD_FIT_CASES[name]
+    tt = {k: torch.from_numpy(v).to(dtype).requires_grad_(k in wrt) for k, v in tens.items()}
+    out = _run(_model(name), tt, opts)
+    loss = sum((o * torch.from_numpy(gg['cot_' + k]).to(dtype)).sum() for k, o in zip(FIT_OUTPUTS, out))
+    grads = torch.autograd.grad(loss, [tt[k] for k in wrt])
+    for k, gr in zip(wrt, grads):
+        ref = gg['ref_grad_' + k]
+        assert torch.isfinite(gr).all()
+        err = np.abs(gr.numpy() - ref).max() / np.abs(ref).max()
+        assert err < tol, (k, err)
+
+
+@pytest.mark.parametrize('name', sorted(GRAD_FORWARD_CASES))
+def test_forward_gradients_match_reference_autograd(name):
+    g, gg = gc.load(name), gc.load('grad_' + name)
+    bm = pt.BodyModel(GRAD_FORWARD_CASES[name])
+    c = _adjoint.constants(bm, torch.float64, torch.device('cpu'))
+    tt = {k: torch.from_numpy(g[k]).double().requires_grad_(True) for k in ('pose', 'betas', 'trans')}
+    with torch.no_grad():  # the values of the fixture were taken with a kid factor
+        out = _adjoint.lbs(c, tt['pose'], tt['betas'], tt['trans'], torch.from_numpy(g['kid']).double())
+    for k, o in zip(FWD_OUTPUTS, out):
+        o = o.numpy()[:, ::int(g['stride'])] if k == 'vertices' else o.numpy()  # (vertices are stored strided)
+        assert np.abs(o - g[k]).max() < 2e-5, k
+    out = _adjoint.lbs(c, tt['pose'], tt['betas'], tt['trans'])
+    loss = sum((o * torch.from_numpy(gg['cot_' + k]).double()).sum() for k, o in zip(FWD_OUTPUTS, out))
+    grads = torch.autograd.grad(loss, list(tt.values()))
+    for k, gr in zip(tt, grads):
+        ref = gg['ref_grad_' + k]
+        assert np.abs(gr.numpy() - ref).max() / np.abs(ref).max() < 1e-4, k
+
+
+@pytest.mark.parametrize('name', ['fit_tiny_it3', 'fit_tiny_weights', 'fit_tiny_nojoints'])
+def test_fit_gradient_vs_finite_differences(name):
+    """Directional central difference in float64 (the reference's own check, tests/pt/test_fitter_grad.py:56-99, at
+    float64 resolution instead of its 5 %)."""
+    g, gg = gc.load(name), gc.load('grad_' + name)
+    tens, opts = fit_inputs(name, g)
+    bm = _model(name)
+    base = {k: torch.from_numpy(v).double() for k, v in tens.items()}
+    cot = {k: torch.from_numpy(gg['cot_' + k]).double() for k in FIT_OUTPUTS}
+
+    def loss_of(tt):
+        return sum((o * cot[k]).sum() for k, o in zip(FIT_OUTPUTS, _run(bm, tt, opts)))
+
+    rs = np.random.RandomState(7)
+    for key in GRAD_FIT_CASES[name]:
+        tt = dict(base)
+        tt[key] = base[key].clone().requires_grad_(True)
+        gr, = torch.autograd.grad(loss_of(tt), tt[key])
+        d = torch.from_numpy(rs.randn(*base[key].shape))
+        d /= d.norm()
+        eps = 1e-6
+        with torch.no_grad():
+            fd = (loss_of(dict(base, **{key: base[key] + eps * d})) - loss_of(dict(base, **{key: base[key] - eps * d}))) / (2 * eps)
+        an = (gr * d).sum()
+        assert abs(float(an - fd)) < 1e-6 * max(1.0, abs(float(fd))), (key, float(an), float(fd))
+
+
+def test_proj_so3_pullback():
+    torch.manual_seed(0)
+    A = torch.randn(6, 3, 3, dtype=torch.float64)
+    A[1] = -A[1] if torch.linalg.det(A[1]) > 0 else A[1]  # reflection branch
+    Q = torch.linalg.qr(torch.randn(3, 3, dtype=torch.float64))[0]
+    A[2] = Q @ torch.diag(torch.tensor([2.0, 2.0, 0.5], dtype=torch.float64)) @ Q.T  # equal singular values
+    A[3] = 1.7 * Q  # all equal (isotropic covariance)
+    A.requires_grad_(True)
+    R = _adjoint.proj_so3(A)
+    eye = torch.eye(3, dtype=torch.float64)
+    assert (R @ R.transpose(-1, -2) - eye).abs().max() < 1e-12 and (torch.linalg.det(R) - 1).abs().max() < 1e-12
+    assert torch.autograd.gradcheck(_adjoint.proj_so3, (A,), eps=1e-7, atol=1e-6)
+
+
+def test_rotation_maps_differentiable_at_identity():
+    rv = torch.zeros(2, 3, dtype=torch.float64, requires_grad=True)
+    R = _adjoint.rotvec2mat(rv)
+    back = _adjoint.mat2rotvec(R)
+    g, = torch.autograd.grad(back.sum(), rv)
+    assert torch.isfinite(g).all() and (g - 1).abs().max() < 1e-12
+    rv2 = (torch.randn(5, 3, dtype=torch.float64) * 1.2).requires_grad_(True)
+    assert torch.autograd.gradcheck(lambda x: _adjoint.mat2rotvec(_adjoint.rotvec2mat(x)), (rv2,), eps=1e-7, atol=1e-6)
+    # (like the reference's, the log map may return the angle > pi representative: compare as rotations)
+    assert (_adjoint.rotvec2mat(_adjoint.mat2rotvec(_adjoint.rotvec2mat(rv2))) - _adjoint.rotvec2mat(rv2)).abs().max() < 1e-12
+
+
+def test_backward_of_the_fit_op_slices_and_accumulates(monkeypatch):
+    """The registered backward (pt/_ops.py) on the CPU: the op's CUDA body is replaced by the float32 evaluation, so
+    this covers the wiring -- saved inputs, None / empty cotangents, batch slicing, broadcast (batch-1) inputs -- against
+    a direct back-propagation through the same evaluation."""
+    name = 'fit_tiny_initial'
+    g = gc.load(name)
+    tens, opts = fit_inputs(name, g)
+    bm = _model(name)
+    fitter = pt.BodyFitter(bm)
+
+    def fake_impl(tv, tj, vw, jw, num_iter, reg, reg2, sreg, kreg, share, adj, st, sf, ip, ib, ik, keys):
+        with torch.no_grad():
+            o = _adjoint.fit(bm, bm.num_betas, tv, tj, vw, jw, num_iter, reg, reg2, adj, ip, ib,
+                             'pose_rotvecs' in keys, 'relative_orientations' in keys)
+        res = dict(zip(FIT_OUTPUTS, o))
+        return {k: v for k, v in res.items() if v is not None}
+
+    monkeypatch.setattr(fitter, '_fit_impl', fake_impl)
+    monkeypatch.setattr(_adjoint, '_slices', lambda B, per, budget=0: [(a, min(a + 3, B)) for a in range(0, B, 3)])
+    tt = {k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in tens.items()}
+    tt['initial_pose_rotvecs'] = tt['initial_pose_rotvecs'][:1].detach().clone().requires_grad_(True)  # broadcast input
+    tt['initial_shape_betas'] = tt['initial_shape_betas'][:1].detach().clone().requires_grad_(True)
+    out = fitter.fit(**tt, **opts, requested_keys=['pose_rotvecs'])
+    assert out['pose_rotvecs'].requires_grad and out['shape_betas'].requires_grad
+    loss = out['pose_rotvecs'].pow(2).sum() + out['shape_betas'].sum()  # trans / orientations get no cotangent
+    loss.backward()
+    t2 = {k: v.detach().clone().requires_grad_(True) for k, v in tt.items()}
+    o2 = _adjoint.fit(bm, bm.num_betas, want_pose_rotvecs=True, **t2,
+                      **{k: v for k, v in opts.items() if k in ADJ_OPTS})
+    (o2[4].pow(2).sum() + o2[0].sum()).backward()
+    for k in tt:
+        assert tt[k].grad is not None and torch.isfinite(tt[k].grad).all()
+        scale = t2[k].grad.abs().max()
+        assert (tt[k].grad - t2[k].grad).abs().max() < 1e-3 * scale, k
+    # no gradient requested: the op's outputs do not track
+    out = fitter.fit(**{k: v.detach() for k, v in tt.items()}, **opts)
+    assert not out['pose_rotvecs'].requires_grad
+    # options outside the differentiable path fail loudly instead of returning a wrong gradient
+    with pytest.raises(NotImplementedError):
+        fitter.fit(**tt, **opts, scale_target=True)

@@ -1,0 +1,206 @@
+"""Gradients through the CUDA ops (reference feature, /root/reference/tests/pt/test_fitter_grad.py:31-99).
+
+The values come from the CUDA kernels, the gradient from the backward registered on the ``smplfit_b200::fit`` /
+``::forward`` ops (pt/_adjoint.py).  Checked here: the reference's own two gradient tests restated on this API
+(finite + non-zero for smpl / smplx and num_iter 1 / 3; directional finite differences of the CUDA fit within 5 %),
+the gradients back-propagated through the UNMODIFIED reference for the golden cases (tests/golden/grad_*.npz), and the
+batch slicing of the backward on a batch that does not fit one slice."""
+
+import numpy as np
+import pytest
+import torch
+
+from tests import golden_cases as gc
+import smplfitter_b200.pt as pt
+from oracle.make_golden import FIT_CASES
+from oracle.make_grad_golden import FIT_OUTPUTS, FWD_OUTPUTS, GRAD_FIT_CASES, GRAD_FORWARD_CASES, fit_inputs
+from smplfitter_b200.pt import _adjoint
+
+pytestmark = pytest.mark.gpu
+
+
+def _targets(model_name, batch_size, seed=0):
+    torch.manual_seed(seed)
+    bm = pt.BodyModel(model_name, num_betas=10).cuda()
+    pose = (torch.randn(batch_size, bm.num_joints * 3) * 0.1).cuda()
+    shape = (torch.randn(batch_size, 10) * 0.5).cuda()
+    trans = torch.randn(batch_size, 3).cuda()
+    with torch.no_grad():
+        out = bm(pose_rotvecs=pose, shape_betas=shape, trans=trans)
+    return bm, out['vertices'].detach(), out['joints'].detach()
+
+
+def _loss(fit):
+    return sum(fit[k].pow(2).sum() for k in ['pose_rotvecs', 'shape_betas', 'trans'])
+
+
+@pytest.mark.parametrize('model_name', ['smpl', 'smplx'])
+@pytest.mark.parametrize('num_iter', [1, 3])
+def test_fitter_grad_finite(model_name, num_iter):
+    bm, target_v, target_j = _targets(model_name, 2)
+    fitter = pt.BodyFitter(bm).cuda()
+    tv = target_v.clone().requires_grad_(True)
+    tj = target_j.clone().requires_grad_(True)
+    fit = fitter.fit(target_vertices=tv, target_joints=tj, num_iter=num_iter, beta_regularizer=1.0,
+                     requested_keys=['pose_rotvecs', 'shape_betas', 'trans'])
+    _loss(fit).backward()
+    for name, g in [('target_vertices', tv.grad), ('target_joints', tj.grad)]:
+        assert g is not None, name
+        assert g.is_cuda and torch.isfinite(g).all(), name
+        assert g.abs().max().item() > 0, name
+
+
+@pytest.mark.parametrize('seed', [0, 1, 2])
+def test_fitter_grad_vs_finite_diff(seed):
+    """Directional derivative from the registered backward against a central difference of the CUDA fit itself."""
+    bm, target_v, target_j = _targets('smpl', 1, seed)
+    fitter = pt.BodyFitter(bm).cuda()
+
+    def loss_fn(tv, tj):
+        return _loss(fitter.fit(target_vertices=tv, target_joints=tj, num_iter=1, beta_regularizer=1.0,
+                                requested_keys=['pose_rotvecs', 'shape_betas', 'trans']))
+
+    tv = target_v.clone().requires_grad_(True)
+    tj = target_j.clone().requires_grad_(True)
+    loss_fn(tv, tj).backward()
+    g = torch.Generator().manual_seed(seed + 100)
+    dv = torch.randn(target_v.shape, generator=g)
+    dj = torch.randn(target_j.shape, generator=g)
+    dv, dj = (dv / dv.norm()).cuda(), (dj / dj.norm()).cuda()
+    ag = (tv.grad * dv).sum().item() + (tj.grad * dj).sum().item()
+    eps = 1e-2
+    with torch.no_grad():
+        lp = loss_fn(target_v + eps * dv, target_j + eps * dj).item()
+        lm = loss_fn(target_v - eps * dv, target_j - eps * dj).item()
+    fd = (lp - lm) / (2 * eps)
+    rel = abs(ag - fd) / max(abs(ag), abs(fd), 1e-3)
+    assert rel < 5e-2, f'seed={seed}: autograd={ag:.4e}, fd={fd:.4e}, rel={rel:.3e}'
+
+
+@pytest.mark.parametrize('name', sorted(GRAD_FIT_CASES))
+def test_fit_gradients_match_reference_autograd(name):
+    g, gg = gc.load(name), gc.load('grad_' + name)
+    tens, opts = fit_inputs(name, g)
+    wrt = GRAD_FIT_CASES[name]
+    mname, mkw = FIT_CASES[name][0], FIT_CASES[name][1]
+    fitter = pt.BodyFitter(pt.BodyModel(mname, **mkw).cuda()).cuda()
+    tt = {k: torch.from_numpy(v).cuda().requires_grad_(k in wrt) for k, v in tens.items()}
+    out = fitter.fit(**tt, **opts, requested_keys=['pose_rotvecs', 'shape_betas', 'relative_orientations'])
+    loss = sum((out[k] * torch.from_numpy(gg['cot_' + k]).cuda()).sum() for k in FIT_OUTPUTS)
+    loss.backward()
+    tol = 5e-2 if 'smplx' in name else 1e-2
+    for k in wrt:
+        ref = gg['ref_grad_' + k]
+        gr = tt[k].grad.cpu().numpy()
+        assert np.isfinite(gr).all(), k
+        err = np.abs(gr - ref).max() / np.abs(ref).max()
+        assert err < tol, (k, err)
+
+
+@pytest.mark.parametrize('name', sorted(GRAD_FORWARD_CASES))
+def test_forward_gradients_match_reference_autograd(name):
+    g, gg = gc.load(name), gc.load('grad_' + name)
+    bm = pt.BodyModel(GRAD_FORWARD_CASES[name]).cuda()
+    tt = {k: torch.from_numpy(g[k]).cuda().requires_grad_(True) for k in ('pose', 'betas', 'trans')}
+    out = bm(tt['pose'], tt['betas'], tt['trans'])
+    sum((out[k] * torch.from_numpy(gg['cot_' + k]).cuda()).sum() for k in FWD_OUTPUTS).backward()
+    for k in tt:
+        ref = gg['ref_grad_' + k]
+        assert np.abs(tt[k].grad.cpu().numpy() - ref).max() / np.abs(ref).max() < 1e-4, k
+
+
+def test_forward_gradient_other_rotation_inputs():
+    """rel_rotmats / glob_rotmats / kid_factor inputs and return_vertices=False: finite differences of the CUDA forward."""
+    bm = pt.BodyModel('smpl_tiny').cuda()
+    torch.manual_seed(3)
+    B, J = 3, bm.num_joints
+    rel = _adjoint.rotvec2mat(torch.randn(B, J, 3) * 0.3).cuda()
+    betas, kid = (torch.randn(B, 10) * 0.5).cuda(), (torch.rand(B) * 0.5).cuda()
+    cot = torch.randn(B, bm.num_vertices, 3).cuda()
+    for key in ('rel_rotmats', 'glob_rotmats'):
+        rot = rel if key == 'rel_rotmats' else bm(rel_rotmats=rel, return_vertices=False)['orientations']
+        x = rot.clone().requires_grad_(True)
+        k = kid.clone().requires_grad_(True)
+        (bm(shape_betas=betas, kid_factor=k, **{key: x})['vertices'] * cot).sum().backward()
+        d = torch.randn_like(rot)
+        d /= d.norm()
+        eps = 1e-2
+        with torch.no_grad():
+            f = lambda r, kk: (bm(shape_betas=betas, kid_factor=kk, **{key: r})['vertices'] * cot).sum().item()  # noqa: E731
+            fd = (f(rot + eps * d, kid) - f(rot - eps * d, kid)) / (2 * eps)
+            fdk = (f(rot, kid + eps) - f(rot, kid - eps)) / (2 * eps)
+        an = (x.grad * d).sum().item()
+        assert abs(an - fd) < 2e-2 * max(abs(fd), 1.0), (key, an, fd)
+        assert abs(k.grad.sum().item() - fdk) < 2e-2 * max(abs(fdk), 1.0), (key, k.grad.sum().item(), fdk)
+    p = (torch.randn(B, 3 * J) * 0.2).cuda().requires_grad_(True)
+    out = bm(pose_rotvecs=p, return_vertices=False)
+    assert 'vertices' not in out
+    out['joints'].sum().backward()
+    assert torch.isfinite(p.grad).all() and p.grad.abs().max() > 0
+
+
+def test_backward_slices_large_batch(monkeypatch):
+    """A batch that needs several slices gives, per instance, the gradient of that instance fitted alone."""
+    bm, tv, tj = _targets('smpl', 70, seed=5)
+    fitter = pt.BodyFitter(bm).cuda()
+    calls = []
+    real = _adjoint._slices
+    monkeypatch.setattr(_adjoint, '_slices', lambda B, per, budget=1.5e9: calls.append(B) or real(B, per, 16 * per))
+    a = tv.clone().requires_grad_(True)
+    _loss(fitter.fit(a, tj, num_iter=2, requested_keys=['pose_rotvecs', 'shape_betas', 'trans'])).backward()
+    assert calls == [70]
+    for i in (0, 37, 69):
+        b = tv[i:i + 1].clone().requires_grad_(True)
+        _loss(fitter.fit(b, tj[i:i + 1], num_iter=2, requested_keys=['pose_rotvecs', 'shape_betas', 'trans'])).backward()
+        assert (a.grad[i] - b.grad[0]).abs().max() < 2e-3 * b.grad.abs().max(), i
+
+
+def test_gradient_refinement_lowers_the_loss():
+    """What the reference uses the gradients for (pt/bodyfitter_opt.py:131-255): starting from the closed-form fit, a few
+    Adam steps on pose / shape / translation through the CUDA forward reduce the vertex error to a noisy target."""
+    bm, tv, tj = _targets('smpl', 8, seed=9)
+    tv = tv + 0.01 * torch.randn_like(tv)
+    fitter = pt.BodyFitter(bm).cuda()
+    fit = fitter.fit(tv, tj, num_iter=1, requested_keys=['pose_rotvecs', 'shape_betas', 'trans'])
+    params = [fit[k].detach().clone().requires_grad_(True) for k in ('pose_rotvecs', 'shape_betas', 'trans')]
+    opt = torch.optim.Adam(params, lr=2e-3)
+    losses = []
+    for _ in range(15):
+        opt.zero_grad()
+        loss = (bm(*params)['vertices'] - tv).pow(2).sum(-1).mean()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert losses[-1] < losses[0]
+
+
+def test_body_fitter_opt():
+    """pt/bodyfitter_opt.py: refine_steps=0 is the closed-form fit; the refinement lowers the vertex error of a
+    one-iteration fit without final adjustment on noisy targets."""
+    from smplfitter_b200.pt.bodyfitter_opt import BodyFitterOpt, rot6d_to_rotmat, rotmat_to_rot6d
+
+    bm, tv, tj = _targets('smpl', 6, seed=11)
+    tv = tv + 0.005 * torch.randn_like(tv)
+    opt = BodyFitterOpt(bm).cuda()
+    plain = opt.fit(tv, tj, num_iter=1)
+    ref = opt.fitter.fit(tv, tj, num_iter=1, requested_keys=['pose_rotvecs', 'shape_betas', 'trans'])
+    for k in ('pose_rotvecs', 'shape_betas', 'trans'):
+        assert torch.equal(plain[k], ref[k]), k
+    err = lambda r: (bm(r['pose_rotvecs'], r['shape_betas'], r['trans'])['vertices'] - tv).norm(dim=-1).mean().item()  # noqa: E731
+    start = opt.fitter.fit(tv, tj, num_iter=1, final_adjust_rots=False, requested_keys=['pose_rotvecs', 'shape_betas', 'trans'])
+    refined = opt.fit(tv, tj, num_iter=1, refine_steps=30, refine_lr=0.003)
+    assert set(refined) == {'pose_rotvecs', 'shape_betas', 'trans'}
+    assert err(refined) < err(start), (err(refined), err(start))
+    R = _adjoint.rotvec2mat(torch.randn(5, 3))
+    assert (rot6d_to_rotmat(rotmat_to_rot6d(R)) - R).abs().max() < 1e-5
+
+
+def test_unsupported_options_raise_when_grad_is_requested():
+    bm = pt.BodyModel('smpl_tiny').cuda()
+    fitter = pt.BodyFitter(bm).cuda()
+    tv = bm(shape_betas=torch.zeros(2, 10).cuda())['vertices'].requires_grad_(True)
+    with pytest.raises(NotImplementedError):
+        fitter.fit(tv, scale_target=True)
+    with pytest.raises(NotImplementedError):
+        fitter.fit(tv, share_beta=True)
+    assert 'pose_rotvecs' in fitter.fit(tv.detach(), scale_target=True)  # fine without grad
