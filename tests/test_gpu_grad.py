@@ -19,10 +19,10 @@ from smplfitter_b200.pt import _adjoint
 pytestmark = pytest.mark.gpu
 
 
-def _targets(model_name, batch_size, seed=0):
+def _targets(model_name, batch_size, seed=0, pose_scale=0.1):
     torch.manual_seed(seed)
     bm = pt.BodyModel(model_name, num_betas=10).cuda()
-    pose = (torch.randn(batch_size, bm.num_joints * 3) * 0.1).cuda()
+    pose = (torch.randn(batch_size, bm.num_joints * 3) * pose_scale).cuda()
     shape = (torch.randn(batch_size, 10) * 0.5).cuda()
     trans = torch.randn(batch_size, 3).cuda()
     with torch.no_grad():
@@ -176,10 +176,11 @@ def test_gradient_refinement_lowers_the_loss():
 
 def test_body_fitter_opt():
     """pt/bodyfitter_opt.py: refine_steps=0 is the closed-form fit; the refinement lowers the vertex error of a
-    one-iteration fit without final adjustment on noisy targets."""
+    one-iteration fit without final adjustment on noisy targets (no shape regulariser: with the default weight of 1 the
+    objective trades vertex error for smaller betas, in the reference as here)."""
     from smplfitter_b200.pt.bodyfitter_opt import BodyFitterOpt, rot6d_to_rotmat, rotmat_to_rot6d
 
-    bm, tv, tj = _targets('smpl', 6, seed=11)
+    bm, tv, tj = _targets('smpl', 6, seed=11, pose_scale=0.4)
     tv = tv + 0.005 * torch.randn_like(tv)
     opt = BodyFitterOpt(bm).cuda()
     plain = opt.fit(tv, tj, num_iter=1)
@@ -187,10 +188,11 @@ def test_body_fitter_opt():
     for k in ('pose_rotvecs', 'shape_betas', 'trans'):
         assert torch.equal(plain[k], ref[k]), k
     err = lambda r: (bm(r['pose_rotvecs'], r['shape_betas'], r['trans'])['vertices'] - tv).norm(dim=-1).mean().item()  # noqa: E731
-    start = opt.fitter.fit(tv, tj, num_iter=1, final_adjust_rots=False, requested_keys=['pose_rotvecs', 'shape_betas', 'trans'])
-    refined = opt.fit(tv, tj, num_iter=1, refine_steps=30, refine_lr=0.003)
+    start = opt.fitter.fit(tv, tj, num_iter=1, beta_regularizer=0.0, final_adjust_rots=False,
+                           requested_keys=['pose_rotvecs', 'shape_betas', 'trans'])
+    refined = opt.fit(tv, tj, num_iter=1, beta_regularizer=0.0, refine_steps=30, refine_lr=0.003)
     assert set(refined) == {'pose_rotvecs', 'shape_betas', 'trans'}
-    assert err(refined) < err(start), (err(refined), err(start))
+    assert err(refined) < 0.97 * err(start), (err(refined), err(start))
     R = _adjoint.rotvec2mat(torch.randn(5, 3))
     assert (rot6d_to_rotmat(rotmat_to_rot6d(R)) - R).abs().max() < 1e-5
 
