@@ -443,7 +443,7 @@ static int fit_direct(const smplfit_model_t* m, int64_t batch, const float* targ
   const int V = m->num_vertices, J = m->num_joints;
 
   // -- re-layout + centring (pt/bodyfitter.py:355-361) --
-  SF_LAUNCH(k_mean, (c.Bp * 32 + 255) / 256, 256, 0, c.st, target_vertices, target_joints, V, J, c.B, c.Bp, w.mean);
+  SF_LAUNCH(k_mean, c.Bp, MEAN_THREADS, 0, c.st, target_vertices, target_joints, V, J, c.B, c.Bp, w.mean);
   run_transpose<3>(c, target_vertices, V, m->inv_order, w.mean, w.tT);
   if (vertex_weights) run_transpose<1>(c, vertex_weights, V, m->inv_order, nullptr, w.vwT);
   if (joint_weights) run_transpose<1>(c, joint_weights, J, nullptr, nullptr, w.jwT);
@@ -717,7 +717,7 @@ extern "C" int smplfit_fit_known_pose(const smplfit_model_t* m, int64_t batch, c
   if (!workspace || c.w.bytes > workspace_bytes) return fail(SMPLFIT_ERR_WORKSPACE, "workspace too small");
   FitWs& w = c.w;
   const int V = m->num_vertices, J = m->num_joints;
-  SF_LAUNCH(k_mean, (c.Bp * 32 + 255) / 256, 256, 0, c.st, target_vertices, target_joints, V, J, c.B, c.Bp, w.mean);
+  SF_LAUNCH(k_mean, c.Bp, MEAN_THREADS, 0, c.st, target_vertices, target_joints, V, J, c.B, c.Bp, w.mean);
   run_transpose<3>(c, target_vertices, V, m->inv_order, w.mean, w.tT);
   if (vertex_weights) run_transpose<1>(c, vertex_weights, V, m->inv_order, nullptr, w.vwT);
   if (joint_weights) run_transpose<1>(c, joint_weights, J, nullptr, nullptr, w.jwT);
@@ -804,7 +804,7 @@ extern "C" int smplfit_fit_known_shape(const smplfit_model_t* m, int64_t batch, 
   if (!workspace || c.w.bytes > workspace_bytes) return fail(SMPLFIT_ERR_WORKSPACE, "workspace too small");
   FitWs& w = c.w;
   const int V = m->num_vertices, J = m->num_joints;
-  SF_LAUNCH(k_mean, (c.Bp * 32 + 255) / 256, 256, 0, c.st, target_vertices, target_joints, V, J, c.B, c.Bp, w.mean);
+  SF_LAUNCH(k_mean, c.Bp, MEAN_THREADS, 0, c.st, target_vertices, target_joints, V, J, c.B, c.Bp, w.mean);
   run_transpose<3>(c, target_vertices, V, m->inv_order, w.mean, w.tT);
   if (vertex_weights) run_transpose<1>(c, vertex_weights, V, m->inv_order, nullptr, w.vwT);
   if (joint_weights) run_transpose<1>(c, joint_weights, J, nullptr, nullptr, w.jwT);

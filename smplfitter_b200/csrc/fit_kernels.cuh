@@ -20,54 +20,66 @@ namespace sf {
 #define SF_IM(ptr, row, Bp, b) (ptr)[(size_t)(row) * (size_t)(Bp) + (size_t)(b)]
 
 // ---------------------------------------------------------------------------------------
-// k_mean: unweighted mean over cat[vertices, joints] (pt/bodyfitter.py:355-361); one warp
-// per instance, coalesced row reads, shuffle reduction.
+// k_mean: unweighted mean over cat[vertices, joints] (pt/bodyfitter.py:355-361).  One CTA of MEAN_THREADS per
+// instance: the 12 V bytes of an instance are one contiguous row, read with a stride of 3 * MEAN_THREADS elements so
+// that each of a thread's three accumulators keeps one coordinate ((tid + k) % 3 since MEAN_THREADS % 3 == 1), six
+// independent loads in flight per thread; shuffle + shared-memory reduction in a fixed order.
 // ---------------------------------------------------------------------------------------
-static __global__ void k_mean(const float* __restrict__ tv, const float* __restrict__ tj, int V, int J, int B,
-                       int Bp, float* __restrict__ mean) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= Bp) return;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f;  // phases k%3 = 0,1,2 -> coordinate (lane + 2k) % 3
-  if (warp < B) {
-    const float* row = tv + (size_t)warp * 3 * V;
-    const int n = 3 * V;
-    int i = lane;
-    for (; i + 64 < n; i += 96) {
-      a0 += row[i];
-      a1 += row[i + 32];
-      a2 += row[i + 64];
-    }
-    if (i < n) a0 += row[i];
-    if (i + 32 < n) a1 += row[i + 32];
-    if (tj != nullptr) {
-      const float* jr = tj + (size_t)warp * 3 * J;
-      const int nj = 3 * J;
-      int k = lane;
-      for (; k + 64 < nj; k += 96) {
-        a0 += jr[k];
-        a1 += jr[k + 32];
-        a2 += jr[k + 64];
-      }
-      if (k < nj) a0 += jr[k];
-      if (k + 32 < nj) a1 += jr[k + 32];
-    }
+constexpr int MEAN_THREADS = 256;
+static_assert(MEAN_THREADS % 3 == 1, "coordinate phase of the strided accumulators");
+
+static __device__ __forceinline__ void mean_row(const float* __restrict__ row, int n, int tid, float& a0, float& a1, float& a2) {
+  constexpr int T = MEAN_THREADS;
+  int i = tid;
+  float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+  for (; i + 5 * T < n; i += 6 * T) {
+    a0 += row[i];
+    a1 += row[i + T];
+    a2 += row[i + 2 * T];
+    b0 += row[i + 3 * T];
+    b1 += row[i + 4 * T];
+    b2 += row[i + 5 * T];
   }
-  const int c0 = lane % 3;
+  a0 += b0;
+  a1 += b1;
+  a2 += b2;
+  for (; i + 2 * T < n; i += 3 * T) {
+    a0 += row[i];
+    a1 += row[i + T];
+    a2 += row[i + 2 * T];
+  }
+  if (i < n) a0 += row[i];
+  if (i + T < n) a1 += row[i + T];
+}
+
+static __global__ void __launch_bounds__(MEAN_THREADS) k_mean(const float* __restrict__ tv, const float* __restrict__ tj, int V,
+                                                              int J, int B, int Bp, float* __restrict__ mean) {
+  __shared__ float red[MEAN_THREADS / 32][3];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;  // coordinates tid % 3, (tid + 1) % 3, (tid + 2) % 3
+  if (b < B) {
+    mean_row(tv + (size_t)b * 3 * V, 3 * V, tid, a0, a1, a2);
+    if (tj != nullptr) mean_row(tj + (size_t)b * 3 * J, 3 * J, tid, a0, a1, a2);
+  }
+  const int c0 = tid % 3;
   float s[3];
   s[c0] = a0;
-  s[(c0 + 2) % 3] = a1;
-  s[(c0 + 1) % 3] = a2;
+  s[(c0 + 1) % 3] = a1;
+  s[(c0 + 2) % 3] = a2;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     float v = s[c];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    s[c] = v;
+    if (lane == 0) red[warp][c] = v;
   }
-  if (lane < 3) {
+  __syncthreads();
+  if (tid < 3) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < MEAN_THREADS / 32; ++w) v += red[w][tid];
     const float cnt = (float)(V + (tj != nullptr ? J : 0));
-    SF_IM(mean, lane, Bp, warp) = (warp < B) ? s[lane] / cnt : 0.f;
+    SF_IM(mean, tid, Bp, b) = (b < B) ? v / cnt : 0.f;
   }
 }
 

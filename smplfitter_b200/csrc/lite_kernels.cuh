@@ -756,13 +756,22 @@ k_stats_lite(const StatsLiteArgs a, const __grid_constant__ CUtensorMap map_t, c
 // ---------------------------------------------------------------------------------------
 // k_stats_tmpl<WEIGHTED, WARPS>: the statistics pass of the FIRST rotation fit, against the constant template mesh
 // (pt/bodyfitter.py:384-394; REF == 0 of k_stats_rec).  Only the targets stream from HBM: per-warp ring of
-// TMPL_NST stages of TMPL_VS vertices (one 2D TMA box each); the template coordinates of a stage are one coalesced
-// load per lane, broadcast by shuffles.  9 FMAs per vertex: the pass is bandwidth-bound.
+// TMPL_NST stages of TMPL_VS vertices (one 2D TMA box each).  9 FMAs per vertex: the pass is bound by the latency of
+// what it loads, so nothing a segment needs is requested when the segment starts:
+//   * the descriptors of the warp's (<= 32) segments are read once, one segment per lane, and handed out by shuffles;
+//   * the target ring runs across segment boundaries (a producer cursor NST - 1 boxes ahead of the consumer);
+//   * the part centres and the template coordinates of segment q + 1 (<= 96 floats = 3 registers per lane) are
+//     requested before segment q is processed.
 // ---------------------------------------------------------------------------------------
 constexpr int TMPL_VS = 8, TMPL_NST = 3;
 __host__ __device__ inline size_t stats_tmpl_smem_bytes(int warps) {
   return (size_t)warps * TMPL_NST * (3 * TMPL_VS * 32) * sizeof(float) + (size_t)warps * TMPL_NST * 8 + 16;
 }
+
+struct TmplSeg {
+  float ct[3], ca[3], tm[3];
+  int i0, i1, seg;
+};
 
 template <bool WEIGHTED, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1)
@@ -770,39 +779,85 @@ k_stats_tmpl(const StatsLiteArgs a, const float* __restrict__ template_fit, cons
              const __grid_constant__ CUtensorMap map_t) {
   extern __shared__ __align__(128) float s_tm[];
   constexpr int BOX = 3 * TMPL_VS * 32;
+  constexpr unsigned FULL = 0xffffffffu;
   const int g = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int Bp = a.Bp;
+  const int Bp = a.Bp, spw = a.segs_per_warp;
   const int b = g * 32 + lane;
   float* buf = s_tm + (size_t)warp * TMPL_NST * BOX;
   uint64_t* bar = reinterpret_cast<uint64_t*>(s_tm + (size_t)WARPS * TMPL_NST * BOX) + TMPL_NST * warp;
   if (lane == 0)
     for (int s = 0; s < TMPL_NST; ++s) sf_mbar_init(bar + s, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  // descriptors of this warp's segments: lane q holds segment q
+  int m_i0 = 0, m_i1 = 0, m_part = 0;
+  bool m_act = false;
+  if (lane < spw) {
+    const int seg = (blockIdx.x * spw + lane) * WARPS + warp;
+    if (seg < a.n_segments) {
+      m_part = a.seg_part[seg];
+      m_act = (a.part_flags[m_part] & 1) != 0;
+      m_i0 = a.seg_start[seg];
+      m_i1 = a.seg_start[seg + 1];
+    }
+  }
   __syncwarp();
-  uint32_t phase = 0;
-  for (int q = 0; q < a.segs_per_warp; ++q) {
-    const int seg = (blockIdx.x * a.segs_per_warp + q) * WARPS + warp;
-    if (seg >= a.n_segments) break;
-    const int part = a.seg_part[seg];
-    if ((a.part_flags[part] & 1) == 0) continue;
-    const int i0 = a.seg_start[seg], i1 = a.seg_start[seg + 1];
-    const int nsub = (i1 - i0 + TMPL_VS - 1) / TMPL_VS;
-    auto issue = [&](int k) {
-      __syncwarp();
-      if (k < nsub && lane == 0) {
-        const int s = k % TMPL_NST;
+  const unsigned act = __ballot_sync(FULL, m_act && m_i1 > m_i0);
+  for (unsigned em = __ballot_sync(FULL, m_act && m_i1 <= m_i0); em; em &= em - 1) {  // empty segment of a live part
+    float* out = a.partials + (size_t)((blockIdx.x * spw + (__ffs(em) - 1)) * WARPS + warp) * 16 * Bp + b;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) out[(size_t)e * Bp] = 0.f;
+  }
+  // producer cursor over (segment, box)
+  unsigned pm = act;
+  int pi0 = 0, pnsub = 0, pk = 0, issued = 0;
+  auto p_seg = [&]() {
+    const int q = pm ? __ffs(pm) - 1 : 0;
+    pi0 = __shfl_sync(FULL, m_i0, q);
+    pnsub = (__shfl_sync(FULL, m_i1, q) - pi0 + TMPL_VS - 1) / TMPL_VS;
+    pk = 0;
+  };
+  p_seg();
+  auto issue = [&]() {
+    __syncwarp();
+    if (pm != 0) {
+      if (lane == 0) {
+        const int s = issued % TMPL_NST;
         sf_mbar_expect_tx(bar + s, (uint32_t)BOX * 4u);
-        sf_tma_2d(buf + (size_t)s * BOX, &map_t, bar + s, g * 32, (i0 + k * TMPL_VS) * 3);
+        sf_tma_2d(buf + (size_t)s * BOX, &map_t, bar + s, g * 32, (pi0 + pk * TMPL_VS) * 3);
       }
-    };
-    for (int k = 0; k < TMPL_NST - 1; ++k) issue(k);
-    float ct[3], ca[3];
+      ++issued;
+      if (++pk == pnsub) {
+        pm &= pm - 1;
+        p_seg();
+      }
+    }
+  };
+  auto fetch = [&](int q, TmplSeg& d) {
+    d.i0 = __shfl_sync(FULL, m_i0, q);
+    d.i1 = __shfl_sync(FULL, m_i1, q);
+    const int part = __shfl_sync(FULL, m_part, q);
+    d.seg = (blockIdx.x * spw + q) * WARPS + warp;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      ct[c] = SF_IM(a.ct0, part * 3 + c, Bp, b);
-      ca[c] = __ldg(ca0_const + part * 3 + c);
+      d.ct[c] = SF_IM(a.ct0, part * 3 + c, Bp, b);
+      d.ca[c] = __ldg(ca0_const + part * 3 + c);
     }
+    const int n3 = (d.i1 - d.i0) * 3;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) d.tm[r] = (r * 32 + lane < n3) ? __ldg(template_fit + (size_t)d.i0 * 3 + r * 32 + lane) : 0.f;
+  };
+  for (int k = 0; k < TMPL_NST - 1; ++k) issue();
+  unsigned cm = act;
+  int consumed = 0;
+  uint32_t phase = 0;
+  TmplSeg cur, nxt;
+  if (cm) fetch(__ffs(cm) - 1, cur);
+  while (cm) {
+    cm &= cm - 1;
+    if (cm) fetch(__ffs(cm) - 1, nxt);
+    const int i0 = cur.i0, i1 = cur.i1;
+    const int nsub = (i1 - i0 + TMPL_VS - 1) / TMPL_VS;
     float M[9], st[3], sa[3], W = 0.f;
 #pragma unroll
     for (int e = 0; e < 9; ++e) M[e] = 0.f;
@@ -811,29 +866,39 @@ k_stats_tmpl(const StatsLiteArgs a, const float* __restrict__ template_fit, cons
     for (int k = 0; k < nsub; ++k) {
       const int first = i0 + k * TMPL_VS;
       const int nv = min(TMPL_VS, i1 - first);
-      const float tm = (lane < nv * 3) ? __ldg(template_fit + (size_t)first * 3 + lane) : 0.f;
+      // the template coordinates of this box: flat element k * 24 + lane of the segment's (prefetched) 96
+      float tm;
+      if (k < 96 / (3 * TMPL_VS)) {
+        const int f = k * 3 * TMPL_VS + lane;
+        const float v0 = __shfl_sync(FULL, cur.tm[0], f & 31), v1 = __shfl_sync(FULL, cur.tm[1], f & 31),
+                    v2 = __shfl_sync(FULL, cur.tm[2], f & 31);
+        tm = (f < 32) ? v0 : ((f < 64) ? v1 : v2);
+      } else {  // (segments longer than 32 vertices: not produced by the current tables)
+        tm = (lane < nv * 3) ? __ldg(template_fit + (size_t)first * 3 + lane) : 0.f;
+      }
       float wv8[TMPL_VS];
       if (WEIGHTED) {
 #pragma unroll
         for (int u = 0; u < TMPL_VS; ++u) wv8[u] = (u < nv) ? SF_IM(a.vwT, first + u, Bp, b) : 0.f;
       }
-      issue(k + TMPL_NST - 1);
-      const int s = k % TMPL_NST;
+      issue();
+      const int s = consumed % TMPL_NST;
       sf_mbar_wait(bar + s, (phase >> s) & 1u);
       phase ^= 1u << s;
+      ++consumed;
       const float* sg = buf + (size_t)s * BOX;
 #pragma unroll
       for (int u = 0; u < TMPL_VS; ++u) {
         float x[3];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) x[c] = __shfl_sync(0xffffffffu, tm, u * 3 + c);
+        for (int c = 0; c < 3; ++c) x[c] = __shfl_sync(FULL, tm, u * 3 + c);
         if (u < nv) {
           const float wv = WEIGHTED ? wv8[u] : 1.f;
           float dt[3], wa[3];
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            dt[c] = sg[(u * 3 + c) * 32 + lane] - ct[c];
-            wa[c] = WEIGHTED ? wv * (x[c] - ca[c]) : (x[c] - ca[c]);
+            dt[c] = sg[(u * 3 + c) * 32 + lane] - cur.ct[c];
+            wa[c] = WEIGHTED ? wv * (x[c] - cur.ca[c]) : (x[c] - cur.ca[c]);
             st[c] = WEIGHTED ? fmaf(wv, dt[c], st[c]) : st[c] + dt[c];
             sa[c] += wa[c];
           }
@@ -845,7 +910,7 @@ k_stats_tmpl(const StatsLiteArgs a, const float* __restrict__ template_fit, cons
         }
       }
     }
-    float* out = a.partials + (size_t)seg * 16 * Bp + b;
+    float* out = a.partials + (size_t)cur.seg * 16 * Bp + b;
 #pragma unroll
     for (int e = 0; e < 9; ++e) out[(size_t)e * Bp] = M[e];
 #pragma unroll
@@ -854,6 +919,7 @@ k_stats_tmpl(const StatsLiteArgs a, const float* __restrict__ template_fit, cons
       out[(size_t)(12 + c) * Bp] = sa[c];
     }
     out[(size_t)15 * Bp] = W;
+    cur = nxt;
   }
 }
 
