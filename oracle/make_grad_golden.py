@@ -40,14 +40,21 @@ GRAD_FIT_CASES = {
     'fit_tiny_it4_noadjust': ('target_vertices', 'target_joints'),
     'fit_tiny_nojoints_vw': ('target_vertices', 'vertex_weights'),
     'fit_smplx_tiny_it3': ('target_vertices', 'target_joints'),
+    'fit_tiny_kid': ('target_vertices', 'target_joints'),
+    'fit_tiny_converter_style': ('target_vertices',),
+    'fit_tiny_scale_target': ('target_vertices', 'target_joints'),
+    'fit_tiny_scale_fit': ('target_vertices', 'target_joints'),
+    'fit_tiny_share_beta': ('target_vertices', 'target_joints'),
+    'fit_tiny_share_beta_scale': ('target_vertices', 'target_joints'),
 }
 GRAD_FORWARD_CASES = {'fwd_tiny': 'smpl_tiny', 'fwd_smplx_tiny': 'smplx_tiny'}
-FIT_OUTPUTS = ('shape_betas', 'trans', 'orientations', 'relative_orientations', 'pose_rotvecs')
+FIT_OUTPUTS = ('shape_betas', 'trans', 'orientations', 'relative_orientations', 'pose_rotvecs', 'kid_factor', 'scale_corr')
 FWD_OUTPUTS = ('joints', 'orientations', 'vertices')
 
 
 def fit_inputs(name, g):
-    """fit() kwargs of a golden fit case as float32 numpy arrays (tensor arguments) + plain options."""
+    """fit() kwargs of a golden fit case as float32 numpy arrays (tensor arguments) + plain options (the fitter's
+    constructor options are ``FIT_CASES[name][2]``)."""
     _, _, _, _, _, _, fkw, flags = FIT_CASES[name]
     tens = dict(target_vertices=g['target_vertices'])
     if flags.get('joints'):
@@ -78,8 +85,8 @@ def main():
         tens, opts = fit_inputs(name, g)
         tt = {k: torch.from_numpy(v).clone().requires_grad_(k in wrt) for k, v in tens.items()}
         out = fitter.fit(**tt, **opts, requested_keys=['pose_rotvecs', 'shape_betas', 'relative_orientations'])
-        cot = cotangents({k: tuple(out[k].shape) for k in FIT_OUTPUTS}, seed=900 + idx)
-        sum((out[k] * torch.from_numpy(cot[k])).sum() for k in FIT_OUTPUTS).backward()
+        cot = cotangents({k: tuple(out[k].shape) for k in FIT_OUTPUTS if k in out}, seed=900 + idx)
+        sum((out[k] * torch.from_numpy(cot[k])).sum() for k in cot).backward()
         rec = {('cot_' + k): v for k, v in cot.items()}
         for k in wrt:
             gr = tt[k].grad.numpy()

@@ -59,7 +59,6 @@ static FitWs carve(void* base, const smplfit_model_t* m, int64_t B, int has_join
   const size_t Bp = roundup((int)B, 32);
   const int V = m->num_vertices, J = m->num_joints, NS = m->fit_ns;
   const int Kp = roundup(m->num_pose_feats, 16);
-  const int n_chunks = (V + m->chunk_len - 1) / m->chunk_len;
   w.mean = c.take<float>(3 * Bp);
   w.tT = c.take<float>((size_t)3 * V * Bp);
   w.tjT = c.take<float>((size_t)3 * J * Bp);

@@ -18,9 +18,9 @@ where the fit operates:
 * ``rotvec2mat`` / ``mat2rotvec`` use series forms near the identity so that the derivative exists at zero rotation.
 
 What is differentiable: ``forward`` with respect to every tensor input; ``fit`` with respect to the targets, the
-weights and the initial guesses, for the options of the closed-form gram path (joints or not, weights, ``num_iter``,
-``final_adjust_rots``, the two regularisers, initial pose / shape).  ``enable_kid``, ``share_beta`` and the scale
-modes raise ``NotImplementedError`` when a gradient is requested.
+weights and the initial guesses (joints or not, weights, ``num_iter``,
+``final_adjust_rots``, the regularisers, initial pose / shape / kid factor, ``enable_kid``, ``scale_target`` /
+``scale_fit``, ``share_beta`` -- every option of ``fit``).
 """
 
 from __future__ import annotations
@@ -283,12 +283,19 @@ def _fit_global_rotations(c: Constants, t, tj, a, aj, vw, jw):
     return torch.cat([Rm, Rl, Rb], 1)[:, c.assemble]
 
 
-def _fit_shape(c: Constants, S: int, glob, t, tj, vw, jw, reg: float, reg2: float, beta_ref):
-    """Shape and translation for given orientations: weighted, centred normal equations in the betas
-    (pt/bodyfitter.py:863-1102).  Returns betas, trans, relative orientations, joints, vertices."""
-    B, J = glob.shape[0], c.J
+def _fit_shape(c: Constants, S: int, glob, t, tj, vw, jw, reg: float, reg2: float, beta_ref, enable_kid: bool = False,
+               kid_reg: Optional[float] = None, kid_ref=None, scale_mode: int = 0, scale_reg: float = 0.0,
+               share_beta: bool = False):
+    """Shape (+ kid factor, + scale correction) and translation for given orientations: weighted, centred normal
+    equations (pt/bodyfitter.py:863-1319; ``share_beta``: pt/lstsq.py:32-90).  ``scale_mode``: 0 none, 1 target,
+    2 fit.  Returns a dict with shape_betas, trans, relative_orientations, joints, vertices (+ kid_factor, scale_corr)."""
+    B, J = t.shape[0], c.J
     rel = _relative(c, glob)
-    Jt = torch.cat([c.J_template[:, :, None], c.J_shapedirs[:, :, :S]], 2)  # (J, 3, 1+S)
+    sd, Jt = c.shapedirs[:, :, :S], torch.cat([c.J_template[:, :, None], c.J_shapedirs[:, :, :S]], 2)
+    if enable_kid:
+        sd = torch.cat([sd, c.kid_shapedir[:, :, None]], 2)
+        Jt = torch.cat([Jt, c.kid_J_shapedir[:, :, None]], 2)
+    n_sh = sd.shape[2]  # shared-able unknowns: betas (+ kid)
     P = [Jt[0][None].expand(B, -1, -1)]
     for i in range(1, J):
         p = c.parents[i]
@@ -298,13 +305,17 @@ def _fit_shape(c: Constants, S: int, glob, t, tj, vw, jw, reg: float, reg2: floa
     v_posed = c.v_template[None] + torch.einsum('vcp,bp->bvc', c.posedirs, rel[:, 1:].reshape(B, (J - 1) * 9))
     blend = torch.einsum('vj,bjk->bvk', c.weights, glob.reshape(B, J, 9)).reshape(B, c.V, 3, 3)
     ext = torch.cat([torch.einsum('bvCc,bvc->bvC', blend, v_posed)[..., None],
-                     torch.einsum('bvCc,vcs->bvCs', blend, c.shapedirs[:, :, :S])], 3)
+                     torch.einsum('bvCc,vcs->bvCs', blend, sd)], 3)
     ext = ext + torch.einsum('vj,bjCs->bvCs', c.weights, T)
     if tj is None:
         tgt, full = t, ext
     else:
         tgt, full = torch.cat([t, tj], 1), torch.cat([ext, P], 1)
     pos, jac = full[..., 0], full[..., 1:]
+    if scale_mode == 1:
+        jac = torch.cat([jac, -tgt[..., None]], 3)
+    elif scale_mode == 2:
+        jac = torch.cat([jac, pos[..., None]], 3)
     b = tgt - pos
     # weights enter the shape stage only as a complete set (pt/bodyfitter.py:1018-1028)
     if tj is not None and vw is not None and jw is not None:
@@ -320,22 +331,60 @@ def _fit_shape(c: Constants, S: int, glob, t, tj, vw, jw, reg: float, reg2: floa
     Ac, bc = jac - mean_A[:, None], b - mean_b[:, None]
     WA = Ac * w[:, :, None, None]
     d = torch.float64
-    lam = torch.tensor([reg2] * min(2, S) + [reg] * max(S - 2, 0), dtype=d, device=t.device)
-    G = torch.einsum('bncs,bnct->bst', WA, Ac).to(d) + torch.diag(lam)[None]
-    r = torch.einsum('bncs,bnc->bs', WA, bc).to(d)
+    lam = [reg2] * min(2, S) + [reg] * max(S - 2, 0)
+    ref = torch.zeros((1, S), dtype=d, device=t.device)
     if beta_ref is not None:
         n = min(beta_ref.shape[1], S)
-        ref = torch.zeros((beta_ref.shape[0], S), dtype=d, device=t.device)
-        ref = torch.cat([beta_ref[:, :n].to(d), ref[:, n:]], 1)
-        r = r + lam * ref
-    x = torch.linalg.solve(G, r[..., None])[..., 0].to(t.dtype)
+        ref = torch.cat([beta_ref[:, :n].to(d), torch.zeros((beta_ref.shape[0], S - n), dtype=d, device=t.device)], 1)
+    if enable_kid:
+        lam.append(reg if kid_reg is None else kid_reg)
+        kr = torch.zeros((1, 1), dtype=d, device=t.device) if kid_ref is None else kid_ref.reshape(-1, 1).to(d)
+        ref = torch.cat([ref.expand(max(ref.shape[0], kr.shape[0]), -1), kr.expand(max(ref.shape[0], kr.shape[0]), -1)], 1)
+    if scale_mode:
+        lam.append(scale_reg)
+        ref = torch.cat([ref, torch.zeros((ref.shape[0], 1), dtype=d, device=t.device)], 1)
+    lam = torch.tensor(lam, dtype=d, device=t.device)
+    G = torch.einsum('bncs,bnct->bst', WA, Ac).to(d) + torch.diag(lam)[None]
+    r = torch.einsum('bncs,bnc->bs', WA, bc).to(d)
+    npar = G.shape[-1]
+    if share_beta and npar > n_sh:
+        # betas (+ kid) shared over the batch, the scale column per instance: the per-instance unknown is eliminated
+        # (Schur complement), the shared system is summed over the batch.  The regulariser enters lstsq_partial_share
+        # as extra rows (weight lam_i, right-hand side lam_i ref_i), hence lam^2 ref here.
+        rp = r + lam * lam * ref
+        Gss, Gsz, Gzz = G[:, :n_sh, :n_sh], G[:, :n_sh, n_sh:], G[:, n_sh:, n_sh:]
+        c_s = torch.linalg.solve(Gzz, Gsz.transpose(1, 2))
+        c_r = torch.linalg.solve(Gzz, rp[:, n_sh:, None])
+        x_s = torch.linalg.solve((Gss - Gsz @ c_s).sum(0), (rp[:, :n_sh, None] - Gsz @ c_r).sum(0))
+        x_z = c_r - c_s @ x_s[None]
+        x = torch.cat([x_s[None, :, 0].expand(B, -1), x_z[:, :, 0]], 1)
+    elif share_beta:
+        # lstsq(..., shared=True): the regulariser sits inside every instance's Gramian, no reference term
+        x = torch.linalg.solve(G.sum(0), r.sum(0)[:, None])[None, :, 0].expand(B, -1)
+    else:
+        x = torch.linalg.solve(G, (r + lam * ref)[..., None])[..., 0]
+    x = x.to(t.dtype)
     trans = mean_b - torch.einsum('bcs,bs->bc', mean_A, x)
-    joints = P[..., 0] + torch.einsum('bjcs,bs->bjc', P[..., 1:], x) + trans[:, None]
-    verts = ext[..., 0] + torch.einsum('bvcs,bs->bvc', ext[..., 1:], x) + trans[:, None]
-    return x, trans, rel, joints, verts
+    out = {'relative_orientations': rel}
+    beta = x[:, :S]
+    kid = x[:, S] if enable_kid else None
+    out['shape_betas'], out['trans'] = beta, trans
+    if kid is not None:
+        out['kid_factor'] = kid
+    if scale_mode:
+        sc = x[:, -1] + 1
+        out['scale_corr'] = sc
+        if scale_mode == 2:  # the returned betas / kid factor stay unscaled; the mesh of the next stage uses beta / s
+            beta = beta / sc[:, None]
+            kid = kid / sc if kid is not None else None
+    coef = beta if kid is None else torch.cat([beta, kid[:, None]], 1)
+    out['joints'] = P[..., 0] + torch.einsum('bjcs,bs->bjc', P[..., 1:], coef) + trans[:, None]
+    out['vertices'] = ext[..., 0] + torch.einsum('bvcs,bs->bvc', ext[..., 1:], coef) + trans[:, None]
+    return out
 
 
-def _fit_global_rotations_dependent(c: Constants, S: int, t, tj, a, aj, vw, jw, R_prev, betas, trans):
+def _fit_global_rotations_dependent(c: Constants, S: int, t, tj, a, aj, vw, jw, R_prev, betas, trans, kid=None,
+                                    scale_corr=None):
     """Final adjustment along the kinematic chain (pt/bodyfitter.py:1418-1469, :1546-1595): each adjustable part is
     re-fitted about the position its joint gets from the already adjusted parents."""
     true_aj = aj
@@ -346,6 +395,10 @@ def _fit_global_rotations_dependent(c: Constants, S: int, t, tj, a, aj, vw, jw, 
         true_aj = aj
     p = c.plan
     j = c.J_template[None] + torch.einsum('jcs,bs->bjc', c.J_shapedirs[:, :, :S], betas[:, :S])
+    if kid is not None:
+        j = j + c.kid_J_shapedir[None] * kid[:, None, None]
+    if scale_corr is not None:
+        j = j * scale_corr[:, None, None]
     raw, s_t, s_a, s_w = _part_sums(c, t, a, vw)
     R: List[torch.Tensor] = [R_prev[:, i] for i in range(c.J)]
     pos: List[Optional[torch.Tensor]] = [None] * c.J
@@ -376,13 +429,17 @@ def _fit_global_rotations_dependent(c: Constants, S: int, t, tj, a, aj, vw, jw, 
 def fit(bm, n_betas: int, target_vertices, target_joints=None, vertex_weights=None, joint_weights=None,
         num_iter: int = 1, beta_regularizer: float = 1.0, beta_regularizer2: float = 0.0,
         final_adjust_rots: bool = True, initial_pose_rotvecs=None, initial_shape_betas=None,
-        want_pose_rotvecs: bool = True, want_rel_orient: bool = False):
-    """Differentiable evaluation of the closed-form fit.  Returns (shape_betas, trans, orientations,
-    relative_orientations, pose_rotvecs or None) -- the tensors of the ``smplfit_b200::fit`` op in its order."""
+        want_pose_rotvecs: bool = True, want_rel_orient: bool = False, enable_kid: bool = False,
+        scale_regularizer: float = 0.0, kid_regularizer: Optional[float] = None, share_beta: bool = False,
+        scale_target: bool = False, scale_fit: bool = False, initial_kid_factor=None):
+    """Differentiable evaluation of the closed-form fit (driver: pt/bodyfitter.py:283-549).  Returns (shape_betas,
+    trans, orientations, relative_orientations, pose_rotvecs | None, kid_factor | None, scale_corr | None) -- the
+    tensors of the ``smplfit_b200::fit`` op in its order."""
     t = target_vertices
     c = constants(bm, t.dtype, t.device)
     S = n_betas
     tj, vw, jw = target_joints, vertex_weights, joint_weights
+    scale_mode = 1 if scale_target else (2 if scale_fit else 0)
     if tj is None:
         mean = t.mean(1)
         t = t - mean[:, None]
@@ -390,24 +447,44 @@ def fit(bm, n_betas: int, target_vertices, target_joints=None, vertex_weights=No
         mean = torch.cat([t, tj], 1).mean(1)
         t, tj = t - mean[:, None], tj - mean[:, None]
     if initial_pose_rotvecs is not None or initial_shape_betas is not None:
-        ij, io, iv = lbs(c, pose_rotvecs=initial_pose_rotvecs, shape_betas=initial_shape_betas)
+        ij, io, iv = lbs(c, pose_rotvecs=initial_pose_rotvecs, shape_betas=initial_shape_betas, kid_factor=initial_kid_factor)
         glob = _fit_global_rotations(c, t, tj, iv, ij, vw, jw) @ io
     else:
         if c.template_mesh is None:
             with torch.no_grad():
                 c.template_mesh = lbs(c)[2]
         glob = _fit_global_rotations(c, t, tj, c.template_mesh, c.J_template[None], vw, jw)
+    kid_ref = initial_kid_factor if enable_kid else None
+    shape = lambda g, sm, sr: _fit_shape(c, S, g, t, tj, vw, jw, beta_regularizer, beta_regularizer2,  # noqa: E731
+                                         initial_shape_betas, enable_kid, kid_regularizer, kid_ref, sm, sr, share_beta)
     for _ in range(num_iter - 1):
-        _, _, _, rj, rv = _fit_shape(c, S, glob, t, tj, vw, jw, beta_regularizer, beta_regularizer2, initial_shape_betas)
-        glob = _fit_global_rotations(c, t, tj, rv, rj if tj is not None else None, vw, jw) @ glob
-    betas, trans, rel, rj, rv = _fit_shape(c, S, glob, t, tj, vw, jw, beta_regularizer, beta_regularizer2,
-                                           initial_shape_betas)
+        res = shape(glob, 0, 0.0)
+        glob = _fit_global_rotations(c, t, tj, res['vertices'], res['joints'] if tj is not None else None, vw, jw) @ glob
+    res = shape(glob, scale_mode, scale_regularizer)
+    betas, trans, rel = res['shape_betas'], res['trans'], res['relative_orientations']
+    kid, sc = res.get('kid_factor'), res.get('scale_corr')
     if final_adjust_rots:
-        glob = _fit_global_rotations_dependent(c, S, t, tj, rv, rj, vw, jw, glob, betas, trans)
+        rv, rj = res['vertices'], res['joints']
+        if scale_mode == 1:
+            s3 = sc[:, None, None]
+            glob = _fit_global_rotations_dependent(c, S, t * s3, tj * s3 if tj is not None else None, rv, rj, vw, jw, glob,
+                                                   betas, trans, kid)
+        elif scale_mode == 2:
+            s3, tr = sc[:, None, None], trans[:, None]
+            glob = _fit_global_rotations_dependent(c, S, t, tj, s3 * rv + (1 - s3) * tr, s3 * rj + (1 - s3) * tr, vw, jw,
+                                                   glob, betas, trans, kid, sc)
+        else:
+            glob = _fit_global_rotations_dependent(c, S, t, tj, rv, rj, vw, jw, glob, betas, trans, kid)
+    if scale_mode == 1:
+        trans = trans + mean * sc[:, None]
+    elif scale_mode == 2:
+        trans = trans + mean / sc[:, None]
+    else:
+        trans = trans + mean
     if want_pose_rotvecs or want_rel_orient:
         rel = _relative(c, glob)
     rotvecs = mat2rotvec(rel).reshape(glob.shape[0], -1) if want_pose_rotvecs else None
-    return betas, trans + mean, glob, rel, rotvecs
+    return betas, trans, glob, rel, rotvecs, kid, sc
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -478,15 +555,17 @@ def forward_backward(bm, tensors, needs, return_vertices: bool, grads_out):
 
 def fit_backward(fitter, tensors, needs, opts: dict, grads_out):
     """Backward of ``smplfit_b200::fit``.  ``tensors`` = (target_vertices, target_joints, vertex_weights, joint_weights,
-    initial_pose_rotvecs, initial_shape_betas); ``grads_out`` = cotangents of (shape_betas, trans, orientations,
-    relative_orientations, pose_rotvecs)."""
+    initial_pose_rotvecs, initial_shape_betas, initial_kid_factor); ``grads_out`` = cotangents of (shape_betas, trans,
+    orientations, relative_orientations, pose_rotvecs, kid_factor, scale_corr); ``opts`` = the keyword options of
+    ``fit`` above.  ``share_beta`` couples the instances: one slice."""
     bm = fitter.body_model
     B = tensors[0].shape[0]
     S = fitter.n_betas
 
-    def run(tv, tj, vw, jw, ip, ib):
-        return fit(bm, S, tv, tj, vw, jw, opts['num_iter'], opts['beta_regularizer'], opts['beta_regularizer2'],
-                   opts['final_adjust_rots'], ip, ib, opts['want_pose_rotvecs'], opts['want_rel_orient'])
+    def run(tv, tj, vw, jw, ip, ib, ik):
+        return fit(bm, S, tv, tj, vw, jw, initial_pose_rotvecs=ip, initial_shape_betas=ib, initial_kid_factor=ik,
+                   enable_kid=fitter.enable_kid, **opts)
 
     per = 4.0 * bm.num_vertices * 3 * (S + 14) * 6 * max(1, opts['num_iter'])  # Jacobians kept per shape stage
-    return _pullback(B, tensors, needs, run, grads_out, _slices(B, per), bm.v_template.device)
+    slices = [(0, B)] if opts.get('share_beta') else _slices(B, per)
+    return _pullback(B, tensors, needs, run, grads_out, slices, bm.v_template.device)

@@ -151,15 +151,13 @@ def _(handle, target_vertices, target_joints, vertex_weights, joint_weights, num
 
 
 def _fit_setup(ctx, inputs, output):
-    (handle, tv, tj, vw, jw, num_iter, reg, reg2, _scale_reg, _kid_reg, share_beta, final_adjust_rots, scale_target,
+    (handle, tv, tj, vw, jw, num_iter, reg, reg2, scale_reg, kid_reg, share_beta, final_adjust_rots, scale_target,
      scale_fit, init_pose, init_betas, init_kid, want_rv, want_rel) = inputs
-    if _get(handle).enable_kid or share_beta or scale_target or scale_fit or init_kid is not None:
-        raise NotImplementedError(
-            'smplfitter_b200: gradients through fit() are available for the closed-form gram path only (no enable_kid, '
-            'share_beta, scale_target / scale_fit, initial_kid_factor); detach the inputs or drop those options')
-    tensors = [tv, tj, vw, jw, init_pose, init_betas]
+    tensors = [tv, tj, vw, jw, init_pose, init_betas, init_kid]
     ctx.handle, ctx.needs = handle, _needs(tensors)
-    ctx.opts = dict(num_iter=num_iter, beta_regularizer=reg, beta_regularizer2=reg2, final_adjust_rots=final_adjust_rots,
+    ctx.opts = dict(num_iter=num_iter, beta_regularizer=reg, beta_regularizer2=reg2, scale_regularizer=scale_reg,
+                    kid_regularizer=None if kid_reg != kid_reg else kid_reg, share_beta=share_beta,
+                    final_adjust_rots=final_adjust_rots, scale_target=scale_target, scale_fit=scale_fit,
                     want_pose_rotvecs=want_rv, want_rel_orient=want_rel)
     ctx.save_for_backward(*tensors)
 
@@ -168,8 +166,8 @@ def _fit_backward(ctx, grads):
     """Gradient of the fit with respect to targets, weights and initial guesses: see ``_adjoint``."""
     from . import _adjoint
 
-    g = _adjoint.fit_backward(_get(ctx.handle), list(ctx.saved_tensors), ctx.needs, ctx.opts, grads[:5])
-    return (None, g[0], g[1], g[2], g[3], None, None, None, None, None, None, None, None, None, g[4], g[5], None, None,
+    g = _adjoint.fit_backward(_get(ctx.handle), list(ctx.saved_tensors), ctx.needs, ctx.opts, grads)
+    return (None, g[0], g[1], g[2], g[3], None, None, None, None, None, None, None, None, None, g[4], g[5], g[6], None,
             None)
 
 

@@ -14,17 +14,16 @@ from oracle.make_golden import FIT_CASES
 from oracle.make_grad_golden import FIT_OUTPUTS, FWD_OUTPUTS, GRAD_FIT_CASES, GRAD_FORWARD_CASES, fit_inputs
 from smplfitter_b200.pt import _adjoint
 
-ADJ_OPTS = ('num_iter', 'beta_regularizer', 'beta_regularizer2', 'final_adjust_rots')
-
-
 def _model(name):
     mname, mkw = FIT_CASES[name][0], FIT_CASES[name][1]
     return pt.BodyModel(mname, **mkw)
 
 
-def _run(bm, tens, opts, want_rel=True):
-    kw = {k: v for k, v in opts.items() if k in ADJ_OPTS}
-    return _adjoint.fit(bm, bm.num_betas, want_pose_rotvecs=True, want_rel_orient=want_rel, **tens, **kw)
+def _run(bm, tens, opts, want_rel=True, name=None):
+    """-> dict of the outputs present (FIT_OUTPUTS order)."""
+    fitkw = FIT_CASES[name][2] if name else {}
+    out = _adjoint.fit(bm, bm.num_betas, want_pose_rotvecs=True, want_rel_orient=want_rel, **tens, **opts, **fitkw)
+    return {k: o for k, o in zip(FIT_OUTPUTS, out) if o is not None}
 
 
 @pytest.mark.parametrize('name', sorted(GRAD_FIT_CASES))
@@ -32,9 +31,11 @@ def test_adjoint_evaluation_is_the_fit(name):
     """float64 evaluation == float64 oracle of the same case (1e-9), i.e. the function differentiated is the fit."""
     g = gc.load(name)
     tens, opts = fit_inputs(name, g)
-    out = _run(_model(name), {k: torch.from_numpy(v).double() for k, v in tens.items()}, opts)
-    for k, o in zip(FIT_OUTPUTS, out):
-        assert np.abs(o.numpy() - g['exact_' + k]).max() < 1e-9, k
+    out = _run(_model(name), {k: torch.from_numpy(v).double() for k, v in tens.items()}, opts, name=name)
+    assert set(out) == {k[6:] for k in g if k.startswith('exact_')}
+    for k, o in out.items():
+        # (1e9 kid regulariser of the converter-style case: the float64 solve itself is only good to ~1e-7 there)
+        assert np.abs(o.numpy() - g['exact_' + k]).max() < (1e-6 if 'converter' in name else 1e-9), k
 
 
 @pytest.mark.parametrize('dtype,tol', [(torch.float64, 2e-3), (torch.float32, 1e-2)])
@@ -50,8 +51,8 @@ def test_fit_gradients_match_reference_autograd(name, dtype, tol):
     tens, opts = fit_inputs(name, g)
     wrt = GRAD_FIT_CASES[name]
     tt = {k: torch.from_numpy(v).to(dtype).requires_grad_(k in wrt) for k, v in tens.items()}
-    out = _run(_model(name), tt, opts)
-    loss = sum((o * torch.from_numpy(gg['cot_' + k]).to(dtype)).sum() for k, o in zip(FIT_OUTPUTS, out))
+    out = _run(_model(name), tt, opts, name=name)
+    loss = sum((o * torch.from_numpy(gg['cot_' + k]).to(dtype)).sum() for k, o in out.items())
     grads = torch.autograd.grad(loss, [tt[k] for k in wrt])
     for k, gr in zip(wrt, grads):
         ref = gg['ref_grad_' + k]
@@ -79,7 +80,8 @@ def test_forward_gradients_match_reference_autograd(name):
         assert np.abs(gr.numpy() - ref).max() / np.abs(ref).max() < 1e-4, k
 
 
-@pytest.mark.parametrize('name', ['fit_tiny_it3', 'fit_tiny_weights', 'fit_tiny_nojoints'])
+@pytest.mark.parametrize('name', ['fit_tiny_it3', 'fit_tiny_weights', 'fit_tiny_nojoints', 'fit_tiny_kid',
+                                  'fit_tiny_scale_fit', 'fit_tiny_share_beta', 'fit_tiny_share_beta_scale'])
 def test_fit_gradient_vs_finite_differences(name):
     """Directional central difference in float64 (the reference's own check, tests/pt/test_fitter_grad.py:56-99, at
     float64 resolution instead of its 5 %)."""
@@ -87,10 +89,10 @@ def test_fit_gradient_vs_finite_differences(name):
     tens, opts = fit_inputs(name, g)
     bm = _model(name)
     base = {k: torch.from_numpy(v).double() for k, v in tens.items()}
-    cot = {k: torch.from_numpy(gg['cot_' + k]).double() for k in FIT_OUTPUTS}
+    cot = {k[4:]: torch.from_numpy(v).double() for k, v in gg.items() if k.startswith('cot_')}
 
     def loss_of(tt):
-        return sum((o * cot[k]).sum() for k, o in zip(FIT_OUTPUTS, _run(bm, tt, opts)))
+        return sum((o * cot[k]).sum() for k, o in _run(bm, tt, opts, name=name).items())
 
     rs = np.random.RandomState(7)
     for key in GRAD_FIT_CASES[name]:
@@ -145,7 +147,8 @@ def test_backward_of_the_fit_op_slices_and_accumulates(monkeypatch):
     def fake_impl(tv, tj, vw, jw, num_iter, reg, reg2, sreg, kreg, share, adj, st, sf, ip, ib, ik, keys):
         with torch.no_grad():
             o = _adjoint.fit(bm, bm.num_betas, tv, tj, vw, jw, num_iter, reg, reg2, adj, ip, ib,
-                             'pose_rotvecs' in keys, 'relative_orientations' in keys)
+                             'pose_rotvecs' in keys, 'relative_orientations' in keys, scale_regularizer=sreg,
+                             kid_regularizer=kreg, share_beta=share, scale_target=st, scale_fit=sf, initial_kid_factor=ik)
         res = dict(zip(FIT_OUTPUTS, o))
         return {k: v for k, v in res.items() if v is not None}
 
@@ -159,8 +162,7 @@ def test_backward_of_the_fit_op_slices_and_accumulates(monkeypatch):
     loss = out['pose_rotvecs'].pow(2).sum() + out['shape_betas'].sum()  # trans / orientations get no cotangent
     loss.backward()
     t2 = {k: v.detach().clone().requires_grad_(True) for k, v in tt.items()}
-    o2 = _adjoint.fit(bm, bm.num_betas, want_pose_rotvecs=True, **t2,
-                      **{k: v for k, v in opts.items() if k in ADJ_OPTS})
+    o2 = _adjoint.fit(bm, bm.num_betas, want_pose_rotvecs=True, **t2, **opts)
     (o2[4].pow(2).sum() + o2[0].sum()).backward()
     for k in tt:
         assert tt[k].grad is not None and torch.isfinite(tt[k].grad).all()
@@ -169,6 +171,9 @@ def test_backward_of_the_fit_op_slices_and_accumulates(monkeypatch):
     # no gradient requested: the op's outputs do not track
     out = fitter.fit(**{k: v.detach() for k, v in tt.items()}, **opts)
     assert not out['pose_rotvecs'].requires_grad
-    # options outside the differentiable path fail loudly instead of returning a wrong gradient
-    with pytest.raises(NotImplementedError):
-        fitter.fit(**tt, **opts, scale_target=True)
+    # scale estimation through the op: the extra output carries a gradient too
+    for v in tt.values():
+        v.grad = None
+    out = fitter.fit(**tt, **opts, scale_target=True, requested_keys=['pose_rotvecs'])
+    (out['scale_corr'].sum() + out['trans'].sum()).backward()
+    assert all(torch.isfinite(v.grad).all() for v in tt.values()) and tt['target_vertices'].grad.abs().max() > 0

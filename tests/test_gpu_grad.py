@@ -79,15 +79,17 @@ def test_fitter_grad_vs_finite_diff(seed):
 
 @pytest.mark.parametrize('name', sorted(GRAD_FIT_CASES))
 def test_fit_gradients_match_reference_autograd(name):
+    """Every option family of fit(): joints or not, weights, initial guesses, kid factor, scale estimation, shared betas."""
     g, gg = gc.load(name), gc.load('grad_' + name)
     tens, opts = fit_inputs(name, g)
     wrt = GRAD_FIT_CASES[name]
-    mname, mkw = FIT_CASES[name][0], FIT_CASES[name][1]
-    fitter = pt.BodyFitter(pt.BodyModel(mname, **mkw).cuda()).cuda()
+    mname, mkw, fitkw = FIT_CASES[name][0], FIT_CASES[name][1], FIT_CASES[name][2]
+    fitter = pt.BodyFitter(pt.BodyModel(mname, **mkw).cuda(), **fitkw).cuda()
     tt = {k: torch.from_numpy(v).cuda().requires_grad_(k in wrt) for k, v in tens.items()}
     out = fitter.fit(**tt, **opts, requested_keys=['pose_rotvecs', 'shape_betas', 'relative_orientations'])
-    loss = sum((out[k] * torch.from_numpy(gg['cot_' + k]).cuda()).sum() for k in FIT_OUTPUTS)
-    loss.backward()
+    cot = {k[4:]: torch.from_numpy(v).cuda() for k, v in gg.items() if k.startswith('cot_')}
+    assert set(cot) <= set(out)
+    sum((out[k] * c).sum() for k, c in cot.items()).backward()
     tol = 5e-2 if 'smplx' in name else 1e-2
     for k in wrt:
         ref = gg['ref_grad_' + k]
@@ -197,12 +199,13 @@ def test_body_fitter_opt():
     assert (rot6d_to_rotmat(rotmat_to_rot6d(R)) - R).abs().max() < 1e-5
 
 
-def test_unsupported_options_raise_when_grad_is_requested():
-    bm = pt.BodyModel('smpl_tiny').cuda()
+def test_share_beta_backward_is_one_slice(monkeypatch):
+    """share_beta couples the instances: the backward must not cut the batch."""
+    bm, tv, tj = _targets('smpl_tiny', 6, seed=4)
     fitter = pt.BodyFitter(bm).cuda()
-    tv = bm(shape_betas=torch.zeros(2, 10).cuda())['vertices'].requires_grad_(True)
-    with pytest.raises(NotImplementedError):
-        fitter.fit(tv, scale_target=True)
-    with pytest.raises(NotImplementedError):
-        fitter.fit(tv, share_beta=True)
-    assert 'pose_rotvecs' in fitter.fit(tv.detach(), scale_target=True)  # fine without grad
+    monkeypatch.setattr(_adjoint, '_slices', lambda *a, **k: pytest.fail('share_beta backward was sliced'))
+    a = tv.clone().requires_grad_(True)
+    out = fitter.fit(a, tj, num_iter=2, share_beta=True, requested_keys=['pose_rotvecs', 'shape_betas', 'trans'])
+    assert (out['shape_betas'] - out['shape_betas'][:1]).abs().max() == 0
+    _loss(out).backward()
+    assert torch.isfinite(a.grad).all() and a.grad.abs().max() > 0
