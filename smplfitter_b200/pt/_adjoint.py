@@ -490,8 +490,15 @@ def fit(bm, n_betas: int, target_vertices, target_joints=None, vertex_weights=No
 # ----------------------------------------------------------------------------------------------------------------------
 # backward of the custom ops: slice the batch, re-evaluate with grad, pull the cotangents back
 # ----------------------------------------------------------------------------------------------------------------------
-def _slices(B: int, per_instance_bytes: float, budget: float = 1.5e9):
-    n = int(max(1, min(B, budget // max(per_instance_bytes, 1.0))))
+def _slices(B: int, per_instance_bytes: float, budget: Optional[float] = None, device=None, cap: int = 512):
+    """Cut the batch so that one slice's saved intermediates stay within ``budget`` bytes (default: 30 % of the free
+    device memory, at least 1.5 GB) and within ``cap`` instances (beyond a few hundred instances the evaluation is
+    no longer launch-bound, so larger slices only cost memory)."""
+    if budget is None:
+        budget = 1.5e9
+        if device is not None and torch.device(device).type == 'cuda':
+            budget = max(budget, 0.3 * torch.cuda.mem_get_info(device)[0])
+    n = int(max(1, min(B, cap, budget // max(per_instance_bytes, 1.0))))
     return [(a, min(a + n, B)) for a in range(0, B, n)]
 
 
@@ -550,7 +557,7 @@ def forward_backward(bm, tensors, needs, return_vertices: bool, grads_out):
         return lbs(c, pose, betas, trans, kid, rel, glob, return_vertices)
 
     per = 4.0 * c.V * (3 * 12 + 9 + c.J)  # posed template, blended transforms, outputs
-    return _pullback(B, tensors, needs, run, grads_out, _slices(B, per), dev)
+    return _pullback(B, tensors, needs, run, grads_out, _slices(B, per, device=dev, cap=4096), dev)
 
 
 def fit_backward(fitter, tensors, needs, opts: dict, grads_out):
@@ -566,6 +573,9 @@ def fit_backward(fitter, tensors, needs, opts: dict, grads_out):
         return fit(bm, S, tv, tj, vw, jw, initial_pose_rotvecs=ip, initial_shape_betas=ib, initial_kid_factor=ik,
                    enable_kid=fitter.enable_kid, **opts)
 
-    per = 4.0 * bm.num_vertices * 3 * (S + 14) * 6 * max(1, opts['num_iter'])  # Jacobians kept per shape stage
-    slices = [(0, B)] if opts.get('share_beta') else _slices(B, per)
-    return _pullback(B, tensors, needs, run, grads_out, slices, bm.v_template.device)
+    # saved per shape stage: the (V, 3, 1 + S) skinned basis, its centred / weighted copies, the blend matrices
+    # (measured on the B200: 12 MB per SMPL instance at num_iter = 3, this estimate gives 15 MB)
+    per = 4.0 * bm.num_vertices * 3 * (S + 14) * 2.5 * max(1, opts['num_iter'])
+    dev = bm.v_template.device
+    slices = [(0, B)] if opts.get('share_beta') else _slices(B, per, device=dev)
+    return _pullback(B, tensors, needs, run, grads_out, slices, dev)

@@ -502,18 +502,16 @@ class BodyModel(_ops.RegisteredModule, nn.Module):
         """
         from .rotation import mat2rotvec, rotvec2mat
 
-        if t is None:
-            t = torch.zeros(3, device=R.device, dtype=R.dtype)
-        if pose_rotvecs is None or shape_betas is None or trans is None:
+        missing = [n for n, v in (('pose_rotvecs', pose_rotvecs), ('shape_betas', shape_betas), ('trans', trans)) if v is None]
+        if missing:
             raise ValueError('pose_rotvecs, shape_betas, and trans are required.')
-        new_rotmat = R @ rotvec2mat(pose_rotvecs[:3])
-        new_pose_rotvec = torch.cat([mat2rotvec(new_rotmat), pose_rotvecs[3:]], dim=0)
-        pelvis = self.J_template[0] + self.J_shapedirs[0, :, : shape_betas.shape[0]] @ shape_betas
+        shift = R.new_zeros(3) if t is None else t
+        # the root joint turns with R about the rest pelvis p(beta): x -> R (x - p) + p, so the body translation
+        # picks up (R - I) p on top of the rigid motion of `trans`
+        n_b = shape_betas.shape[0]
+        p = self.J_template[0] + self.J_shapedirs[0, :, :n_b] @ shape_betas
         if kid_factor is not None:
-            pelvis = pelvis + self.kid_J_shapedir[0] * kid_factor
-        eye3 = torch.eye(3, device=R.device, dtype=R.dtype)
-        if post_translate:
-            new_trans = trans @ R.mT + t + pelvis @ (R.mT - eye3)
-        else:
-            new_trans = (trans - t) @ R.mT + pelvis @ (R.mT - eye3)
-        return new_pose_rotvec, new_trans
+            p = p + kid_factor * self.kid_J_shapedir[0]
+        root = mat2rotvec(R @ rotvec2mat(pose_rotvecs[:3]))
+        moved = R @ trans + shift if post_translate else R @ (trans - shift)
+        return torch.cat([root, pose_rotvecs[3:]]), moved + (R @ p - p)

@@ -153,7 +153,7 @@ def test_backward_of_the_fit_op_slices_and_accumulates(monkeypatch):
         return {k: v for k, v in res.items() if v is not None}
 
     monkeypatch.setattr(fitter, '_fit_impl', fake_impl)
-    monkeypatch.setattr(_adjoint, '_slices', lambda B, per, budget=0: [(a, min(a + 3, B)) for a in range(0, B, 3)])
+    monkeypatch.setattr(_adjoint, '_slices', lambda B, per, *a, **k: [(a, min(a + 3, B)) for a in range(0, B, 3)])
     tt = {k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in tens.items()}
     tt['initial_pose_rotvecs'] = tt['initial_pose_rotvecs'][:1].detach().clone().requires_grad_(True)  # broadcast input
     tt['initial_shape_betas'] = tt['initial_shape_betas'][:1].detach().clone().requires_grad_(True)
@@ -177,3 +177,26 @@ def test_backward_of_the_fit_op_slices_and_accumulates(monkeypatch):
     out = fitter.fit(**tt, **opts, scale_target=True, requested_keys=['pose_rotvecs'])
     (out['scale_corr'].sum() + out['trans'].sum()).backward()
     assert all(torch.isfinite(v.grad).all() for v in tt.values()) and tt['target_vertices'].grad.abs().max() > 0
+
+
+@pytest.mark.parametrize('post_translate', [True, False])
+@pytest.mark.parametrize('kid', [False, True])
+def test_rototranslate_moves_the_mesh_rigidly(post_translate, kid):
+    """BodyModel.rototranslate (pt/bodymodel.py:382-453): the returned parameters pose the mesh at R x + t
+    (post_translate) or R (x - t), checked with the torch evaluation of the forward pass."""
+    bm = pt.BodyModel('smpl_tiny')
+    c = _adjoint.constants(bm, torch.float64, torch.device('cpu'))
+    torch.manual_seed(1)
+    pose, betas, trans = torch.randn(72).double() * 0.3, torch.randn(10).double() * 0.5, torch.randn(3).double()
+    kf = torch.tensor(0.4, dtype=torch.float64) if kid else None
+    R = _adjoint.rotvec2mat(torch.tensor([0.3, -1.1, 0.6], dtype=torch.float64))
+    t = torch.tensor([0.2, -0.5, 1.5], dtype=torch.float64)
+    bm64 = pt.BodyModel('smpl_tiny').double()
+    new_pose, new_trans = bm64.rototranslate(R, t, pose, betas, trans, kf, post_translate=post_translate)
+    kb = None if kf is None else kf[None]
+    v0 = _adjoint.lbs(c, pose[None], betas[None], trans[None], kb)[2][0]
+    v1 = _adjoint.lbs(c, new_pose[None], betas[None], new_trans[None], kb)[2][0]
+    want = v0 @ R.T + t if post_translate else (v0 - t) @ R.T
+    assert (v1 - want).abs().max() < 1e-7
+    with pytest.raises(ValueError):
+        bm64.rototranslate(R, t, pose, None, trans)

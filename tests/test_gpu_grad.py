@@ -147,7 +147,7 @@ def test_backward_slices_large_batch(monkeypatch):
     fitter = pt.BodyFitter(bm).cuda()
     calls = []
     real = _adjoint._slices
-    monkeypatch.setattr(_adjoint, '_slices', lambda B, per, budget=1.5e9: calls.append(B) or real(B, per, 16 * per))
+    monkeypatch.setattr(_adjoint, '_slices', lambda B, per, *a, **k: calls.append(B) or real(B, per, 16 * per))
     a = tv.clone().requires_grad_(True)
     _loss(fitter.fit(a, tj, num_iter=2, requested_keys=['pose_rotvecs', 'shape_betas', 'trans'])).backward()
     assert calls == [70]
