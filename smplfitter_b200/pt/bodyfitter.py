@@ -35,7 +35,7 @@ class BodyFitter(_ops.RegisteredModule, nn.Module):
         plan = body_model._plan
         self.is_smpl_family = plan.is_smpl_family
         # reference-named static tables (pt/bodyfitter.py:36-233)
-        i64 = lambda x: torch.tensor(np.ascontiguousarray(np.asarray(x), dtype=np.int64))  # noqa: E731
+        i64 = lambda x: torch.from_numpy(np.array(x, dtype=np.int64, order='C'))  # noqa: E731
         self.part_assignment = nn.Buffer(i64(plan.part_assignment))
         self.part_vertex_selectors = [i64(s) for s in plan.part_vertex_selectors]
         self.children_and_self = plan.children_and_self
@@ -82,7 +82,7 @@ class BodyFitter(_ops.RegisteredModule, nn.Module):
         sd_np = sd.cpu().numpy().astype(np.float32)
         w_np = body_model.weights.cpu().numpy()
         wS = np.einsum('vk,vcs->kcs', w_np.astype(np.float64), sd_np.astype(np.float64))
-        self.register_buffer('_t_fit_wS', torch.tensor(np.ascontiguousarray(wS)), persistent=False)
+        self.register_buffer('_t_fit_wS', torch.from_numpy(np.ascontiguousarray(wS)), persistent=False)
         self.register_buffer('_t_fit_wsum', torch.tensor(w_np.astype(np.float64).sum(axis=0)), persistent=False)
         K = body_model._dims['skin_k']
         nsp = (ns + 1) // 2 * 2
@@ -102,7 +102,7 @@ class BodyFitter(_ops.RegisteredModule, nn.Module):
             rec[:, 4:8] = idx4.view(np.float32)
             for x in range(3):
                 rec[:, 8 + x * nsp:8 + x * nsp + ns] = sd_np[:, x, :]
-            self.register_buffer('_t_fit_rec', torch.tensor(np.ascontiguousarray(rec[order])), persistent=False)
+            self.register_buffer('_t_fit_rec', torch.from_numpy(np.ascontiguousarray(rec[order])), persistent=False)
             # per vertex (internal order): bit k set when skinning slot k must (re)load its joint rows, i.e. its weight
             # is non-zero and its joint differs from the last one loaded for that slot in the same segment -- the
             # kernels' register cache of joint rows (lite_kernels.cuh JointCache) replayed on the host
@@ -174,21 +174,21 @@ class BodyFitter(_ops.RegisteredModule, nn.Module):
                     bm_cells.append(cell)
                     wh_cells.append(0.5 * Wkl[p])
             lstart.append(len(lk))
-        i32 = lambda x: torch.tensor(np.ascontiguousarray(x), dtype=torch.int32)  # noqa: E731
+        i32 = lambda x: torch.from_numpy(np.array(x, dtype=np.int32, order='C'))  # noqa: E731
         reg = lambda n, t: self.register_buffer(n, t, persistent=False)  # noqa: E731
         reg('_t_gcf_pairs', i32(np.array(off or [(0, 0)], np.int32).reshape(-1, 2)))
-        reg('_t_gcf_A', torch.tensor(np.ascontiguousarray(A)))
+        reg('_t_gcf_A', torch.from_numpy(np.ascontiguousarray(A)))
         # the same constants as a GEMM operand: AT[e][p*9 + ab], rows padded to the 256-row tile, K to 32, hi/lo split
         kt = (9 * max(len(off), 1) + 31) // 32 * 32
         AT = np.zeros(((ng + 255) // 256 * 256, kt), np.float32)
         AT[:ng, :9 * A.shape[0]] = A[:, :, :ng].reshape(-1, ng).T
         at_hi = (AT.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
-        reg('_t_gcf_AT_hi', torch.tensor(np.ascontiguousarray(at_hi)))
-        reg('_t_gcf_AT_lo', torch.tensor(np.ascontiguousarray(AT - at_hi)))
+        reg('_t_gcf_AT_hi', torch.from_numpy(np.ascontiguousarray(at_hi)))
+        reg('_t_gcf_AT_lo', torch.from_numpy(np.ascontiguousarray(AT - at_hi)))
         reg('_t_gcf_G0', torch.tensor(G0))
         reg('_t_gcf_lstart', i32(np.array(lstart)))
         reg('_t_gcf_lk', i32(np.array(lk)))
-        reg('_t_gcf_Bm', torch.tensor(np.ascontiguousarray(np.stack(bm_cells).astype(np.float32))))
+        reg('_t_gcf_Bm', torch.from_numpy(np.ascontiguousarray(np.stack(bm_cells).astype(np.float32))))
         reg('_t_gcf_Wh', torch.tensor(np.array(wh_cells, np.float32)))
         self._gcf_npairs = len(off)
 
@@ -228,10 +228,9 @@ class BodyFitter(_ops.RegisteredModule, nn.Module):
                     pack = (m << 24) | (1 << 28)
                     for k in range(4):
                         pack |= (max(cached[k], 0) & 63) << (6 * k)
-                    s_ = 32 * q + (i - int(seg_start[q]))
-                    rec[s_, 0:4] = w_o[i].astype(np.float32).view(np.uint32)
-                    rec[s_, 4] = pack
-                    rec[s_, 5:8] = v_rest[i].astype(np.float32).view(np.uint32)
+                    rec[32 * q + (i - int(seg_start[q])), 4] = pack
+        rec[live, 0:4] = np.ascontiguousarray(w_o, dtype=np.float32).view(np.uint32)[slot_of[live]]
+        rec[live, 5:8] = v_rest.astype(np.float32).view(np.uint32)[slot_of[live]]
         # bits 29 / 30 of the first record of every 8-slot block: some slot reloads within the first / second four slots
         # of the block (the kernel's branch-free fast path needs four vertices without reloads)
         any_rl = ((rec[:, 4] >> 24) & 0xF).reshape(-1, 2, 4).max(axis=2) != 0

@@ -97,7 +97,7 @@ class BodyModel(_ops.RegisteredModule, nn.Module):
             model_name, gender, model_root, num_betas, vertex_subset_size, vertex_subset, faces,
             joint_regressor_post_lbs,
         )
-        f32 = lambda x: torch.tensor(np.ascontiguousarray(np.asarray(x), dtype=np.float32))  # noqa: E731
+        f32 = lambda x: torch.from_numpy(np.array(x, dtype=np.float32, order='C'))  # (a private copy)  # noqa: E731
         self.v_template = nn.Buffer(f32(data.v_template))
         self.shapedirs = nn.Buffer(f32(data.shapedirs))
         self.posedirs = nn.Buffer(f32(data.posedirs))
@@ -168,7 +168,7 @@ class BodyModel(_ops.RegisteredModule, nn.Module):
         template_mesh = (v_posed0 * w32.sum(axis=1, keepdims=True)).astype(np.float32)  # pt/bodyfitter.py:49
         flags = (plan.part_is_stat.astype(np.int32) | (plan.part_is_adjustable.astype(np.int32) << 1))
         jreg = self.J_regressor_post_lbs.numpy()
-        i32 = lambda x: torch.tensor(np.ascontiguousarray(x), dtype=torch.int32)  # noqa: E731
+        i32 = lambda x: torch.from_numpy(np.array(x, dtype=np.int32, order='C'))  # noqa: E731
         t = {
             'parents': i32(plan.parents), 'skin_idx': i32(skin_idx), 'skin_w': f32(skin_w),
             'order': i32(order), 'inv_order': i32(inv_order), 'seg_start': i32(seg_start),
@@ -226,6 +226,7 @@ class BodyModel(_ops.RegisteredModule, nn.Module):
         # one sequential replay of the cache over the whole processing order: every record carries the cache content
         # AFTER its vertex (the joint of each slot), so a warp entering the order anywhere loads all four slots from the
         # record of its first vertex (the kernel does that at the start of its share of every tile)
+        v_rest32 = v_rest.astype(np.float32).view(np.uint32)
         cache = [-1, -1, -1, -1]
         for c0 in range(0, Vp, CH):
             todo = [v for v in range(c0, min(c0 + CH, V))]
@@ -255,7 +256,7 @@ class BodyModel(_ops.RegisteredModule, nn.Module):
                 pack |= (v - c0) << 28
                 rec[pos, 0:4] = w.view(np.uint32)
                 rec[pos, 4] = pack
-                rec[pos, 5:8] = v_rest[v].astype(np.float32).view(np.uint32)
+                rec[pos, 5:8] = v_rest32[v]
                 proc[pos] = v
                 pos += 1
             for q in range(pos, c0 + CH):  # padding of the last chunk(s): zero weights, distinct local indices
