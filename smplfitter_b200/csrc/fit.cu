@@ -78,7 +78,7 @@ static FitWs carve(void* base, const smplfit_model_t* m, int64_t B, int has_join
   }
   w.RT12 = lite_available(m) ? c.take<float>((size_t)12 * J * Bp) : nullptr;
   w.gcfpart = lite_available(m) ? c.take<float>((size_t)gram_closed_blocks(m) * (NS * (NS + 1) / 2) * Bp) : nullptr;
-  w.Yd = lite_available(m) ? c.take<double>((size_t)3 * J * Bp) : nullptr;
+  w.Yd = lite_available(m) ? c.take<double>((size_t)(3 * J + NS + 3) * Bp) : nullptr;  // Y_k | sums of r | Sb
   w.pairfeat = (lite_available(m) && gram_pairs_scratch_floats(m, (int)Bp) > 0) ? c.take<float>(gram_pairs_scratch_floats(m, (int)Bp)) : nullptr;
   w.Gd = c.take<double>((size_t)shape_nacc(NS) * Bp);
   w.beta = c.take<float>((size_t)NS * Bp);

@@ -292,18 +292,33 @@ k_shape_lite(const LiteArgs a, const __grid_constant__ CUtensorMap map_t, const 
   }
 }
 
-// k_lite_reduce: one thread per (instance, joint): Y_k = sum over the (segment, slot) cells of joint k, in double.
+// k_lite_reduce: one thread per (instance, joint): Y_k = sum over the (segment, slot) cells of joint k, in double;
+// blockIdx.y >= J: row r of [r | Sb] summed over all segments (what the r / Sb entries of the normal equations need:
+// done here, next to chains of the same length, instead of as the longest chains of k_gram_entries).
 struct LiteReduceArgs {
   const float* partials;
   const int32_t* yj_start;
   const int32_t* yj_entry;
-  double* Yd;  // [3J][Bp]
-  int NL, NS, Bp;
+  double* Yd;  // [3J + NS + 3][Bp]
+  int NL, NS, Bp, J, n_segments;
 };
 static __global__ void __launch_bounds__(32) k_lite_reduce(const LiteReduceArgs a) {
   const int b = blockIdx.x * 32 + threadIdx.x;
   const int j = blockIdx.y;
   if (b >= a.Bp) return;
+  if (j >= a.J) {
+    const int row = j - a.J;
+    const float* pr = a.partials + (size_t)row * a.Bp + b;
+    const size_t qs = (size_t)a.NL * a.Bp;
+    double acc = 0.0;
+    int q = 0;
+#pragma unroll 8
+    for (; q + 4 <= a.n_segments; q += 4)  // four segment partials added in fp32, then one double accumulation
+      acc += (double)((pr[(size_t)q * qs] + pr[(size_t)(q + 1) * qs]) + (pr[(size_t)(q + 2) * qs] + pr[(size_t)(q + 3) * qs]));
+    for (; q < a.n_segments; ++q) acc += (double)pr[(size_t)q * qs];
+    a.Yd[(size_t)(3 * a.J + row) * a.Bp + b] = acc;
+    return;
+  }
   double y[3] = {0.0, 0.0, 0.0};
   auto cell = [&](int q) {
     const int e = a.yj_entry[q];

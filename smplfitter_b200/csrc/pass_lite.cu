@@ -167,15 +167,15 @@ static void lite_t(const LiteArgs& a, const smplfit_model_t* m, int groups, doub
   else lite_launch_t<NS, 8>(a, m->num_vertices, groups, st);
   LiteReduceArgs ra;
   ra.partials = a.partials; ra.yj_start = m->yj_start; ra.yj_entry = m->yj_entry; ra.Yd = Yd; ra.NL = lite_rows(NS);
-  ra.NS = NS; ra.Bp = a.Bp;
-  SF_LAUNCH(k_lite_reduce, dim3(groups, m->num_joints), 32, 0, st, ra);
+  ra.NS = NS; ra.Bp = a.Bp; ra.J = m->num_joints; ra.n_segments = m->n_segments;
+  SF_LAUNCH(k_lite_reduce, dim3(groups, m->num_joints + NS + 3), 32, 0, st, ra);
 }
 
 void launch_lite_reduce(const LiteArgs& a, const smplfit_model_t* m, int groups, double* Yd, cudaStream_t st) {
   LiteReduceArgs ra;
   ra.partials = a.partials; ra.yj_start = m->yj_start; ra.yj_entry = m->yj_entry; ra.Yd = Yd; ra.NL = lite_rows(m->fit_ns);
-  ra.NS = m->fit_ns; ra.Bp = a.Bp;
-  SF_LAUNCH(k_lite_reduce, dim3(groups, m->num_joints), 32, 0, st, ra);
+  ra.NS = m->fit_ns; ra.Bp = a.Bp; ra.J = m->num_joints; ra.n_segments = m->n_segments;
+  SF_LAUNCH(k_lite_reduce, dim3(groups, m->num_joints + m->fit_ns + 3), 32, 0, st, ra);
 }
 
 void launch_shape_lite(const LiteArgs& a, const smplfit_model_t* m, int groups, double* Yd, cudaStream_t st) {

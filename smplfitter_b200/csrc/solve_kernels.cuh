@@ -514,7 +514,7 @@ struct SolveArgs {
   int lite, lite_nl, n_gcf;
   const float* gcf_part;
   const double* G0;
-  const double* Yd;  // [3J][Bp]
+  const double* Yd;  // [3J + NS + 3][Bp]: Y_k, then the segment sums of r and Sb (k_lite_reduce)
   // feature rows of the fused statistics pass (fit_fused.cu): k_shape_out writes the solved unknowns into columns
   // [fq_p, fq_p + NS) as fp16 hi / lo; null = the caller builds the rows itself
   __half* fq_hi;
@@ -549,14 +549,8 @@ __device__ __forceinline__ void gram_entry(const SolveArgs& a, double* __restric
 #pragma unroll 4
       for (int q = 0; q < a.n_gcf; ++q) acc += (double)a.gcf_part[((size_t)q * NG + e) * Bp + b];
     } else {
-      const int row = (kind == 1) ? s : NS + c;
-      const float* pr = a.partials + (size_t)row * Bp + b;
-      const size_t qs = (size_t)a.lite_nl * Bp;
-      int q = 0;
-#pragma unroll 4
-      for (; q + 4 <= a.n_chunks; q += 4)  // four segment partials added in fp32, then one double accumulation
-        acc += (double)((pr[(size_t)q * qs] + pr[(size_t)(q + 1) * qs]) + (pr[(size_t)(q + 2) * qs] + pr[(size_t)(q + 3) * qs]));
-      for (; q < a.n_chunks; ++q) acc += (double)pr[(size_t)q * qs];
+      // r / Sb: the sum over the segment partials was taken by k_lite_reduce (rows 3J .. 3J + NS + 2 of Yd)
+      acc = a.Yd[(size_t)(3 * J + ((kind == 1) ? s : NS + c)) * Bp + b];
       if (kind == 1) {
 #pragma unroll 4
         for (int k = 0; k < J; ++k)
@@ -629,7 +623,11 @@ template <int NS>
 __global__ void __launch_bounds__(32) k_gram_entries(const SolveArgs a, double* __restrict__ Gd) {
   const int b = blockIdx.x * 32 + threadIdx.x;
   if (b >= a.Bp) return;
-  gram_entry<NS>(a, Gd, (int)blockIdx.y, b);
+  // the r and Sb entries sum one partial per segment (the longest chains of dependent round trips): dispatched first
+  constexpr int NG = NS * (NS + 1) / 2, NL = NS + 3;
+  const int y = (int)blockIdx.y;
+  const int e = (y < NL) ? NG + y : ((y < NL + NG) ? y - NL : y);
+  gram_entry<NS>(a, Gd, e, b);
 }
 
 // k_shape_solve<NS>: one thread per instance: centre with the covariance identity, regularise,
