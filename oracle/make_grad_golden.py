@@ -26,7 +26,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 from oracle import refload  # noqa: E402
-from oracle.make_golden import FIT_CASES  # noqa: E402
+from oracle.make_golden import FIT_CASES, KNOWN_POSE_CASES, KNOWN_SHAPE_CASES, aux_call_kwargs  # noqa: E402
 
 GOLD = os.path.join(ROOT, 'tests', 'golden')
 
@@ -48,6 +48,20 @@ GRAD_FIT_CASES = {
     'fit_tiny_share_beta_scale': ('target_vertices', 'target_joints'),
 }
 GRAD_FORWARD_CASES = {'fwd_tiny': 'smpl_tiny', 'fwd_smplx_tiny': 'smplx_tiny'}
+# fit_with_known_pose / fit_with_known_shape cases -> inputs differentiated (kshape_tiny_scale_fit is left out: the
+# reference's scale_fit branch mixes instances and coordinates, see make_golden.py)
+GRAD_KNOWN_POSE_CASES = {
+    'kpose_tiny': ('pose_rotvecs', 'target_vertices', 'target_joints'),
+    'kpose_tiny_weights': ('target_vertices', 'target_joints', 'vertex_weights', 'joint_weights'),
+    'kpose_tiny_kid_nojoints': ('pose_rotvecs', 'target_vertices'),
+    'kpose_tiny_scale_target': ('target_vertices', 'target_joints'),
+    'kpose_tiny_share_beta': ('target_vertices', 'target_joints'),
+}
+GRAD_KNOWN_SHAPE_CASES = {
+    'kshape_tiny': ('shape_betas', 'target_vertices', 'target_joints'),
+    'kshape_tiny_nojoints': ('shape_betas', 'target_vertices'),
+    'kshape_tiny_weights_init': ('target_vertices', 'target_joints', 'vertex_weights', 'joint_weights', 'initial_pose_rotvecs'),
+}
 FIT_OUTPUTS = ('shape_betas', 'trans', 'orientations', 'relative_orientations', 'pose_rotvecs', 'kid_factor', 'scale_corr')
 FWD_OUTPUTS = ('joints', 'orientations', 'vertices')
 
@@ -69,6 +83,23 @@ def fit_inputs(name, g):
     return tens, dict(fkw)
 
 
+def known_inputs(name, g):
+    """(method, fitter kwargs, model name, tensor kwargs as numpy, plain options) of a known-pose / known-shape case."""
+    if name in KNOWN_POSE_CASES:
+        mname, fitkw, _, ckw, flags = KNOWN_POSE_CASES[name]
+        kw = aux_call_kwargs(g, flags, ckw, lambda x: x)
+        kw['pose_rotvecs'] = g['in_pose']
+        method = 'fit_with_known_pose'
+    else:
+        mname, fitkw, _, ckw, flags = KNOWN_SHAPE_CASES[name]
+        kw = aux_call_kwargs(g, flags, dict(ckw, requested_keys=['pose_rotvecs', 'relative_orientations']), lambda x: x)
+        kw['shape_betas'] = g['in_betas']
+        method = 'fit_with_known_shape'
+    tens = {k: v for k, v in kw.items() if isinstance(v, np.ndarray)}
+    opts = {k: v for k, v in kw.items() if not isinstance(v, np.ndarray)}
+    return method, fitkw, mname, tens, opts
+
+
 def cotangents(shapes: dict, seed: int):
     rs = np.random.RandomState(seed)
     return {k: rs.randn(*s).astype(np.float32) for k, s in shapes.items()}
@@ -86,6 +117,21 @@ def main():
         tt = {k: torch.from_numpy(v).clone().requires_grad_(k in wrt) for k, v in tens.items()}
         out = fitter.fit(**tt, **opts, requested_keys=['pose_rotvecs', 'shape_betas', 'relative_orientations'])
         cot = cotangents({k: tuple(out[k].shape) for k in FIT_OUTPUTS if k in out}, seed=900 + idx)
+        sum((out[k] * torch.from_numpy(cot[k])).sum() for k in cot).backward()
+        rec = {('cot_' + k): v for k, v in cot.items()}
+        for k in wrt:
+            gr = tt[k].grad.numpy()
+            assert np.isfinite(gr).all() and np.abs(gr).max() > 0, (name, k)
+            rec['ref_grad_' + k] = gr
+        np.savez_compressed(os.path.join(GOLD, 'grad_' + name + '.npz'), **rec)
+        print(f'[grad] {name}: ' + ' '.join(f"{k}={np.abs(rec['ref_grad_' + k]).max():.2e}" for k in wrt))
+    for idx, (name, wrt) in enumerate({**GRAD_KNOWN_POSE_CASES, **GRAD_KNOWN_SHAPE_CASES}.items()):
+        g = dict(np.load(os.path.join(GOLD, name + '.npz')))
+        method, fitkw, mname, tens, opts = known_inputs(name, g)
+        fitter = rpt.BodyFitter(rpt.BodyModel(mname, 'neutral'), **fitkw)
+        tt = {k: torch.from_numpy(v).clone().requires_grad_(k in wrt) for k, v in tens.items()}
+        out = getattr(fitter, method)(**tt, **opts)
+        cot = cotangents({k: tuple(v.shape) for k, v in sorted(out.items())}, seed=970 + idx)
         sum((out[k] * torch.from_numpy(cot[k])).sum() for k in cot).backward()
         rec = {('cot_' + k): v for k, v in cot.items()}
         for k in wrt:

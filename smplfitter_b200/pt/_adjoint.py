@@ -487,6 +487,91 @@ def fit(bm, n_betas: int, target_vertices, target_joints=None, vertex_weights=No
     return betas, trans, glob, rel, rotvecs, kid, sc
 
 
+def _centre(t, tj):
+    if tj is None:
+        mean = t.mean(1)
+        return t - mean[:, None], None, mean
+    mean = torch.cat([t, tj], 1).mean(1)
+    return t - mean[:, None], tj - mean[:, None], mean
+
+
+def fit_with_known_pose(bm, n_betas: int, enable_kid: bool, pose_rotvecs, target_vertices, target_joints=None,
+                        vertex_weights=None, joint_weights=None, beta_regularizer_reference=None,
+                        kid_regularizer_reference=None, beta_regularizer: float = 1.0, beta_regularizer2: float = 0.0,
+                        scale_regularizer: float = 0.0, kid_regularizer: Optional[float] = None, share_beta: bool = False,
+                        scale_target: bool = False, scale_fit: bool = False):
+    """Differentiable evaluation of ``BodyFitter.fit_with_known_pose`` (pt/bodyfitter.py:552-653): one shape stage with
+    the orientations of the given pose.  Returns the result dict of the method."""
+    c = constants(bm, target_vertices.dtype, target_vertices.device)
+    t, tj, mean = _centre(target_vertices, target_joints)
+    B = t.shape[0]
+    glob = lbs(c, pose_rotvecs=pose_rotvecs, return_vertices=False)[1].expand(B, -1, -1, -1)
+    res = _fit_shape(c, n_betas, glob, t, tj, vertex_weights, joint_weights, beta_regularizer, beta_regularizer2,
+                     beta_regularizer_reference, enable_kid, kid_regularizer,
+                     kid_regularizer_reference if enable_kid else None, 1 if scale_target else (2 if scale_fit else 0),
+                     scale_regularizer, share_beta)
+    out = {'shape_betas': res['shape_betas'], 'trans': res['trans'] + mean, 'relative_orientations': res['relative_orientations']}
+    for k in ('kid_factor', 'scale_corr'):
+        if k in res:
+            out[k] = res[k]
+    return out
+
+
+def _fit_scale_and_translation(t, a, tj, aj, vw, jw, scale: bool):
+    """pt/bodyfitter.py:1628-1681: weighted centroids (and the ratio of the weighted spreads)."""
+    if tj is None or aj is None:
+        tb, ab = t, a
+        w = vw if vw is not None else torch.ones(t.shape[:2], dtype=t.dtype, device=t.device)
+    else:
+        tb, ab = torch.cat([t, tj], 1), torch.cat([a, aj], 1)
+        w = torch.cat([vw, jw], 1) if (vw is not None and jw is not None) else torch.ones(tb.shape[:2], dtype=t.dtype,
+                                                                                         device=t.device)
+    w = (w / w.sum(1, keepdim=True))[..., None]
+    mt, ma = (tb * w).sum(1), (ab * w).sum(1)
+    if not scale:
+        return None, mt - ma
+    sc = ((((tb - mt[:, None]) ** 2) * w).sum((1, 2)) / (((ab - ma[:, None]) ** 2) * w).sum((1, 2))).sqrt()
+    return sc, mt - sc[:, None] * ma
+
+
+def fit_with_known_shape(bm, n_betas: int, shape_betas, target_vertices, target_joints=None, vertex_weights=None,
+                         joint_weights=None, kid_factor=None, initial_pose_rotvecs=None, num_iter: int = 1,
+                         final_adjust_rots: bool = True, scale_fit: bool = False, want_pose_rotvecs: bool = True,
+                         want_rel_orient: bool = False):
+    """Differentiable evaluation of ``BodyFitter.fit_with_known_shape`` (pt/bodyfitter.py:656-838): rotation fits
+    against the forward pass of the known betas, then scale / translation, then the final adjustment."""
+    c = constants(bm, target_vertices.dtype, target_vertices.device)
+    t, tj, mean = _centre(target_vertices, target_joints)
+    vw, jw = vertex_weights, joint_weights
+    B = t.shape[0]
+    betas = shape_betas.expand(B, -1)
+    kid = None if kid_factor is None else kid_factor.reshape(-1).expand(B)
+    ij, io, iv = lbs(c, pose_rotvecs=initial_pose_rotvecs, shape_betas=betas, kid_factor=kid)
+    glob = _fit_global_rotations(c, t, tj, iv, ij, vw, jw) @ io
+    for _ in range(num_iter - 1):
+        rj, _, rv = lbs(c, glob_rotmats=glob, shape_betas=betas, kid_factor=kid)
+        glob = _fit_global_rotations(c, t, tj, rv, rj if tj is not None else None, vw, jw) @ glob
+    rj, _, rv = lbs(c, glob_rotmats=glob, shape_betas=betas, kid_factor=kid)
+    sc, tr = _fit_scale_and_translation(t, rv, tj, rj, vw, jw, scale_fit)
+    if final_adjust_rots:
+        nb = min(betas.shape[1], c.S)
+        if scale_fit:
+            s3 = sc[:, None, None]
+            glob = _fit_global_rotations_dependent(c, nb, t, tj, s3 * rv + tr[:, None], s3 * rj + tr[:, None], vw, jw, glob,
+                                                   betas, tr, kid, sc)
+        else:
+            glob = _fit_global_rotations_dependent(c, nb, t, tj, rv + tr[:, None], rj + tr[:, None], vw, jw, glob, betas,
+                                                   tr, kid)
+    out = {'trans': tr + mean, 'orientations': glob}
+    if scale_fit:
+        out['scale_corr'] = sc
+    if want_pose_rotvecs or want_rel_orient:
+        out['relative_orientations'] = _relative(c, glob)
+        if want_pose_rotvecs:
+            out['pose_rotvecs'] = mat2rotvec(out['relative_orientations']).reshape(B, -1)
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # backward of the custom ops: slice the batch, re-evaluate with grad, pull the cotangents back
 # ----------------------------------------------------------------------------------------------------------------------
@@ -579,3 +664,37 @@ def fit_backward(fitter, tensors, needs, opts: dict, grads_out):
     dev = bm.v_template.device
     slices = [(0, B)] if opts.get('share_beta') else _slices(B, per, device=dev)
     return _pullback(B, tensors, needs, run, grads_out, slices, dev)
+
+
+class _Recompute(torch.autograd.Function):
+    """Values from ``run_cuda`` (the CUDA entry point, no grad), gradient by re-evaluating ``run_torch`` on slices of
+    the batch: the wrapper of the methods that do not go through a custom op (``fit_with_known_pose`` /
+    ``fit_with_known_shape``).  Both callables take the tensor arguments positionally and return the result dict."""
+
+    @staticmethod
+    def forward(ctx, run_cuda, run_torch, keys, B, device, per, coupled, *tensors):
+        with torch.no_grad():
+            res = run_cuda(*[None if x is None else x.detach() for x in tensors])
+        ctx.run_torch, ctx.keys, ctx.B, ctx.device, ctx.per, ctx.coupled = run_torch, keys, B, device, per, coupled
+        ctx.needs = [x is not None and x.requires_grad for x in tensors]
+        ctx.save_for_backward(*tensors)
+        return tuple(res[k] for k in keys)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        tensors = list(ctx.saved_tensors)
+        keys = ctx.keys
+
+        def run(*xs):
+            res = ctx.run_torch(*xs)
+            return [res[k] for k in keys]
+
+        slices = [(0, ctx.B)] if ctx.coupled else _slices(ctx.B, ctx.per, device=ctx.device)
+        g = _pullback(ctx.B, tensors, ctx.needs, run, list(grads), slices, ctx.device)
+        return (None,) * 7 + tuple(g)
+
+
+def differentiable_call(run_cuda, run_torch, keys, B: int, device, per_instance_bytes: float, coupled: bool, tensors):
+    """-> result dict whose tensors carry the gradient of ``run_torch`` and the values of ``run_cuda``."""
+    outs = _Recompute.apply(run_cuda, run_torch, tuple(keys), B, device, per_instance_bytes, coupled, *tensors)
+    return dict(zip(keys, outs))

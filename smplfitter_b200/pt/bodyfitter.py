@@ -565,9 +565,31 @@ class BodyFitter(_ops.RegisteredModule, nn.Module):
         kid_regularizer_reference: Optional[torch.Tensor] = None,
         requested_keys: Optional[list] = None,
     ) -> dict[str, torch.Tensor]:
-        """Shape and translation for a known pose (pt/bodyfitter.py:552-653)."""
+        """Shape and translation for a known pose (pt/bodyfitter.py:552-653).  Differentiable like the reference's:
+        with a ``requires_grad`` input the values still come from the CUDA path and the gradient from ``_adjoint``."""
         if scale_target and scale_fit:
             raise ValueError('Only one of estim_scale_target and estim_scale_fit can be True')
+        tensors = [pose_rotvecs, target_vertices, target_joints, vertex_weights, joint_weights,
+                   beta_regularizer_reference, kid_regularizer_reference]
+        if torch.is_grad_enabled() and any(isinstance(x, torch.Tensor) and x.requires_grad for x in tensors):
+            from . import _adjoint
+
+            opts = dict(beta_regularizer=beta_regularizer, beta_regularizer2=beta_regularizer2,
+                        scale_regularizer=scale_regularizer, kid_regularizer=kid_regularizer, share_beta=share_beta,
+                        scale_target=scale_target, scale_fit=scale_fit)
+            names = ['pose_rotvecs', 'target_vertices', 'target_joints', 'vertex_weights', 'joint_weights',
+                     'beta_regularizer_reference', 'kid_regularizer_reference']
+            keys = ['shape_betas', 'trans', 'relative_orientations'] + (['kid_factor'] if self.enable_kid else []) + (
+                ['scale_corr'] if (scale_target or scale_fit) else [])
+            tensors = [x if (x is None or isinstance(x, torch.Tensor)) else torch.as_tensor(x) for x in tensors]
+            if tensors[6] is not None:
+                tensors[6] = tensors[6].reshape(-1)
+            bm = self.body_model
+            return _adjoint.differentiable_call(
+                lambda *xs: self.fit_with_known_pose(**dict(zip(names, xs)), **opts),
+                lambda *xs: _adjoint.fit_with_known_pose(bm, self.n_betas, self.enable_kid, *xs, **opts),
+                keys, target_vertices.shape[0], bm.v_template.device,
+                4.0 * bm.num_vertices * 3 * (self.n_betas + 14) * 2.5, bool(share_beta), tensors)
         scale_mode = 1 if scale_target else (2 if scale_fit else 0)
         bm = self.body_model
         dev = bm.v_template.device
@@ -639,9 +661,32 @@ class BodyFitter(_ops.RegisteredModule, nn.Module):
         scale_fit: bool = False,
         requested_keys: Optional[list] = None,
     ) -> dict[str, torch.Tensor]:
-        """Pose and translation for known betas (pt/bodyfitter.py:656-838)."""
+        """Pose and translation for known betas (pt/bodyfitter.py:656-838).  Differentiable like the reference's (values
+        from the CUDA path, gradient from ``_adjoint``)."""
         if requested_keys is None:
             requested_keys = ['pose_rotvecs']
+        tensors = [shape_betas, target_vertices, target_joints, vertex_weights, joint_weights, kid_factor,
+                   initial_pose_rotvecs]
+        if torch.is_grad_enabled() and any(isinstance(x, torch.Tensor) and x.requires_grad for x in tensors):
+            from . import _adjoint
+
+            opts = dict(num_iter=num_iter, final_adjust_rots=final_adjust_rots, scale_fit=scale_fit)
+            names = ['shape_betas', 'target_vertices', 'target_joints', 'vertex_weights', 'joint_weights', 'kid_factor',
+                     'initial_pose_rotvecs']
+            want_rv = 'pose_rotvecs' in requested_keys
+            want_rel = want_rv or 'relative_orientations' in requested_keys
+            keys = ['trans', 'orientations'] + (['scale_corr'] if scale_fit else []) + (
+                ['relative_orientations'] if want_rel else []) + (['pose_rotvecs'] if want_rv else [])
+            tensors = [x if (x is None or isinstance(x, torch.Tensor)) else torch.as_tensor(x) for x in tensors]
+            if tensors[5] is not None:
+                tensors[5] = tensors[5].reshape(-1)
+            bm = self.body_model
+            return _adjoint.differentiable_call(
+                lambda *xs: self.fit_with_known_shape(**dict(zip(names, xs)), **opts, requested_keys=requested_keys),
+                lambda *xs: _adjoint.fit_with_known_shape(bm, self.n_betas, *xs, **opts, want_pose_rotvecs=want_rv,
+                                                          want_rel_orient=want_rel),
+                keys, target_vertices.shape[0], bm.v_template.device,
+                4.0 * bm.num_vertices * 3 * 30 * max(1, num_iter), False, tensors)
         bm = self.body_model
         dev = bm.v_template.device
         _native.require_cuda(bm.v_template, 'the body model')

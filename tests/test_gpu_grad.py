@@ -209,3 +209,28 @@ def test_share_beta_backward_is_one_slice(monkeypatch):
     assert (out['shape_betas'] - out['shape_betas'][:1]).abs().max() == 0
     _loss(out).backward()
     assert torch.isfinite(a.grad).all() and a.grad.abs().max() > 0
+
+
+# ---- fit_with_known_pose / fit_with_known_shape: values from their CUDA entry points, gradient through the wrapper ----
+from oracle.make_grad_golden import GRAD_KNOWN_POSE_CASES, GRAD_KNOWN_SHAPE_CASES, known_inputs  # noqa: E402
+
+
+@pytest.mark.parametrize('name', sorted({**GRAD_KNOWN_POSE_CASES, **GRAD_KNOWN_SHAPE_CASES}))
+def test_known_pose_shape_gradients_match_reference_autograd(name):
+    g, gg = gc.load(name), gc.load('grad_' + name)
+    wrt = {**GRAD_KNOWN_POSE_CASES, **GRAD_KNOWN_SHAPE_CASES}[name]
+    method, fitkw, mname, tens, opts = known_inputs(name, g)
+    fitter = pt.BodyFitter(pt.BodyModel(mname).cuda(), **fitkw).cuda()
+    tt = {k: torch.from_numpy(v).cuda().requires_grad_(k in wrt) for k, v in tens.items()}
+    out = getattr(fitter, method)(**tt, **opts)
+    with torch.no_grad():
+        plain = getattr(fitter, method)(**{k: v.detach() for k, v in tt.items()}, **opts)
+    assert set(out) == set(plain)
+    for k in out:  # the values are the CUDA path's
+        assert torch.equal(out[k], plain[k]) and out[k].requires_grad, k
+    sum((out[k[4:]] * torch.from_numpy(v).cuda()).sum() for k, v in gg.items() if k.startswith('cot_')).backward()
+    for k in wrt:
+        ref = gg['ref_grad_' + k]
+        gr = tt[k].grad.cpu().numpy()
+        err = np.abs(gr - ref).max() / np.abs(ref).max()
+        assert np.isfinite(gr).all() and err < 1e-2, (k, err)
