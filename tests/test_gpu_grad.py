@@ -234,3 +234,25 @@ def test_known_pose_shape_gradients_match_reference_autograd(name):
         gr = tt[k].grad.cpu().numpy()
         err = np.abs(gr - ref).max() / np.abs(ref).max()
         assert np.isfinite(gr).all() and err < 1e-2, (k, err)
+
+
+def test_scripted_fitter_and_foreign_inputs_carry_gradients():
+    """The backward is registered on the custom op, so it is there for the TorchScript-compiled fitter too; inputs in
+    float64 or living on the CPU get their gradient back in their own dtype / on their own device."""
+    bm, tv, tj = _targets('smpl_tiny', 3, seed=2)
+    fitter = pt.BodyFitter(bm).cuda()
+    scripted = torch.jit.script(fitter)
+    keys = ['pose_rotvecs', 'shape_betas', 'trans']
+    a = tv.clone().requires_grad_(True)
+    _loss(fitter.fit(a, tj, num_iter=2, requested_keys=keys)).backward()
+    b = tv.clone().requires_grad_(True)
+    _loss(scripted.fit(b, tj, num_iter=2, requested_keys=keys)).backward()
+    # (the re-evaluation sums with atomics on the GPU: equal up to the summation order)
+    assert (a.grad - b.grad).abs().max() < 1e-4 * a.grad.abs().max()
+    c = tv.double().cpu().requires_grad_(True)
+    _loss(fitter.fit(c, tj, num_iter=2, requested_keys=keys)).backward()
+    assert c.grad.dtype == torch.float64 and not c.grad.is_cuda
+    assert (c.grad.float().cuda() - a.grad).abs().max() < 1e-4 * a.grad.abs().max()
+    with torch.no_grad():
+        out = fitter.fit(a, tj, num_iter=2, requested_keys=keys)
+    assert not out['trans'].requires_grad
