@@ -248,7 +248,7 @@ def lbs(c: Constants, pose_rotvecs=None, shape_betas=None, trans=None, kid_facto
         v = v + c.kid_shapedir[None] * kid_factor.reshape(-1)[:, None, None]
     transl = pos - _mv3(glob, j)
     blend = torch.einsum('vj,bjk->bvk', c.weights, torch.cat([glob.reshape(B, c.J, 9), transl], 2))
-    verts = torch.einsum('bvCc,bvc->bvC', blend[..., :9].reshape(B, c.V, 3, 3), v) + blend[..., 9:]
+    verts = _mv3(blend[..., :9].reshape(B, c.V, 3, 3), v) + blend[..., 9:]  # (not einsum: B V batched 3x3 GEMVs)
     return out + [verts + tr[:, None]]
 
 
@@ -329,7 +329,7 @@ def _fit_shape(c: Constants, S: int, glob, t, tj, vw, jw, reg: float, reg2: floa
     T = P - _mm3(glob, Jt[None])
     v_posed = c.v_template[None] + torch.einsum('vcp,bp->bvc', c.posedirs, rel[:, 1:].reshape(B, (J - 1) * 9))
     blend = torch.einsum('vj,bjk->bvk', c.weights, glob.reshape(B, J, 9)).reshape(B, c.V, 3, 3)
-    ext = torch.cat([torch.einsum('bvCc,bvc->bvC', blend, v_posed)[..., None],
+    ext = torch.cat([_mv3(blend, v_posed)[..., None],
                      torch.einsum('bvCc,vcs->bvCs', blend, sd)], 3)
     ext = ext + torch.einsum('vj,bjCs->bvCs', c.weights, T)
     if tj is None:
