@@ -5,7 +5,6 @@ sparse topology transfer, fit of the output model -- all three steps in the CUDA
 
 from __future__ import annotations
 
-import ctypes as C
 import os
 from typing import Optional
 

@@ -13,7 +13,7 @@ import torch
 from tests import golden_cases as gc
 import smplfitter_b200.pt as pt
 from oracle.make_golden import FIT_CASES
-from oracle.make_grad_golden import FIT_OUTPUTS, FWD_OUTPUTS, GRAD_FIT_CASES, GRAD_FORWARD_CASES, fit_inputs
+from oracle.make_grad_golden import FWD_OUTPUTS, GRAD_FIT_CASES, GRAD_FORWARD_CASES, fit_inputs
 from smplfitter_b200.pt import _adjoint
 
 pytestmark = pytest.mark.gpu
