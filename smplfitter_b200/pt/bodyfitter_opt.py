@@ -15,8 +15,8 @@ from typing import Dict, Optional
 import torch
 import torch.nn as nn
 
-from . import _adjoint
 from .bodyfitter import BodyFitter
+from .rotation import mat2rotvec
 
 
 def rot6d_to_rotmat(x: torch.Tensor) -> torch.Tensor:
@@ -97,7 +97,7 @@ class BodyFitterOpt(nn.Module):
             glob = rot6d_to_rotmat(rot6d)
             par = bm.kintree_parents_tensor[1:].to(dev)
             rel = torch.cat([glob[:, :1], glob[:, par].transpose(-1, -2) @ glob[:, 1:]], dim=1)
-            result = {'pose_rotvecs': _adjoint.mat2rotvec(rel).reshape(glob.shape[0], -1), 'shape_betas': betas.detach(),
+            result = {'pose_rotvecs': mat2rotvec(rel).reshape(glob.shape[0], -1), 'shape_betas': betas.detach(),
                       'trans': trans.detach()}
         if kid is not None:
             result['kid_factor'] = kid.detach()

@@ -256,3 +256,21 @@ def test_scripted_fitter_and_foreign_inputs_carry_gradients():
     with torch.no_grad():
         out = fitter.fit(a, tj, num_iter=2, requested_keys=keys)
     assert not out['trans'].requires_grad
+
+
+def test_inference_never_evaluates_the_adjoint(monkeypatch):
+    """Without a requires_grad input every entry point is the CUDA path alone, in grad mode too."""
+    def boom(*a, **k):
+        raise AssertionError('pt/_adjoint.py evaluated on the inference path')
+
+    for name in ('fit', 'lbs', 'fit_with_known_pose', 'fit_with_known_shape', '_pullback', 'differentiable_call'):
+        monkeypatch.setattr(_adjoint, name, boom)
+    bm, tv, tj = _targets('smpl_tiny', 3, seed=6)
+    fitter = pt.BodyFitter(bm).cuda()
+    res = fitter.fit(tv, tj, num_iter=2, requested_keys=['pose_rotvecs', 'shape_betas', 'trans'])
+    assert not res['trans'].requires_grad
+    out = bm(res['pose_rotvecs'], res['shape_betas'], res['trans'])
+    assert not out['vertices'].requires_grad
+    fitter.fit_with_known_pose(res['pose_rotvecs'], tv, tj)
+    fitter.fit_with_known_shape(res['shape_betas'], tv, tj, num_iter=2)
+    pt.BodyConverter(bm, bm).cuda().convert(res['pose_rotvecs'], res['shape_betas'], res['trans'])

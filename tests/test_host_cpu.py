@@ -290,3 +290,29 @@ def test_copies_get_their_own_handle():
     assert _ops._get(f2._handle) is f2 and _ops._get(f2.body_model._handle) is f2.body_model
     bm3 = pickle.loads(pickle.dumps(bm))
     assert bm3._handle != bm._handle and _ops._get(bm3._handle) is bm3
+
+
+def test_gradient_evaluation_is_reachable_only_from_backward_paths():
+    """pt/_adjoint.py holds a differentiable torch evaluation of the fit.  It must never serve values: it is imported
+    only inside the registered backward functions of the custom ops and inside the ``requires_grad`` branches of the
+    known-pose / known-shape wrappers (whose values still come from their CUDA entry points)."""
+    import ast
+    import smplfitter_b200.pt as ptpkg
+
+    pkg = os.path.dirname(ptpkg.__file__)
+    allowed = {'_ops.py': {'_forward_backward', '_fit_backward'},
+               'bodyfitter.py': {'fit_with_known_pose', 'fit_with_known_shape'}}
+    for name in sorted(os.listdir(pkg)):
+        if not name.endswith('.py') or name == '_adjoint.py':
+            continue
+        tree = ast.parse(open(os.path.join(pkg, name)).read())
+        for fn in ast.walk(tree):
+            if not isinstance(fn, (ast.FunctionDef, ast.Module)):
+                continue
+            for node in ast.iter_child_nodes(fn) if isinstance(fn, ast.Module) else ast.walk(fn):
+                if isinstance(node, ast.ImportFrom) and any(a.name == '_adjoint' for a in node.names):
+                    where = getattr(fn, 'name', '<module>')
+                    assert where in allowed.get(name, set()), f'{name}: _adjoint imported in {where}'
+    src = open(os.path.join(pkg, 'bodyfitter.py')).read()
+    for chunk in src.split('from . import _adjoint')[:-1]:
+        assert 'requires_grad' in chunk[-400:], 'the known-* wrappers may reach _adjoint only when a gradient is requested'
