@@ -183,3 +183,16 @@ def convert_vertices_op(handle: int, inp_vertices: torch.Tensor) -> torch.Tensor
 def _(handle, inp_vertices):
     c = _get(handle)
     return inp_vertices.new_empty((inp_vertices.shape[0], c.body_model_out.num_vertices, 3), dtype=torch.float32)
+
+
+def _convert_setup(ctx, inputs, output):
+    ctx.handle = inputs[0]
+
+
+def _convert_backward(ctx, grad):
+    """The topology transfer is linear (out = M x per coordinate): the pull-back is M^T, applied as a scatter-add over
+    the non-zeros (pt/bodyconverter.py:129-149 is differentiable the same way through its sparse matmul)."""
+    return None, _get(ctx.handle)._convert_vertices_transpose(grad)
+
+
+convert_vertices_op.register_autograd(_convert_backward, setup_context=_convert_setup)

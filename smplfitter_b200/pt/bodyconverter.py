@@ -111,6 +111,21 @@ class BodyConverter(_ops.RegisteredModule, nn.Module):
         return torch.ops.smplfit_b200.convert_vertices(self._handle, inp_vertices)
 
     @torch.jit.unused
+    def _convert_vertices_transpose(self, grad_out: torch.Tensor) -> torch.Tensor:
+        """(B, V_out, 3) cotangent -> (B, V_in, 3): M^T applied non-zero by non-zero (backward of ``convert_vertices``)."""
+        dev = grad_out.device
+        indptr = self._csr_indptr.to(dev).long()
+        cols, data = self._csr_indices.to(dev).long(), self._csr_data.to(dev)
+        rows = torch.repeat_interleave(torch.arange(indptr.numel() - 1, device=dev), indptr[1:] - indptr[:-1])
+        B = grad_out.shape[0]
+        out = torch.zeros((B, self.body_model_in.num_vertices, 3), device=dev, dtype=grad_out.dtype)
+        step = max(1, int(2 ** 28 // max(1, 12 * rows.numel())))  # <= 256 MB of gathered non-zeros at a time
+        for a in range(0, B, step):
+            g = grad_out[a:a + step]
+            out[a:a + step].index_add_(1, cols, g[:, rows] * data.to(g.dtype)[None, :, None])
+        return out
+
+    @torch.jit.unused
     def _convert_vertices_impl(self, inp_vertices: torch.Tensor) -> torch.Tensor:
         _native.require_cuda(self._csr_data, 'the converter')
         dev = self._csr_data.device

@@ -273,3 +273,19 @@ def test_differentiable_call_wrapper():
     (o2['pose_rotvecs'].pow(2).sum() + o2['trans'].sum()).backward()
     for a, b in zip(tt, t2):
         assert (a.grad - b.grad).abs().max() < 1e-3 * b.grad.abs().max()
+
+
+def test_convert_vertices_backward_is_the_transpose(monkeypatch):
+    """The registered backward of the topology transfer against a dense M^T (CPU: the op's CUDA body replaced by a
+    dense product)."""
+    from oracle.make_golden import synthetic_converter_csr
+
+    bm_in, bm_out = pt.BodyModel('smpl_tiny'), pt.BodyModel('smplx_tiny')
+    csr = synthetic_converter_csr(bm_in.num_vertices, bm_out.num_vertices)
+    conv = pt.BodyConverter(bm_in, bm_out, vertex_converter_csr=csr)
+    M = torch.from_numpy(csr.toarray().astype(np.float32))
+    monkeypatch.setattr(conv, '_convert_vertices_impl', lambda x: torch.einsum('oi,bic->boc', M, x))
+    x = torch.randn(5, bm_in.num_vertices, 3, requires_grad=True)
+    cot = torch.randn(5, bm_out.num_vertices, 3)
+    (conv.convert_vertices(x) * cot).sum().backward()
+    assert (x.grad - torch.einsum('oi,boc->bic', M, cot)).abs().max() < 1e-5

@@ -274,3 +274,31 @@ def test_inference_never_evaluates_the_adjoint(monkeypatch):
     fitter.fit_with_known_pose(res['pose_rotvecs'], tv, tj)
     fitter.fit_with_known_shape(res['shape_betas'], tv, tj, num_iter=2)
     pt.BodyConverter(bm, bm).cuda().convert(res['pose_rotvecs'], res['shape_betas'], res['trans'])
+
+
+def test_converter_is_differentiable_end_to_end():
+    """BodyConverter.convert = forward op -> topology transfer op -> fit op: a directional finite difference of the
+    converted parameters with respect to the input pose / betas against the chained backward."""
+    from oracle.make_golden import synthetic_converter_csr
+
+    bm_in, bm_out = pt.BodyModel('smpl_tiny').cuda(), pt.BodyModel('smplx_tiny').cuda()
+    conv = pt.BodyConverter(bm_in, bm_out, vertex_converter_csr=synthetic_converter_csr(
+        bm_in.num_vertices, bm_out.num_vertices)).cuda()
+    torch.manual_seed(8)
+    pose, betas, trans = (torch.randn(2, 72) * 0.2).cuda(), (torch.randn(2, 10) * 0.5).cuda(), torch.randn(2, 3).cuda()
+    cot = {k: torch.randn(s).cuda() for k, s in (('pose_rotvecs', (2, 165)), ('shape_betas', (2, 16)), ('trans', (2, 3)))}
+
+    def loss(p, b):
+        out = conv.convert(p, b, trans, num_iter=2)
+        return sum((out[k] * cot[k]).sum() for k in cot)
+
+    p, b = pose.clone().requires_grad_(True), betas.clone().requires_grad_(True)
+    loss(p, b).backward()
+    assert torch.isfinite(p.grad).all() and torch.isfinite(b.grad).all() and p.grad.abs().max() > 0
+    dp, db = torch.randn_like(pose), torch.randn_like(betas)
+    dp, db = dp / dp.norm(), db / db.norm()
+    eps = 1e-2
+    with torch.no_grad():
+        fd = (loss(pose + eps * dp, betas + eps * db) - loss(pose - eps * dp, betas - eps * db)).item() / (2 * eps)
+    an = ((p.grad * dp).sum() + (b.grad * db).sum()).item()
+    assert abs(an - fd) < 5e-2 * max(abs(an), abs(fd), 1e-3), (an, fd)
