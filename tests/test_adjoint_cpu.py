@@ -289,3 +289,31 @@ def test_convert_vertices_backward_is_the_transpose(monkeypatch):
     cot = torch.randn(5, bm_out.num_vertices, 3)
     (conv.convert_vertices(x) * cot).sum().backward()
     assert (x.grad - torch.einsum('oi,boc->bic', M, cot)).abs().max() < 1e-5
+
+
+def test_converter_chain_gradient_in_float64():
+    """forward -> transfer matrix -> converter-style fit (kid unknown pinned by a 1e9 regulariser, no joints), the
+    chain BodyConverter.convert differentiates on the GPU: autograd against a central difference at eps = 1e-6."""
+    from oracle.make_golden import synthetic_converter_csr
+
+    bm_in, bm_out = pt.BodyModel('smpl_tiny'), pt.BodyModel('smplx_tiny')
+    M = torch.from_numpy(synthetic_converter_csr(bm_in.num_vertices, bm_out.num_vertices).toarray()).double()
+    ci = _adjoint.constants(bm_in, torch.float64, torch.device('cpu'))
+    torch.manual_seed(8)
+    pose, betas, trans = torch.randn(2, 72).double() * 0.2, torch.randn(2, 10).double() * 0.5, torch.randn(2, 3).double()
+    cot = [torch.randn(2, 16).double(), torch.randn(2, 3).double(), torch.randn(2, 165).double()]
+
+    def loss(p, b):
+        verts = torch.einsum('oi,bic->boc', M, _adjoint.lbs(ci, p, b, trans)[2])
+        o = _adjoint.fit(bm_out, 16, verts, num_iter=2, beta_regularizer=0.0, final_adjust_rots=False, enable_kid=True,
+                         kid_regularizer=1e9)
+        return (o[0] * cot[0]).sum() + (o[1] * cot[1]).sum() + (o[4] * cot[2]).sum()
+
+    p, b = pose.clone().requires_grad_(True), betas.clone().requires_grad_(True)
+    loss(p, b).backward()
+    dp, db = torch.randn_like(pose), torch.randn_like(betas)
+    dp, db = dp / dp.norm(), db / db.norm()
+    with torch.no_grad():
+        fd = (loss(pose + 1e-6 * dp, betas + 1e-6 * db) - loss(pose - 1e-6 * dp, betas - 1e-6 * db)).item() / 2e-6
+    an = ((p.grad * dp).sum() + (b.grad * db).sum()).item()
+    assert abs(an - fd) < 1e-5 * max(1.0, abs(fd)), (an, fd)
