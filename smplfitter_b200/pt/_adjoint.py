@@ -1,13 +1,16 @@
-"""Gradient path of ``BodyModel.forward`` and ``BodyFitter.fit`` (reference feature: README.md:13,
-tests/pt/test_fitter_grad.py:31-99 -- backprop through the fit must give finite gradients that agree with finite
-differences).
+"""Gradient path of ``BodyModel.forward``, ``BodyFitter.fit`` / ``fit_with_known_pose`` / ``fit_with_known_shape``
+(reference feature: README.md:13, tests/pt/test_fitter_grad.py:31-99 -- backprop through the fit must give finite
+gradients that agree with finite differences).
 
 The VALUES always come from the CUDA kernels.  Only when an input of the ``smplfit_b200::forward`` / ``::fit`` custom
-op requires grad does autograd call the backward registered here, which re-evaluates the same closed-form algorithm
-with differentiable torch operations on slices of the batch (instances are independent) and pulls the incoming output
+op (or of a known-pose / known-shape call, wrapped by ``differentiable_call``) requires grad does autograd call the
+backward registered here, which re-evaluates the same closed-form algorithm with differentiable torch operations on
+slices of the batch (instances are independent; ``share_beta`` couples them: one slice) and pulls the incoming output
 gradients back through that evaluation.  It is a recompute-in-backward adjoint: nothing here runs on the inference
-path, nothing is kept alive between forward and backward except the inputs, and the memory of the intermediate
-Jacobians is bounded by the slice size instead of the batch size.
+path (``tests/test_host_cpu.py::test_gradient_evaluation_is_reachable_only_from_backward_paths``,
+``tests/test_gpu_grad.py::test_inference_never_evaluates_the_adjoint``), nothing is kept alive between forward and
+backward except the inputs, and the memory of the intermediate Jacobians is bounded by the slice size instead of
+the batch size.
 
 Two pieces are hand-derived instead of left to torch's autograd because the stock derivatives are singular exactly
 where the fit operates:
@@ -17,10 +20,15 @@ where the fit operates:
   s_i + s_j, see ``_ProjSO3.backward``.
 * ``rotvec2mat`` / ``mat2rotvec`` use series forms near the identity so that the derivative exists at zero rotation.
 
-What is differentiable: ``forward`` with respect to every tensor input; ``fit`` with respect to the targets, the
-weights and the initial guesses (joints or not, weights, ``num_iter``,
-``final_adjust_rots``, the regularisers, initial pose / shape / kid factor, ``enable_kid``, ``scale_target`` /
-``scale_fit``, ``share_beta`` -- every option of ``fit``).
+Shaped by a profiler pass on the B200 (``scripts/grad_profile.py``): 3x3 products are broadcast multiply-sums
+(``_mm3`` / ``_mv3``; batched BLAS ran them as one tiny GEMV per matrix), the joint chains are path sums over an
+ancestor matrix or one product per tree level instead of a loop over the joints.
+
+What is differentiable: ``forward`` with respect to every tensor input; the three fits with respect to the targets,
+the weights, the initial guesses and the known pose / betas, for every option (joints or not, weights, ``num_iter``,
+``final_adjust_rots``, the regularisers and their references, ``enable_kid``, ``scale_target`` / ``scale_fit``,
+``share_beta``).  It is the same function as the CUDA path's: in float64 it reproduces the float64 oracle of the
+golden cases to 1e-13 (``tests/test_adjoint_cpu.py``).
 """
 
 from __future__ import annotations
