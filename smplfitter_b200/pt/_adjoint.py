@@ -27,8 +27,8 @@ ancestor matrix or one product per tree level instead of a loop over the joints.
 What is differentiable: ``forward`` with respect to every tensor input; the three fits with respect to the targets,
 the weights, the initial guesses and the known pose / betas, for every option (joints or not, weights, ``num_iter``,
 ``final_adjust_rots``, the regularisers and their references, ``enable_kid``, ``scale_target`` / ``scale_fit``,
-``share_beta``).  It is the same function as the CUDA path's: in float64 it reproduces the float64 oracle of the
-golden cases to 1e-13 (``tests/test_adjoint_cpu.py``).
+``share_beta``).  It is the same function as the CUDA path's: in float64 it reproduces the float64 evaluation stored
+with the golden cases (their ``exact_*`` arrays) to 1e-13 (``tests/test_adjoint_cpu.py``).
 """
 
 from __future__ import annotations
