@@ -316,3 +316,49 @@ def test_gradient_evaluation_is_reachable_only_from_backward_paths():
     src = open(os.path.join(pkg, 'bodyfitter.py')).read()
     for chunk in src.split('from . import _adjoint')[:-1]:
         assert 'requires_grad' in chunk[-400:], 'the known-* wrappers may reach _adjoint only when a gradient is requested'
+
+
+def test_fit_plan_on_random_trees():
+    """masks.build_fit_plan against the oracle's independent re-derivation (OraclePlan) on random kinematic trees and
+    skin weights, beyond the four models the reference-generated mask fixtures cover: partition, part kinds,
+    children-and-self lists, used vertices, and the invariants the kernels rely on (levels cover every joint once,
+    every parent precedes its children in the level order, the assembly order is a permutation)."""
+    from hypothesis import given, settings, strategies as st
+
+    from oracle import oracle_np
+    from smplfitter_b200 import masks
+
+    class Model:
+        pass
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.integers(3, 20), st.integers(30, 200), st.integers(0, 2 ** 31 - 1), st.booleans())
+    def check(J, V, seed, smpl_family):
+        rs = np.random.RandomState(seed)
+        if smpl_family:
+            J = max(J, 20)  # the SMPL-family adjustable list names joints up to 19
+        parents = [0] + [int(rs.randint(0, i)) for i in range(1, J)]
+        w = np.zeros((V, J), np.float32)
+        for v in range(V):
+            js = rs.choice(J, size=min(J, 1 + rs.randint(0, 4)), replace=False)
+            w[v, js] = rs.dirichlet(np.ones(len(js))).astype(np.float32)
+        name = 'smpl' if smpl_family else 'other'
+        plan = masks.build_fit_plan(w, parents, name)
+        m = Model()
+        m.model_name, m.weights, m.parents, m.num_joints, m.num_vertices = name, w, parents, J, V
+        ora = oracle_np.OraclePlan(m)
+        assert np.array_equal(plan.part_assignment, ora.part)
+        assert plan.children_and_self == ora.cas
+        assert (plan.multi_joint_parts, plan.bone_parts, plan.leaf_parts) == (ora.multi, ora.bone, ora.leaf)
+        assert plan.adjustable_parts == ora.adjustable
+        assert np.array_equal(plan.used_vertex_indices, ora.used)
+        assert sorted(plan.fk_js.tolist()) == list(range(1, J))
+        seen = {0}
+        for j, p in zip(plan.fk_js.tolist(), plan.fk_ps.tolist()):
+            assert p == parents[j] and p in seen
+            seen.add(j)
+        order = plan.multi_joint_parts + plan.leaf_parts + plan.bone_parts
+        assert sorted(order) == [i for i in range(J) if not (smpl_family and i in (10, 11))]
+        assert sum(plan.fk_level_sizes) == J - 1 and sum(plan.adj_level_sizes) == len(plan.adj_parts)
+
+    check()
