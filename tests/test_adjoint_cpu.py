@@ -317,3 +317,47 @@ def test_converter_chain_gradient_in_float64():
         fd = (loss(pose + 1e-6 * dp, betas + 1e-6 * db) - loss(pose - 1e-6 * dp, betas - 1e-6 * db)).item() / 2e-6
     an = ((p.grad * dp).sum() + (b.grad * db).sum()).item()
     assert abs(an - fd) < 1e-5 * max(1.0, abs(fd)), (an, fd)
+
+
+def test_two_restatements_agree_on_random_options():
+    """The numpy oracle (per part / per joint loops) and the torch evaluation (vectorised, differentiable) are
+    independent statements of the same algorithm: in float64 they must agree on random inputs and option mixes,
+    beyond the golden cases."""
+    from hypothesis import given, settings, strategies as st
+
+    from oracle import oracle_np
+    from smplfitter_b200 import modeldata
+
+    data = modeldata.initialize('smpl_tiny')
+    bm = pt.BodyModel('smpl_tiny')
+    c = _adjoint.constants(bm, torch.float64, torch.device('cpu'))
+
+    @settings(max_examples=12, deadline=None)
+    @given(st.integers(0, 2 ** 31 - 1), st.integers(1, 3), st.booleans(), st.booleans(), st.booleans(), st.booleans(),
+           st.sampled_from([0, 1, 2]))
+    def check(seed, num_iter, joints, weights, adjust, share, scale_mode):
+        rs = np.random.RandomState(seed)
+        B = 3
+        pose, betas, trans = rs.randn(B, 72) * 0.25, rs.randn(B, 10) * 0.6, rs.randn(B, 3)
+        with torch.no_grad():
+            j, _, v = _adjoint.lbs(c, *(torch.from_numpy(x) for x in (pose, betas, trans)))
+        tv = v.numpy() * (1.05 if scale_mode else 1.0) + rs.randn(B, bm.num_vertices, 3) * 0.003
+        tj = j.numpy() * (1.05 if scale_mode else 1.0) + rs.randn(B, 24, 3) * 0.003 if joints else None
+        vw = rs.uniform(0.3, 1.5, (B, bm.num_vertices)) if weights else None
+        jw = rs.uniform(0.3, 1.5, (B, 24)) if (weights and joints) else None
+        kw = dict(num_iter=num_iter, beta_regularizer=float(rs.uniform(0, 2)), beta_regularizer2=float(rs.uniform(0, 0.5)),
+                  final_adjust_rots=adjust, share_beta=share, scale_target=scale_mode == 1, scale_fit=scale_mode == 2,
+                  scale_regularizer=float(rs.uniform(0, 1)))
+        oracle_np.set_precision(np.float64)
+        try:
+            ora = oracle_np.OracleFitter(oracle_np.OracleModel(data, 'smpl_tiny')).fit(
+                tv, tj, vw, jw, requested_keys=['pose_rotvecs', 'shape_betas', 'relative_orientations'], **kw)
+        finally:
+            oracle_np.set_precision(np.float32)
+        T = lambda x: None if x is None else torch.from_numpy(x)  # noqa: E731
+        out = _adjoint.fit(bm, 10, T(tv), T(tj), T(vw), T(jw), want_pose_rotvecs=True, want_rel_orient=True, **kw)
+        for k, o in zip(FIT_OUTPUTS, out):
+            if o is not None:
+                assert np.abs(o.numpy() - ora[k]).max() < 1e-8, (k, kw)
+
+    check()
